@@ -515,8 +515,14 @@ uint32_t cpo_cp_type_2d(const double J[2][2], int symmetric)
       else if (r0 > 0 && r1 > 0) return 2;
       else if (r0 < 0 && r1 < 0) return 8;
       else return 1;
-    } else { /* conjugate roots: real part = (-P1 + 0) / (2 P2) */
-      const double re = (-P1 + 0.0) / (2 * P2);
+    } else {
+      /* conjugate roots (or NaN delta): x0 = (-P1 + complex_sqrt(delta)) / (2 P2) with
+       * complex_sqrt(z) = std::pow(std::complex<T>(z), 0.5)  (ref: numeric/sqrt.hh:9-15).
+       * libstdc++ evaluates that as polar(exp(0.5 * log|z|), 0.5 * arg(z)), so the real part of
+       * the root is not exactly -P1/2: it carries rho * cos(pi/2) ~ rho * 6.1e-17, and a NaN
+       * delta makes it NaN (=> "center"). */
+      const double rho = exp(0.5 * log(fabs(delta))), theta = 0.5 * atan2(0.0, delta);
+      const double re = (-P1 + rho * cos(theta)) / (2 * P2);
       if (re < 0) return 16;
       else if (re > 0) return 32;
       else return 64;
