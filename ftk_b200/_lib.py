@@ -1,0 +1,104 @@
+"""ctypes binding of the C ABI declared in include/ftkb200.h (libftkb200.so, built in-tree).
+
+This is the reference-side binding a Python caller would use; it has no torch dependency.
+There is no fallback: if the shared library is missing, loading raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libftkb200.so")
+
+ABI_VERSION = 1
+OK, ERR_INVALID, ERR_NO_DEVICE, ERR_CUDA, ERR_NOMEM, ERR_OVERFLOW = range(6)
+SOURCE_NONE, SOURCE_GIVEN, SOURCE_DERIVED = 0, 1, 2
+MEM_HOST, MEM_DEVICE, MEM_DEVICE_BORROW = 0, 1, 2
+SYN_MOVING_EXTREMUM, SYN_WOVEN, SYN_DOUBLE_GYRE, SYN_ABC, SYN_MERGER = range(5)
+
+
+class Config(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_int32), ("nd", C.c_int32), ("dims", C.c_int32 * 3), ("lb", C.c_int32 * 3), ("ub", C.c_int32 * 3),
+        ("scalar_source", C.c_int32), ("vector_source", C.c_int32), ("jacobian_source", C.c_int32),
+        ("jacobian_symmetric", C.c_int32), ("robust_detection", C.c_int32), ("compute_degrees", C.c_int32),
+        ("use_type_filter", C.c_int32), ("type_filter", C.c_uint32), ("start_timestep", C.c_int32), ("device", C.c_int32),
+        ("resolution_init", C.c_double), ("point_capacity", C.c_uint64),
+    ]
+
+
+class Stats(C.Structure):
+    _fields_ = [
+        ("simplices_tested", C.c_uint64), ("cells_scanned", C.c_uint64), ("cells_refined", C.c_uint64), ("points", C.c_uint64),
+        ("kernel_launches", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
+        ("ms_derive", C.c_double), ("ms_scan", C.c_double), ("ms_test", C.c_double), ("ms_finalize_device", C.c_double),
+        ("ms_finalize_host", C.c_double), ("last_ms_scan", C.c_double), ("last_ms_derive", C.c_double),
+        ("scaling_factor", C.c_double), ("resolution", C.c_double),
+    ]
+
+    def as_dict(self):
+        return {name: getattr(self, name) for name, _ in self._fields_}
+
+
+POINT_DTYPE = np.dtype([
+    ("corner", np.int32, 4), ("simplex_type", np.int32), ("ordinal", np.int32), ("timestep", np.int32),
+    ("cp_type", np.uint32), ("x", np.float64, 3), ("t", np.float64), ("scalar", np.float64),
+], align=True)
+assert POINT_DTYPE.itemsize == 72
+
+# every symbol include/ftkb200.h declares
+EXPORTS = [
+    "ftkb_abi_version", "ftkb_device_count", "ftkb_create", "ftkb_destroy", "ftkb_last_error", "ftkb_push_snapshot",
+    "ftkb_push_synthetic", "ftkb_update_timestep", "ftkb_advance_timestep", "ftkb_finalize", "ftkb_current_timestep",
+    "ftkb_last_layer_resolution", "ftkb_set_resolution", "ftkb_num_points", "ftkb_get_points", "ftkb_import_points",
+    "ftkb_num_trajectories", "ftkb_get_trajectories", "ftkb_get_component_labels", "ftkb_get_degrees", "ftkb_get_stats",
+    "ftkb_reset_stats", "ftkb_synchronize", "ftkb_mesh_ntypes", "ftkb_mesh_unit_simplex", "ftkb_mesh_scope_type",
+    "ftkb_mesh_sides", "ftkb_mesh_side_of",
+]
+
+_lib = None
+
+
+class FTKBError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__(f"ftkb error {code}: {message}")
+        self.code = code
+
+
+def lib():
+    """Load libftkb200.so (raises if it has not been built: python -m ftk_b200.build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise FileNotFoundError(f"{LIB_PATH} is missing: build it with `python -m ftk_b200.build` (there is no fallback path)")
+    L = C.CDLL(LIB_PATH)
+    vp, u64p = C.c_void_p, C.POINTER(C.c_uint64)
+    L.ftkb_create.argtypes = [C.POINTER(Config), C.POINTER(vp)]
+    L.ftkb_destroy.argtypes = [vp]
+    L.ftkb_destroy.restype = None
+    L.ftkb_last_error.argtypes = [vp]
+    L.ftkb_last_error.restype = C.c_char_p
+    L.ftkb_push_snapshot.argtypes = [vp, vp, vp, vp, C.c_int]
+    L.ftkb_push_synthetic.argtypes = [vp, C.c_int, C.POINTER(C.c_double), C.c_int, C.c_double]
+    for name in ("ftkb_update_timestep", "ftkb_advance_timestep", "ftkb_finalize", "ftkb_reset_stats", "ftkb_synchronize"):
+        getattr(L, name).argtypes = [vp]
+    L.ftkb_current_timestep.argtypes = [vp, C.POINTER(C.c_int32)]
+    L.ftkb_last_layer_resolution.argtypes = [vp, C.POINTER(C.c_double)]
+    L.ftkb_set_resolution.argtypes = [vp, C.c_double]
+    L.ftkb_num_points.argtypes = [vp, u64p]
+    L.ftkb_get_points.argtypes = [vp, vp, C.c_uint64]
+    L.ftkb_import_points.argtypes = [vp, vp, C.c_uint64]
+    L.ftkb_num_trajectories.argtypes = [vp, u64p]
+    L.ftkb_get_trajectories.argtypes = [vp, vp, vp, vp]
+    L.ftkb_get_component_labels.argtypes = [vp, vp]
+    L.ftkb_get_degrees.argtypes = [vp, vp]
+    L.ftkb_get_stats.argtypes = [vp, C.POINTER(Stats)]
+    L.ftkb_mesh_ntypes.argtypes = [C.c_int, C.c_int, C.c_int]
+    L.ftkb_mesh_unit_simplex.argtypes = [C.c_int, C.c_int, C.c_int, vp]
+    L.ftkb_mesh_scope_type.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int]
+    L.ftkb_mesh_sides.argtypes = [C.c_int, C.c_int, C.c_int, vp]
+    L.ftkb_mesh_side_of.argtypes = [C.c_int, C.c_int, C.c_int, vp]
+    _lib = L
+    return L

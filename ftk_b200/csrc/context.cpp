@@ -1,0 +1,770 @@
+// Host side of the engine: the stateful context behind the C ABI (include/ftkb200.h).
+//
+// Mirrors the control flow of ftk::critical_point_tracker_{2d,3d}_regular
+//   push_*_snapshot   ref: critical_point_tracker_2d_regular.hh:238-261, _3d_regular.hh:125-148
+//   update_timestep   ref: critical_point_tracker_2d_regular.hh:263-433, _3d_regular.hh:150-308
+//   advance_timestep  ref: critical_point_tracker.hh:841-848
+//   finalize          ref: critical_point_tracker.hh:668-817, geometry/cc2curves.hh:10-122
+// but keeps every field layer resident in HBM, never materialises the Jacobian and runs all
+// per-simplex work in the CUDA kernels of kernels.cu.  There is no CPU code path for the sweep.
+#include <algorithm>
+#include <cfloat>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <deque>
+#include <string>
+#include <vector>
+
+#include "kernels.h"
+
+using namespace ftkb;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct Layer {
+  double *S = nullptr, *V = nullptr, *J = nullptr;
+  bool ownS = false, ownV = false, ownJ = false;
+  int slot = 0;                  // resolution slot
+};
+
+}  // namespace
+
+struct ftkb_ctx {
+  ftkb_config cfg{};
+  int n = 0;                     // spatial dims
+  size_t nvert = 0;
+  uint64_t ncore = 0;
+  int n_ord = 0, n_int = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // 0-2: sweep, 3: spare, 4-5: derive
+  bool derive_timed = false;
+  std::string error;
+
+  std::deque<Layer> layers;
+  std::vector<double *> freeS, freeV, freeJ;   // buffer pools
+  int current_timestep = 0;
+  double resolution = DBL_MAX;
+  double factor = 1.0;
+  int nbits = 0;
+  int next_slot = 0;
+
+  // device scalars: [0..7] per-layer resolution bits, [8] worklist count, [9] point count, [10] unique count
+  unsigned long long *d_scalars = nullptr;
+  unsigned long long *h_scalars = nullptr;     // pinned mirror
+  static constexpr int SLOT_WL = 8, SLOT_PT = 9, SLOT_UQ = 10, NSLOTS = 16;
+
+  unsigned long long *d_wl = nullptr;
+  uint64_t wl_cap = 0;
+  ftkb_point *d_pts = nullptr;
+  uint64_t pt_cap = 0, npts = 0;
+
+  // sorted / traced results (host)
+  bool sorted = false, traced = false;
+  std::vector<ftkb_point> pts_sorted;
+  ftkb_point *d_pts_sorted = nullptr;          // device copy of the sorted unique points
+  unsigned long long *d_keys_sorted = nullptr;
+  uint64_t nsorted = 0;
+  std::vector<uint64_t> labels;
+  std::vector<int32_t> deg;
+  std::vector<uint64_t> traj_off, traj_idx;
+  std::vector<uint8_t> traj_loop;
+
+  ftkb_stats stats{};
+};
+
+#define CK(call)                                                                                         \
+  do {                                                                                                   \
+    cudaError_t e_ = (call);                                                                             \
+    if (e_ != cudaSuccess) {                                                                             \
+      c->error = std::string(#call) + ": " + cudaGetErrorString(e_);                                     \
+      return e_ == cudaErrorMemoryAllocation ? FTKB_ERR_NOMEM : FTKB_ERR_CUDA;                           \
+    }                                                                                                    \
+  } while (0)
+
+static int fail(ftkb_ctx *c, int code, const std::string &msg) {
+  if (c) c->error = msg;
+  else g_create_error = msg;
+  return code;
+}
+
+static int check_launch(ftkb_ctx *c, const char *what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(c, FTKB_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+  return FTKB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+extern "C" int ftkb_abi_version(void) { return FTKB_ABI_VERSION; }
+
+extern "C" int ftkb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  int usable = 0;
+  for (int i = 0; i < n; i++) {
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, i) == cudaSuccess && prop.major == 10) usable++;
+  }
+  return usable;
+}
+
+extern "C" const char *ftkb_last_error(const ftkb_ctx *c) { return c ? c->error.c_str() : g_create_error.c_str(); }
+
+static void release_layer(ftkb_ctx *c, Layer &l) {
+  if (l.ownS && l.S) c->freeS.push_back(l.S);
+  if (l.ownV && l.V) c->freeV.push_back(l.V);
+  if (l.ownJ && l.J) c->freeJ.push_back(l.J);
+  l = Layer();
+}
+
+extern "C" void ftkb_destroy(ftkb_ctx *c) {
+  if (!c) return;
+  cudaSetDevice(c->cfg.device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  for (auto &l : c->layers) release_layer(c, l);
+  for (auto *p : c->freeS) cudaFree(p);
+  for (auto *p : c->freeV) cudaFree(p);
+  for (auto *p : c->freeJ) cudaFree(p);
+  cudaFree(c->d_scalars);
+  if (c->h_scalars) cudaFreeHost(c->h_scalars);
+  cudaFree(c->d_wl);
+  cudaFree(c->d_pts);
+  cudaFree(c->d_pts_sorted);
+  cudaFree(c->d_keys_sorted);
+  for (auto &e : c->ev) if (e) cudaEventDestroy(e);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+extern "C" int ftkb_create(const ftkb_config *cfg, ftkb_ctx **out) {
+  if (!cfg || !out) return fail(nullptr, FTKB_ERR_INVALID, "ftkb_create: null argument");
+  *out = nullptr;
+  if (cfg->abi_version != FTKB_ABI_VERSION) return fail(nullptr, FTKB_ERR_INVALID, "ftkb_create: ABI version mismatch");
+  if (cfg->nd != 2 && cfg->nd != 3) return fail(nullptr, FTKB_ERR_INVALID, "ftkb_create: nd must be 2 or 3");
+  const int n = cfg->nd;
+  for (int j = 0; j < n; j++) {
+    if (cfg->dims[j] < 2) return fail(nullptr, FTKB_ERR_INVALID, "ftkb_create: array dims must be >= 2");
+    if (cfg->lb[j] < 0 || cfg->ub[j] > cfg->dims[j] - 1 || cfg->lb[j] > cfg->ub[j])
+      return fail(nullptr, FTKB_ERR_INVALID, "ftkb_create: domain must lie inside the array");
+  }
+  if (cfg->start_timestep < 0) return fail(nullptr, FTKB_ERR_INVALID, "ftkb_create: start_timestep must be >= 0");
+  // no CPU fallback: a Blackwell device is required
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(nullptr, FTKB_ERR_NO_DEVICE, "ftkb_create: no CUDA device (this engine has no CPU fallback)");
+  }
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, FTKB_ERR_NO_DEVICE, "ftkb_create: device ordinal out of range");
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess || prop.major != 10)
+    return fail(nullptr, FTKB_ERR_NO_DEVICE, "ftkb_create: device is not compute capability 10.x (kernels are built for sm_100a only)");
+
+  ftkb_ctx *c = new ftkb_ctx();
+  c->cfg = *cfg;
+  c->n = n;
+  c->nvert = (size_t)cfg->dims[0] * cfg->dims[1] * (n == 3 ? cfg->dims[2] : 1);
+  c->ncore = 1;
+  for (int j = 0; j < n; j++) c->ncore *= (uint64_t)(cfg->ub[j] - cfg->lb[j] + 1);
+  // element keys pack (x, y, z, t, type) into 64 bits
+  {
+    const long double cap = 18446744073709551616.0L / (long double)(1ull << (KEY_TIME_BITS + KEY_TYPE_BITS));
+    if ((long double)c->ncore >= cap) { delete c; return fail(nullptr, FTKB_ERR_OVERFLOW, "ftkb_create: domain too large for 64-bit element ids"); }
+  }
+  const MeshTables &mt = mesh_tables(n + 1);
+  c->n_ord = (int)mt.ordinal_types[n].size();
+  c->n_int = (int)mt.interval_types[n].size();
+  c->current_timestep = cfg->start_timestep;
+  c->resolution = cfg->resolution_init > 0 ? cfg->resolution_init : DBL_MAX;
+
+  auto bail = [&](const std::string &m, int code) { g_create_error = m; ftkb_destroy(c); return code; };
+  cudaError_t e;
+  if ((e = cudaSetDevice(cfg->device)) != cudaSuccess) return bail(std::string("cudaSetDevice: ") + cudaGetErrorString(e), FTKB_ERR_CUDA);
+  if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(std::string("cudaStreamCreate: ") + cudaGetErrorString(e), FTKB_ERR_CUDA);
+  for (auto &ev : c->ev)
+    if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail(std::string("cudaEventCreate: ") + cudaGetErrorString(e), FTKB_ERR_CUDA);
+  if ((e = cudaMalloc(&c->d_scalars, sizeof(unsigned long long) * ftkb_ctx::NSLOTS)) != cudaSuccess) return bail("cudaMalloc(scalars) failed", FTKB_ERR_NOMEM);
+  if ((e = cudaMallocHost(&c->h_scalars, sizeof(unsigned long long) * ftkb_ctx::NSLOTS)) != cudaSuccess) return bail("cudaMallocHost failed", FTKB_ERR_NOMEM);
+  cudaMemsetAsync(c->d_scalars, 0, sizeof(unsigned long long) * ftkb_ctx::NSLOTS, c->stream);
+  c->wl_cap = std::max<uint64_t>(1 << 16, c->ncore / 64);
+  if ((e = cudaMalloc(&c->d_wl, sizeof(unsigned long long) * c->wl_cap)) != cudaSuccess) return bail("cudaMalloc(worklist) failed", FTKB_ERR_NOMEM);
+  c->pt_cap = cfg->point_capacity ? cfg->point_capacity : (1 << 18);
+  if ((e = cudaMalloc(&c->d_pts, sizeof(ftkb_point) * c->pt_cap)) != cudaSuccess) return bail("cudaMalloc(points) failed", FTKB_ERR_NOMEM);
+  DeviceMeshTables t2, t3;
+  fill_device_tables(3, &t2);
+  fill_device_tables(4, &t3);
+  upload_mesh_tables(t2, t3);
+  if ((e = cudaStreamSynchronize(c->stream)) != cudaSuccess) return bail(std::string("init: ") + cudaGetErrorString(e), FTKB_ERR_CUDA);
+  *out = c;
+  return FTKB_OK;
+}
+
+static int take_buffer(ftkb_ctx *c, std::vector<double *> &pool, size_t count, double **out) {
+  if (!pool.empty()) { *out = pool.back(); pool.pop_back(); return FTKB_OK; }
+  CK(cudaMalloc(out, sizeof(double) * count));
+  return FTKB_OK;
+}
+
+// resolution of the layer's vector field into its slot; the value reaches the host asynchronously
+static int queue_resolution(ftkb_ctx *c, Layer &l, bool fused_in_gradient) {
+  if (!fused_in_gradient) launch_resolution(l.V, (uint64_t)c->nvert * c->n, c->d_scalars + l.slot, c->stream);
+  c->stats.kernel_launches += fused_in_gradient ? 0 : 1;
+  CK(cudaMemcpyAsync(c->h_scalars + l.slot, c->d_scalars + l.slot, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+  c->stats.d2h_bytes += 8;
+  return check_launch(c, "resolution");
+}
+
+static int derive_layer(ftkb_ctx *c, Layer &l) {
+  // slot <- DBL_MAX
+  unsigned long long init;
+  const double dmax = DBL_MAX;
+  std::memcpy(&init, &dmax, 8);
+  launch_fill_u64(c->d_scalars + l.slot, init, c->stream);
+  c->stats.kernel_launches++;
+  bool fused = false;
+  if (!l.V && c->cfg.vector_source == FTKB_SOURCE_DERIVED && l.S) {
+    int rc = take_buffer(c, c->freeV, c->nvert * c->n, &l.V);
+    if (rc) return rc;
+    l.ownV = true;
+    CK(cudaEventRecord(c->ev[4], c->stream));
+    launch_gradient(c->n, l.S, l.V, c->cfg.dims[0], c->cfg.dims[1], c->n == 3 ? c->cfg.dims[2] : 1, c->d_scalars + l.slot, c->stream);
+    CK(cudaEventRecord(c->ev[5], c->stream));
+    c->derive_timed = true;
+    c->stats.kernel_launches++;
+    fused = true;
+  }
+  if (l.V) {
+    int rc = queue_resolution(c, l, fused);
+    if (rc) return rc;
+  }
+  return check_launch(c, "derive");
+}
+
+static int new_layer(ftkb_ctx *c, Layer &l) {
+  if (c->layers.size() >= 4) return fail(c, FTKB_ERR_INVALID, "push: more than 4 resident snapshots (call advance_timestep)");
+  l.slot = c->next_slot;
+  c->next_slot = (c->next_slot + 1) % 8;
+  return FTKB_OK;
+}
+
+extern "C" int ftkb_push_snapshot(ftkb_ctx *c, const double *scalar, const double *vector, const double *jacobian, int where) {
+  if (!c) return FTKB_ERR_INVALID;
+  if (where < FTKB_MEM_HOST || where > FTKB_MEM_DEVICE_BORROW) return fail(c, FTKB_ERR_INVALID, "push: bad memory kind");
+  if (c->cfg.scalar_source == FTKB_SOURCE_GIVEN && !scalar) return fail(c, FTKB_ERR_INVALID, "push: scalar field is GIVEN but no scalar array was passed");
+  if (c->cfg.vector_source == FTKB_SOURCE_GIVEN && !vector) return fail(c, FTKB_ERR_INVALID, "push: vector field is GIVEN but no vector array was passed");
+  if (c->cfg.vector_source == FTKB_SOURCE_DERIVED && !vector && !scalar) return fail(c, FTKB_ERR_INVALID, "push: vector field is DERIVED but no scalar array was passed");
+  if (c->cfg.jacobian_source == FTKB_SOURCE_GIVEN && !jacobian) return fail(c, FTKB_ERR_INVALID, "push: jacobian is GIVEN but no jacobian array was passed");
+  CK(cudaSetDevice(c->cfg.device));
+  Layer l;
+  int rc = new_layer(c, l);
+  if (rc) return rc;
+  const size_t nS = c->nvert, nV = c->nvert * c->n, nJ = c->nvert * c->n * c->n;
+  auto ingest = [&](const double *src, size_t count, std::vector<double *> &pool, double **dst, bool *own) -> int {
+    if (!src) return FTKB_OK;
+    if (where == FTKB_MEM_DEVICE_BORROW) { *dst = const_cast<double *>(src); *own = false; return FTKB_OK; }
+    int r = take_buffer(c, pool, count, dst);
+    if (r) return r;
+    *own = true;
+    CK(cudaMemcpyAsync(*dst, src, sizeof(double) * count, where == FTKB_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, c->stream));
+    if (where == FTKB_MEM_HOST) c->stats.h2d_bytes += sizeof(double) * count;
+    return FTKB_OK;
+  };
+  if ((rc = ingest(scalar, nS, c->freeS, &l.S, &l.ownS))) { release_layer(c, l); return rc; }
+  if ((rc = ingest(vector, nV, c->freeV, &l.V, &l.ownV))) { release_layer(c, l); return rc; }
+  if ((rc = ingest(jacobian, nJ, c->freeJ, &l.J, &l.ownJ))) { release_layer(c, l); return rc; }
+  if ((rc = derive_layer(c, l))) { release_layer(c, l); return rc; }
+  if (where == FTKB_MEM_HOST) CK(cudaStreamSynchronize(c->stream));   // host buffers are borrowed only until return
+  c->layers.push_back(l);
+  return FTKB_OK;
+}
+
+extern "C" int ftkb_push_synthetic(ftkb_ctx *c, int kind, const double *params, int nparams, double t) {
+  if (!c) return FTKB_ERR_INVALID;
+  if (nparams < 0 || nparams > 8 || (nparams && !params)) return fail(c, FTKB_ERR_INVALID, "push_synthetic: bad params");
+  const bool vector_kind = kind == FTKB_SYN_DOUBLE_GYRE || kind == FTKB_SYN_ABC;
+  const bool ok2 = kind == FTKB_SYN_WOVEN || kind == FTKB_SYN_DOUBLE_GYRE || kind == FTKB_SYN_MERGER;
+  if (kind < 0 || kind > FTKB_SYN_MERGER || (ok2 && c->n != 2) || (kind == FTKB_SYN_ABC && c->n != 3))
+    return fail(c, FTKB_ERR_INVALID, "push_synthetic: generator does not match the context's dimensionality");
+  if (vector_kind ? c->cfg.vector_source != FTKB_SOURCE_GIVEN : c->cfg.scalar_source != FTKB_SOURCE_GIVEN)
+    return fail(c, FTKB_ERR_INVALID, "push_synthetic: generator kind does not match the configured field sources");
+  CK(cudaSetDevice(c->cfg.device));
+  double p[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int i = 0; i < nparams; i++) p[i] = params[i];
+  Layer l;
+  int rc = new_layer(c, l);
+  if (rc) return rc;
+  double **dst = vector_kind ? &l.V : &l.S;
+  if ((rc = take_buffer(c, vector_kind ? c->freeV : c->freeS, vector_kind ? c->nvert * c->n : c->nvert, dst))) return rc;
+  (vector_kind ? l.ownV : l.ownS) = true;
+  launch_synthetic(kind, c->n, c->cfg.dims[0], c->cfg.dims[1], c->n == 3 ? c->cfg.dims[2] : 1, p, t, *dst, c->stream);
+  c->stats.kernel_launches++;
+  if ((rc = derive_layer(c, l))) { release_layer(c, l); return rc; }
+  c->layers.push_back(l);
+  return FTKB_OK;
+}
+
+static double slot_value(const ftkb_ctx *c, int slot) {
+  double v;
+  std::memcpy(&v, c->h_scalars + slot, 8);
+  return v;
+}
+
+extern "C" int ftkb_last_layer_resolution(ftkb_ctx *c, double *res) {
+  if (!c || !res) return FTKB_ERR_INVALID;
+  if (c->layers.empty()) return fail(c, FTKB_ERR_INVALID, "last_layer_resolution: no resident snapshot");
+  CK(cudaSetDevice(c->cfg.device));
+  CK(cudaStreamSynchronize(c->stream));
+  *res = c->layers.back().V ? slot_value(c, c->layers.back().slot) : DBL_MAX;
+  return FTKB_OK;
+}
+
+extern "C" int ftkb_set_resolution(ftkb_ctx *c, double res) {
+  if (!c) return FTKB_ERR_INVALID;
+  if (res > 0 && res < c->resolution) c->resolution = res;
+  return FTKB_OK;
+}
+
+extern "C" int ftkb_current_timestep(const ftkb_ctx *c, int32_t *t) {
+  if (!c || !t) return FTKB_ERR_INVALID;
+  *t = c->current_timestep;
+  return FTKB_OK;
+}
+
+static int grow_points(ftkb_ctx *c, uint64_t need) {
+  uint64_t cap = c->pt_cap;
+  while (cap < need) cap *= 2;
+  ftkb_point *np = nullptr;
+  CK(cudaMalloc(&np, sizeof(ftkb_point) * cap));
+  CK(cudaMemcpyAsync(np, c->d_pts, sizeof(ftkb_point) * c->npts, cudaMemcpyDeviceToDevice, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  cudaFree(c->d_pts);
+  c->d_pts = np;
+  c->pt_cap = cap;
+  return FTKB_OK;
+}
+
+// ref: critical_point_tracker_{2d,3d}_regular::update_timestep (xl == NONE branch)
+extern "C" int ftkb_update_timestep(ftkb_ctx *c) {
+  if (!c) return FTKB_ERR_INVALID;
+  if (c->layers.empty()) return fail(c, FTKB_ERR_INVALID, "update_timestep: no snapshot has been pushed");
+  if (!c->layers[0].V) return fail(c, FTKB_ERR_INVALID, "update_timestep: the snapshot has no vector field");
+  if (c->current_timestep + 1 >= (1 << KEY_TIME_BITS)) return fail(c, FTKB_ERR_OVERFLOW, "update_timestep: timestep exceeds the element id range");
+  CK(cudaSetDevice(c->cfg.device));
+  CK(cudaStreamSynchronize(c->stream));   // per-layer resolutions are on the host now
+  // derive timing of the most recent gradient launch
+  if (c->derive_timed) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]) == cudaSuccess) { c->stats.ms_derive += ms; c->stats.last_ms_derive = ms; }
+    else cudaGetLastError();
+    c->derive_timed = false;
+  }
+  // ref: critical_point_tracker.hh:850-864 (running minimum over every resident snapshot, every sweep)
+  for (const Layer &l : c->layers)
+    if (l.V) c->resolution = std::min(c->resolution, slot_value(c, l.slot));
+  int nbits = (int)std::ceil(std::log2(1.0 / c->resolution));
+  const int minbits = 8, maxbits = 21;
+  nbits = std::max(minbits, std::min(nbits, maxbits));
+  c->nbits = nbits;
+  c->factor = (double)(uint64_t)(1 << nbits);
+
+  const bool has_next = c->layers.size() >= 2;
+  if (has_next && !c->layers[1].V) return fail(c, FTKB_ERR_INVALID, "update_timestep: the next snapshot has no vector field");
+  SweepParams p{};
+  p.nd = c->n;
+  p.W = c->cfg.dims[0]; p.H = c->cfg.dims[1]; p.D = c->n == 3 ? c->cfg.dims[2] : 1;
+  for (int j = 0; j < 3; j++) {
+    const bool used = j < c->n;
+    p.lb[j] = used ? c->cfg.lb[j] : 0;
+    p.ub[j] = used ? c->cfg.ub[j] : 0;
+    p.nc[j] = p.ub[j] - p.lb[j] + 1;
+    p.vmax[j] = used ? std::min(c->cfg.ub[j] + 1, c->cfg.dims[j] - 1) : 0;
+  }
+  p.t = c->current_timestep;
+  p.has_next = has_next;
+  p.nbits = nbits;
+  p.factor = c->factor;
+  p.no_filter = (c->n == 3 && !c->cfg.robust_detection);
+  p.scalar_source = c->layers[0].S ? c->cfg.scalar_source : FTKB_SOURCE_NONE;
+  p.jacobian_source = c->cfg.jacobian_source;
+  p.jacobian_symmetric = c->cfg.jacobian_symmetric;
+  // 2D: jacobian2D<double,true> on the scalar path, <double,false> when the vector field was pushed
+  p.derived_symmetric = c->cfg.vector_source == FTKB_SOURCE_DERIVED;
+  p.robust = c->cfg.robust_detection;
+  p.compute_degrees = c->cfg.compute_degrees;
+  p.use_type_filter = c->cfg.use_type_filter;
+  p.type_filter = c->cfg.type_filter;
+  for (int k = 0; k < 2; k++) {
+    const Layer &l = c->layers[has_next ? k : 0];
+    p.L[k].S = l.S; p.L[k].V = l.V; p.L[k].J = l.J;
+  }
+  if (has_next && p.scalar_source != FTKB_SOURCE_NONE && !c->layers[1].S) return fail(c, FTKB_ERR_INVALID, "update_timestep: the next snapshot has no scalar field");
+  p.nsx = (p.nc[0] + 30) / 31;
+  if (c->n == 2) {
+    p.rows = 64;
+    p.nsy = (p.nc[1] + p.rows - 1) / p.rows;
+    p.nsz = 1;
+  } else {
+    p.rows = 32;
+    p.nsy = (p.nc[1] + 14) / 15;
+    p.nsz = (p.nc[2] + p.rows - 1) / p.rows;
+  }
+  p.wl_count = c->d_scalars + ftkb_ctx::SLOT_WL;
+  p.pt_count = c->d_scalars + ftkb_ctx::SLOT_PT;
+
+  for (int attempt = 0; attempt < 8; attempt++) {
+    p.wl = c->d_wl; p.wl_cap = c->wl_cap;
+    p.pts = c->d_pts; p.pt_cap = c->pt_cap;
+    c->h_scalars[ftkb_ctx::SLOT_WL] = 0;
+    c->h_scalars[ftkb_ctx::SLOT_PT] = c->npts;
+    CK(cudaMemcpyAsync(c->d_scalars + ftkb_ctx::SLOT_WL, c->h_scalars + ftkb_ctx::SLOT_WL, 16, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaEventRecord(c->ev[0], c->stream));
+    launch_scan(p, c->stream);
+    CK(cudaEventRecord(c->ev[1], c->stream));
+    launch_test(p, c->stream);
+    CK(cudaEventRecord(c->ev[2], c->stream));
+    c->stats.kernel_launches += 2;
+    int rc = check_launch(c, "sweep");
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(c->h_scalars + ftkb_ctx::SLOT_WL, c->d_scalars + ftkb_ctx::SLOT_WL, 16, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->stats.d2h_bytes += 16;
+    float ms_scan = 0, ms_test = 0;
+    CK(cudaEventElapsedTime(&ms_scan, c->ev[0], c->ev[1]));
+    CK(cudaEventElapsedTime(&ms_test, c->ev[1], c->ev[2]));
+    c->stats.ms_scan += ms_scan; c->stats.ms_test += ms_test; c->stats.last_ms_scan = ms_scan;
+    const uint64_t nwl = c->h_scalars[ftkb_ctx::SLOT_WL], npt = c->h_scalars[ftkb_ctx::SLOT_PT];
+    if (nwl > c->wl_cap) {           // worklist overflow: grow and redo the step (inputs are still resident)
+      cudaFree(c->d_wl);
+      c->d_wl = nullptr;
+      c->wl_cap = nwl + nwl / 8 + 1024;
+      CK(cudaMalloc(&c->d_wl, sizeof(unsigned long long) * c->wl_cap));
+      continue;
+    }
+    if (npt > c->pt_cap) {
+      int rc2 = grow_points(c, npt);
+      if (rc2) return rc2;
+      continue;
+    }
+    c->stats.cells_scanned += c->ncore;
+    c->stats.cells_refined += nwl;
+    c->stats.simplices_tested += c->ncore * (uint64_t)(c->n_ord + (has_next ? c->n_int : 0));
+    if (npt != c->npts) { c->sorted = false; c->traced = false; }
+    c->npts = npt;
+    c->stats.points = npt;
+    return FTKB_OK;
+  }
+  return fail(c, FTKB_ERR_CUDA, "update_timestep: buffers kept overflowing");
+}
+
+extern "C" int ftkb_advance_timestep(ftkb_ctx *c) {
+  if (!c) return FTKB_ERR_INVALID;
+  const int rc = ftkb_update_timestep(c);
+  if (rc) return rc;
+  if (!c->layers.empty()) {
+    release_layer(c, c->layers.front());
+    c->layers.pop_front();
+  }
+  c->current_timestep++;
+  return FTKB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// results
+// ------------------------------------------------------------------------------------------------
+static void fill_trace_params(const ftkb_ctx *c, TraceParams &tp) {
+  tp.nd = c->n;
+  for (int j = 0; j < 3; j++) {
+    const bool used = j < c->n;
+    tp.lb[j] = used ? c->cfg.lb[j] : 0;
+    tp.ub[j] = used ? c->cfg.ub[j] : 0;
+  }
+  tp.ny = tp.ub[1] - tp.lb[1] + 1;
+  tp.nz = tp.ub[2] - tp.lb[2] + 1;
+}
+
+// sort the punctured simplices by element order and drop duplicates (std::map semantics of the
+// reference's discrete_critical_points, critical_point_tracker_regular.hh:13-38)
+static int ensure_sorted(ftkb_ctx *c) {
+  if (c->sorted) return FTKB_OK;
+  CK(cudaSetDevice(c->cfg.device));
+  cudaFree(c->d_pts_sorted); c->d_pts_sorted = nullptr;
+  cudaFree(c->d_keys_sorted); c->d_keys_sorted = nullptr;
+  c->pts_sorted.clear();
+  c->nsorted = 0;
+  const uint64_t n = c->npts;
+  if (n == 0) { c->sorted = true; return FTKB_OK; }
+  if (n >= 0xffffffffull) return fail(c, FTKB_ERR_OVERFLOW, "more than 2^32 punctured simplices");
+  TraceParams tp{};
+  fill_trace_params(c, tp);
+  unsigned long long *k0 = nullptr, *k1 = nullptr;
+  uint32_t *i0 = nullptr, *i1 = nullptr;
+  void *temp = nullptr;
+  auto cleanup = [&]() { cudaFree(k0); cudaFree(k1); cudaFree(i0); cudaFree(i1); cudaFree(temp); };
+#define CKC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); c->error = std::string(#call) + ": " + cudaGetErrorString(e_); return FTKB_ERR_CUDA; } } while (0)
+  CKC(cudaMalloc(&k0, 8 * n)); CKC(cudaMalloc(&k1, 8 * n)); CKC(cudaMalloc(&i0, 4 * n)); CKC(cudaMalloc(&i1, 4 * n));
+  CKC(cudaEventRecord(c->ev[0], c->stream));
+  launch_point_keys(c->d_pts, n, tp, k0, i0, c->stream);
+  size_t tb = std::max(sort_pairs_u64(nullptr, 0, k0, k1, i0, i1, n, c->stream),
+                       unique_by_key_u64(nullptr, 0, k1, i1, k0, i0, c->d_scalars + ftkb_ctx::SLOT_UQ, n, c->stream));
+  CKC(cudaMalloc(&temp, tb));
+  sort_pairs_u64(temp, tb, k0, k1, i0, i1, n, c->stream);
+  unique_by_key_u64(temp, tb, k1, i1, k0, i0, c->d_scalars + ftkb_ctx::SLOT_UQ, n, c->stream);
+  CKC(cudaMemcpyAsync(c->h_scalars + ftkb_ctx::SLOT_UQ, c->d_scalars + ftkb_ctx::SLOT_UQ, 8, cudaMemcpyDeviceToHost, c->stream));
+  CKC(cudaStreamSynchronize(c->stream));
+  const uint64_t nu = c->h_scalars[ftkb_ctx::SLOT_UQ];
+  CKC(cudaMalloc(&c->d_pts_sorted, sizeof(ftkb_point) * nu));
+  launch_gather_points(c->d_pts, i0, nu, c->d_pts_sorted, c->stream);
+  CKC(cudaEventRecord(c->ev[1], c->stream));
+  c->pts_sorted.resize(nu);
+  CKC(cudaMemcpyAsync(c->pts_sorted.data(), c->d_pts_sorted, sizeof(ftkb_point) * nu, cudaMemcpyDeviceToHost, c->stream));
+  CKC(cudaStreamSynchronize(c->stream));
+  CKC(cudaGetLastError());
+  float ms = 0;
+  CKC(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]));
+  c->stats.ms_finalize_device += ms;
+  c->stats.kernel_launches += 4;
+  c->stats.d2h_bytes += sizeof(ftkb_point) * nu;
+  c->d_keys_sorted = k0;   // unique sorted keys
+  k0 = nullptr;
+  c->nsorted = nu;
+  cleanup();
+#undef CKC
+  c->sorted = true;
+  return FTKB_OK;
+}
+
+extern "C" int ftkb_num_points(ftkb_ctx *c, uint64_t *n) {
+  if (!c || !n) return FTKB_ERR_INVALID;
+  const int rc = ensure_sorted(c);
+  if (rc) return rc;
+  *n = c->nsorted;
+  return FTKB_OK;
+}
+
+extern "C" int ftkb_get_points(ftkb_ctx *c, ftkb_point *out, uint64_t cap) {
+  if (!c || (!out && cap)) return FTKB_ERR_INVALID;
+  const int rc = ensure_sorted(c);
+  if (rc) return rc;
+  if (cap < c->nsorted) return fail(c, FTKB_ERR_INVALID, "get_points: output buffer too small");
+  if (c->nsorted) std::memcpy(out, c->pts_sorted.data(), sizeof(ftkb_point) * c->nsorted);
+  return FTKB_OK;
+}
+
+extern "C" int ftkb_import_points(ftkb_ctx *c, const ftkb_point *pts, uint64_t n) {
+  if (!c || (!pts && n)) return FTKB_ERR_INVALID;
+  if (!n) return FTKB_OK;
+  CK(cudaSetDevice(c->cfg.device));
+  if (c->npts + n > c->pt_cap) {
+    const int rc = grow_points(c, c->npts + n);
+    if (rc) return rc;
+  }
+  CK(cudaMemcpyAsync(c->d_pts + c->npts, pts, sizeof(ftkb_point) * n, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  c->stats.h2d_bytes += sizeof(ftkb_point) * n;
+  c->npts += n;
+  c->stats.points = c->npts;
+  c->sorted = false;
+  c->traced = false;
+  return FTKB_OK;
+}
+
+// ref: critical_point_tracker.hh:668-817 trace_critical_points_offline; cc2curves.hh:10-122
+extern "C" int ftkb_finalize(ftkb_ctx *c) {
+  if (!c) return FTKB_ERR_INVALID;
+  if (c->traced) return FTKB_OK;
+  int rc = ensure_sorted(c);
+  if (rc) return rc;
+  const uint64_t n = c->nsorted;
+  c->labels.assign(n, 0);
+  c->deg.assign(n, 0);
+  c->traj_off.assign(1, 0);
+  c->traj_idx.clear();
+  c->traj_loop.clear();
+  if (n == 0) { c->traced = true; return FTKB_OK; }
+
+  // device: neighbour search among punctured simplices + union-find (all nodes / ordinary nodes)
+  TraceParams tp{};
+  fill_trace_params(c, tp);
+  tp.n = n;
+  tp.keys = c->d_keys_sorted;
+  tp.pts = c->d_pts_sorted;
+  uint32_t *d_nb = nullptr, *d_pa = nullptr, *d_po = nullptr;
+  int32_t *d_deg = nullptr;
+  auto cleanup = [&]() { cudaFree(d_nb); cudaFree(d_pa); cudaFree(d_po); cudaFree(d_deg); };
+#define CKC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); c->error = std::string(#call) + ": " + cudaGetErrorString(e_); return FTKB_ERR_CUDA; } } while (0)
+  CKC(cudaMalloc(&d_nb, 4 * 8 * n)); CKC(cudaMalloc(&d_pa, 4 * n)); CKC(cudaMalloc(&d_po, 4 * n)); CKC(cudaMalloc(&d_deg, 4 * n));
+  tp.nb = d_nb; tp.deg = d_deg; tp.parent_all = d_pa; tp.parent_ord = d_po;
+  CKC(cudaEventRecord(c->ev[0], c->stream));
+  launch_neighbors(tp, c->stream);
+  launch_union_find(tp, c->stream);
+  CKC(cudaEventRecord(c->ev[1], c->stream));
+  c->stats.kernel_launches += 3;
+  std::vector<uint32_t> nb(8 * n), pa(n), po(n);
+  CKC(cudaMemcpyAsync(nb.data(), d_nb, 4 * 8 * n, cudaMemcpyDeviceToHost, c->stream));
+  CKC(cudaMemcpyAsync(pa.data(), d_pa, 4 * n, cudaMemcpyDeviceToHost, c->stream));
+  CKC(cudaMemcpyAsync(po.data(), d_po, 4 * n, cudaMemcpyDeviceToHost, c->stream));
+  CKC(cudaMemcpyAsync(c->deg.data(), d_deg, 4 * n, cudaMemcpyDeviceToHost, c->stream));
+  CKC(cudaStreamSynchronize(c->stream));
+  CKC(cudaGetLastError());
+  float ms = 0;
+  CKC(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]));
+  c->stats.ms_finalize_device += ms;
+  c->stats.d2h_bytes += 4 * 11 * n;
+  cleanup();
+#undef CKC
+
+  // host: order every trajectory with the reference's deterministic walk (cc2curves.hh:46-108)
+  const auto t0 = std::chrono::steady_clock::now();
+  for (uint64_t i = 0; i < n; i++) c->labels[i] = pa[i];
+  std::vector<uint8_t> visited(n, 0);
+  std::vector<uint32_t> fwd, bwd;
+  auto ordinary = [&](uint32_t i) { return c->deg[i] <= 2; };
+  auto next_unvisited = [&](uint32_t cur, uint32_t &out) {
+    for (int q = 0; q < 8; q++) {
+      const uint32_t j = nb[(size_t)cur * 8 + q];
+      if (j == 0xffffffffu) break;
+      if (ordinary(j) && !visited[j]) { out = j; return true; }
+    }
+    return false;
+  };
+  c->traj_idx.reserve(n);
+  for (uint64_t seed = 0; seed < n; seed++) {
+    if (!ordinary((uint32_t)seed) || po[seed] != seed) continue;   // the smallest member starts the walk
+    fwd.clear(); bwd.clear();
+    visited[seed] = 1;
+    uint32_t sn[8]; int nsn = 0;
+    for (int q = 0; q < 8; q++) {
+      const uint32_t j = nb[seed * 8 + q];
+      if (j == 0xffffffffu) break;
+      if (ordinary(j)) sn[nsn++] = j;
+    }
+    for (int dir = 0; dir < 2 && nsn > 0; dir++) {
+      uint32_t cur = dir == 0 ? sn[0] : sn[nsn - 1];
+      while (true) {
+        if (!visited[cur]) { (dir == 0 ? fwd : bwd).push_back(cur); visited[cur] = 1; }
+        uint32_t nx;
+        if (!next_unvisited(cur, nx)) break;
+        cur = nx;
+      }
+      if (nsn == 1) break;
+    }
+    const uint64_t start = c->traj_idx.size();
+    for (size_t k = bwd.size(); k > 0; k--) c->traj_idx.push_back(bwd[k - 1]);
+    c->traj_idx.push_back(seed);
+    for (uint32_t v : fwd) c->traj_idx.push_back(v);
+    const uint64_t len = c->traj_idx.size() - start;
+    bool loop = false;
+    if (len > 1) {   // is_loop: the back is a neighbour of the front (cc2curves.hh:113-122)
+      const uint64_t front = c->traj_idx[start], back = c->traj_idx.back();
+      for (int q = 0; q < 8; q++) loop = loop || nb[front * 8 + q] == back;
+    }
+    c->traj_loop.push_back(loop);
+    c->traj_off.push_back(c->traj_idx.size());
+  }
+  c->stats.ms_finalize_host += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  c->traced = true;
+  return FTKB_OK;
+}
+
+extern "C" int ftkb_num_trajectories(ftkb_ctx *c, uint64_t *n) {
+  if (!c || !n) return FTKB_ERR_INVALID;
+  if (!c->traced) return fail(c, FTKB_ERR_INVALID, "num_trajectories: call finalize first");
+  *n = c->traj_loop.size();
+  return FTKB_OK;
+}
+
+extern "C" int ftkb_get_trajectories(ftkb_ctx *c, uint64_t *offsets, uint64_t *point_idx, uint8_t *loop) {
+  if (!c || !offsets) return FTKB_ERR_INVALID;
+  if (!c->traced) return fail(c, FTKB_ERR_INVALID, "get_trajectories: call finalize first");
+  std::memcpy(offsets, c->traj_off.data(), 8 * c->traj_off.size());
+  if (point_idx && !c->traj_idx.empty()) std::memcpy(point_idx, c->traj_idx.data(), 8 * c->traj_idx.size());
+  if (loop && !c->traj_loop.empty()) std::memcpy(loop, c->traj_loop.data(), c->traj_loop.size());
+  return FTKB_OK;
+}
+
+extern "C" int ftkb_get_component_labels(ftkb_ctx *c, uint64_t *labels) {
+  if (!c || !labels) return FTKB_ERR_INVALID;
+  if (!c->traced) return fail(c, FTKB_ERR_INVALID, "get_component_labels: call finalize first");
+  if (!c->labels.empty()) std::memcpy(labels, c->labels.data(), 8 * c->labels.size());
+  return FTKB_OK;
+}
+
+extern "C" int ftkb_get_degrees(ftkb_ctx *c, int32_t *deg) {
+  if (!c || !deg) return FTKB_ERR_INVALID;
+  if (!c->traced) return fail(c, FTKB_ERR_INVALID, "get_degrees: call finalize first");
+  if (!c->deg.empty()) std::memcpy(deg, c->deg.data(), 4 * c->deg.size());
+  return FTKB_OK;
+}
+
+extern "C" int ftkb_get_stats(ftkb_ctx *c, ftkb_stats *out) {
+  if (!c || !out) return FTKB_ERR_INVALID;
+  c->stats.scaling_factor = c->factor;
+  c->stats.resolution = c->resolution;
+  *out = c->stats;
+  return FTKB_OK;
+}
+
+extern "C" int ftkb_reset_stats(ftkb_ctx *c) {
+  if (!c) return FTKB_ERR_INVALID;
+  const uint64_t pts = c->stats.points;
+  c->stats = ftkb_stats{};
+  c->stats.points = pts;
+  return FTKB_OK;
+}
+
+extern "C" int ftkb_synchronize(ftkb_ctx *c) {
+  if (!c) return FTKB_ERR_INVALID;
+  CK(cudaSetDevice(c->cfg.device));
+  CK(cudaStreamSynchronize(c->stream));
+  return FTKB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// mesh tables (host only)
+// ------------------------------------------------------------------------------------------------
+extern "C" int ftkb_mesh_ntypes(int nd_mesh, int k, int scope) {
+  if ((nd_mesh != 3 && nd_mesh != 4) || k < 0 || k > nd_mesh) return -1;
+  const MeshTables &m = mesh_tables(nd_mesh);
+  return scope == 0 ? m.ntypes(k) : scope == 1 ? (int)m.ordinal_types[k].size() : (int)m.interval_types[k].size();
+}
+
+extern "C" int ftkb_mesh_unit_simplex(int nd_mesh, int k, int type, int32_t *out) {
+  if ((nd_mesh != 3 && nd_mesh != 4) || k < 0 || k > nd_mesh || !out) return -1;
+  const MeshTables &m = mesh_tables(nd_mesh);
+  if (type < 0 || type >= m.ntypes(k)) return -1;
+  for (int i = 0; i <= k; i++)
+    for (int j = 0; j < nd_mesh; j++) out[i * nd_mesh + j] = (m.unit[k][type][i] >> j) & 1;
+  return 0;
+}
+
+extern "C" int ftkb_mesh_scope_type(int nd_mesh, int k, int scope, int itype) {
+  if ((nd_mesh != 3 && nd_mesh != 4) || k < 0 || k > nd_mesh) return -1;
+  const MeshTables &m = mesh_tables(nd_mesh);
+  const std::vector<int> *v = scope == 1 ? &m.ordinal_types[k] : scope == 2 ? &m.interval_types[k] : nullptr;
+  if (!v) return itype;
+  return itype >= 0 && itype < (int)v->size() ? (*v)[itype] : -1;
+}
+
+static int copy_offsets(const std::vector<TypeOffset> &v, int nd, int32_t *out) {
+  for (size_t i = 0; i < v.size(); i++) {
+    out[i * (nd + 1)] = v[i].type;
+    for (int j = 0; j < nd; j++) out[i * (nd + 1) + 1 + j] = v[i].off[j];
+  }
+  return (int)v.size();
+}
+
+extern "C" int ftkb_mesh_sides(int nd_mesh, int k, int type, int32_t *out) {
+  if ((nd_mesh != 3 && nd_mesh != 4) || k < 0 || k > nd_mesh || !out) return -1;
+  const MeshTables &m = mesh_tables(nd_mesh);
+  if (type < 0 || type >= m.ntypes(k)) return -1;
+  return copy_offsets(m.sides[k][type], nd_mesh, out);
+}
+
+extern "C" int ftkb_mesh_side_of(int nd_mesh, int k, int type, int32_t *out) {
+  if ((nd_mesh != 3 && nd_mesh != 4) || k < 0 || k > nd_mesh || !out) return -1;
+  const MeshTables &m = mesh_tables(nd_mesh);
+  if (type < 0 || type >= m.ntypes(k)) return -1;
+  return copy_offsets(m.side_of[k][type], nd_mesh, out);
+}

@@ -1,0 +1,1055 @@
+// Device code of the critical-point sweep, sm_100a.  Compile with -fmad=false: the reference's CPU
+// path (x86-64, no FMA contraction) is the parity target, so every floating-point expression below
+// keeps the reference's literal operation order and is never contracted; fma() appears only where
+// the reference calls it.
+//
+// Kernels
+//   scan2d / scan3d   streaming pass over the space-time cubes of one step: exact sign early-out
+//                     (all vertices of the cube strictly on one side of zero in some component =>
+//                     no simplex of the cube is punctured), survivors appended to a worklist.
+//                     HBM-bound: each vertex of layers t and t+1 is read once.
+//   test<ND>          the fused per-simplex test on the surviving cubes: ordinal->vertex decode,
+//                     gather, fixed-point quantisation, simulation-of-simplicity predicates,
+//                     inverse interpolation, lerp of position/time/scalar/Jacobian, type
+//                     classification, warp-aggregated append.
+//   gradient2d/3d, resolution, synthetic generators, element keys, neighbour search, union-find.
+#include "kernels.h"
+
+#include <cfloat>
+#include <climits>
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_select.cuh>
+
+namespace ftkb {
+
+typedef long long i64;
+typedef unsigned long long u64;
+
+__constant__ DeviceMeshTables c_mesh[2];   // [0]: 2D+t (12 triangle types), [1]: 3D+t (60 tetrahedron types)
+
+void upload_mesh_tables(const DeviceMeshTables &t2, const DeviceMeshTables &t3) {
+  DeviceMeshTables h[2] = {t2, t3};
+  cudaMemcpyToSymbol(c_mesh, h, sizeof(h));
+}
+
+// =============================================================================================
+// 1. scan: exact sign early-out on whole cubes
+// =============================================================================================
+//
+// Only the high word of each fp64 component is inspected.  With factor = 2^nbits the scaled value
+// p = v * factor has high word hi(v) + (nbits << 20) (exact for normal v), and the reference's
+// quantised integer trunc(p) is >= 1 iff p >= 1.0 and <= -1 iff p <= -1.0.  An order-preserving
+// 32-bit key k of p brackets it: p in [key_lo(k), key_hi(k)].  Per cube we keep min/max keys per
+// component; "all vertices strictly positive" is  kmin >= key(1.0).
+//
+// The early-out claims "the reference's predicate returns false".  The reference evaluates its
+// determinants in wrapping int64 arithmetic, which equals exact arithmetic only while the true
+// determinant values fit; the magnitude guard below proves that from the cube's value range, and
+// cubes that fail it are refined like any other survivor (they then go through the same wrapping
+// arithmetic as the reference).
+constexpr int KEY_ONE = 0x3FF00000;        // high word of 1.0
+constexpr int KEY_POISON_EXP = 0x43E00000; // |p| >= 2^63 (also Inf / NaN after scaling)
+
+struct KeyRange { int mn, mx; };
+
+__device__ __forceinline__ KeyRange neutral_range() { return KeyRange{INT_MAX, INT_MIN}; }
+
+__device__ __forceinline__ KeyRange vertex_range(int hi, int nbits20) {
+  const int m = hi & 0x7fffffff;
+  const int ms = (m >> 20) ? m + nbits20 : 0;      // zero / denormal: |p| < 2^-1000
+  const int k = hi < 0 ? -1 - ms : ms;
+  const bool bad = ms >= KEY_POISON_EXP;
+  return KeyRange{bad ? INT_MIN : k, bad ? INT_MAX : k};
+}
+
+__device__ __forceinline__ KeyRange merge(KeyRange a, KeyRange b) { return KeyRange{min(a.mn, b.mn), max(a.mx, b.mx)}; }
+
+__device__ __forceinline__ KeyRange shfl_down1(KeyRange a) {
+  return KeyRange{__shfl_down_sync(0xffffffffu, a.mn, 1), __shfl_down_sync(0xffffffffu, a.mx, 1)};
+}
+
+__device__ __forceinline__ double key_lo(int k) { return k >= 0 ? __hiloint2double(k, 0) : -__hiloint2double(-k, 0); }
+__device__ __forceinline__ double key_hi(int k) { return k >= 0 ? __hiloint2double(k + 1, 0) : -__hiloint2double(-1 - k, 0); }
+
+__device__ __forceinline__ bool one_sided(KeyRange r) { return r.mn >= KEY_ONE || r.mx <= -1 - KEY_ONE; }
+
+// bound on |quantised value| and on the spread of quantised values over the cube (+ truncation slack)
+__device__ __forceinline__ void magnitude_range(KeyRange r, double &M, double &R) {
+  const double lo = key_lo(r.mn), hi = key_hi(r.mx);
+  M = fmax(fabs(lo), fabs(hi)) + 1.0;
+  R = (hi - lo) + 2.0;
+}
+
+// true: no simplex with vertices in this cube can be punctured, and the reference agrees
+__device__ __forceinline__ bool cube_excluded2(KeyRange x, KeyRange y) {
+  if (!(one_sided(x) || one_sided(y))) return false;
+  if (x.mn == INT_MIN || y.mn == INT_MIN) return false;
+  double Mx, Rx, My, Ry;
+  magnitude_range(x, Mx, Rx);
+  magnitude_range(y, My, Ry);
+  // every determinant of the 2D cascade is bounded by 2 (Mx Ry + My Rx); require < 2^63 with slack
+  return Mx * Ry + My * Rx < 4.5e18;
+}
+
+__device__ __forceinline__ bool cube_excluded3(KeyRange x, KeyRange y, KeyRange z) {
+  if (!(one_sided(x) || one_sided(y) || one_sided(z))) return false;
+  if (x.mn == INT_MIN || y.mn == INT_MIN || z.mn == INT_MIN) return false;
+  double Mx, Rx, My, Ry, Mz, Rz;
+  magnitude_range(x, Mx, Rx);
+  magnitude_range(y, My, Ry);
+  magnitude_range(z, Mz, Rz);
+  // 4x4 level: <= 4 (Mx Ry Rz + My Rx Rz + Mz Rx Ry); 3x3 sub-levels: <= 2 (Ma Rb + Mb Ra)
+  const bool d4 = 4.0 * (Mx * Ry * Rz + My * Rx * Rz + Mz * Rx * Ry) < 9.0e18;
+  const bool d3 = (Mx * Ry + My * Rx < 4.5e18) && (Mx * Rz + Mz * Rx < 4.5e18) && (My * Rz + Mz * Ry < 4.5e18);
+  return d4 && d3;
+}
+
+__device__ __forceinline__ void append_survivors(const SweepParams &p, bool surv, u64 lin) {
+  const unsigned b = __ballot_sync(0xffffffffu, surv);
+  if (b == 0) return;
+  const int lane = threadIdx.x & 31;
+  u64 base = 0;
+  if (lane == __ffs(b) - 1) base = atomicAdd(p.wl_count, (u64)__popc(b));
+  base = __shfl_sync(0xffffffffu, base, __ffs(b) - 1);
+  if (surv) {
+    const u64 i = base + __popc(b & ((1u << lane) - 1));
+    if (i < p.wl_cap) p.wl[i] = lin;
+  }
+}
+
+// ---- 2D: one warp owns a strip of 32 vertex columns (31 corners) and marches along y -------------
+template <bool HAS_NEXT>
+__global__ void __launch_bounds__(256) scan2d_kernel(const SweepParams p) {
+  const int lane = threadIdx.x & 31;
+  const i64 warp = (i64)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int sx = (int)(warp % p.nsx), cy = (int)(warp / p.nsx);
+  if (cy >= p.nsy) return;
+  const int x = p.lb[0] + sx * 31 + lane;
+  const bool col_ok = x <= p.vmax[0];
+  const bool corner_col = lane < 31 && x <= p.ub[0];
+  const int ys = p.lb[1] + cy * p.rows;
+  const int ye = min(ys + p.rows - 1, p.ub[1]);
+  const int nbits20 = p.nbits << 20;
+  const int4 *__restrict__ V0 = reinterpret_cast<const int4 *>(p.L[0].V);
+  const int4 *__restrict__ V1 = reinterpret_cast<const int4 *>(p.L[1].V);
+
+  KeyRange px = neutral_range(), py = neutral_range();   // previous row, already merged over t and x..x+1
+#pragma unroll 2
+  for (int y = ys; y <= ye + 1; y++) {
+    KeyRange rx = neutral_range(), ry = neutral_range();
+    if (col_ok && y <= p.vmax[1]) {
+      const size_t i = (size_t)x + (size_t)p.W * (size_t)y;
+      const int4 a = __ldg(V0 + i);
+      rx = vertex_range(a.y, nbits20);
+      ry = vertex_range(a.w, nbits20);
+      if (HAS_NEXT) {
+        const int4 b = __ldg(V1 + i);
+        rx = merge(rx, vertex_range(b.y, nbits20));
+        ry = merge(ry, vertex_range(b.w, nbits20));
+      }
+    }
+    rx = merge(rx, shfl_down1(rx));
+    ry = merge(ry, shfl_down1(ry));
+    if (y > ys) {
+      const bool active = corner_col;
+      const bool surv = active && (p.no_filter || !cube_excluded2(merge(px, rx), merge(py, ry)));
+      append_survivors(p, surv, (u64)(x - p.lb[0]) + (u64)p.nc[0] * (u64)(y - 1 - p.lb[1]));
+    }
+    px = rx;
+    py = ry;
+  }
+}
+
+// ---- 3D: a block owns a 32 x BY column tile (31 x (BY-1) corners) and marches along z -------------
+constexpr int SCAN3_BY = 16;
+
+template <bool HAS_NEXT>
+__global__ void __launch_bounds__(32 * SCAN3_BY) scan3d_kernel(const SweepParams p) {
+  __shared__ int sh[2][6][SCAN3_BY][32];
+  const int lane = threadIdx.x, ty = threadIdx.y;
+  int b = blockIdx.x;
+  const int bx = b % p.nsx; b /= p.nsx;
+  const int by = b % p.nsy;
+  const int bz = b / p.nsy;
+  const int x = p.lb[0] + bx * 31 + lane;
+  const int y = p.lb[1] + by * (SCAN3_BY - 1) + ty;
+  const bool col_ok = x <= p.vmax[0] && y <= p.vmax[1];
+  const bool corner_col = lane < 31 && ty < SCAN3_BY - 1 && x <= p.ub[0] && y <= p.ub[1];
+  const int zs = p.lb[2] + bz * p.rows;
+  const int ze = min(zs + p.rows - 1, p.ub[2]);
+  const int nbits20 = p.nbits << 20;
+  const int *__restrict__ V0 = reinterpret_cast<const int *>(p.L[0].V);
+  const int *__restrict__ V1 = reinterpret_cast<const int *>(p.L[1].V);
+  const size_t plane = (size_t)p.W * (size_t)p.H;
+  const size_t col = (size_t)x + (size_t)p.W * (size_t)y;
+
+  KeyRange pr[3] = {neutral_range(), neutral_range(), neutral_range()};   // previous plane, merged over t, x, y
+  for (int z = zs; z <= ze + 1; z++) {
+    KeyRange r[3] = {neutral_range(), neutral_range(), neutral_range()};
+    if (col_ok && z <= p.vmax[2]) {
+      const size_t w = (col + plane * (size_t)z) * 6 + 1;   // high word of component 0
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        r[c] = vertex_range(__ldg(V0 + w + 2 * c), nbits20);
+        if (HAS_NEXT) r[c] = merge(r[c], vertex_range(__ldg(V1 + w + 2 * c), nbits20));
+      }
+    }
+    const int buf = z & 1;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      r[c] = merge(r[c], shfl_down1(r[c]));
+      sh[buf][2 * c][ty][lane] = r[c].mn;
+      sh[buf][2 * c + 1][ty][lane] = r[c].mx;
+    }
+    __syncthreads();
+    if (ty < SCAN3_BY - 1) {
+#pragma unroll
+      for (int c = 0; c < 3; c++)
+        r[c] = merge(r[c], KeyRange{sh[buf][2 * c][ty + 1][lane], sh[buf][2 * c + 1][ty + 1][lane]});
+    }
+    if (z > zs) {
+      const bool surv = corner_col &&
+          (p.no_filter || !cube_excluded3(merge(pr[0], r[0]), merge(pr[1], r[1]), merge(pr[2], r[2])));
+      append_survivors(p, surv, (u64)(x - p.lb[0]) + (u64)p.nc[0] * ((u64)(y - p.lb[1]) + (u64)p.nc[1] * (u64)(z - 1 - p.lb[2])));
+    }
+#pragma unroll
+    for (int c = 0; c < 3; c++) pr[c] = r[c];
+  }
+}
+
+void launch_scan(const SweepParams &p, cudaStream_t s) {
+  if (p.nd == 2) {
+    const i64 warps = (i64)p.nsx * p.nsy;
+    const int wpb = 8;
+    const unsigned grid = (unsigned)((warps + wpb - 1) / wpb);
+    if (p.has_next) scan2d_kernel<true><<<grid, wpb * 32, 0, s>>>(p);
+    else scan2d_kernel<false><<<grid, wpb * 32, 0, s>>>(p);
+  } else {
+    const unsigned grid = (unsigned)((i64)p.nsx * p.nsy * p.nsz);
+    const dim3 block(32, SCAN3_BY);
+    if (p.has_next) scan3d_kernel<true><<<grid, block, 0, s>>>(p);
+    else scan3d_kernel<false><<<grid, block, 0, s>>>(p);
+  }
+}
+
+// =============================================================================================
+// 2. exact predicates (ref: include/ftk/numeric/sign_det.hh, det.hh, critical_point_test.hh)
+// =============================================================================================
+// All integer arithmetic wraps mod 2^64 exactly like the reference's int64 (-fwrapv) evaluation;
+// the determinant expansions below are polynomial identities of the reference's, hence equal
+// mod 2^64 term order notwithstanding.
+__device__ __forceinline__ int sgn(i64 v) { return (v > 0) - (v < 0); }
+__device__ __forceinline__ u64 U(i64 v) { return (u64)v; }
+
+// | a0 a1 1 |
+// | b0 b1 1 |
+// | c0 c1 1 |
+__device__ __forceinline__ i64 det3_h(i64 a0, i64 a1, i64 b0, i64 b1, i64 c0, i64 c1) {
+  return (i64)(U(a0) * (U(b1) - U(c1)) - U(a1) * (U(b0) - U(c0)) + (U(b0) * U(c1) - U(b1) * U(c0)));
+}
+
+// 4x4 determinant of rows (x, y, z, 1): subtracting row 0 and expanding along the last column
+// gives -det3 of the difference rows
+__device__ __forceinline__ i64 det4_h(const i64 X[4][3]) {
+  u64 d[3][3];
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) d[i][j] = U(X[i + 1][j]) - U(X[0][j]);
+  const u64 det = d[0][0] * (d[1][1] * d[2][2] - d[1][2] * d[2][1])
+                - d[0][1] * (d[1][0] * d[2][2] - d[1][2] * d[2][0])
+                + d[0][2] * (d[1][0] * d[2][1] - d[1][1] * d[2][0]);
+  return (i64)(0 - det);
+}
+
+// sign of the 3x3 orientation determinant with the symbolic perturbation cascade (sign_det.hh:44-90)
+__device__ int sos_sign3(const i64 X[3][2]) {
+  int s = sgn(det3_h(X[0][0], X[0][1], X[1][0], X[1][1], X[2][0], X[2][1]));
+  if (s) return s;
+  s = -sgn((i64)(U(X[1][0]) - U(X[2][0])));
+  if (s) return s;
+  s = sgn((i64)(U(X[1][1]) - U(X[2][1])));
+  if (s) return s;
+  s = sgn((i64)(U(X[0][0]) - U(X[2][0])));
+  if (s) return s;
+  return 1;
+}
+
+// 4x4 cascade (sign_det.hh:92-200): 15 levels
+__device__ int sos_sign4(const i64 X[4][3]) {
+  int s = sgn(det4_h(X));
+  if (s) return s;
+#define D3(r0, r1, r2, c0, c1) det3_h(X[r0][c0], X[r0][c1], X[r1][c0], X[r1][c1], X[r2][c0], X[r2][c1])
+#define D2(r0, r1, c) ((i64)(U(X[r0][c]) - U(X[r1][c])))
+  s = sgn(D3(1, 2, 3, 0, 1)); if (s) return s;
+  s = -sgn(D3(1, 2, 3, 0, 2)); if (s) return s;
+  s = sgn(D3(1, 2, 3, 1, 2)); if (s) return s;
+  s = -sgn(D3(0, 2, 3, 0, 1)); if (s) return s;
+  s = sgn(D2(2, 3, 0)); if (s) return s;
+  s = -sgn(D2(2, 3, 1)); if (s) return s;
+  s = sgn(D3(0, 2, 3, 0, 2)); if (s) return s;
+  s = sgn(D2(2, 3, 2)); if (s) return s;
+  s = -sgn(D3(0, 2, 3, 1, 2)); if (s) return s;
+  s = sgn(D3(0, 1, 3, 0, 1)); if (s) return s;
+  s = -sgn(D2(1, 3, 0)); if (s) return s;
+  s = sgn(D2(1, 3, 1)); if (s) return s;
+  s = sgn(D2(0, 3, 0)); if (s) return s;
+#undef D3
+#undef D2
+  return 1;
+}
+
+// rows sorted by vertex rank with the reference's bubble sort (strict >, adjacent swaps); the
+// sign flips with the parity of the number of swaps (sign_det.hh:203-289)
+template <int NV, int NC>
+__device__ int oriented_sign(const i64 Xin[NV][NC], const int idx_in[NV]) {
+  int idx[NV], ord[NV];
+#pragma unroll
+  for (int i = 0; i < NV; i++) { idx[i] = idx_in[i]; ord[i] = i; }
+  int swaps = 0;
+#pragma unroll
+  for (int i = 0; i < NV - 1; i++)
+#pragma unroll
+    for (int j = 0; j < NV - 1 - i; j++)
+      if (idx[j] > idx[j + 1]) {
+        int t = idx[j]; idx[j] = idx[j + 1]; idx[j + 1] = t;
+        t = ord[j]; ord[j] = ord[j + 1]; ord[j + 1] = t;
+        swaps++;
+      }
+  i64 X[NV][NC];
+#pragma unroll
+  for (int i = 0; i < NV; i++)
+#pragma unroll
+    for (int j = 0; j < NC; j++) {
+      // ord[] is a register-resident permutation: select without dynamic indexing
+      i64 v = 0;
+#pragma unroll
+      for (int q = 0; q < NV; q++) v = (ord[i] == q) ? Xin[q][j] : v;
+      X[i][j] = v;
+    }
+  int s;
+  if constexpr (NV == 3) s = sos_sign3(X);
+  else s = sos_sign4(X);
+  return (swaps & 1) ? -s : s;
+}
+
+// origin (rank -1) inside the simplex: the orientation must not change when any one row is
+// replaced by the origin (sign_det.hh:360-414, critical_point_test.hh:22-34)
+template <int NV, int NC>
+__device__ bool origin_in_simplex(const i64 X[NV][NC], const int idx[NV]) {
+  const int s = oriented_sign<NV, NC>(X, idx);
+#pragma unroll 1
+  for (int i = 0; i < NV; i++) {
+    i64 Y[NV][NC];
+    int my[NV];
+#pragma unroll
+    for (int j = 0; j < NV; j++) {
+      const bool rep = (j == i);
+      my[j] = rep ? -1 : idx[j];
+#pragma unroll
+      for (int c = 0; c < NC; c++) Y[j][c] = rep ? 0 : X[j][c];
+    }
+    if (oriented_sign<NV, NC>(Y, my) != s) return false;
+  }
+  return true;
+}
+
+// =============================================================================================
+// 3. floating-point leaves (literal operation order of the reference)
+// =============================================================================================
+__device__ __forceinline__ double std_max(double a, double b) { return (a < b) ? b : a; }
+__device__ __forceinline__ double std_min(double a, double b) { return (b < a) ? b : a; }
+
+// ref: include/ftk/numeric/clamp.hh:15-37
+template <int N>
+__device__ __forceinline__ void clamp_barycentric(double *x) {
+  double sum = 0.0;
+#pragma unroll
+  for (int i = 0; i < N; i++) { x[i] = std_min(std_max(0.0, x[i]), 1.0); sum += x[i]; }
+#pragma unroll
+  for (int i = 0; i < N; i++) x[i] /= sum;
+  if (isnan(x[0]) || isinf(x[0])) {
+#pragma unroll
+    for (int i = 0; i < N; i++) x[i] = 1.0 / N;
+  }
+}
+
+// ref: inverse_linear_interpolation_solver.hh:32-54, linear_solver.hh:22-34 (Cramer)
+__device__ bool inverse_lerp2(const double V[3][2], double mu[3]) {
+  const double eps = DBL_EPSILON;
+  const double A00 = V[0][0] - V[2][0], A01 = V[1][0] - V[2][0], A10 = V[0][1] - V[2][1], A11 = V[1][1] - V[2][1];
+  const double b0 = -V[2][0], b1 = -V[2][1];
+  const double D = A00 * A11 - A10 * A01, Dx = b0 * A11 - A01 * b1, Dy = A00 * b1 - b0 * A10;
+  mu[0] = Dx / D;
+  mu[1] = Dy / D;
+  mu[2] = 1.0 - mu[0] - mu[1];
+  return mu[0] >= -eps && mu[0] <= 1.0 + eps && mu[1] >= -eps && mu[1] <= 1.0 + eps && mu[2] >= -eps && mu[2] <= 1.0 + eps;
+}
+
+// ref: inverse_linear_interpolation_solver.hh:143-167, linear_solver.hh:12-20, matrix_inverse.hh:23-45
+__device__ bool inverse_lerp3(const double V[4][3], double l[4]) {
+  const double eps = DBL_EPSILON;
+  double m[3][3], inv[3][3];
+#pragma unroll
+  for (int r = 0; r < 3; r++)
+#pragma unroll
+    for (int c = 0; c < 3; c++) m[r][c] = V[c][r] - V[3][r];
+  const double b[3] = {-V[3][0], -V[3][1], -V[3][2]};
+  inv[0][0] = m[1][1] * m[2][2] - m[1][2] * m[2][1];
+  inv[0][1] = -m[0][1] * m[2][2] + m[0][2] * m[2][1];
+  inv[0][2] = m[0][1] * m[1][2] - m[0][2] * m[1][1];
+  inv[1][0] = -m[1][0] * m[2][2] + m[1][2] * m[2][0];
+  inv[1][1] = m[0][0] * m[2][2] - m[0][2] * m[2][0];
+  inv[1][2] = -m[0][0] * m[1][2] + m[0][2] * m[1][0];
+  inv[2][0] = m[1][0] * m[2][1] - m[1][1] * m[2][0];
+  inv[2][1] = -m[0][0] * m[2][1] + m[0][1] * m[2][0];
+  inv[2][2] = m[0][0] * m[1][1] - m[0][1] * m[1][0];
+  const double det = m[0][0] * inv[0][0] + m[0][1] * inv[1][0] + m[0][2] * inv[2][0];
+  const double invdet = 1.0 / det;
+#pragma unroll
+  for (int r = 0; r < 3; r++)
+#pragma unroll
+    for (int c = 0; c < 3; c++) inv[r][c] = inv[r][c] * invdet;
+#pragma unroll
+  for (int r = 0; r < 3; r++) l[r] = inv[r][0] * b[0] + inv[r][1] * b[1] + inv[r][2] * b[2];
+  l[3] = 1.0 - l[0] - l[1] - l[2];
+  return l[0] >= -eps && l[0] < 1.0 + eps && l[1] >= -eps && l[1] < 1.0 + eps &&
+         l[2] >= -eps && l[2] < 1.0 + eps && l[3] >= -eps && l[3] < 1.0 + eps;
+}
+
+// ref: critical_point_type.hh:40-72, eigen_solver2.hh:18-41,63-68, quadratic_solver.hh:12-25
+__device__ unsigned cp_type_2d(const double J[2][2], bool symmetric) {
+  if (symmetric) {
+    const double m00 = J[0][0], m10 = J[1][0], m11 = J[1][1];
+    const double b = -(m00 + m11), c = m00 * m11 - m10 * m10;
+    const double delta = fma(b, b, -4 * c);
+    const double sq = delta < 0 ? 0 : sqrt(delta);
+    double e0 = 0.5 * (-b + sq), e1 = 0.5 * (-b - sq);
+    if (fabs(e0) < fabs(e1)) { const double t = e0; e0 = e1; e1 = t; }
+    if (e0 > 0 && e1 > 0) return 2;
+    if (e0 < 0 && e1 < 0) return 8;
+    if (e0 * e1 < 0) return 4;
+    return 1;
+  }
+  const double P1 = -(J[0][0] + J[1][1]), P0 = J[0][0] * J[1][1] - J[1][0] * J[0][1];
+  const double delta = P1 * P1 - 4 * 1.0 * P0;
+  if (delta >= 0) {
+    const double r0 = (-P1 + sqrt(delta)) / 2.0, r1 = (-P1 - sqrt(delta)) / 2.0;
+    if (r0 * r1 < 0) return 4;
+    if (r0 > 0 && r1 > 0) return 2;
+    if (r0 < 0 && r1 < 0) return 8;
+    return 1;
+  }
+  // conjugate pair (or NaN): real part of (-P1 + pow(complex(delta), 0.5)) / 2, evaluated the way
+  // libstdc++ does (polar form), so a vanishing trace still yields the tiny positive real part
+  const double rho = exp(0.5 * log(fabs(delta))), theta = 0.5 * atan2(0.0, delta);
+  const double re = (-P1 + rho * cos(theta)) / 2.0;
+  if (re < 0) return 16;
+  if (re > 0) return 32;
+  return 64;
+}
+
+// ref: critical_point_type.hh:74-93, eigen_solver3.hh:16-47, characteristic_polynomial.hh:36-47
+__device__ unsigned cp_type_3d(const double A[3][3], bool symmetric) {
+  if (!symmetric) return 0;
+  const double b = -(A[0][0] + A[1][1] + A[2][2]);
+  const double c = A[1][1] * A[2][2] + A[0][0] * A[2][2] + A[0][0] * A[1][1] - A[0][1] * A[1][0] - A[1][2] * A[2][1] - A[0][2] * A[2][0];
+  const double d = -(A[0][0] * (A[1][1] * A[2][2] - A[1][2] * A[2][1]) - A[0][1] * (A[1][0] * A[2][2] - A[1][2] * A[2][0]) +
+                     A[0][2] * (A[1][0] * A[2][1] - A[1][1] * A[2][0]));
+  double x0, x1, x2;
+  double q = (3.0 * c - (b * b)) / 9.0;
+  const double r = (-(27.0 * d) + b * (9.0 * c - 2.0 * (b * b))) / 54.0;
+  const double disc = q * q * q + r * r;
+  const double term1 = (b / 3.0);
+  if (disc >= 0) {
+    const double r13 = (r < 0) ? -pow(-r, (1.0 / 3.0)) : pow(r, (1.0 / 3.0));
+    x0 = -term1 + 2.0 * r13;
+    x1 = -(r13 + term1);
+    x2 = -(r13 + term1);
+  } else {
+    const double kPi = 3.14159265358979323846;
+    q = -q;
+    double dum1 = q * q * q;
+    dum1 = acos(r / sqrt(dum1));
+    const double r13 = 2.0 * sqrt(q);
+    x0 = -term1 + r13 * cos(dum1 / 3.0);
+    x1 = -term1 + r13 * cos((dum1 + 2.0 * kPi) / 3.0);
+    x2 = -term1 + r13 * cos((dum1 + 4.0 * kPi) / 3.0);
+  }
+  if (x0 * x1 * x2 == 0.0) return 1;
+  if (x0 < 0 && x1 < 0 && x2 < 0) return 8;
+  if (x0 > 0 && x1 > 0 && x2 > 0) return 2;
+  return 4;
+}
+
+// =============================================================================================
+// 4. the fused per-simplex test
+// =============================================================================================
+__device__ __forceinline__ int clampi(int i, int n) { return i < 0 ? 0 : (i > n - 1 ? n - 1 : i); }
+
+// x86-64 cvttsd2si semantics: out-of-range and NaN give INT64_MIN (the reference's cast, compiled for x86-64)
+__device__ __forceinline__ i64 quantise(double v, double factor) {
+  const double pq = v * factor;
+  if (!(pq < 9223372036854775808.0) || pq < -9223372036854775808.0) return LLONG_MIN;
+  return (i64)pq;
+}
+
+// Jacobian at one vertex, derived on demand from the resident vector layer with the reference's
+// formulas (ref: include/ftk/ndarray/grad.hh:54-86, incl. the unscaled first term and the
+// non-symmetric variant's off-diagonals landing on array element 0 only).
+__device__ void jacobian2d_at(const SweepParams &p, const double *V, int i, int j, double G[2][2] /* G[a][b] = jacobian(a,b,i,j) */) {
+  const int W = p.W, H = p.H;
+#define F2(c, ii, jj) __ldg(V + (c) + 2 * ((size_t)clampi(ii, W) + (size_t)W * clampi(jj, H)))
+  const double H00 = F2(0, i + 1, j) - F2(0, i - 1, j) * (W - 1), H11 = F2(1, i, j + 1) - F2(1, i, j - 1) * (H - 1);
+  G[0][0] = H00;
+  G[1][1] = H11;
+  if (p.derived_symmetric) {
+    const double H01 = F2(0, i, j + 1) - F2(0, i, j - 1) * (H - 1), H10 = F2(1, i + 1, j) - F2(1, i - 1, j) * (W - 1);
+    G[0][1] = G[1][0] = (H01 + H10) * 0.5;
+  } else if (i == 0 && j == 0) {
+    const int li = W - 1, lj = H - 1;   // the last vertex written by the reference's loop
+    G[0][1] = F2(0, li, lj + 1) - F2(0, li, lj - 1) * (H - 1);
+    G[1][0] = F2(1, li + 1, lj) - F2(1, li - 1, lj) * (W - 1);
+  } else {
+    G[0][1] = G[1][0] = 0.0;
+  }
+#undef F2
+}
+
+// ref: grad.hh:175-212 (interior [2, D-3] only, zero elsewhere)
+__device__ void jacobian3d_at(const SweepParams &p, const double *V, int i, int j, int k, double G[3][3] /* G[c][d] = dV_c/dx_d * 0.5 form */) {
+  const int W = p.W, H = p.H, D = p.D;
+  const bool in = i >= 2 && i < W - 2 && j >= 2 && j < H - 2 && k >= 2 && k < D - 2;
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    if (!in) { G[c][0] = G[c][1] = G[c][2] = 0.0; continue; }
+#define F3(c, ii, jj, kk) __ldg(V + (c) + 3 * ((size_t)(ii) + (size_t)W * ((size_t)(jj) + (size_t)H * (size_t)(kk))))
+    G[c][0] = 0.5 * (F3(c, i + 1, j, k) - F3(c, i - 1, j, k));
+    G[c][1] = 0.5 * (F3(c, i, j + 1, k) - F3(c, i, j - 1, k));
+    G[c][2] = 0.5 * (F3(c, i, j, k + 1) - F3(c, i, j, k - 1));
+#undef F3
+  }
+}
+
+// SoS vertex rank: position in the mesh lattice (domain x time), uint64 truncated to int
+// (ref: regular_tracker.hh:188-194, lattice.hh:196-207)
+template <int ND>
+__device__ __forceinline__ int sos_rank(const SweepParams &p, const int *v /* ND spatial + time */) {
+  u64 prod = 1, i = 0;
+#pragma unroll
+  for (int j = 0; j <= ND; j++) {
+    const int lbj = j < ND ? p.lb[j] : 0;
+    const u64 d = (u64)(i64)(v[j] - lbj);
+    i += d * prod;
+    if (j < ND) prod *= (u64)(p.ub[j] - p.lb[j] + 1);
+  }
+  return (int)(unsigned)i;
+}
+
+template <int ND>
+__device__ bool check_simplex(const SweepParams &p, const DeviceMeshTables &mt, const int corner[3], int type, ftkb_point &cp) {
+  constexpr int NV = ND + 1;
+  int vt[NV][ND + 1];
+  const LayerPtrs *L[NV];
+  size_t vi[NV];
+  // vertices + validity (ref: simplicial_regular_mesh.hh:356-386)
+#pragma unroll
+  for (int k = 0; k < NV; k++) {
+    const int m = mt.vmask[type][k];
+#pragma unroll
+    for (int j = 0; j < ND; j++) {
+      vt[k][j] = corner[j] + ((m >> j) & 1);
+      if (vt[k][j] < p.lb[j] || vt[k][j] > p.ub[j]) return false;
+    }
+    const int dt = (m >> ND) & 1;
+    vt[k][ND] = p.t + dt;
+    if (vt[k][ND] < 0) return false;
+    L[k] = &p.L[dt];
+    vi[k] = ND == 2 ? (size_t)vt[k][0] + (size_t)p.W * (size_t)vt[k][1]
+                    : (size_t)vt[k][0] + (size_t)p.W * ((size_t)vt[k][1] + (size_t)p.H * (size_t)vt[k][2]);
+  }
+  double v[NV][ND];
+#pragma unroll
+  for (int k = 0; k < NV; k++)
+#pragma unroll
+    for (int c = 0; c < ND; c++) v[k][c] = __ldg(L[k]->V + ND * vi[k] + c);
+
+  double mu[NV];
+  bool inside = false;
+  if constexpr (ND == 3) inside = inverse_lerp3(v, mu);
+
+  i64 vf[NV][ND];
+  int rank[NV];
+  if (ND == 2 || p.robust) {
+#pragma unroll
+    for (int k = 0; k < NV; k++)
+#pragma unroll
+      for (int c = 0; c < ND; c++) {
+        if (isnan(v[k][c]) || isinf(v[k][c])) return false;
+        vf[k][c] = quantise(v[k][c], p.factor);
+      }
+#pragma unroll
+    for (int k = 0; k < NV; k++) rank[k] = sos_rank<ND>(p, vt[k]);
+    // cheap exact exclusion on the quantised integers before the full cascade: one strictly
+    // signed component, with magnitudes small enough that no determinant can leave int64
+    {
+      const i64 lim = ND == 2 ? (1ll << 29) : (1ll << 19);
+      bool small = true, sided = false;
+#pragma unroll
+      for (int c = 0; c < ND; c++) {
+        bool pos = true, neg = true;
+#pragma unroll
+        for (int k = 0; k < NV; k++) {
+          pos = pos && vf[k][c] > 0;
+          neg = neg && vf[k][c] < 0;
+          small = small && vf[k][c] < lim && vf[k][c] > -lim;
+        }
+        sided = sided || pos || neg;
+      }
+      if (small && sided) return false;
+    }
+    if (!origin_in_simplex<NV, ND>(vf, rank)) return false;
+  } else {
+    if (!inside) return false;
+  }
+
+  if constexpr (ND == 2) {
+    inside = inverse_lerp2(v, mu);
+    if (!inside) clamp_barycentric<3>(mu);
+  } else {
+    clamp_barycentric<4>(mu);
+  }
+
+  // position / time: lerp of the integer vertex coordinates (REGULAR_COORDS_SIMPLE), ref linear_interpolation.hh:81-99
+  double xo[4];
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    double acc;
+    if constexpr (ND == 2) {
+      const double c0 = q < 2 ? (double)vt[0][q] : (q == 2 ? 0.0 : (double)vt[0][2]);
+      const double c1 = q < 2 ? (double)vt[1][q] : (q == 2 ? 0.0 : (double)vt[1][2]);
+      const double c2 = q < 2 ? (double)vt[2][q] : (q == 2 ? 0.0 : (double)vt[2][2]);
+      acc = c0 * mu[0] + c1 * mu[1] + c2 * mu[2];
+    } else {
+      acc = (double)vt[0][q] * mu[0] + (double)vt[1][q] * mu[1] + (double)vt[2][q] * mu[2] + (double)vt[ND][q] * mu[ND];
+    }
+    xo[q] = acc;
+  }
+  cp.x[0] = xo[0]; cp.x[1] = xo[1]; cp.x[2] = xo[2]; cp.t = xo[3];
+
+  cp.scalar = 0.0;
+  if (p.scalar_source != FTKB_SOURCE_NONE) {
+    double acc = __ldg(L[0]->S + vi[0]) * mu[0] + __ldg(L[1]->S + vi[1]) * mu[1] + __ldg(L[2]->S + vi[2]) * mu[2];
+    if constexpr (ND == 3) acc = acc + __ldg(L[ND]->S + vi[ND]) * mu[ND];
+    cp.scalar = acc;
+  }
+  cp.corner[0] = corner[0]; cp.corner[1] = corner[1];
+  cp.corner[2] = ND == 3 ? corner[2] : 0;
+  cp.corner[3] = p.t;
+  cp.simplex_type = type;
+  cp.ordinal = mt.ordinal[type];
+  cp.timestep = p.t;
+
+  if constexpr (ND == 2) {
+    if (p.compute_degrees) {
+      if (cp.ordinal) {
+        int deg = oriented_sign<3, 2>(vf, rank);
+        deg *= (type == 4) ? 1 : -1;
+        cp.cp_type = deg == 1 ? 1 : 2;
+      } else cp.cp_type = 0;
+    } else {
+      double J[2][2] = {{0, 0}, {0, 0}};
+      if (p.jacobian_source != FTKB_SOURCE_NONE) {
+        double Js[3][2][2];
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+          if (L[k]->J) {
+#pragma unroll
+            for (int a = 0; a < 2; a++)
+#pragma unroll
+              for (int b = 0; b < 2; b++) Js[k][a][b] = __ldg(L[k]->J + b + 2 * (a + 2 * vi[k]));
+          } else {
+            double G[2][2];
+            jacobian2d_at(p, L[k]->V, vt[k][0], vt[k][1], G);
+#pragma unroll
+            for (int a = 0; a < 2; a++)
+#pragma unroll
+              for (int b = 0; b < 2; b++) Js[k][a][b] = G[b][a];
+          }
+        }
+#pragma unroll
+        for (int a = 0; a < 2; a++)
+#pragma unroll
+          for (int b = 0; b < 2; b++) J[a][b] = Js[0][a][b] * mu[0] + Js[1][a][b] * mu[1] + Js[2][a][b] * mu[2];
+        const double sym = 0.5 * (J[0][1] + J[1][0]);
+        J[0][1] = J[1][0] = sym;
+      }
+      cp.cp_type = cp_type_2d(J, p.jacobian_symmetric != 0);
+    }
+    if (p.use_type_filter && !(p.type_filter & cp.cp_type)) return false;
+  } else {
+    double Js[4][3][3];
+#pragma unroll 1
+    for (int k = 0; k < 4; k++) {
+      if (L[k]->J) {
+        for (int a = 0; a < 3; a++)
+          for (int b = 0; b < 3; b++) Js[k][a][b] = __ldg(L[k]->J + b + 3 * (a + 3 * vi[k]));
+      } else if (p.jacobian_source == FTKB_SOURCE_DERIVED) {
+        double G[3][3];
+        jacobian3d_at(p, L[k]->V, vt[k][0], vt[k][1], vt[k][2], G);
+        for (int a = 0; a < 3; a++)
+          for (int b = 0; b < 3; b++) Js[k][a][b] = G[b][a];
+      } else {
+        for (int a = 0; a < 3; a++)
+          for (int b = 0; b < 3; b++) Js[k][a][b] = 0.0;
+      }
+    }
+    double J[3][3];
+#pragma unroll
+    for (int a = 0; a < 3; a++)
+#pragma unroll
+      for (int b = 0; b < 3; b++) {
+        double acc = 0.0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) acc += Js[k][a][b] * mu[k];
+        J[a][b] = acc;
+      }
+    cp.cp_type = cp_type_3d(J, p.jacobian_symmetric != 0);
+  }
+  return true;
+}
+
+template <int ND>
+__global__ void __launch_bounds__(128) test_kernel(const SweepParams p) {
+  const DeviceMeshTables &mt = c_mesh[ND - 2];
+  const int ntypes = ND == 2 ? 12 : 60;
+  u64 ncubes = *p.wl_count;
+  if (ncubes > p.wl_cap) ncubes = p.wl_cap;
+  const u64 total = ncubes * ntypes;
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  const u64 rounds = (total + stride - 1) / stride;
+  const int lane = threadIdx.x & 31;
+  for (u64 r = 0; r < rounds; r++) {
+    const u64 i = r * stride + (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    bool hit = false;
+    ftkb_point cp;
+    if (i < total) {
+      const u64 lin = p.wl[i / ntypes];
+      const int type = (int)(i % ntypes);
+      if (p.has_next || mt.ordinal[type]) {
+        int corner[3];
+        u64 q = lin;
+        corner[0] = (int)(q % (u64)p.nc[0]) + p.lb[0]; q /= (u64)p.nc[0];
+        corner[1] = (int)(q % (u64)p.nc[1]) + p.lb[1]; q /= (u64)p.nc[1];
+        corner[2] = ND == 3 ? (int)q + p.lb[2] : 0;
+        hit = check_simplex<ND>(p, mt, corner, type, cp);
+      }
+    }
+    const unsigned b = __ballot_sync(0xffffffffu, hit);
+    if (b) {
+      u64 base = 0;
+      const int leader = __ffs(b) - 1;
+      if (lane == leader) base = atomicAdd(p.pt_count, (u64)__popc(b));
+      base = __shfl_sync(0xffffffffu, base, leader);
+      if (hit) {
+        const u64 o = base + __popc(b & ((1u << lane) - 1));
+        if (o < p.pt_cap) p.pts[o] = cp;
+      }
+    }
+  }
+}
+
+void launch_test(const SweepParams &p, cudaStream_t s) {
+  // the number of surviving cubes is only known on the device: fixed grid, grid-stride loop
+  const unsigned grid = 148 * 8;
+  if (p.nd == 2) test_kernel<2><<<grid, 128, 0, s>>>(p);
+  else test_kernel<3><<<grid, 128, 0, s>>>(p);
+}
+
+// =============================================================================================
+// 5. field derivation + resolution
+// =============================================================================================
+__device__ __forceinline__ void block_min_nonzero(double m, unsigned long long *res_bits) {
+  // positive doubles order like their bit patterns
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmin(m, __shfl_xor_sync(0xffffffffu, m, o));
+  __shared__ double sm[32];
+  const int tid = threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z);
+  const int nw = (blockDim.x * blockDim.y * blockDim.z + 31) >> 5;
+  if ((tid & 31) == 0) sm[tid >> 5] = m;
+  __syncthreads();
+  if (tid < 32) {
+    m = tid < nw ? sm[tid] : DBL_MAX;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmin(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (tid == 0 && m < DBL_MAX) atomicMin(res_bits, (unsigned long long)__double_as_longlong(m));
+  }
+}
+
+__device__ __forceinline__ double nz_abs(double v) { const double a = fabs(v); return (v != 0.0 && !isnan(v)) ? a : DBL_MAX; }
+
+// ref: grad.hh:10-31 (clamped one-sided borders, scaled by (DW-1)/(DH-1), no 1/2)
+__global__ void __launch_bounds__(256) gradient2d_kernel(const double *__restrict__ S, double2 *__restrict__ V, int W, int H, unsigned long long *res_bits) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y * blockDim.y + threadIdx.y;
+  double m = DBL_MAX;
+  if (i < W && j < H) {
+    const size_t row = (size_t)W * j;
+    const double gx = (__ldg(S + row + clampi(i + 1, W)) - __ldg(S + row + clampi(i - 1, W))) * (W - 1);
+    const double gy = (__ldg(S + (size_t)W * clampi(j + 1, H) + i) - __ldg(S + (size_t)W * clampi(j - 1, H) + i)) * (H - 1);
+    V[row + i] = make_double2(gx, gy);
+    m = fmin(nz_abs(gx), nz_abs(gy));
+  }
+  block_min_nonzero(m, res_bits);
+}
+
+// ref: grad.hh:130-149 (interior only, 1/2 central difference, border stays zero)
+__global__ void __launch_bounds__(256) gradient3d_kernel(const double *__restrict__ S, double *__restrict__ V, int W, int H, int D, unsigned long long *res_bits) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y * blockDim.y + threadIdx.y, k = blockIdx.z;
+  double m = DBL_MAX;
+  if (i < W && j < H) {
+    const size_t idx = (size_t)i + (size_t)W * ((size_t)j + (size_t)H * k);
+    double g0 = 0.0, g1 = 0.0, g2 = 0.0;
+    if (i >= 1 && i < W - 1 && j >= 1 && j < H - 1 && k >= 1 && k < D - 1) {
+      const size_t sy = W, sz = (size_t)W * H;
+      g0 = 0.5 * (__ldg(S + idx + 1) - __ldg(S + idx - 1));
+      g1 = 0.5 * (__ldg(S + idx + sy) - __ldg(S + idx - sy));
+      g2 = 0.5 * (__ldg(S + idx + sz) - __ldg(S + idx - sz));
+    }
+    V[3 * idx] = g0; V[3 * idx + 1] = g1; V[3 * idx + 2] = g2;
+    m = fmin(nz_abs(g0), fmin(nz_abs(g1), nz_abs(g2)));
+  }
+  block_min_nonzero(m, res_bits);
+}
+
+void launch_gradient(int nd, const double *S, double *V, int W, int H, int D, unsigned long long *res_bits, cudaStream_t s) {
+  const dim3 block(64, 4);
+  if (nd == 2) {
+    const dim3 grid((W + 63) / 64, (H + 3) / 4);
+    gradient2d_kernel<<<grid, block, 0, s>>>(S, reinterpret_cast<double2 *>(V), W, H, res_bits);
+  } else {
+    const dim3 grid((W + 63) / 64, (H + 3) / 4, D);
+    gradient3d_kernel<<<grid, block, 0, s>>>(S, V, W, H, D, res_bits);
+  }
+}
+
+// ref: ndarray.hh:769-779 resolution(): min |p| over the non-zero entries
+__global__ void __launch_bounds__(256) resolution_kernel(const double *__restrict__ p, u64 n, unsigned long long *res_bits) {
+  double m = DBL_MAX;
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) m = fmin(m, nz_abs(__ldg(p + i)));
+  block_min_nonzero(m, res_bits);
+}
+
+void launch_resolution(const double *p, uint64_t n, unsigned long long *res_bits, cudaStream_t s) {
+  const u64 blocks = (n + 255) / 256;
+  const unsigned grid = (unsigned)(blocks < 148ull * 16 ? (blocks ? blocks : 1) : 148ull * 16);
+  resolution_kernel<<<grid, 256, 0, s>>>(p, n, res_bits);
+}
+
+__global__ void fill_u64_kernel(unsigned long long *p, unsigned long long v) { *p = v; }
+void launch_fill_u64(unsigned long long *p, unsigned long long v, cudaStream_t s) { fill_u64_kernel<<<1, 1, 0, s>>>(p, v); }
+
+// =============================================================================================
+// 6. synthetic generators (benchmark inputs; ref: include/ftk/ndarray/synthetic.hh)
+// =============================================================================================
+struct SynParams { double p[8]; };
+
+__global__ void __launch_bounds__(256) synthetic_kernel(int kind, int nd, int W, int H, int D, SynParams sp, double t, double *__restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y * blockDim.y + threadIdx.y, k = blockIdx.z;
+  if (i >= W || j >= H) return;
+  const size_t idx = (size_t)i + (size_t)W * ((size_t)j + (size_t)H * k);
+  const double kPi = 3.14159265358979323846;
+  switch (kind) {
+    case FTKB_SYN_MOVING_EXTREMUM: {   // synthetic.hh:332-354; pow(d, 2) is the correctly rounded square
+      const int xi[3] = {i, j, k};
+      double d = 0;
+      for (int q = 0; q < nd; q++) {
+        const double xc = sp.p[q] + sp.p[nd + q] * t;
+        const double e = xi[q] - xc;
+        d += e * e;
+      }
+      out[idx] = d;
+    } break;
+    case FTKB_SYN_WOVEN: {             // synthetic.hh:32-48, scaling_factor = 15
+      const double x = (((double)i / (W - 1)) - 0.5) * 15, y = (((double)j / (H - 1)) - 0.5) * 15;
+      out[idx] = cos(x * cos(t) - y * sin(t)) * sin(x * sin(t) + y * cos(t));
+    } break;
+    case FTKB_SYN_MERGER: {            // synthetic.hh:262-297
+      double x = (((double)i / (W - 1)) - 0.5) * 4, y = (((double)j / (H - 1)) - 0.5) * 4;
+      const double xp = x * cos(t) - y * sin(t), yp = x * sin(t) + y * cos(t);
+      x = xp; y = yp;
+      const double cx0 = sin(t - kPi / 2), cx1 = sin(t + kPi / 2), cy = 1e-4;
+      const double f0 = exp(-((x - cx0) * (x - cx0) + (y - cy) * (y - cy))), f1 = exp(-((x - cx1) * (x - cx1) + (y - cy) * (y - cy)));
+      out[idx] = std_max(f0, f1);
+    } break;
+    case FTKB_SYN_DOUBLE_GYRE: {       // synthetic.hh:130-150,193-217 on [0,2]x[0,1]
+      const double A = sp.p[0], omega = sp.p[1], eps = sp.p[2];
+      const double x = ((double)i / (W - 1)) * 2, y = ((double)j / (H - 1));
+      const double a = eps * sin(omega * t), b = 1 - 2 * eps * sin(omega * t);
+      const double f = a * x * x + b * x, dfdx = 2 * a * x + b;
+      out[2 * idx] = -kPi * A * sin(kPi * f) * cos(kPi * y);
+      out[2 * idx + 1] = kPi * A * cos(kPi * f) * sin(kPi * y) * dfdx;
+    } break;
+    case FTKB_SYN_ABC: {               // synthetic.hh:239-260 on [0, 2 pi]^3
+      const double A = sp.p[0], B = sp.p[1], C = sp.p[2];
+      const double x = (((double)i / (W - 1))) * 2 * kPi, y = (((double)j / (H - 1))) * 2 * kPi, z = (((double)k / (D - 1))) * 2 * kPi;
+      out[3 * idx] = A * sin(z) + C * cos(y);
+      out[3 * idx + 1] = B * sin(x) + A * cos(z);
+      out[3 * idx + 2] = C * sin(y) + B * cos(x);
+    } break;
+  }
+}
+
+void launch_synthetic(int kind, int nd, int W, int H, int D, const double *params, double t, double *out, cudaStream_t s) {
+  SynParams sp;
+  for (int i = 0; i < 8; i++) sp.p[i] = params[i];
+  const dim3 block(64, 4), grid((W + 63) / 64, (H + 3) / 4, D);
+  synthetic_kernel<<<grid, block, 0, s>>>(kind, nd, W, H, D, sp, t, out);
+}
+
+// =============================================================================================
+// 7. trajectory construction: element keys, neighbour search, union-find
+// =============================================================================================
+// element key = reference element order (corner compared x first, then y[, z], t, then type;
+// simplicial_regular_mesh.hh:327-337) packed into 64 bits
+__device__ __forceinline__ bool element_key(const TraceParams &tp, int x, int y, int z, int t, int type, u64 &key) {
+  if (x < tp.lb[0] || x > tp.ub[0] || y < tp.lb[1] || y > tp.ub[1] || t < 0 || t >= (1 << KEY_TIME_BITS)) return false;
+  if (tp.nd == 3 && (z < tp.lb[2] || z > tp.ub[2])) return false;
+  u64 k = (u64)(x - tp.lb[0]);
+  k = k * (u64)tp.ny + (u64)(y - tp.lb[1]);
+  k = k * (u64)tp.nz + (u64)(tp.nd == 3 ? z - tp.lb[2] : 0);
+  k = (k << KEY_TIME_BITS) | (u64)t;
+  key = (k << KEY_TYPE_BITS) | (u64)type;
+  return true;
+}
+
+__global__ void point_keys_kernel(const ftkb_point *__restrict__ pts, u64 n, TraceParams tp, u64 *keys, uint32_t *idx) {
+  const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  u64 k = ~0ull;
+  element_key(tp, pts[i].corner[0], pts[i].corner[1], pts[i].corner[2], pts[i].corner[3], pts[i].simplex_type, k);
+  keys[i] = k;
+  idx[i] = (uint32_t)i;
+}
+
+void launch_point_keys(const ftkb_point *pts, uint64_t n, const TraceParams &tp, unsigned long long *keys, uint32_t *idx, cudaStream_t s) {
+  if (n) point_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(pts, n, tp, keys, idx);
+}
+
+__global__ void gather_points_kernel(const ftkb_point *__restrict__ src, const uint32_t *__restrict__ idx, u64 n, ftkb_point *dst) {
+  const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[idx[i]];
+}
+
+void launch_gather_points(const ftkb_point *src, const uint32_t *idx, uint64_t n, ftkb_point *dst, cudaStream_t s) {
+  if (n) gather_points_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(src, idx, n, dst);
+}
+
+// neighbours of a punctured simplex = the other facets of its two cofaces that are punctured too
+// (ref: critical_point_tracker_2d_regular.hh:189-197); found by binary search in the sorted keys
+__global__ void neighbors_kernel(TraceParams tp) {
+  const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= tp.n) return;
+  const DeviceMeshTables &mt = c_mesh[tp.nd - 2];
+  const ftkb_point pt = tp.pts[i];
+  const int type = pt.simplex_type;
+  uint32_t found[8];
+  int cnt = 0;
+  for (int q = 0; q < mt.n_nb[type]; q++) {
+    const int x = pt.corner[0] + mt.nb_off[type][q][0], y = pt.corner[1] + mt.nb_off[type][q][1];
+    const int z = tp.nd == 3 ? pt.corner[2] + mt.nb_off[type][q][2] : 0;
+    const int t = pt.corner[3] + mt.nb_off[type][q][tp.nd];
+    u64 key;
+    if (!element_key(tp, x, y, z, t, mt.nb_type[type][q], key)) continue;
+    u64 lo = 0, hi = tp.n;
+    while (lo < hi) {
+      const u64 mid = (lo + hi) >> 1;
+      if (tp.keys[mid] < key) lo = mid + 1; else hi = mid;
+    }
+    if (lo < tp.n && tp.keys[lo] == key) found[cnt++] = (uint32_t)lo;
+  }
+  // ascending order (= element order); candidates are distinct elements
+  for (int a = 1; a < cnt; a++)
+    for (int b = a; b > 0 && found[b - 1] > found[b]; b--) { const uint32_t t = found[b]; found[b] = found[b - 1]; found[b - 1] = t; }
+  for (int q = 0; q < 8; q++) tp.nb[i * 8 + q] = q < cnt ? found[q] : 0xffffffffu;
+  tp.deg[i] = cnt;
+  tp.parent_all[i] = (uint32_t)i;
+  tp.parent_ord[i] = (uint32_t)i;
+}
+
+void launch_neighbors(const TraceParams &tp, cudaStream_t s) {
+  if (tp.n) neighbors_kernel<<<(unsigned)((tp.n + 127) / 128), 128, 0, s>>>(tp);
+}
+
+// union-find with atomicMin hooking: the larger root is hooked under the smaller one, so the root of
+// every tree is its smallest member (the reference's duf hooks the same way, basic/duf.hh:41-72)
+__device__ __forceinline__ uint32_t uf_find(uint32_t *parent, uint32_t i) {
+  uint32_t p = parent[i];
+  while (p != i) {
+    const uint32_t g = parent[p];
+    if (g != p) atomicMin(parent + i, g);   // path halving; parents only ever decrease towards the root
+    i = p;
+    p = g;
+  }
+  return i;
+}
+
+__device__ void uf_unite(uint32_t *parent, uint32_t a, uint32_t b) {
+  while (true) {
+    a = uf_find(parent, a);
+    b = uf_find(parent, b);
+    if (a == b) return;
+    if (a < b) { const uint32_t t = a; a = b; b = t; }
+    const uint32_t old = atomicMin(parent + a, b);
+    if (old == a) return;
+    a = old;
+  }
+}
+
+__global__ void uf_hook_kernel(TraceParams tp) {
+  const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= tp.n) return;
+  const bool special = tp.deg[i] > 2;
+  for (int q = 0; q < 8; q++) {
+    const uint32_t j = tp.nb[i * 8 + q];
+    if (j == 0xffffffffu) break;
+    if (j < i) continue;                       // each edge once
+    uf_unite(tp.parent_all, (uint32_t)i, j);
+    if (!special && tp.deg[j] <= 2) uf_unite(tp.parent_ord, (uint32_t)i, j);
+  }
+}
+
+// pointer jumping to the root
+__global__ void uf_flatten_kernel(TraceParams tp) {
+  const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= tp.n) return;
+  uint32_t r = tp.parent_all[i];
+  while (tp.parent_all[r] != r) r = tp.parent_all[r];
+  uint32_t o = tp.parent_ord[i];
+  while (tp.parent_ord[o] != o) o = tp.parent_ord[o];
+  tp.parent_all[i] = r;
+  tp.parent_ord[i] = o;
+}
+
+void launch_union_find(const TraceParams &tp, cudaStream_t s) {
+  if (!tp.n) return;
+  const unsigned grid = (unsigned)((tp.n + 127) / 128);
+  uf_hook_kernel<<<grid, 128, 0, s>>>(tp);
+  uf_flatten_kernel<<<grid, 128, 0, s>>>(tp);
+}
+
+// ---- cub wrappers ---------------------------------------------------------------------------------
+size_t sort_pairs_u64(void *temp, size_t temp_bytes, const unsigned long long *kin, unsigned long long *kout,
+                      const uint32_t *vin, uint32_t *vout, uint64_t n, cudaStream_t s) {
+  size_t bytes = temp_bytes;
+  cub::DeviceRadixSort::SortPairs(temp, bytes, kin, kout, vin, vout, (int64_t)n, 0, 64, s);
+  return bytes;
+}
+
+size_t unique_by_key_u64(void *temp, size_t temp_bytes, const unsigned long long *kin, const uint32_t *vin,
+                         unsigned long long *kout, uint32_t *vout, unsigned long long *n_out, uint64_t n, cudaStream_t s) {
+  size_t bytes = temp_bytes;
+  cub::DeviceSelect::UniqueByKey(temp, bytes, kin, vin, kout, vout, n_out, (int64_t)n, s);
+  return bytes;
+}
+
+}  // namespace ftkb

@@ -1,0 +1,91 @@
+// Kernel parameter blocks and launchers (host-callable).  Device code lives in kernels.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+#include "../../include/ftkb200.h"
+#include "mesh_tables.h"
+
+namespace ftkb {
+
+// One resident time layer (device pointers; any may be null)
+struct LayerPtrs {
+  const double *S;  // (W,H[,D])
+  const double *V;  // (n,W,H[,D])
+  const double *J;  // (n,n,W,H[,D]) only when the Jacobian is GIVEN
+};
+
+struct SweepParams {
+  int32_t nd;                 // 2 or 3
+  int32_t W, H, D;            // array dims (D = 1 in 2D)
+  int32_t lb[3], ub[3];       // domain (inclusive)
+  int32_t nc[3];              // corners per dimension = ub - lb + 1 (1 for the unused dim)
+  int32_t vmax[3];            // last loadable vertex per dim = min(ub + 1, dim - 1)
+  int32_t t;                  // current timestep (time of layer 0)
+  int32_t has_next;           // layer 1 present -> interval simplices are swept too
+  int32_t nbits;              // factor = 2^nbits
+  double factor;
+  int32_t no_filter;          // 3D with robust detection off: every cube is refined
+  // sources / options (see ftkb_config)
+  int32_t scalar_source, jacobian_source, jacobian_symmetric, derived_symmetric;
+  int32_t robust, compute_degrees, use_type_filter;
+  uint32_t type_filter;
+  LayerPtrs L[2];
+  // scan decomposition
+  int32_t nsx;                // x strips (31 corners each)
+  int32_t nsy;                // 2D: row chunks; 3D: y tiles (BY-1 corners each)
+  int32_t nsz;                // 3D: z chunks
+  int32_t rows;               // corner rows (2D) / corner planes (3D) per chunk
+  // worklist of surviving cubes (linear corner index, x fastest over the domain)
+  unsigned long long *wl_count;
+  unsigned long long wl_cap;
+  unsigned long long *wl;
+  // output
+  unsigned long long *pt_count;
+  unsigned long long pt_cap;
+  ftkb_point *pts;
+};
+
+void upload_mesh_tables(const DeviceMeshTables &t2, const DeviceMeshTables &t3);
+
+void launch_scan(const SweepParams &p, cudaStream_t s);
+// thread-per-(surviving cube, type) exact test; grid sized for `expected` cubes, grid-stride otherwise
+void launch_test(const SweepParams &p, cudaStream_t s);
+
+// field derivation (ref: include/ftk/ndarray/grad.hh) + min non-zero |v| (ndarray.hh:769-779).
+// res_bits: the running minimum as the bit pattern of a positive double (atomicMin on u64).
+void launch_gradient(int nd, const double *S, double *V, int W, int H, int D, unsigned long long *res_bits, cudaStream_t s);
+void launch_resolution(const double *p, uint64_t n, unsigned long long *res_bits, cudaStream_t s);
+void launch_fill_u64(unsigned long long *p, unsigned long long v, cudaStream_t s);
+
+// synthetic generators (ref: include/ftk/ndarray/synthetic.hh); out is S (scalar kinds) or V (vector kinds)
+void launch_synthetic(int kind, int nd, int W, int H, int D, const double *params, double t, double *out, cudaStream_t s);
+
+// finalize
+struct TraceParams {
+  int32_t nd;
+  int32_t lb[3], ub[3];
+  int64_t ny, nz;             // domain extents used by the element key
+  uint64_t n;                 // number of (sorted, unique) points
+  const unsigned long long *keys;   // sorted
+  const ftkb_point *pts;            // sorted
+  uint32_t *nb;               // n * 8 neighbour indices (ascending), 0xffffffff padded
+  int32_t *deg;
+  uint32_t *parent_all;       // union-find over every punctured simplex
+  uint32_t *parent_ord;       // union-find over ordinary nodes (degree <= 2)
+};
+constexpr int KEY_TYPE_BITS = 6;
+constexpr int KEY_TIME_BITS = 22;
+
+void launch_point_keys(const ftkb_point *pts, uint64_t n, const TraceParams &tp, unsigned long long *keys, uint32_t *idx, cudaStream_t s);
+void launch_gather_points(const ftkb_point *src, const uint32_t *idx, uint64_t n, ftkb_point *dst, cudaStream_t s);
+void launch_neighbors(const TraceParams &tp, cudaStream_t s);
+void launch_union_find(const TraceParams &tp, cudaStream_t s);
+
+// cub wrappers (sort by key, then drop duplicate keys); return bytes of temp storage needed when temp == nullptr
+size_t sort_pairs_u64(void *temp, size_t temp_bytes, const unsigned long long *kin, unsigned long long *kout,
+                      const uint32_t *vin, uint32_t *vout, uint64_t n, cudaStream_t s);
+size_t unique_by_key_u64(void *temp, size_t temp_bytes, const unsigned long long *kin, const uint32_t *vin,
+                         unsigned long long *kout, uint32_t *vout, unsigned long long *n_out, uint64_t n, cudaStream_t s);
+
+}  // namespace ftkb

@@ -1,0 +1,174 @@
+/* ftkb200.h -- C ABI of the B200-native critical-point extraction/tracking engine.
+ *
+ * This is the drop-in boundary for ONE path of hguo/ftk: critical-point tracking on regular grids.
+ * It replaces the reference's accelerator entry points, which are C++ free functions with C++
+ * types and per-call cudaMalloc/H2D/launch/D2H/cudaFree:
+ *
+ *   extract_cp2dt_cuda(scope, t, domain, core, ext, Vc, Vn, Jc, Jn, Sc, Sn, use_explicit_coords, coords)
+ *       ref: include/ftk/filters/critical_point_tracker_2d_regular.hh:33-47,
+ *            src/filters/critical_point_tracer_2d_regular.cu:274-310
+ *   extract_cp3dt_cuda(scope, t, domain4, core4, ext3, Vc, Vl, Jc, Jl, Sc, Sl)
+ *       ref: include/ftk/filters/critical_point_tracker_3d_regular.hh:42-56,
+ *            src/filters/critical_point_tracer_3d_regular.cu:252-276
+ *
+ * and, one level up, carries the whole operator surface of
+ * ftk::critical_point_tracker_{2d,3d}_regular (set_domain / push_field_data_snapshot /
+ * advance_timestep / update_timestep / finalize / get_traced_critical_points), so that the C++
+ * shim classes (include/ftk_b200/critical_point_tracker_regular.hh), the Python module
+ * (ftk_b200/) and the CLI call ONLY this ABI.  Unlike the reference entry points it is stateful:
+ * field layers stay resident in HBM between calls and results are produced to match the
+ * reference's CPU tracker (not its fixed-precision CUDA kernel).
+ *
+ * Conventions: extern "C", plain pointers and sizes.  Every function returns an int status
+ * (0 = FTKB_OK) and never calls exit(); ftkb_last_error() returns a message for the last failure
+ * on that context.  The caller owns every output buffer; the library owns all device memory.
+ * One context is driven from one host thread at a time (internally: one device, one stream).
+ * There is NO CPU fallback: ftkb_create() fails with FTKB_ERR_NO_DEVICE without a usable
+ * sm_100 device.
+ */
+#ifndef FTKB200_H
+#define FTKB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FTKB_ABI_VERSION 1
+
+enum {
+  FTKB_OK = 0,
+  FTKB_ERR_INVALID = 1,      /* bad argument / bad call order */
+  FTKB_ERR_NO_DEVICE = 2,    /* no CUDA device of compute capability 10.x */
+  FTKB_ERR_CUDA = 3,         /* a CUDA runtime call or kernel failed (message has the detail) */
+  FTKB_ERR_NOMEM = 4,
+  FTKB_ERR_OVERFLOW = 5      /* an index range does not fit the 64-bit element id */
+};
+
+/* field sources, same values as ftk::SOURCE_* (ref: include/ftk/filters/critical_point_tracker.hh:21-25) */
+enum { FTKB_SOURCE_NONE = 0, FTKB_SOURCE_GIVEN = 1, FTKB_SOURCE_DERIVED = 2 };
+
+/* where the pointers handed to ftkb_push_snapshot live */
+enum {
+  FTKB_MEM_HOST = 0,          /* host memory; copied to the device before the call returns */
+  FTKB_MEM_DEVICE = 1,        /* device memory on the context's device; copied (D2D) */
+  FTKB_MEM_DEVICE_BORROW = 2  /* device memory used in place: must stay valid and unchanged until the
+                                 layer has been popped (two ftkb_advance_timestep calls later) */
+};
+
+/* synthetic generators of ftkb_push_synthetic (ref: include/ftk/ndarray/synthetic.hh) */
+enum {
+  FTKB_SYN_MOVING_EXTREMUM = 0, /* scalar; params: x0[nd], dir[nd]        synthetic.hh:332-354 */
+  FTKB_SYN_WOVEN = 1,           /* 2D scalar; params: (none); t = time     synthetic.hh:32-48  */
+  FTKB_SYN_DOUBLE_GYRE = 2,     /* 2D vector; params: A, omega, eps        synthetic.hh:130-217 */
+  FTKB_SYN_ABC = 3,             /* 3D vector; params: A, B, C              synthetic.hh:239-260 */
+  FTKB_SYN_MERGER = 4           /* 2D scalar; params: (none)               synthetic.hh:262-297 */
+};
+
+typedef struct ftkb_config {
+  int32_t abi_version;        /* FTKB_ABI_VERSION */
+  int32_t nd;                 /* spatial dimensionality: 2 or 3 */
+  int32_t dims[3];            /* array dims W, H, D (dim 0 fastest); set_array_domain, regular_tracker.hh:27 */
+  int32_t lb[3], ub[3];       /* tracker domain, inclusive; set_domain, regular_tracker.hh:24 */
+  int32_t scalar_source, vector_source, jacobian_source;   /* FTKB_SOURCE_* */
+  int32_t jacobian_symmetric; /* set_jacobian_symmetric */
+  int32_t robust_detection;   /* 3D only; critical_point_tracker_3d_regular.hh:442 */
+  int32_t compute_degrees;    /* 2D only; critical_point_tracker_2d_regular.hh:653-662 */
+  int32_t use_type_filter;    /* 2D only; critical_point_tracker.hh:190-200 */
+  uint32_t type_filter;
+  int32_t start_timestep;     /* initial current_timestep (tracker.hh:76); a time slab starts here */
+  int32_t device;             /* CUDA device ordinal */
+  double  resolution_init;    /* running min non-zero |v| inherited from earlier time slabs; <= 0: DBL_MAX
+                                 (critical_point_tracker.hh:850-864 keeps a running minimum over all sweeps) */
+  uint64_t point_capacity;    /* initial capacity of the punctured-simplex buffer; 0: default (grows on demand) */
+} ftkb_config;
+
+/* one punctured simplex; same 72-byte layout the parity oracle uses */
+typedef struct ftkb_point {
+  int32_t corner[4];          /* x, y, z, t of the simplex's corner (z = 0 in 2D) */
+  int32_t simplex_type;       /* index among all n-simplex types of the (n+1)-D mesh */
+  int32_t ordinal;            /* 1: all vertices in one time layer */
+  int32_t timestep;
+  uint32_t cp_type;           /* ftk critical point type bits, critical_point_type.hh:10-36 */
+  double x[3], t, scalar;
+} ftkb_point;
+
+typedef struct ftkb_stats {
+  uint64_t simplices_tested;  /* enumerated work items, valid or not */
+  uint64_t cells_scanned;     /* space-time cubes visited by the scan kernel */
+  uint64_t cells_refined;     /* cubes that survived the exact sign early-out */
+  uint64_t points;            /* punctured simplices found so far */
+  uint64_t kernel_launches;   /* launches of this library's own kernels */
+  uint64_t h2d_bytes, d2h_bytes;
+  double ms_derive;           /* device time (CUDA events on the context's stream), accumulated */
+  double ms_scan;
+  double ms_test;
+  double ms_finalize_device;
+  double ms_finalize_host;
+  double last_ms_scan;        /* most recent scan launch */
+  double last_ms_derive;
+  double scaling_factor;      /* current quantisation factor (1 << nbits) */
+  double resolution;          /* running min non-zero |v| */
+} ftkb_stats;
+
+typedef struct ftkb_ctx ftkb_ctx;
+
+int ftkb_abi_version(void);
+/* number of usable devices (compute capability 10.x); 0 if none */
+int ftkb_device_count(void);
+
+int ftkb_create(const ftkb_config *cfg, ftkb_ctx **out);
+void ftkb_destroy(ftkb_ctx *);
+const char *ftkb_last_error(const ftkb_ctx *);   /* ctx may be NULL: last create() failure */
+
+/* push_field_data_snapshot(scalar, vector, jacobian): critical_point_tracker.hh:202-213.
+ * Arrays are dim-0-fastest: scalar (W,H[,D]); vector (n,W,H[,D]); jacobian (n,n,W,H[,D]).
+ * A pointer may be NULL when its source is NONE or DERIVED. */
+int ftkb_push_snapshot(ftkb_ctx *, const double *scalar, const double *vector, const double *jacobian, int where);
+/* device-side generator for snapshot time `t` (benchmarks; no host data involved) */
+int ftkb_push_synthetic(ftkb_ctx *, int kind, const double *params, int nparams, double t);
+
+int ftkb_update_timestep(ftkb_ctx *);    /* critical_point_tracker_{2d,3d}_regular::update_timestep */
+int ftkb_advance_timestep(ftkb_ctx *);   /* critical_point_tracker.hh:841-848 */
+int ftkb_finalize(ftkb_ctx *);           /* trace_critical_points_offline, critical_point_tracker.hh:668-817 */
+int ftkb_current_timestep(const ftkb_ctx *, int32_t *t);
+
+/* resolution (min non-zero |v|) of the most recently pushed layer; lets time slabs exchange the
+ * running minimum */
+int ftkb_last_layer_resolution(ftkb_ctx *, double *res);
+int ftkb_set_resolution(ftkb_ctx *, double res);   /* lower the running minimum (never raises it) */
+
+/* punctured simplices, sorted by the reference's element order (corner x first, then type;
+ * simplicial_regular_mesh.hh:327-337), duplicates removed */
+int ftkb_num_points(ftkb_ctx *, uint64_t *n);
+int ftkb_get_points(ftkb_ctx *, ftkb_point *out, uint64_t cap);
+/* add punctured simplices found elsewhere (another time slab) before ftkb_finalize */
+int ftkb_import_points(ftkb_ctx *, const ftkb_point *pts, uint64_t n);
+
+/* after ftkb_finalize: trajectories as CSR over the sorted point array */
+int ftkb_num_trajectories(ftkb_ctx *, uint64_t *n);
+int ftkb_get_trajectories(ftkb_ctx *, uint64_t *offsets /* n+1 */, uint64_t *point_idx, uint8_t *loop /* n */);
+/* label of the connected component (special nodes included) of each sorted point = index of its
+ * smallest member; and the number of punctured neighbours of each sorted point */
+int ftkb_get_component_labels(ftkb_ctx *, uint64_t *labels);
+int ftkb_get_degrees(ftkb_ctx *, int32_t *deg);
+
+int ftkb_get_stats(ftkb_ctx *, ftkb_stats *out);
+int ftkb_reset_stats(ftkb_ctx *);
+/* block until all work queued on the context's stream is complete */
+int ftkb_synchronize(ftkb_ctx *);
+
+/* implicit simplicial mesh tables (simplicial_regular_mesh.hh:620-831); no device needed.
+ * nd_mesh = 3 (2D+t) or 4 (3D+t); scope: 0 all, 1 ordinal, 2 interval */
+int ftkb_mesh_ntypes(int nd_mesh, int k, int scope);
+int ftkb_mesh_unit_simplex(int nd_mesh, int k, int type, int32_t *out /* (k+1)*nd_mesh */);
+int ftkb_mesh_scope_type(int nd_mesh, int k, int scope, int itype);
+/* out[] = entries of (type, off[nd_mesh]); returns the number of entries */
+int ftkb_mesh_sides(int nd_mesh, int k, int type, int32_t *out);
+int ftkb_mesh_side_of(int nd_mesh, int k, int type, int32_t *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

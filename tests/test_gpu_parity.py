@@ -1,0 +1,275 @@
+"""GPU: the CUDA path, called through the C ABI (libftkb200.so), against the parity oracle and the
+fixtures produced by the unmodified reference.
+
+Bar (north_star / SURVEY.md App. A10): punctured set, simplex types, ordinal flags, timesteps and
+critical-point types bit-exact; trajectories equal as a set of ordered sequences; interpolated
+x/y/z/t and scalar within 1e-9 absolute in grid units.
+"""
+import numpy as np
+import pytest
+
+import _parity as P
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-9   # north_star tolerance on interpolated coordinates / scalar
+
+
+@pytest.fixture(scope="module")
+def ftk():
+    import ftk_b200
+    from ftk_b200 import _lib
+    if _lib.lib().ftkb_device_count() < 1:
+        pytest.fail("no sm_100 device visible: the CUDA path cannot run (there is no fallback)")
+    return ftk_b200
+
+
+def cuda_result(tr):
+    return {"points": tr.get_discrete_critical_points(), "trajectories": tr.get_trajectory_index()}
+
+
+@pytest.mark.parametrize("name", P.golden_names())
+def test_cuda_matches_reference_golden(name, ftk, oracle):
+    meta, gold, inp = P.load_golden(name)
+    snaps = P.golden_snapshots(meta, inp, oracle)
+    field = "scalar" if meta["nv"] == 1 else "vector"
+    tr = ftk.track(snaps, meta["dims"], field=field, jacobian_symmetric=meta["symmetric"])
+    got = cuda_result(tr)
+    P.assert_same_result(got, gold, tol=TOL, what=name)
+    st = tr.stats()
+    assert st["kernel_launches"] > 0 and st["simplices_tested"] > 0
+    tr.close()
+
+
+def _both(ftk, oracle, snaps, dims, field, **kw):
+    o = oracle.track(snaps, dims, field=field, **kw)
+    c = ftk.track(snaps, dims, field=field, **kw)
+    return c, o
+
+
+def _rand_series(rng, dims, T, nv, kind):
+    shape = tuple(reversed(dims)) + ((nv,) if nv > 1 else ())
+    if kind == "int":
+        return [rng.integers(-3, 4, size=shape).astype(np.float64) for _ in range(T)]
+    if kind == "smooth":
+        grids = np.meshgrid(*[np.arange(d, dtype=np.float64) for d in reversed(dims)], indexing="ij")
+        out = []
+        for k in range(T):
+            comps = []
+            for c in range(max(nv, 1)):
+                f = 0.0
+                for q, g in enumerate(grids):
+                    f = f + np.cos(0.7 * g + 0.3 * q + 0.11 * k + 1.3 * c) * (1.0 + 0.2 * q)
+                comps.append(f + 0.05 * rng.standard_normal(size=f.shape))
+            out.append(np.stack(comps, axis=-1) if nv > 1 else comps[0])
+        return out
+    return [rng.standard_normal(size=shape) for _ in range(T)]
+
+
+CASES = [
+    # dims, T, field, kind, extra tracker kwargs
+    ([17, 13], 4, "scalar", "normal", {}),
+    ([17, 13], 4, "scalar", "int", {}),
+    ([40, 35], 5, "scalar", "smooth", {}),
+    ([16, 12], 4, "vector", "normal", {}),
+    ([16, 12], 4, "vector", "int", {}),
+    ([16, 12], 4, "vector", "normal", {"jacobian_symmetric": True}),
+    ([33, 9], 3, "vector", "smooth", {}),
+    ([14, 12], 3, "scalar", "normal", {"compute_degrees": True}),
+    ([14, 12], 3, "scalar", "normal", {"type_filter": 0x2 | 0x8}),
+    ([14, 12], 3, "vector", "normal", {"lb": [0, 0], "ub": [13, 11]}),           # domain = whole array
+    ([14, 12], 3, "scalar", "normal", {"lb": [3, 1], "ub": [9, 10]}),
+    ([14, 12], 3, "scalar", "normal", {"start_timestep": 5}),
+    ([70, 5], 3, "vector", "normal", {}),                                        # several x strips, ragged
+    ([9, 8, 7], 3, "scalar", "normal", {}),
+    ([9, 8, 7], 3, "scalar", "int", {}),
+    ([12, 11, 10], 3, "scalar", "smooth", {}),
+    ([8, 7, 7], 3, "vector", "normal", {}),
+    ([8, 7, 7], 3, "vector", "int", {}),
+    ([8, 7, 7], 3, "vector", "normal", {"jacobian_symmetric": True}),
+    ([8, 7, 7], 3, "vector", "normal", {"robust": False}),
+    ([8, 7, 6], 3, "vector", "normal", {"lb": [0, 0, 0], "ub": [7, 6, 5]}),
+    ([36, 20, 5], 2, "vector", "smooth", {}),                                    # several x/y tiles
+    ([7, 6, 40], 2, "scalar", "smooth", {}),                                     # several z chunks
+]
+
+
+@pytest.mark.parametrize("case", range(len(CASES)))
+def test_cuda_matches_oracle_random(case, ftk, oracle):
+    dims, T, field, kind, kw = CASES[case]
+    rng = np.random.default_rng(1000 + case)
+    nv = 1 if field == "scalar" else len(dims)
+    snaps = _rand_series(rng, dims, T, nv, kind)
+    c, o = _both(ftk, oracle, snaps, dims, field, **kw)
+    got, want = cuda_result(c), P.oracle_result(o)
+    assert len(want["points"]) > 0, "degenerate test case: the oracle found nothing"
+    P.assert_same_result(got, want, tol=TOL, what=f"case {case}")
+    # component partition (special nodes included) and node degrees, bit-exact
+    assert np.array_equal(c.get_component_labels(), o.component_labels())
+    assert np.array_equal(c.get_degrees(), o.degrees())
+    assert c.stats()["scaling_factor"] == o.scaling_factor
+    c.close()
+
+
+def test_given_jacobian_and_scalar(ftk, oracle):
+    """push_field_data_snapshot(scalar, vector, jacobian) with every field GIVEN"""
+    rng = np.random.default_rng(5)
+    dims, T = [13, 11], 3
+    ot = oracle.Tracker(dims, field="vector", scalar_source=1, vector_source=1, jacobian_source=1, jacobian_symmetric=False)
+    ct = ftk.make_tracker(dims, field="vector", scalar_source=1, vector_source=1, jacobian_source=1, jacobian_symmetric=False)
+    for k in range(T):
+        s, v, j = rng.standard_normal((11, 13)), rng.standard_normal((11, 13, 2)), rng.standard_normal((11, 13, 2, 2))
+        for t in (ot, ct):
+            t.push_field_data_snapshot(scalar=s, vector=v, jacobian=j)
+            if k:
+                t.advance_timestep()
+            if k == T - 1:
+                t.update_timestep()
+    ot.finalize()
+    ct.finalize()
+    P.assert_same_result(cuda_result(ct), P.oracle_result(ot), tol=TOL, what="given jacobian")
+    assert len(set(ct.get_discrete_critical_points()["cp_type"])) > 2   # foci / centres appear with a full Jacobian
+    ct.close()
+
+
+def test_empty_and_single_snapshot(ftk, oracle):
+    """no punctured simplex at all; and a single snapshot (ordinal sweep only, extractors path)"""
+    dims = [12, 10]
+    s = np.ones((10, 12)) + np.arange(12)[None, :] * 1.0     # constant gradient: no critical point
+    c, o = _both(ftk, oracle, [s, s + 1.0], dims, "scalar")
+    assert len(c.get_discrete_critical_points()) == 0 == len(o.points())
+    assert c.get_trajectory_index() == []
+    c.close()
+    rng = np.random.default_rng(11)
+    c, o = _both(ftk, oracle, [rng.standard_normal((10, 12))], dims, "scalar")
+    got = cuda_result(c)
+    assert got["points"]["ordinal"].all() and len(got["points"]) > 0
+    P.assert_same_result(got, P.oracle_result(o), tol=TOL, what="single snapshot")
+    c.close()
+
+
+def test_repeated_update_is_idempotent(ftk):
+    """a second update_timestep on the same snapshots re-inserts the same map keys (std::map semantics)"""
+    rng = np.random.default_rng(3)
+    snaps = [rng.standard_normal((10, 12)) for _ in range(2)]
+    tr = ftk.make_tracker([12, 10], field="scalar")
+    tr.push_scalar_field_snapshot(snaps[0])
+    tr.push_scalar_field_snapshot(snaps[1])
+    tr.update_timestep()
+    a = tr.get_discrete_critical_points().copy()
+    tr.update_timestep()
+    b = tr.get_discrete_critical_points()
+    assert len(a) > 0 and np.array_equal(a, b)
+    tr.close()
+
+
+def test_buffers_grow_on_demand(ftk, oracle):
+    """a noisy field larger than the initial worklist / point buffers: results still match the oracle"""
+    rng = np.random.default_rng(21)
+    dims, T = [300, 260], 2
+    snaps = [rng.standard_normal((260, 300)) for _ in range(T)]
+    c, o = _both(ftk, oracle, snaps, dims, "scalar", trace=False)
+    got, want = c.get_discrete_critical_points(), o.points()
+    assert len(want) > 2000
+    P.assert_same_result({"points": got}, {"points": want}, check_trajectories=False, tol=TOL, what="noisy 300x260")
+    st = c.stats()
+    assert st["cells_refined"] > 65536    # the default worklist had to grow
+    c.close()
+
+
+def test_device_generator_matches_host_input(ftk, oracle):
+    """ftkb_push_synthetic(moving_extremum) is bit-identical to pushing the host-generated field"""
+    dims, T = [64, 48], 6
+    x0, d = [30.3, 21.7], [0.4, 0.3]
+    host = [oracle.gen_moving_extremum(dims, x0, d, float(k)) for k in range(T)]
+    a = ftk.track(host, dims, field="scalar")
+    b = ftk.make_tracker(dims, field="scalar")
+    for k in range(T):
+        b.push_synthetic_snapshot(0, x0 + d, float(k))
+        if k:
+            b.advance_timestep()
+        if k == T - 1:
+            b.update_timestep()
+    b.finalize()
+    pa, pb = a.get_discrete_critical_points(), b.get_discrete_critical_points()
+    assert len(pa) > 0 and np.array_equal(pa, pb)
+    assert P.canonical_trajectories(a.get_trajectory_index()) == P.canonical_trajectories(b.get_trajectory_index())
+    a.close()
+    b.close()
+
+
+# ---- full-size properties (sizes the oracle cannot finish in seconds) ----------------------------
+def _track_moving_extremum(ftk, dims, x0, d, T):
+    tr = ftk.make_tracker(dims, field="scalar")
+    for k in range(T):
+        tr.push_synthetic_snapshot(0, list(x0) + list(d), float(k))
+        if k:
+            tr.advance_timestep()
+        if k == T - 1:
+            tr.update_timestep()
+    tr.finalize()
+    return tr
+
+
+def test_moving_extremum_2d_full_width_line_equation(ftk):
+    """BASELINE configs[1] at full spatial size (8192^2), 4 timesteps: exactly one trajectory, every
+    point on x = x0 + dir t (the reference's own moving-extremum check,
+    tests/test_critical_point_tracking_moving_extremum_2d.cpp:23-95), all minima, and the
+    scan kernel refined only a handful of the 6.7e7 cubes per step."""
+    dims, x0, d, T = [8192, 8192], (4096.3, 4095.7), (0.1, 0.1), 4
+    tr = _track_moving_extremum(ftk, dims, x0, d, T)
+    pts = tr.get_discrete_critical_points()
+    trajs = tr.get_trajectory_index()
+    assert len(trajs) == 1 and len(trajs[0][0]) == len(pts) and len(pts) >= 2 * T - 1
+    for q in range(2):
+        assert np.abs(pts["x"][:, q] - (x0[q] + d[q] * pts["t"])).max() < 1e-9
+    assert (pts["cp_type"] == 2).all()
+    st = tr.stats()
+    assert st["simplices_tested"] == 8189 * 8189 * (12 * (T - 1) + 2)
+    assert st["cells_refined"] < 64 * T
+    tr.close()
+
+
+def test_moving_extremum_3d_line_equation(ftk):
+    """BASELINE configs[2] generator at 256^3 x 3 (pentachora mesh)"""
+    dims, x0, d, T = [256, 256, 256], (128.3, 127.7, 128.1), (0.1, 0.11, 0.1), 3
+    tr = _track_moving_extremum(ftk, dims, x0, d, T)
+    pts = tr.get_discrete_critical_points()
+    trajs = tr.get_trajectory_index()
+    assert len(trajs) == 1 and len(trajs[0][0]) == len(pts) and len(pts) >= 2 * T - 1
+    for q in range(3):
+        assert np.abs(pts["x"][:, q] - (x0[q] + d[q] * pts["t"])).max() < 1e-9
+    assert (pts["cp_type"] == 2).all()
+    assert tr.stats()["simplices_tested"] == 253 ** 3 * (60 * (T - 1) + 6)
+    tr.close()
+
+
+def test_time_slab_split_equals_single_run(ftk, oracle):
+    """two contexts, each owning a contiguous time slab (+ one halo layer and the inherited running
+    resolution), merged by a final union-find over the imported points == one sequential run"""
+    rng = np.random.default_rng(77)
+    dims, T, cut = [24, 20], 8, 4
+    snaps = _rand_series(rng, dims, T, 1, "smooth")
+    whole = ftk.track(snaps, dims, field="scalar")
+    want = cuda_result(whole)
+    o = oracle.track(snaps, dims, field="scalar")
+    P.assert_same_result(want, P.oracle_result(o), tol=TOL, what="whole run")
+    # slab 0: timesteps [0, cut) needs layers 0..cut ; slab 1: [cut, T) needs layers cut..T-1
+    a = ftk.make_tracker(dims, field="scalar")
+    for k in range(0, cut + 1):
+        a.push_scalar_field_snapshot(snaps[k])
+        if k:
+            a.advance_timestep()
+    res = a.stats()["resolution"]
+    b = ftk.make_tracker(dims, field="scalar", start_timestep=cut, resolution_init=res)
+    for k in range(cut, T):
+        b.push_scalar_field_snapshot(snaps[k])
+        if k > cut:
+            b.advance_timestep()
+        if k == T - 1:
+            b.update_timestep()
+    a.import_points(b.get_discrete_critical_points())
+    a.finalize()
+    P.assert_same_result(cuda_result(a), want, tol=0.0, what="time-slab merge")
+    for t in (whole, a, b):
+        t.close()
