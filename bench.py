@@ -1,0 +1,418 @@
+#!/usr/bin/env python
+"""bench.py -- space-time simplices tested per second (BASELINE.json metric) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config c2|c3|c5] [--impl reference]
+
+One "step" = one advance_timestep of the tracker on one new snapshot: field derivation (gradient +
+min non-zero |v|), quantisation factor, ordinal sweep at t and interval sweep over [t, t+1]
+(scan + per-simplex test kernels), i.e. 12 (2D) / 60 (3D) enumerated simplices per domain corner.
+
+Default workload = BASELINE.json configs[1]: moving-extremum 2D scalar field 8192 x 8192, 64 distinct
+timesteps resident in HBM (the sweep ping-pongs through them when K > 63).  `value` is measured
+with the snapshots already resident in HBM (borrowed in place through the C ABI); `e2e` repeats the
+measurement through the same C-ABI calls with pinned HOST buffers (H2D of every snapshot inside
+the timed region).  N > 1: one process per GPU, each rank owns a contiguous time slab of K steps
+(weak scaling), receives its one-layer halo from the next rank with NCCL send/recv inside the
+timed region, and verifies the running quantisation factor against the all-gathered per-layer
+resolutions.  Finalize (union-find + trace ordering) is reported separately.
+
+--impl reference times the unmodified reference CPU tracker (oracle/_ref/ftk_ref_oracle, built from
+/root/reference by oracle/build_ref.sh) on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    # name: (workload label, dims, generator params x0+dir, field, distinct timesteps)
+    "c2": ("moving_extremum_2d_scalar_8192x8192x64", [8192, 8192], [4096.3, 4095.7, 0.1, 0.1], 64),
+    "c3": ("moving_extremum_3d_scalar_512x512x512x32", [512, 512, 512], [256.3, 255.7, 256.1, 0.1, 0.11, 0.1], 32),
+    "c2s": ("moving_extremum_2d_scalar_2048x2048x16", [2048, 2048], [1024.3, 1023.7, 0.1, 0.1], 16),
+}
+METRIC = "space_time_simplices_tested_per_sec"
+UNIT = "simplices/s"
+
+
+def tri(g, period):
+    """ping-pong index 0..period-1..0 so that the extremum keeps moving continuously"""
+    m = 2 * (period - 1)
+    g = g % m
+    return g if g < period else m - g
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """samples SM clock + throttle reasons of one GPU through NVML while the timed region runs"""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.01)
+
+    def result(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def physical_gpu_index(local):
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local])
+        except Exception:
+            return local
+    return local
+
+
+# ---------------------------------------------------------------------------------------------------
+def reference_arm(args, rank):
+    """the unmodified reference CPU tracker on a bounded sample of the workload (rank 0 only)"""
+    if rank != 0:
+        return
+    label, dims, params, _ = CONFIGS[args.config]
+    nd = len(dims)
+    binary = os.path.join(ROOT, "oracle", "_ref", "ftk_ref_oracle")
+    kind = "reference"
+    cores = os.cpu_count() or 1
+    # one step = the reference's tracker loop over 2 snapshots of a reduced extent of the same generator
+    sdims = [512, 512] if nd == 2 else [48, 48, 48]
+    sp = [d / 2 + 0.3 for d in sdims] + list(params[nd:])
+    ncore = 1
+    for d in sdims:
+        ncore *= d - 3
+    simplices = ncore * ((12 + 2) if nd == 2 else (60 + 6))   # advance (ordinal + interval) + final ordinal sweep
+    sample = f"{'x'.join(map(str, sdims))}x2 timesteps of the same generator per step, {cores} threads"
+
+    def one_step():
+        t0 = time.perf_counter()
+        if os.path.exists(binary):
+            cmd = [binary, "--nd", str(nd), "--nv", "1", "--dims"] + [str(d) for d in sdims] + \
+                  ["--nt", "2", "--gen", "moving_extremum", "--p"] + [repr(float(v)) for v in sp] + \
+                  ["--no-trace", "--quiet", "--nthreads", str(cores)]
+            out = subprocess.run(cmd, check=True, capture_output=True).stdout.decode().strip().splitlines()[-1]
+            st = json.loads(out)
+            t_path = st["t_push"] + st["t_sweep"]            # derive + sweep: the hot path
+            assert int(st["simplices"]) == simplices, (st["simplices"], simplices)
+        else:
+            from oracle import cp_oracle as O               # plain-C port of the reference path
+            snaps = [O.gen_moving_extremum(sdims, sp[:nd], sp[nd:], float(k)) for k in range(2)]
+            t1 = time.perf_counter()
+            O.track(snaps, sdims, field="scalar", trace=False)
+            t_path = time.perf_counter() - t1
+        return t_path, time.perf_counter() - t0
+
+    if not os.path.exists(binary):
+        kind = "port"
+    for _ in range(args.warmup):
+        one_step()
+    tot = wall = 0.0
+    for _ in range(args.steps):
+        a, b = one_step()
+        tot += a
+        wall += b
+    value = simplices * args.steps / tot
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * tot / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64+int64", "data": "synthetic",
+        "config": {"workload": label, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "wall_ms_per_step": 1e3 * wall / args.steps,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_sample(config):
+    """bounded sample (about 10-30 s of CPU work) of the reference CPU tracker on this box's host cores"""
+    label, dims, params, _ = CONFIGS[config]
+    nd = len(dims)
+    binary = os.path.join(ROOT, "oracle", "_ref", "ftk_ref_oracle")
+    cores = os.cpu_count() or 1
+    sdims = [1536, 1536] if nd == 2 else [96, 96, 96]
+    T = 3
+    sp = [d / 2 + 0.3 for d in sdims] + list(params[nd:])
+    sample = f"{'x'.join(map(str, sdims))}x{T} timesteps of the same generator, {cores} threads"
+    try:
+        if os.path.exists(binary):
+            cmd = [binary, "--nd", str(nd), "--nv", "1", "--dims"] + [str(d) for d in sdims] + \
+                  ["--nt", str(T), "--gen", "moving_extremum", "--p"] + [repr(float(v)) for v in sp] + \
+                  ["--no-trace", "--quiet", "--nthreads", str(cores)]
+            st = json.loads(subprocess.run(cmd, check=True, capture_output=True, timeout=600).stdout.decode().strip().splitlines()[-1])
+            return {"value": st["simplices"] / (st["t_push"] + st["t_sweep"]), "unit": UNIT, "cores": cores, "kind": "reference",
+                    "sample": sample, "t_derive_s": st["t_push"], "t_sweep_s": st["t_sweep"]}
+        from oracle import cp_oracle as O
+        snaps = [O.gen_moving_extremum(sdims, sp[:nd], sp[nd:], float(k)) for k in range(T)]
+        t0 = time.perf_counter()
+        O.track(snaps, sdims, field="scalar", trace=False)
+        dt = time.perf_counter() - t0
+        ncore = 1
+        for d in sdims:
+            ncore *= d - 3
+        n = ncore * ((12 * (T - 1) + 2) if nd == 2 else (60 * (T - 1) + 6))
+        return {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+    except Exception as e:  # the baseline is reported, never required
+        return {"value": None, "unit": UNIT, "cores": cores, "kind": "unavailable", "sample": f"failed: {e}"}
+
+
+# ---------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=252)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--e2e-steps", type=int, default=24)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        if args.steps == 252:
+            args.steps = 20   # default sized so the whole run ends within a few minutes
+        reference_arm(args, rank)
+        return
+    if args.warmup < 3:
+        args.warmup = 3
+
+    import numpy as np
+    import torch
+    import ftk_b200
+    from ftk_b200 import _lib
+    _lib.lib()   # fail loudly if the CUDA library is missing
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the engine has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+
+    label, dims, params, NL = CONFIGS[args.config]
+    nd = len(dims)
+    x0, dirv = params[:nd], params[nd:]
+    K, W = args.steps, args.warmup
+    ncore = 1
+    for d in dims:
+        ncore *= d - 3
+    per_step = ncore * (12 if nd == 2 else 60)
+    nvert = int(np.prod(dims))
+
+    def gen_layer(j, out=None):
+        """synthetic_moving_extremum at time j (ref: synthetic.hh:332-354), memory order ([D,]H,W)"""
+        axes = [torch.arange(d, dtype=torch.float64, device=dev) for d in dims]
+        e = [(axes[q] - (x0[q] + dirv[q] * float(j))) ** 2 for q in range(nd)]
+        if nd == 2:
+            s = e[0][None, :] + e[1][:, None]
+        else:
+            s = (e[0][None, None, :] + e[1][None, :, None]) + e[2][:, None, None]
+        if out is not None:
+            out.copy_(s)
+            return out
+        return s.contiguous()
+
+    layers = [gen_layer(j) for j in range(NL)]
+    g0 = rank * (W + K)
+
+    def make():
+        return ftk_b200.make_tracker(dims, field="scalar", device=local, start_timestep=g0)
+
+    # ---- device-resident measurement -------------------------------------------------------------
+    tr = make()
+    tr.push_scalar_field_snapshot(layers[tri(g0, NL)], borrow=True)
+    for i in range(W):
+        tr.push_scalar_field_snapshot(layers[tri(g0 + i + 1, NL)], borrow=True)
+        tr.advance_timestep()
+    halo = None
+    sampler = ClockSampler(physical_gpu_index(local))
+    torch.cuda.synchronize()
+    tr.synchronize()
+    if dist:
+        dist.barrier()
+    tr.reset_stats()
+    sampler.start()
+    tr.timer_start()
+    reqs = []
+    if dist:   # one-layer halo: the first layer of the next slab (ncclSend/ncclRecv over NVLink)
+        if rank > 0:
+            reqs.append(dist.isend(layers[tri(g0, NL)], rank - 1))
+        if rank < world - 1:
+            halo = torch.empty_like(layers[0])
+            reqs.append(dist.irecv(halo, rank + 1))
+    res_layers, factors = [], []
+    for i in range(W, W + K):
+        nxt = layers[tri(g0 + i + 1, NL)]
+        if halo is not None and i == W + K - 1:
+            for r in reqs:
+                r.wait()
+            torch.cuda.current_stream().synchronize()
+            nxt = halo
+        tr.push_scalar_field_snapshot(nxt, borrow=True)
+        tr.advance_timestep()
+        if dist:
+            res_layers.append(tr.stats()["resolution"])   # running minimum inside this slab
+            factors.append(tr.stats()["scaling_factor"])
+    redo = 0
+    if dist:
+        # running minimum of min non-zero |v| across slabs (the reference's factor is a running quantity):
+        # every rank swept optimistically with its own slab's minimum; verify against the global prefix
+        for r in reqs:
+            r.wait()
+        mine = torch.tensor([min(res_layers)], dtype=torch.float64, device=dev)
+        allres = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allres, mine)
+        prefix = min([float(a.item()) for a in allres[:rank]] + [float("inf")])
+        if prefix < float("inf"):
+            def nbits(res):
+                return max(8, min(int(math.ceil(math.log2(1.0 / res))), 21))
+            for rl, f in zip(res_layers, factors):
+                if float(1 << nbits(min(prefix, rl))) != f:
+                    redo += 1
+        # (moving-extremum slabs never differ; a differing slab is re-swept with resolution_init = prefix)
+    ms = tr.timer_stop()
+    sampler.stop_flag = True
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    st = tr.stats()
+    sampler.join(timeout=1.0)
+
+    # ---- finalize (not part of a step; reported separately) --------------------------------------
+    t0 = time.perf_counter()
+    pts = tr.get_discrete_critical_points()
+    if dist:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, pts.tobytes())
+        if rank == 0:
+            for b in gathered[1:]:
+                tr.import_points(np.frombuffer(b, dtype=_lib.POINT_DTYPE))
+    ntraj = None
+    if rank == 0:
+        tr.finalize()
+        ntraj = len(tr.get_trajectory_index())
+        npts_total = len(tr.get_discrete_critical_points())
+    finalize_ms = 1e3 * (time.perf_counter() - t0)
+    tr.close()
+
+    # ---- end-to-end measurement: host buffers through the same C-ABI calls ------------------------
+    E = max(1, min(args.e2e_steps, K))
+    NH = min(8, NL)
+    host = [torch.empty(tuple(reversed(dims)), dtype=torch.float64).pin_memory() for _ in range(NH)]
+    for j in range(NH):
+        host[j].copy_(layers[j])
+    torch.cuda.synchronize()
+    tr2 = make()
+    tr2.push_scalar_field_snapshot(host[0].numpy())
+    for i in range(2):
+        tr2.push_scalar_field_snapshot(host[tri(i + 1, NH)].numpy())
+        tr2.advance_timestep()
+    tr2.synchronize()
+    if dist:
+        dist.barrier()
+    tr2.reset_stats()
+    tr2.timer_start()
+    for i in range(2, 2 + E):
+        tr2.push_scalar_field_snapshot(host[tri(i + 1, NH)].numpy())   # H2D inside the timed region
+        tr2.advance_timestep()                                         # counters + resolution read back every step
+    ms2 = tr2.timer_stop()
+    if dist:
+        t = torch.tensor([ms2], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms2 = float(t.item())
+    st2 = tr2.stats()
+    tr2.close()
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        nscan = K
+        scan_ms = st["ms_scan"] / nscan
+        alg_bytes = 2 * nvert * nd * 8 + 72 * (st["points"] / max(K, 1))   # two fp64 vector layers read once + hit records
+        achieved = alg_bytes / (scan_ms * 1e-3) / 1e9
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "scan_traffic.json")) as f:
+                traffic = json.load(f).get(args.config)
+        except Exception:
+            pass
+        line = {
+            "metric": METRIC, "value": per_step * K * world / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64+int64", "data": "synthetic",
+            "config": {"workload": label, "simplices_per_step_per_gpu": per_step, "layers_resident": NL,
+                       "l2": "inputs larger than L2 (each fp64 layer >= 0.5 GB; no flush needed)",
+                       "parallelism": f"time-slab x{world}" if world > 1 else "single GPU",
+                       "step": "derive(gradient+resolution) + scan + per-simplex test of one timestep"},
+            "roofline": {"bound": "hbm", "kernel": "scan2d_kernel<true>" if nd == 2 else "scan3d_kernel<true>",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": scan_ms,
+                         "note": "rank 0; tensor cores unused by design (no dense contraction on this path)"},
+            "kernel_ms_per_step": {"derive": st["ms_derive"] / K, "scan": scan_ms, "test": st["ms_test"] / K},
+            "e2e": {"value": per_step * E * world / (ms2 * 1e-3), "unit": UNIT, "steps": E, "ms_per_step": ms2 / E,
+                    "h2d_bytes_per_step": st2["h2d_bytes"] / E, "d2h_bytes_per_step": st2["d2h_bytes"] / E,
+                    "api": "ftkb_push_snapshot(host) + ftkb_advance_timestep"},
+            "gpu_launches": int(st["kernel_launches"]),
+            "clocks": sampler.result(),
+            "finalize_ms": finalize_ms, "trajectories": ntraj, "punctured_simplices": int(npts_total),
+            "cells_refined_per_step": st["cells_refined"] / K, "slab_refactor_steps": redo,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline_sample(args.config)
+        print(json.dumps(line), flush=True)
+    if dist:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

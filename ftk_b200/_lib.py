@@ -53,7 +53,7 @@ EXPORTS = [
     "ftkb_push_synthetic", "ftkb_update_timestep", "ftkb_advance_timestep", "ftkb_finalize", "ftkb_current_timestep",
     "ftkb_last_layer_resolution", "ftkb_set_resolution", "ftkb_num_points", "ftkb_get_points", "ftkb_import_points",
     "ftkb_num_trajectories", "ftkb_get_trajectories", "ftkb_get_component_labels", "ftkb_get_degrees", "ftkb_get_stats",
-    "ftkb_reset_stats", "ftkb_synchronize", "ftkb_mesh_ntypes", "ftkb_mesh_unit_simplex", "ftkb_mesh_scope_type",
+    "ftkb_reset_stats", "ftkb_synchronize", "ftkb_timer_start", "ftkb_timer_stop", "ftkb_mesh_ntypes", "ftkb_mesh_unit_simplex", "ftkb_mesh_scope_type",
     "ftkb_mesh_sides", "ftkb_mesh_side_of",
 ]
 
@@ -82,8 +82,9 @@ def lib():
     L.ftkb_last_error.restype = C.c_char_p
     L.ftkb_push_snapshot.argtypes = [vp, vp, vp, vp, C.c_int]
     L.ftkb_push_synthetic.argtypes = [vp, C.c_int, C.POINTER(C.c_double), C.c_int, C.c_double]
-    for name in ("ftkb_update_timestep", "ftkb_advance_timestep", "ftkb_finalize", "ftkb_reset_stats", "ftkb_synchronize"):
+    for name in ("ftkb_update_timestep", "ftkb_advance_timestep", "ftkb_finalize", "ftkb_reset_stats", "ftkb_synchronize", "ftkb_timer_start"):
         getattr(L, name).argtypes = [vp]
+    L.ftkb_timer_stop.argtypes = [vp, C.POINTER(C.c_double)]
     L.ftkb_current_timestep.argtypes = [vp, C.POINTER(C.c_int32)]
     L.ftkb_last_layer_resolution.argtypes = [vp, C.POINTER(C.c_double)]
     L.ftkb_set_resolution.argtypes = [vp, C.c_double]

@@ -40,7 +40,7 @@ struct ftkb_ctx {
   uint64_t ncore = 0;
   int n_ord = 0, n_int = 0;
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // 0-2: sweep, 3: spare, 4-5: derive
+  cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // 0-2: sweep, 3: spare, 4-5: derive, 6-7: stopwatch
   bool derive_timed = false;
   std::string error;
 
@@ -379,7 +379,7 @@ extern "C" int ftkb_update_timestep(ftkb_ctx *c) {
     p.lb[j] = used ? c->cfg.lb[j] : 0;
     p.ub[j] = used ? c->cfg.ub[j] : 0;
     p.nc[j] = p.ub[j] - p.lb[j] + 1;
-    p.vmax[j] = used ? std::min(c->cfg.ub[j] + 1, c->cfg.dims[j] - 1) : 0;
+    p.vmax[j] = p.ub[j];   // vertices outside the domain belong to no valid simplex: keep them out of the cube ranges
   }
   p.t = c->current_timestep;
   p.has_next = has_next;
@@ -718,6 +718,24 @@ extern "C" int ftkb_synchronize(ftkb_ctx *c) {
   if (!c) return FTKB_ERR_INVALID;
   CK(cudaSetDevice(c->cfg.device));
   CK(cudaStreamSynchronize(c->stream));
+  return FTKB_OK;
+}
+
+extern "C" int ftkb_timer_start(ftkb_ctx *c) {
+  if (!c) return FTKB_ERR_INVALID;
+  CK(cudaSetDevice(c->cfg.device));
+  CK(cudaEventRecord(c->ev[6], c->stream));
+  return FTKB_OK;
+}
+
+extern "C" int ftkb_timer_stop(ftkb_ctx *c, double *ms) {
+  if (!c || !ms) return FTKB_ERR_INVALID;
+  CK(cudaSetDevice(c->cfg.device));
+  CK(cudaEventRecord(c->ev[7], c->stream));
+  CK(cudaEventSynchronize(c->ev[7]));
+  float f = 0;
+  CK(cudaEventElapsedTime(&f, c->ev[6], c->ev[7]));
+  *ms = f;
   return FTKB_OK;
 }
 

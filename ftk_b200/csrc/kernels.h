@@ -20,7 +20,7 @@ struct SweepParams {
   int32_t W, H, D;            // array dims (D = 1 in 2D)
   int32_t lb[3], ub[3];       // domain (inclusive)
   int32_t nc[3];              // corners per dimension = ub - lb + 1 (1 for the unused dim)
-  int32_t vmax[3];            // last loadable vertex per dim = min(ub + 1, dim - 1)
+  int32_t vmax[3];            // last vertex that enters a cube's value range per dim (= ub)
   int32_t t;                  // current timestep (time of layer 0)
   int32_t has_next;           // layer 1 present -> interval simplices are swept too
   int32_t nbits;              // factor = 2^nbits

@@ -299,6 +299,14 @@ class _RegularTracker:
         self._check(L.lib().ftkb_get_stats(self._h, C.byref(s)))
         return s.as_dict()
 
+    def timer_start(self):
+        self._check(L.lib().ftkb_timer_start(self._h))
+
+    def timer_stop(self):
+        ms = C.c_double()
+        self._check(L.lib().ftkb_timer_stop(self._h, C.byref(ms)))
+        return ms.value
+
     def reset_stats(self):
         self._check(L.lib().ftkb_reset_stats(self._h))
 

@@ -158,6 +158,10 @@ int ftkb_get_stats(ftkb_ctx *, ftkb_stats *out);
 int ftkb_reset_stats(ftkb_ctx *);
 /* block until all work queued on the context's stream is complete */
 int ftkb_synchronize(ftkb_ctx *);
+/* device-side stopwatch: CUDA events recorded on the context's stream (the stream every kernel of
+ * this library is launched on); stop synchronises and returns the elapsed milliseconds */
+int ftkb_timer_start(ftkb_ctx *);
+int ftkb_timer_stop(ftkb_ctx *, double *ms);
 
 /* implicit simplicial mesh tables (simplicial_regular_mesh.hh:620-831); no device needed.
  * nd_mesh = 3 (2D+t) or 4 (3D+t); scope: 0 all, 1 ordinal, 2 interval */

@@ -59,7 +59,7 @@ def _rand_series(rng, dims, T, nv, kind):
             for c in range(max(nv, 1)):
                 f = 0.0
                 for q, g in enumerate(grids):
-                    f = f + np.cos(0.7 * g + 0.3 * q + 0.11 * k + 1.3 * c) * (1.0 + 0.2 * q)
+                    f = f + np.cos((0.7 + 0.17 * c * (q + 1)) * g + 0.3 * q + 0.11 * k + 1.3 * c) * (1.0 + 0.2 * q)
                 comps.append(f + 0.05 * rng.standard_normal(size=f.shape))
             out.append(np.stack(comps, axis=-1) if nv > 1 else comps[0])
         return out
