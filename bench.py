@@ -375,10 +375,16 @@ def main():
 
     if rank == 0:
         peak, peak_src = measured_peaks()
-        nscan = K
+        nscan = max(int(st["scan_launches"]), 1)
         scan_ms = st["ms_scan"] / nscan
-        alg_bytes = 2 * nvert * nd * 8 + 72 * (st["points"] / max(K, 1))   # two fp64 vector layers read once + hit records
+        fused = nd == 2   # 2D scalar input: gradient fused into the scan, the vector field is never materialised
+        # algorithmic bytes of one scan launch (DESIGN.md "Kernels"): the two input layers read once each
+        # (fused: fp64 scalar layers, 8 B/vertex; otherwise fp64 vector layers, nd*8 B/vertex) + 72-B hit records
+        in_bytes = 2 * nvert * (1 if fused else nd) * 8
+        alg_bytes = in_bytes + 72 * (st["points"] / max(K, 1))
         achieved = alg_bytes / (scan_ms * 1e-3) / 1e9
+        # SURVEY.md 8(d) counts materialised vector layers (2.667 B/simplex in 2D, 0.8 in 3D) for the same launch
+        survey_bytes = (32.0 / 12.0 if nd == 2 else 48.0 / 60.0) * per_step
         traffic = None
         try:
             with open(os.path.join(ROOT, "profiles", "scan_traffic.json")) as f:
@@ -392,10 +398,14 @@ def main():
             "config": {"workload": label, "simplices_per_step_per_gpu": per_step, "layers_resident": NL,
                        "l2": "inputs larger than L2 (each fp64 layer >= 0.5 GB; no flush needed)",
                        "parallelism": f"time-slab x{world}" if world > 1 else "single GPU",
-                       "step": "derive(gradient+resolution) + scan + per-simplex test of one timestep"},
-            "roofline": {"bound": "hbm", "kernel": "scan2d_kernel<true>" if nd == 2 else "scan3d_kernel<true>",
+                       "step": "one advance_timestep: gradient + min|v| + exact sign early-out (fused scan kernel) + per-simplex test kernel" if nd == 2 else
+                               "one advance_timestep: derive(gradient+resolution) + scan + per-simplex test"},
+            "roofline": {"bound": "hbm", "kernel": "scan2d_fused_kernel<true,true>" if nd == 2 else "scan3d_kernel<true>",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": scan_ms,
+                         "launches_timed": nscan, "sweeps_repeated": int(st["sweeps_repeated"]),
+                         "survey_8d_equivalent": {"bytes_per_launch": survey_bytes, "gbs": survey_bytes / (scan_ms * 1e-3) / 1e9,
+                                                  "note": "SURVEY.md 8(d) assumes materialised fp64 vector layers; the fused kernel reads the scalar layers instead"},
                          "note": "rank 0; tensor cores unused by design (no dense contraction on this path)"},
             "kernel_ms_per_step": {"derive": st["ms_derive"] / K, "scan": scan_ms, "test": st["ms_test"] / K},
             "e2e": {"value": per_step * E * world / (ms2 * 1e-3), "unit": UNIT, "steps": E, "ms_per_step": ms2 / E,

@@ -35,6 +35,7 @@ class Stats(C.Structure):
         ("ms_derive", C.c_double), ("ms_scan", C.c_double), ("ms_test", C.c_double), ("ms_finalize_device", C.c_double),
         ("ms_finalize_host", C.c_double), ("last_ms_scan", C.c_double), ("last_ms_derive", C.c_double),
         ("scaling_factor", C.c_double), ("resolution", C.c_double),
+        ("scan_launches", C.c_uint64), ("sweeps_repeated", C.c_uint64),
     ]
 
     def as_dict(self):

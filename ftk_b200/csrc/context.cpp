@@ -29,6 +29,7 @@ struct Layer {
   double *S = nullptr, *V = nullptr, *J = nullptr;
   bool ownS = false, ownV = false, ownJ = false;
   int slot = 0;                  // resolution slot
+  bool res_pending = false;      // min non-zero |v| not computed yet: the fused scan produces it
 };
 
 }  // namespace
@@ -51,6 +52,7 @@ struct ftkb_ctx {
   double factor = 1.0;
   int nbits = 0;
   int next_slot = 0;
+  int sm_count = 148;
 
   // device scalars: [0..7] per-layer resolution bits, [8] worklist count, [9] point count, [10] unique count
   unsigned long long *d_scalars = nullptr;
@@ -164,6 +166,7 @@ extern "C" int ftkb_create(const ftkb_config *cfg, ftkb_ctx **out) {
 
   ftkb_ctx *c = new ftkb_ctx();
   c->cfg = *cfg;
+  c->sm_count = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : 148;
   c->n = n;
   c->nvert = (size_t)cfg->dims[0] * cfg->dims[1] * (n == 3 ? cfg->dims[2] : 1);
   c->ncore = 1;
@@ -224,6 +227,12 @@ static int derive_layer(ftkb_ctx *c, Layer &l) {
   launch_fill_u64(c->d_scalars + l.slot, init, c->stream);
   c->stats.kernel_launches++;
   bool fused = false;
+  if (!l.V && c->cfg.vector_source == FTKB_SOURCE_DERIVED && l.S && c->n == 2) {
+    // 2D: the gradient is never materialised; the fused scan derives it on the fly and computes this
+    // layer's resolution during the first sweep that reads it
+    l.res_pending = true;
+    return check_launch(c, "derive");
+  }
   if (!l.V && c->cfg.vector_source == FTKB_SOURCE_DERIVED && l.S) {
     int rc = take_buffer(c, c->freeV, c->nvert * c->n, &l.V);
     if (rc) return rc;
@@ -305,6 +314,8 @@ extern "C" int ftkb_push_synthetic(ftkb_ctx *c, int kind, const double *params, 
   return FTKB_OK;
 }
 
+static int resolve_pending(ftkb_ctx *c, Layer &l);
+
 static double slot_value(const ftkb_ctx *c, int slot) {
   double v;
   std::memcpy(&v, c->h_scalars + slot, 8);
@@ -315,8 +326,13 @@ extern "C" int ftkb_last_layer_resolution(ftkb_ctx *c, double *res) {
   if (!c || !res) return FTKB_ERR_INVALID;
   if (c->layers.empty()) return fail(c, FTKB_ERR_INVALID, "last_layer_resolution: no resident snapshot");
   CK(cudaSetDevice(c->cfg.device));
+  Layer &l = c->layers.back();
+  if (l.res_pending) {
+    const int rc = resolve_pending(c, l);
+    if (rc) return rc;
+  }
   CK(cudaStreamSynchronize(c->stream));
-  *res = c->layers.back().V ? slot_value(c, c->layers.back().slot) : DBL_MAX;
+  *res = (l.V || l.S) ? slot_value(c, l.slot) : DBL_MAX;
   return FTKB_OK;
 }
 
@@ -345,33 +361,14 @@ static int grow_points(ftkb_ctx *c, uint64_t need) {
   return FTKB_OK;
 }
 
-// ref: critical_point_tracker_{2d,3d}_regular::update_timestep (xl == NONE branch)
-extern "C" int ftkb_update_timestep(ftkb_ctx *c) {
-  if (!c) return FTKB_ERR_INVALID;
-  if (c->layers.empty()) return fail(c, FTKB_ERR_INVALID, "update_timestep: no snapshot has been pushed");
-  if (!c->layers[0].V) return fail(c, FTKB_ERR_INVALID, "update_timestep: the snapshot has no vector field");
-  if (c->current_timestep + 1 >= (1 << KEY_TIME_BITS)) return fail(c, FTKB_ERR_OVERFLOW, "update_timestep: timestep exceeds the element id range");
-  CK(cudaSetDevice(c->cfg.device));
-  CK(cudaStreamSynchronize(c->stream));   // per-layer resolutions are on the host now
-  // derive timing of the most recent gradient launch
-  if (c->derive_timed) {
-    float ms = 0;
-    if (cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]) == cudaSuccess) { c->stats.ms_derive += ms; c->stats.last_ms_derive = ms; }
-    else cudaGetLastError();
-    c->derive_timed = false;
-  }
-  // ref: critical_point_tracker.hh:850-864 (running minimum over every resident snapshot, every sweep)
-  for (const Layer &l : c->layers)
-    if (l.V) c->resolution = std::min(c->resolution, slot_value(c, l.slot));
-  int nbits = (int)std::ceil(std::log2(1.0 / c->resolution));
+static int nbits_of(double resolution) {
+  // ref: critical_point_tracker.hh:850-864
+  int nbits = (int)std::ceil(std::log2(1.0 / resolution));
   const int minbits = 8, maxbits = 21;
-  nbits = std::max(minbits, std::min(nbits, maxbits));
-  c->nbits = nbits;
-  c->factor = (double)(uint64_t)(1 << nbits);
+  return std::max(minbits, std::min(nbits, maxbits));
+}
 
-  const bool has_next = c->layers.size() >= 2;
-  if (has_next && !c->layers[1].V) return fail(c, FTKB_ERR_INVALID, "update_timestep: the next snapshot has no vector field");
-  SweepParams p{};
+static void fill_sweep_geometry(const ftkb_ctx *c, SweepParams &p) {
   p.nd = c->n;
   p.W = c->cfg.dims[0]; p.H = c->cfg.dims[1]; p.D = c->n == 3 ? c->cfg.dims[2] : 1;
   for (int j = 0; j < 3; j++) {
@@ -381,10 +378,76 @@ extern "C" int ftkb_update_timestep(ftkb_ctx *c) {
     p.nc[j] = p.ub[j] - p.lb[j] + 1;
     p.vmax[j] = p.ub[j];   // vertices outside the domain belong to no valid simplex: keep them out of the cube ranges
   }
+}
+
+// strips x row chunks of the fused 2D scan: about two equal waves of warps over the resident slots
+static void fused2d_decomposition(const ftkb_ctx *c, SweepParams &p) {
+  p.nsx = std::max(1, (p.W - 1 + 59) / 60);
+  const int64_t resident_warps = (int64_t)c->sm_count * 2 * 8;
+  int64_t nsy = (2 * resident_warps + p.nsx / 2) / p.nsx;
+  nsy = std::max<int64_t>(1, std::min<int64_t>(nsy, (p.H + 31) / 32));
+  p.rows = (int)((p.H + nsy - 1) / nsy);
+  p.nsy = (p.H + p.rows - 1) / p.rows;
+  p.nsz = 1;
+}
+
+static bool rows_aligned16(const ftkb_ctx *c, const double *a, const double *b) {
+  return (c->cfg.dims[0] % 2 == 0) && ((uintptr_t)a % 16 == 0) && (!b || (uintptr_t)b % 16 == 0);
+}
+
+// resolution of a layer whose vector field is derived on the fly, outside a sweep (time-slab exchange)
+static int resolve_pending(ftkb_ctx *c, Layer &l) {
+  SweepParams p{};
+  fill_sweep_geometry(c, p);
+  p.lb[1] = 1; p.ub[1] = 0;           // empty domain: gradient + resolution only, no cube is tested
+  p.fused = 1;
+  p.has_next = 0;
+  p.thrp_f = 1.f; p.thr2_f = 1.f; p.lim_f = 0.f;
+  p.L[0].S = l.S; p.L[1].S = l.S;
+  p.aligned16 = rows_aligned16(c, l.S, nullptr);
+  p.res_slot[0] = c->d_scalars + l.slot;
+  p.wl_count = c->d_scalars + ftkb_ctx::SLOT_WL;
+  p.wl = c->d_wl; p.wl_cap = 0;
+  fused2d_decomposition(c, p);
+  launch_scan(p, c->stream);
+  c->stats.kernel_launches++;
+  CK(cudaMemcpyAsync(c->h_scalars + l.slot, c->d_scalars + l.slot, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+  c->stats.d2h_bytes += 8;
+  l.res_pending = false;
+  return check_launch(c, "resolution (fused)");
+}
+
+// ref: critical_point_tracker_{2d,3d}_regular::update_timestep (xl == NONE branch)
+extern "C" int ftkb_update_timestep(ftkb_ctx *c) {
+  if (!c) return FTKB_ERR_INVALID;
+  if (c->layers.empty()) return fail(c, FTKB_ERR_INVALID, "update_timestep: no snapshot has been pushed");
+  const bool fused = c->n == 2 && !c->layers[0].V && c->layers[0].S && c->cfg.vector_source == FTKB_SOURCE_DERIVED;
+  if (!c->layers[0].V && !fused) return fail(c, FTKB_ERR_INVALID, "update_timestep: the snapshot has no vector field");
+  if (c->current_timestep + 1 >= (1 << KEY_TIME_BITS)) return fail(c, FTKB_ERR_OVERFLOW, "update_timestep: timestep exceeds the element id range");
+  CK(cudaSetDevice(c->cfg.device));
+  CK(cudaStreamSynchronize(c->stream));   // resolutions of layers derived at push time are on the host now
+  // derive timing of the most recent gradient launch
+  if (c->derive_timed) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]) == cudaSuccess) { c->stats.ms_derive += ms; c->stats.last_ms_derive = ms; }
+    else cudaGetLastError();
+    c->derive_timed = false;
+  }
+  const bool has_next = c->layers.size() >= 2;
+  if (has_next && !c->layers[1].V && !(fused && c->layers[1].S)) return fail(c, FTKB_ERR_INVALID, "update_timestep: the next snapshot has no vector field");
+  if (has_next && fused && c->layers[1].V) return fail(c, FTKB_ERR_INVALID, "update_timestep: resident snapshots mix derived and given vector fields");
+  // ref: critical_point_tracker.hh:850-864 (running minimum over every resident snapshot, every sweep).
+  // Layers whose resolution the fused scan still has to produce are left out here: the sweep runs with
+  // the factor known so far and is repeated if the completed minimum changes nbits (nbits only ever
+  // grows and is clamped to [8, 21], so at most 13 sweeps of a whole run are repeated).
+  for (const Layer &l : c->layers)
+    if ((l.V || l.S) && !l.res_pending) c->resolution = std::min(c->resolution, slot_value(c, l.slot));
+  int nbits = nbits_of(c->resolution);
+
+  SweepParams p{};
+  fill_sweep_geometry(c, p);
   p.t = c->current_timestep;
   p.has_next = has_next;
-  p.nbits = nbits;
-  p.factor = c->factor;
   p.no_filter = (c->n == 3 && !c->cfg.robust_detection);
   p.scalar_source = c->layers[0].S ? c->cfg.scalar_source : FTKB_SOURCE_NONE;
   p.jacobian_source = c->cfg.jacobian_source;
@@ -395,25 +458,39 @@ extern "C" int ftkb_update_timestep(ftkb_ctx *c) {
   p.compute_degrees = c->cfg.compute_degrees;
   p.use_type_filter = c->cfg.use_type_filter;
   p.type_filter = c->cfg.type_filter;
-  for (int k = 0; k < 2; k++) {
-    const Layer &l = c->layers[has_next ? k : 0];
-    p.L[k].S = l.S; p.L[k].V = l.V; p.L[k].J = l.J;
-  }
+  Layer *lay[2] = {&c->layers[0], &c->layers[has_next ? 1 : 0]};
+  for (int k = 0; k < 2; k++) { p.L[k].S = lay[k]->S; p.L[k].V = lay[k]->V; p.L[k].J = lay[k]->J; }
   if (has_next && p.scalar_source != FTKB_SOURCE_NONE && !c->layers[1].S) return fail(c, FTKB_ERR_INVALID, "update_timestep: the next snapshot has no scalar field");
-  p.nsx = (p.nc[0] + 30) / 31;
-  if (c->n == 2) {
-    p.rows = 64;
-    p.nsy = (p.nc[1] + p.rows - 1) / p.rows;
-    p.nsz = 1;
+  p.fused = fused;
+  if (fused) {
+    p.aligned16 = rows_aligned16(c, lay[0]->S, lay[1]->S);
+    fused2d_decomposition(c, p);
   } else {
-    p.rows = 32;
-    p.nsy = (p.nc[1] + 14) / 15;
-    p.nsz = (p.nc[2] + p.rows - 1) / p.rows;
+    p.nsx = (p.nc[0] + 30) / 31;
+    if (c->n == 2) {
+      p.rows = 64;
+      p.nsy = (p.nc[1] + p.rows - 1) / p.rows;
+      p.nsz = 1;
+    } else {
+      p.rows = 32;
+      p.nsy = (p.nc[1] + 14) / 15;
+      p.nsz = (p.nc[2] + p.rows - 1) / p.rows;
+    }
   }
   p.wl_count = c->d_scalars + ftkb_ctx::SLOT_WL;
   p.pt_count = c->d_scalars + ftkb_ctx::SLOT_PT;
 
-  for (int attempt = 0; attempt < 8; attempt++) {
+  for (int attempt = 0; attempt < 12; attempt++) {
+    p.nbits = nbits;
+    p.factor = (double)(uint64_t)(1 << nbits);
+    p.thrp_f = (float)((1.0 / p.factor) * (1.0 + 1.0 / 1048576.0));
+    p.thr2_f = (float)(2.0 / p.factor);
+    p.lim_f = (float)(0.999 * 4.5e18 / (p.factor * p.factor));
+    p.res_slot[0] = p.res_slot[1] = nullptr;
+    bool pending = false;
+    if (fused)
+      for (int k = 0; k < (has_next ? 2 : 1); k++)
+        if (lay[k]->res_pending) { p.res_slot[k] = c->d_scalars + lay[k]->slot; pending = true; }
     p.wl = c->d_wl; p.wl_cap = c->wl_cap;
     p.pts = c->d_pts; p.pt_cap = c->pt_cap;
     c->h_scalars[ftkb_ctx::SLOT_WL] = 0;
@@ -428,25 +505,47 @@ extern "C" int ftkb_update_timestep(ftkb_ctx *c) {
     int rc = check_launch(c, "sweep");
     if (rc) return rc;
     CK(cudaMemcpyAsync(c->h_scalars + ftkb_ctx::SLOT_WL, c->d_scalars + ftkb_ctx::SLOT_WL, 16, cudaMemcpyDeviceToHost, c->stream));
+    if (pending) {   // slots 0..7 hold the per-layer resolutions
+      CK(cudaMemcpyAsync(c->h_scalars, c->d_scalars, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+      c->stats.d2h_bytes += 64;
+    }
     CK(cudaStreamSynchronize(c->stream));
     c->stats.d2h_bytes += 16;
     float ms_scan = 0, ms_test = 0;
     CK(cudaEventElapsedTime(&ms_scan, c->ev[0], c->ev[1]));
     CK(cudaEventElapsedTime(&ms_test, c->ev[1], c->ev[2]));
     c->stats.ms_scan += ms_scan; c->stats.ms_test += ms_test; c->stats.last_ms_scan = ms_scan;
+    c->stats.scan_launches++;
+    if (pending) {
+      for (int k = 0; k < (has_next ? 2 : 1); k++)
+        if (lay[k]->res_pending) {
+          lay[k]->res_pending = false;
+          c->resolution = std::min(c->resolution, slot_value(c, lay[k]->slot));
+        }
+      const int nb = nbits_of(c->resolution);
+      if (nb != nbits) {           // the speculated factor was stale: repeat the sweep with the right one
+        nbits = nb;
+        c->stats.sweeps_repeated++;
+        continue;
+      }
+    }
     const uint64_t nwl = c->h_scalars[ftkb_ctx::SLOT_WL], npt = c->h_scalars[ftkb_ctx::SLOT_PT];
     if (nwl > c->wl_cap) {           // worklist overflow: grow and redo the step (inputs are still resident)
       cudaFree(c->d_wl);
       c->d_wl = nullptr;
       c->wl_cap = nwl + nwl / 8 + 1024;
       CK(cudaMalloc(&c->d_wl, sizeof(unsigned long long) * c->wl_cap));
+      c->stats.sweeps_repeated++;
       continue;
     }
     if (npt > c->pt_cap) {
       int rc2 = grow_points(c, npt);
       if (rc2) return rc2;
+      c->stats.sweeps_repeated++;
       continue;
     }
+    c->nbits = nbits;
+    c->factor = p.factor;
     c->stats.cells_scanned += c->ncore;
     c->stats.cells_refined += nwl;
     c->stats.simplices_tested += c->ncore * (uint64_t)(c->n_ord + (has_next ? c->n_int : 0));

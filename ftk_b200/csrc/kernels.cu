@@ -50,6 +50,8 @@ void upload_mesh_tables(const DeviceMeshTables &t2, const DeviceMeshTables &t3) 
 constexpr int KEY_ONE = 0x3FF00000;        // high word of 1.0
 constexpr int KEY_POISON_EXP = 0x43E00000; // |p| >= 2^63 (also Inf / NaN after scaling)
 
+__device__ __forceinline__ int clampi(int i, int n) { return i < 0 ? 0 : (i > n - 1 ? n - 1 : i); }
+
 struct KeyRange { int mn, mx; };
 
 __device__ __forceinline__ KeyRange neutral_range() { return KeyRange{INT_MAX, INT_MIN}; }
@@ -217,8 +219,206 @@ __global__ void __launch_bounds__(32 * SCAN3_BY) scan3d_kernel(const SweepParams
   }
 }
 
+// ---- 2D, scalar input: central-difference gradient (grad.hh:10-31) fused into the scan -------------
+// The vector field is never materialised.  A warp owns a strip of 64 vertex columns (two per lane,
+// one 16-byte load per lane, row and layer) and marches along y with a four-row register window
+// per layer (three rows of stencil + one row of prefetch; the row loop is unrolled by four so the
+// window rotates without register moves); x neighbours come from warp shuffles.
+//
+// Per row the kernel derives the fp64 gradient of both layers exactly as gradient2D does, rounds
+// each component to fp32 and keeps fp32 min/max ranges per component (merged over the two layers,
+// then x..x+1, then y..y+1).  The exclusion test on those ranges is conservative in every rounding:
+//   * sidedness uses thr+ = 2^-nbits (1 + 2^-20): approx(v) >= thr+  =>  v >= 2^-nbits  <=>
+//     trunc(v 2^nbits) >= 1 (scaling by a power of two is exact); values closer to the threshold
+//     than fp32 resolves simply leave the cube to the exact test;
+//   * the magnitude bound pads M and R by more than the fp32 rounding of their inputs;
+//   * vertices outside the tracker's domain or the array are NOT masked out of the ranges: a range
+//     that covers more vertices than the valid simplices use can only refine more cubes;
+//   * NaN components never enter a range (FMNMX drops them): a simplex with a NaN vertex is rejected
+//     by the reference before the predicate; +-Inf makes the bound infinite, so the cube is refined.
+// Survivors go to the same exact per-simplex test as in the vector-layer path, so results do not
+// depend on any of these approximations.
+//
+// By-product: min non-zero |v| (ndarray.hh:769-779) of the layers whose resolution is still unknown,
+// over the WHOLE array -- which is why strips cover the array and not only the tracker's domain.
+struct FRange { float mn, mx; };
+
+__device__ __forceinline__ FRange fmerge(FRange a, FRange b) { return FRange{fminf(a.mn, b.mn), fmaxf(a.mx, b.mx)}; }
+__device__ __forceinline__ FRange fshfl_down1(FRange a) {
+  return FRange{__shfl_down_sync(0xffffffffu, a.mn, 1), __shfl_down_sync(0xffffffffu, a.mx, 1)};
+}
+
+// thrp = 2^-nbits (1 + 2^-20), thr2 = 2^(1-nbits), limf = 0.999 * 4.5e18 / factor^2; all values in field units
+__device__ __forceinline__ bool cube_excluded2_f(FRange x, FRange y, float thrp, float thr2, float limf) {
+  const bool sided = x.mn >= thrp || x.mx <= -thrp || y.mn >= thrp || y.mx <= -thrp;
+  // |quantised| <= |v| factor; quantised spread <= spread factor + 1; fp32 rounding of the inputs is
+  // covered by the relative pads (2^-20 >> 2^-24)
+  const float Mx = __fmaf_rn(fmaxf(-x.mn, x.mx), 1.000001f, thr2), My = __fmaf_rn(fmaxf(-y.mn, y.mx), 1.000001f, thr2);
+  const float Rx = __fmaf_rn(Mx, 9.5367431640625e-7f, x.mx - x.mn) + thr2;
+  const float Ry = __fmaf_rn(My, 9.5367431640625e-7f, y.mx - y.mn) + thr2;
+  return sided && (__fmaf_rn(Mx, Ry, My * Rx) < limf);      // NaN / Inf compare false: the cube is refined
+}
+
+__device__ __forceinline__ void warp_res_commit(double m, unsigned long long *slot) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmin(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m < DBL_MAX) atomicMin(slot, (unsigned long long)__double_as_longlong(m));
+}
+
+__device__ __forceinline__ double nz_abs_d(double v) { const double a = fabs(v); return (v != 0.0 && a < DBL_MAX) ? a : DBL_MAX; }
+
+template <bool HAS_NEXT, bool ALIGNED, bool BORDER>
+__device__ __forceinline__ void fused2d_strip(const SweepParams &p, const int b, const int cy, const int lane) {
+  constexpr int NL = HAS_NEXT ? 2 : 1;
+  const int W = p.W, H = p.H;
+  const int e = b + 2 * lane, o = e + 1;     // this lane's two columns
+  const bool e_in = !BORDER || e < W, o_in = !BORDER || o < W, o1_in = !BORDER || o + 1 < W;
+  // the gradient needs both x neighbours inside the strip (or the array border, where the index clamps)
+  const bool e_valid = e_in && (lane > 0 || b == 0);
+  const bool o_valid = o_in && (lane < 31 || o == W - 1);
+  // corner columns b+1 .. b+60 belong to this strip (strip 0 also owns column 0)
+  const bool e_own = ((lane >= 1 && lane <= 30) || (lane == 0 && b == 0)) && e >= p.lb[0] && e <= p.ub[0];
+  const bool o_own = lane <= 29 && o >= p.lb[0] && o <= p.ub[0];
+  const int r0 = cy * p.rows;
+  const int r1 = min(r0 + p.rows - 1, H - 1);        // last corner row of the chunk
+  const int jl = r1 + 1;                             // last gradient row visited
+  const double cw = (double)(W - 1), ch = (double)(H - 1);
+  const float cwf = (float)(W - 1), chf = (float)(H - 1);
+  const float thrp = p.thrp_f, thr2 = p.thr2_f, limf = p.lim_f;
+  const bool want_res[2] = {p.res_slot[0] != nullptr, HAS_NEXT && p.res_slot[1] != nullptr};
+  double rmin[2] = {DBL_MAX, DBL_MAX};
+  float rminf[2] = {3.4028234e38f, 3.4028234e38f};   // fp32 candidate filter: slightly above rmin
+
+  // row pointers advance by one row per step; rows past the array's last row re-read it (index clamp)
+  const double *q[NL];
+  {
+    const size_t off = (size_t)W * (size_t)clampi(r0 - 1, H) + e;
+#pragma unroll
+    for (int L = 0; L < NL; L++) q[L] = (L == 0 ? p.L[0].S : p.L[1].S) + off;
+  }
+  int qrow = clampi(r0 - 1, H);
+  auto loadrow = [&](const int r, double (&dst)[NL][2]) {   // r is requested in increasing order, one row at a time
+    const int rc = clampi(r, H);
+    if (rc != qrow) {
+      qrow = rc;
+#pragma unroll
+      for (int L = 0; L < NL; L++) q[L] += W;
+    }
+#pragma unroll
+    for (int L = 0; L < NL; L++) {
+      if (ALIGNED) {
+        double2 t = make_double2(0.0, 0.0);
+        if (e_in) t = __ldg(reinterpret_cast<const double2 *>(q[L]));
+        dst[L][0] = t.x; dst[L][1] = t.y;
+      } else {
+        dst[L][0] = e_in ? __ldg(q[L]) : 0.0;
+        dst[L][1] = o_in ? __ldg(q[L] + 1) : 0.0;
+      }
+    }
+  };
+
+  // one gradient row j: stencil rows (m1, c0, p1); pf receives row j+2; prev/cur are the x-merged
+  // ranges of rows j-1 / j for the corner columns e and o: [corner column][component]
+  auto step = [&](const int j, double (&m1)[NL][2], double (&c0)[NL][2], double (&p1)[NL][2], double (&pf)[NL][2],
+                  FRange (&prev)[2][2], FRange (&cur)[2][2]) {
+    if (j + 1 <= jl) loadrow(j + 2, pf);
+    FRange ve[2], vo[2];   // per component, layers merged
+#pragma unroll
+    for (int L = 0; L < NL; L++) {
+      double left = __shfl_up_sync(0xffffffffu, c0[L][1], 1), right = __shfl_down_sync(0xffffffffu, c0[L][0], 1);
+      double mid_e = c0[L][1];
+      if (BORDER) {
+        if (e == 0) left = c0[L][0];
+        if (!o_in) mid_e = c0[L][0];
+        if (!o1_in) right = c0[L][1];
+      }
+      // exact fp64 differences; the scaling by (W-1), (H-1) is done in fp32 here (only the conservative
+      // ranges use it) and in fp64, as the reference does, wherever a value is needed exactly
+      const double dxe = mid_e - left, dxo = right - c0[L][0], dye = p1[L][0] - m1[L][0], dyo = p1[L][1] - m1[L][1];
+      const float fxe = __double2float_rn(dxe) * cwf, fxo = __double2float_rn(dxo) * cwf;
+      const float fye = __double2float_rn(dye) * chf, fyo = __double2float_rn(dyo) * chf;
+      if (want_res[L] && j < H) {
+        // candidates for a new minimum of the non-zero |v|: decided in fp32 against a filter that sits
+        // above the fp64 minimum; exact zeros (and fp32 underflow) also take the exact path
+        const float ae = e_valid ? fminf(fabsf(fxe), fabsf(fye)) : 3.4028234e38f;
+        const float ao = o_valid ? fminf(fabsf(fxo), fabsf(fyo)) : 3.4028234e38f;
+        if (fminf(ae, ao) < rminf[L]) {
+          double m = rmin[L];
+          if (e_valid) m = fmin(m, fmin(nz_abs_d(dxe * cw), nz_abs_d(dye * ch)));
+          if (o_valid) m = fmin(m, fmin(nz_abs_d(dxo * cw), nz_abs_d(dyo * ch)));
+          rmin[L] = m;
+          rminf[L] = m < 1e38 ? __double2float_ru(m) * 1.000001f : 3.4028234e38f;
+        }
+      }
+      if (L == 0) {
+        ve[0] = FRange{fxe, fxe}; ve[1] = FRange{fye, fye}; vo[0] = FRange{fxo, fxo}; vo[1] = FRange{fyo, fyo};
+      } else {
+        ve[0] = fmerge(ve[0], FRange{fxe, fxe}); ve[1] = fmerge(ve[1], FRange{fye, fye});
+        vo[0] = fmerge(vo[0], FRange{fxo, fxo}); vo[1] = fmerge(vo[1], FRange{fyo, fyo});
+      }
+    }
+    // x merge: corner column c covers vertex columns c and c+1
+#pragma unroll
+    for (int c = 0; c < 2; c++) {
+      cur[0][c] = fmerge(ve[c], vo[c]);
+      cur[1][c] = fmerge(vo[c], fshfl_down1(ve[c]));
+    }
+    if (j > r0) {
+      const int y = j - 1;
+      const bool yrow = y >= p.lb[1] && y <= p.ub[1];
+      const bool se = yrow && e_own && !cube_excluded2_f(fmerge(prev[0][0], cur[0][0]), fmerge(prev[0][1], cur[0][1]), thrp, thr2, limf);
+      const bool so = yrow && o_own && !cube_excluded2_f(fmerge(prev[1][0], cur[1][0]), fmerge(prev[1][1], cur[1][1]), thrp, thr2, limf);
+      if (__any_sync(0xffffffffu, se || so)) {
+        append_survivors(p, se, (u64)(e - p.lb[0]) + (u64)p.nc[0] * (u64)(y - p.lb[1]));
+        append_survivors(p, so, (u64)(o - p.lb[0]) + (u64)p.nc[0] * (u64)(y - p.lb[1]));
+      }
+    }
+  };
+
+  double s[4][NL][2];
+  FRange R[2][2][2];
+  loadrow(r0 - 1, s[0]);
+  loadrow(r0, s[1]);
+  loadrow(r0 + 1, s[2]);
+#pragma unroll
+  for (int a = 0; a < 2; a++)
+#pragma unroll
+    for (int c = 0; c < 2; c++) R[1][a][c] = FRange{0.f, 0.f};   // never read: the first row has no previous row
+  for (int j = r0; j <= jl; j += 4) {
+    step(j, s[0], s[1], s[2], s[3], R[1], R[0]);
+    if (j + 1 <= jl) step(j + 1, s[1], s[2], s[3], s[0], R[0], R[1]);
+    if (j + 2 <= jl) step(j + 2, s[2], s[3], s[0], s[1], R[1], R[0]);
+    if (j + 3 <= jl) step(j + 3, s[3], s[0], s[1], s[2], R[0], R[1]);
+  }
+#pragma unroll
+  for (int L = 0; L < NL; L++)
+    if (want_res[L]) warp_res_commit(rmin[L], p.res_slot[L]);
+}
+
+template <bool HAS_NEXT, bool ALIGNED>
+__global__ void __launch_bounds__(256, 2) scan2d_fused_kernel(const SweepParams p) {
+  const int lane = threadIdx.x & 31;
+  const i64 warp = (i64)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int sx = (int)(warp % p.nsx), cy = (int)(warp / p.nsx);
+  if (cy >= p.nsy) return;
+  const int b = sx * 60;                     // first loaded column of the strip (even)
+  if (b == 0 || b + 65 > p.W) fused2d_strip<HAS_NEXT, ALIGNED, true>(p, b, cy, lane);    // touches the array's left / right edge
+  else fused2d_strip<HAS_NEXT, ALIGNED, false>(p, b, cy, lane);
+}
+
 void launch_scan(const SweepParams &p, cudaStream_t s) {
-  if (p.nd == 2) {
+  if (p.nd == 2 && p.fused) {
+    const i64 warps = (i64)p.nsx * p.nsy;
+    const int wpb = 8;
+    const unsigned grid = (unsigned)((warps + wpb - 1) / wpb);
+    if (p.has_next) {
+      if (p.aligned16) scan2d_fused_kernel<true, true><<<grid, wpb * 32, 0, s>>>(p);
+      else scan2d_fused_kernel<true, false><<<grid, wpb * 32, 0, s>>>(p);
+    } else {
+      if (p.aligned16) scan2d_fused_kernel<false, true><<<grid, wpb * 32, 0, s>>>(p);
+      else scan2d_fused_kernel<false, false><<<grid, wpb * 32, 0, s>>>(p);
+    }
+  } else if (p.nd == 2) {
     const i64 warps = (i64)p.nsx * p.nsy;
     const int wpb = 8;
     const unsigned grid = (unsigned)((warps + wpb - 1) / wpb);
@@ -485,7 +685,6 @@ __device__ unsigned cp_type_3d(const double A[3][3], bool symmetric) {
 // =============================================================================================
 // 4. the fused per-simplex test
 // =============================================================================================
-__device__ __forceinline__ int clampi(int i, int n) { return i < 0 ? 0 : (i > n - 1 ? n - 1 : i); }
 
 // x86-64 cvttsd2si semantics: out-of-range and NaN give INT64_MIN (the reference's cast, compiled for x86-64)
 __device__ __forceinline__ i64 quantise(double v, double factor) {
@@ -497,9 +696,31 @@ __device__ __forceinline__ i64 quantise(double v, double factor) {
 // Jacobian at one vertex, derived on demand from the resident vector layer with the reference's
 // formulas (ref: include/ftk/ndarray/grad.hh:54-86, incl. the unscaled first term and the
 // non-symmetric variant's off-diagonals landing on array element 0 only).
-__device__ void jacobian2d_at(const SweepParams &p, const double *V, int i, int j, double G[2][2] /* G[a][b] = jacobian(a,b,i,j) */) {
+// component c of the vector field at vertex (i, j) (indices clamped to the array like the reference's
+// accessor lambdas): read from the resident vector layer, or -- when the layer only holds the scalar
+// field -- derived with gradient2D's formula (grad.hh:10-31)
+__device__ __forceinline__ double vec2_at(const SweepParams &p, const LayerPtrs &L, int c, int i, int j) {
   const int W = p.W, H = p.H;
-#define F2(c, ii, jj) __ldg(V + (c) + 2 * ((size_t)clampi(ii, W) + (size_t)W * clampi(jj, H)))
+  i = clampi(i, W); j = clampi(j, H);
+  if (L.V) return __ldg(L.V + c + 2 * ((size_t)i + (size_t)W * j));
+#define SF(ii, jj) __ldg(L.S + (size_t)clampi(ii, W) + (size_t)W * clampi(jj, H))
+  return c == 0 ? (SF(i + 1, j) - SF(i - 1, j)) * (W - 1) : (SF(i, j + 1) - SF(i, j - 1)) * (H - 1);
+#undef SF
+}
+
+// gradient3D (grad.hh:130-149): 1/2 central differences on the interior, zero on the array border
+__device__ __forceinline__ double vec3_at(const SweepParams &p, const LayerPtrs &L, int c, int i, int j, int k) {
+  const int W = p.W, H = p.H, D = p.D;
+  const size_t idx = (size_t)i + (size_t)W * ((size_t)j + (size_t)H * (size_t)k);
+  if (L.V) return __ldg(L.V + c + 3 * idx);
+  if (!(i >= 1 && i < W - 1 && j >= 1 && j < H - 1 && k >= 1 && k < D - 1)) return 0.0;
+  const size_t st = c == 0 ? 1 : (c == 1 ? (size_t)W : (size_t)W * H);
+  return 0.5 * (__ldg(L.S + idx + st) - __ldg(L.S + idx - st));
+}
+
+__device__ void jacobian2d_at(const SweepParams &p, const LayerPtrs &L, int i, int j, double G[2][2] /* G[a][b] = jacobian(a,b,i,j) */) {
+  const int W = p.W, H = p.H;
+#define F2(c, ii, jj) vec2_at(p, L, c, ii, jj)
   const double H00 = F2(0, i + 1, j) - F2(0, i - 1, j) * (W - 1), H11 = F2(1, i, j + 1) - F2(1, i, j - 1) * (H - 1);
   G[0][0] = H00;
   G[1][1] = H11;
@@ -517,13 +738,13 @@ __device__ void jacobian2d_at(const SweepParams &p, const double *V, int i, int 
 }
 
 // ref: grad.hh:175-212 (interior [2, D-3] only, zero elsewhere)
-__device__ void jacobian3d_at(const SweepParams &p, const double *V, int i, int j, int k, double G[3][3] /* G[c][d] = dV_c/dx_d * 0.5 form */) {
+__device__ void jacobian3d_at(const SweepParams &p, const LayerPtrs &L, int i, int j, int k, double G[3][3] /* G[c][d] = dV_c/dx_d * 0.5 form */) {
   const int W = p.W, H = p.H, D = p.D;
   const bool in = i >= 2 && i < W - 2 && j >= 2 && j < H - 2 && k >= 2 && k < D - 2;
 #pragma unroll
   for (int c = 0; c < 3; c++) {
     if (!in) { G[c][0] = G[c][1] = G[c][2] = 0.0; continue; }
-#define F3(c, ii, jj, kk) __ldg(V + (c) + 3 * ((size_t)(ii) + (size_t)W * ((size_t)(jj) + (size_t)H * (size_t)(kk))))
+#define F3(c, ii, jj, kk) vec3_at(p, L, c, ii, jj, kk)
     G[c][0] = 0.5 * (F3(c, i + 1, j, k) - F3(c, i - 1, j, k));
     G[c][1] = 0.5 * (F3(c, i, j + 1, k) - F3(c, i, j - 1, k));
     G[c][2] = 0.5 * (F3(c, i, j, k + 1) - F3(c, i, j, k - 1));
@@ -572,7 +793,10 @@ __device__ bool check_simplex(const SweepParams &p, const DeviceMeshTables &mt, 
 #pragma unroll
   for (int k = 0; k < NV; k++)
 #pragma unroll
-    for (int c = 0; c < ND; c++) v[k][c] = __ldg(L[k]->V + ND * vi[k] + c);
+    for (int c = 0; c < ND; c++) {
+      if constexpr (ND == 2) v[k][c] = vec2_at(p, *L[k], c, vt[k][0], vt[k][1]);
+      else v[k][c] = vec3_at(p, *L[k], c, vt[k][0], vt[k][1], vt[k][2]);
+    }
 
   double mu[NV];
   bool inside = false;
@@ -670,7 +894,7 @@ __device__ bool check_simplex(const SweepParams &p, const DeviceMeshTables &mt, 
               for (int b = 0; b < 2; b++) Js[k][a][b] = __ldg(L[k]->J + b + 2 * (a + 2 * vi[k]));
           } else {
             double G[2][2];
-            jacobian2d_at(p, L[k]->V, vt[k][0], vt[k][1], G);
+            jacobian2d_at(p, *L[k], vt[k][0], vt[k][1], G);
 #pragma unroll
             for (int a = 0; a < 2; a++)
 #pragma unroll
@@ -696,7 +920,7 @@ __device__ bool check_simplex(const SweepParams &p, const DeviceMeshTables &mt, 
           for (int b = 0; b < 3; b++) Js[k][a][b] = __ldg(L[k]->J + b + 3 * (a + 3 * vi[k]));
       } else if (p.jacobian_source == FTKB_SOURCE_DERIVED) {
         double G[3][3];
-        jacobian3d_at(p, L[k]->V, vt[k][0], vt[k][1], vt[k][2], G);
+        jacobian3d_at(p, *L[k], vt[k][0], vt[k][1], vt[k][2], G);
         for (int a = 0; a < 3; a++)
           for (int b = 0; b < 3; b++) Js[k][a][b] = G[b][a];
       } else {

@@ -31,6 +31,13 @@ struct SweepParams {
   int32_t robust, compute_degrees, use_type_filter;
   uint32_t type_filter;
   LayerPtrs L[2];
+  // fused mode: the vector field is derived from the scalar layers on the fly (L[].V == nullptr)
+  int32_t fused;
+  int32_t aligned16;          // rows of S start 16-byte aligned (W even, base aligned): vector loads allowed
+  float thrp_f;               // 2^-nbits (1 + 2^-20): approx(v) >= thrp_f  =>  |quantised v| >= 1
+  float thr2_f;               // 2^(1-nbits)
+  float lim_f;                // 0.999 * 4.5e18 / factor^2 (determinant magnitude bound, field units)
+  unsigned long long *res_slot[2];   // non-null: accumulate min non-zero |v| of that layer during the scan
   // scan decomposition
   int32_t nsx;                // x strips (31 corners each)
   int32_t nsy;                // 2D: row chunks; 3D: y tiles (BY-1 corners each)

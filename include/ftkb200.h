@@ -110,6 +110,8 @@ typedef struct ftkb_stats {
   double last_ms_derive;
   double scaling_factor;      /* current quantisation factor (1 << nbits) */
   double resolution;          /* running min non-zero |v| */
+  uint64_t scan_launches;     /* scan kernel launches (one per sweep, repeated sweeps included) */
+  uint64_t sweeps_repeated;   /* sweeps run again: stale quantisation factor or output buffers grown */
 } ftkb_stats;
 
 typedef struct ftkb_ctx ftkb_ctx;
