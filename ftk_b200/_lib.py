@@ -53,7 +53,7 @@ EXPORTS = [
     "ftkb_abi_version", "ftkb_device_count", "ftkb_create", "ftkb_destroy", "ftkb_last_error", "ftkb_push_snapshot",
     "ftkb_push_synthetic", "ftkb_update_timestep", "ftkb_advance_timestep", "ftkb_finalize", "ftkb_current_timestep",
     "ftkb_last_layer_resolution", "ftkb_set_resolution", "ftkb_num_points", "ftkb_get_points", "ftkb_import_points",
-    "ftkb_num_trajectories", "ftkb_get_trajectories", "ftkb_get_component_labels", "ftkb_get_degrees", "ftkb_get_stats",
+    "ftkb_num_trajectories", "ftkb_get_trajectories", "ftkb_get_component_labels", "ftkb_get_degrees", "ftkb_get_last_worklist", "ftkb_get_stats",
     "ftkb_reset_stats", "ftkb_synchronize", "ftkb_timer_start", "ftkb_timer_stop", "ftkb_mesh_ntypes", "ftkb_mesh_unit_simplex", "ftkb_mesh_scope_type",
     "ftkb_mesh_sides", "ftkb_mesh_side_of",
 ]
@@ -96,6 +96,7 @@ def lib():
     L.ftkb_get_trajectories.argtypes = [vp, vp, vp, vp]
     L.ftkb_get_component_labels.argtypes = [vp, vp]
     L.ftkb_get_degrees.argtypes = [vp, vp]
+    L.ftkb_get_last_worklist.argtypes = [vp, vp, C.c_uint64, u64p]
     L.ftkb_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.ftkb_mesh_ntypes.argtypes = [C.c_int, C.c_int, C.c_int]
     L.ftkb_mesh_unit_simplex.argtypes = [C.c_int, C.c_int, C.c_int, vp]

@@ -12,6 +12,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <string>
@@ -53,6 +54,7 @@ struct ftkb_ctx {
   int nbits = 0;
   int next_slot = 0;
   int sm_count = 148;
+  bool use_bulk = true;          // FTKB_SCAN=ldg selects the register-staged fused scan (A/B measurements)
 
   // device scalars: [0..7] per-layer resolution bits, [8] worklist count, [9] point count, [10] unique count
   unsigned long long *d_scalars = nullptr;
@@ -60,7 +62,7 @@ struct ftkb_ctx {
   static constexpr int SLOT_WL = 8, SLOT_PT = 9, SLOT_UQ = 10, NSLOTS = 16;
 
   unsigned long long *d_wl = nullptr;
-  uint64_t wl_cap = 0;
+  uint64_t wl_cap = 0, last_wl = 0;
   ftkb_point *d_pts = nullptr;
   uint64_t pt_cap = 0, npts = 0;
 
@@ -167,6 +169,7 @@ extern "C" int ftkb_create(const ftkb_config *cfg, ftkb_ctx **out) {
   ftkb_ctx *c = new ftkb_ctx();
   c->cfg = *cfg;
   c->sm_count = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : 148;
+  if (const char *e = std::getenv("FTKB_SCAN")) c->use_bulk = std::string(e) != "ldg";
   c->n = n;
   c->nvert = (size_t)cfg->dims[0] * cfg->dims[1] * (n == 3 ? cfg->dims[2] : 1);
   c->ncore = 1;
@@ -199,6 +202,7 @@ extern "C" int ftkb_create(const ftkb_config *cfg, ftkb_ctx **out) {
   fill_device_tables(3, &t2);
   fill_device_tables(4, &t3);
   upload_mesh_tables(t2, t3);
+  init_kernel_attributes();
   if ((e = cudaStreamSynchronize(c->stream)) != cudaSuccess) return bail(std::string("init: ") + cudaGetErrorString(e), FTKB_ERR_CUDA);
   *out = c;
   return FTKB_OK;
@@ -382,8 +386,10 @@ static void fill_sweep_geometry(const ftkb_ctx *c, SweepParams &p) {
 
 // strips x row chunks of the fused 2D scan: about two equal waves of warps over the resident slots
 static void fused2d_decomposition(const ftkb_ctx *c, SweepParams &p) {
-  p.nsx = std::max(1, (p.W - 1 + 59) / 60);
-  const int64_t resident_warps = (int64_t)c->sm_count * 2 * 8;
+  // bulk-async kernel: 62 corner columns per strip, 3 blocks of 8 warps per SM; register kernel: 60, 2 blocks
+  p.bulk = p.aligned16 && c->use_bulk;
+  p.nsx = p.bulk ? std::max(1, (p.W + 61) / 62) : std::max(1, (p.W - 1 + 59) / 60);
+  const int64_t resident_warps = (int64_t)c->sm_count * (p.bulk ? 3 : 2) * 8;
   int64_t nsy = (2 * resident_warps + p.nsx / 2) / p.nsx;
   nsy = std::max<int64_t>(1, std::min<int64_t>(nsy, (p.H + 31) / 32));
   p.rows = (int)((p.H + nsy - 1) / nsy);
@@ -548,6 +554,7 @@ extern "C" int ftkb_update_timestep(ftkb_ctx *c) {
     c->factor = p.factor;
     c->stats.cells_scanned += c->ncore;
     c->stats.cells_refined += nwl;
+    c->last_wl = nwl;
     c->stats.simplices_tested += c->ncore * (uint64_t)(c->n_ord + (has_next ? c->n_int : 0));
     if (npt != c->npts) { c->sorted = false; c->traced = false; }
     c->npts = npt;
@@ -794,6 +801,17 @@ extern "C" int ftkb_get_degrees(ftkb_ctx *c, int32_t *deg) {
   if (!c || !deg) return FTKB_ERR_INVALID;
   if (!c->traced) return fail(c, FTKB_ERR_INVALID, "get_degrees: call finalize first");
   if (!c->deg.empty()) std::memcpy(deg, c->deg.data(), 4 * c->deg.size());
+  return FTKB_OK;
+}
+
+extern "C" int ftkb_get_last_worklist(ftkb_ctx *c, uint64_t *out, uint64_t cap, uint64_t *n) {
+  if (!c || !n || (!out && cap)) return FTKB_ERR_INVALID;
+  CK(cudaSetDevice(c->cfg.device));
+  CK(cudaStreamSynchronize(c->stream));
+  const uint64_t have = std::min<uint64_t>(c->last_wl, c->wl_cap);
+  *n = have;
+  const uint64_t m = std::min(have, cap);
+  if (m) CK(cudaMemcpy(out, c->d_wl, sizeof(uint64_t) * m, cudaMemcpyDeviceToHost));
   return FTKB_OK;
 }
 

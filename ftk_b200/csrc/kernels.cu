@@ -406,8 +406,240 @@ __global__ void __launch_bounds__(256, 2) scan2d_fused_kernel(const SweepParams 
   else fused2d_strip<HAS_NEXT, ALIGNED, false>(p, b, cy, lane);
 }
 
+// ---- 2D, scalar input, bulk-async staging ----------------------------------------------------------
+// Same algorithm as scan2d_fused_kernel, but the scalar rows are staged in shared memory by the
+// async copy engine (cp.async.bulk global -> shared, completion on an mbarrier: UBLKCP in SASS)
+// instead of through registers.  Every warp owns a private ring of FB_NST row stages (both layers),
+// so there is no block-level synchronisation at all: lane 0 issues the copy of row j + FB_NST as
+// soon as row j is dead, every lane waits on the stage's mbarrier before reading it.  This keeps
+// FB_NST-2 rows (x 2 layers x 544 B) per warp in flight independent of register pressure, which is
+// what an HBM-bound stencil needs; x neighbours are read from the staged row, so no shuffles either.
+// Requires 16-byte aligned rows (W even, aligned base); otherwise scan2d_fused_kernel runs.
+constexpr int FB_NST = 6;          // ring stages (rows) per warp; the row loop is unrolled by 6 = lcm(3-row window, 2 range buffers, ring)
+constexpr int FB_SEG = 68;         // doubles per staged row segment: columns c0-2 .. c0+65
+constexpr int FB_STRIDE = 62;      // corner columns owned per strip (c0 .. c0+61)
+constexpr int FB_WARPS = 8;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *q) { return (uint32_t)__cvta_generic_to_shared(q); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  } while (!done);
+}
+
+template <int K> struct IC { static constexpr int value = K; };
+
+template <bool HAS_NEXT, bool BORDER>
+__device__ __forceinline__ void fused2d_bulk_strip(const SweepParams &p, const int c0, const int cy, const int lane,
+                                                   double *ring /* [FB_NST][NL][FB_SEG] */, const uint32_t bar0 /* FB_NST barriers */) {
+  constexpr int NL = HAS_NEXT ? 2 : 1;
+  const int W = p.W, H = p.H;
+  const int e = c0 + 2 * lane, o = e + 1;
+  const bool e_in = !BORDER || e < W, o_in = !BORDER || o < W, o1_in = !BORDER || o + 1 < W;
+  const bool e_own = lane <= 30 && e >= p.lb[0] && e <= p.ub[0];
+  const bool o_own = lane <= 30 && o >= p.lb[0] && o <= p.ub[0];
+  const bool e_last = BORDER && e == p.ub[0], o_last = BORDER && o == p.ub[0];   // the vertex column right of the domain's last one is not part of any valid simplex
+  const int r0 = cy * p.rows;
+  const int r1 = min(r0 + p.rows - 1, H - 1);        // last corner row of the chunk
+  const int jl = r1 + 1;                             // last gradient row visited
+  const int nrows = jl - r0 + 3;                     // staged rows r0-1 .. jl+1 (ring index 0 .. nrows-1)
+  const double cw = (double)(W - 1), ch = (double)(H - 1);
+  const float cwf = (float)(W - 1), chf = (float)(H - 1);
+  const float thrp = p.thrp_f, thr2 = p.thr2_f, limf = p.lim_f;
+  const bool want_res[2] = {p.res_slot[0] != nullptr, HAS_NEXT && p.res_slot[1] != nullptr};
+  double rmin[2] = {DBL_MAX, DBL_MAX};
+  float rminf[2] = {3.4028234e38f, 3.4028234e38f};
+
+  // producer side (lane 0): copy the clipped segment of one row of every layer into its stage
+  const int col_lo = max(c0 - 2, 0), col_hi = min(c0 + FB_SEG - 2, W);
+  const uint32_t seg_bytes = (uint32_t)(col_hi - col_lo) * 8u;
+  const uint32_t ring_u32 = smem_u32(ring) + (uint32_t)(col_lo - (c0 - 2)) * 8u;
+  auto issue = [&](const int rr) {     // rr: ring row index, array row r0 - 1 + rr (clamped like the reference's accessor)
+    if (lane == 0) {
+      const int st = rr % FB_NST;
+      const uint32_t bar = bar0 + 8u * (uint32_t)st;
+      const size_t off = (size_t)W * (size_t)clampi(r0 - 1 + rr, H) + (size_t)col_lo;
+      mbar_expect_tx(bar, seg_bytes * NL);
+#pragma unroll
+      for (int L = 0; L < NL; L++)
+        bulk_g2s(ring_u32 + (uint32_t)((st * NL + L) * FB_SEG) * 8u, (L == 0 ? p.L[0].S : p.L[1].S) + off, seg_bytes, bar);
+    }
+  };
+  const double *lane_base = ring + 2 * lane;    // [1]: column e-1, [2..3]: e, o, [4]: o+1
+  auto centre = [&](const int st, double (&dst)[NL][2]) {
+#pragma unroll
+    for (int L = 0; L < NL; L++) {
+      const double2 t = *reinterpret_cast<const double2 *>(lane_base + (st * NL + L) * FB_SEG + 2);
+      dst[L][0] = t.x; dst[L][1] = t.y;
+    }
+  };
+
+  for (int rr = 0; rr < FB_NST && rr < nrows; rr++) issue(rr);
+  double win[3][NL][2];
+  FRange R[2][2][2];
+  mbar_wait(bar0, 0);
+  centre(0, win[0]);
+  mbar_wait(bar0 + 8, 0);
+  centre(1, win[1]);
+  __syncwarp();
+  if (FB_NST < nrows) issue(FB_NST);             // row 0 is dead: only its centre columns are ever needed
+#pragma unroll
+  for (int a = 0; a < 2; a++)
+#pragma unroll
+    for (int c = 0; c < 2; c++) R[1][a][c] = FRange{0.f, 0.f};   // never read: the first row has no previous row
+
+  // gradient row j = r0 + 6 i + K; ring index of row j is 1 + 6 i + K
+  auto step = [&](auto KC, const int j, const int i) {
+    constexpr int K = decltype(KC)::value;
+    constexpr int ST_J = (1 + K) % FB_NST, ST_P = (2 + K) % FB_NST;
+    double (&m1)[NL][2] = win[K % 3];
+    double (&c0v)[NL][2] = win[(K + 1) % 3];
+    double (&p1)[NL][2] = win[(K + 2) % 3];
+    FRange (&prev)[2][2] = R[(K + 1) & 1];
+    FRange (&cur)[2][2] = R[K & 1];
+    mbar_wait(bar0 + 8u * ST_P, (uint32_t)((i + (2 + K >= FB_NST ? 1 : 0)) & 1));
+    centre(ST_P, p1);
+    FRange ve[2], vo[2];   // per component, layers merged
+#pragma unroll
+    for (int L = 0; L < NL; L++) {
+      const double *rowj = lane_base + (ST_J * NL + L) * FB_SEG;
+      double left = rowj[1], right = rowj[4];
+      double mid_e = c0v[L][1];
+      if (BORDER) {
+        if (e == 0) left = c0v[L][0];
+        if (!o_in) mid_e = c0v[L][0];
+        if (!o1_in) right = c0v[L][1];
+      }
+      const double dxe = mid_e - left, dxo = right - c0v[L][0], dye = p1[L][0] - m1[L][0], dyo = p1[L][1] - m1[L][1];
+      const float fxe = __double2float_rn(dxe) * cwf, fxo = __double2float_rn(dxo) * cwf;
+      const float fye = __double2float_rn(dye) * chf, fyo = __double2float_rn(dyo) * chf;
+      if (want_res[L] && j < H) {
+        const float ae = e_in ? fminf(fabsf(fxe), fabsf(fye)) : 3.4028234e38f;
+        const float ao = o_in ? fminf(fabsf(fxo), fabsf(fyo)) : 3.4028234e38f;
+        if (fminf(ae, ao) < rminf[L]) {
+          double m = rmin[L];
+          if (e_in) m = fmin(m, fmin(nz_abs_d(dxe * cw), nz_abs_d(dye * ch)));
+          if (o_in) m = fmin(m, fmin(nz_abs_d(dxo * cw), nz_abs_d(dyo * ch)));
+          rmin[L] = m;
+          rminf[L] = m < 1e38 ? __double2float_ru(m) * 1.000001f : 3.4028234e38f;
+        }
+      }
+      if (L == 0) {
+        ve[0] = FRange{fxe, fxe}; ve[1] = FRange{fye, fye}; vo[0] = FRange{fxo, fxo}; vo[1] = FRange{fyo, fyo};
+      } else {
+        ve[0] = fmerge(ve[0], FRange{fxe, fxe}); ve[1] = fmerge(ve[1], FRange{fye, fye});
+        vo[0] = fmerge(vo[0], FRange{fxo, fxo}); vo[1] = fmerge(vo[1], FRange{fyo, fyo});
+      }
+    }
+    // x merge: corner column c covers vertex columns c and c+1 (only c when c is the domain's last column)
+#pragma unroll
+    for (int c = 0; c < 2; c++) {
+      const FRange nx = fshfl_down1(ve[c]);
+      cur[0][c] = e_last ? ve[c] : fmerge(ve[c], vo[c]);
+      cur[1][c] = o_last ? vo[c] : fmerge(vo[c], nx);
+    }
+    if (j == p.ub[1] + 1) {   // rows above the domain's last row take no part in its cubes
+      const float qn = __int_as_float(0x7fc00000);
+#pragma unroll
+      for (int a = 0; a < 2; a++)
+#pragma unroll
+        for (int c = 0; c < 2; c++) cur[a][c] = FRange{qn, qn};
+    }
+    if (j > r0) {
+      const int y = j - 1;
+      const bool yrow = y >= p.lb[1] && y <= p.ub[1];
+      bool se, so;
+      bool slow = BORDER;
+      if (!BORDER) {
+        // both cubes of the lane at once: if their union passes, each of them does
+        const FRange ux = fmerge(fmerge(prev[0][0], prev[1][0]), fmerge(cur[0][0], cur[1][0]));
+        const FRange uy = fmerge(fmerge(prev[0][1], prev[1][1]), fmerge(cur[0][1], cur[1][1]));
+        const bool ok = cube_excluded2_f(ux, uy, thrp, thr2, limf) || !(yrow && (e_own || o_own));
+        slow = __any_sync(0xffffffffu, !ok);
+        se = so = false;
+      }
+      if (slow) {
+        se = yrow && e_own && !cube_excluded2_f(fmerge(prev[0][0], cur[0][0]), fmerge(prev[0][1], cur[0][1]), thrp, thr2, limf);
+        so = yrow && o_own && !cube_excluded2_f(fmerge(prev[1][0], cur[1][0]), fmerge(prev[1][1], cur[1][1]), thrp, thr2, limf);
+        if (__any_sync(0xffffffffu, se || so)) {
+          append_survivors(p, se, (u64)(e - p.lb[0]) + (u64)p.nc[0] * (u64)(y - p.lb[1]));
+          append_survivors(p, so, (u64)(o - p.lb[0]) + (u64)p.nc[0] * (u64)(y - p.lb[1]));
+        }
+      }
+    }
+    // row j is dead now (its centre went into the window one step ago, its x neighbours were read above):
+    // refill its stage with row j + FB_NST
+    __syncwarp();
+    const int rr_next = 1 + FB_NST * i + K + FB_NST;
+    if (rr_next < nrows) issue(rr_next);
+  };
+
+  for (int j = r0, i = 0; j <= jl; j += FB_NST, i++) {
+    step(IC<0>{}, j, i);
+    if (j + 1 <= jl) step(IC<1>{}, j + 1, i);
+    if (j + 2 <= jl) step(IC<2>{}, j + 2, i);
+    if (j + 3 <= jl) step(IC<3>{}, j + 3, i);
+    if (j + 4 <= jl) step(IC<4>{}, j + 4, i);
+    if (j + 5 <= jl) step(IC<5>{}, j + 5, i);
+  }
+#pragma unroll
+  for (int L = 0; L < NL; L++)
+    if (want_res[L]) warp_res_commit(rmin[L], p.res_slot[L]);
+}
+
+template <bool HAS_NEXT>
+__global__ void __launch_bounds__(FB_WARPS * 32, 3) scan2d_bulk_kernel(const SweepParams p) {
+  constexpr int NL = HAS_NEXT ? 2 : 1;
+  extern __shared__ __align__(128) unsigned char fb_smem[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  double *ring = reinterpret_cast<double *>(fb_smem) + (size_t)wib * (FB_NST * NL * FB_SEG);
+  unsigned long long *bars = reinterpret_cast<unsigned long long *>(fb_smem + (size_t)FB_WARPS * FB_NST * NL * FB_SEG * 8) + wib * FB_NST;
+  const uint32_t bar0 = smem_u32(bars);
+  if (lane == 0) {
+#pragma unroll
+    for (int q = 0; q < FB_NST; q++) mbar_init(bar0 + 8u * q, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncwarp();
+  const i64 warp = (i64)blockIdx.x * FB_WARPS + wib;
+  const int sx = (int)(warp % p.nsx), cy = (int)(warp / p.nsx);
+  if (cy >= p.nsy) return;
+  const int c0 = sx * FB_STRIDE;
+  // strips that touch the array's left / right edge or hold the domain's last column take the masked path
+  const bool border = c0 == 0 || c0 + FB_SEG - 2 > p.W || (p.ub[0] >= c0 - 1 && p.ub[0] <= c0 + 63);
+  if (border) fused2d_bulk_strip<HAS_NEXT, true>(p, c0, cy, lane, ring, bar0);
+  else fused2d_bulk_strip<HAS_NEXT, false>(p, c0, cy, lane, ring, bar0);
+}
+
+static size_t bulk_smem_bytes(bool has_next) {
+  return (size_t)FB_WARPS * FB_NST * (has_next ? 2 : 1) * FB_SEG * 8 + (size_t)FB_WARPS * FB_NST * 8;
+}
+
+void init_kernel_attributes() {
+  cudaFuncSetAttribute(scan2d_bulk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bulk_smem_bytes(true));
+  cudaFuncSetAttribute(scan2d_bulk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bulk_smem_bytes(false));
+}
+
 void launch_scan(const SweepParams &p, cudaStream_t s) {
-  if (p.nd == 2 && p.fused) {
+  if (p.nd == 2 && p.fused && p.aligned16 && p.bulk) {
+    const i64 warps = (i64)p.nsx * p.nsy;
+    const unsigned grid = (unsigned)((warps + FB_WARPS - 1) / FB_WARPS);
+    if (p.has_next) scan2d_bulk_kernel<true><<<grid, FB_WARPS * 32, bulk_smem_bytes(true), s>>>(p);
+    else scan2d_bulk_kernel<false><<<grid, FB_WARPS * 32, bulk_smem_bytes(false), s>>>(p);
+  } else if (p.nd == 2 && p.fused) {
     const i64 warps = (i64)p.nsx * p.nsy;
     const int wpb = 8;
     const unsigned grid = (unsigned)((warps + wpb - 1) / wpb);

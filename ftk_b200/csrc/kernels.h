@@ -34,6 +34,7 @@ struct SweepParams {
   // fused mode: the vector field is derived from the scalar layers on the fly (L[].V == nullptr)
   int32_t fused;
   int32_t aligned16;          // rows of S start 16-byte aligned (W even, base aligned): vector loads allowed
+  int32_t bulk;               // stage rows with cp.async.bulk + mbarrier (needs aligned16)
   float thrp_f;               // 2^-nbits (1 + 2^-20): approx(v) >= thrp_f  =>  |quantised v| >= 1
   float thr2_f;               // 2^(1-nbits)
   float lim_f;                // 0.999 * 4.5e18 / factor^2 (determinant magnitude bound, field units)
@@ -54,6 +55,7 @@ struct SweepParams {
 };
 
 void upload_mesh_tables(const DeviceMeshTables &t2, const DeviceMeshTables &t3);
+void init_kernel_attributes();   // opt-in shared memory sizes; once per device
 
 void launch_scan(const SweepParams &p, cudaStream_t s);
 // thread-per-(surviving cube, type) exact test; grid sized for `expected` cubes, grid-stride otherwise

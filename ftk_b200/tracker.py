@@ -294,6 +294,14 @@ class _RegularTracker:
         self._check(L.lib().ftkb_get_degrees(self._h, out.ctypes.data))
         return out[:n]
 
+    def get_last_worklist(self):
+        """diagnostic: linear corner indices (x fastest over the domain) the last scan left for the exact test"""
+        n = C.c_uint64()
+        self._check(L.lib().ftkb_get_last_worklist(self._h, None, 0, C.byref(n)))
+        out = np.zeros(max(n.value, 1), np.uint64)
+        self._check(L.lib().ftkb_get_last_worklist(self._h, out.ctypes.data, n.value, C.byref(n)))
+        return out[:n.value]
+
     def stats(self):
         s = L.Stats()
         self._check(L.lib().ftkb_get_stats(self._h, C.byref(s)))

@@ -156,6 +156,10 @@ int ftkb_get_trajectories(ftkb_ctx *, uint64_t *offsets /* n+1 */, uint64_t *poi
 int ftkb_get_component_labels(ftkb_ctx *, uint64_t *labels);
 int ftkb_get_degrees(ftkb_ctx *, int32_t *deg);
 
+/* diagnostic: the cubes (linear corner index over the domain, x fastest) that the most recent sweep's
+ * scan kernel left for the exact test; *n receives the count, at most cap entries are copied */
+int ftkb_get_last_worklist(ftkb_ctx *, uint64_t *out, uint64_t cap, uint64_t *n);
+
 int ftkb_get_stats(ftkb_ctx *, ftkb_stats *out);
 int ftkb_reset_stats(ftkb_ctx *);
 /* block until all work queued on the context's stream is complete */
