@@ -54,7 +54,7 @@ struct ftkb_ctx {
   int nbits = 0;
   int next_slot = 0;
   int sm_count = 148;
-  bool use_bulk = true;          // FTKB_SCAN=ldg selects the register-staged fused scan (A/B measurements)
+  int scan_mode = 2;             // FTKB_SCAN=ldg|warp|tile selects the fused scan's staging (A/B measurements); default tile
 
   // device scalars: [0..7] per-layer resolution bits, [8] worklist count, [9] point count, [10] unique count
   unsigned long long *d_scalars = nullptr;
@@ -169,7 +169,7 @@ extern "C" int ftkb_create(const ftkb_config *cfg, ftkb_ctx **out) {
   ftkb_ctx *c = new ftkb_ctx();
   c->cfg = *cfg;
   c->sm_count = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : 148;
-  if (const char *e = std::getenv("FTKB_SCAN")) c->use_bulk = std::string(e) != "ldg";
+  if (const char *e = std::getenv("FTKB_SCAN")) c->scan_mode = std::string(e) == "ldg" ? 0 : (std::string(e) == "warp" ? 1 : 2);
   c->n = n;
   c->nvert = (size_t)cfg->dims[0] * cfg->dims[1] * (n == 3 ? cfg->dims[2] : 1);
   c->ncore = 1;
@@ -387,10 +387,16 @@ static void fill_sweep_geometry(const ftkb_ctx *c, SweepParams &p) {
 // strips x row chunks of the fused 2D scan: about two equal waves of warps over the resident slots
 static void fused2d_decomposition(const ftkb_ctx *c, SweepParams &p) {
   // bulk-async kernel: 62 corner columns per strip, 3 blocks of 8 warps per SM; register kernel: 60, 2 blocks
-  p.bulk = p.aligned16 && c->use_bulk;
-  p.nsx = p.bulk ? std::max(1, (p.W + 61) / 62) : std::max(1, (p.W - 1 + 59) / 60);
-  const int64_t resident_warps = (int64_t)c->sm_count * (p.bulk ? 3 : 2) * 8;
-  int64_t nsy = (2 * resident_warps + p.nsx / 2) / p.nsx;
+  p.bulk = p.aligned16 ? c->scan_mode : 0;
+  int64_t nsy;
+  if (p.bulk == 2) {      // CTA tiles of 7 x 62 corner columns, 3 CTAs per SM: about two waves of CTAs
+    p.nsx = std::max(1, (p.W + 7 * 62 - 1) / (7 * 62));
+    nsy = (2 * (int64_t)c->sm_count * 3 + p.nsx / 2) / p.nsx;
+  } else {
+    p.nsx = p.bulk ? std::max(1, (p.W + 61) / 62) : std::max(1, (p.W - 1 + 59) / 60);
+    const int64_t resident_warps = (int64_t)c->sm_count * (p.bulk ? 3 : 2) * 8;
+    nsy = (2 * resident_warps + p.nsx / 2) / p.nsx;
+  }
   nsy = std::max<int64_t>(1, std::min<int64_t>(nsy, (p.H + 31) / 32));
   p.rows = (int)((p.H + nsy - 1) / nsy);
   p.nsy = (p.H + p.rows - 1) / p.rows;

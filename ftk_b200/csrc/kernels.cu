@@ -441,10 +441,64 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 
 template <int K> struct IC { static constexpr int value = K; };
 
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
+// exact update of the running min non-zero |v| with the four gradient values of one step (v = d * c in
+// fp64, as gradient2D computes them); m keeps the signed value with the smallest non-zero magnitude
+__device__ __forceinline__ void res_update4(double &m, float &mf, bool e_in, bool o_in, double dxe, double dye, double dxo, double dyo, double cw, double ch) {
+  const double vxe = dxe * cw, vye = dye * ch, vxo = dxo * cw, vyo = dyo * ch;
+  if (e_in) {
+    if (vxe != 0.0 && fabs(vxe) < fabs(m)) m = vxe;     // NaN / Inf never compare below
+    if (vye != 0.0 && fabs(vye) < fabs(m)) m = vye;
+  }
+  if (o_in) {
+    if (vxo != 0.0 && fabs(vxo) < fabs(m)) m = vxo;
+    if (vyo != 0.0 && fabs(vyo) < fabs(m)) m = vyo;
+  }
+  mf = fabs(m) < 1e38 ? __double2float_ru(fabs(m)) * 1.000001f : 3.4028234e38f;
+}
+
+// cold path of the bulk scan: per-corner tests of one lane's two cubes + worklist append.
+// top: the row above belongs to no cube of this corner row (domain's last row): ranges of the lower row only
+struct SlowArgs {          // what the cold path needs of SweepParams (passed by value: no stack copy of the whole block)
+  float thrp, thr2, limf;
+  int lb0, lb1, nc0;
+  unsigned long long *wl_count, *wl;
+  unsigned long long wl_cap;
+};
+
+__device__ __noinline__ void bulk_slow_tests(const SlowArgs a, bool top, bool e_act, bool o_act, int e, int y,
+                                             FRange pex, FRange pey, FRange pox, FRange poy, FRange cex, FRange cey, FRange cox, FRange coy) {
+  if (top) { cex = pex; cey = pey; cox = pox; coy = poy; }
+  const bool se = e_act && !cube_excluded2_f(fmerge(pex, cex), fmerge(pey, cey), a.thrp, a.thr2, a.limf);
+  const bool so = o_act && !cube_excluded2_f(fmerge(pox, cox), fmerge(poy, coy), a.thrp, a.thr2, a.limf);
+  if (!__any_sync(0xffffffffu, se || so)) return;
+  const int lane = threadIdx.x & 31;
+  const u64 lin = (u64)(e - a.lb0) + (u64)a.nc0 * (u64)(y - a.lb1);
+#pragma unroll
+  for (int q = 0; q < 2; q++) {
+    const bool surv = q ? so : se;
+    const unsigned b = __ballot_sync(0xffffffffu, surv);
+    if (b == 0) continue;
+    u64 base = 0;
+    if (lane == __ffs(b) - 1) base = atomicAdd(a.wl_count, (u64)__popc(b));
+    base = __shfl_sync(0xffffffffu, base, __ffs(b) - 1);
+    if (surv) {
+      const u64 i = base + __popc(b & ((1u << lane) - 1));
+      if (i < a.wl_cap) a.wl[i] = lin + q;
+    }
+  }
+}
+
 template <bool HAS_NEXT, bool BORDER>
 __device__ __forceinline__ void fused2d_bulk_strip(const SweepParams &p, const int c0, const int cy, const int lane,
                                                    double *ring /* [FB_NST][NL][FB_SEG] */, const uint32_t bar0 /* FB_NST barriers */) {
   constexpr int NL = HAS_NEXT ? 2 : 1;
+  constexpr uint32_t STAGE_BYTES = NL * FB_SEG * 8;
   const int W = p.W, H = p.H;
   const int e = c0 + 2 * lane, o = e + 1;
   const bool e_in = !BORDER || e < W, o_in = !BORDER || o < W, o1_in = !BORDER || o + 1 < W;
@@ -455,27 +509,39 @@ __device__ __forceinline__ void fused2d_bulk_strip(const SweepParams &p, const i
   const int r1 = min(r0 + p.rows - 1, H - 1);        // last corner row of the chunk
   const int jl = r1 + 1;                             // last gradient row visited
   const int nrows = jl - r0 + 3;                     // staged rows r0-1 .. jl+1 (ring index 0 .. nrows-1)
-  const double cw = (double)(W - 1), ch = (double)(H - 1);
+  const int ytop = p.ub[1];
   const float cwf = (float)(W - 1), chf = (float)(H - 1);
   const float thrp = p.thrp_f, thr2 = p.thr2_f, limf = p.lim_f;
   const bool want_res[2] = {p.res_slot[0] != nullptr, HAS_NEXT && p.res_slot[1] != nullptr};
   double rmin[2] = {DBL_MAX, DBL_MAX};
   float rminf[2] = {3.4028234e38f, 3.4028234e38f};
 
-  // producer side (lane 0): copy the clipped segment of one row of every layer into its stage
+  // producer side (one elected lane; every operand is warp-uniform): copy the clipped segment of one row
+  // of every layer into its stage.  The source pointers walk the rows r0-1, r0, ... with the array's
+  // index clamp (rows below 0 / above H-1 re-read the border row).
   const int col_lo = max(c0 - 2, 0), col_hi = min(c0 + FB_SEG - 2, W);
   const uint32_t seg_bytes = (uint32_t)(col_hi - col_lo) * 8u;
   const uint32_t ring_u32 = smem_u32(ring) + (uint32_t)(col_lo - (c0 - 2)) * 8u;
-  auto issue = [&](const int rr) {     // rr: ring row index, array row r0 - 1 + rr (clamped like the reference's accessor)
-    if (lane == 0) {
-      const int st = rr % FB_NST;
-      const uint32_t bar = bar0 + 8u * (uint32_t)st;
-      const size_t off = (size_t)W * (size_t)clampi(r0 - 1 + rr, H) + (size_t)col_lo;
+  const size_t row_bytes = (size_t)W * 8;
+  const char *src[NL];
+  int src_row = clampi(r0 - 1, H);
+#pragma unroll
+  for (int L = 0; L < NL; L++)
+    src[L] = reinterpret_cast<const char *>((L == 0 ? p.L[0].S : p.L[1].S) + (size_t)W * (size_t)src_row + (size_t)col_lo);
+  int rr_issue = 0;                                  // next ring row to issue; rows are issued strictly in order
+  auto issue = [&](const uint32_t stage_off, const uint32_t bar) {
+    const int want = clampi(r0 - 1 + rr_issue, H);
+    if (want != src_row) {
+      src_row = want;
+#pragma unroll
+      for (int L = 0; L < NL; L++) src[L] += row_bytes;
+    }
+    if (elect_one()) {
       mbar_expect_tx(bar, seg_bytes * NL);
 #pragma unroll
-      for (int L = 0; L < NL; L++)
-        bulk_g2s(ring_u32 + (uint32_t)((st * NL + L) * FB_SEG) * 8u, (L == 0 ? p.L[0].S : p.L[1].S) + off, seg_bytes, bar);
+      for (int L = 0; L < NL; L++) bulk_g2s(ring_u32 + stage_off + (uint32_t)(L * FB_SEG) * 8u, src[L], seg_bytes, bar);
     }
+    rr_issue++;
   };
   const double *lane_base = ring + 2 * lane;    // [1]: column e-1, [2..3]: e, o, [4]: o+1
   auto centre = [&](const int st, double (&dst)[NL][2]) {
@@ -486,7 +552,9 @@ __device__ __forceinline__ void fused2d_bulk_strip(const SweepParams &p, const i
     }
   };
 
-  for (int rr = 0; rr < FB_NST && rr < nrows; rr++) issue(rr);
+#pragma unroll
+  for (int q = 0; q < FB_NST; q++)
+    if (q < nrows) issue(q * STAGE_BYTES, bar0 + 8u * q);
   double win[3][NL][2];
   FRange R[2][2][2];
   mbar_wait(bar0, 0);
@@ -494,7 +562,7 @@ __device__ __forceinline__ void fused2d_bulk_strip(const SweepParams &p, const i
   mbar_wait(bar0 + 8, 0);
   centre(1, win[1]);
   __syncwarp();
-  if (FB_NST < nrows) issue(FB_NST);             // row 0 is dead: only its centre columns are ever needed
+  if (rr_issue < nrows) issue(0, bar0);             // row 0 is dead: only its centre columns are ever needed
 #pragma unroll
   for (int a = 0; a < 2; a++)
 #pragma unroll
@@ -522,19 +590,17 @@ __device__ __forceinline__ void fused2d_bulk_strip(const SweepParams &p, const i
         if (!o_in) mid_e = c0v[L][0];
         if (!o1_in) right = c0v[L][1];
       }
+      // exact fp64 differences; the scaling by (W-1), (H-1) is done in fp32 here (only the conservative
+      // ranges use it) and in fp64, as the reference does, wherever a value is needed exactly
       const double dxe = mid_e - left, dxo = right - c0v[L][0], dye = p1[L][0] - m1[L][0], dyo = p1[L][1] - m1[L][1];
       const float fxe = __double2float_rn(dxe) * cwf, fxo = __double2float_rn(dxo) * cwf;
       const float fye = __double2float_rn(dye) * chf, fyo = __double2float_rn(dyo) * chf;
       if (want_res[L] && j < H) {
-        const float ae = e_in ? fminf(fabsf(fxe), fabsf(fye)) : 3.4028234e38f;
-        const float ao = o_in ? fminf(fabsf(fxo), fabsf(fyo)) : 3.4028234e38f;
-        if (fminf(ae, ao) < rminf[L]) {
-          double m = rmin[L];
-          if (e_in) m = fmin(m, fmin(nz_abs_d(dxe * cw), nz_abs_d(dye * ch)));
-          if (o_in) m = fmin(m, fmin(nz_abs_d(dxo * cw), nz_abs_d(dyo * ch)));
-          rmin[L] = m;
-          rminf[L] = m < 1e38 ? __double2float_ru(m) * 1.000001f : 3.4028234e38f;
-        }
+        // candidates for a new minimum of the non-zero |v|: decided in fp32 against a filter that sits
+        // above the fp64 minimum; exact zeros (and fp32 underflow) also take the exact path
+        float a = fminf(fminf(fabsf(fxe), fabsf(fye)), fminf(fabsf(fxo), fabsf(fyo)));
+        if (BORDER) a = fminf(e_in ? fminf(fabsf(fxe), fabsf(fye)) : 3.4028234e38f, o_in ? fminf(fabsf(fxo), fabsf(fyo)) : 3.4028234e38f);
+        if (a < rminf[L]) res_update4(rmin[L], rminf[L], e_in, o_in, dxe, dye, dxo, dyo, (double)(W - 1), (double)(H - 1));
       }
       if (L == 0) {
         ve[0] = FRange{fxe, fxe}; ve[1] = FRange{fye, fye}; vo[0] = FRange{fxo, fxo}; vo[1] = FRange{fyo, fyo};
@@ -550,40 +616,25 @@ __device__ __forceinline__ void fused2d_bulk_strip(const SweepParams &p, const i
       cur[0][c] = e_last ? ve[c] : fmerge(ve[c], vo[c]);
       cur[1][c] = o_last ? vo[c] : fmerge(vo[c], nx);
     }
-    if (j == p.ub[1] + 1) {   // rows above the domain's last row take no part in its cubes
-      const float qn = __int_as_float(0x7fc00000);
-#pragma unroll
-      for (int a = 0; a < 2; a++)
-#pragma unroll
-        for (int c = 0; c < 2; c++) cur[a][c] = FRange{qn, qn};
-    }
     if (j > r0) {
       const int y = j - 1;
-      const bool yrow = y >= p.lb[1] && y <= p.ub[1];
-      bool se, so;
-      bool slow = BORDER;
-      if (!BORDER) {
+      const bool yrow = y >= p.lb[1] && y <= ytop;
+      bool slow = BORDER || y == ytop;      // masked columns / the domain's last row: per-corner path
+      if (!BORDER && y != ytop) {
         // both cubes of the lane at once: if their union passes, each of them does
         const FRange ux = fmerge(fmerge(prev[0][0], prev[1][0]), fmerge(cur[0][0], cur[1][0]));
         const FRange uy = fmerge(fmerge(prev[0][1], prev[1][1]), fmerge(cur[0][1], cur[1][1]));
         const bool ok = cube_excluded2_f(ux, uy, thrp, thr2, limf) || !(yrow && (e_own || o_own));
         slow = __any_sync(0xffffffffu, !ok);
-        se = so = false;
       }
-      if (slow) {
-        se = yrow && e_own && !cube_excluded2_f(fmerge(prev[0][0], cur[0][0]), fmerge(prev[0][1], cur[0][1]), thrp, thr2, limf);
-        so = yrow && o_own && !cube_excluded2_f(fmerge(prev[1][0], cur[1][0]), fmerge(prev[1][1], cur[1][1]), thrp, thr2, limf);
-        if (__any_sync(0xffffffffu, se || so)) {
-          append_survivors(p, se, (u64)(e - p.lb[0]) + (u64)p.nc[0] * (u64)(y - p.lb[1]));
-          append_survivors(p, so, (u64)(o - p.lb[0]) + (u64)p.nc[0] * (u64)(y - p.lb[1]));
-        }
-      }
+      if (slow && yrow)
+        bulk_slow_tests(SlowArgs{thrp, thr2, limf, p.lb[0], p.lb[1], p.nc[0], p.wl_count, p.wl, p.wl_cap}, y == ytop, e_own, o_own, e, y,
+                        prev[0][0], prev[0][1], prev[1][0], prev[1][1], cur[0][0], cur[0][1], cur[1][0], cur[1][1]);
     }
     // row j is dead now (its centre went into the window one step ago, its x neighbours were read above):
-    // refill its stage with row j + FB_NST
+    // refill its stage with the next row in line (ring row 1 + 6 i + K + FB_NST)
     __syncwarp();
-    const int rr_next = 1 + FB_NST * i + K + FB_NST;
-    if (rr_next < nrows) issue(rr_next);
+    if (rr_issue < nrows) issue(ST_J * STAGE_BYTES, bar0 + 8u * ST_J);
   };
 
   for (int j = r0, i = 0; j <= jl; j += FB_NST, i++) {
@@ -596,14 +647,15 @@ __device__ __forceinline__ void fused2d_bulk_strip(const SweepParams &p, const i
   }
 #pragma unroll
   for (int L = 0; L < NL; L++)
-    if (want_res[L]) warp_res_commit(rmin[L], p.res_slot[L]);
+    if (want_res[L]) warp_res_commit(fabs(rmin[L]), p.res_slot[L]);
 }
 
 template <bool HAS_NEXT>
 __global__ void __launch_bounds__(FB_WARPS * 32, 3) scan2d_bulk_kernel(const SweepParams p) {
   constexpr int NL = HAS_NEXT ? 2 : 1;
   extern __shared__ __align__(128) unsigned char fb_smem[];
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int wib = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);     // warp-uniform by construction
   double *ring = reinterpret_cast<double *>(fb_smem) + (size_t)wib * (FB_NST * NL * FB_SEG);
   unsigned long long *bars = reinterpret_cast<unsigned long long *>(fb_smem + (size_t)FB_WARPS * FB_NST * NL * FB_SEG * 8) + wib * FB_NST;
   const uint32_t bar0 = smem_u32(bars);
@@ -624,17 +676,212 @@ __global__ void __launch_bounds__(FB_WARPS * 32, 3) scan2d_bulk_kernel(const Swe
   else fused2d_bulk_strip<HAS_NEXT, false>(p, c0, cy, lane, ring, bar0);
 }
 
+// ---- 2D, scalar input, CTA-wide staging with a producer warp -----------------------------------------
+// The per-warp rings above issue two 544-byte copies per warp and row, and ncu shows the copy engine's
+// request queue (stall_mio on UBLKCP, long scoreboard behind it) as the limiter.  Here a CTA of seven
+// consumer warps + one producer warp shares ONE ring of row stages that spans all seven strips
+// (7 x 62 corner columns + halo = 442 doubles = 3.5 KB per row and layer): 7x fewer, 7x larger bulk
+// copies, no column overlap between the strips of a CTA, and no copy-issue instructions at all in the
+// consumer warps.  Classic full/empty mbarrier pipeline: the producer's elected lane waits for a
+// stage's `empty` barrier (one arrival per consumer warp), arms `full` with the byte count and issues
+// the copies; consumers wait on `full`, read, and arrive on `empty` when a row is dead for them.
+constexpr int TL_CW = 7;                               // consumer warps per CTA
+constexpr int TL_SEG = TL_CW * FB_STRIDE + 8;          // staged doubles per row: columns C0-2 .. C0+439
+constexpr int TL_NST = FB_NST;
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+template <bool HAS_NEXT, bool BORDER>
+__device__ __forceinline__ void fused2d_tile_strip(const SweepParams &p, const int c0, const int r0, const int r1, const int lane,
+                                                   const double *tile /* this warp's column 0 = c0-2 */, const uint32_t full0, const uint32_t empty0) {
+  constexpr int NL = HAS_NEXT ? 2 : 1;
+  const int W = p.W, H = p.H;
+  const int e = c0 + 2 * lane, o = e + 1;
+  const bool e_in = !BORDER || e < W, o_in = !BORDER || o < W, o1_in = !BORDER || o + 1 < W;
+  const bool e_own = lane <= 30 && e >= p.lb[0] && e <= p.ub[0];
+  const bool o_own = lane <= 30 && o >= p.lb[0] && o <= p.ub[0];
+  const bool e_last = BORDER && e == p.ub[0], o_last = BORDER && o == p.ub[0];
+  const int jl = r1 + 1;                             // last gradient row visited
+  const int ytop = p.ub[1];
+  const float cwf = (float)(W - 1), chf = (float)(H - 1);
+  const float thrp = p.thrp_f, thr2 = p.thr2_f, limf = p.lim_f;
+  const bool want_res[2] = {p.res_slot[0] != nullptr, HAS_NEXT && p.res_slot[1] != nullptr};
+  double rmin[2] = {DBL_MAX, DBL_MAX};
+  float rminf[2] = {3.4028234e38f, 3.4028234e38f};
+
+  const double *lane_base = tile + 2 * lane;    // [1]: column e-1, [2..3]: e, o, [4]: o+1
+  auto centre = [&](const int st, double (&dst)[NL][2]) {
+#pragma unroll
+    for (int L = 0; L < NL; L++) {
+      const double2 t = *reinterpret_cast<const double2 *>(lane_base + (st * NL + L) * TL_SEG + 2);
+      dst[L][0] = t.x; dst[L][1] = t.y;
+    }
+  };
+  auto release = [&](const int st) {     // this warp is done with the stage
+    __syncwarp();
+    if (elect_one()) mbar_arrive(empty0 + 8u * st);
+  };
+
+  double win[3][NL][2];
+  FRange R[2][2][2];
+  mbar_wait(full0, 0);
+  centre(0, win[0]);
+  mbar_wait(full0 + 8, 0);
+  centre(1, win[1]);
+  release(0);                                      // row r0-1: only its centre columns are ever needed
+#pragma unroll
+  for (int a = 0; a < 2; a++)
+#pragma unroll
+    for (int c = 0; c < 2; c++) R[1][a][c] = FRange{0.f, 0.f};   // never read: the first row has no previous row
+
+  // gradient row j = r0 + 6 i + K; ring index of row j is 1 + 6 i + K
+  auto step = [&](auto KC, const int j, const int i) {
+    constexpr int K = decltype(KC)::value;
+    constexpr int ST_J = (1 + K) % TL_NST, ST_P = (2 + K) % TL_NST;
+    double (&m1)[NL][2] = win[K % 3];
+    double (&c0v)[NL][2] = win[(K + 1) % 3];
+    double (&p1)[NL][2] = win[(K + 2) % 3];
+    FRange (&prev)[2][2] = R[(K + 1) & 1];
+    FRange (&cur)[2][2] = R[K & 1];
+    mbar_wait(full0 + 8u * ST_P, (uint32_t)((i + (2 + K >= TL_NST ? 1 : 0)) & 1));
+    centre(ST_P, p1);
+    FRange ve[2], vo[2];   // per component, layers merged
+#pragma unroll
+    for (int L = 0; L < NL; L++) {
+      const double *rowj = lane_base + (ST_J * NL + L) * TL_SEG;
+      double left = rowj[1], right = rowj[4];
+      double mid_e = c0v[L][1];
+      if (BORDER) {
+        if (e == 0) left = c0v[L][0];
+        if (!o_in) mid_e = c0v[L][0];
+        if (!o1_in) right = c0v[L][1];
+      }
+      const double dxe = mid_e - left, dxo = right - c0v[L][0], dye = p1[L][0] - m1[L][0], dyo = p1[L][1] - m1[L][1];
+      const float fxe = __double2float_rn(dxe) * cwf, fxo = __double2float_rn(dxo) * cwf;
+      const float fye = __double2float_rn(dye) * chf, fyo = __double2float_rn(dyo) * chf;
+      if (want_res[L] && j < H) {
+        float a = fminf(fminf(fabsf(fxe), fabsf(fye)), fminf(fabsf(fxo), fabsf(fyo)));
+        if (BORDER) a = fminf(e_in ? fminf(fabsf(fxe), fabsf(fye)) : 3.4028234e38f, o_in ? fminf(fabsf(fxo), fabsf(fyo)) : 3.4028234e38f);
+        if (a < rminf[L]) res_update4(rmin[L], rminf[L], e_in, o_in, dxe, dye, dxo, dyo, (double)(W - 1), (double)(H - 1));
+      }
+      if (L == 0) {
+        ve[0] = FRange{fxe, fxe}; ve[1] = FRange{fye, fye}; vo[0] = FRange{fxo, fxo}; vo[1] = FRange{fyo, fyo};
+      } else {
+        ve[0] = fmerge(ve[0], FRange{fxe, fxe}); ve[1] = fmerge(ve[1], FRange{fye, fye});
+        vo[0] = fmerge(vo[0], FRange{fxo, fxo}); vo[1] = fmerge(vo[1], FRange{fyo, fyo});
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 2; c++) {
+      const FRange nx = fshfl_down1(ve[c]);
+      cur[0][c] = e_last ? ve[c] : fmerge(ve[c], vo[c]);
+      cur[1][c] = o_last ? vo[c] : fmerge(vo[c], nx);
+    }
+    if (j > r0) {
+      const int y = j - 1;
+      const bool yrow = y >= p.lb[1] && y <= ytop;
+      bool slow = BORDER || y == ytop;      // masked columns / the domain's last row: per-corner path
+      if (!BORDER && y != ytop) {
+        const FRange ux = fmerge(fmerge(prev[0][0], prev[1][0]), fmerge(cur[0][0], cur[1][0]));
+        const FRange uy = fmerge(fmerge(prev[0][1], prev[1][1]), fmerge(cur[0][1], cur[1][1]));
+        const bool ok = cube_excluded2_f(ux, uy, thrp, thr2, limf) || !(yrow && (e_own || o_own));
+        slow = __any_sync(0xffffffffu, !ok);
+      }
+      if (slow && yrow)
+        bulk_slow_tests(SlowArgs{thrp, thr2, limf, p.lb[0], p.lb[1], p.nc[0], p.wl_count, p.wl, p.wl_cap}, y == ytop, e_own, o_own, e, y,
+                        prev[0][0], prev[0][1], prev[1][0], prev[1][1], cur[0][0], cur[0][1], cur[1][0], cur[1][1]);
+    }
+    release(ST_J);     // row j: its centre went into the window one step ago, its x neighbours were read above
+  };
+
+  for (int j = r0, i = 0; j <= jl; j += TL_NST, i++) {
+    step(IC<0>{}, j, i);
+    if (j + 1 <= jl) step(IC<1>{}, j + 1, i);
+    if (j + 2 <= jl) step(IC<2>{}, j + 2, i);
+    if (j + 3 <= jl) step(IC<3>{}, j + 3, i);
+    if (j + 4 <= jl) step(IC<4>{}, j + 4, i);
+    if (j + 5 <= jl) step(IC<5>{}, j + 5, i);
+  }
+#pragma unroll
+  for (int L = 0; L < NL; L++)
+    if (want_res[L]) warp_res_commit(fabs(rmin[L]), p.res_slot[L]);
+}
+
+template <bool HAS_NEXT>
+__global__ void __launch_bounds__((TL_CW + 1) * 32, 3) scan2d_tile_kernel(const SweepParams p) {
+  constexpr int NL = HAS_NEXT ? 2 : 1;
+  constexpr uint32_t STAGE_BYTES = NL * TL_SEG * 8;
+  extern __shared__ __align__(128) unsigned char fb_smem[];
+  const int lane = threadIdx.x & 31;
+  const int wib = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);     // warp-uniform by construction
+  double *ring = reinterpret_cast<double *>(fb_smem);
+  const uint32_t full0 = smem_u32(fb_smem + (size_t)TL_NST * STAGE_BYTES), empty0 = full0 + 8u * TL_NST;
+  const int W = p.W, H = p.H;
+  const int bx = blockIdx.x % p.nsx, cy = blockIdx.x / p.nsx;
+  const int C0 = bx * (TL_CW * FB_STRIDE);
+  // consumer warps whose strip starts inside the array
+  const int nactive = min(TL_CW, (W - C0 + FB_STRIDE - 1) / FB_STRIDE);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int q = 0; q < TL_NST; q++) { mbar_init(full0 + 8u * q, 1); mbar_init(empty0 + 8u * q, (uint32_t)nactive); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  const int r0 = cy * p.rows;
+  const int r1 = min(r0 + p.rows - 1, H - 1);
+  const int nrows = (r1 + 1) - r0 + 3;               // staged rows r0-1 .. r1+2 (ring index 0 .. nrows-1)
+  if (wib == TL_CW) {
+    // producer: one elected lane walks the rows with the array's index clamp (rows below 0 / above H-1
+    // re-read the border row) and keeps the ring full
+    if (elect_one()) {
+      const int col_lo = max(C0 - 2, 0), col_hi = min(C0 - 2 + TL_SEG, W);
+      const uint32_t seg_bytes = (uint32_t)(col_hi - col_lo) * 8u;
+      const uint32_t dst0 = smem_u32(ring) + (uint32_t)(col_lo - (C0 - 2)) * 8u;
+      for (int rr = 0; rr < nrows; rr++) {
+        const int st = rr % TL_NST;
+        if (rr >= TL_NST) mbar_wait(empty0 + 8u * st, (uint32_t)((rr / TL_NST - 1) & 1));
+        const size_t off = (size_t)W * (size_t)clampi(r0 - 1 + rr, H) + (size_t)col_lo;
+        mbar_expect_tx(full0 + 8u * st, seg_bytes * NL);
+#pragma unroll
+        for (int L = 0; L < NL; L++)
+          bulk_g2s(dst0 + (uint32_t)st * STAGE_BYTES + (uint32_t)(L * TL_SEG) * 8u, (L == 0 ? p.L[0].S : p.L[1].S) + off, seg_bytes, full0 + 8u * st);
+      }
+    }
+    return;
+  }
+  if (wib >= nactive) return;
+  const int c0 = C0 + wib * FB_STRIDE;
+  const double *tile = ring + wib * FB_STRIDE;
+  // strips that touch the array's left / right edge or hold the domain's last column take the masked path
+  const bool border = c0 == 0 || c0 + FB_SEG - 2 > W || (p.ub[0] >= c0 - 1 && p.ub[0] <= c0 + 63);
+  if (border) fused2d_tile_strip<HAS_NEXT, true>(p, c0, r0, r1, lane, tile, full0, empty0);
+  else fused2d_tile_strip<HAS_NEXT, false>(p, c0, r0, r1, lane, tile, full0, empty0);
+}
+
+static size_t tile_smem_bytes(bool has_next) {
+  return (size_t)TL_NST * (has_next ? 2 : 1) * TL_SEG * 8 + (size_t)2 * TL_NST * 8;
+}
+
 static size_t bulk_smem_bytes(bool has_next) {
   return (size_t)FB_WARPS * FB_NST * (has_next ? 2 : 1) * FB_SEG * 8 + (size_t)FB_WARPS * FB_NST * 8;
 }
 
 void init_kernel_attributes() {
+  cudaFuncSetAttribute(scan2d_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem_bytes(true));
+  cudaFuncSetAttribute(scan2d_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem_bytes(false));
   cudaFuncSetAttribute(scan2d_bulk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bulk_smem_bytes(true));
   cudaFuncSetAttribute(scan2d_bulk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bulk_smem_bytes(false));
 }
 
 void launch_scan(const SweepParams &p, cudaStream_t s) {
-  if (p.nd == 2 && p.fused && p.aligned16 && p.bulk) {
+  if (p.nd == 2 && p.fused && p.aligned16 && p.bulk == 2) {
+    const unsigned grid = (unsigned)((i64)p.nsx * p.nsy);
+    if (p.has_next) scan2d_tile_kernel<true><<<grid, (TL_CW + 1) * 32, tile_smem_bytes(true), s>>>(p);
+    else scan2d_tile_kernel<false><<<grid, (TL_CW + 1) * 32, tile_smem_bytes(false), s>>>(p);
+  } else if (p.nd == 2 && p.fused && p.aligned16 && p.bulk) {
     const i64 warps = (i64)p.nsx * p.nsy;
     const unsigned grid = (unsigned)((warps + FB_WARPS - 1) / FB_WARPS);
     if (p.has_next) scan2d_bulk_kernel<true><<<grid, FB_WARPS * 32, bulk_smem_bytes(true), s>>>(p);

@@ -34,7 +34,7 @@ struct SweepParams {
   // fused mode: the vector field is derived from the scalar layers on the fly (L[].V == nullptr)
   int32_t fused;
   int32_t aligned16;          // rows of S start 16-byte aligned (W even, base aligned): vector loads allowed
-  int32_t bulk;               // stage rows with cp.async.bulk + mbarrier (needs aligned16)
+  int32_t bulk;               // row staging with cp.async.bulk + mbarrier (needs aligned16): 2 = CTA-wide ring + producer warp, 1 = per-warp rings, 0 = registers
   float thrp_f;               // 2^-nbits (1 + 2^-20): approx(v) >= thrp_f  =>  |quantised v| >= 1
   float thr2_f;               // 2^(1-nbits)
   float lim_f;                // 0.999 * 4.5e18 / factor^2 (determinant magnitude bound, field units)
