@@ -267,9 +267,10 @@ def main():
 
     # ---- device-resident measurement -------------------------------------------------------------
     tr = make()
-    tr.push_scalar_field_snapshot(layers[tri(g0, NL)], borrow=True)
+    ptrs = [int(l.data_ptr()) for l in layers]     # resident layers are borrowed in place through the C ABI
+    tr.push_device_pointers(scalar=ptrs[tri(g0, NL)])
     for i in range(W):
-        tr.push_scalar_field_snapshot(layers[tri(g0 + i + 1, NL)], borrow=True)
+        tr.push_device_pointers(scalar=ptrs[tri(g0 + i + 1, NL)])
         tr.advance_timestep()
     halo = None
     sampler = ClockSampler(physical_gpu_index(local))
@@ -289,13 +290,13 @@ def main():
             reqs.append(dist.irecv(halo, rank + 1))
     res_layers, factors = [], []
     for i in range(W, W + K):
-        nxt = layers[tri(g0 + i + 1, NL)]
+        nxt = ptrs[tri(g0 + i + 1, NL)]
         if halo is not None and i == W + K - 1:
             for r in reqs:
                 r.wait()
             torch.cuda.current_stream().synchronize()
-            nxt = halo
-        tr.push_scalar_field_snapshot(nxt, borrow=True)
+            nxt = int(halo.data_ptr())
+        tr.push_device_pointers(scalar=nxt)
         tr.advance_timestep()
         if dist:
             res_layers.append(tr.stats()["resolution"])   # running minimum inside this slab

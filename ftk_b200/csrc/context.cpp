@@ -224,12 +224,9 @@ static int queue_resolution(ftkb_ctx *c, Layer &l, bool fused_in_gradient) {
 }
 
 static int derive_layer(ftkb_ctx *c, Layer &l) {
-  // slot <- DBL_MAX
-  unsigned long long init;
-  const double dmax = DBL_MAX;
-  std::memcpy(&init, &dmax, 8);
-  launch_fill_u64(c->d_scalars + l.slot, init, c->stream);
-  c->stats.kernel_launches++;
+  // slot <- all ones: above the bit pattern of every finite double, so the kernels' atomicMin on the
+  // bit patterns of |v| works unchanged and "nothing found" reads back as DBL_MAX (slot_value)
+  CK(cudaMemsetAsync(c->d_scalars + l.slot, 0xff, sizeof(unsigned long long), c->stream));
   bool fused = false;
   if (!l.V && c->cfg.vector_source == FTKB_SOURCE_DERIVED && l.S && c->n == 2) {
     // 2D: the gradient is never materialised; the fused scan derives it on the fly and computes this
@@ -323,7 +320,7 @@ static int resolve_pending(ftkb_ctx *c, Layer &l);
 static double slot_value(const ftkb_ctx *c, int slot) {
   double v;
   std::memcpy(&v, c->h_scalars + slot, 8);
-  return v;
+  return (c->h_scalars[slot] >> 52) >= 0x7ff ? DBL_MAX : v;    // untouched slot (all ones): no non-zero finite value
 }
 
 extern "C" int ftkb_last_layer_resolution(ftkb_ctx *c, double *res) {
@@ -391,11 +388,11 @@ static void fused2d_decomposition(const ftkb_ctx *c, SweepParams &p) {
   int64_t nsy;
   if (p.bulk == 2) {      // CTA tiles of 7 x 62 corner columns, 3 CTAs per SM: about two waves of CTAs
     p.nsx = std::max(1, (p.W + 7 * 62 - 1) / (7 * 62));
-    nsy = (2 * (int64_t)c->sm_count * 3 + p.nsx / 2) / p.nsx;
+    nsy = (2 * (int64_t)c->sm_count * 3) / p.nsx;          // floor: a few CTAs more than two waves would cost a third one
   } else {
     p.nsx = p.bulk ? std::max(1, (p.W + 61) / 62) : std::max(1, (p.W - 1 + 59) / 60);
     const int64_t resident_warps = (int64_t)c->sm_count * (p.bulk ? 3 : 2) * 8;
-    nsy = (2 * resident_warps + p.nsx / 2) / p.nsx;
+    nsy = (2 * resident_warps) / p.nsx;
   }
   nsy = std::max<int64_t>(1, std::min<int64_t>(nsy, (p.H + 31) / 32));
   p.rows = (int)((p.H + nsy - 1) / nsy);

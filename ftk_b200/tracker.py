@@ -213,6 +213,12 @@ class _RegularTracker:
             self._keep = self._keep[-4:]
         self._check(L.lib().ftkb_push_snapshot(self._h, ptrs[0], ptrs[1], ptrs[2], where if where is not None else L.MEM_HOST))
 
+    def push_device_pointers(self, scalar=0, vector=0, jacobian=0):
+        """Raw device pointers (ints), used in place (FTKB_MEM_DEVICE_BORROW): the thinnest wrapper over
+        ftkb_push_snapshot for callers that keep their time series resident in HBM.  The arrays must stay
+        valid and unchanged until two advance_timestep() calls later."""
+        self._check(L.lib().ftkb_push_snapshot(self._h, scalar or None, vector or None, jacobian or None, L.MEM_DEVICE_BORROW))
+
     def push_scalar_field_snapshot(self, scalar, borrow=False):
         self.push_field_data_snapshot(scalar=scalar, borrow=borrow)
 
