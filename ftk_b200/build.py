@@ -11,6 +11,9 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libftkb200.so")
+CLI = os.path.join(HERE, "bin", "ftkb200")          # `ftk -f cp` front end (C++ host code over the C ABI)
+CLI_SOURCES = [os.path.join(CSRC, "cli.cpp"), os.path.join(HERE, "..", "include", "ftk_b200", "critical_point_tracker_regular.hh"),
+               os.path.join(HERE, "..", "include", "ftkb200.h")]
 SOURCES = ["kernels.cu", "context.cpp", "mesh_tables.cpp"]
 HEADERS = ["kernels.h", "mesh_tables.h", os.path.join("..", "..", "include", "ftkb200.h")]
 # -fmad=false: the parity target is the reference's x86-64 CPU path (no FMA contraction)
@@ -32,7 +35,26 @@ def stale():
     return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS) or os.path.getmtime(__file__) > t
 
 
+def build_cli(force=False):
+    """g++ host program linked against the in-tree library (rpath $ORIGIN/..)"""
+    if not force and os.path.exists(CLI) and all(os.path.getmtime(f) <= os.path.getmtime(CLI) for f in CLI_SOURCES + [LIB]):
+        return CLI
+    os.makedirs(os.path.dirname(CLI), exist_ok=True)
+    cmd = ["g++", "-O2", "-std=c++17", "-Wall", CLI_SOURCES[0], "-o", CLI, "-L" + HERE, "-lftkb200", "-Wl,-rpath,$ORIGIN/.."]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("g++ failed: " + " ".join(cmd))
+    return CLI
+
+
 def build(force=False, verbose=False):
+    _build_lib(force, verbose)
+    build_cli(force)
+    return LIB
+
+
+def _build_lib(force=False, verbose=False):
     if not force and not stale():
         return LIB
     cmd = [nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + [os.path.join(CSRC, f) for f in SOURCES]

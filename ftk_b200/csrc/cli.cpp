@@ -1,0 +1,315 @@
+// ftkb200 -- command-line front end with the `ftk -f cp` flags of the reference
+// (ref: src/cli/ftk.cpp:885-1078 option table and main; include/ftk/filters/json_interface.hh:606-725
+// consume_regular: the push / advance / update loop; include/ftk/ndarray/stream.hh:258-440,1443-1568
+// synthetic stream defaults and per-timestep time conventions).
+//
+// Host code only: inputs are produced (closed-form generators, same formulas and libm as the
+// reference, so snapshots are bit-identical) or read (raw float32/float64 series), pushed through
+// the C++ tracker classes of include/ftk_b200/critical_point_tracker_regular.hh, which call the
+// C ABI of libftkb200.so; every per-simplex computation runs on the GPU.  Without a B200 the
+// program fails with the library's error message -- there is no CPU path.
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <iostream>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/ftk_b200/critical_point_tracker_regular.hh"
+
+using namespace ftk_b200;
+
+namespace {
+
+struct Options {
+  std::string feature = "cp", input, input_format = "float64", synthetic, output, output_type = "traced", output_format = "auto";
+  std::string type_filter, accelerator = "cuda", var;
+  long width = -1, height = -1, depth = -1, timesteps = -1;
+  int device = 0, nthreads = 0;
+  bool timing = false, compute_degrees = false, no_robust = false, verbose = false, device_generators = false, help = false;
+  std::vector<double> x0, dir;
+  double time_scale = 0.1;
+};
+
+[[noreturn]] void die(const std::string &m) {
+  std::fprintf(stderr, "ftkb200: %s\n", m.c_str());
+  std::exit(1);
+}
+
+void usage() {
+  std::puts(
+      "usage: ftkb200 -f cp (--synthetic NAME | --input PATTERN) -o OUTPUT [options]\n"
+      "  -f, --feature cp|critical_point   feature type (only critical points are implemented)\n"
+      "      --synthetic NAME              woven | moving_extremum_2d | moving_extremum_3d | double_gyre | merger_2d\n"
+      "  -i, --input PATTERN               raw file: one file holding all timesteps, or a printf pattern (e.g. s-%03d.raw)\n"
+      "      --input-format float32|float64\n"
+      "      --var a[,b[,c]]               variable names; 2 / 3 names = vector field with the component index fastest\n"
+      "  -w, --width N  -h, --height N  -d, --depth N  -n, --timesteps N\n"
+      "      --x0 a,b[,c]  --dir a,b[,c]   moving_extremum parameters;  --time-scale s (double_gyre)\n"
+      "  -o, --output FILE                 result file\n"
+      "      --output-type traced|discrete     (default traced)\n"
+      "      --output-format text|json         (default: by file name, .json -> json, else text)\n"
+      "      --type-filter min|max|saddle|...  (2D; names joined with |)\n"
+      "      --compute-degrees  --no-robust-detection  --timing  -v/--verbose\n"
+      "  -a, --accelerator cuda            (the only back end)   --device ID   --nthreads N (ignored)\n"
+      "      --device-generators           synthesise inputs on the GPU (CUDA libm; not bit-identical to the host generators)");
+}
+
+std::vector<double> parse_list(const std::string &s) {
+  std::vector<double> v;
+  size_t a = 0;
+  while (a <= s.size()) {
+    const size_t b = s.find(',', a);
+    v.push_back(std::atof(s.substr(a, b == std::string::npos ? std::string::npos : b - a).c_str()));
+    if (b == std::string::npos) break;
+    a = b + 1;
+  }
+  return v;
+}
+
+Options parse(int argc, char **argv) {
+  Options o;
+  auto need = [&](int &i) -> std::string { if (i + 1 >= argc) die(std::string("missing value for ") + argv[i]); return argv[++i]; };
+  for (int i = 1; i < argc; i++) {
+    const std::string a = argv[i];
+    if (a == "-f" || a == "--feature") o.feature = need(i);
+    else if (a == "-i" || a == "--input") o.input = need(i);
+    else if (a == "--input-format") o.input_format = need(i);
+    else if (a == "--synthetic") o.synthetic = need(i);
+    else if (a == "-w" || a == "--width") o.width = std::atol(need(i).c_str());
+    else if (a == "-h" || a == "--height") o.height = std::atol(need(i).c_str());
+    else if (a == "-d" || a == "--depth") o.depth = std::atol(need(i).c_str());
+    else if (a == "-n" || a == "--timesteps") o.timesteps = std::atol(need(i).c_str());
+    else if (a == "--var") o.var = need(i);
+    else if (a == "--x0") o.x0 = parse_list(need(i));
+    else if (a == "--dir") o.dir = parse_list(need(i));
+    else if (a == "--time-scale") o.time_scale = std::atof(need(i).c_str());
+    else if (a == "-o" || a == "--output") o.output = need(i);
+    else if (a == "--output-type") o.output_type = need(i);
+    else if (a == "--output-format") o.output_format = need(i);
+    else if (a == "--type-filter") o.type_filter = need(i);
+    else if (a == "--nthreads") o.nthreads = std::atoi(need(i).c_str());
+    else if (a == "--thread-backend" || a == "--device-buffer" || a == "--nblocks") need(i);   // accepted, meaningless here
+    else if (a == "--affinity" || a == "--async") {}
+    else if (a == "--timing") o.timing = true;
+    else if (a == "-a" || a == "--accelerator") o.accelerator = need(i);
+    else if (a == "--device") o.device = std::atoi(need(i).c_str());
+    else if (a == "--compute-degrees") o.compute_degrees = true;
+    else if (a == "--no-robust-detection") o.no_robust = true;
+    else if (a == "--device-generators") o.device_generators = true;
+    else if (a == "-v" || a == "--verbose") o.verbose = true;
+    else if (a == "--help") o.help = true;
+    else if (a == "--stream" || a == "--post-process") die(a + " is not implemented (SURVEY.md 8 f3/f4)");
+    else die("unknown option " + a);
+  }
+  return o;
+}
+
+// ref: src/cli/ftk.cpp:104-117 (names joined with '|')
+unsigned parse_type_filter(const std::string &s) {
+  unsigned f = 0;
+  size_t a = 0;
+  while (a <= s.size()) {
+    const size_t b = s.find('|', a);
+    const std::string w = s.substr(a, b == std::string::npos ? std::string::npos : b - a);
+    if (w == "degenerate") f |= CRITICAL_POINT_2D_DEGENERATE;
+    else if (w == "min" || w == "repelling") f |= CRITICAL_POINT_2D_MINIMUM;
+    else if (w == "max" || w == "attracting") f |= CRITICAL_POINT_2D_MAXIMUM;
+    else if (w == "saddle") f |= CRITICAL_POINT_2D_SADDLE;
+    else if (w == "attracting_focus") f |= CRITICAL_POINT_2D_ATTRACTING_FOCUS;
+    else if (w == "repelling_focus") f |= CRITICAL_POINT_2D_REPELLING_FOCUS;
+    else if (w == "center") f |= CRITICAL_POINT_2D_CENTER;
+    else die("unknown critical point type '" + w + "'");
+    if (b == std::string::npos) break;
+    a = b + 1;
+  }
+  return f;
+}
+
+// ---- host generators: closed forms of include/ftk/ndarray/synthetic.hh, evaluated with the host libm -------------
+void gen_woven(long W, long H, double t, double *out) {               // synthetic.hh:32-48 (scaling factor 15)
+  for (long j = 0; j < H; j++)
+    for (long i = 0; i < W; i++) {
+      const double x = ((double(i) / (W - 1)) - 0.5) * 15.0, y = ((double(j) / (H - 1)) - 0.5) * 15.0;
+      out[i + W * j] = std::cos(x * std::cos(t) - y * std::sin(t)) * std::sin(x * std::sin(t) + y * std::cos(t));
+    }
+}
+
+void gen_merger(long W, long H, double t, double *out) {              // synthetic.hh:262-297
+  const double cx0 = std::sin(t - M_PI_2), cx1 = std::sin(t + M_PI_2), cy = 1e-4;
+  for (long j = 0; j < H; j++)
+    for (long i = 0; i < W; i++) {
+      double x = ((double(i) / (W - 1)) - 0.5) * 4.0, y = ((double(j) / (H - 1)) - 0.5) * 4.0;
+      const double xp = x * std::cos(t) - y * std::sin(t), yp = x * std::sin(t) + y * std::cos(t);
+      x = xp; y = yp;
+      const double f0 = std::exp(-((x - cx0) * (x - cx0) + (y - cy) * (y - cy))), f1 = std::exp(-((x - cx1) * (x - cx1) + (y - cy) * (y - cy)));
+      out[i + W * j] = std::max(f0, f1);
+    }
+}
+
+void gen_moving_extremum(int nd, const long *dims, const double *x0, const double *dir, double t, double *out) {   // synthetic.hh:332-354
+  const long W = dims[0], H = dims[1], D = nd == 3 ? dims[2] : 1;
+  double xc[3] = {0, 0, 0};
+  for (int q = 0; q < nd; q++) xc[q] = x0[q] + dir[q] * t;
+  for (long k = 0; k < D; k++)
+    for (long j = 0; j < H; j++)
+      for (long i = 0; i < W; i++) {
+        const double x[3] = {double(i), double(j), double(k)};
+        double d = 0;
+        for (int q = 0; q < nd; q++) d += std::pow(x[q] - xc[q], 2.0);
+        out[i + W * (j + H * k)] = d;
+      }
+}
+
+void gen_double_gyre(long W, long H, double time, double *out) {      // synthetic.hh:130-150,193-217: A = 0.1, omega = 2 pi, eps = 0.25
+  const double A = 0.1, omega = M_PI * 2, eps = 0.25;
+  for (long j = 0; j < H; j++)
+    for (long i = 0; i < W; i++) {
+      const double x = (double(i) / (W - 1)) * 2, y = double(j) / (H - 1);
+      const double a = eps * std::sin(omega * time), b = 1 - 2 * eps * std::sin(omega * time);
+      const double f = a * x * x + b * x, dfdx = 2 * a * x + b;
+      out[2 * (i + W * j)] = -M_PI * A * std::sin(M_PI * f) * std::cos(M_PI * y);
+      out[2 * (i + W * j) + 1] = M_PI * A * std::cos(M_PI * f) * std::sin(M_PI * y) * dfdx;
+    }
+}
+
+// raw input: snapshot k from one big file (offset k * bytes) or from sprintf(pattern, k)
+void read_raw(const Options &o, long k, size_t count, bool f32, double *out) {
+  std::string path = o.input;
+  long offset = 0;
+  if (o.input.find('%') != std::string::npos) {
+    char buf[4096];
+    std::snprintf(buf, sizeof(buf), o.input.c_str(), (int)k);
+    path = buf;
+  } else {
+    offset = k * (long)count * (f32 ? 4 : 8);
+  }
+  FILE *f = std::fopen(path.c_str(), "rb");
+  if (!f) die("cannot open " + path);
+  if (std::fseek(f, offset, SEEK_SET) != 0) die("cannot seek in " + path);
+  if (f32) {
+    std::vector<float> tmp(count);
+    if (std::fread(tmp.data(), 4, count, f) != count) die("short read from " + path);
+    for (size_t i = 0; i < count; i++) out[i] = tmp[i];
+  } else if (std::fread(out, 8, count, f) != count) die("short read from " + path);
+  std::fclose(f);
+}
+
+double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+}  // namespace
+
+int main(int argc, char **argv) {
+  Options o = parse(argc, argv);
+  if (o.help || argc == 1) { usage(); return 0; }
+  if (o.feature != "cp" && o.feature != "critical_point") die("only '-f cp' (critical points on regular grids) is implemented");
+  if (o.accelerator != "cuda") die("invalid '--accelerator': this build runs on CUDA (sm_100a) only, there is no CPU path");
+  if (o.output.empty()) die("Missing '--output'.");
+  if (o.synthetic.empty() == o.input.empty()) die("give exactly one of --synthetic and --input");
+
+  // stream description (stream.hh:258-440 defaults)
+  int nd = 2, nv = 1;
+  long dims[3] = {32, 32, 32}, T = 32;
+  int syn = -1;   // FTKB_SYN_* for --device-generators
+  if (!o.synthetic.empty()) {
+    const std::string &s = o.synthetic;
+    if (s == "woven") { syn = FTKB_SYN_WOVEN; }
+    else if (s == "moving_extremum_2d") { dims[0] = dims[1] = 21; syn = FTKB_SYN_MOVING_EXTREMUM; if (o.x0.empty()) o.x0 = {10.0, 10.0}; if (o.dir.empty()) o.dir = {0.1, 0.1}; }
+    else if (s == "moving_extremum_3d") { nd = 3; dims[0] = dims[1] = dims[2] = 21; syn = FTKB_SYN_MOVING_EXTREMUM; if (o.x0.empty()) o.x0 = {10, 10, 10}; if (o.dir.empty()) o.dir = {0.1, 0.11, 0.1}; }
+    else if (s == "double_gyre") { dims[0] = 64; dims[1] = 32; T = 50; nv = 2; syn = FTKB_SYN_DOUBLE_GYRE; }
+    else if (s == "merger_2d") { T = 100; syn = FTKB_SYN_MERGER; }
+    else die("synthetic case not available: " + s);
+    if (syn == FTKB_SYN_MOVING_EXTREMUM && ((int)o.x0.size() != nd || (int)o.dir.size() != nd)) die("invalid x0 / dir");
+  } else {
+    if (o.width < 0 || o.height < 0 || o.timesteps < 0) die("--input needs --width, --height[, --depth] and --timesteps");
+    nd = o.depth > 0 ? 3 : 2;
+    if (!o.var.empty()) nv = (int)parse_list(o.var).size();
+    if (nv != 1 && nv != nd) die("--var must name 1 variable (scalar field) or as many as spatial dimensions (vector field)");
+    if (o.input_format != "float32" && o.input_format != "float64") die("--input-format must be float32 or float64");
+  }
+  if (o.width > 0) dims[0] = o.width;
+  if (o.height > 0) dims[1] = o.height;
+  if (o.depth > 0) { if (nd != 3) die("--depth is valid only for 3D data"); dims[2] = o.depth; }
+  if (o.timesteps > 0) T = o.timesteps;
+
+  const double t_start = now();
+  std::unique_ptr<critical_point_tracker_regular> tr;
+  if (nd == 2) tr.reset(new critical_point_tracker_2d_regular()); else tr.reset(new critical_point_tracker_3d_regular());
+  // json_interface.hh:634-656: scalar -> derived gradient + symmetric Jacobian on [2, D-2]; vector -> given, non-symmetric, [1, D-2]
+  std::vector<int> lo(nd), sz(nd), zero(nd, 0), full(nd);
+  for (int i = 0; i < nd; i++) { lo[i] = nv == 1 ? 2 : 1; sz[i] = (int)dims[i] - (nv == 1 ? 3 : 2); full[i] = (int)dims[i]; }
+  try {
+    tr->set_domain(lattice(lo, sz));
+    tr->set_array_domain(lattice(zero, full));
+    if (nv == 1) {
+      tr->set_scalar_field_source(SOURCE_GIVEN); tr->set_vector_field_source(SOURCE_DERIVED); tr->set_jacobian_field_source(SOURCE_DERIVED);
+      tr->set_jacobian_symmetric(true);
+    } else {
+      tr->set_scalar_field_source(SOURCE_NONE); tr->set_vector_field_source(SOURCE_GIVEN); tr->set_jacobian_field_source(SOURCE_DERIVED);
+      tr->set_jacobian_symmetric(false);
+      tr->set_scalar_components({});
+    }
+    tr->set_number_of_threads(o.nthreads);
+    tr->use_accelerator(o.accelerator);
+    tr->set_device_ids({o.device});
+    if (!o.type_filter.empty()) tr->set_type_filter(parse_type_filter(o.type_filter));
+    if (o.compute_degrees) tr->set_enable_computing_degrees(true);
+    if (o.no_robust) tr->set_enable_robust_detection(false);
+    tr->initialize();
+    const double t_init = now();
+
+    size_t nvert = 1;
+    for (int i = 0; i < nd; i++) nvert *= (size_t)dims[i];
+    std::vector<double> buf(nvert * nv);
+    std::vector<size_t> shape;
+    if (nv > 1) shape.push_back(nv);
+    for (int i = 0; i < nd; i++) shape.push_back((size_t)dims[i]);
+    for (long k = 0; k < T; k++) {
+      if (o.verbose) std::fprintf(stderr, "current_timestep=%ld\n", k);
+      if (syn >= 0 && o.device_generators) {
+        std::vector<double> p;
+        double t = double(k);
+        if (syn == FTKB_SYN_WOVEN) t = T == 1 ? 0.0 : double(k) / (T - 1);
+        else if (syn == FTKB_SYN_MERGER) t = double(k) * 0.1;
+        else if (syn == FTKB_SYN_DOUBLE_GYRE) { t = k * o.time_scale; p = {0.1, M_PI * 2, 0.25}; }
+        else { p = o.x0; p.insert(p.end(), o.dir.begin(), o.dir.end()); }
+        tr->push_synthetic_snapshot(syn, p, t);
+      } else {
+        if (syn == FTKB_SYN_WOVEN) gen_woven(dims[0], dims[1], T == 1 ? 0.0 : double(k) / (T - 1), buf.data());        // stream.hh:1468-1480
+        else if (syn == FTKB_SYN_MERGER) gen_merger(dims[0], dims[1], double(k) * 0.1, buf.data());                   // stream.hh:1540
+        else if (syn == FTKB_SYN_DOUBLE_GYRE) gen_double_gyre(dims[0], dims[1], k * o.time_scale, buf.data());        // stream.hh:1542-1555
+        else if (syn == FTKB_SYN_MOVING_EXTREMUM) gen_moving_extremum(nd, dims, o.x0.data(), o.dir.data(), double(k), buf.data());
+        else read_raw(o, k, nvert * nv, o.input_format == "float32", buf.data());
+        const ndarray<double> a = ndarray<double>::wrap(buf.data(), shape);
+        if (nv == 1) tr->push_scalar_field_snapshot(a); else tr->push_vector_field_snapshot(a);
+      }
+      if (k != 0) tr->advance_timestep();          // json_interface.hh:699-706
+      if (k == T - 1) tr->update_timestep();
+    }
+    const double t_compute = now();
+    if (o.output_type == "traced") tr->finalize();
+    const double t_final = now();
+
+    std::string fmt = o.output_format;
+    if (fmt == "auto") fmt = (o.output.size() > 5 && o.output.substr(o.output.size() - 5) == ".json") ? "json" : "text";
+    if (o.output_type == "traced") {
+      if (fmt == "json") tr->write_traced_critical_points_json(o.output); else if (fmt == "text") tr->write_traced_critical_points_text(o.output); else die("unsupported --output-format " + fmt);
+    } else if (o.output_type == "discrete") {
+      if (fmt == "json") tr->write_critical_points_json(o.output); else if (fmt == "text") tr->write_critical_points_text(o.output); else die("unsupported --output-format " + fmt);
+    } else die("unsupported --output-type " + o.output_type + " (traced | discrete)");
+
+    if (o.timing) {   // same line as json_interface.hh:718-723, plus the device-side split
+      const ftkb_stats st = tr->stats();
+      std::fprintf(stderr, "t_init=%f, t_compute=%f, t_finalize=%f\n", t_init - t_start, t_compute - t_init, t_final - t_compute);
+      std::fprintf(stderr, "simplices_tested=%llu, punctured=%llu, kernel_launches=%llu, ms_scan=%f, ms_test=%f, ms_derive=%f, h2d_bytes=%llu\n",
+                   (unsigned long long)st.simplices_tested, (unsigned long long)st.points, (unsigned long long)st.kernel_launches, st.ms_scan, st.ms_test, st.ms_derive,
+                   (unsigned long long)st.h2d_bytes);
+    }
+  } catch (const std::exception &e) {
+    die(e.what());
+  }
+  return 0;
+}

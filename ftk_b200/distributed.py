@@ -1,0 +1,159 @@
+"""Time-slab sharding of the tracker over the ranks of a torch.distributed group (one process per GPU).
+
+The path shards along time: the sweeps of different timesteps are independent once the
+quantisation factor is known, only the interval sweep of a slab's last timestep needs one layer of the
+next slab, and only trace construction needs a global view.  Rank r of R owns the contiguous
+timesteps [t0, t1) = slab_range(T, R, r):
+
+  ownership   a simplex belongs to the slab that owns its corner's timestep.  Rank r therefore runs the
+              ordinal sweeps at t0 .. t1-1 and the interval sweeps over [t, t+1] for t0 <= t < t1 (the
+              last rank has no interval sweep at T-1: the reference's final update_timestep sees one
+              snapshot, json_interface.hh:699-706).  Nothing is swept twice, nothing is dropped.
+  halo        one layer: the first layer of slab r+1, sent by its owner (send/recv: ncclSend/ncclRecv
+              over NVLink for CUDA tensors).  Skipped when the source can produce any layer locally.
+  factor      the reference's quantisation factor is a RUNNING quantity (min non-zero |v| over every layer
+              seen so far, critical_point_tracker.hh:850-864).  Every rank sweeps optimistically with the
+              minimum of its own slab, then the slab minima are all-gathered; a rank whose factor would
+              have differed at any of its steps under the exclusive prefix minimum repeats its slab with
+              that prefix as the initial resolution (rare: nbits is clamped to [8, 21]).
+  merge       the sparse punctured simplices (72-byte records) are gathered on rank 0, which imports them
+              and runs the union-find + trace ordering once (ftkb_import_points + ftkb_finalize): the
+              labels of components that cross slab boundaries are merged there.
+
+The collective plumbing is backend-agnostic (nccl on the GPUs; gloo in the CPU tests, where the tracker
+factory is the test's stand-in); the sweep itself always runs in the CUDA library.
+"""
+import math
+
+import numpy as np
+
+from . import _lib as L
+
+
+def slab_range(T, world, rank):
+    """contiguous, balanced partition of timesteps 0..T-1: the first T % world slabs get one more"""
+    base, extra = divmod(int(T), int(world))
+    t0 = rank * base + min(rank, extra)
+    return t0, t0 + base + (1 if rank < extra else 0)
+
+
+def nbits_of(resolution):
+    """ref: critical_point_tracker.hh:850-864 (minbits 8, maxbits 21)"""
+    if not (resolution > 0) or math.isinf(resolution):
+        return 8
+    return max(8, min(int(math.ceil(math.log2(1.0 / resolution))), 21))
+
+
+def exclusive_prefix_min(values, rank):
+    return min([float(v) for v in values[:rank]] + [float("inf")])
+
+
+def _default_factory(dims, field, start_timestep, resolution_init, **kw):
+    from .tracker import make_tracker
+    return make_tracker(dims, field=field, start_timestep=start_timestep, resolution_init=resolution_init, **kw)
+
+
+def _sweep_slab(make, layer, push, t0, t1, T, halo_layer, resolution_init):
+    """one pass over the slab; returns (tracker, [(running resolution, factor) per sweep])"""
+    tr = make(t0, resolution_init)
+    log = []
+    last = t1 == T
+    for k in range(t0, t1 + (0 if last else 1)):
+        push(tr, halo_layer if (k == t1 and halo_layer is not None) else layer(k))
+        if k > t0:
+            tr.advance_timestep()
+            log.append(_res_factor(tr))
+    if last:
+        tr.update_timestep()
+        log.append(_res_factor(tr))
+    return tr, log
+
+
+def _res_factor(tr):
+    st = tr.stats()
+    return float(st["resolution"]), float(st["scaling_factor"])
+
+
+def track_time_sharded(layer, dims, T, field="scalar", group=None, tracker_factory=None, exchange_halo=True, trace=True, **kw):
+    """Run the tracker over T timesteps sharded into time slabs over the ranks of `group`.
+
+    layer(k)         -> snapshot k in memory order (numpy array or CUDA tensor); called on the rank that owns
+                        timestep k (and for the halo layer k = t1 when exchange_halo is False)
+    tracker_factory  (dims, field, start_timestep, resolution_init, **kw) -> tracker; default: the CUDA tracker
+    Returns the rank-0 tracker holding every punctured simplex (finalized when trace=True) on rank 0 and the
+    local slab's tracker elsewhere, plus a dict of bookkeeping (slab, halo bytes, repeated slabs)."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    if T < world:
+        raise ValueError("fewer timesteps than ranks")
+    t0, t1 = slab_range(T, world, rank)
+    factory = tracker_factory or _default_factory
+
+    def make(start, res_init):
+        return factory(dims, field, start, res_init, **kw)
+
+    def push(tr, a):
+        if field == "scalar":
+            tr.push_scalar_field_snapshot(a)
+        else:
+            tr.push_vector_field_snapshot(a)
+
+    info = {"rank": rank, "world": world, "slab": (t0, t1), "halo_bytes": 0, "slab_repeated": False}
+    # ---- halo: first layer of the next slab --------------------------------------------------------------
+    halo = None
+    first = None
+    if world > 1 and exchange_halo:
+        reqs = []
+        if rank > 0:
+            first = layer(t0)
+            send_t = first if torch.is_tensor(first) else torch.from_numpy(np.ascontiguousarray(first, dtype=np.float64))
+            reqs.append(dist.isend(send_t.contiguous(), rank - 1, group=group))
+        if rank < world - 1:
+            proto = first if first is not None else layer(t0)
+            if first is None:
+                first = proto
+            halo = torch.empty_like(proto) if torch.is_tensor(proto) else torch.empty(np.shape(proto), dtype=torch.float64)
+            reqs.append(dist.irecv(halo, rank + 1, group=group))
+            info["halo_bytes"] = halo.numel() * 8
+        for r in reqs:
+            r.wait()
+        if halo is not None and halo.is_cuda:
+            torch.cuda.current_stream(halo.device).synchronize()
+        if halo is not None and not halo.is_cuda:
+            halo = halo.numpy()
+    cached_first = first
+
+    def layer_c(k):
+        return cached_first if (k == t0 and cached_first is not None) else layer(k)
+
+    # ---- optimistic sweep with the slab's own running minimum ---------------------------------------------
+    tr, log = _sweep_slab(make, layer_c, push, t0, t1, T, halo, 0.0)
+    if world > 1:
+        mine = torch.tensor([min(r for r, _ in log)], dtype=torch.float64)
+        dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+        mine = mine.to(dev)
+        allres = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allres, mine, group=group)
+        prefix = exclusive_prefix_min([float(a.item()) for a in allres], rank)
+        info["prefix_resolution"] = prefix
+        if prefix < float("inf") and any(float(1 << nbits_of(min(prefix, r))) != f for r, f in log):
+            # the factor this slab used differs from the sequential run's: repeat it with the inherited minimum
+            tr.close() if hasattr(tr, "close") else None
+            tr, log = _sweep_slab(make, layer_c, push, t0, t1, T, halo, prefix)
+            info["slab_repeated"] = True
+    info["factors"] = [f for _, f in log]
+
+    # ---- merge on rank 0 -------------------------------------------------------------------------------------
+    pts = tr.get_discrete_critical_points()
+    if world > 1:
+        gathered = [None] * world if rank == 0 else None
+        dist.gather_object(pts.tobytes(), gathered, dst=0, group=group)
+        if rank == 0:
+            for b in gathered[1:]:
+                if len(b):
+                    tr.import_points(np.frombuffer(b, dtype=L.POINT_DTYPE))
+    if rank == 0 and trace:
+        tr.finalize()
+    return tr, info

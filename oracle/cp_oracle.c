@@ -1010,6 +1010,19 @@ static void sort_points(cpo_ctx *c)
   c->sorted = 1;
 }
 
+/* time-slab helpers (test infrastructure for the multi-GPU protocol; not reference functions): a slab
+ * inherits the running minimum of critical_point_tracker.hh:850-864 from the slabs before it, and the
+ * root merges the punctured simplices of every slab before trace_critical_points_offline */
+void cpo_set_resolution(cpo_ctx *c, double r) { if (r > 0 && r < c->resolution) c->resolution = r; }
+void cpo_import_points(cpo_ctx *c, const cpo_point *pts, uint64_t n)
+{
+  for (uint64_t i = 0; i < n; i ++) {
+    if (c->npts == c->cap) { c->cap = c->cap ? c->cap * 2 : 1024; c->pts = (cpo_point *)realloc(c->pts, sizeof(cpo_point) * c->cap); }
+    c->pts[c->npts ++] = pts[i];
+  }
+  c->sorted = 0;
+}
+
 uint64_t cpo_num_points(const cpo_ctx *c) { sort_points((cpo_ctx *)c); return c->npts; }
 void cpo_get_points(const cpo_ctx *c, cpo_point *out) { sort_points((cpo_ctx *)c); memcpy(out, c->pts, sizeof(cpo_point) * c->npts); }
 

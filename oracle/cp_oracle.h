@@ -55,6 +55,10 @@ int cpo_finalize(cpo_ctx *);
 double cpo_scaling_factor(const cpo_ctx *);
 double cpo_resolution(const cpo_ctx *);
 
+/* time-slab helpers (not reference functions; see cp_oracle.c) */
+void cpo_set_resolution(cpo_ctx *, double r);
+void cpo_import_points(cpo_ctx *, const cpo_point *pts, uint64_t n);
+
 uint64_t cpo_num_points(const cpo_ctx *);
 /* sorted by the reference's element order (corner lexicographic x first, then type) */
 void cpo_get_points(const cpo_ctx *, cpo_point *out);

@@ -64,6 +64,10 @@ def lib():
             getattr(L, name).argtypes = [C.c_void_p]
             getattr(L, name).restype = C.c_uint64
         L.cpo_get_points.argtypes = [C.c_void_p, C.c_void_p]
+        L.cpo_set_resolution.argtypes = [C.c_void_p, C.c_double]
+        L.cpo_set_resolution.restype = None
+        L.cpo_import_points.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+        L.cpo_import_points.restype = None
         L.cpo_get_trajectories.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.cpo_get_component_labels.argtypes = [C.c_void_p, C.c_void_p]
         L.cpo_get_degrees.argtypes = [C.c_void_p, C.c_void_p]
@@ -250,6 +254,15 @@ class Tracker:
         if nt:
             lib().cpo_get_trajectories(self._h, _ptr(off), _ptr(idx), _ptr(loop))
         return [(idx[int(off[i]):int(off[i + 1])].astype(np.int64), bool(loop[i])) for i in range(nt)]
+
+    # time-slab helpers (multi-GPU protocol tests)
+    def set_resolution(self, r):
+        lib().cpo_set_resolution(self._h, float(r))
+
+    def import_points(self, pts):
+        pts = np.ascontiguousarray(pts, dtype=POINT_DTYPE)
+        if len(pts):
+            lib().cpo_import_points(self._h, _ptr(pts), len(pts))
 
     def component_labels(self):
         n = lib().cpo_num_points(self._h)
