@@ -378,7 +378,7 @@ def main():
         peak, peak_src = measured_peaks()
         nscan = max(int(st["scan_launches"]), 1)
         scan_ms = st["ms_scan"] / nscan
-        fused = nd == 2   # 2D scalar input: gradient fused into the scan, the vector field is never materialised
+        fused = st["ms_derive"] == 0.0   # scalar input: gradient fused into the scan, the vector field is never materialised
         # algorithmic bytes of one scan launch (DESIGN.md "Kernels"): the two input layers read once each
         # (fused: fp64 scalar layers, 8 B/vertex; otherwise fp64 vector layers, nd*8 B/vertex) + 72-B hit records
         in_bytes = 2 * nvert * (1 if fused else nd) * 8
@@ -399,9 +399,9 @@ def main():
             "config": {"workload": label, "simplices_per_step_per_gpu": per_step, "layers_resident": NL,
                        "l2": "inputs larger than L2 (each fp64 layer >= 0.5 GB; no flush needed)",
                        "parallelism": f"time-slab x{world}" if world > 1 else "single GPU",
-                       "step": "one advance_timestep: gradient + min|v| + exact sign early-out (fused scan kernel) + per-simplex test kernel" if nd == 2 else
+                       "step": "one advance_timestep: gradient + min|v| + exact sign early-out (fused scan kernel) + per-simplex test kernel" if fused else
                                "one advance_timestep: derive(gradient+resolution) + scan + per-simplex test"},
-            "roofline": {"bound": "hbm", "kernel": "scan2d_fused_kernel<true,true>" if nd == 2 else "scan3d_kernel<true>",
+            "roofline": {"bound": "hbm", "kernel": "scan2d_tile_kernel<true>" if nd == 2 else ("scan3d_fused_kernel<true>" if fused else "scan3d_kernel<true>"),
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": scan_ms,
                          "launches_timed": nscan, "sweeps_repeated": int(st["sweeps_repeated"]),

@@ -55,11 +55,12 @@ struct ftkb_ctx {
   int next_slot = 0;
   int sm_count = 148;
   int scan_mode = 2;             // FTKB_SCAN=ldg|warp|tile selects the fused scan's staging (A/B measurements); default tile
+  bool fused3d = false;          // 3D scalar input: gradient fused into the scan (TMA-staged); FTKB_SCAN3D=plain materialises the gradient instead
 
   // device scalars: [0..7] per-layer resolution bits, [8] worklist count, [9] point count, [10] unique count
   unsigned long long *d_scalars = nullptr;
   unsigned long long *h_scalars = nullptr;     // pinned mirror
-  static constexpr int SLOT_WL = 8, SLOT_PT = 9, SLOT_UQ = 10, NSLOTS = 16;
+  static constexpr int SLOT_WL = 8, SLOT_PT = 9, SLOT_UQ = 10, SLOT_POISON = 11, NSLOTS = 16;
 
   unsigned long long *d_wl = nullptr;
   uint64_t wl_cap = 0, last_wl = 0;
@@ -170,6 +171,12 @@ extern "C" int ftkb_create(const ftkb_config *cfg, ftkb_ctx **out) {
   c->cfg = *cfg;
   c->sm_count = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : 148;
   if (const char *e = std::getenv("FTKB_SCAN")) c->scan_mode = std::string(e) == "ldg" ? 0 : (std::string(e) == "warp" ? 1 : 2);
+  {
+    // the fused 3D scan needs TMA-compatible rows (W even) and the exact early-out (robust detection on)
+    const char *e = std::getenv("FTKB_SCAN3D");
+    c->fused3d = n == 3 && cfg->vector_source == FTKB_SOURCE_DERIVED && cfg->robust_detection && cfg->dims[0] % 2 == 0 &&
+                 !(e && std::string(e) == "plain");
+  }
   c->n = n;
   c->nvert = (size_t)cfg->dims[0] * cfg->dims[1] * (n == 3 ? cfg->dims[2] : 1);
   c->ncore = 1;
@@ -228,8 +235,8 @@ static int derive_layer(ftkb_ctx *c, Layer &l) {
   // bit patterns of |v| works unchanged and "nothing found" reads back as DBL_MAX (slot_value)
   CK(cudaMemsetAsync(c->d_scalars + l.slot, 0xff, sizeof(unsigned long long), c->stream));
   bool fused = false;
-  if (!l.V && c->cfg.vector_source == FTKB_SOURCE_DERIVED && l.S && c->n == 2) {
-    // 2D: the gradient is never materialised; the fused scan derives it on the fly and computes this
+  if (!l.V && c->cfg.vector_source == FTKB_SOURCE_DERIVED && l.S && (c->n == 2 || (c->fused3d && (uintptr_t)l.S % 16 == 0))) {
+    // the gradient is never materialised; the fused scan derives it on the fly and computes this
     // layer's resolution during the first sweep that reads it
     l.res_pending = true;
     return check_launch(c, "derive");
@@ -400,6 +407,42 @@ static void fused2d_decomposition(const ftkb_ctx *c, SweepParams &p) {
   p.nsz = 1;
 }
 
+// tiles x z chunks of the fused 3D scan: about two equal waves of CTAs (one CTA per SM)
+static void fused3d_decomposition(const ftkb_ctx *c, SweepParams &p) {
+  p.nsx = (p.W + F3_STRIDE - 1) / F3_STRIDE;
+  p.nsy = (p.H + F3_TROWS - 1) / F3_TROWS;
+  const int64_t tiles = (int64_t)p.nsx * p.nsy;
+  int64_t nsz = std::max<int64_t>(1, (2 * (int64_t)c->sm_count) / tiles);
+  nsz = std::min<int64_t>(nsz, std::max(1, p.D / 8));
+  p.rows = (int)((p.D + nsz - 1) / nsz);
+  p.nsz = (p.D + p.rows - 1) / p.rows;
+}
+
+// a resident layer of the fused 3D path gets its gradient materialised after all (non-finite or huge scalars)
+static int materialise_gradient(ftkb_ctx *c, Layer &l) {
+  if (l.V || !l.S) return FTKB_OK;
+  CK(cudaMemsetAsync(c->d_scalars + l.slot, 0xff, sizeof(unsigned long long), c->stream));
+  int rc = take_buffer(c, c->freeV, c->nvert * c->n, &l.V);
+  if (rc) return rc;
+  l.ownV = true;
+  launch_gradient(c->n, l.S, l.V, c->cfg.dims[0], c->cfg.dims[1], c->n == 3 ? c->cfg.dims[2] : 1, c->d_scalars + l.slot, c->stream);
+  c->stats.kernel_launches++;
+  l.res_pending = false;
+  CK(cudaMemcpyAsync(c->h_scalars + l.slot, c->d_scalars + l.slot, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+  c->stats.d2h_bytes += 8;
+  return check_launch(c, "gradient");
+}
+
+static int abandon_fused3d(ftkb_ctx *c) {
+  c->fused3d = false;
+  for (Layer &l : c->layers) {
+    const int rc = materialise_gradient(c, l);
+    if (rc) return rc;
+  }
+  CK(cudaStreamSynchronize(c->stream));
+  return FTKB_OK;
+}
+
 static bool rows_aligned16(const ftkb_ctx *c, const double *a, const double *b) {
   return (c->cfg.dims[0] % 2 == 0) && ((uintptr_t)a % 16 == 0) && (!b || (uintptr_t)b % 16 == 0);
 }
@@ -417,6 +460,25 @@ static int resolve_pending(ftkb_ctx *c, Layer &l) {
   p.res_slot[0] = c->d_scalars + l.slot;
   p.wl_count = c->d_scalars + ftkb_ctx::SLOT_WL;
   p.wl = c->d_wl; p.wl_cap = 0;
+  if (c->n == 3) {
+    p.nbits = 8;
+    p.poison = c->d_scalars + ftkb_ctx::SLOT_POISON;
+    if (!encode_scalar_tmap3d(l.S, p.W, p.H, p.D, &p.tmap[0])) { c->fused3d = false; return materialise_gradient(c, l); }
+    p.tmap[1] = p.tmap[0];
+    CK(cudaMemsetAsync(p.poison, 0, sizeof(unsigned long long), c->stream));
+    fused3d_decomposition(c, p);
+    launch_scan(p, c->stream);
+    c->stats.kernel_launches++;
+    CK(cudaMemcpyAsync(c->h_scalars + l.slot, c->d_scalars + l.slot, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(c->h_scalars + ftkb_ctx::SLOT_POISON, p.poison, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    c->stats.d2h_bytes += 16;
+    int rc = check_launch(c, "resolution (fused 3D)");
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(c->stream));
+    l.res_pending = false;
+    if (c->h_scalars[ftkb_ctx::SLOT_POISON]) return abandon_fused3d(c);
+    return FTKB_OK;
+  }
   fused2d_decomposition(c, p);
   launch_scan(p, c->stream);
   c->stats.kernel_launches++;
@@ -430,7 +492,21 @@ static int resolve_pending(ftkb_ctx *c, Layer &l) {
 extern "C" int ftkb_update_timestep(ftkb_ctx *c) {
   if (!c) return FTKB_ERR_INVALID;
   if (c->layers.empty()) return fail(c, FTKB_ERR_INVALID, "update_timestep: no snapshot has been pushed");
-  const bool fused = c->n == 2 && !c->layers[0].V && c->layers[0].S && c->cfg.vector_source == FTKB_SOURCE_DERIVED;
+  CK(cudaSetDevice(c->cfg.device));
+  if (c->n == 3 && c->fused3d && c->cfg.vector_source == FTKB_SOURCE_DERIVED) {
+    // a layer whose pointer TMA cannot take was materialised at push time: the sweep cannot mix the two forms
+    bool anyV = false, anyS = false;
+    for (const Layer &l : c->layers) { anyV = anyV || l.V; anyS = anyS || (!l.V && l.S); }
+    if (anyV && anyS) c->fused3d = false;
+  }
+  if (c->n == 3 && !c->fused3d) {
+    // layers pushed while the fused 3D path was still on (it was abandoned since): materialise their gradient
+    bool any = false;
+    for (Layer &l : c->layers)
+      if (!l.V && l.S && c->cfg.vector_source == FTKB_SOURCE_DERIVED) { const int rc = materialise_gradient(c, l); if (rc) return rc; any = true; }
+    if (any) CK(cudaStreamSynchronize(c->stream));
+  }
+  const bool fused = !c->layers[0].V && c->layers[0].S && c->cfg.vector_source == FTKB_SOURCE_DERIVED && (c->n == 2 || c->fused3d);
   if (!c->layers[0].V && !fused) return fail(c, FTKB_ERR_INVALID, "update_timestep: the snapshot has no vector field");
   if (c->current_timestep + 1 >= (1 << KEY_TIME_BITS)) return fail(c, FTKB_ERR_OVERFLOW, "update_timestep: timestep exceeds the element id range");
   CK(cudaSetDevice(c->cfg.device));
@@ -471,7 +547,14 @@ extern "C" int ftkb_update_timestep(ftkb_ctx *c) {
   for (int k = 0; k < 2; k++) { p.L[k].S = lay[k]->S; p.L[k].V = lay[k]->V; p.L[k].J = lay[k]->J; }
   if (has_next && p.scalar_source != FTKB_SOURCE_NONE && !c->layers[1].S) return fail(c, FTKB_ERR_INVALID, "update_timestep: the next snapshot has no scalar field");
   p.fused = fused;
-  if (fused) {
+  p.poison = c->d_scalars + ftkb_ctx::SLOT_POISON;
+  if (fused && c->n == 3) {
+    if (!encode_scalar_tmap3d(lay[0]->S, p.W, p.H, p.D, &p.tmap[0]) || !encode_scalar_tmap3d(lay[1]->S, p.W, p.H, p.D, &p.tmap[1])) {
+      const int rc = abandon_fused3d(c);      // no TMA descriptor (driver entry point or alignment): unfused path
+      return rc ? rc : ftkb_update_timestep(c);
+    }
+    fused3d_decomposition(c, p);
+  } else if (fused) {
     p.aligned16 = rows_aligned16(c, lay[0]->S, lay[1]->S);
     fused2d_decomposition(c, p);
   } else {
@@ -504,7 +587,9 @@ extern "C" int ftkb_update_timestep(ftkb_ctx *c) {
     p.pts = c->d_pts; p.pt_cap = c->pt_cap;
     c->h_scalars[ftkb_ctx::SLOT_WL] = 0;
     c->h_scalars[ftkb_ctx::SLOT_PT] = c->npts;
-    CK(cudaMemcpyAsync(c->d_scalars + ftkb_ctx::SLOT_WL, c->h_scalars + ftkb_ctx::SLOT_WL, 16, cudaMemcpyHostToDevice, c->stream));
+    c->h_scalars[ftkb_ctx::SLOT_UQ] = 0;
+    c->h_scalars[ftkb_ctx::SLOT_POISON] = 0;
+    CK(cudaMemcpyAsync(c->d_scalars + ftkb_ctx::SLOT_WL, c->h_scalars + ftkb_ctx::SLOT_WL, 32, cudaMemcpyHostToDevice, c->stream));
     CK(cudaEventRecord(c->ev[0], c->stream));
     launch_scan(p, c->stream);
     CK(cudaEventRecord(c->ev[1], c->stream));
@@ -513,13 +598,19 @@ extern "C" int ftkb_update_timestep(ftkb_ctx *c) {
     c->stats.kernel_launches += 2;
     int rc = check_launch(c, "sweep");
     if (rc) return rc;
-    CK(cudaMemcpyAsync(c->h_scalars + ftkb_ctx::SLOT_WL, c->d_scalars + ftkb_ctx::SLOT_WL, 16, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(c->h_scalars + ftkb_ctx::SLOT_WL, c->d_scalars + ftkb_ctx::SLOT_WL, 32, cudaMemcpyDeviceToHost, c->stream));
     if (pending) {   // slots 0..7 hold the per-layer resolutions
       CK(cudaMemcpyAsync(c->h_scalars, c->d_scalars, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
       c->stats.d2h_bytes += 64;
     }
     CK(cudaStreamSynchronize(c->stream));
-    c->stats.d2h_bytes += 16;
+    c->stats.d2h_bytes += 32;
+    if (fused && c->n == 3 && c->h_scalars[ftkb_ctx::SLOT_POISON]) {
+      // a scalar was NaN / Inf / >= 2^1000: the fused scan's keys cannot bracket such values; redo the step unfused
+      c->stats.sweeps_repeated++;
+      const int rc2 = abandon_fused3d(c);
+      return rc2 ? rc2 : ftkb_update_timestep(c);
+    }
     float ms_scan = 0, ms_test = 0;
     CK(cudaEventElapsedTime(&ms_scan, c->ev[0], c->ev[1]));
     CK(cudaEventElapsedTime(&ms_test, c->ev[1], c->ev[2]));

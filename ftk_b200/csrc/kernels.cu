@@ -861,6 +861,316 @@ __global__ void __launch_bounds__((TL_CW + 1) * 32, 3) scan2d_tile_kernel(const 
   else fused2d_tile_strip<HAS_NEXT, false>(p, c0, r0, r1, lane, tile, full0, empty0);
 }
 
+// ---- 3D, scalar input: gradient (grad.hh:130-149) fused into the scan, planes staged by TMA -----------
+// The vector field is never materialised.  A CTA owns a tile of F3_STRIDE x F3_TROWS corner columns and
+// marches along z over a chunk of planes.  One producer warp keeps a ring of F3_NST scalar planes (both
+// layers, tile + halo) in shared memory with cp.async.bulk.tensor (TMA tile mode, one 3D box per layer and
+// plane, out-of-bounds elements zero-filled, completion on a `full` mbarrier); eight consumer warps read
+// planes z-1, z, z+1, release plane z-1 through an `empty` mbarrier and never synchronise with each other.
+//
+// gradient3D is 1/2 (S[+1] - S[-1]) on the array interior and zero on its border, so the quantised value
+// trunc(v 2^nbits) is trunc(d 2^(nbits-1)) with d the plain difference: scaling by a power of two is exact,
+// and the HIGH WORD of the fp64 difference, reinterpreted as an fp32 bit pattern, is a monotone key of d
+// (sign-magnitude order; truncated towards zero).  The kernel therefore keeps min/max of those keys with
+// FMNMX -- no conversion instruction at all -- and "every vertex >= 1 after quantisation" is the exact
+// comparison key >= key(2^(1-nbits)) because the threshold is a power of two.  NaN keys are the neutral
+// element (FMNMX drops NaN); real NaN / Inf / >= 2^1000 scalars raise p.poison instead and the host
+// repeats the sweep on the unfused path.
+//
+// Exclusion is decided per THREAD first: a lane covers 2 columns x (F3_RW + 1) gradient rows per plane; the
+// union of its values, its right neighbour's and the previous plane's is a superset of the vertices of
+// the lane's 2 x F3_RW cubes, so if the union passes the exclusion test every one of them does.  Lanes whose
+// union fails (near a common zero of all three components) test their cubes one by one from global
+// memory (cold path) and append survivors to the worklist.
+//
+// By-product: min non-zero |v| (ndarray.hh:769-779) of layers whose resolution is still unknown, over the
+// whole array -- tiles cover the array, not only the tracker's domain.
+constexpr int F3_LAYER_BYTES = ((F3_ROWS * F3_COLS * 8 + 127) / 128) * 128;   // one staged plane of one layer
+constexpr int F3_LAYER_DOUBLES = F3_LAYER_BYTES / 8;
+constexpr uint32_t F3_BOX_BYTES = F3_ROWS * F3_COLS * 8;
+constexpr int KEYF_BIG = 0x7E700000;     // high word of 2^1000
+constexpr int KEYF_NAN = 0x7FC00000;
+
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *tm, int c0, int c1, int c2, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+               ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
+}
+
+__device__ __forceinline__ float hikey(double d) { return __int_as_float(__double2hiint(d)); }
+
+// cold path: the lane's cubes (columns e, e+1; rows y0 .. y0+F3_RW-1; plane z) one by one, ranges over the
+// vertices valid simplices can use (<= ub), read from global memory; same key logic as the vector-layer scan
+__device__ __noinline__ void fused3d_slow_cubes(const SweepParams &p, const bool need, const int e, const int y0, const int z, const int nl) {
+  const int nbits20 = (p.nbits - 1) << 20;
+  const size_t sy = (size_t)p.W, sz = (size_t)p.W * (size_t)p.H;
+#pragma unroll 1
+  for (int r = 0; r < F3_RW; r++) {
+    const int y = y0 + r;
+#pragma unroll 1
+    for (int q = 0; q < 2; q++) {
+      const int x = e + q;
+      bool surv = false;
+      if (need && x >= p.lb[0] && x <= p.ub[0] && y >= p.lb[1] && y <= p.ub[1]) {
+        KeyRange rg[3] = {neutral_range(), neutral_range(), neutral_range()};
+#pragma unroll 1
+        for (int v = 0; v < 8; v++) {
+          const int vx = x + (v & 1), vy = y + ((v >> 1) & 1), vz = z + (v >> 2);
+          if (vx > p.ub[0] || vy > p.ub[1] || vz > p.ub[2]) continue;
+          const bool border = vx < 1 || vx > p.W - 2 || vy < 1 || vy > p.H - 2 || vz < 1 || vz > p.D - 2;
+          const size_t idx = (size_t)vx + sy * (size_t)vy + sz * (size_t)vz;
+          for (int L = 0; L < nl; L++) {
+            const double *S = p.L[L].S;
+            int h0 = 0, h1 = 0, h2 = 0;
+            if (!border) {
+              h0 = __double2hiint(__ldg(S + idx + 1) - __ldg(S + idx - 1));
+              h1 = __double2hiint(__ldg(S + idx + sy) - __ldg(S + idx - sy));
+              h2 = __double2hiint(__ldg(S + idx + sz) - __ldg(S + idx - sz));
+            }
+            rg[0] = merge(rg[0], vertex_range(h0, nbits20));
+            rg[1] = merge(rg[1], vertex_range(h1, nbits20));
+            rg[2] = merge(rg[2], vertex_range(h2, nbits20));
+          }
+        }
+        surv = !cube_excluded3(rg[0], rg[1], rg[2]);
+      }
+      append_survivors(p, surv, (u64)(x - p.lb[0]) + (u64)p.nc[0] * ((u64)(y - p.lb[1]) + (u64)p.nc[1] * (u64)(z - p.lb[2])));
+    }
+  }
+}
+
+// exact path of the running min non-zero |v| (v = d / 2): m keeps the signed value of smallest magnitude
+__device__ __forceinline__ void res_update3(double &m, const bool in, const double dx, const double dy, const double dz) {
+  if (!in) return;
+  const double vx = 0.5 * dx, vy = 0.5 * dy, vz = 0.5 * dz;
+  if (vx != 0.0 && fabs(vx) < fabs(m)) m = vx;      // NaN / Inf never compare below
+  if (vy != 0.0 && fabs(vy) < fabs(m)) m = vy;
+  if (vz != 0.0 && fabs(vz) < fabs(m)) m = vz;
+}
+
+// precise exclusion test of a union given as float keys (rare: the exponent bound below failed)
+__device__ __noinline__ bool fused3d_union_excluded_precise(const float mn0, const float mx0, const float mn1, const float mx1,
+                                                            const float mn2, const float mx2, const int nbits20) {
+  const KeyRange x{vertex_range(__float_as_int(mn0), nbits20).mn, vertex_range(__float_as_int(mx0), nbits20).mx};
+  const KeyRange y{vertex_range(__float_as_int(mn1), nbits20).mn, vertex_range(__float_as_int(mx1), nbits20).mx};
+  const KeyRange z{vertex_range(__float_as_int(mn2), nbits20).mn, vertex_range(__float_as_int(mx2), nbits20).mx};
+  return cube_excluded3(x, y, z);
+}
+
+template <bool HAS_NEXT, bool EDGE>
+__device__ __forceinline__ void fused3d_consume(const SweepParams &p, const unsigned char *ring, const uint32_t full0, const uint32_t empty0,
+                                                const int C0, const int Y0, const int zc0, const int zc1, const int wib, const int lane) {
+  constexpr int NL = HAS_NEXT ? 2 : 1;
+  const int W = p.W, H = p.H, D = p.D;
+  const int e = C0 + 2 * lane;                 // this lane's columns: e, e + 1
+  const int y0 = Y0 + wib * F3_RW;             // first corner row of this warp
+  const int tr0 = wib * F3_RW;                 // its row in the staged tile is tr0 + 1 (tile row 0 = Y0 - 1)
+  const float nanf_ = __int_as_float(KEYF_NAN);
+  const float kthr = __int_as_float((1023 + 1 - p.nbits) << 20);    // key of 2^(1-nbits): |d| >= 2^(1-nbits) <=> |quantised v| >= 1
+  const int esum_max = 3119 - 3 * p.nbits;     // exponent bound of the determinant guard (see below)
+  const float kfloor = __int_as_float((1023 - p.nbits) << 20);      // key of 2^-nbits: smaller magnitudes quantise to 0
+  const int nbits20 = (p.nbits - 1) << 20;
+  const bool want_res[2] = {p.res_slot[0] != nullptr, HAS_NEXT && p.res_slot[1] != nullptr};
+  double rmin[2] = {DBL_MAX, DBL_MAX};
+  float rkey[2] = {__int_as_float(0x7F800000), __int_as_float(0x7F800000)};   // key of 2 |rmin|; +Inf (as a float): nothing found yet
+  bool bad = false;
+
+  // EDGE tiles: columns / rows outside the tracker's domain stay out of the ranges (NaN key), vertices on the
+  // array border have a zero gradient, vertices outside the array interior stay out of the resolution
+  bool arr_c[2] = {true, true}, dom_c[2] = {true, true};
+  bool own_any = lane <= 30;
+  if (EDGE) {
+    bool any_col = false;
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+      arr_c[q] = e + q >= 1 && e + q <= W - 2;
+      dom_c[q] = e + q >= p.lb[0] && e + q <= p.ub[0];
+      any_col = any_col || dom_c[q];
+    }
+    own_any = own_any && any_col && y0 <= p.ub[1] && y0 + F3_RW - 1 >= p.lb[1];
+  }
+
+  float pmin[3] = {nanf_, nanf_, nanf_}, pmax[3] = {nanf_, nanf_, nanf_};   // previous plane's union (neighbour lane merged)
+  int st_m = 0, st_c = 1, st_p = 2;            // ring stages of planes zg-1, zg, zg+1
+  uint32_t par_p = 0;                          // parity of the next completion of full[st_p]
+  mbar_wait(full0, 0);
+  mbar_wait(full0 + 8, 0);
+  for (int zg = zc0; zg <= zc1 + 1; zg++) {
+    mbar_wait(full0 + 8u * st_p, par_p);
+    const bool zarr = zg >= 1 && zg <= D - 2;
+    const bool zdom = zg >= p.lb[2] && zg <= p.ub[2];
+    float umin[3] = {nanf_, nanf_, nanf_}, umax[3] = {nanf_, nanf_, nanf_};
+#pragma unroll
+    for (int L = 0; L < NL; L++) {
+      const double *Pc = reinterpret_cast<const double *>(ring + (size_t)st_c * (NL * F3_LAYER_BYTES) + (size_t)L * F3_LAYER_BYTES) + 2 * lane;
+      const double *Pm = reinterpret_cast<const double *>(ring + (size_t)st_m * (NL * F3_LAYER_BYTES) + (size_t)L * F3_LAYER_BYTES) + 2 * lane;
+      const double *Pp = reinterpret_cast<const double *>(ring + (size_t)st_p * (NL * F3_LAYER_BYTES) + (size_t)L * F3_LAYER_BYTES) + 2 * lane;
+      const bool res_now = want_res[L] && zarr;
+      double2 rm = *reinterpret_cast<const double2 *>(Pc + (tr0 + 0) * F3_COLS + 2);
+      double2 rc = *reinterpret_cast<const double2 *>(Pc + (tr0 + 1) * F3_COLS + 2);
+#pragma unroll
+      for (int r = 0; r <= F3_RW; r++) {
+        const int row = tr0 + r + 1;
+        const double2 rp = *reinterpret_cast<const double2 *>(Pc + (row + 1) * F3_COLS + 2);
+        const double left = Pc[row * F3_COLS + 1], right = Pc[row * F3_COLS + 4];
+        const double2 zm = *reinterpret_cast<const double2 *>(Pm + row * F3_COLS + 2);
+        const double2 zp = *reinterpret_cast<const double2 *>(Pp + row * F3_COLS + 2);
+        const double dxe = rc.y - left, dxo = right - rc.x;
+        const double dye = rp.x - rm.x, dyo = rp.y - rm.y;
+        const double dze = zp.x - zm.x, dzo = zp.y - zm.y;
+        float kxe = hikey(dxe), kxo = hikey(dxo), kye = hikey(dye), kyo = hikey(dyo), kze = hikey(dze), kzo = hikey(dzo);
+        bad = bad || !(fabsf(hikey(rc.x)) < __int_as_float(KEYF_BIG)) || !(fabsf(hikey(rc.y)) < __int_as_float(KEYF_BIG));
+        bool in_e = true, in_o = true;
+        if (EDGE) {
+          const int y = y0 + r;
+          const bool arr_y = y >= 1 && y <= H - 2;
+          in_e = arr_c[0] && arr_y; in_o = arr_c[1] && arr_y;
+        }
+        if (res_now) {
+          float a = fminf(fminf(fabsf(kxe), fabsf(kye)), fabsf(kze)), b = fminf(fminf(fabsf(kxo), fabsf(kyo)), fabsf(kzo));
+          if (EDGE) { a = in_e ? a : __int_as_float(0x7F800000); b = in_o ? b : __int_as_float(0x7F800000); }
+          if (fminf(a, b) <= rkey[L]) {
+            res_update3(rmin[L], in_e, dxe, dye, dze);
+            res_update3(rmin[L], in_o, dxo, dyo, dzo);
+            rkey[L] = hikey(2.0 * fabs(rmin[L]));
+          }
+        }
+        if (EDGE) {
+          const int y = y0 + r;
+          const bool dom_y = y >= p.lb[1] && y <= p.ub[1];
+          const int keep_e = (in_e && dom_c[0] && dom_y) ? -1 : 0, fill_e = (dom_c[0] && dom_y) ? 0 : KEYF_NAN;
+          const int keep_o = (in_o && dom_c[1] && dom_y) ? -1 : 0, fill_o = (dom_c[1] && dom_y) ? 0 : KEYF_NAN;
+          kxe = __int_as_float((__float_as_int(kxe) & keep_e) | fill_e); kxo = __int_as_float((__float_as_int(kxo) & keep_o) | fill_o);
+          kye = __int_as_float((__float_as_int(kye) & keep_e) | fill_e); kyo = __int_as_float((__float_as_int(kyo) & keep_o) | fill_o);
+          kze = __int_as_float((__float_as_int(kze) & keep_e) | fill_e); kzo = __int_as_float((__float_as_int(kzo) & keep_o) | fill_o);
+        }
+        umin[0] = fminf(umin[0], fminf(kxe, kxo)); umax[0] = fmaxf(umax[0], fmaxf(kxe, kxo));
+        umin[1] = fminf(umin[1], fminf(kye, kyo)); umax[1] = fmaxf(umax[1], fmaxf(kye, kyo));
+        umin[2] = fminf(umin[2], fminf(kze, kzo)); umax[2] = fmaxf(umax[2], fmaxf(kze, kzo));
+        rm = rc; rc = rp;
+      }
+    }
+    // plane-level masks (warp-uniform): planes outside the domain stay out of the ranges; the array's first and
+    // last plane have a zero gradient
+    if (!zdom || !zarr) {
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        const bool has = zdom && !(umin[c] != umin[c]);     // lanes with no in-domain vertex keep the neutral element
+        umin[c] = has ? 0.f : nanf_; umax[c] = has ? 0.f : nanf_;
+      }
+    }
+    // x neighbour: corner column e+1 also uses the next lane's first column
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      umin[c] = fminf(umin[c], __shfl_down_sync(0xffffffffu, umin[c], 1));
+      umax[c] = fmaxf(umax[c], __shfl_down_sync(0xffffffffu, umax[c], 1));
+    }
+    if (zg > zc0) {
+      const int zc = zg - 1;                     // corner plane decided now (warp-uniform)
+      if (zc >= p.lb[2] && zc <= p.ub[2]) {
+        float cmn[3], cmx[3];
+        bool sided = false;
+        int esum = 0;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+          cmn[c] = fminf(pmin[c], umin[c]); cmx[c] = fmaxf(pmax[c], umax[c]);
+          sided = sided || cmn[c] >= kthr || cmx[c] <= -kthr;
+          esum += (__float_as_int(fmaxf(fmaxf(fabsf(cmn[c]), fabsf(cmx[c])), kfloor)) >> 20);
+        }
+        // determinant guard, exponent form: with e_c the biased exponent of max |d_c| (at least that of 2^-nbits),
+        // |quantised v_c| < 2^(e_c - 1023 + nbits) and M_c := |quantised| + 1 <= 2^(e_c - 1022 + nbits).  Every determinant of the
+        // cascade is at most 48 Mx My Mz (cube_excluded3 with R <= 2 M) < 2^(6 + sum(e_c) - 3066 + 3 nbits), which stays
+        // below 2^62 for sum(e_c) <= 3119 - 3 nbits.
+        // A NaN union (no vertex) or Inf fails the bound and takes the precise / cold path.
+        bool excl = sided && esum <= esum_max && !(cmn[0] != cmn[0]);
+        if (sided && !excl && own_any) excl = fused3d_union_excluded_precise(cmn[0], cmx[0], cmn[1], cmx[1], cmn[2], cmx[2], nbits20);
+        const bool fail = own_any && !excl;
+        if (__any_sync(0xffffffffu, fail)) fused3d_slow_cubes(p, fail, e, y0, zc, NL);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; c++) { pmin[c] = umin[c]; pmax[c] = umax[c]; }
+    // plane zg-1 is dead for this warp
+    __syncwarp();
+    if (elect_one()) mbar_arrive(empty0 + 8u * st_m);
+    st_m = st_c; st_c = st_p;
+    st_p = st_p + 1 == F3_NST ? 0 : st_p + 1;
+    if (st_p == 0) par_p ^= 1u;
+  }
+#pragma unroll
+  for (int L = 0; L < NL; L++)
+    if (want_res[L]) warp_res_commit(fabs(rmin[L]), p.res_slot[L]);
+  if (bad) atomicExch(p.poison, 1ull);
+}
+
+template <bool HAS_NEXT>
+__global__ void __launch_bounds__((F3_CW + 1) * 32, 1) scan3d_fused_kernel(const __grid_constant__ SweepParams p) {
+  constexpr int NL = HAS_NEXT ? 2 : 1;
+  constexpr uint32_t STAGE_BYTES = NL * F3_LAYER_BYTES;
+  extern __shared__ __align__(128) unsigned char fb_smem[];
+  const int lane = threadIdx.x & 31;
+  const int wib = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);     // warp-uniform by construction
+  const uint32_t ring_u32 = smem_u32(fb_smem);
+  const uint32_t full0 = ring_u32 + (uint32_t)F3_NST * STAGE_BYTES, empty0 = full0 + 8u * F3_NST;
+  int b = blockIdx.x;
+  const int bx = b % p.nsx; b /= p.nsx;
+  const int by = b % p.nsy;
+  const int bz = b / p.nsy;
+  const int C0 = bx * F3_STRIDE, Y0 = by * F3_TROWS;
+  const int zc0 = bz * p.rows, zc1 = min(zc0 + p.rows - 1, p.D - 1);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int q = 0; q < F3_NST; q++) { mbar_init(full0 + 8u * q, 1); mbar_init(empty0 + 8u * q, F3_CW); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  if (wib == F3_CW) {
+    // producer: scalar planes zc0-1 .. zc1+2 of every layer, one TMA box (tile + halo) each
+    if (elect_one()) {
+      const int nplanes = zc1 - zc0 + 4;
+      for (int s = 0; s < nplanes; s++) {
+        const int st = s % F3_NST;
+        if (s >= F3_NST) mbar_wait(empty0 + 8u * st, (uint32_t)((s / F3_NST - 1) & 1));
+        mbar_expect_tx(full0 + 8u * st, F3_BOX_BYTES * NL);
+#pragma unroll
+        for (int L = 0; L < NL; L++)
+          tma_load_3d(ring_u32 + (uint32_t)st * STAGE_BYTES + (uint32_t)L * F3_LAYER_BYTES, &p.tmap[L], C0 - 2, Y0 - 1, zc0 - 1 + s, full0 + 8u * st);
+      }
+    }
+    return;
+  }
+  // tiles whose 64 x (TROWS + 1) gradient vertices all lie in the array interior and in the tracker's domain skip the masks
+  const bool interior = C0 >= max(1, p.lb[0]) && C0 + 63 <= min(p.W - 2, p.ub[0]) && Y0 >= max(1, p.lb[1]) && Y0 + F3_TROWS <= min(p.H - 2, p.ub[1]);
+  if (interior) fused3d_consume<HAS_NEXT, false>(p, fb_smem, full0, empty0, C0, Y0, zc0, zc1, wib, lane);
+  else fused3d_consume<HAS_NEXT, true>(p, fb_smem, full0, empty0, C0, Y0, zc0, zc1, wib, lane);
+}
+
+static size_t fused3d_smem_bytes(bool has_next) {
+  return (size_t)F3_NST * (has_next ? 2 : 1) * F3_LAYER_BYTES + (size_t)2 * F3_NST * 8;
+}
+
+typedef CUresult (*TmapEncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                 const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+bool encode_scalar_tmap3d(const double *S, int W, int H, int D, CUtensorMap *out) {
+  static TmapEncodeFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void *ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<TmapEncodeFn>(ptr);
+    else cudaGetLastError();
+  }
+  if (!fn || (W & 1) || ((uintptr_t)S & 15)) return false;     // strides must be multiples of 16 B
+  const cuuint64_t gdim[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D};
+  const cuuint64_t gstride[2] = {(cuuint64_t)W * 8, (cuuint64_t)W * (cuuint64_t)H * 8};
+  const cuuint32_t box[3] = {F3_COLS, F3_ROWS, 1}, estr[3] = {1, 1, 1};
+  return fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double *>(S), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 static size_t tile_smem_bytes(bool has_next) {
   return (size_t)TL_NST * (has_next ? 2 : 1) * TL_SEG * 8 + (size_t)2 * TL_NST * 8;
 }
@@ -874,6 +1184,8 @@ void init_kernel_attributes() {
   cudaFuncSetAttribute(scan2d_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem_bytes(false));
   cudaFuncSetAttribute(scan2d_bulk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bulk_smem_bytes(true));
   cudaFuncSetAttribute(scan2d_bulk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bulk_smem_bytes(false));
+  cudaFuncSetAttribute(scan3d_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused3d_smem_bytes(true));
+  cudaFuncSetAttribute(scan3d_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused3d_smem_bytes(false));
 }
 
 void launch_scan(const SweepParams &p, cudaStream_t s) {
@@ -897,6 +1209,10 @@ void launch_scan(const SweepParams &p, cudaStream_t s) {
       if (p.aligned16) scan2d_fused_kernel<false, true><<<grid, wpb * 32, 0, s>>>(p);
       else scan2d_fused_kernel<false, false><<<grid, wpb * 32, 0, s>>>(p);
     }
+  } else if (p.nd == 3 && p.fused) {
+    const unsigned grid = (unsigned)((i64)p.nsx * p.nsy * p.nsz);
+    if (p.has_next) scan3d_fused_kernel<true><<<grid, (F3_CW + 1) * 32, fused3d_smem_bytes(true), s>>>(p);
+    else scan3d_fused_kernel<false><<<grid, (F3_CW + 1) * 32, fused3d_smem_bytes(false), s>>>(p);
   } else if (p.nd == 2) {
     const i64 warps = (i64)p.nsx * p.nsy;
     const int wpb = 8;

@@ -1,5 +1,6 @@
 // Kernel parameter blocks and launchers (host-callable).  Device code lives in kernels.cu.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <cstdint>
 
@@ -39,6 +40,9 @@ struct SweepParams {
   float thr2_f;               // 2^(1-nbits)
   float lim_f;                // 0.999 * 4.5e18 / factor^2 (determinant magnitude bound, field units)
   unsigned long long *res_slot[2];   // non-null: accumulate min non-zero |v| of that layer during the scan
+  unsigned long long *poison;        // fused 3D scan: set non-zero when a scalar is NaN / Inf / >= 2^1000 (the sweep is redone unfused)
+  // fused 3D scan: TMA descriptors of the two scalar layers (box = one tile plane incl. halo)
+  alignas(64) CUtensorMap tmap[2];
   // scan decomposition
   int32_t nsx;                // x strips (31 corners each)
   int32_t nsy;                // 2D: row chunks; 3D: y tiles (BY-1 corners each)
@@ -56,6 +60,18 @@ struct SweepParams {
 
 void upload_mesh_tables(const DeviceMeshTables &t2, const DeviceMeshTables &t3);
 void init_kernel_attributes();   // opt-in shared memory sizes; once per device
+
+// fused 3D scan geometry (host needs it for the grid decomposition and the TMA box)
+constexpr int F3_CW = 8;                       // consumer warps per CTA
+constexpr int F3_RW = 4;                       // corner rows per consumer warp
+constexpr int F3_NST = 5;                      // ring stages (scalar planes)
+constexpr int F3_STRIDE = 62;                  // corner columns per tile
+constexpr int F3_COLS = 68;                    // staged columns: C0-2 .. C0+65
+constexpr int F3_TROWS = F3_CW * F3_RW;        // corner rows per tile
+constexpr int F3_ROWS = F3_TROWS + 3;          // staged rows: Y0-1 .. Y0+TROWS+1
+// encode the TMA descriptor of one scalar layer (W,H,D) fp64 for the fused 3D scan; false if the driver
+// entry point is unavailable or the layer does not meet TMA's alignment rules
+bool encode_scalar_tmap3d(const double *S, int W, int H, int D, CUtensorMap *out);
 
 void launch_scan(const SweepParams &p, cudaStream_t s);
 // thread-per-(surviving cube, type) exact test; grid sized for `expected` cubes, grid-stride otherwise

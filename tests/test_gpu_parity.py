@@ -91,6 +91,14 @@ CASES = [
     ([8, 7, 6], 3, "vector", "normal", {"lb": [0, 0, 0], "ub": [7, 6, 5]}),
     ([36, 20, 5], 2, "vector", "smooth", {}),                                    # several x/y tiles
     ([7, 6, 40], 2, "scalar", "smooth", {}),                                     # several z chunks
+    # fused 3D scan (even W: gradient derived inside the TMA-staged scan kernel)
+    ([132, 70, 9], 2, "scalar", "smooth", {}),                                   # interior + edge tiles, 3 x strips, 3 y tiles
+    ([14, 12, 10], 3, "scalar", "int", {}),                                      # ties and exact zeros
+    ([20, 40, 30], 2, "scalar", "normal", {}),                                   # noise: every lane takes the per-cube path
+    ([64, 36, 20], 2, "scalar", "smooth", {"lb": [0, 0, 0], "ub": [63, 35, 19]}),  # domain = whole array (zero-gradient border)
+    ([66, 34, 12], 2, "scalar", "smooth", {"lb": [5, 3, 2], "ub": [60, 33, 7]}),
+    ([16, 12, 60], 2, "scalar", "smooth", {}),                                   # z chunks
+    ([64, 10, 8], 3, "scalar", "smooth", {"start_timestep": 3}),
 ]
 
 
@@ -109,6 +117,48 @@ def test_cuda_matches_oracle_random(case, ftk, oracle):
     assert np.array_equal(c.get_degrees(), o.degrees())
     assert c.stats()["scaling_factor"] == o.scaling_factor
     c.close()
+
+
+def test_fused_3d_scan_non_finite_scalars_fall_back(ftk, oracle):
+    """NaN / Inf / huge scalars cannot be bracketed by the fused 3D scan's keys: it raises its poison flag and
+    the step is redone on the unfused path -- results still match the oracle"""
+    rng = np.random.default_rng(314)
+    dims, T = [16, 14, 12], 3
+    snaps = _rand_series(rng, dims, T, 1, "smooth")
+    snaps[1][5, 6, 7] = np.nan
+    snaps[1][3, 3, 3] = np.inf
+    snaps[2][8, 9, 10] = 1e305
+    c, o = _both(ftk, oracle, snaps, dims, "scalar")
+    P.assert_same_result(cuda_result(c), P.oracle_result(o), tol=TOL, what="non-finite 3D scalars")
+    assert c.stats()["sweeps_repeated"] >= 1
+    c.close()
+
+
+def test_fused_3d_scan_equals_unfused(ftk, monkeypatch):
+    """FTKB_SCAN3D=plain materialises the gradient and runs the vector-layer scan: same points, same
+    trajectories, same quantisation factor as the fused scan, and the fused worklist is a superset filter"""
+    rng = np.random.default_rng(2718)
+    dims, T = [130, 68, 10], 3
+    snaps = _rand_series(rng, dims, T, 1, "smooth")
+    a = ftk.track(snaps, dims, field="scalar")
+    monkeypatch.setenv("FTKB_SCAN3D", "plain")
+    b = ftk.track(snaps, dims, field="scalar")
+    monkeypatch.delenv("FTKB_SCAN3D")
+    pa, pb = a.get_discrete_critical_points(), b.get_discrete_critical_points()
+    assert len(pa) > 0 and np.array_equal(pa, pb)
+    assert P.canonical_trajectories(a.get_trajectory_index()) == P.canonical_trajectories(b.get_trajectory_index())
+    sa, sb = a.stats(), b.stats()
+    assert sa["scaling_factor"] == sb["scaling_factor"] and sa["resolution"] == sb["resolution"]
+    assert sa["ms_derive"] == 0.0 and sb["ms_derive"] > 0.0          # the fused path never launches the gradient kernel
+    # every punctured simplex's cube is in the fused scan's worklist (last sweep: ordinal simplices at T-1)
+    wl = set(int(v) for v in a.get_last_worklist())
+    last = pa[(pa["timestep"] == T - 1)]
+    nc = [d - 3 for d in dims]
+    for q in last:
+        cx, cy, cz = int(q["corner"][0]) - 2, int(q["corner"][1]) - 2, int(q["corner"][2]) - 2
+        assert cx + nc[0] * (cy + nc[1] * cz) in wl
+    a.close()
+    b.close()
 
 
 def test_given_jacobian_and_scalar(ftk, oracle):
