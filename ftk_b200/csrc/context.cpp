@@ -31,6 +31,8 @@ struct Layer {
   bool ownS = false, ownV = false, ownJ = false;
   int slot = 0;                  // resolution slot
   bool res_pending = false;      // min non-zero |v| not computed yet: the fused scan produces it
+  uint4 *cells = nullptr;        // fused 3D scan: this layer's range cells (kernels.cu, "range summaries")
+  bool cells_valid = false;
 };
 
 }  // namespace
@@ -55,6 +57,9 @@ struct ftkb_ctx {
   int next_slot = 0;
   int sm_count = 148;
   int scan_mode = 2;             // FTKB_SCAN=ldg|warp|tile selects the fused scan's staging (A/B measurements); default tile
+  bool cells3d = true;           // fused 3D scan streams each layer once and keeps its range cells; FTKB_SCAN3D=twolayer re-reads both layers every step
+  std::vector<uint4 *> freeCells;
+  size_t ncells = 0;             // cells per layer (fixed by the dims)
   bool fused3d = false;          // 3D scalar input: gradient fused into the scan (TMA-staged); FTKB_SCAN3D=plain materialises the gradient instead
 
   // device scalars: [0..7] per-layer resolution bits, [8] worklist count, [9] point count, [10] unique count
@@ -122,6 +127,7 @@ static void release_layer(ftkb_ctx *c, Layer &l) {
   if (l.ownS && l.S) c->freeS.push_back(l.S);
   if (l.ownV && l.V) c->freeV.push_back(l.V);
   if (l.ownJ && l.J) c->freeJ.push_back(l.J);
+  if (l.cells) c->freeCells.push_back(l.cells);
   l = Layer();
 }
 
@@ -133,6 +139,7 @@ extern "C" void ftkb_destroy(ftkb_ctx *c) {
   for (auto *p : c->freeS) cudaFree(p);
   for (auto *p : c->freeV) cudaFree(p);
   for (auto *p : c->freeJ) cudaFree(p);
+  for (auto *p : c->freeCells) cudaFree(p);
   cudaFree(c->d_scalars);
   if (c->h_scalars) cudaFreeHost(c->h_scalars);
   cudaFree(c->d_wl);
@@ -176,6 +183,7 @@ extern "C" int ftkb_create(const ftkb_config *cfg, ftkb_ctx **out) {
     const char *e = std::getenv("FTKB_SCAN3D");
     c->fused3d = n == 3 && cfg->vector_source == FTKB_SOURCE_DERIVED && cfg->robust_detection && cfg->dims[0] % 2 == 0 &&
                  !(e && std::string(e) == "plain");
+    c->cells3d = !(e && std::string(e) == "twolayer");
   }
   c->n = n;
   c->nvert = (size_t)cfg->dims[0] * cfg->dims[1] * (n == 3 ? cfg->dims[2] : 1);
@@ -412,10 +420,32 @@ static void fused3d_decomposition(const ftkb_ctx *c, SweepParams &p) {
   p.nsx = (p.W + F3_STRIDE - 1) / F3_STRIDE;
   p.nsy = (p.H + F3_TROWS - 1) / F3_TROWS;
   const int64_t tiles = (int64_t)p.nsx * p.nsy;
+  if (c->cells3d) {
+    // two CTAs per SM; pick the z split whose (waves of CTAs) x (planes per CTA incl. the 3 halo planes) is smallest
+    const int64_t slots = 2 * (int64_t)c->sm_count;
+    int64_t best = 1, best_cost = INT64_MAX;
+    for (int64_t nsz = 1; nsz <= std::max(1, p.D / 16); nsz++) {
+      const int64_t rows = (p.D + nsz - 1) / nsz, chunks = (p.D + rows - 1) / rows;
+      const int64_t cost = ((tiles * chunks + slots - 1) / slots) * (rows + 3);
+      if (cost < best_cost) { best_cost = cost; best = nsz; }
+    }
+    p.rows = (int)((p.D + best - 1) / best);
+    if (const char *e = std::getenv("FTKB_S3_ROWS")) p.rows = std::max(1, std::min(p.D, std::atoi(e)));   // A/B measurements
+    p.nsz = (p.D + p.rows - 1) / p.rows;
+    return;
+  }
   int64_t nsz = std::max<int64_t>(1, (2 * (int64_t)c->sm_count) / tiles);
   nsz = std::min<int64_t>(nsz, std::max(1, p.D / 8));
   p.rows = (int)((p.D + nsz - 1) / nsz);
   p.nsz = (p.D + p.rows - 1) / p.rows;
+}
+
+static int ensure_cells(ftkb_ctx *c, Layer &l, const SweepParams &p) {
+  if (l.cells) return FTKB_OK;
+  if (!c->ncells) c->ncells = scan3d_cells_per_layer(p);
+  if (!c->freeCells.empty()) { l.cells = c->freeCells.back(); c->freeCells.pop_back(); return FTKB_OK; }
+  CK(cudaMalloc(&l.cells, sizeof(uint4) * c->ncells));
+  return FTKB_OK;
 }
 
 // a resident layer of the fused 3D path gets its gradient materialised after all (non-finite or huge scalars)
@@ -425,6 +455,7 @@ static int materialise_gradient(ftkb_ctx *c, Layer &l) {
   int rc = take_buffer(c, c->freeV, c->nvert * c->n, &l.V);
   if (rc) return rc;
   l.ownV = true;
+  l.cells_valid = false;
   launch_gradient(c->n, l.S, l.V, c->cfg.dims[0], c->cfg.dims[1], c->n == 3 ? c->cfg.dims[2] : 1, c->d_scalars + l.slot, c->stream);
   c->stats.kernel_launches++;
   l.res_pending = false;
@@ -467,7 +498,17 @@ static int resolve_pending(ftkb_ctx *c, Layer &l) {
     p.tmap[1] = p.tmap[0];
     CK(cudaMemsetAsync(p.poison, 0, sizeof(unsigned long long), c->stream));
     fused3d_decomposition(c, p);
-    launch_scan(p, c->stream);
+    if (c->cells3d) {
+      // stream the layer once: its range cells (with the real domain masks) and min |v|; no cube is tested
+      fill_sweep_geometry(c, p);
+      int rc = ensure_cells(c, l, p);
+      if (rc) return rc;
+      p.sum_mode = SUM_BUILD; p.build_layer = 0; p.sum_out = l.cells;
+      launch_scan3d_cells(p, c->stream);
+      l.cells_valid = true;
+    } else {
+      launch_scan(p, c->stream);
+    }
     c->stats.kernel_launches++;
     CK(cudaMemcpyAsync(c->h_scalars + l.slot, c->d_scalars + l.slot, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaMemcpyAsync(c->h_scalars + ftkb_ctx::SLOT_POISON, p.poison, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
@@ -591,7 +632,33 @@ extern "C" int ftkb_update_timestep(ftkb_ctx *c) {
     c->h_scalars[ftkb_ctx::SLOT_POISON] = 0;
     CK(cudaMemcpyAsync(c->d_scalars + ftkb_ctx::SLOT_WL, c->h_scalars + ftkb_ctx::SLOT_WL, 32, cudaMemcpyHostToDevice, c->stream));
     CK(cudaEventRecord(c->ev[0], c->stream));
-    launch_scan(p, c->stream);
+    if (fused && c->n == 3 && c->cells3d) {
+      // each layer is streamed once (the step that first sees it); everything else reads its 16-byte range cells
+      int rc0 = ensure_cells(c, *lay[0], p);
+      if (!rc0 && has_next) rc0 = ensure_cells(c, *lay[1], p);
+      if (rc0) return rc0;
+      p.sum_in[0] = lay[0]->cells; p.sum_in[1] = lay[1]->cells;
+      if (!lay[0]->cells_valid) {
+        p.sum_mode = has_next ? SUM_BUILD : SUM_BUILD_TEST1; p.build_layer = 0; p.sum_out = lay[0]->cells;
+        launch_scan3d_cells(p, c->stream);
+        lay[0]->cells_valid = true;
+        if (has_next) {
+          c->stats.kernel_launches++;       // the very first step streams two layers
+          p.sum_mode = lay[1]->cells_valid ? SUM_TEST2 : SUM_BUILD_TEST2; p.build_layer = 1; p.sum_out = lay[1]->cells;
+          launch_scan3d_cells(p, c->stream);
+          lay[1]->cells_valid = true;
+        }
+      } else if (has_next && !lay[1]->cells_valid) {
+        p.sum_mode = SUM_BUILD_TEST2; p.build_layer = 1; p.sum_out = lay[1]->cells;
+        launch_scan3d_cells(p, c->stream);
+        lay[1]->cells_valid = true;
+      } else {
+        p.sum_mode = has_next ? SUM_TEST2 : SUM_TEST1;
+        launch_scan3d_cells(p, c->stream);
+      }
+    } else {
+      launch_scan(p, c->stream);
+    }
     CK(cudaEventRecord(c->ev[1], c->stream));
     launch_test(p, c->stream);
     CK(cudaEventRecord(c->ev[2], c->stream));

@@ -1031,7 +1031,7 @@ __device__ __forceinline__ void fused3d_consume(const SweepParams &p, const unsi
           if (fminf(a, b) <= rkey[L]) {
             res_update3(rmin[L], in_e, dxe, dye, dze);
             res_update3(rmin[L], in_o, dxo, dyo, dzo);
-            rkey[L] = hikey(2.0 * fabs(rmin[L]));
+            rkey[L] = rmin[L] == DBL_MAX ? __int_as_float(0x7F800000) : hikey(2.0 * fabs(rmin[L]));
           }
         }
         if (EDGE) {
@@ -1145,6 +1145,394 @@ __global__ void __launch_bounds__((F3_CW + 1) * 32, 1) scan3d_fused_kernel(const
   else fused3d_consume<HAS_NEXT, true>(p, fb_smem, full0, empty0, C0, Y0, zc0, zc1, wib, lane);
 }
 
+// ---- 3D, scalar input, per-layer range summaries ("build once, test from summaries") -----------------------
+// The per-thread unions of the fused scan depend on ONE layer only (raw keys of the gradient, domain masks),
+// not on the quantisation factor.  A layer is therefore streamed from HBM once in its life: the step that
+// first sees it (as the "next" layer) derives its gradient keys, folds min non-zero |v|, and stores each
+// thread's union (after the x-neighbour merge) as a 16-byte cell -- six keys truncated to their upper 16
+// bits (sign, 11 exponent bits, 4 mantissa bits).  The exclusion test only compares keys against powers of
+// two and sums exponents, so truncation towards zero changes none of its decisions.  The same step reads
+// the CURRENT layer's cells (written one step earlier) instead of the layer itself: 8 B/vertex of scalars
+// + 2 B/vertex of cells written + 2 B/vertex read, against 16 B/vertex for the two-layer scan, and half the
+// arithmetic.  Re-sweeps (a stale speculated factor, worklist growth) and the final ordinal-only sweep read
+// cells only.
+//
+// Staging: as above (TMA box per plane, full/empty mbarriers, producer warp), one layer per stage.  Each
+// consumer thread keeps a three-plane register window of its 2 columns x (S3_RW + 3) rows, so a plane is read
+// from shared memory once (plus the two x-neighbour columns while it is the centre plane).
+constexpr int S3_RW = F3_RW;                       // corner rows per consumer warp
+constexpr int S3_WR = S3_RW + 3;                   // window rows: y0-1 .. y0+RW+1
+constexpr int S3_NST = 5;                          // ring stages (planes)
+constexpr int S3_STAGE_BYTES = F3_LAYER_BYTES;
+
+__device__ __forceinline__ uint32_t pack_keys(float mn, float mx) {
+  return __byte_perm((uint32_t)__float_as_int(mn), (uint32_t)__float_as_int(mx), 0x7632);
+}
+__device__ __forceinline__ void merge_cell(float (&mn)[3], float (&mx)[3], const uint4 w) {
+  mn[0] = fminf(mn[0], __int_as_float((int)(w.x << 16))); mx[0] = fmaxf(mx[0], __int_as_float((int)(w.x & 0xffff0000u)));
+  mn[1] = fminf(mn[1], __int_as_float((int)(w.y << 16))); mx[1] = fmaxf(mx[1], __int_as_float((int)(w.y & 0xffff0000u)));
+  mn[2] = fminf(mn[2], __int_as_float((int)(w.z << 16))); mx[2] = fmaxf(mx[2], __int_as_float((int)(w.z & 0xffff0000u)));
+}
+
+struct S3Thresholds { float kthr, kfloor; int esum_max, nbits20; double half_factor; };
+__device__ __forceinline__ S3Thresholds s3_thresholds(const int nbits) {
+  S3Thresholds t;
+  t.kthr = __int_as_float((1023 + 1 - nbits) << 20);     // key of 2^(1-nbits): |d| >= 2^(1-nbits) <=> |quantised v| >= 1
+  t.kfloor = __int_as_float((1023 - nbits) << 20);       // key of 2^-nbits: smaller magnitudes quantise to 0
+  t.esum_max = 3119 - 3 * nbits;                          // determinant guard, see fused3d_consume
+  t.nbits20 = (nbits - 1) << 20;
+  t.half_factor = __hiloint2double((1023 + nbits - 1) << 20, 0);   // v 2^nbits = d 2^(nbits-1)
+  return t;
+}
+
+// third level of the determinant guard (rare): the range form of cube_excluded3.  Keys may have lost their low 16
+// bits (cells are stored truncated towards zero), so bounds that truncation moved inwards are pushed back out.
+__device__ __noinline__ bool s3_union_excluded_precise(const float mn0, const float mx0, const float mn1, const float mx1,
+                                                       const float mn2, const float mx2, const int nbits20) {
+  const auto lo = [](float f) { const int k = __float_as_int(f); return k < 0 ? (k | 0xFFFF) : k; };
+  const auto hi = [](float f) { const int k = __float_as_int(f); return k < 0 ? k : (k | 0xFFFF); };
+  const KeyRange x{vertex_range(lo(mn0), nbits20).mn, vertex_range(hi(mx0), nbits20).mx};
+  const KeyRange y{vertex_range(lo(mn1), nbits20).mn, vertex_range(hi(mx1), nbits20).mx};
+  const KeyRange z{vertex_range(lo(mn2), nbits20).mn, vertex_range(hi(mx2), nbits20).mx};
+  return cube_excluded3(x, y, z);
+}
+
+// decide corner plane zc of this lane's 2 x S3_RW cubes from the union of the cells of planes zc, zc+1 (all layers)
+__device__ __forceinline__ void s3_test(const SweepParams &p, const S3Thresholds &T, const float (&cmn)[3], const float (&cmx)[3],
+                                        const bool own_any, const int e, const int y0, const int zc, const int nl) {
+  bool sided = false;
+  int esum = 0;
+  float mag[3];
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    sided = sided || cmn[c] >= T.kthr || cmx[c] <= -T.kthr;
+    mag[c] = fmaxf(fabsf(cmn[c]), fabsf(cmx[c]));
+    esum += (__float_as_int(fmaxf(mag[c], T.kfloor)) >> 20);
+  }
+  // determinant guard, level 1 (exponents only, see fused3d_consume).  A NaN union (no vertex) fails every level and
+  // takes the cold path, which is exact.
+  bool excl = sided && esum <= T.esum_max && !(cmn[0] != cmn[0]);
+  if (sided && !excl && own_any && !(cmn[0] != cmn[0])) {
+    // level 2: M_c = |quantised v_c| + 1 <= D_c 2^(nbits-1) + 1 with D_c the next key above max |d_c| (also above every
+    // value a truncated key stands for); every determinant of the cascade is at most 48 Mx My Mz (cube_excluded3, R <= 2 M)
+    double P = 48.0;
+#pragma unroll
+    for (int c = 0; c < 3; c++) P *= fma(__hiloint2double((__float_as_int(mag[c]) | 0xFFFF) + 1, 0), T.half_factor, 1.0);
+    excl = P < 9.0e18;           // Inf / NaN magnitudes compare false
+    if (!excl) excl = s3_union_excluded_precise(cmn[0], cmx[0], cmn[1], cmx[1], cmn[2], cmx[2], T.nbits20);
+  }
+  const bool fail = own_any && !excl;
+  if (__any_sync(0xffffffffu, fail)) fused3d_slow_cubes(p, fail, e, y0, zc, nl);
+}
+
+__device__ __forceinline__ size_t s3_cell_index(const SweepParams &p, const int tile, const int wib, const int z, const int lane) {
+  return (((size_t)tile * F3_CW + (size_t)wib) * (size_t)(p.D + 1) + (size_t)z) * 32u + (size_t)lane;
+}
+
+// exact (cold) part of the running min non-zero |v|: entered only when a key of this row undercuts the best so far
+__device__ __noinline__ double s3_res_row(double rmin, const bool in_e, const bool in_o, const double dxe, const double dye,
+                                          const double dze, const double dxo, const double dyo, const double dzo) {
+  res_update3(rmin, in_e, dxe, dye, dze);
+  res_update3(rmin, in_o, dxo, dyo, dzo);
+  return rmin;
+}
+
+__device__ __forceinline__ double lds_f64(const uint32_t a) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ double2 lds_f64x2(const uint32_t a) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a));
+  return v;
+}
+
+// one plane step of the build: zm / zc / zp are the register windows of planes zg-1, zg, zg+1 (zp is loaded here)
+//
+// EDGE tiles (they touch the array border or leave the tracker's domain): vertices outside the domain stay out of
+// the ranges (NaN key, the neutral element of FMNMX); a thread whose block holds in-domain vertices ON the array
+// border, where gradient3D is zero (grad.hh:130-149), adds 0 to its ranges (whatever the stencil computed there from
+// the zero-filled halo only widens them further: still a superset); border vertices stay out of min |v|.
+template <bool EDGE, int NPREV, bool TEST>
+struct S3Build {
+  const SweepParams &p;
+  uint32_t ring;             // shared-memory address of the ring
+  uint32_t full0;
+  uint32_t cnt;              // shared-memory address of the per-stage release counters
+  const CUtensorMap *tm;
+  int C0, Y0, nplanes;
+  int lane, e, y0, zc0;
+  uint32_t lane_off;         // byte offset of this thread's first window element within a stage
+  int sidx;                  // index of the centre plane within this CTA's chunk (plane zc0-1 is 0)
+  S3Thresholds T;
+  bool want_res, bad, own_any, touches;
+  // EDGE: bit r (+0 / +8): gradient row r of column e / e+1 lies in the array interior; bit r (+16 / +24): in the domain
+  unsigned masks;
+  double rmin, r2;           // signed value of smallest magnitude so far; 2 |rmin| (the differences are 2 v)
+  float rkey;                // high word of r2
+  uint32_t pcell[3];         // previous plane's merged cell (packed like a stored cell)
+  int st_c, st_p;
+  uint32_t par_p;
+  const uint4 *sum_prev;     // cells of the current layer at the plane being processed (this warp, this lane)
+  uint4 *sum_out;            // cells of the layer being built, likewise
+
+  __device__ __forceinline__ void load_plane(double2 (&P)[S3_WR], const int st) const {
+    const uint32_t base = ring + (uint32_t)st * S3_STAGE_BYTES + lane_off + 16u;
+#pragma unroll
+    for (int r = 0; r < S3_WR; r++) P[r] = lds_f64x2(base + (uint32_t)(r * F3_COLS * 8));
+  }
+  // Release the stage of plane `sx`.  There is no producer warp: the LAST consumer warp to release a stage
+  // (a monotone shared-memory counter per stage) issues the TMA load of plane sx + S3_NST into it, so nobody
+  // ever waits for a stage to drain.
+  __device__ __forceinline__ void release(const int st, const int sx) const {
+    __syncwarp();
+    if (lane == 0) {
+      unsigned old;
+      asm volatile("atom.acq_rel.cta.shared.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(cnt + 4u * (uint32_t)st) : "memory");
+      if ((old + 1u) % F3_CW == 0u && sx + S3_NST < nplanes) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(full0 + 8u * st, F3_BOX_BYTES);
+        tma_load_3d(ring + (uint32_t)st * S3_STAGE_BYTES, tm, C0 - 2, Y0 - 1, zc0 - 1 + sx + S3_NST, full0 + 8u * st);
+      }
+    }
+  }
+  __device__ __forceinline__ void advance_stage() {
+    st_c = st_p;
+    st_p = st_p + 1 == S3_NST ? 0 : st_p + 1;
+    if (st_p == 0) par_p ^= 1u;
+  }
+
+  __device__ __forceinline__ void step(const double2 (&zm)[S3_WR], const double2 (&zc)[S3_WR], double2 (&zp)[S3_WR], const int zg) {
+    const float nanf_ = __int_as_float(KEYF_NAN);
+    const float inff_ = __int_as_float(0x7F800000);
+    uint4 prev = make_uint4(0x7FC07FC0u, 0x7FC07FC0u, 0x7FC07FC0u, 0u);
+    if (NPREV) prev = __ldg(sum_prev);
+    mbar_wait(full0 + 8u * st_p, par_p);
+    load_plane(zp, st_p);
+    const uint32_t cen = ring + (uint32_t)st_c * S3_STAGE_BYTES + lane_off + (uint32_t)(F3_COLS * 8);
+    const bool zarr = zg >= 1 && zg <= p.D - 2;
+    const bool zdom = zg >= p.lb[2] && zg <= p.ub[2];
+    const bool res_now = want_res && zarr;
+    float umin[3] = {nanf_, nanf_, nanf_}, umax[3] = {nanf_, nanf_, nanf_};
+    int big = 0;
+    unsigned mk = masks;
+    if (EDGE) asm volatile("" : "+r"(mk));       // keep the per-row tests as single bit tests of one register
+#pragma unroll
+    for (int r = 0; r <= S3_RW; r++) {
+      const double left = lds_f64(cen + (uint32_t)(r * F3_COLS * 8 + 8)), right = lds_f64(cen + (uint32_t)(r * F3_COLS * 8 + 32));
+      const double2 rc = zc[r + 1];
+      const double dxe = rc.y - left, dxo = right - rc.x;
+      const double dye = zc[r + 2].x - zc[r].x, dyo = zc[r + 2].y - zc[r].y;
+      const double dze = zp[r + 1].x - zm[r + 1].x, dzo = zp[r + 1].y - zm[r + 1].y;
+      float kxe = hikey(dxe), kxo = hikey(dxo), kye = hikey(dye), kyo = hikey(dyo), kze = hikey(dze), kzo = hikey(dzo);
+      big = max(big, max(__double2hiint(rc.x) & 0x7fffffff, __double2hiint(rc.y) & 0x7fffffff));   // NaN / Inf patterns compare high
+      if (res_now) {
+        float a = fminf(fminf(fabsf(kxe), fabsf(kye)), fabsf(kze)), b = fminf(fminf(fabsf(kxo), fabsf(kyo)), fabsf(kzo));
+        bool in_e = true, in_o = true;
+        if (EDGE) {
+          in_e = (mk >> r) & 1u; in_o = (mk >> (r + 8)) & 1u;
+          a = in_e ? a : inff_; b = in_o ? b : inff_;
+        }
+        const float m = fminf(a, b);
+        if (m <= rkey) {
+          // a high word below the best so far, or a tie on the high word that a low word may break
+          bool go = m < rkey;
+          // (no key of this row is below rkey here, so none of the six values is zero)
+          if (!go) go = fabs(dxe) < r2 || fabs(dye) < r2 || fabs(dze) < r2 || fabs(dxo) < r2 || fabs(dyo) < r2 || fabs(dzo) < r2;
+          if (go) {
+            rmin = s3_res_row(rmin, in_e, in_o, dxe, dye, dze, dxo, dyo, dzo);
+            r2 = 2.0 * fabs(rmin);
+            rkey = rmin == DBL_MAX ? inff_ : hikey(r2);      // nothing found yet: keep accepting every key
+          }
+        }
+      }
+      if (EDGE) {
+        const bool de = (mk >> (r + 16)) & 1u, dq = (mk >> (r + 24)) & 1u;
+        kxe = de ? kxe : nanf_; kye = de ? kye : nanf_; kze = de ? kze : nanf_;
+        kxo = dq ? kxo : nanf_; kyo = dq ? kyo : nanf_; kzo = dq ? kzo : nanf_;
+      }
+      umin[0] = fminf(umin[0], fminf(kxe, kxo)); umax[0] = fmaxf(umax[0], fmaxf(kxe, kxo));
+      umin[1] = fminf(umin[1], fminf(kye, kyo)); umax[1] = fmaxf(umax[1], fmaxf(kye, kyo));
+      umin[2] = fminf(umin[2], fminf(kze, kzo)); umax[2] = fmaxf(umax[2], fmaxf(kze, kzo));
+    }
+    bad = bad || big >= KEYF_BIG;
+    release(st_c, sidx);                    // the centre plane's x neighbours were the last shared-memory reads of plane zg
+    sidx++;
+    if (EDGE && touches) {
+#pragma unroll
+      for (int c = 0; c < 3; c++) { umin[c] = fminf(umin[c], 0.f); umax[c] = fmaxf(umax[c], 0.f); }
+    }
+    // plane-level masks (warp-uniform): planes outside the domain stay out of the ranges; the array's first and
+    // last plane have a zero gradient
+    if (!zdom || !zarr) {
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        const bool has = zdom && !(umin[c] != umin[c]);     // lanes with no in-domain vertex keep the neutral element
+        umin[c] = has ? 0.f : nanf_; umax[c] = has ? 0.f : nanf_;
+      }
+    }
+    // x neighbour: corner column e+1 also uses the next lane's first column
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      umin[c] = fminf(umin[c], __shfl_down_sync(0xffffffffu, umin[c], 1));
+      umax[c] = fmaxf(umax[c], __shfl_down_sync(0xffffffffu, umax[c], 1));
+    }
+    *sum_out = make_uint4(pack_keys(umin[0], umax[0]), pack_keys(umin[1], umax[1]), pack_keys(umin[2], umax[2]), 0u);
+    sum_out += 32;
+    if (NPREV) sum_prev += 32;
+    if (TEST) {
+      if (NPREV) merge_cell(umin, umax, prev);
+      if (zg > zc0) {
+        const int zc_ = zg - 1;                   // corner plane decided now (warp-uniform)
+        if (zc_ >= p.lb[2] && zc_ <= p.ub[2]) {
+          float cmn[3] = {umin[0], umin[1], umin[2]}, cmx[3] = {umax[0], umax[1], umax[2]};
+          merge_cell(cmn, cmx, make_uint4(pcell[0], pcell[1], pcell[2], 0u));
+          s3_test(p, T, cmn, cmx, own_any, e, y0, zc_, NPREV + 1);
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 3; c++) pcell[c] = pack_keys(umin[c], umax[c]);
+    }
+    advance_stage();
+  }
+};
+
+template <bool EDGE, int NPREV, bool TEST>
+__device__ __forceinline__ void s3_consume(const SweepParams &p, const uint32_t ring, const uint32_t full0, const uint32_t cnt,
+                                           const int tile, const int C0, const int Y0, const int zc0, const int zc1, const int wib, const int lane) {
+  const int B = p.build_layer;
+  S3Build<EDGE, NPREV, TEST> s{p, ring, full0, cnt};
+  s.tm = &p.tmap[B];
+  s.C0 = C0; s.Y0 = Y0; s.nplanes = zc1 - zc0 + 4;
+  s.lane = lane;
+  s.e = C0 + 2 * lane;
+  s.y0 = Y0 + wib * S3_RW;
+  s.lane_off = (uint32_t)((wib * S3_RW * F3_COLS + 2 * lane) * 8);
+  s.zc0 = zc0;
+  s.T = s3_thresholds(p.nbits);
+  s.want_res = p.res_slot[B] != nullptr;
+  s.bad = false;
+  s.own_any = lane <= 30;
+  s.touches = false;
+  s.masks = 0xffffffffu;
+  if (EDGE) {
+    const bool arr_c0 = s.e >= 1 && s.e <= p.W - 2, arr_c1 = s.e + 1 >= 1 && s.e + 1 <= p.W - 2;
+    const bool dom_c0 = s.e >= p.lb[0] && s.e <= p.ub[0], dom_c1 = s.e + 1 >= p.lb[0] && s.e + 1 <= p.ub[0];
+    s.own_any = s.own_any && (dom_c0 || dom_c1) && s.y0 <= p.ub[1] && s.y0 + S3_RW - 1 >= p.lb[1];
+    unsigned rows = 0, rows_dom = 0;
+#pragma unroll
+    for (int r = 0; r <= S3_RW; r++) {
+      rows |= (s.y0 + r >= 1 && s.y0 + r <= p.H - 2) ? (1u << r) : 0u;
+      rows_dom |= (s.y0 + r >= p.lb[1] && s.y0 + r <= p.ub[1]) ? (1u << r) : 0u;
+    }
+    const unsigned in_e = arr_c0 ? rows : 0u, in_o = arr_c1 ? rows : 0u, dom_e = dom_c0 ? rows_dom : 0u, dom_o = dom_c1 ? rows_dom : 0u;
+    s.masks = in_e | (in_o << 8) | (dom_e << 16) | (dom_o << 24);
+    // in-domain vertices of this thread's block that lie on the array border
+    s.touches = ((dom_e & ~in_e) | (dom_o & ~in_o)) != 0u;
+  }
+  s.rmin = DBL_MAX;
+  s.r2 = __hiloint2double(0x7FF00000, 0);
+  s.rkey = __int_as_float(0x7F800000);
+#pragma unroll
+  for (int c = 0; c < 3; c++) s.pcell[c] = 0x7FC07FC0u;
+  const size_t cell0 = s3_cell_index(p, tile, wib, zc0, lane);
+  s.sum_prev = NPREV ? p.sum_in[0] + cell0 : nullptr;
+  s.sum_out = p.sum_out + cell0;
+
+  double2 A[S3_WR], Bw[S3_WR], Cw[S3_WR];
+  mbar_wait(full0, 0);
+  s.load_plane(A, 0);          // plane zc0-1: only ever the z-1 neighbour
+  s.release(0, 0);
+  mbar_wait(full0 + 8, 0);
+  s.load_plane(Bw, 1);         // plane zc0: first centre plane
+  s.st_c = 1; s.st_p = 2; s.par_p = 0; s.sidx = 1;
+  const int zend = zc1 + 1;
+  int zg = zc0;
+  while (true) {
+    s.step(A, Bw, Cw, zg); if (++zg > zend) break;
+    s.step(Bw, Cw, A, zg); if (++zg > zend) break;
+    s.step(Cw, A, Bw, zg); if (++zg > zend) break;
+  }
+  if (s.want_res) warp_res_commit(fabs(s.rmin), p.res_slot[B]);
+  if (s.bad) atomicExch(p.poison, 1ull);
+}
+
+template <int NPREV, bool TEST>
+__global__ void __launch_bounds__(F3_CW * 32, 2) scan3d_build_kernel(const __grid_constant__ SweepParams p) {
+  extern __shared__ __align__(128) unsigned char fb_smem[];
+  const int lane = threadIdx.x & 31;
+  const int wib = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);     // warp-uniform by construction
+  const uint32_t ring_u32 = smem_u32(fb_smem);
+  const uint32_t full0 = ring_u32 + (uint32_t)S3_NST * S3_STAGE_BYTES;
+  unsigned *cnt = reinterpret_cast<unsigned *>(fb_smem + (size_t)S3_NST * S3_STAGE_BYTES + 8u * S3_NST);
+  int b = blockIdx.x;
+  const int bx = b % p.nsx; b /= p.nsx;
+  const int by = b % p.nsy;
+  const int bz = b / p.nsy;
+  const int C0 = bx * F3_STRIDE, Y0 = by * F3_TROWS;
+  const int zc0 = bz * p.rows, zc1 = min(zc0 + p.rows - 1, p.D - 1);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int q = 0; q < S3_NST; q++) { mbar_init(full0 + 8u * q, 1); cnt[q] = 0u; }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    // scalar planes zc0-1 .. zc1+2 of the layer being built, one TMA box (tile + halo) each: the first S3_NST here,
+    // the rest by whichever warp drains a stage last
+    const int nplanes = zc1 - zc0 + 4;
+    for (int s = 0; s < min(S3_NST, nplanes); s++) {
+      mbar_expect_tx(full0 + 8u * s, F3_BOX_BYTES);
+      tma_load_3d(ring_u32 + (uint32_t)s * S3_STAGE_BYTES, &p.tmap[p.build_layer], C0 - 2, Y0 - 1, zc0 - 1 + s, full0 + 8u * s);
+    }
+  }
+  __syncthreads();
+  const int tile = by * p.nsx + bx;
+  const bool interior = C0 >= max(1, p.lb[0]) && C0 + 63 <= min(p.W - 2, p.ub[0]) && Y0 >= max(1, p.lb[1]) && Y0 + F3_TROWS <= min(p.H - 2, p.ub[1]);
+  if (interior) s3_consume<false, NPREV, TEST>(p, ring_u32, full0, smem_u32(cnt), tile, C0, Y0, zc0, zc1, wib, lane);
+  else s3_consume<true, NPREV, TEST>(p, ring_u32, full0, smem_u32(cnt), tile, C0, Y0, zc0, zc1, wib, lane);
+}
+
+// cells only: the final ordinal sweep (one layer) and re-sweeps (both layers' cells exist)
+template <int NL>
+__global__ void __launch_bounds__(F3_CW * 32) scan3d_cells_kernel(const SweepParams p) {
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  int b = blockIdx.x;
+  const int bx = b % p.nsx; b /= p.nsx;
+  const int by = b % p.nsy;
+  const int bz = b / p.nsy;
+  const int C0 = bx * F3_STRIDE, Y0 = by * F3_TROWS;
+  const int zc0 = bz * p.rows, zc1 = min(zc0 + p.rows - 1, p.D - 1);
+  const int e = C0 + 2 * lane, y0 = Y0 + wib * S3_RW;
+  const bool any_col = (e >= p.lb[0] && e <= p.ub[0]) || (e + 1 >= p.lb[0] && e + 1 <= p.ub[0]);
+  const bool own_any = lane <= 30 && any_col && y0 <= p.ub[1] && y0 + S3_RW - 1 >= p.lb[1];
+  if (!__any_sync(0xffffffffu, own_any)) return;
+  const S3Thresholds T = s3_thresholds(p.nbits);
+  const size_t cell0 = s3_cell_index(p, by * p.nsx + bx, wib, 0, lane);
+  const float nanf_ = __int_as_float(KEYF_NAN);
+  float pmn[3] = {nanf_, nanf_, nanf_}, pmx[3] = {nanf_, nanf_, nanf_};
+  for (int zg = zc0; zg <= zc1 + 1; zg++) {
+    float umn[3] = {nanf_, nanf_, nanf_}, umx[3] = {nanf_, nanf_, nanf_};
+#pragma unroll
+    for (int L = 0; L < NL; L++) merge_cell(umn, umx, __ldg(p.sum_in[L] + cell0 + (size_t)zg * 32u));
+    if (zg > zc0) {
+      const int zc_ = zg - 1;
+      if (zc_ >= p.lb[2] && zc_ <= p.ub[2]) {
+        float cmn[3], cmx[3];
+#pragma unroll
+        for (int c = 0; c < 3; c++) { cmn[c] = fminf(pmn[c], umn[c]); cmx[c] = fmaxf(pmx[c], umx[c]); }
+        s3_test(p, T, cmn, cmx, own_any, e, y0, zc_, NL);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; c++) { pmn[c] = umn[c]; pmx[c] = umx[c]; }
+  }
+}
+
+static size_t s3_smem_bytes() { return (size_t)S3_NST * S3_STAGE_BYTES + (size_t)S3_NST * 8 + (size_t)S3_NST * 4; }
+
+size_t scan3d_cells_per_layer(const SweepParams &p) { return (size_t)p.nsx * p.nsy * F3_CW * (size_t)(p.D + 1) * 32u; }
+
 static size_t fused3d_smem_bytes(bool has_next) {
   return (size_t)F3_NST * (has_next ? 2 : 1) * F3_LAYER_BYTES + (size_t)2 * F3_NST * 8;
 }
@@ -1186,6 +1574,21 @@ void init_kernel_attributes() {
   cudaFuncSetAttribute(scan2d_bulk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bulk_smem_bytes(false));
   cudaFuncSetAttribute(scan3d_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused3d_smem_bytes(true));
   cudaFuncSetAttribute(scan3d_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused3d_smem_bytes(false));
+  cudaFuncSetAttribute(scan3d_build_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s3_smem_bytes());
+  cudaFuncSetAttribute(scan3d_build_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s3_smem_bytes());
+  cudaFuncSetAttribute(scan3d_build_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s3_smem_bytes());
+}
+
+// summary path of the fused 3D scan: p.sum_mode selects what one launch does (see SweepParams)
+void launch_scan3d_cells(const SweepParams &p, cudaStream_t s) {
+  const unsigned grid = (unsigned)((i64)p.nsx * p.nsy * p.nsz);
+  switch (p.sum_mode) {
+    case SUM_BUILD: scan3d_build_kernel<0, false><<<grid, F3_CW * 32, s3_smem_bytes(), s>>>(p); break;
+    case SUM_BUILD_TEST1: scan3d_build_kernel<0, true><<<grid, F3_CW * 32, s3_smem_bytes(), s>>>(p); break;
+    case SUM_BUILD_TEST2: scan3d_build_kernel<1, true><<<grid, F3_CW * 32, s3_smem_bytes(), s>>>(p); break;
+    case SUM_TEST1: scan3d_cells_kernel<1><<<grid, F3_CW * 32, 0, s>>>(p); break;
+    default: scan3d_cells_kernel<2><<<grid, F3_CW * 32, 0, s>>>(p); break;
+  }
 }
 
 void launch_scan(const SweepParams &p, cudaStream_t s) {

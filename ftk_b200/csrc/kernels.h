@@ -43,6 +43,11 @@ struct SweepParams {
   unsigned long long *poison;        // fused 3D scan: set non-zero when a scalar is NaN / Inf / >= 2^1000 (the sweep is redone unfused)
   // fused 3D scan: TMA descriptors of the two scalar layers (box = one tile plane incl. halo)
   alignas(64) CUtensorMap tmap[2];
+  // fused 3D scan, summary path: 16-byte range cells per (tile, warp, plane, lane), one buffer per layer
+  int32_t sum_mode;                  // SUM_*: what this launch does
+  int32_t build_layer;               // which of L[0] / L[1] (tmap, res_slot) the build streams
+  const uint4 *sum_in[2];            // cells read (layer order as L[])
+  uint4 *sum_out;                    // cells written by a build
   // scan decomposition
   int32_t nsx;                // x strips (31 corners each)
   int32_t nsy;                // 2D: row chunks; 3D: y tiles (BY-1 corners each)
@@ -74,6 +79,14 @@ constexpr int F3_ROWS = F3_TROWS + 3;          // staged rows: Y0-1 .. Y0+TROWS+
 bool encode_scalar_tmap3d(const double *S, int W, int H, int D, CUtensorMap *out);
 
 void launch_scan(const SweepParams &p, cudaStream_t s);
+// summary path of the fused 3D scan
+enum { SUM_BUILD = 0,          // stream layer build_layer, write its cells (+ min |v|); no cube is tested
+       SUM_BUILD_TEST1 = 1,    // ... and test the ordinal cubes of that single layer (single-snapshot sweep)
+       SUM_BUILD_TEST2 = 2,    // stream L[1], write its cells, read L[0]'s cells, test the cubes over both layers
+       SUM_TEST1 = 3,          // cells of L[0] only (final ordinal sweep, repeats)
+       SUM_TEST2 = 4 };        // cells of L[0] and L[1] (repeats)
+void launch_scan3d_cells(const SweepParams &p, cudaStream_t s);
+size_t scan3d_cells_per_layer(const SweepParams &p);
 // thread-per-(surviving cube, type) exact test; grid sized for `expected` cubes, grid-stride otherwise
 void launch_test(const SweepParams &p, cudaStream_t s);
 
