@@ -57,6 +57,7 @@ struct ftkb_ctx {
   int next_slot = 0;
   int sm_count = 148;
   int scan_mode = 2;             // FTKB_SCAN=ldg|warp|tile selects the fused scan's staging (A/B measurements); default tile
+  bool cells2d = true;           // same for the fused 2D tile scan; FTKB_SCAN2D=twolayer re-reads both layers every step
   bool cells3d = true;           // fused 3D scan streams each layer once and keeps its range cells; FTKB_SCAN3D=twolayer re-reads both layers every step
   std::vector<uint4 *> freeCells;
   size_t ncells = 0;             // cells per layer (fixed by the dims)
@@ -184,6 +185,8 @@ extern "C" int ftkb_create(const ftkb_config *cfg, ftkb_ctx **out) {
     c->fused3d = n == 3 && cfg->vector_source == FTKB_SOURCE_DERIVED && cfg->robust_detection && cfg->dims[0] % 2 == 0 &&
                  !(e && std::string(e) == "plain");
     c->cells3d = !(e && std::string(e) == "twolayer");
+    const char *e2 = std::getenv("FTKB_SCAN2D");
+    c->cells2d = n == 2 && cfg->vector_source == FTKB_SOURCE_DERIVED && c->scan_mode == 2 && !(e2 && std::string(e2) == "twolayer");
   }
   c->n = n;
   c->nvert = (size_t)cfg->dims[0] * cfg->dims[1] * (n == 3 ? cfg->dims[2] : 1);
@@ -411,6 +414,14 @@ static void fused2d_decomposition(const ftkb_ctx *c, SweepParams &p) {
   }
   nsy = std::max<int64_t>(1, std::min<int64_t>(nsy, (p.H + 31) / 32));
   p.rows = (int)((p.H + nsy - 1) / nsy);
+  if (p.bulk == 2 && c->cells2d) {
+    // about six waves of CTAs (costs differ: border strips, cold paths), at least two cell blocks per chunk
+    const int R = SCAN2D_CELL_ROWS;
+    const int64_t want = std::max<int64_t>(1, (6 * (int64_t)c->sm_count * 3) / p.nsx);
+    p.rows = std::max(2 * R, (int)((p.H + want - 1) / want));
+    p.rows = (p.rows + R - 1) / R * R;      // chunks start on cell-block boundaries
+    if (const char *e = std::getenv("FTKB_C2_ROWS")) p.rows = std::max(R, std::atoi(e) / R * R);   // A/B measurements
+  }
   p.nsy = (p.H + p.rows - 1) / p.rows;
   p.nsz = 1;
 }
@@ -421,15 +432,11 @@ static void fused3d_decomposition(const ftkb_ctx *c, SweepParams &p) {
   p.nsy = (p.H + F3_TROWS - 1) / F3_TROWS;
   const int64_t tiles = (int64_t)p.nsx * p.nsy;
   if (c->cells3d) {
-    // two CTAs per SM; pick the z split whose (waves of CTAs) x (planes per CTA incl. the 3 halo planes) is smallest
+    // two CTAs per SM.  CTA costs differ (edge tiles, cold paths), so aim for about six waves of CTAs and let the
+    // hardware scheduler balance them, but keep at least 16 planes per CTA (3 halo planes are re-read per chunk)
     const int64_t slots = 2 * (int64_t)c->sm_count;
-    int64_t best = 1, best_cost = INT64_MAX;
-    for (int64_t nsz = 1; nsz <= std::max(1, p.D / 16); nsz++) {
-      const int64_t rows = (p.D + nsz - 1) / nsz, chunks = (p.D + rows - 1) / rows;
-      const int64_t cost = ((tiles * chunks + slots - 1) / slots) * (rows + 3);
-      if (cost < best_cost) { best_cost = cost; best = nsz; }
-    }
-    p.rows = (int)((p.D + best - 1) / best);
+    const int64_t nsz = std::max<int64_t>(1, std::min<int64_t>((6 * slots + tiles - 1) / tiles, std::max(1, p.D / 16)));
+    p.rows = (int)((p.D + nsz - 1) / nsz);
     if (const char *e = std::getenv("FTKB_S3_ROWS")) p.rows = std::max(1, std::min(p.D, std::atoi(e)));   // A/B measurements
     p.nsz = (p.D + p.rows - 1) / p.rows;
     return;
@@ -442,7 +449,7 @@ static void fused3d_decomposition(const ftkb_ctx *c, SweepParams &p) {
 
 static int ensure_cells(ftkb_ctx *c, Layer &l, const SweepParams &p) {
   if (l.cells) return FTKB_OK;
-  if (!c->ncells) c->ncells = scan3d_cells_per_layer(p);
+  if (!c->ncells) c->ncells = c->n == 3 ? scan3d_cells_per_layer(p) : scan2d_cells_per_layer(p);
   if (!c->freeCells.empty()) { l.cells = c->freeCells.back(); c->freeCells.pop_back(); return FTKB_OK; }
   CK(cudaMalloc(&l.cells, sizeof(uint4) * c->ncells));
   return FTKB_OK;
@@ -521,7 +528,17 @@ static int resolve_pending(ftkb_ctx *c, Layer &l) {
     return FTKB_OK;
   }
   fused2d_decomposition(c, p);
-  launch_scan(p, c->stream);
+  if (c->cells2d && p.bulk == 2) {
+    // stream the layer once: its range cells and min |v|; no cube is tested
+    fill_sweep_geometry(c, p);
+    int rc = ensure_cells(c, l, p);
+    if (rc) return rc;
+    p.sum_mode = SUM_BUILD; p.build_layer = 0; p.sum_out = l.cells;
+    launch_scan2d_cells(p, c->stream);
+    l.cells_valid = true;
+  } else {
+    launch_scan(p, c->stream);
+  }
   c->stats.kernel_launches++;
   CK(cudaMemcpyAsync(c->h_scalars + l.slot, c->d_scalars + l.slot, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
   c->stats.d2h_bytes += 8;
@@ -632,29 +649,30 @@ extern "C" int ftkb_update_timestep(ftkb_ctx *c) {
     c->h_scalars[ftkb_ctx::SLOT_POISON] = 0;
     CK(cudaMemcpyAsync(c->d_scalars + ftkb_ctx::SLOT_WL, c->h_scalars + ftkb_ctx::SLOT_WL, 32, cudaMemcpyHostToDevice, c->stream));
     CK(cudaEventRecord(c->ev[0], c->stream));
-    if (fused && c->n == 3 && c->cells3d) {
+    if (fused && ((c->n == 3 && c->cells3d) || (c->n == 2 && c->cells2d && p.bulk == 2))) {
       // each layer is streamed once (the step that first sees it); everything else reads its 16-byte range cells
+      void (*launch_cells)(const SweepParams &, cudaStream_t) = c->n == 3 ? launch_scan3d_cells : launch_scan2d_cells;
       int rc0 = ensure_cells(c, *lay[0], p);
       if (!rc0 && has_next) rc0 = ensure_cells(c, *lay[1], p);
       if (rc0) return rc0;
       p.sum_in[0] = lay[0]->cells; p.sum_in[1] = lay[1]->cells;
       if (!lay[0]->cells_valid) {
         p.sum_mode = has_next ? SUM_BUILD : SUM_BUILD_TEST1; p.build_layer = 0; p.sum_out = lay[0]->cells;
-        launch_scan3d_cells(p, c->stream);
+        launch_cells(p, c->stream);
         lay[0]->cells_valid = true;
         if (has_next) {
           c->stats.kernel_launches++;       // the very first step streams two layers
           p.sum_mode = lay[1]->cells_valid ? SUM_TEST2 : SUM_BUILD_TEST2; p.build_layer = 1; p.sum_out = lay[1]->cells;
-          launch_scan3d_cells(p, c->stream);
+          launch_cells(p, c->stream);
           lay[1]->cells_valid = true;
         }
       } else if (has_next && !lay[1]->cells_valid) {
         p.sum_mode = SUM_BUILD_TEST2; p.build_layer = 1; p.sum_out = lay[1]->cells;
-        launch_scan3d_cells(p, c->stream);
+        launch_cells(p, c->stream);
         lay[1]->cells_valid = true;
       } else {
         p.sum_mode = has_next ? SUM_TEST2 : SUM_TEST1;
-        launch_scan3d_cells(p, c->stream);
+        launch_cells(p, c->stream);
       }
     } else {
       launch_scan(p, c->stream);

@@ -861,6 +861,252 @@ __global__ void __launch_bounds__((TL_CW + 1) * 32, 3) scan2d_tile_kernel(const 
   else fused2d_tile_strip<HAS_NEXT, false>(p, c0, r0, r1, lane, tile, full0, empty0);
 }
 
+// ---- 2D, scalar input, per-layer range cells ("build once, test from cells") ---------------------------------
+// Same idea as the 3D cells below: the fp32 ranges the tile scan keeps per thread depend on one layer only, so
+// a layer is streamed once -- by the step that first sees it -- and leaves a 16-byte cell {min vx, max vx, min vy,
+// max vy} per (lane, block of C2_R corner rows); the step reads the CURRENT layer's cells instead of the layer.
+// A cell spans the lane's two columns, the next lane's two, and gradient rows 9k .. 9k+9: a superset of the
+// vertices of the lane's 2 x 9 cubes.  If the union of the two layers' cells passes cube_excluded2_f, all 18 cubes
+// are excluded; otherwise they are tested one by one from global memory (cold) and survivors are appended.
+// Traffic per step: 8 B/vertex of scalars + ~1 B/vertex of cells written + ~1 B/vertex read (16 B/vertex before).
+constexpr int C2_R = 9;                                // corner rows per cell block (a multiple of 3: the row window rotates by index)
+constexpr int C2_NST = 9;                              // ring stages (rows) = unroll of the row loop = C2_R
+constexpr int C2_CW = TL_CW;
+static_assert(C2_R % 3 == 0 && C2_R == C2_NST && C2_R == SCAN2D_CELL_ROWS, "row window / ring / cell block must stay aligned");
+
+__device__ __forceinline__ size_t cells2d_index(const SweepParams &p, const int strip, const int kb, const int lane) {
+  const size_t nblk = (size_t)(p.H / C2_R + 2);
+  return ((size_t)strip * nblk + (size_t)kb) * 32u + (size_t)lane;
+}
+
+// cold path: for every lane whose cell union failed (bit set in failmask), the WARP tests that lane's 2 x C2_R cubes,
+// one lane per cube: ranges over the vertices valid simplices can use (<= ub) from global memory, gradient exactly
+// as gradient2D indexes it (clamped at the array border); survivors are appended.
+__device__ __noinline__ void cells2d_slow_cubes(const SweepParams &p, unsigned failmask, const int c0, const int y0, const int nl) {
+  static_assert(2 * C2_R <= 32, "one lane per cube");
+  const int W = p.W, H = p.H;
+  const int lane = threadIdx.x & 31;
+  const float cwf = (float)(W - 1), chf = (float)(H - 1);
+  const float nanf_ = __int_as_float(0x7FC00000);
+  const int r = lane >> 1, q = lane & 1;
+  while (failmask) {
+    const int src = __ffs(failmask) - 1;
+    failmask &= failmask - 1;
+    const int x = c0 + 2 * src + q, y = y0 + r;
+    const bool in = lane < 2 * C2_R && x >= p.lb[0] && x <= p.ub[0] && y >= p.lb[1] && y <= p.ub[1];
+    FRange rx{nanf_, nanf_}, ry{nanf_, nanf_};
+#pragma unroll
+    for (int v = 0; v < 4; v++) {
+      const int vx = x + (v & 1), vy = y + (v >> 1);
+      if (!in || vx > p.ub[0] || vy > p.ub[1]) continue;
+      const size_t row = (size_t)W * (size_t)vy;
+      for (int L = 0; L < nl; L++) {
+        const double *S = p.L[L].S;
+        const double dx = __ldg(S + row + clampi(vx + 1, W)) - __ldg(S + row + clampi(vx - 1, W));
+        const double dy = __ldg(S + (size_t)W * (size_t)clampi(vy + 1, H) + vx) - __ldg(S + (size_t)W * (size_t)clampi(vy - 1, H) + vx);
+        const float fx = __double2float_rn(dx) * cwf, fy = __double2float_rn(dy) * chf;
+        rx = fmerge(rx, FRange{fx, fx}); ry = fmerge(ry, FRange{fy, fy});
+      }
+    }
+    const bool surv = in && !cube_excluded2_f(rx, ry, p.thrp_f, p.thr2_f, p.lim_f);
+    append_survivors(p, surv, (u64)(x - p.lb[0]) + (u64)p.nc[0] * (u64)(y - p.lb[1]));
+  }
+}
+
+// union of the cells of all layers for one block -> excluded, or the cold path
+__device__ __forceinline__ void cells2d_decide(const SweepParams &p, const FRange ux, const FRange uy, const bool own, const int e, const int y0, const int nl) {
+  const bool fail = own && !cube_excluded2_f(ux, uy, p.thrp_f, p.thr2_f, p.lim_f);
+  const unsigned fm = __ballot_sync(0xffffffffu, fail);
+  if (fm) cells2d_slow_cubes(p, fm, e - 2 * (int)(threadIdx.x & 31), y0, nl);
+}
+
+template <bool BORDER, int NPREV, bool TEST>
+__device__ __forceinline__ void cells2d_strip(const SweepParams &p, const int c0, const int r0, const int r1, const int lane,
+                                              const double *tile /* this warp's column 0 = c0-2 */, const uint32_t full0, const uint32_t empty0,
+                                              const int strip) {
+  const int W = p.W, H = p.H, B = p.build_layer;
+  const int e = c0 + 2 * lane, o = e + 1;
+  const bool e_in = !BORDER || e < W, o_in = !BORDER || o < W, o1_in = !BORDER || o + 1 < W;
+  const bool own_cols = lane <= 30 && ((e >= p.lb[0] && e <= p.ub[0]) || (o >= p.lb[0] && o <= p.ub[0]));
+  const int jl = r1 + 1;                             // last gradient row visited
+  const float cwf = (float)(W - 1), chf = (float)(H - 1);
+  const bool want_res = p.res_slot[B] != nullptr;
+  double rmin = DBL_MAX;
+  float rminf = 3.4028234e38f;
+  const uint4 *sum_prev = NPREV ? p.sum_in[0] + cells2d_index(p, strip, 0, lane) : nullptr;
+  uint4 *sum_out = p.sum_out + cells2d_index(p, strip, 0, lane);
+
+  const double *lane_base = tile + 2 * lane;    // [1]: column e-1, [2..3]: e, o, [4]: o+1
+  auto centre = [&](const int st, double (&dst)[2]) {
+    const double2 t = *reinterpret_cast<const double2 *>(lane_base + st * TL_SEG + 2);
+    dst[0] = t.x; dst[1] = t.y;
+  };
+  auto release = [&](const int st) {     // this warp is done with the stage
+    __syncwarp();
+    if (elect_one()) mbar_arrive(empty0 + 8u * st);
+  };
+  // a block of C2_R corner rows is complete: x-neighbour merge, store the cell, test against the other layer's cell
+  auto finish_block = [&](const int kb, FRange bx, FRange by, const uint4 prevc) {
+    bx = fmerge(bx, fshfl_down1(bx));
+    by = fmerge(by, fshfl_down1(by));
+    sum_out[(size_t)kb * 32u] = make_uint4(__float_as_uint(bx.mn), __float_as_uint(bx.mx), __float_as_uint(by.mn), __float_as_uint(by.mx));
+    if (TEST) {
+      if (NPREV) {
+        bx = fmerge(bx, FRange{__uint_as_float(prevc.x), __uint_as_float(prevc.y)});
+        by = fmerge(by, FRange{__uint_as_float(prevc.z), __uint_as_float(prevc.w)});
+      }
+      const int y0 = kb * C2_R;
+      const bool own = own_cols && y0 <= p.ub[1] && y0 + C2_R - 1 >= p.lb[1];
+      cells2d_decide(p, bx, by, own, e, y0, NPREV + 1);
+    }
+  };
+
+  double win[3][2];
+  mbar_wait(full0, 0);
+  centre(0, win[0]);
+  mbar_wait(full0 + 8, 0);
+  centre(1, win[1]);
+  release(0);                                      // row r0-1: only its centre columns are ever needed
+  FRange bx{0.f, 0.f}, by{0.f, 0.f};
+  uint4 prevc = make_uint4(0x7FC00000u, 0x7FC00000u, 0x7FC00000u, 0x7FC00000u);
+
+  // gradient row j = r0 + C2_NST i + K (r0 is a multiple of C2_R = C2_NST); ring index of row j is 1 + C2_NST i + K
+  auto step = [&](auto KC, const int j, const int i) {
+    constexpr int K = decltype(KC)::value;
+    constexpr int ST_J = (1 + K) % C2_NST, ST_P = (2 + K) % C2_NST;
+    double (&m1)[2] = win[K % 3];
+    double (&c0v)[2] = win[(K + 1) % 3];
+    double (&p1)[2] = win[(K + 2) % 3];
+    mbar_wait(full0 + 8u * ST_P, (uint32_t)((i + (2 + K >= C2_NST ? 1 : 0)) & 1));
+    centre(ST_P, p1);
+    const double *rowj = lane_base + ST_J * TL_SEG;
+    double left = rowj[1], right = rowj[4];
+    double mid_e = c0v[1];
+    if (BORDER) {
+      if (e == 0) left = c0v[0];
+      if (!o_in) mid_e = c0v[0];
+      if (!o1_in) right = c0v[1];
+    }
+    const double dxe = mid_e - left, dxo = right - c0v[0], dye = p1[0] - m1[0], dyo = p1[1] - m1[1];
+    const float fxe = __double2float_rn(dxe) * cwf, fxo = __double2float_rn(dxo) * cwf;
+    const float fye = __double2float_rn(dye) * chf, fyo = __double2float_rn(dyo) * chf;
+    if (want_res && j < H) {
+      float a = fminf(fminf(fabsf(fxe), fabsf(fye)), fminf(fabsf(fxo), fabsf(fyo)));
+      if (BORDER) a = fminf(e_in ? fminf(fabsf(fxe), fabsf(fye)) : 3.4028234e38f, o_in ? fminf(fabsf(fxo), fabsf(fyo)) : 3.4028234e38f);
+      if (a < rminf) res_update4(rmin, rminf, e_in, o_in, dxe, dye, dxo, dyo, (double)(W - 1), (double)(H - 1));
+    }
+    const FRange rx{fminf(fxe, fxo), fmaxf(fxe, fxo)}, ry{fminf(fye, fyo), fmaxf(fye, fyo)};
+    if (K == 0) {
+      // gradient row C2_R k closes block k-1 and opens block k
+      if (j > r0) finish_block(j / C2_R - 1, fmerge(bx, rx), fmerge(by, ry), prevc);
+      bx = rx; by = ry;
+      if (NPREV && j < jl) prevc = __ldg(sum_prev + (size_t)(j / C2_R) * 32u);
+    } else {
+      bx = fmerge(bx, rx); by = fmerge(by, ry);
+    }
+    release(ST_J);     // row j: its centre went into the window one step ago, its x neighbours were read above
+  };
+
+  for (int j = r0, i = 0; j <= jl; j += C2_NST, i++) {
+    step(IC<0>{}, j, i);
+    if (j + 1 <= jl) step(IC<1>{}, j + 1, i);
+    if (j + 2 <= jl) step(IC<2>{}, j + 2, i);
+    if (j + 3 <= jl) step(IC<3>{}, j + 3, i);
+    if (j + 4 <= jl) step(IC<4>{}, j + 4, i);
+    if (j + 5 <= jl) step(IC<5>{}, j + 5, i);
+    if (j + 6 <= jl) step(IC<6>{}, j + 6, i);
+    if (j + 7 <= jl) step(IC<7>{}, j + 7, i);
+    if (j + 8 <= jl) step(IC<8>{}, j + 8, i);
+  }
+  if (jl % C2_R != 0) finish_block(jl / C2_R, bx, by, prevc);     // the array's last, partial block
+  if (want_res) warp_res_commit(fabs(rmin), p.res_slot[B]);
+}
+
+template <int NPREV, bool TEST>
+__global__ void __launch_bounds__((C2_CW + 1) * 32, 3) scan2d_build_kernel(const __grid_constant__ SweepParams p) {
+  constexpr uint32_t STAGE_BYTES = TL_SEG * 8;
+  extern __shared__ __align__(128) unsigned char fb_smem[];
+  const int lane = threadIdx.x & 31;
+  const int wib = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);     // warp-uniform by construction
+  double *ring = reinterpret_cast<double *>(fb_smem);
+  const uint32_t full0 = smem_u32(fb_smem + (size_t)C2_NST * STAGE_BYTES), empty0 = full0 + 8u * C2_NST;
+  const int W = p.W, H = p.H;
+  const int bx = blockIdx.x % p.nsx, cy = blockIdx.x / p.nsx;
+  const int C0 = bx * (C2_CW * FB_STRIDE);
+  const int nactive = min(C2_CW, (W - C0 + FB_STRIDE - 1) / FB_STRIDE);     // consumer warps whose strip starts inside the array
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int q = 0; q < C2_NST; q++) { mbar_init(full0 + 8u * q, 1); mbar_init(empty0 + 8u * q, (uint32_t)nactive); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  const int r0 = cy * p.rows;                        // p.rows is a multiple of C2_R
+  const int r1 = min(r0 + p.rows - 1, H - 1);
+  const int nrows = (r1 + 1) - r0 + 3;               // staged rows r0-1 .. r1+2 (ring index 0 .. nrows-1)
+  if (wib == C2_CW) {
+    // producer: one elected lane walks the rows with the array's index clamp and keeps the ring full
+    if (elect_one()) {
+      const double *S = p.L[p.build_layer].S;
+      const int col_lo = max(C0 - 2, 0), col_hi = min(C0 - 2 + TL_SEG, W);
+      const uint32_t seg_bytes = (uint32_t)(col_hi - col_lo) * 8u;
+      const uint32_t dst0 = smem_u32(ring) + (uint32_t)(col_lo - (C0 - 2)) * 8u;
+      for (int rr = 0; rr < nrows; rr++) {
+        const int st = rr % C2_NST;
+        if (rr >= C2_NST) mbar_wait(empty0 + 8u * st, (uint32_t)((rr / C2_NST - 1) & 1));
+        const size_t off = (size_t)W * (size_t)clampi(r0 - 1 + rr, H) + (size_t)col_lo;
+        mbar_expect_tx(full0 + 8u * st, seg_bytes);
+        bulk_g2s(dst0 + (uint32_t)st * STAGE_BYTES, S + off, seg_bytes, full0 + 8u * st);
+      }
+    }
+    return;
+  }
+  if (wib >= nactive) return;
+  const int c0 = C0 + wib * FB_STRIDE;
+  const double *tile = ring + wib * FB_STRIDE;
+  const bool border = c0 == 0 || c0 + FB_SEG - 2 > W;      // strips that touch the array's left / right edge clamp their columns
+  if (border) cells2d_strip<true, NPREV, TEST>(p, c0, r0, r1, lane, tile, full0, empty0, bx * C2_CW + wib);
+  else cells2d_strip<false, NPREV, TEST>(p, c0, r0, r1, lane, tile, full0, empty0, bx * C2_CW + wib);
+}
+
+// cells only: the final ordinal sweep (one layer) and re-sweeps (both layers' cells exist); thread per cell
+template <int NL>
+__global__ void __launch_bounds__(256) scan2d_cells_kernel(const __grid_constant__ SweepParams p, const int nstrips, const int nblk_used) {
+  const int lane = threadIdx.x & 31;
+  const long long w = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);   // 8 warps per CTA
+  if (w >= (long long)nstrips * nblk_used) return;
+  const int strip = (int)(w / nblk_used), kb = (int)(w % nblk_used);
+  const int e = strip * FB_STRIDE + 2 * lane, y0 = kb * C2_R;
+  const bool own = lane <= 30 && ((e >= p.lb[0] && e <= p.ub[0]) || (e + 1 >= p.lb[0] && e + 1 <= p.ub[0])) && y0 <= p.ub[1] && y0 + C2_R - 1 >= p.lb[1];
+  if (!__any_sync(0xffffffffu, own)) return;
+  const float nanf_ = __int_as_float(0x7FC00000);
+  FRange ux{nanf_, nanf_}, uy{nanf_, nanf_};
+#pragma unroll
+  for (int L = 0; L < NL; L++) {
+    const uint4 c = __ldg(p.sum_in[L] + cells2d_index(p, strip, kb, lane));
+    ux = fmerge(ux, FRange{__uint_as_float(c.x), __uint_as_float(c.y)});
+    uy = fmerge(uy, FRange{__uint_as_float(c.z), __uint_as_float(c.w)});
+  }
+  cells2d_decide(p, ux, uy, own, e, y0, NL);
+}
+
+static size_t c2_smem_bytes() { return (size_t)C2_NST * TL_SEG * 8 + (size_t)2 * C2_NST * 8; }
+
+size_t scan2d_cells_per_layer(const SweepParams &p) { return (size_t)p.nsx * C2_CW * (size_t)(p.H / C2_R + 2) * 32u; }
+
+void launch_scan2d_cells(const SweepParams &p, cudaStream_t s) {
+  const unsigned grid = (unsigned)((i64)p.nsx * p.nsy);
+  const int nstrips = (p.W + FB_STRIDE - 1) / FB_STRIDE, nblk = (p.H + C2_R - 1) / C2_R;
+  const unsigned tgrid = (unsigned)(((i64)nstrips * nblk + 7) / 8);
+  switch (p.sum_mode) {
+    case SUM_BUILD: scan2d_build_kernel<0, false><<<grid, (C2_CW + 1) * 32, c2_smem_bytes(), s>>>(p); break;
+    case SUM_BUILD_TEST1: scan2d_build_kernel<0, true><<<grid, (C2_CW + 1) * 32, c2_smem_bytes(), s>>>(p); break;
+    case SUM_BUILD_TEST2: scan2d_build_kernel<1, true><<<grid, (C2_CW + 1) * 32, c2_smem_bytes(), s>>>(p); break;
+    case SUM_TEST1: scan2d_cells_kernel<1><<<tgrid, 256, 0, s>>>(p, nstrips, nblk); break;
+    default: scan2d_cells_kernel<2><<<tgrid, 256, 0, s>>>(p, nstrips, nblk); break;
+  }
+}
+
 // ---- 3D, scalar input: gradient (grad.hh:130-149) fused into the scan, planes staged by TMA -----------
 // The vector field is never materialised.  A CTA owns a tile of F3_STRIDE x F3_TROWS corner columns and
 // marches along z over a chunk of planes.  One producer warp keeps a ring of F3_NST scalar planes (both
@@ -898,43 +1144,52 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *tm,
 
 __device__ __forceinline__ float hikey(double d) { return __int_as_float(__double2hiint(d)); }
 
-// cold path: the lane's cubes (columns e, e+1; rows y0 .. y0+F3_RW-1; plane z) one by one, ranges over the
-// vertices valid simplices can use (<= ub), read from global memory; same key logic as the vector-layer scan
-__device__ __noinline__ void fused3d_slow_cubes(const SweepParams &p, const bool need, const int e, const int y0, const int z, const int nl) {
+// cold path: for every lane whose union failed (bit set in failmask), the WARP tests that lane's 2 x F3_RW cubes of
+// plane z: four lanes per cube, two vertices each (ranges over the vertices valid simplices can use, <= ub, read from
+// global memory with the same key logic as the vector-layer scan), combined by shuffles; survivors are appended.
+// Warp-wide so that a failing lane costs a couple of memory round trips instead of several hundred serialised loads.
+__device__ __noinline__ void fused3d_slow_cubes(const SweepParams &p, unsigned failmask, const int C0, const int y0, const int z, const int nl) {
+  static_assert(2 * F3_RW * 4 == 32, "four lanes per cube");
+  const int lane = threadIdx.x & 31;
   const int nbits20 = (p.nbits - 1) << 20;
   const size_t sy = (size_t)p.W, sz = (size_t)p.W * (size_t)p.H;
-#pragma unroll 1
-  for (int r = 0; r < F3_RW; r++) {
-    const int y = y0 + r;
-#pragma unroll 1
-    for (int q = 0; q < 2; q++) {
-      const int x = e + q;
-      bool surv = false;
-      if (need && x >= p.lb[0] && x <= p.ub[0] && y >= p.lb[1] && y <= p.ub[1]) {
-        KeyRange rg[3] = {neutral_range(), neutral_range(), neutral_range()};
-#pragma unroll 1
-        for (int v = 0; v < 8; v++) {
-          const int vx = x + (v & 1), vy = y + ((v >> 1) & 1), vz = z + (v >> 2);
-          if (vx > p.ub[0] || vy > p.ub[1] || vz > p.ub[2]) continue;
-          const bool border = vx < 1 || vx > p.W - 2 || vy < 1 || vy > p.H - 2 || vz < 1 || vz > p.D - 2;
-          const size_t idx = (size_t)vx + sy * (size_t)vy + sz * (size_t)vz;
-          for (int L = 0; L < nl; L++) {
-            const double *S = p.L[L].S;
-            int h0 = 0, h1 = 0, h2 = 0;
-            if (!border) {
-              h0 = __double2hiint(__ldg(S + idx + 1) - __ldg(S + idx - 1));
-              h1 = __double2hiint(__ldg(S + idx + sy) - __ldg(S + idx - sy));
-              h2 = __double2hiint(__ldg(S + idx + sz) - __ldg(S + idx - sz));
-            }
-            rg[0] = merge(rg[0], vertex_range(h0, nbits20));
-            rg[1] = merge(rg[1], vertex_range(h1, nbits20));
-            rg[2] = merge(rg[2], vertex_range(h2, nbits20));
-          }
+  const int cube = lane >> 2, sub = lane & 3;
+  const int r = cube >> 1, q = cube & 1;
+  while (failmask) {
+    const int src = __ffs(failmask) - 1;
+    failmask &= failmask - 1;
+    const int x = C0 + 2 * src + q, y = y0 + r;
+    const bool in = x >= p.lb[0] && x <= p.ub[0] && y >= p.lb[1] && y <= p.ub[1];
+    KeyRange rg[3] = {neutral_range(), neutral_range(), neutral_range()};
+#pragma unroll
+    for (int vv = 0; vv < 2; vv++) {
+      const int v = 2 * sub + vv;
+      const int vx = x + (v & 1), vy = y + ((v >> 1) & 1), vz = z + (v >> 2);
+      if (!in || vx > p.ub[0] || vy > p.ub[1] || vz > p.ub[2]) continue;
+      const bool border = vx < 1 || vx > p.W - 2 || vy < 1 || vy > p.H - 2 || vz < 1 || vz > p.D - 2;
+      const size_t idx = (size_t)vx + sy * (size_t)vy + sz * (size_t)vz;
+      for (int L = 0; L < nl; L++) {
+        const double *S = p.L[L].S;
+        int h0 = 0, h1 = 0, h2 = 0;
+        if (!border) {
+          h0 = __double2hiint(__ldg(S + idx + 1) - __ldg(S + idx - 1));
+          h1 = __double2hiint(__ldg(S + idx + sy) - __ldg(S + idx - sy));
+          h2 = __double2hiint(__ldg(S + idx + sz) - __ldg(S + idx - sz));
         }
-        surv = !cube_excluded3(rg[0], rg[1], rg[2]);
+        rg[0] = merge(rg[0], vertex_range(h0, nbits20));
+        rg[1] = merge(rg[1], vertex_range(h1, nbits20));
+        rg[2] = merge(rg[2], vertex_range(h2, nbits20));
       }
-      append_survivors(p, surv, (u64)(x - p.lb[0]) + (u64)p.nc[0] * ((u64)(y - p.lb[1]) + (u64)p.nc[1] * (u64)(z - p.lb[2])));
     }
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+#pragma unroll
+      for (int off = 1; off <= 2; off <<= 1) {
+        rg[c].mn = min(rg[c].mn, __shfl_xor_sync(0xffffffffu, rg[c].mn, off));
+        rg[c].mx = max(rg[c].mx, __shfl_xor_sync(0xffffffffu, rg[c].mx, off));
+      }
+    const bool surv = in && sub == 0 && !cube_excluded3(rg[0], rg[1], rg[2]);
+    append_survivors(p, surv, (u64)(x - p.lb[0]) + (u64)p.nc[0] * ((u64)(y - p.lb[1]) + (u64)p.nc[1] * (u64)(z - p.lb[2])));
   }
 }
 
@@ -1084,7 +1339,7 @@ __device__ __forceinline__ void fused3d_consume(const SweepParams &p, const unsi
         bool excl = sided && esum <= esum_max && !(cmn[0] != cmn[0]);
         if (sided && !excl && own_any) excl = fused3d_union_excluded_precise(cmn[0], cmx[0], cmn[1], cmx[1], cmn[2], cmx[2], nbits20);
         const bool fail = own_any && !excl;
-        if (__any_sync(0xffffffffu, fail)) fused3d_slow_cubes(p, fail, e, y0, zc, NL);
+        { const unsigned fm = __ballot_sync(0xffffffffu, fail); if (fm) fused3d_slow_cubes(p, fm, C0, y0, zc, NL); }
       }
     }
 #pragma unroll
@@ -1161,7 +1416,8 @@ __global__ void __launch_bounds__((F3_CW + 1) * 32, 1) scan3d_fused_kernel(const
 // consumer thread keeps a three-plane register window of its 2 columns x (S3_RW + 3) rows, so a plane is read
 // from shared memory once (plus the two x-neighbour columns while it is the centre plane).
 constexpr int S3_RW = F3_RW;                       // corner rows per consumer warp
-constexpr int S3_WR = S3_RW + 3;                   // window rows: y0-1 .. y0+RW+1
+constexpr int S3_WR = S3_RW + 1;                   // window rows per plane: the gradient rows y0 .. y0+RW (the two halo rows of the
+                                                   // centre plane are re-read from shared memory while it is the centre)
 constexpr int S3_NST = 5;                          // ring stages (planes)
 constexpr int S3_STAGE_BYTES = F3_LAYER_BYTES;
 
@@ -1222,7 +1478,8 @@ __device__ __forceinline__ void s3_test(const SweepParams &p, const S3Thresholds
     if (!excl) excl = s3_union_excluded_precise(cmn[0], cmx[0], cmn[1], cmx[1], cmn[2], cmx[2], T.nbits20);
   }
   const bool fail = own_any && !excl;
-  if (__any_sync(0xffffffffu, fail)) fused3d_slow_cubes(p, fail, e, y0, zc, nl);
+  const unsigned fm = __ballot_sync(0xffffffffu, fail);
+  if (fm) fused3d_slow_cubes(p, fm, e - 2 * (int)(threadIdx.x & 31), y0, zc, nl);
 }
 
 __device__ __forceinline__ size_t s3_cell_index(const SweepParams &p, const int tile, const int wib, const int z, const int lane) {
@@ -1278,7 +1535,7 @@ struct S3Build {
   uint4 *sum_out;            // cells of the layer being built, likewise
 
   __device__ __forceinline__ void load_plane(double2 (&P)[S3_WR], const int st) const {
-    const uint32_t base = ring + (uint32_t)st * S3_STAGE_BYTES + lane_off + 16u;
+    const uint32_t base = ring + (uint32_t)st * S3_STAGE_BYTES + lane_off + (uint32_t)(F3_COLS * 8) + 16u;
 #pragma unroll
     for (int r = 0; r < S3_WR; r++) P[r] = lds_f64x2(base + (uint32_t)(r * F3_COLS * 8));
   }
@@ -1314,6 +1571,7 @@ struct S3Build {
     const bool zarr = zg >= 1 && zg <= p.D - 2;
     const bool zdom = zg >= p.lb[2] && zg <= p.ub[2];
     const bool res_now = want_res && zarr;
+    const double2 top = lds_f64x2(cen - (uint32_t)(F3_COLS * 8) + 16u), bot = lds_f64x2(cen + (uint32_t)((S3_RW + 1) * F3_COLS * 8) + 16u);
     float umin[3] = {nanf_, nanf_, nanf_}, umax[3] = {nanf_, nanf_, nanf_};
     int big = 0;
     unsigned mk = masks;
@@ -1321,10 +1579,11 @@ struct S3Build {
 #pragma unroll
     for (int r = 0; r <= S3_RW; r++) {
       const double left = lds_f64(cen + (uint32_t)(r * F3_COLS * 8 + 8)), right = lds_f64(cen + (uint32_t)(r * F3_COLS * 8 + 32));
-      const double2 rc = zc[r + 1];
+      const double2 rc = zc[r];
+      const double2 up = r == S3_RW ? bot : zc[r == S3_RW ? r : r + 1], dn = r == 0 ? top : zc[r == 0 ? r : r - 1];
       const double dxe = rc.y - left, dxo = right - rc.x;
-      const double dye = zc[r + 2].x - zc[r].x, dyo = zc[r + 2].y - zc[r].y;
-      const double dze = zp[r + 1].x - zm[r + 1].x, dzo = zp[r + 1].y - zm[r + 1].y;
+      const double dye = up.x - dn.x, dyo = up.y - dn.y;
+      const double dze = zp[r].x - zm[r].x, dzo = zp[r].y - zm[r].y;
       float kxe = hikey(dxe), kxo = hikey(dxo), kye = hikey(dye), kyo = hikey(dyo), kze = hikey(dze), kzo = hikey(dzo);
       big = max(big, max(__double2hiint(rc.x) & 0x7fffffff, __double2hiint(rc.y) & 0x7fffffff));   // NaN / Inf patterns compare high
       if (res_now) {
@@ -1494,7 +1753,7 @@ __global__ void __launch_bounds__(F3_CW * 32, 2) scan3d_build_kernel(const __gri
 
 // cells only: the final ordinal sweep (one layer) and re-sweeps (both layers' cells exist)
 template <int NL>
-__global__ void __launch_bounds__(F3_CW * 32) scan3d_cells_kernel(const SweepParams p) {
+__global__ void __launch_bounds__(F3_CW * 32) scan3d_cells_kernel(const __grid_constant__ SweepParams p) {
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
   int b = blockIdx.x;
@@ -1574,6 +1833,9 @@ void init_kernel_attributes() {
   cudaFuncSetAttribute(scan2d_bulk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bulk_smem_bytes(false));
   cudaFuncSetAttribute(scan3d_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused3d_smem_bytes(true));
   cudaFuncSetAttribute(scan3d_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused3d_smem_bytes(false));
+  cudaFuncSetAttribute(scan2d_build_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c2_smem_bytes());
+  cudaFuncSetAttribute(scan2d_build_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c2_smem_bytes());
+  cudaFuncSetAttribute(scan2d_build_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c2_smem_bytes());
   cudaFuncSetAttribute(scan3d_build_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s3_smem_bytes());
   cudaFuncSetAttribute(scan3d_build_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s3_smem_bytes());
   cudaFuncSetAttribute(scan3d_build_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s3_smem_bytes());

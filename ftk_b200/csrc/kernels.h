@@ -87,6 +87,9 @@ enum { SUM_BUILD = 0,          // stream layer build_layer, write its cells (+ m
        SUM_TEST2 = 4 };        // cells of L[0] and L[1] (repeats)
 void launch_scan3d_cells(const SweepParams &p, cudaStream_t s);
 size_t scan3d_cells_per_layer(const SweepParams &p);
+constexpr int SCAN2D_CELL_ROWS = 9;
+void launch_scan2d_cells(const SweepParams &p, cudaStream_t s);     // needs p.bulk == 2 geometry with p.rows a multiple of SCAN2D_CELL_ROWS
+size_t scan2d_cells_per_layer(const SweepParams &p);
 // thread-per-(surviving cube, type) exact test; grid sized for `expected` cubes, grid-stride otherwise
 void launch_test(const SweepParams &p, cudaStream_t s);
 
