@@ -9,6 +9,7 @@ from . import _lib
 from .tracker import (Lattice, critical_point_tracker_2d_regular, critical_point_tracker_3d_regular,  # noqa: F401
                       critical_point_type_to_string, make_tracker, track, SOURCE_NONE, SOURCE_GIVEN, SOURCE_DERIVED)
 from . import trackers, extractors, synthesizers  # noqa: F401
+from .curves import CurveSet  # noqa: F401
 
 __version__ = "0.1.0"
 lattice = Lattice

@@ -48,6 +48,16 @@ POINT_DTYPE = np.dtype([
 ], align=True)
 assert POINT_DTYPE.itemsize == 72
 
+# ftkb_curve_point / ftkb_curve_info (trajectory post-processing)
+CURVE_POINT_DTYPE = np.dtype([("p", POINT_DTYPE), ("v", np.float64, 3), ("id", np.int32), ("reserved", np.int32)], align=True)
+assert CURVE_POINT_DTYPE.itemsize == 104
+CURVE_INFO_DTYPE = np.dtype([
+    ("id", np.int32), ("loop", np.int32), ("complete", np.int32), ("consistent_type", np.uint32), ("first", np.uint64), ("count", np.uint64),
+    ("tmin", np.float64), ("tmax", np.float64), ("bbmin", np.float64, 3), ("bbmax", np.float64, 3),
+    ("smin", np.float64), ("smax", np.float64), ("persistence", np.float64), ("vmmin", np.float64), ("vmmax", np.float64),
+], align=True)
+assert CURVE_INFO_DTYPE.itemsize == 136
+
 # every symbol include/ftkb200.h declares
 EXPORTS = [
     "ftkb_abi_version", "ftkb_device_count", "ftkb_create", "ftkb_destroy", "ftkb_last_error", "ftkb_push_snapshot",
@@ -56,6 +66,8 @@ EXPORTS = [
     "ftkb_num_trajectories", "ftkb_get_trajectories", "ftkb_get_component_labels", "ftkb_get_degrees", "ftkb_get_last_worklist", "ftkb_get_stats",
     "ftkb_reset_stats", "ftkb_synchronize", "ftkb_timer_start", "ftkb_timer_stop", "ftkb_mesh_ntypes", "ftkb_mesh_unit_simplex", "ftkb_mesh_scope_type",
     "ftkb_mesh_sides", "ftkb_mesh_side_of",
+    "ftkb_curveset_create", "ftkb_get_curveset", "ftkb_curveset_destroy", "ftkb_curveset_post_process", "ftkb_curveset_size",
+    "ftkb_curveset_get", "ftkb_curveset_last_error",
 ]
 
 _lib = None
@@ -103,5 +115,14 @@ def lib():
     L.ftkb_mesh_scope_type.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int]
     L.ftkb_mesh_sides.argtypes = [C.c_int, C.c_int, C.c_int, vp]
     L.ftkb_mesh_side_of.argtypes = [C.c_int, C.c_int, C.c_int, vp]
+    L.ftkb_curveset_create.argtypes = [vp, C.c_uint64, vp, vp, vp, C.c_uint64, C.POINTER(vp)]
+    L.ftkb_get_curveset.argtypes = [vp, C.POINTER(vp)]
+    L.ftkb_curveset_destroy.argtypes = [vp]
+    L.ftkb_curveset_destroy.restype = None
+    L.ftkb_curveset_post_process.argtypes = [vp, C.c_char_p]
+    L.ftkb_curveset_size.argtypes = [vp, u64p, u64p]
+    L.ftkb_curveset_get.argtypes = [vp, vp, vp]
+    L.ftkb_curveset_last_error.argtypes = [vp]
+    L.ftkb_curveset_last_error.restype = C.c_char_p
     _lib = L
     return L

@@ -26,7 +26,7 @@ namespace {
 
 struct Options {
   std::string feature = "cp", input, input_format = "float64", synthetic, output, output_type = "traced", output_format = "auto";
-  std::string type_filter, accelerator = "cuda", var;
+  std::string type_filter, accelerator = "cuda", var, post_process;
   long width = -1, height = -1, depth = -1, timesteps = -1;
   int device = 0, nthreads = 0;
   bool timing = false, compute_degrees = false, no_robust = false, verbose = false, device_generators = false, help = false;
@@ -53,6 +53,7 @@ void usage() {
       "      --output-type traced|discrete     (default traced)\n"
       "      --output-format text|json         (default: by file name, .json -> json, else text)\n"
       "      --type-filter min|max|saddle|...  (2D; names joined with |)\n"
+      "      --post-process OPS                smooth_types,rotate,split,discard_interval_points,reorder,adjust_time,derive_velocity,...\n"
       "      --compute-degrees  --no-robust-detection  --timing  -v/--verbose\n"
       "  -a, --accelerator cuda            (the only back end)   --device ID   --nthreads N (ignored)\n"
       "      --device-generators           synthesise inputs on the GPU (CUDA libm; not bit-identical to the host generators)");
@@ -102,7 +103,8 @@ Options parse(int argc, char **argv) {
     else if (a == "--device-generators") o.device_generators = true;
     else if (a == "-v" || a == "--verbose") o.verbose = true;
     else if (a == "--help") o.help = true;
-    else if (a == "--stream" || a == "--post-process") die(a + " is not implemented (SURVEY.md 8 f3/f4)");
+    else if (a == "--post-process") o.post_process = need(i);      // src/cli/ftk.cpp:253-257, :971
+    else if (a == "--stream") die(a + " is not implemented (SURVEY.md 8 f4)");
     else die("unknown option " + a);
   }
   return o;
@@ -290,7 +292,10 @@ int main(int argc, char **argv) {
       if (k == T - 1) tr->update_timestep();
     }
     const double t_compute = now();
-    if (o.output_type == "traced") tr->finalize();
+    if (o.output_type == "traced") {
+      tr->finalize();
+      if (!o.post_process.empty()) tr->post_process(o.post_process);     // feature_curve_set_post_processor_t(ops).filter(trajs)
+    }
     const double t_final = now();
 
     std::string fmt = o.output_format;

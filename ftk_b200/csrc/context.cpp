@@ -969,6 +969,15 @@ extern "C" int ftkb_get_trajectories(ftkb_ctx *c, uint64_t *offsets, uint64_t *p
   return FTKB_OK;
 }
 
+extern "C" int ftkb_get_curveset(ftkb_ctx *c, ftkb_curveset **out) {
+  if (!c || !out) return FTKB_ERR_INVALID;
+  if (!c->traced) return fail(c, FTKB_ERR_INVALID, "get_curveset: call finalize first");
+  const uint64_t ntraj = c->traj_off.empty() ? 0 : c->traj_off.size() - 1;
+  static const uint64_t zero = 0;
+  return ftkb_curveset_create(c->pts_sorted.data(), c->pts_sorted.size(), ntraj ? c->traj_off.data() : &zero, c->traj_idx.data(),
+                              c->traj_loop.data(), ntraj, out);
+}
+
 extern "C" int ftkb_get_component_labels(ftkb_ctx *c, uint64_t *labels) {
   if (!c || !labels) return FTKB_ERR_INVALID;
   if (!c->traced) return fail(c, FTKB_ERR_INVALID, "get_component_labels: call finalize first");

@@ -364,6 +364,42 @@ class critical_point_tracker_regular {
     }
   }
 
+  // ---- trajectory post-processing: feature_curve_set_post_processor.hh:23-70 (op list), json_interface.hh:758-800
+  // ("legacy[:duration_threshold[:discard_interval_points[:derive_velocities]]]").  The curve operations run in the
+  // library (ftkb_curveset_*); the traced set is replaced by the processed curves, in the multimap's order.
+  void post_process(const std::string &ops = "legacy") {
+    need();
+    ftkb_curveset *cs = nullptr;
+    check(ftkb_get_curveset(ctx_, &cs));
+    if (ftkb_curveset_post_process(cs, ops.c_str()) != FTKB_OK) {
+      const std::string msg = ftkb_curveset_last_error(cs);
+      ftkb_curveset_destroy(cs);
+      throw std::runtime_error("ftk_b200: " + msg);
+    }
+    uint64_t nc = 0, np = 0;
+    ftkb_curveset_size(cs, &nc, &np);
+    std::vector<ftkb_curve_info> infos(nc ? nc : 1);
+    std::vector<ftkb_curve_point> pts(np ? np : 1);
+    ftkb_curveset_get(cs, infos.data(), pts.data());
+    ftkb_curveset_destroy(cs);
+    traced_.clear();
+    for (uint64_t i = 0; i < nc; i++) {
+      const ftkb_curve_info &in = infos[i];
+      feature_curve_t c;
+      for (uint64_t k = in.first; k < in.first + in.count; k++) {
+        feature_point_t p = to_feature_point(pts[k].p);
+        p.v = {{pts[k].v[0], pts[k].v[1], pts[k].v[2]}};
+        p.id = (unsigned long long)pts[k].id;
+        c.push_back(p);
+      }
+      c.id = in.id; c.loop = in.loop != 0; c.complete = in.complete != 0; c.consistent_type = in.consistent_type;
+      c.tmin = in.tmin; c.tmax = in.tmax;
+      c.min = {{in.smin, 0, 0}}; c.max = {{in.smax, 0, 0}}; c.persistence = {{in.persistence, 0, 0}};
+      c.bbmin = {{in.bbmin[0], in.bbmin[1], in.bbmin[2]}}; c.bbmax = {{in.bbmax[0], in.bbmax[1], in.bbmax[2]}};
+      traced_.insert(std::make_pair(in.id, c));
+    }
+  }
+
   // ---- results: critical_point_tracker.hh:68-69,105, critical_point_tracker_regular.hh:24-38 ------
   const feature_curve_set_t &get_traced_critical_points() const { return traced_; }
   feature_curve_set_t &get_traced_critical_points() { return traced_; }
@@ -397,10 +433,14 @@ class critical_point_tracker_regular {
     std::vector<ftkb_point> raw(n ? n : 1);
     if (n) check(ftkb_get_points(ctx_, raw.data(), n));
     points_.assign(n, feature_point_t());
+    for (uint64_t i = 0; i < n; i++) points_[i] = to_feature_point(raw[i]);
+    points_valid_ = true;
+  }
+
+  feature_point_t to_feature_point(const ftkb_point &r) const {
     const unsigned long long ntypes = nd_ == 2 ? 12 : 60;
-    for (uint64_t i = 0; i < n; i++) {
-      const ftkb_point &r = raw[i];
-      feature_point_t &p = points_[i];
+    feature_point_t p;
+    {
       p.x = {{r.x[0], r.x[1], r.x[2]}};
       p.t = r.t;
       p.timestep = r.timestep;
@@ -416,7 +456,7 @@ class critical_point_tracker_regular {
       rank += (unsigned long long)r.corner[3] * prod;
       p.tag = rank * ntypes + (unsigned long long)r.simplex_type;
     }
-    points_valid_ = true;
+    return p;
   }
 
   int nd_;

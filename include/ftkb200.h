@@ -156,6 +156,43 @@ int ftkb_get_trajectories(ftkb_ctx *, uint64_t *offsets /* n+1 */, uint64_t *poi
 int ftkb_get_component_labels(ftkb_ctx *, uint64_t *labels);
 int ftkb_get_degrees(ftkb_ctx *, int32_t *deg);
 
+/* ---- trajectory post-processing (host code) ----------------------------------------------------
+ * A curve set holds the traced trajectories as mutable curves -- the reference's feature_curve_set_t, a multimap
+ * keyed by curve id (include/ftk/features/feature_curve_set.hh:21-70, :447-532) -- and applies the reference's
+ * per-curve operations (include/ftk/features/feature_curve.hh:113-417).  ops is a comma-separated list as
+ * feature_curve_set_post_processor_t takes it (include/ftk/filters/feature_curve_set_post_processor.hh:23-70):
+ *   smooth_types, rotate, split, discard_interval_points, reorder, adjust_time, derive_velocity,
+ *   duration_pruning:THRESHOLD, plus discard_degenerate_points, update_statistics, and
+ *   legacy[:duration_threshold[:discard_interval_points[:derive_velocities]]] = json_interface::post_process()
+ *   (include/ftk/filters/json_interface.hh:758-800).
+ * An unknown op returns FTKB_ERR_INVALID (the reference calls fatal()). */
+typedef struct ftkb_curve_point {
+  ftkb_point p;               /* cp_type and t are what post-processing may change */
+  double v[3];                /* derive_velocity; zero before */
+  int32_t id;                 /* id of the curve the point was traced into (feature_point_t::id) */
+  int32_t reserved;
+} ftkb_curve_point;
+
+typedef struct ftkb_curve_info {
+  int32_t id, loop, complete;
+  uint32_t consistent_type;   /* 0 if the curve's points disagree, or before any update_statistics */
+  uint64_t first, count;      /* the curve's points in the array ftkb_curveset_get fills */
+  double tmin, tmax, bbmin[3], bbmax[3];
+  double smin, smax, persistence, vmmin, vmmax;   /* statistics of scalar[0] and of |v| (feature_curve.hh:145-186) */
+} ftkb_curve_info;
+
+typedef struct ftkb_curveset ftkb_curveset;
+/* trajectories as CSR over a point array (what ftkb_get_trajectories returns); curves get ids 0 .. ntraj-1 */
+int ftkb_curveset_create(const ftkb_point *pts, uint64_t npts, const uint64_t *offsets, const uint64_t *point_idx,
+                         const uint8_t *loop, uint64_t ntraj, ftkb_curveset **out);
+/* get_traced_critical_points() of a finalized context; the caller destroys the set */
+int ftkb_get_curveset(ftkb_ctx *, ftkb_curveset **out);
+void ftkb_curveset_destroy(ftkb_curveset *);
+int ftkb_curveset_post_process(ftkb_curveset *, const char *ops);
+int ftkb_curveset_size(const ftkb_curveset *, uint64_t *ncurves, uint64_t *npoints);
+int ftkb_curveset_get(const ftkb_curveset *, ftkb_curve_info *infos /* ncurves */, ftkb_curve_point *pts /* npoints */);
+const char *ftkb_curveset_last_error(const ftkb_curveset *);
+
 /* diagnostic: the cubes (linear corner index over the domain, x fastest) that the most recent sweep's
  * scan kernel left for the exact test; *n receives the count, at most cap entries are copied */
 int ftkb_get_last_worklist(ftkb_ctx *, uint64_t *out, uint64_t cap, uint64_t *n);

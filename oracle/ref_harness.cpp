@@ -15,11 +15,15 @@
 //                  (--gen NAME [--p a b c ...] | --input raw.f64)
 //                  [--domain lb0 ub0 lb1 ub1 [lb2 ub2]] [--symmetric 0|1] [--nthreads N]
 //                  [--no-trace] [--out file.ftkg] [--dump-input raw.f64] [--quiet]
+//                  [--post OPS --out-curves file.ftkc]   trajectory post-processing by the reference's own curve code:
+//                  OPS as feature_curve_set_post_processor_t takes them, plus legacy[:thr[:discard[:velocity]]] = the
+//                  call sequence of json_interface::post_process() (json_interface.hh:758-800) on the same methods
 //   raw.f64 holds T consecutive snapshots, each (nv, W, H[, D]) float64 with dim 0 fastest.
 
 #include <ftk/filters/critical_point_tracker_2d_regular.hh>
 #include <ftk/filters/critical_point_tracker_3d_regular.hh>
 #include <ftk/ndarray/synthetic.hh>
+#include <ftk/filters/feature_curve_set_post_processor.hh>
 #include <chrono>
 #include <cstdio>
 #include <cstring>
@@ -34,7 +38,7 @@ struct args_t {
   int symmetric = -1;
   bool trace = true, quiet = false, have_domain = false;
   int dom[6] = {0, 0, 0, 0, 0, 0};
-  std::string gen, input, out, dump_input;
+  std::string gen, input, out, dump_input, post, out_curves;
   std::vector<double> p;
 };
 
@@ -158,6 +162,53 @@ static int run(const args_t &a)
     ntraj = trajs.size();
   }
 
+  if (a.trace && !a.out_curves.empty()) {
+    auto &set = tr.get_traced_critical_points();
+    for (const std::string &op : ftk::split(a.post, ",")) {
+      if (op.empty()) continue;
+      if (op.rfind("legacy", 0) == 0) {          // json_interface::post_process(), same calls in the same order
+        const auto f = ftk::split(op, ":");
+        const double thr = f.size() > 1 ? atof(f[1].c_str()) : 0.0;
+        const bool disc = f.size() > 2 && atoi(f[2].c_str()), vel = f.size() > 3 && atoi(f[3].c_str());
+        set.foreach([](ftk::feature_curve_t &t) { t.smooth_ordinal_types(); t.smooth_interval_types(); t.rotate(); t.update_statistics(); });
+        if (thr > 0) set.filter([&](const ftk::feature_curve_t &t) { return !(t.tmax - t.tmin < thr); });
+        set.split_all();
+        if (disc) set.foreach([](ftk::feature_curve_t &t) { t.discard_interval_points(); });
+        set.foreach([](ftk::feature_curve_t &t) { t.reorder(); t.adjust_time(); t.update_statistics(); });
+        if (vel) set.foreach([](ftk::feature_curve_t &t) { t.discard_interval_points(); t.derive_velocity(); t.update_statistics(); });
+      } else if (op.rfind("duration_pruning:", 0) == 0) {
+        const double thr = atof(op.c_str() + 17);
+        if (thr > 0) set.filter([&](const ftk::feature_curve_t &t) { return !(t.tmax - t.tmin < thr); });
+      } else if (op == "discard_degenerate_points") {
+        set.foreach([](ftk::feature_curve_t &t) { t.discard_degenerate_points(); t.update_statistics(); });
+      } else if (op == "update_statistics") {
+        set.foreach([](ftk::feature_curve_t &t) { t.update_statistics(); });
+      } else {
+        ftk::feature_curve_set_post_processor_t pp(op);
+        pp.filter(set);
+      }
+    }
+    FILE *fc = fopen(a.out_curves.c_str(), "wb"); if (!fc) { perror("out-curves"); return 2; }
+    const uint32_t magic = 0x434b5446 /*FTKC*/, version = 1;
+    const uint64_t nc = set.size();
+    fwrite(&magic, 4, 1, fc); fwrite(&version, 4, 1, fc); fwrite(&nc, 8, 1, fc);
+    for (const auto &kv : set) {
+      const auto &t = kv.second;
+      const int32_t h[4] = {kv.first, t.loop ? 1 : 0, t.complete ? 1 : 0, (int32_t)t.consistent_type};
+      const uint64_t n = t.size();
+      const double st[13] = {t.tmin, t.tmax, t.bbmin[0], t.bbmin[1], t.bbmin[2], t.bbmax[0], t.bbmax[1], t.bbmax[2],
+                             t.min[0], t.max[0], t.persistence[0], t.vmmin, t.vmmax};
+      fwrite(h, 4, 4, fc); fwrite(&n, 8, 1, fc); fwrite(st, 8, 13, fc);
+      for (const auto &cp : t) {
+        const uint64_t idx = tag2idx.at(cp.tag);
+        const int32_t q[4] = {(int32_t)cp.type, cp.ordinal ? 1 : 0, (int32_t)cp.timestep, (int32_t)cp.id};
+        const double d[8] = {cp.x[0], cp.x[1], cp.x[2], cp.t, cp.scalar[0], cp.v[0], cp.v[1], cp.v[2]};
+        fwrite(&idx, 8, 1, fc); fwrite(q, 4, 4, fc); fwrite(d, 8, 8, fc);
+      }
+    }
+    fclose(fc);
+  }
+
   // simplices enumerated: N_core * (n_ord * T + n_int * (T-1))   
   double ncore = 1; for (int i = 0; i < nd; i ++) ncore *= double(dsz[i]);
   const int n_ord = nd == 2 ? 2 : 6, n_int = nd == 2 ? 10 : 54;
@@ -212,6 +263,8 @@ int main(int argc, char **argv)
     else if (s == "--symmetric") a.symmetric = atoi(next());
     else if (s == "--nthreads") a.nthreads = atoi(next());
     else if (s == "--no-trace") a.trace = false;
+    else if (s == "--post") a.post = next();
+    else if (s == "--out-curves") a.out_curves = next();
     else if (s == "--quiet") a.quiet = true;
     else if (s == "--domain") { a.have_domain = true; for (int j = 0; j < 2 * a.nd; j ++) a.dom[j] = atoi(next()); }
     else if (s == "--p") { while (i + 1 < argc && strncmp(argv[i+1], "--", 2) != 0) a.p.push_back(atof(argv[++i])); }

@@ -164,3 +164,32 @@ def test_cli_raw_input_matches_oracle(cli, tmp_path, oracle):
     assert r.returncode == 0, r.stderr
     got32 = _sorted_like_reference(_decode(json.load(open(out32)), dims, 1))
     P.assert_same_result({"points": got32, "trajectories": []}, {"points": o32.points(), "trajectories": []}, check_trajectories=False, tol=1e-9, what="cli float32")
+
+
+@pytest.mark.gpu
+def test_cli_post_process_matches_reference_curves(cli, tmp_path):
+    """--post-process OPS (src/cli/ftk.cpp:253-257): merger_2d, traced text after the legacy op sequence; the curves
+    (length, consistent type, loop flag) are those the unmodified reference produced for the same ops
+    (tests/golden/post/merger_32x32x100.npz, op list 0)"""
+    z = np.load(os.path.join(P.GOLDEN_DIR, "post", "merger_32x32x100.npz"))
+    ops = json.loads(bytes(z["meta"]).decode())["ops"][0]
+    out = tmp_path / "pp.txt"
+    r = subprocess.run([cli, "-f", "cp", "--synthetic", "merger_2d", "--post-process", ops, "-o", str(out)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    text = open(out).read().splitlines()
+    want = z["curves_0"]
+    assert text[0] == f"#trajectories={len(want)}"
+    got, cur = [], None
+    for line in text[1:]:
+        if line.startswith("--trajectory"):
+            if cur is not None:
+                got.append(tuple(cur))
+            m = re.search(r"consistent_type=(\d+), loop=(\d+)", line)
+            cur = [0, int(m.group(1)), int(m.group(2))]
+        elif line.startswith("---"):
+            cur[0] += 1
+    if cur is not None:
+        got.append(tuple(cur))
+    assert sorted(got) == sorted((int(c["count"]), int(c["consistent_type"]), int(c["loop"])) for c in want)
+    bad = subprocess.run([cli, "-f", "cp", "--synthetic", "merger_2d", "--post-process", "no_such_op", "-o", str(out)], capture_output=True, text=True)
+    assert bad.returncode == 1 and "unknown operation" in bad.stderr
