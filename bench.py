@@ -36,7 +36,12 @@ CONFIGS = {
     "c2": ("moving_extremum_2d_scalar_8192x8192x64", [8192, 8192], [4096.3, 4095.7, 0.1, 0.1], 64),
     "c3": ("moving_extremum_3d_scalar_512x512x512x32", [512, 512, 512], [256.3, 255.7, 256.1, 0.1, 0.11, 0.1], 32),
     "c2s": ("moving_extremum_2d_scalar_2048x2048x16", [2048, 2048], [1024.3, 1023.7, 0.1, 0.1], 16),
+    # vector input (field GIVEN, Jacobian derived at punctured simplices): BASELINE configs[3] and configs[4]
+    "c4": ("unsteady_abc_3d_vector_1024x1024x1024x64", [1024, 1024, 1024], None, 4),      # 25.8 GB per layer: 4 distinct layers resident
+    "c5": ("double_gyre_2d_vector_16384x8192x256", [16384, 8192], None, 32),
+    "c4s": ("unsteady_abc_3d_vector_256x256x256x64", [256, 256, 256], None, 8),
 }
+VECTOR_CONFIGS = ("c4", "c5", "c4s")
 METRIC = "space_time_simplices_tested_per_sec"
 UNIT = "simplices/s"
 
@@ -238,11 +243,12 @@ def main():
 
     label, dims, params, NL = CONFIGS[args.config]
     nd = len(dims)
-    x0, dirv = params[:nd], params[nd:]
+    vector = args.config in VECTOR_CONFIGS
+    x0, dirv = (params[:nd], params[nd:]) if params else (None, None)
     K, W = args.steps, args.warmup
     ncore = 1
     for d in dims:
-        ncore *= d - 3
+        ncore *= d - (2 if vector else 3)      # json_interface.hh:639-654: [1, D-2] for vector input, [2, D-2] for scalar input
     per_step = ncore * (12 if nd == 2 else 60)
     nvert = int(np.prod(dims))
 
@@ -259,18 +265,48 @@ def main():
             return out
         return s.contiguous()
 
-    layers = [gen_layer(j) for j in range(NL)]
+    def gen_vector_layer(j):
+        """C5: synthetic_double_gyre(time = 0.1 j) (synthetic.hh:130-150,193-217); C4: synthetic_abc_flow (synthetic.hh:239-260)
+        with A(j) = sqrt(3) + 0.5 (j/64) sin(pi j/64) (the time dependence is ours); memory order ([D,]H,W,n)"""
+        out = torch.empty(tuple(reversed(dims)) + (nd,), dtype=torch.float64, device=dev)
+        ax = [torch.arange(d, dtype=torch.float64, device=dev) / (d - 1) for d in dims]
+        if nd == 2:
+            A, omega, eps, t = 0.1, 2 * math.pi, 0.25, 0.1 * j
+            x, y = ax[0] * 2, ax[1]
+            a, b = eps * math.sin(omega * t), 1 - 2 * eps * math.sin(omega * t)
+            f, dfdx = a * x * x + b * x, 2 * a * x + b
+            out[..., 0] = (-math.pi * A * torch.sin(math.pi * f))[None, :] * torch.cos(math.pi * y)[:, None]
+            out[..., 1] = (math.pi * A * torch.cos(math.pi * f) * dfdx)[None, :] * torch.sin(math.pi * y)[:, None]
+        else:
+            A, B, Cc = math.sqrt(3.0) + 0.5 * (j / 64.0) * math.sin(math.pi * j / 64.0), math.sqrt(2.0), 1.0
+            x, y, z = (a * 2 * math.pi for a in ax)
+            for k0 in range(0, dims[2], 64):       # slabs of 64 planes keep the temporaries small next to 25.8 GB layers
+                zs = z[k0:k0 + 64]
+                o = out[k0:k0 + 64]
+                o[..., 0] = (A * torch.sin(zs))[:, None, None] + (Cc * torch.cos(y))[None, :, None]
+                o[..., 1] = (B * torch.sin(x))[None, None, :] + (A * torch.cos(zs))[:, None, None]
+                o[..., 2] = (Cc * torch.sin(y))[None, :, None] + (B * torch.cos(x))[None, None, :]
+        return out
+
+    layers = [gen_vector_layer(j) if vector else gen_layer(j) for j in range(NL)]
     g0 = rank * (W + K)
+    fld = "vector" if vector else "scalar"
 
     def make():
-        return ftk_b200.make_tracker(dims, field="scalar", device=local, start_timestep=g0)
+        return ftk_b200.make_tracker(dims, field=fld, device=local, start_timestep=g0)
+
+    def push_ptr(t, ptr):
+        if vector:
+            t.push_device_pointers(vector=ptr)
+        else:
+            t.push_device_pointers(scalar=ptr)
 
     # ---- device-resident measurement -------------------------------------------------------------
     tr = make()
     ptrs = [int(l.data_ptr()) for l in layers]     # resident layers are borrowed in place through the C ABI
-    tr.push_device_pointers(scalar=ptrs[tri(g0, NL)])
+    push_ptr(tr, ptrs[tri(g0, NL)])
     for i in range(W):
-        tr.push_device_pointers(scalar=ptrs[tri(g0 + i + 1, NL)])
+        push_ptr(tr, ptrs[tri(g0 + i + 1, NL)])
         tr.advance_timestep()
     halo = None
     sampler = ClockSampler(physical_gpu_index(local))
@@ -312,7 +348,7 @@ def main():
                 r.wait()
             torch.cuda.current_stream().synchronize()
             nxt = int(halo.data_ptr())
-        tr.push_device_pointers(scalar=nxt)
+        push_ptr(tr, nxt)
         tr.advance_timestep()
         if dist:
             _L.lib().ftkb_get_stats(tr._h, _C.byref(_st))   # one struct read per step: running minimum inside this slab + factor used
@@ -363,39 +399,57 @@ def main():
     finalize_ms = 1e3 * (time.perf_counter() - t0)
     tr.close()
 
+    def run_e2e():
+        nonlocal layers
+        E = max(1, min(args.e2e_steps, K))
+        NH = min(8, NL) if layers[0].numel() * 8 < (4 << 30) else 2      # pinned host copies: two are enough for 25.8 GB layers
+        E = E if NH > 2 else min(E, 2)
+        host = [torch.empty(tuple(layers[0].shape), dtype=torch.float64).pin_memory() for _ in range(NH)]
+        for j in range(NH):
+            host[j].copy_(layers[j])
+        torch.cuda.synchronize()
+        if NH == 2:       # 25.8 GB layers: the context's own copies need the room the resident series occupied
+            layers = []
+            torch.cuda.empty_cache()
+        tr2 = make()
+
+        def push_host(t, a):
+            if vector:
+                t.push_vector_field_snapshot(a)
+            else:
+                t.push_scalar_field_snapshot(a)
+
+        push_host(tr2, host[0].numpy())
+        for i in range(2):
+            push_host(tr2, host[tri(i + 1, NH)].numpy())
+            tr2.advance_timestep()
+        tr2.synchronize()
+        if dist:
+            dist.barrier()
+        tr2.reset_stats()
+        tr2.timer_start()
+        for i in range(2, 2 + E):
+            push_host(tr2, host[tri(i + 1, NH)].numpy())   # H2D inside the timed region
+            tr2.advance_timestep()                                         # counters + resolution read back every step
+        ms2 = tr2.timer_stop()
+        if dist:
+            t = torch.tensor([ms2], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms2 = float(t.item())
+        st2 = tr2.stats()
+        tr2.close()
+        return ms2, E, st2
+
     # ---- end-to-end measurement: host buffers through the same C-ABI calls ------------------------
-    E = max(1, min(args.e2e_steps, K))
-    NH = min(8, NL)
-    host = [torch.empty(tuple(reversed(dims)), dtype=torch.float64).pin_memory() for _ in range(NH)]
-    for j in range(NH):
-        host[j].copy_(layers[j])
-    torch.cuda.synchronize()
-    tr2 = make()
-    tr2.push_scalar_field_snapshot(host[0].numpy())
-    for i in range(2):
-        tr2.push_scalar_field_snapshot(host[tri(i + 1, NH)].numpy())
-        tr2.advance_timestep()
-    tr2.synchronize()
-    if dist:
-        dist.barrier()
-    tr2.reset_stats()
-    tr2.timer_start()
-    for i in range(2, 2 + E):
-        tr2.push_scalar_field_snapshot(host[tri(i + 1, NH)].numpy())   # H2D inside the timed region
-        tr2.advance_timestep()                                         # counters + resolution read back every step
-    ms2 = tr2.timer_stop()
-    if dist:
-        t = torch.tensor([ms2], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms2 = float(t.item())
-    st2 = tr2.stats()
-    tr2.close()
+    ms2, E, st2 = None, 0, None
+    if args.e2e_steps > 0:
+        ms2, E, st2 = run_e2e()
 
     if rank == 0:
         peak, peak_src = measured_peaks()
         nscan = max(int(st["scan_launches"]), 1)
         scan_ms = st["ms_scan"] / nscan
-        fused = st["ms_derive"] == 0.0   # scalar input: gradient fused into the scan, the vector field is never materialised
+        fused = (not vector) and st["ms_derive"] == 0.0   # scalar input: gradient fused into the scan, the vector field is never materialised
         # algorithmic bytes of one scan launch (DESIGN.md "Kernels"): the two input layers read once each
         # (fused: fp64 scalar layers, 8 B/vertex; otherwise fp64 vector layers, nd*8 B/vertex) + 72-B hit records
         in_bytes = 2 * nvert * (1 if fused else nd) * 8
@@ -413,7 +467,9 @@ def main():
         # (DESIGN.md 4.2); FTKB_SCAN2D / FTKB_SCAN3D = twolayer selects the kernels that re-read both layers
         cells = fused and os.environ.get("FTKB_SCAN2D" if nd == 2 else "FTKB_SCAN3D", "") not in ("twolayer", "plain") \
             and os.environ.get("FTKB_SCAN", "tile") == "tile"
-        if nd == 2:
+        if vector:
+            kname = "scan2d_kernel<true>" if nd == 2 else "scan3d_kernel<true>"
+        elif nd == 2:
             kname = "scan2d_build_kernel<1,true>" if cells else "scan2d_tile_kernel<true>"
         else:
             kname = "scan3d_build_kernel<1,true>" if cells else ("scan3d_fused_kernel<true>" if fused else "scan3d_kernel<true>")
@@ -440,15 +496,15 @@ def main():
                                                   "note": "SURVEY.md 8(d) assumes materialised fp64 vector layers; the fused kernel reads the scalar layers instead"},
                          "note": "rank 0; tensor cores unused by design (no dense contraction on this path)"},
             "kernel_ms_per_step": {"derive": st["ms_derive"] / K, "scan": scan_ms, "test": st["ms_test"] / K},
-            "e2e": {"value": per_step * E * world / (ms2 * 1e-3), "unit": UNIT, "steps": E, "ms_per_step": ms2 / E,
-                    "h2d_bytes_per_step": st2["h2d_bytes"] / E, "d2h_bytes_per_step": st2["d2h_bytes"] / E,
-                    "api": "ftkb_push_snapshot(host) + ftkb_advance_timestep"},
+            "e2e": ({"value": per_step * E * world / (ms2 * 1e-3), "unit": UNIT, "steps": E, "ms_per_step": ms2 / E,
+                     "h2d_bytes_per_step": st2["h2d_bytes"] / E, "d2h_bytes_per_step": st2["d2h_bytes"] / E,
+                     "api": "ftkb_push_snapshot(host) + ftkb_advance_timestep"} if E else None),
             "gpu_launches": int(st["kernel_launches"]),
             "clocks": sampler.result(),
             "finalize_ms": finalize_ms, "trajectories": ntraj, "punctured_simplices": int(npts_total),
             "cells_refined_per_step": st["cells_refined"] / K, "slab_refactor_steps": redo,
         }
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and not vector:
             line["cpu_baseline"] = cpu_baseline_sample(args.config)
         print(json.dumps(line), flush=True)
     if dist:

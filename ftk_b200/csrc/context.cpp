@@ -57,6 +57,7 @@ struct ftkb_ctx {
   int next_slot = 0;
   int sm_count = 148;
   int scan_mode = 2;             // FTKB_SCAN=ldg|warp|tile selects the fused scan's staging (A/B measurements); default tile
+  bool cellsV = true;            // same for vector input (field GIVEN); FTKB_VSCAN=twolayer re-reads both layers and runs the resolution pass
   bool cells2d = true;           // same for the fused 2D tile scan; FTKB_SCAN2D=twolayer re-reads both layers every step
   bool cells3d = true;           // fused 3D scan streams each layer once and keeps its range cells; FTKB_SCAN3D=twolayer re-reads both layers every step
   std::vector<uint4 *> freeCells;
@@ -185,6 +186,9 @@ extern "C" int ftkb_create(const ftkb_config *cfg, ftkb_ctx **out) {
     c->fused3d = n == 3 && cfg->vector_source == FTKB_SOURCE_DERIVED && cfg->robust_detection && cfg->dims[0] % 2 == 0 &&
                  !(e && std::string(e) == "plain");
     c->cells3d = !(e && std::string(e) == "twolayer");
+    const char *ev = std::getenv("FTKB_VSCAN");
+    c->cellsV = cfg->vector_source == FTKB_SOURCE_GIVEN && !(n == 3 && !cfg->robust_detection) && (n == 2 || cfg->dims[0] % 2 == 0) &&
+                !(ev && std::string(ev) == "twolayer");
     const char *e2 = std::getenv("FTKB_SCAN2D");
     c->cells2d = n == 2 && cfg->vector_source == FTKB_SOURCE_DERIVED && c->scan_mode == 2 && !(e2 && std::string(e2) == "twolayer");
   }
@@ -262,6 +266,11 @@ static int derive_layer(ftkb_ctx *c, Layer &l) {
     c->derive_timed = true;
     c->stats.kernel_launches++;
     fused = true;
+  }
+  if (l.V && !fused && c->cellsV && c->cfg.vector_source == FTKB_SOURCE_GIVEN && (uintptr_t)l.V % 16 == 0) {
+    // the range-cell scan streams this layer once and folds min non-zero |v| into that pass
+    l.res_pending = true;
+    return check_launch(c, "derive");
   }
   if (l.V) {
     int rc = queue_resolution(c, l, fused);
@@ -427,11 +436,11 @@ static void fused2d_decomposition(const ftkb_ctx *c, SweepParams &p) {
 }
 
 // tiles x z chunks of the fused 3D scan: about two equal waves of CTAs (one CTA per SM)
-static void fused3d_decomposition(const ftkb_ctx *c, SweepParams &p) {
+static void fused3d_decomposition(const ftkb_ctx *c, SweepParams &p, bool cells = false) {
   p.nsx = (p.W + F3_STRIDE - 1) / F3_STRIDE;
   p.nsy = (p.H + F3_TROWS - 1) / F3_TROWS;
   const int64_t tiles = (int64_t)p.nsx * p.nsy;
-  if (c->cells3d) {
+  if (c->cells3d || cells) {
     // two CTAs per SM.  CTA costs differ (edge tiles, cold paths), so aim for about six waves of CTAs and let the
     // hardware scheduler balance them, but keep at least 16 planes per CTA (3 halo planes are re-read per chunk)
     const int64_t slots = 2 * (int64_t)c->sm_count;
@@ -449,7 +458,7 @@ static void fused3d_decomposition(const ftkb_ctx *c, SweepParams &p) {
 
 static int ensure_cells(ftkb_ctx *c, Layer &l, const SweepParams &p) {
   if (l.cells) return FTKB_OK;
-  if (!c->ncells) c->ncells = c->n == 3 ? scan3d_cells_per_layer(p) : scan2d_cells_per_layer(p);
+  if (!c->ncells) c->ncells = c->n == 3 ? scan3d_cells_per_layer(p) : (p.fused ? scan2d_cells_per_layer(p) : vscan2d_cells_per_layer(p));
   if (!c->freeCells.empty()) { l.cells = c->freeCells.back(); c->freeCells.pop_back(); return FTKB_OK; }
   CK(cudaMalloc(&l.cells, sizeof(uint4) * c->ncells));
   return FTKB_OK;
@@ -487,6 +496,10 @@ static bool rows_aligned16(const ftkb_ctx *c, const double *a, const double *b) 
 
 // resolution of a layer whose vector field is derived on the fly, outside a sweep (time-slab exchange)
 static int resolve_pending(ftkb_ctx *c, Layer &l) {
+  if (l.V) {          // vector input: the plain resolution pass
+    l.res_pending = false;
+    return queue_resolution(c, l, false);
+  }
   SweepParams p{};
   fill_sweep_geometry(c, p);
   p.lb[1] = 1; p.ub[1] = 0;           // empty domain: gradient + resolution only, no cube is tested
@@ -578,6 +591,19 @@ extern "C" int ftkb_update_timestep(ftkb_ctx *c) {
   }
   const bool has_next = c->layers.size() >= 2;
   if (has_next && !c->layers[1].V && !(fused && c->layers[1].S)) return fail(c, FTKB_ERR_INVALID, "update_timestep: the next snapshot has no vector field");
+  // vector input: the range-cell scan streams each layer once and produces its min |v|; layers it cannot take now
+  // (misaligned, or pushed further ahead than this sweep reads) get the plain resolution pass
+  bool vcells = !fused && c->cellsV && c->layers[0].V && c->cfg.vector_source == FTKB_SOURCE_GIVEN;
+  for (size_t k = 0; vcells && k < (has_next ? 2u : 1u); k++)
+    if (!c->layers[k].V || (uintptr_t)c->layers[k].V % 16 != 0) vcells = false;
+  {
+    bool any = false;
+    for (size_t k = 0; k < c->layers.size(); k++) {
+      Layer &l = c->layers[k];
+      if (l.V && l.res_pending && !(vcells && k < 2)) { const int rc = resolve_pending(c, l); if (rc) return rc; any = true; }
+    }
+    if (any) CK(cudaStreamSynchronize(c->stream));
+  }
   if (has_next && fused && c->layers[1].V) return fail(c, FTKB_ERR_INVALID, "update_timestep: resident snapshots mix derived and given vector fields");
   // ref: critical_point_tracker.hh:850-864 (running minimum over every resident snapshot, every sweep).
   // Layers whose resolution the fused scan still has to produce are left out here: the sweep runs with
@@ -615,6 +641,17 @@ extern "C" int ftkb_update_timestep(ftkb_ctx *c) {
   } else if (fused) {
     p.aligned16 = rows_aligned16(c, lay[0]->S, lay[1]->S);
     fused2d_decomposition(c, p);
+  } else if (vcells && c->n == 3) {
+    fused3d_decomposition(c, p, true);
+  } else if (vcells) {
+    // warps = strips of 62 corner columns x row chunks (a multiple of the cell block); two CTAs of 8 warps per SM, about six waves
+    const int R = VSCAN2D_CELL_ROWS;
+    p.nsx = std::max(1, (p.W + 61) / 62);
+    const int64_t want = std::max<int64_t>(1, (6 * (int64_t)c->sm_count * 16) / p.nsx);
+    p.rows = std::max(2 * R, (int)((p.H + want - 1) / want));
+    p.rows = (p.rows + R - 1) / R * R;
+    p.nsy = (p.H + p.rows - 1) / p.rows;
+    p.nsz = 1;
   } else {
     p.nsx = (p.nc[0] + 30) / 31;
     if (c->n == 2) {
@@ -638,7 +675,7 @@ extern "C" int ftkb_update_timestep(ftkb_ctx *c) {
     p.lim_f = (float)(0.999 * 4.5e18 / (p.factor * p.factor));
     p.res_slot[0] = p.res_slot[1] = nullptr;
     bool pending = false;
-    if (fused)
+    if (fused || vcells)
       for (int k = 0; k < (has_next ? 2 : 1); k++)
         if (lay[k]->res_pending) { p.res_slot[k] = c->d_scalars + lay[k]->slot; pending = true; }
     p.wl = c->d_wl; p.wl_cap = c->wl_cap;
@@ -649,9 +686,9 @@ extern "C" int ftkb_update_timestep(ftkb_ctx *c) {
     c->h_scalars[ftkb_ctx::SLOT_POISON] = 0;
     CK(cudaMemcpyAsync(c->d_scalars + ftkb_ctx::SLOT_WL, c->h_scalars + ftkb_ctx::SLOT_WL, 32, cudaMemcpyHostToDevice, c->stream));
     CK(cudaEventRecord(c->ev[0], c->stream));
-    if (fused && ((c->n == 3 && c->cells3d) || (c->n == 2 && c->cells2d && p.bulk == 2))) {
+    if (vcells || (fused && ((c->n == 3 && c->cells3d) || (c->n == 2 && c->cells2d && p.bulk == 2)))) {
       // each layer is streamed once (the step that first sees it); everything else reads its 16-byte range cells
-      void (*launch_cells)(const SweepParams &, cudaStream_t) = c->n == 3 ? launch_scan3d_cells : launch_scan2d_cells;
+      void (*launch_cells)(const SweepParams &, cudaStream_t) = vcells ? launch_vscan_cells : (c->n == 3 ? launch_scan3d_cells : launch_scan2d_cells);
       int rc0 = ensure_cells(c, *lay[0], p);
       if (!rc0 && has_next) rc0 = ensure_cells(c, *lay[1], p);
       if (rc0) return rc0;
@@ -690,6 +727,13 @@ extern "C" int ftkb_update_timestep(ftkb_ctx *c) {
     }
     CK(cudaStreamSynchronize(c->stream));
     c->stats.d2h_bytes += 32;
+    if (vcells && c->h_scalars[ftkb_ctx::SLOT_POISON]) {
+      // a component was NaN-ordered by the float keys (|v| >= 2^1000, Inf): redo the step with the two-layer scan
+      c->stats.sweeps_repeated++;
+      c->cellsV = false;
+      for (Layer &l : c->layers) l.cells_valid = false;
+      return ftkb_update_timestep(c);
+    }
     if (fused && c->n == 3 && c->h_scalars[ftkb_ctx::SLOT_POISON]) {
       // a scalar was NaN / Inf / >= 2^1000: the fused scan's keys cannot bracket such values; redo the step unfused
       c->stats.sweeps_repeated++;

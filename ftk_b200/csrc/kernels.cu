@@ -1151,7 +1151,8 @@ __device__ __forceinline__ float hikey(double d) { return __int_as_float(__doubl
 __device__ __noinline__ void fused3d_slow_cubes(const SweepParams &p, unsigned failmask, const int C0, const int y0, const int z, const int nl) {
   static_assert(2 * F3_RW * 4 == 32, "four lanes per cube");
   const int lane = threadIdx.x & 31;
-  const int nbits20 = (p.nbits - 1) << 20;
+  const bool vec = !p.fused;                          // vector input: the keys are the vertices' own components
+  const int nbits20 = (p.nbits - (vec ? 0 : 1)) << 20;
   const size_t sy = (size_t)p.W, sz = (size_t)p.W * (size_t)p.H;
   const int cube = lane >> 2, sub = lane & 3;
   const int r = cube >> 1, q = cube & 1;
@@ -1171,7 +1172,10 @@ __device__ __noinline__ void fused3d_slow_cubes(const SweepParams &p, unsigned f
       for (int L = 0; L < nl; L++) {
         const double *S = p.L[L].S;
         int h0 = 0, h1 = 0, h2 = 0;
-        if (!border) {
+        if (vec) {
+          const int *Vh = reinterpret_cast<const int *>(p.L[L].V) + idx * 6 + 1;
+          h0 = __ldg(Vh); h1 = __ldg(Vh + 2); h2 = __ldg(Vh + 4);
+        } else if (!border) {
           h0 = __double2hiint(__ldg(S + idx + 1) - __ldg(S + idx - 1));
           h1 = __double2hiint(__ldg(S + idx + sy) - __ldg(S + idx - sy));
           h2 = __double2hiint(__ldg(S + idx + sz) - __ldg(S + idx - sz));
@@ -1431,13 +1435,16 @@ __device__ __forceinline__ void merge_cell(float (&mn)[3], float (&mx)[3], const
 }
 
 struct S3Thresholds { float kthr, kfloor; int esum_max, nbits20; double half_factor; };
-__device__ __forceinline__ S3Thresholds s3_thresholds(const int nbits) {
+// vec = false: keys of d = 2 v (gradient differences of a scalar layer); vec = true: keys of v itself (vector input), i.e.
+// every threshold one binade lower and every magnitude bound one bit larger
+__device__ __forceinline__ S3Thresholds s3_thresholds(const int nbits, const bool vec) {
+  const int s = vec ? 1 : 0;
   S3Thresholds t;
-  t.kthr = __int_as_float((1023 + 1 - nbits) << 20);     // key of 2^(1-nbits): |d| >= 2^(1-nbits) <=> |quantised v| >= 1
-  t.kfloor = __int_as_float((1023 - nbits) << 20);       // key of 2^-nbits: smaller magnitudes quantise to 0
-  t.esum_max = 3119 - 3 * nbits;                          // determinant guard, see fused3d_consume
-  t.nbits20 = (nbits - 1) << 20;
-  t.half_factor = __hiloint2double((1023 + nbits - 1) << 20, 0);   // v 2^nbits = d 2^(nbits-1)
+  t.kthr = __int_as_float((1023 + 1 - s - nbits) << 20);   // key of 2^(1-nbits) (d) / 2^-nbits (v): at or above it |quantised v| >= 1
+  t.kfloor = __int_as_float((1023 - s - nbits) << 20);     // half of that: smaller magnitudes quantise to 0
+  t.esum_max = 3119 - 3 * s - 3 * nbits;                    // determinant guard, see fused3d_consume
+  t.nbits20 = (nbits - 1 + s) << 20;
+  t.half_factor = __hiloint2double((1023 + nbits - 1 + s) << 20, 0);   // v 2^nbits = d 2^(nbits-1)
   return t;
 }
 
@@ -1669,7 +1676,7 @@ __device__ __forceinline__ void s3_consume(const SweepParams &p, const uint32_t 
   s.y0 = Y0 + wib * S3_RW;
   s.lane_off = (uint32_t)((wib * S3_RW * F3_COLS + 2 * lane) * 8);
   s.zc0 = zc0;
-  s.T = s3_thresholds(p.nbits);
+  s.T = s3_thresholds(p.nbits, false);
   s.want_res = p.res_slot[B] != nullptr;
   s.bad = false;
   s.own_any = lane <= 30;
@@ -1766,7 +1773,7 @@ __global__ void __launch_bounds__(F3_CW * 32) scan3d_cells_kernel(const __grid_c
   const bool any_col = (e >= p.lb[0] && e <= p.ub[0]) || (e + 1 >= p.lb[0] && e + 1 <= p.ub[0]);
   const bool own_any = lane <= 30 && any_col && y0 <= p.ub[1] && y0 + S3_RW - 1 >= p.lb[1];
   if (!__any_sync(0xffffffffu, own_any)) return;
-  const S3Thresholds T = s3_thresholds(p.nbits);
+  const S3Thresholds T = s3_thresholds(p.nbits, !p.fused);
   const size_t cell0 = s3_cell_index(p, by * p.nsx + bx, wib, 0, lane);
   const float nanf_ = __int_as_float(KEYF_NAN);
   float pmn[3] = {nanf_, nanf_, nanf_}, pmx[3] = {nanf_, nanf_, nanf_};
@@ -1791,6 +1798,338 @@ __global__ void __launch_bounds__(F3_CW * 32) scan3d_cells_kernel(const __grid_c
 static size_t s3_smem_bytes() { return (size_t)S3_NST * S3_STAGE_BYTES + (size_t)S3_NST * 8 + (size_t)S3_NST * 4; }
 
 size_t scan3d_cells_per_layer(const SweepParams &p) { return (size_t)p.nsx * p.nsy * F3_CW * (size_t)(p.D + 1) * 32u; }
+
+// =============================================================================================
+// 1c. vector input (field GIVEN): range cells as well -- each vector layer is streamed once
+// =============================================================================================
+// No stencil here: a vertex's keys are the high words of its own components, so the build kernels read global memory
+// directly (16-byte loads, two vertices per lane).  They also fold min non-zero |v| of the layer (the separate
+// resolution pass over the whole layer disappears) and raise p.poison for magnitudes the float keys cannot order
+// (>= 2^1000; the context then falls back to the two-layer scans).  Cell layouts and tests are those of the scalar
+// paths: 3D = six 16-bit keys per (lane, 4-row block, plane), s3_test with thresholds for v instead of d = 2 v;
+// 2D = four full high-word keys per (lane, 8-row block), cube_excluded2 on the key ranges.
+constexpr int V2_R = 8;                                // 2D: corner rows per cell block
+
+__device__ __forceinline__ size_t vcells2d_index(const SweepParams &p, const int strip, const int kb, const int lane) {
+  return ((size_t)strip * (size_t)(p.H / V2_R + 2) + (size_t)kb) * 32u + (size_t)lane;
+}
+
+// exact (cold) update of the running min non-zero |v| with one vertex's components
+template <int N>
+__device__ __noinline__ double vres_vertex(double rmin, const double v0, const double v1, const double v2) {
+  if (v0 != 0.0 && fabs(v0) < fabs(rmin)) rmin = v0;
+  if (v1 != 0.0 && fabs(v1) < fabs(rmin)) rmin = v1;
+  if (N == 3 && v2 != 0.0 && fabs(v2) < fabs(rmin)) rmin = v2;
+  return rmin;
+}
+
+// cold path, 2D vector input: one lane per cube of the failing lane's 2 x V2_R cubes
+__device__ __noinline__ void vcells2d_slow_cubes(const SweepParams &p, unsigned failmask, const int c0, const int y0, const int nl) {
+  static_assert(2 * V2_R <= 32, "one lane per cube");
+  const int lane = threadIdx.x & 31;
+  const int nbits20 = p.nbits << 20;
+  const int r = lane >> 1, q = lane & 1;
+  while (failmask) {
+    const int src = __ffs(failmask) - 1;
+    failmask &= failmask - 1;
+    const int x = c0 + 2 * src + q, y = y0 + r;
+    const bool in = lane < 2 * V2_R && x >= p.lb[0] && x <= p.ub[0] && y >= p.lb[1] && y <= p.ub[1];
+    KeyRange rx = neutral_range(), ry = neutral_range();
+#pragma unroll
+    for (int v = 0; v < 4; v++) {
+      const int vx = x + (v & 1), vy = y + (v >> 1);
+      if (!in || vx > p.ub[0] || vy > p.ub[1]) continue;
+      const size_t i = (size_t)vx + (size_t)p.W * (size_t)vy;
+      for (int L = 0; L < nl; L++) {
+        const int4 a = __ldg(reinterpret_cast<const int4 *>(p.L[L].V) + i);
+        rx = merge(rx, vertex_range(a.y, nbits20));
+        ry = merge(ry, vertex_range(a.w, nbits20));
+      }
+    }
+    const bool surv = in && !cube_excluded2(rx, ry);
+    append_survivors(p, surv, (u64)(x - p.lb[0]) + (u64)p.nc[0] * (u64)(y - p.lb[1]));
+  }
+}
+
+// float-key ranges (raw high words) -> excluded, or the cold path
+__device__ __forceinline__ void vcells2d_decide(const SweepParams &p, const float xmn, const float xmx, const float ymn, const float ymx,
+                                                const bool own, const int c0, const int y0, const int nl) {
+  const int nbits20 = p.nbits << 20;
+  bool excl = false;
+  if (!(xmn != xmn) && !(ymn != ymn)) {       // a NaN union (no vertex) goes to the cold path, which is exact
+    const KeyRange x{vertex_range(__float_as_int(xmn), nbits20).mn, vertex_range(__float_as_int(xmx), nbits20).mx};
+    const KeyRange y{vertex_range(__float_as_int(ymn), nbits20).mn, vertex_range(__float_as_int(ymx), nbits20).mx};
+    excl = cube_excluded2(x, y);
+  }
+  const unsigned fm = __ballot_sync(0xffffffffu, own && !excl);
+  if (fm) vcells2d_slow_cubes(p, fm, c0, y0, nl);
+}
+
+// warp = strip of 62 corner columns (64 vertex columns, two per lane) x a chunk of rows (a multiple of V2_R)
+template <int NPREV, bool TEST>
+__global__ void __launch_bounds__(256) vscan2d_build_kernel(const __grid_constant__ SweepParams p) {
+  const int lane = threadIdx.x & 31;
+  const i64 w = (i64)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int strip = (int)(w % p.nsx), cy = (int)(w / p.nsx);
+  if (cy >= p.nsy) return;
+  const int W = p.W, H = p.H, B = p.build_layer;
+  const int c0 = strip * FB_STRIDE, e = c0 + 2 * lane;
+  const bool e_ok = e < W, o_ok = e + 1 < W;
+  const bool e_dom = e >= p.lb[0] && e <= p.ub[0], o_dom = e + 1 >= p.lb[0] && e + 1 <= p.ub[0];
+  const bool own_cols = lane <= 30 && (e_dom || o_dom);
+  const int r0 = cy * p.rows, r1 = min(r0 + p.rows - 1, H - 1), jl = min(r1 + 1, H - 1);
+  const int4 *__restrict__ V = reinterpret_cast<const int4 *>(p.L[B].V);
+  const bool want_res = p.res_slot[B] != nullptr;
+  const float nanf_ = __int_as_float(KEYF_NAN), inff_ = __int_as_float(0x7F800000);
+  double rmin = DBL_MAX;
+  float rkey = inff_;
+  int big = 0;
+  const uint4 *sum_prev = NPREV ? p.sum_in[0] + vcells2d_index(p, strip, 0, lane) : nullptr;
+  uint4 *sum_out = p.sum_out + vcells2d_index(p, strip, 0, lane);
+  float bxmn = nanf_, bxmx = nanf_, bymn = nanf_, bymx = nanf_;
+  uint4 prevc = make_uint4(0x7FC00000u, 0x7FC00000u, 0x7FC00000u, 0x7FC00000u);
+
+  auto finish_block = [&](const int kb, float xmn, float xmx, float ymn, float ymx) {
+    xmn = fminf(xmn, __shfl_down_sync(0xffffffffu, xmn, 1)); xmx = fmaxf(xmx, __shfl_down_sync(0xffffffffu, xmx, 1));
+    ymn = fminf(ymn, __shfl_down_sync(0xffffffffu, ymn, 1)); ymx = fmaxf(ymx, __shfl_down_sync(0xffffffffu, ymx, 1));
+    sum_out[(size_t)kb * 32u] = make_uint4(__float_as_uint(xmn), __float_as_uint(xmx), __float_as_uint(ymn), __float_as_uint(ymx));
+    if (TEST) {
+      if (NPREV) {
+        xmn = fminf(xmn, __uint_as_float(prevc.x)); xmx = fmaxf(xmx, __uint_as_float(prevc.y));
+        ymn = fminf(ymn, __uint_as_float(prevc.z)); ymx = fmaxf(ymx, __uint_as_float(prevc.w));
+      }
+      const int y0 = kb * V2_R;
+      vcells2d_decide(p, xmn, xmx, ymn, ymx, own_cols && y0 <= p.ub[1] && y0 + V2_R - 1 >= p.lb[1], c0, y0, NPREV + 1);
+    }
+  };
+
+  for (int j0 = r0; j0 <= jl; j0 += V2_R) {
+    // the rows of this block are independent loads: issue them all, then consume
+    int4 a[V2_R][2];
+#pragma unroll
+    for (int k = 0; k < V2_R; k++) {
+      const int j = j0 + k;
+      const size_t i = (size_t)W * (size_t)min(j, H - 1) + (size_t)e;
+      a[k][0] = (e_ok && j <= jl) ? __ldg(V + i) : make_int4(0, 0, 0, 0);
+      a[k][1] = (o_ok && j <= jl) ? __ldg(V + i + 1) : make_int4(0, 0, 0, 0);
+    }
+    uint4 prevn = prevc;
+    if (NPREV) prevn = __ldg(sum_prev + (size_t)(j0 / V2_R) * 32u);     // the block this row opens
+#pragma unroll
+    for (int k = 0; k < V2_R; k++) {
+      const int j = j0 + k;
+      if (j > jl) break;
+      const bool dom_y = j >= p.lb[1] && j <= p.ub[1];
+      float kxe = __int_as_float(a[k][0].y), kye = __int_as_float(a[k][0].w), kxo = __int_as_float(a[k][1].y), kyo = __int_as_float(a[k][1].w);
+      big = max(big, max(max(a[k][0].y & 0x7fffffff, a[k][0].w & 0x7fffffff), max(a[k][1].y & 0x7fffffff, a[k][1].w & 0x7fffffff)));
+      if (want_res) {
+        const float m = fminf(e_ok ? fminf(fabsf(kxe), fabsf(kye)) : inff_, o_ok ? fminf(fabsf(kxo), fabsf(kyo)) : inff_);
+        if (m <= rkey) {
+          const double vxe = __hiloint2double(a[k][0].y, a[k][0].x), vye = __hiloint2double(a[k][0].w, a[k][0].z);
+          const double vxo = __hiloint2double(a[k][1].y, a[k][1].x), vyo = __hiloint2double(a[k][1].w, a[k][1].z);
+          bool go = m < rkey;
+          if (!go) go = (e_ok && (fabs(vxe) < fabs(rmin) || fabs(vye) < fabs(rmin))) || (o_ok && (fabs(vxo) < fabs(rmin) || fabs(vyo) < fabs(rmin)));
+          if (go) {
+            if (e_ok) rmin = vres_vertex<2>(rmin, vxe, vye, 0.0);
+            if (o_ok) rmin = vres_vertex<2>(rmin, vxo, vyo, 0.0);
+            rkey = rmin == DBL_MAX ? inff_ : hikey(fabs(rmin));
+          }
+        }
+      }
+      if (!(e_dom && dom_y)) { kxe = nanf_; kye = nanf_; }
+      if (!(o_dom && dom_y)) { kxo = nanf_; kyo = nanf_; }
+      const float rxmn = fminf(kxe, kxo), rxmx = fmaxf(kxe, kxo), rymn = fminf(kye, kyo), rymx = fmaxf(kye, kyo);
+      if (k == 0) {
+        // vertex row V2_R k closes block k-1 and opens block k
+        if (j > r0) finish_block(j / V2_R - 1, fminf(bxmn, rxmn), fmaxf(bxmx, rxmx), fminf(bymn, rymn), fmaxf(bymx, rymx));
+        bxmn = rxmn; bxmx = rxmx; bymn = rymn; bymx = rymx;
+        prevc = prevn;
+      } else {
+        bxmn = fminf(bxmn, rxmn); bxmx = fmaxf(bxmx, rxmx); bymn = fminf(bymn, rymn); bymx = fmaxf(bymx, rymx);
+      }
+    }
+  }
+  // a chunk's last block is closed by the next chunk's first row (read above as row jl); the array's last block ends at row H-1
+  if (jl == H - 1) finish_block(jl / V2_R, bxmn, bxmx, bymn, bymx);
+  if (want_res) warp_res_commit(fabs(rmin), p.res_slot[B]);
+  if (big >= KEYF_BIG) atomicExch(p.poison, 1ull);
+}
+
+template <int NL>
+__global__ void __launch_bounds__(256) vscan2d_cells_kernel(const __grid_constant__ SweepParams p, const int nstrips, const int nblk_used) {
+  const int lane = threadIdx.x & 31;
+  const long long w = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (w >= (long long)nstrips * nblk_used) return;
+  const int strip = (int)(w / nblk_used), kb = (int)(w % nblk_used);
+  const int c0 = strip * FB_STRIDE, e = c0 + 2 * lane, y0 = kb * V2_R;
+  const bool own = lane <= 30 && ((e >= p.lb[0] && e <= p.ub[0]) || (e + 1 >= p.lb[0] && e + 1 <= p.ub[0])) && y0 <= p.ub[1] && y0 + V2_R - 1 >= p.lb[1];
+  if (!__any_sync(0xffffffffu, own)) return;
+  const float nanf_ = __int_as_float(KEYF_NAN);
+  float xmn = nanf_, xmx = nanf_, ymn = nanf_, ymx = nanf_;
+#pragma unroll
+  for (int L = 0; L < NL; L++) {
+    const uint4 c = __ldg(p.sum_in[L] + vcells2d_index(p, strip, kb, lane));
+    xmn = fminf(xmn, __uint_as_float(c.x)); xmx = fmaxf(xmx, __uint_as_float(c.y));
+    ymn = fminf(ymn, __uint_as_float(c.z)); ymx = fmaxf(ymx, __uint_as_float(c.w));
+  }
+  vcells2d_decide(p, xmn, xmx, ymn, ymx, own, c0, y0, NL);
+}
+
+// 3D: CTA = 8 warps over a tile of 62 x 32 corner columns, marching along a chunk of planes; per plane a thread reads
+// its 2 columns x (S3_RW + 1) rows (three 16-byte loads per row)
+template <bool EDGE, int NPREV, bool TEST>
+__device__ __forceinline__ void vs3_consume(const SweepParams &p, const int tile, const int C0, const int Y0, const int zc0, const int zc1,
+                                            const int wib, const int lane) {
+  const int B = p.build_layer, W = p.W, H = p.H, D = p.D;
+  const int e = C0 + 2 * lane, y0 = Y0 + wib * S3_RW;
+  const S3Thresholds T = s3_thresholds(p.nbits, true);
+  const bool want_res = p.res_slot[B] != nullptr;
+  const float nanf_ = __int_as_float(KEYF_NAN), inff_ = __int_as_float(0x7F800000);
+  const int4 *__restrict__ V = reinterpret_cast<const int4 *>(p.L[B].V);
+  bool own_any = lane <= 30;
+  unsigned mk = 0xffffffffu;     // bit r (+0 / +8): vertex (e / e+1, y0 + r) exists; bit r (+16 / +24): and lies in the domain
+  if (EDGE) {
+    unsigned ok = 0, dom = 0;
+#pragma unroll
+    for (int r = 0; r <= S3_RW; r++) {
+      ok |= (y0 + r < H) ? (1u << r) : 0u;
+      dom |= (y0 + r >= p.lb[1] && y0 + r <= p.ub[1]) ? (1u << r) : 0u;
+    }
+    const bool e_ok = e < W, o_ok = e + 1 < W;
+    const bool e_dom = e >= p.lb[0] && e <= p.ub[0], o_dom = e + 1 >= p.lb[0] && e + 1 <= p.ub[0];
+    mk = (e_ok ? ok : 0u) | ((o_ok ? ok : 0u) << 8) | ((e_dom ? dom : 0u) << 16) | ((o_dom ? dom : 0u) << 24);
+    own_any = own_any && (e_dom || o_dom) && y0 <= p.ub[1] && y0 + S3_RW - 1 >= p.lb[1];
+  }
+  double rmin = DBL_MAX;
+  float rkey = inff_;
+  int big = 0;
+  uint32_t pcell[3] = {0x7FC07FC0u, 0x7FC07FC0u, 0x7FC07FC0u};
+  const size_t cell0 = s3_cell_index(p, tile, wib, zc0, lane);
+  const uint4 *sum_prev = NPREV ? p.sum_in[0] + cell0 : nullptr;
+  uint4 *sum_out = p.sum_out + cell0;
+  const size_t row3 = (size_t)W * 3 / 2;            // int4 per row (W even)
+  for (int zg = zc0; zg <= zc1 + 1; zg++) {
+    uint4 prev = make_uint4(0x7FC07FC0u, 0x7FC07FC0u, 0x7FC07FC0u, 0u);
+    if (NPREV) prev = __ldg(sum_prev);
+    const bool zok = zg < D;
+    const bool zdom = zg >= p.lb[2] && zg <= p.ub[2];
+    float umin[3] = {nanf_, nanf_, nanf_}, umax[3] = {nanf_, nanf_, nanf_};
+    if (zok) {
+      unsigned m2 = mk;
+      if (EDGE) asm volatile("" : "+r"(m2));
+      int4 a[S3_RW + 1][3];
+      const int4 *base = V + ((size_t)zg * (size_t)H + (size_t)y0) * row3 + (size_t)e * 3 / 2;
+#pragma unroll
+      for (int r = 0; r <= S3_RW; r++) {
+        const bool ld = !EDGE || (((m2 >> r) | (m2 >> (r + 8))) & 1u);     // e + 1 < W whenever e < W (W even)
+#pragma unroll
+        for (int q = 0; q < 3; q++) a[r][q] = ld ? __ldg(base + (size_t)r * row3 + q) : make_int4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int r = 0; r <= S3_RW; r++) {
+        // vertex e: (x,y) = a0.xyzw, z = a1.xy; vertex e+1: x = a1.zw, (y,z) = a2.xyzw
+        float kxe = __int_as_float(a[r][0].y), kye = __int_as_float(a[r][0].w), kze = __int_as_float(a[r][1].y);
+        float kxo = __int_as_float(a[r][1].w), kyo = __int_as_float(a[r][2].y), kzo = __int_as_float(a[r][2].w);
+        big = max(big, max(max(a[r][0].y & 0x7fffffff, a[r][0].w & 0x7fffffff), a[r][1].y & 0x7fffffff));
+        big = max(big, max(max(a[r][1].w & 0x7fffffff, a[r][2].y & 0x7fffffff), a[r][2].w & 0x7fffffff));
+        if (want_res) {
+          float ma = fminf(fminf(fabsf(kxe), fabsf(kye)), fabsf(kze)), mb = fminf(fminf(fabsf(kxo), fabsf(kyo)), fabsf(kzo));
+          bool in_e = true, in_o = true;
+          if (EDGE) { in_e = (m2 >> r) & 1u; in_o = (m2 >> (r + 8)) & 1u; ma = in_e ? ma : inff_; mb = in_o ? mb : inff_; }
+          const float m = fminf(ma, mb);
+          if (m <= rkey) {
+            const double vxe = __hiloint2double(a[r][0].y, a[r][0].x), vye = __hiloint2double(a[r][0].w, a[r][0].z), vze = __hiloint2double(a[r][1].y, a[r][1].x);
+            const double vxo = __hiloint2double(a[r][1].w, a[r][1].z), vyo = __hiloint2double(a[r][2].y, a[r][2].x), vzo = __hiloint2double(a[r][2].w, a[r][2].z);
+            bool go = m < rkey;
+            const double ar = fabs(rmin);
+            if (!go) go = (in_e && (fabs(vxe) < ar || fabs(vye) < ar || fabs(vze) < ar)) || (in_o && (fabs(vxo) < ar || fabs(vyo) < ar || fabs(vzo) < ar));
+            if (go) {
+              if (in_e) rmin = vres_vertex<3>(rmin, vxe, vye, vze);
+              if (in_o) rmin = vres_vertex<3>(rmin, vxo, vyo, vzo);
+              rkey = rmin == DBL_MAX ? inff_ : hikey(fabs(rmin));
+            }
+          }
+        }
+        if (EDGE) {
+          const bool de = (m2 >> (r + 16)) & 1u, dq = (m2 >> (r + 24)) & 1u;
+          kxe = de ? kxe : nanf_; kye = de ? kye : nanf_; kze = de ? kze : nanf_;
+          kxo = dq ? kxo : nanf_; kyo = dq ? kyo : nanf_; kzo = dq ? kzo : nanf_;
+        }
+        umin[0] = fminf(umin[0], fminf(kxe, kxo)); umax[0] = fmaxf(umax[0], fmaxf(kxe, kxo));
+        umin[1] = fminf(umin[1], fminf(kye, kyo)); umax[1] = fmaxf(umax[1], fmaxf(kye, kyo));
+        umin[2] = fminf(umin[2], fminf(kze, kzo)); umax[2] = fmaxf(umax[2], fmaxf(kze, kzo));
+      }
+    }
+    if (!zdom) {
+#pragma unroll
+      for (int c = 0; c < 3; c++) { umin[c] = nanf_; umax[c] = nanf_; }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      umin[c] = fminf(umin[c], __shfl_down_sync(0xffffffffu, umin[c], 1));
+      umax[c] = fmaxf(umax[c], __shfl_down_sync(0xffffffffu, umax[c], 1));
+    }
+    *sum_out = make_uint4(pack_keys(umin[0], umax[0]), pack_keys(umin[1], umax[1]), pack_keys(umin[2], umax[2]), 0u);
+    sum_out += 32;
+    if (NPREV) sum_prev += 32;
+    if (TEST) {
+      if (NPREV) merge_cell(umin, umax, prev);
+      if (zg > zc0) {
+        const int zc_ = zg - 1;
+        if (zc_ >= p.lb[2] && zc_ <= p.ub[2]) {
+          float cmn[3] = {umin[0], umin[1], umin[2]}, cmx[3] = {umax[0], umax[1], umax[2]};
+          merge_cell(cmn, cmx, make_uint4(pcell[0], pcell[1], pcell[2], 0u));
+          s3_test(p, T, cmn, cmx, own_any, e, y0, zc_, NPREV + 1);
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 3; c++) pcell[c] = pack_keys(umin[c], umax[c]);
+    }
+  }
+  if (want_res) warp_res_commit(fabs(rmin), p.res_slot[B]);
+  if (big >= KEYF_BIG) atomicExch(p.poison, 1ull);
+}
+
+template <int NPREV, bool TEST>
+__global__ void __launch_bounds__(F3_CW * 32, 2) vscan3d_build_kernel(const __grid_constant__ SweepParams p) {
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  int b = blockIdx.x;
+  const int bx = b % p.nsx; b /= p.nsx;
+  const int by = b % p.nsy;
+  const int bz = b / p.nsy;
+  const int C0 = bx * F3_STRIDE, Y0 = by * F3_TROWS;
+  const int zc0 = bz * p.rows, zc1 = min(zc0 + p.rows - 1, p.D - 1);
+  const int tile = by * p.nsx + bx;
+  const bool interior = C0 >= p.lb[0] && C0 + 63 <= min(p.W - 1, p.ub[0]) && Y0 >= p.lb[1] && Y0 + F3_TROWS <= min(p.H - 1, p.ub[1]);
+  if (interior) vs3_consume<false, NPREV, TEST>(p, tile, C0, Y0, zc0, zc1, wib, lane);
+  else vs3_consume<true, NPREV, TEST>(p, tile, C0, Y0, zc0, zc1, wib, lane);
+}
+
+size_t vscan2d_cells_per_layer(const SweepParams &p) { return (size_t)p.nsx * (size_t)(p.H / V2_R + 2) * 32u; }
+
+void launch_vscan_cells(const SweepParams &p, cudaStream_t s) {
+  if (p.nd == 3) {
+    const unsigned grid = (unsigned)((i64)p.nsx * p.nsy * p.nsz);
+    switch (p.sum_mode) {
+      case SUM_BUILD: vscan3d_build_kernel<0, false><<<grid, F3_CW * 32, 0, s>>>(p); break;
+      case SUM_BUILD_TEST1: vscan3d_build_kernel<0, true><<<grid, F3_CW * 32, 0, s>>>(p); break;
+      case SUM_BUILD_TEST2: vscan3d_build_kernel<1, true><<<grid, F3_CW * 32, 0, s>>>(p); break;
+      case SUM_TEST1: scan3d_cells_kernel<1><<<grid, F3_CW * 32, 0, s>>>(p); break;
+      default: scan3d_cells_kernel<2><<<grid, F3_CW * 32, 0, s>>>(p); break;
+    }
+    return;
+  }
+  const unsigned grid = (unsigned)(((i64)p.nsx * p.nsy + 7) / 8);
+  const int nblk = (p.H + V2_R - 1) / V2_R;
+  const unsigned tgrid = (unsigned)(((i64)p.nsx * nblk + 7) / 8);
+  switch (p.sum_mode) {
+    case SUM_BUILD: vscan2d_build_kernel<0, false><<<grid, 256, 0, s>>>(p); break;
+    case SUM_BUILD_TEST1: vscan2d_build_kernel<0, true><<<grid, 256, 0, s>>>(p); break;
+    case SUM_BUILD_TEST2: vscan2d_build_kernel<1, true><<<grid, 256, 0, s>>>(p); break;
+    case SUM_TEST1: vscan2d_cells_kernel<1><<<tgrid, 256, 0, s>>>(p, p.nsx, nblk); break;
+    default: vscan2d_cells_kernel<2><<<tgrid, 256, 0, s>>>(p, p.nsx, nblk); break;
+  }
+}
 
 static size_t fused3d_smem_bytes(bool has_next) {
   return (size_t)F3_NST * (has_next ? 2 : 1) * F3_LAYER_BYTES + (size_t)2 * F3_NST * 8;

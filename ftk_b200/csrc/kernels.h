@@ -90,6 +90,11 @@ size_t scan3d_cells_per_layer(const SweepParams &p);
 constexpr int SCAN2D_CELL_ROWS = 9;
 void launch_scan2d_cells(const SweepParams &p, cudaStream_t s);     // needs p.bulk == 2 geometry with p.rows a multiple of SCAN2D_CELL_ROWS
 size_t scan2d_cells_per_layer(const SweepParams &p);
+// vector input (field GIVEN): p.fused == 0, p.L[].V set; 2D needs p.nsx = strips of 62 columns and p.rows a multiple of 8,
+// 3D the tile / chunk geometry of the fused 3D scan and W even
+constexpr int VSCAN2D_CELL_ROWS = 8;
+void launch_vscan_cells(const SweepParams &p, cudaStream_t s);
+size_t vscan2d_cells_per_layer(const SweepParams &p);
 // thread-per-(surviving cube, type) exact test; grid sized for `expected` cubes, grid-stride otherwise
 void launch_test(const SweepParams &p, cudaStream_t s);
 

@@ -161,35 +161,41 @@ def test_fused_3d_scan_equals_unfused(ftk, monkeypatch):
     b.close()
 
 
-@pytest.mark.parametrize("dims,T,env", [([200, 150], 4, "FTKB_SCAN2D"), ([130, 70, 44], 3, "FTKB_SCAN3D")])
-def test_range_cell_scan_equals_two_layer_scan(dims, T, env, ftk, oracle, monkeypatch):
+@pytest.mark.parametrize("dims,T,env,field", [([200, 150], 4, "FTKB_SCAN2D", "scalar"), ([130, 70, 44], 3, "FTKB_SCAN3D", "scalar"),
+                                              ([200, 150], 4, "FTKB_VSCAN", "vector"), ([66, 70, 24], 3, "FTKB_VSCAN", "vector"),
+                                              ([131, 37], 3, "FTKB_VSCAN", "vector")])
+def test_range_cell_scan_equals_two_layer_scan(dims, T, env, field, ftk, oracle, monkeypatch):
     """default scan (each layer streamed once, 16-byte range cells kept per layer) against the scan that re-reads both
     layers every step (FTKB_SCAN2D/3D=twolayer) and against the oracle: same points, same trajectories, same factor;
     every punctured simplex's cube is in the cell scan's worklist; a repeated sweep (cells only) changes nothing"""
     rng = np.random.default_rng(4242 + len(dims))
-    snaps = _rand_series(rng, dims, T, 1, "smooth")
-    a = ftk.track(snaps, dims, field="scalar")
+    snaps = _rand_series(rng, dims, T, 1 if field == "scalar" else len(dims), "smooth")
+    a = ftk.track(snaps, dims, field=field)
     monkeypatch.setenv(env, "twolayer")
-    b = ftk.track(snaps, dims, field="scalar")
+    b = ftk.track(snaps, dims, field=field)
     monkeypatch.delenv(env)
     pa, pb = a.get_discrete_critical_points(), b.get_discrete_critical_points()
     assert len(pa) > 0 and np.array_equal(pa, pb)
     assert P.canonical_trajectories(a.get_trajectory_index()) == P.canonical_trajectories(b.get_trajectory_index())
     assert a.stats()["scaling_factor"] == b.stats()["scaling_factor"] and a.stats()["resolution"] == b.stats()["resolution"]
-    o = oracle.track(snaps, dims, field="scalar")
+    o = oracle.track(snaps, dims, field=field)
     P.assert_same_result(cuda_result(a), P.oracle_result(o), tol=TOL, what="range-cell scan")
     wl = set(int(v) for v in a.get_last_worklist())
-    nc = [d - 3 for d in dims]
+    lo = 2 if field == "scalar" else 1
+    nc = [d - 1 - lo for d in dims]
     for q in pa[pa["timestep"] == T - 1]:
-        c = [int(v) - 2 for v in q["corner"][:len(dims)]]
+        c = [int(v) - lo for v in q["corner"][:len(dims)]]
         lin = c[0] + nc[0] * (c[1] + (nc[1] * c[2] if len(dims) == 3 else 0))
         assert lin in wl
     a.close()
     b.close()
     # streaming form: an update_timestep repeated on resident layers sweeps from the cells alone
-    tr = ftk.make_tracker(dims, field="scalar")
-    tr.push_scalar_field_snapshot(snaps[0])
-    tr.push_scalar_field_snapshot(snaps[1])
+    tr = ftk.make_tracker(dims, field=field)
+    for k in range(2):
+        if field == "scalar":
+            tr.push_scalar_field_snapshot(snaps[k])
+        else:
+            tr.push_vector_field_snapshot(snaps[k])
     tr.update_timestep()
     first = tr.get_discrete_critical_points().copy()
     tr.update_timestep()
