@@ -226,6 +226,10 @@ def main():
         return
     if args.warmup < 3:
         args.warmup = 3
+    # stdout carries exactly one JSON line: anything a library prints there (NCCL's version banner) goes to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
 
     import numpy as np
     import torch
@@ -453,6 +457,8 @@ def main():
         # algorithmic bytes of one scan launch (DESIGN.md "Kernels"): the two input layers read once each
         # (fused: fp64 scalar layers, 8 B/vertex; otherwise fp64 vector layers, nd*8 B/vertex) + 72-B hit records
         in_bytes = 2 * nvert * (1 if fused else nd) * 8
+        # one cell buffer (16 B per lane and block): written for the new layer, read for the current one
+        cell_bytes = nvert * (2.1 if nd == 3 else (1.04 if not vector else 1.03))
         alg_bytes = in_bytes + 72 * (st["points"] / max(K, 1))
         achieved = alg_bytes / (scan_ms * 1e-3) / 1e9
         # SURVEY.md 8(d) counts materialised vector layers (2.667 B/simplex in 2D, 0.8 in 3D) for the same launch
@@ -468,7 +474,9 @@ def main():
         cells = fused and os.environ.get("FTKB_SCAN2D" if nd == 2 else "FTKB_SCAN3D", "") not in ("twolayer", "plain") \
             and os.environ.get("FTKB_SCAN", "tile") == "tile"
         if vector:
-            kname = "scan2d_kernel<true>" if nd == 2 else "scan3d_kernel<true>"
+            vcells = os.environ.get("FTKB_VSCAN", "") != "twolayer"
+            kname = (("vscan2d_build_kernel<1,true>" if nd == 2 else "vscan3d_build_kernel<1,true>") if vcells
+                     else ("scan2d_kernel<true>" if nd == 2 else "scan3d_kernel<true>"))
         elif nd == 2:
             kname = "scan2d_build_kernel<1,true>" if cells else "scan2d_tile_kernel<true>"
         else:
@@ -488,8 +496,9 @@ def main():
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "traffic_gbs": (traffic / (scan_ms * 1e-3) / 1e9) if traffic else None,
                          "traffic_frac": (traffic / (scan_ms * 1e-3) / 1e9 / peak) if traffic else None,
-                         "traffic_note": "the scan streams one scalar layer per step and keeps 16-byte range cells for the other, so DRAM traffic "
-                                         "(ncu, per launch) is below the algorithmic bytes of the two-layer contract" if cells else None,
+                         "traffic_note": "the scan streams one layer per step and keeps 16-byte range cells for the other, so DRAM traffic "
+                                         "(ncu, per launch) is below the algorithmic bytes of the two-layer contract" if (cells or (vector and vcells)) else None,
+                         "model_traffic_bytes": (in_bytes / 2 + 2 * cell_bytes) if (cells or (vector and vcells)) else in_bytes,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": scan_ms,
                          "launches_timed": nscan, "sweeps_repeated": int(st["sweeps_repeated"]),
                          "survey_8d_equivalent": {"bytes_per_launch": survey_bytes, "gbs": survey_bytes / (scan_ms * 1e-3) / 1e9,
@@ -506,7 +515,8 @@ def main():
         }
         if world == 1 and not args.no_cpu_baseline and not vector:
             line["cpu_baseline"] = cpu_baseline_sample(args.config)
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if dist:
         dist.barrier()
         dist.destroy_process_group()

@@ -67,7 +67,7 @@ EXPORTS = [
     "ftkb_reset_stats", "ftkb_synchronize", "ftkb_timer_start", "ftkb_timer_stop", "ftkb_mesh_ntypes", "ftkb_mesh_unit_simplex", "ftkb_mesh_scope_type",
     "ftkb_mesh_sides", "ftkb_mesh_side_of",
     "ftkb_curveset_create", "ftkb_get_curveset", "ftkb_curveset_destroy", "ftkb_curveset_post_process", "ftkb_curveset_size",
-    "ftkb_curveset_get", "ftkb_curveset_last_error",
+    "ftkb_curveset_get", "ftkb_curveset_last_error", "ftkb_curveset_slice",
 ]
 
 _lib = None
@@ -122,6 +122,7 @@ def lib():
     L.ftkb_curveset_post_process.argtypes = [vp, C.c_char_p]
     L.ftkb_curveset_size.argtypes = [vp, u64p, u64p]
     L.ftkb_curveset_get.argtypes = [vp, vp, vp]
+    L.ftkb_curveset_slice.argtypes = [vp, C.c_int32, vp, C.c_uint64, u64p]
     L.ftkb_curveset_last_error.argtypes = [vp]
     L.ftkb_curveset_last_error.restype = C.c_char_p
     _lib = L

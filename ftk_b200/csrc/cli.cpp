@@ -50,7 +50,7 @@ void usage() {
       "  -w, --width N  -h, --height N  -d, --depth N  -n, --timesteps N\n"
       "      --x0 a,b[,c]  --dir a,b[,c]   moving_extremum parameters;  --time-scale s (double_gyre)\n"
       "  -o, --output FILE                 result file\n"
-      "      --output-type traced|discrete     (default traced)\n"
+      "      --output-type traced|discrete|sliced  (default traced; sliced: OUTPUT is a printf pattern, one text file per timestep)\n"
       "      --output-format text|json         (default: by file name, .json -> json, else text)\n"
       "      --type-filter min|max|saddle|...  (2D; names joined with |)\n"
       "      --post-process OPS                smooth_types,rotate,split,discard_interval_points,reorder,adjust_time,derive_velocity,...\n"
@@ -292,7 +292,7 @@ int main(int argc, char **argv) {
       if (k == T - 1) tr->update_timestep();
     }
     const double t_compute = now();
-    if (o.output_type == "traced") {
+    if (o.output_type == "traced" || o.output_type == "sliced") {
       tr->finalize();
       if (!o.post_process.empty()) tr->post_process(o.post_process);     // feature_curve_set_post_processor_t(ops).filter(trajs)
     }
@@ -304,7 +304,16 @@ int main(int argc, char **argv) {
       if (fmt == "json") tr->write_traced_critical_points_json(o.output); else if (fmt == "text") tr->write_traced_critical_points_text(o.output); else die("unsupported --output-format " + fmt);
     } else if (o.output_type == "discrete") {
       if (fmt == "json") tr->write_critical_points_json(o.output); else if (fmt == "text") tr->write_critical_points_text(o.output); else die("unsupported --output-format " + fmt);
-    } else die("unsupported --output-type " + o.output_type + " (traced | discrete)");
+    } else if (o.output_type == "sliced") {       // json_interface.hh:805-811,584-592: one file per timestep, series_filename(pattern, k)
+      if (fmt != "text") die("sliced output is written as text");
+      if (o.output.find('%') == std::string::npos) die("--output-type sliced needs a printf pattern in --output (e.g. sliced-%03d.txt)");
+      tr->slice_traced_critical_points();
+      for (const auto &kv : tr->get_sliced_critical_points()) {
+        char name[4096];
+        std::snprintf(name, sizeof(name), o.output.c_str(), kv.first);
+        tr->write_sliced_critical_points_text(kv.first, std::string(name));
+      }
+    } else die("unsupported --output-type " + o.output_type + " (traced | discrete | sliced)");
 
     if (o.timing) {   // same line as json_interface.hh:718-723, plus the device-side split
       const ftkb_stats st = tr->stats();

@@ -190,6 +190,23 @@ static void split_all(ftkb_curveset &s) {
   }
 }
 
+// feature_curve.hh:364-381 per curve (the int bounds compare against the double times), empty results dropped
+void ftkb_curveset::intercept(int t0, int t1) {
+  std::vector<Curve> out;
+  for (const Curve &c : curves) {
+    if (c.pts.empty()) continue;           // (the reference would read back() of an empty vector here)
+    if (t0 > c.pts.back().p.t || t1 < c.pts.front().p.t) continue;
+    Curve r;                                // a default curve: loop / complete cleared
+    for (const auto &q : c.pts)
+      if (q.p.t >= t0 && q.p.t <= t1) r.pts.push_back(q);
+    if (r.pts.empty()) continue;
+    relabel(r, c.id);
+    update_statistics(r);
+    out.push_back(std::move(r));
+  }
+  curves = std::move(out);
+}
+
 int ftkb_curveset::post_process(const std::string &ops) {
   size_t pos = 0;
   while (pos <= ops.size()) {
@@ -217,6 +234,11 @@ int ftkb_curveset::post_process(const std::string &ops) {
         const double thr = std::atof(op.c_str() + colon + 1);
         if (thr > 0) curves.erase(std::remove_if(curves.begin(), curves.end(), [&](const Curve &c) { return c.tmax - c.tmin < thr; }), curves.end());
       }
+    } else if (op.rfind("intercept:", 0) == 0) {
+      // feature_curve_set_t::intercept(t0, t1) (feature_curve_set.hh:534-545) in place; curves are assumed reordered
+      const size_t c1 = op.find(':'), c2 = op.find(':', c1 + 1);
+      if (c2 == std::string::npos) { error = "post_process: intercept needs intercept:t0:t1"; return FTKB_ERR_INVALID; }
+      intercept(std::atoi(op.c_str() + c1 + 1), std::atoi(op.c_str() + c2 + 1));
     } else if (op.rfind("legacy", 0) == 0) {
       // json_interface::post_process(): "legacy[:duration_threshold[:discard_interval_points[:derive_velocities]]]"
       double thr = 0; int disc = 0, vel = 0;
@@ -276,6 +298,21 @@ extern "C" int ftkb_curveset_size(const ftkb_curveset *s, uint64_t *ncurves, uin
   for (const auto &c : s->curves) np += c.pts.size();
   if (ncurves) *ncurves = s->curves.size();
   if (npoints) *npoints = np;
+  return FTKB_OK;
+}
+
+// critical_point_tracker::slice_traced_critical_points (critical_point_tracker.hh:819-835): the ordinal points of one
+// timestep, curves in the set's order, points in curve order
+extern "C" int ftkb_curveset_slice(const ftkb_curveset *s, int32_t timestep, ftkb_curve_point *out, uint64_t cap, uint64_t *n) {
+  if (!s || !n) return FTKB_ERR_INVALID;
+  uint64_t k = 0;
+  for (const auto &c : s->curves)
+    for (const auto &q : c.pts)
+      if (q.p.ordinal && q.p.timestep == timestep) {
+        if (out && k < cap) out[k] = q;
+        k++;
+      }
+  *n = k;
   return FTKB_OK;
 }
 

@@ -27,5 +27,6 @@ struct ftkb_curveset {
 
   int add(Curve c);                        // feature_curve_set.hh:458-465: id = last id + 1, points relabelled
   void add(Curve c, int label);            // :467-472
+  void intercept(int t0, int t1);         // feature_curve_set.hh:534-545
   int post_process(const std::string &ops);
 };

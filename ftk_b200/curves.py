@@ -55,6 +55,15 @@ class CurveSet:
         L.lib().ftkb_curveset_get(self._h, infos.ctypes.data if nc.value else None, pts.ctypes.data if npt.value else None)
         return infos, pts
 
+    def slice(self, timestep):
+        """sliced critical points of one timestep: the ordinal points of the curves (CURVE_POINT_DTYPE array)"""
+        n = C.c_uint64()
+        L.lib().ftkb_curveset_slice(self._h, int(timestep), None, 0, C.byref(n))
+        out = np.zeros(n.value, L.CURVE_POINT_DTYPE)
+        if n.value:
+            L.lib().ftkb_curveset_slice(self._h, int(timestep), out.ctypes.data, n.value, C.byref(n))
+        return out
+
     def curves(self):
         infos, pts = self.arrays()
         return [(infos[i], pts[int(infos[i]["first"]):int(infos[i]["first"] + infos[i]["count"])]) for i in range(len(infos))]

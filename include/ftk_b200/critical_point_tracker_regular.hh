@@ -409,6 +409,23 @@ class critical_point_tracker_regular {
   void write_traced_critical_points_text(std::ostream &os) const { traced_.write_text(os, scalar_components_); }
   void write_traced_critical_points_text(const std::string &f) const { std::ofstream o(f); write_traced_critical_points_text(o); }
   void write_traced_critical_points_json(const std::string &f) const { std::ofstream o(f); traced_.write_json(o); }
+
+  // ---- sliced output: critical_point_tracker.hh:819-835 (slice_traced_critical_points), :465-474 (text) ----
+  void slice_traced_critical_points() {
+    sliced_.clear();
+    for (const auto &kv : traced_)
+      for (const auto &cp : kv.second)
+        if (cp.ordinal) sliced_[cp.timestep].push_back(cp);
+  }
+  const std::map<int, std::vector<feature_point_t>> &get_sliced_critical_points() const { return sliced_; }
+  void write_sliced_critical_points_text(int t, std::ostream &os) const {
+    const auto it = sliced_.find(t);
+    if (it == sliced_.end()) return;
+    for (const auto &cp : it->second) cp.print(os, scalar_components_) << std::endl;
+  }
+  void write_sliced_critical_points_text(int t, const std::string &f) const { std::ofstream o(f); write_sliced_critical_points_text(t, o); }
+  // feature_curve_set_t::intercept (feature_curve_set.hh:534-545) through the library's curve set
+  void intercept_traced_critical_points(int t0, int t1) { post_process("intercept:" + std::to_string(t0) + ":" + std::to_string(t1)); }
   void write_critical_points_text(std::ostream &os) { for (const auto &p : get_critical_points()) p.print(os, scalar_components_) << std::endl; }
   void write_critical_points_text(const std::string &f) { std::ofstream o(f); write_critical_points_text(o); }
   void write_critical_points_json(const std::string &f) {
@@ -471,6 +488,7 @@ class critical_point_tracker_regular {
   std::vector<feature_point_t> points_;
   bool points_valid_ = false;
   feature_curve_set_t traced_;
+  std::map<int, std::vector<feature_point_t>> sliced_;
 };
 
 struct critical_point_tracker_2d_regular : public critical_point_tracker_regular {

@@ -164,7 +164,8 @@ int ftkb_get_degrees(ftkb_ctx *, int32_t *deg);
  *   smooth_types, rotate, split, discard_interval_points, reorder, adjust_time, derive_velocity,
  *   duration_pruning:THRESHOLD, plus discard_degenerate_points, update_statistics, and
  *   legacy[:duration_threshold[:discard_interval_points[:derive_velocities]]] = json_interface::post_process()
- *   (include/ftk/filters/json_interface.hh:758-800).
+ *   (include/ftk/filters/json_interface.hh:758-800), and intercept:T0:T1 = feature_curve_set_t::intercept
+ *   (feature_curve_set.hh:534-545; the "intercepted" output type).
  * An unknown op returns FTKB_ERR_INVALID (the reference calls fatal()). */
 typedef struct ftkb_curve_point {
   ftkb_point p;               /* cp_type and t are what post-processing may change */
@@ -191,6 +192,9 @@ void ftkb_curveset_destroy(ftkb_curveset *);
 int ftkb_curveset_post_process(ftkb_curveset *, const char *ops);
 int ftkb_curveset_size(const ftkb_curveset *, uint64_t *ncurves, uint64_t *npoints);
 int ftkb_curveset_get(const ftkb_curveset *, ftkb_curve_info *infos /* ncurves */, ftkb_curve_point *pts /* npoints */);
+/* the "sliced" output type: ordinal points of one timestep (critical_point_tracker.hh:819-835); *n receives the count,
+ * at most cap points are copied */
+int ftkb_curveset_slice(const ftkb_curveset *, int32_t timestep, ftkb_curve_point *out, uint64_t cap, uint64_t *n);
 const char *ftkb_curveset_last_error(const ftkb_curveset *);
 
 /* diagnostic: the cubes (linear corner index over the domain, x fastest) that the most recent sweep's

@@ -179,6 +179,10 @@ static int run(const args_t &a)
       } else if (op.rfind("duration_pruning:", 0) == 0) {
         const double thr = atof(op.c_str() + 17);
         if (thr > 0) set.filter([&](const ftk::feature_curve_t &t) { return !(t.tmax - t.tmin < thr); });
+      } else if (op.rfind("intercept:", 0) == 0) {                    // feature_curve_set_t::intercept(t0, t1)
+        const auto f = ftk::split(op, ":");
+        const ftk::feature_curve_set_t cut = set.intercept(atoi(f[1].c_str()), atoi(f[2].c_str()));
+        set = cut;
       } else if (op == "discard_degenerate_points") {
         set.foreach([](ftk::feature_curve_t &t) { t.discard_degenerate_points(); t.update_statistics(); });
       } else if (op == "update_statistics") {
@@ -205,6 +209,17 @@ static int run(const args_t &a)
         const double d[8] = {cp.x[0], cp.x[1], cp.x[2], cp.t, cp.scalar[0], cp.v[0], cp.v[1], cp.v[2]};
         fwrite(&idx, 8, 1, fc); fwrite(q, 4, 4, fc); fwrite(d, 8, 8, fc);
       }
+    }
+    // sliced critical points (critical_point_tracker.hh:819-835): ordinal points of the traced curves per timestep
+    tr.slice_traced_critical_points();
+    const auto &sliced = tr.get_sliced_critical_points();
+    const uint64_t ns = sliced.size();
+    fwrite(&ns, 8, 1, fc);
+    for (const auto &kv : sliced) {
+      const int32_t h[2] = {kv.first, 0};
+      const uint64_t n = kv.second.size();
+      fwrite(h, 4, 2, fc); fwrite(&n, 8, 1, fc);
+      for (const auto &cp : kv.second) { const uint64_t idx = tag2idx.at(cp.tag); fwrite(&idx, 8, 1, fc); }
     }
     fclose(fc);
   }

@@ -39,6 +39,7 @@ OPS = [
     "derive_velocity",
     "update_statistics,discard_degenerate_points,reorder",
     "update_statistics,duration_pruning:4,rotate,smooth_types",
+    "reorder,intercept:1:3",                               # feature_curve_set_t::intercept (curves assumed reordered)
 ]
 
 CURVE_REC = np.dtype([("id", np.int32), ("loop", np.int32), ("complete", np.int32), ("consistent_type", np.uint32), ("count", np.uint64),
@@ -62,8 +63,17 @@ def read_ftkc(path):
         n = int(curves[i]["count"])
         points.append(np.frombuffer(buf, POINT_REC, n, off).copy())
         off += POINT_REC.itemsize * n
+    ns = int(np.frombuffer(buf, np.uint64, 1, off)[0])
+    off += 8
+    slices = []
+    for _ in range(ns):
+        t = int(np.frombuffer(buf, np.int32, 1, off)[0])
+        n = int(np.frombuffer(buf, np.uint64, 1, off + 8)[0])
+        off += 16
+        slices.append((t, np.frombuffer(buf, np.uint64, n, off).astype(np.int64)))
+        off += 8 * n
     assert off == len(buf)
-    return curves, (np.concatenate(points) if points else np.zeros(0, POINT_REC))
+    return curves, (np.concatenate(points) if points else np.zeros(0, POINT_REC)), slices
 
 
 def run(meta, inp, ops, tmpdir):
@@ -91,7 +101,7 @@ def main():
         arrays = {"meta": np.frombuffer(json.dumps(dict(case=name, ops=OPS, reference="hguo/ftk@aa4f2cf9 feature_curve(_set)_t, g++ -O2")).encode(), np.uint8)}
         with tempfile.TemporaryDirectory() as tmp:
             for k, ops in enumerate(OPS):
-                raw, (curves, points) = run(meta, inp, ops, tmp)
+                raw, (curves, points, slices) = run(meta, inp, ops, tmp)
                 assert np.array_equal(raw["points"]["corner"], gold["points"]["corner"])     # the tracking fixture's punctured simplices
                 trajs = raw["trajectories"]
                 off = np.zeros(len(trajs) + 1, np.int64)
@@ -100,6 +110,9 @@ def main():
                 arrays[f"trace_offsets_{k}"] = off
                 arrays[f"trace_idx_{k}"] = np.concatenate([t[0] for t in trajs]).astype(np.int32) if trajs else np.zeros(0, np.int32)
                 arrays[f"trace_loop_{k}"] = np.asarray([t[1] for t in trajs], np.uint8)
+                # sliced critical points: (timestep, count) per slice + the concatenated point indices, in the reference's order
+                arrays[f"slice_t_{k}"] = np.asarray([[t, len(ix)] for t, ix in slices], np.int64).reshape(-1, 2)
+                arrays[f"slice_idx_{k}"] = np.concatenate([ix for _, ix in slices]).astype(np.int32) if slices else np.zeros(0, np.int32)
                 arrays[f"curves_{k}"] = curves
                 arrays[f"points_{k}"] = points[["idx", "cp_type", "ordinal", "timestep", "id", "t", "v"]]
                 print(f"{name} [{ops}]: {len(curves)} curves, {len(points)} points")

@@ -193,3 +193,23 @@ def test_cli_post_process_matches_reference_curves(cli, tmp_path):
     assert sorted(got) == sorted((int(c["count"]), int(c["consistent_type"]), int(c["loop"])) for c in want)
     bad = subprocess.run([cli, "-f", "cp", "--synthetic", "merger_2d", "--post-process", "no_such_op", "-o", str(out)], capture_output=True, text=True)
     assert bad.returncode == 1 and "unknown operation" in bad.stderr
+
+
+@pytest.mark.gpu
+def test_cli_sliced_output(cli, tmp_path):
+    """--output-type sliced (json_interface.hh:805-811): one text file per timestep holding the ordinal points of the traced
+    curves; every punctured ordinal simplex of the reference fixture appears exactly once, in its own timestep's file"""
+    meta, gold, _ = P.load_golden("merger_32x32x100")
+    pat = str(tmp_path / "sliced-%03d.txt")
+    r = subprocess.run([cli, "-f", "cp", "--synthetic", "merger_2d", "--output-type", "sliced", "-o", pat], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    pts = gold["points"]
+    want = {int(t): int(n) for t, n in zip(*np.unique(pts["timestep"][pts["ordinal"] != 0], return_counts=True))}
+    got = {}
+    for t in range(meta["T"]):
+        f = pat % t
+        if os.path.exists(f):
+            lines = open(f).read().splitlines()
+            assert all(f"timestep={t}, ordinal=1" in line for line in lines)
+            got[t] = len(lines)
+    assert got == want
