@@ -15,7 +15,7 @@ ABI_VERSION = 1
 OK, ERR_INVALID, ERR_NO_DEVICE, ERR_CUDA, ERR_NOMEM, ERR_OVERFLOW = range(6)
 SOURCE_NONE, SOURCE_GIVEN, SOURCE_DERIVED = 0, 1, 2
 MEM_HOST, MEM_DEVICE, MEM_DEVICE_BORROW = 0, 1, 2
-SYN_MOVING_EXTREMUM, SYN_WOVEN, SYN_DOUBLE_GYRE, SYN_ABC, SYN_MERGER = range(5)
+SYN_MOVING_EXTREMUM, SYN_WOVEN, SYN_DOUBLE_GYRE, SYN_ABC, SYN_MERGER, SYN_TORNADO = range(6)
 
 
 class Config(C.Structure):

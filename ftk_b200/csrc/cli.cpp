@@ -43,7 +43,7 @@ void usage() {
   std::puts(
       "usage: ftkb200 -f cp (--synthetic NAME | --input PATTERN) -o OUTPUT [options]\n"
       "  -f, --feature cp|critical_point   feature type (only critical points are implemented)\n"
-      "      --synthetic NAME              woven | moving_extremum_2d | moving_extremum_3d | double_gyre | merger_2d\n"
+      "      --synthetic NAME              woven | moving_extremum_2d | moving_extremum_3d | double_gyre | merger_2d | tornado\n"
       "  -i, --input PATTERN               raw file: one file holding all timesteps, or a printf pattern (e.g. s-%03d.raw)\n"
       "      --input-format float32|float64\n"
       "      --var a[,b[,c]]               variable names; 2 / 3 names = vector field with the component index fastest\n"
@@ -166,6 +166,33 @@ void gen_moving_extremum(int nd, const long *dims, const double *x0, const doubl
       }
 }
 
+void gen_tornado(long xs, long ys, long zs, int time, double *out) {      // synthetic.hh:441-494
+  const double SMALL = 0.00000000001;
+  const double xdelta = 1.0 / (xs - 1.0), ydelta = 1.0 / (ys - 1.0), zdelta = 1.0 / (zs - 1.0);
+  for (long iz = 0; iz < zs; iz++) {
+    const double z = iz * zdelta;
+    const double xc = 0.5 + 0.1 * std::sin(0.04 * time + 10.0 * z), yc = 0.5 + 0.1 * std::cos(0.03 * time + 3.0 * z);
+    const double r = 0.1 + 0.4 * z * z + 0.1 * z * std::sin(8.0 * z), r2 = 0.2 + 0.1 * z;
+    for (long iy = 0; iy < ys; iy++) {
+      const double y = iy * ydelta;
+      for (long ix = 0; ix < xs; ix++) {
+        const double x = ix * xdelta;
+        double temp = std::sqrt((y - yc) * (y - yc) + (x - xc) * (x - xc));
+        double scale = std::fabs(r - temp);
+        scale = scale > r2 ? 0.8 - scale : 1.0;
+        double z0 = 0.1 * (0.1 - temp * z);
+        if (z0 < 0.0) z0 = 0.0;
+        temp = std::sqrt(temp * temp + z0 * z0);
+        scale = (r + r2 - temp) * scale / (temp + SMALL);
+        scale = scale / (1 + z);
+        *out++ = scale * (y - yc) + 0.1 * (x - xc);
+        *out++ = scale * -(x - xc) + 0.1 * (y - yc);
+        *out++ = scale * z0;
+      }
+    }
+  }
+}
+
 void gen_double_gyre(long W, long H, double time, double *out) {      // synthetic.hh:130-150,193-217: A = 0.1, omega = 2 pi, eps = 0.25
   const double A = 0.1, omega = M_PI * 2, eps = 0.25;
   for (long j = 0; j < H; j++)
@@ -223,6 +250,7 @@ int main(int argc, char **argv) {
     else if (s == "moving_extremum_3d") { nd = 3; dims[0] = dims[1] = dims[2] = 21; syn = FTKB_SYN_MOVING_EXTREMUM; if (o.x0.empty()) o.x0 = {10, 10, 10}; if (o.dir.empty()) o.dir = {0.1, 0.11, 0.1}; }
     else if (s == "double_gyre") { dims[0] = 64; dims[1] = 32; T = 50; nv = 2; syn = FTKB_SYN_DOUBLE_GYRE; }
     else if (s == "merger_2d") { T = 100; syn = FTKB_SYN_MERGER; }
+    else if (s == "tornado") { nd = 3; nv = 3; syn = FTKB_SYN_TORNADO; }                     // stream.hh:431,1560-1567: 32^3 x 32
     else die("synthetic case not available: " + s);
     if (syn == FTKB_SYN_MOVING_EXTREMUM && ((int)o.x0.size() != nd || (int)o.dir.size() != nd)) die("invalid x0 / dir");
   } else {
@@ -283,6 +311,7 @@ int main(int argc, char **argv) {
         if (syn == FTKB_SYN_WOVEN) gen_woven(dims[0], dims[1], T == 1 ? 0.0 : double(k) / (T - 1), buf.data());        // stream.hh:1468-1480
         else if (syn == FTKB_SYN_MERGER) gen_merger(dims[0], dims[1], double(k) * 0.1, buf.data());                   // stream.hh:1540
         else if (syn == FTKB_SYN_DOUBLE_GYRE) gen_double_gyre(dims[0], dims[1], k * o.time_scale, buf.data());        // stream.hh:1542-1555
+        else if (syn == FTKB_SYN_TORNADO) gen_tornado(dims[0], dims[1], dims[2], (int)k, buf.data());                  // stream.hh:1560-1567
         else if (syn == FTKB_SYN_MOVING_EXTREMUM) gen_moving_extremum(nd, dims, o.x0.data(), o.dir.data(), double(k), buf.data());
         else read_raw(o, k, nvert * nv, o.input_format == "float32", buf.data());
         const ndarray<double> a = ndarray<double>::wrap(buf.data(), shape);

@@ -320,9 +320,9 @@ extern "C" int ftkb_push_snapshot(ftkb_ctx *c, const double *scalar, const doubl
 extern "C" int ftkb_push_synthetic(ftkb_ctx *c, int kind, const double *params, int nparams, double t) {
   if (!c) return FTKB_ERR_INVALID;
   if (nparams < 0 || nparams > 8 || (nparams && !params)) return fail(c, FTKB_ERR_INVALID, "push_synthetic: bad params");
-  const bool vector_kind = kind == FTKB_SYN_DOUBLE_GYRE || kind == FTKB_SYN_ABC;
+  const bool vector_kind = kind == FTKB_SYN_DOUBLE_GYRE || kind == FTKB_SYN_ABC || kind == FTKB_SYN_TORNADO;
   const bool ok2 = kind == FTKB_SYN_WOVEN || kind == FTKB_SYN_DOUBLE_GYRE || kind == FTKB_SYN_MERGER;
-  if (kind < 0 || kind > FTKB_SYN_MERGER || (ok2 && c->n != 2) || (kind == FTKB_SYN_ABC && c->n != 3))
+  if (kind < 0 || kind > FTKB_SYN_TORNADO || (ok2 && c->n != 2) || ((kind == FTKB_SYN_ABC || kind == FTKB_SYN_TORNADO) && c->n != 3))
     return fail(c, FTKB_ERR_INVALID, "push_synthetic: generator does not match the context's dimensionality");
   if (vector_kind ? c->cfg.vector_source != FTKB_SOURCE_GIVEN : c->cfg.scalar_source != FTKB_SOURCE_GIVEN)
     return fail(c, FTKB_ERR_INVALID, "push_synthetic: generator kind does not match the configured field sources");

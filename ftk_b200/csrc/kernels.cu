@@ -2912,6 +2912,23 @@ __global__ void __launch_bounds__(256) synthetic_kernel(int kind, int nd, int W,
       out[2 * idx] = -kPi * A * sin(kPi * f) * cos(kPi * y);
       out[2 * idx + 1] = kPi * A * cos(kPi * f) * sin(kPi * y) * dfdx;
     } break;
+    case FTKB_SYN_TORNADO: {           // synthetic.hh:441-494; t = integer time step
+      const double SMALL = 0.00000000001;
+      const double x = i * (1.0 / (W - 1.0)), y = j * (1.0 / (H - 1.0)), z = k * (1.0 / (D - 1.0));
+      const double xc = 0.5 + 0.1 * sin(0.04 * t + 10.0 * z), yc = 0.5 + 0.1 * cos(0.03 * t + 3.0 * z);
+      const double r = 0.1 + 0.4 * z * z + 0.1 * z * sin(8.0 * z), r2 = 0.2 + 0.1 * z;
+      double temp = sqrt((y - yc) * (y - yc) + (x - xc) * (x - xc));
+      double scale = fabs(r - temp);
+      scale = scale > r2 ? 0.8 - scale : 1.0;
+      double z0 = 0.1 * (0.1 - temp * z);
+      if (z0 < 0.0) z0 = 0.0;
+      temp = sqrt(temp * temp + z0 * z0);
+      scale = (r + r2 - temp) * scale / (temp + SMALL);
+      scale = scale / (1 + z);
+      out[3 * idx] = scale * (y - yc) + 0.1 * (x - xc);
+      out[3 * idx + 1] = scale * -(x - xc) + 0.1 * (y - yc);
+      out[3 * idx + 2] = scale * z0;
+    } break;
     case FTKB_SYN_ABC: {               // synthetic.hh:239-260 on [0, 2 pi]^3
       const double A = sp.p[0], B = sp.p[1], C = sp.p[2];
       const double x = (((double)i / (W - 1))) * 2 * kPi, y = (((double)j / (H - 1))) * 2 * kPi, z = (((double)k / (D - 1))) * 2 * kPi;

@@ -63,7 +63,8 @@ enum {
   FTKB_SYN_WOVEN = 1,           /* 2D scalar; params: (none); t = time     synthetic.hh:32-48  */
   FTKB_SYN_DOUBLE_GYRE = 2,     /* 2D vector; params: A, omega, eps        synthetic.hh:130-217 */
   FTKB_SYN_ABC = 3,             /* 3D vector; params: A, B, C              synthetic.hh:239-260 */
-  FTKB_SYN_MERGER = 4           /* 2D scalar; params: (none)               synthetic.hh:262-297 */
+  FTKB_SYN_MERGER = 4,          /* 2D scalar; params: (none)               synthetic.hh:262-297 */
+  FTKB_SYN_TORNADO = 5          /* 3D vector; params: (none); t = integer time step   synthetic.hh:441-494 */
 };
 
 typedef struct ftkb_config {

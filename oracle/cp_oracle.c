@@ -1250,6 +1250,38 @@ void cpo_gen_double_gyre(int DW, int DH, double time, double A, double omega, do
     }
 }
 
+/* ref: synthetic.hh:441-494 synthetic_tornado (vector (3, xs, ys, zs), component fastest) */
+void cpo_gen_tornado(int xs, int ys, int zs, int time, double *out)
+{
+  const double SMALL = 0.00000000001;
+  const double xdelta = 1.0 / (xs-1.0), ydelta = 1.0 / (ys-1.0), zdelta = 1.0 / (zs-1.0);
+  for (int iz = 0; iz < zs; iz ++) {
+    const double z = iz * zdelta;
+    const double xc = 0.5 + 0.1*sin(0.04*time+10.0*z);
+    const double yc = 0.5 + 0.1*cos(0.03*time+3.0*z);
+    const double r = 0.1 + 0.4 * z*z + 0.1 * z * sin(8.0*z);
+    const double r2 = 0.2 + 0.1*z;
+    for (int iy = 0; iy < ys; iy ++) {
+      const double y = iy * ydelta;
+      for (int ix = 0; ix < xs; ix ++) {
+        const double x = ix * xdelta;
+        double temp = sqrt( (y-yc)*(y-yc) + (x-xc)*(x-xc) );
+        double scale = fabs( r - temp );
+        if ( scale > r2 ) scale = 0.8 - scale;
+        else scale = 1.0;
+        double z0 = 0.1 * (0.1 - temp*z );
+        if ( z0 < 0.0 ) z0 = 0.0;
+        temp = sqrt( temp*temp + z0*z0 );
+        scale = (r + r2 - temp) * scale / (temp + SMALL);
+        scale = scale / (1+z);
+        *out++ = scale * (y-yc) + 0.1*(x-xc);
+        *out++ = scale * -(x-xc) + 0.1*(y-yc);
+        *out++ = scale * z0;
+      }
+    }
+  }
+}
+
 /* ref: synthetic.hh:239-260 synthetic_abc_flow */
 void cpo_gen_abc(int DW, int DH, int DD, double A, double B, double C, double *out)
 {

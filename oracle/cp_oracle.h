@@ -103,6 +103,7 @@ void cpo_gen_merger(int W, int H, double t, double *out);                       
 void cpo_gen_moving_extremum(int nd, const int32_t *dims, const double *x0, const double *dir, double t, double *out);
 void cpo_gen_double_gyre(int W, int H, double time, double A, double omega, double eps, double *out); /* vector (2,W,H) */
 void cpo_gen_abc(int W, int H, int D, double A, double B, double C, double *out); /* vector (3,W,H,D) */
+void cpo_gen_tornado(int W, int H, int D, int time, double *out);                /* vector (3,W,H,D) */
 
 #ifdef __cplusplus
 }

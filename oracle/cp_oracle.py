@@ -78,6 +78,7 @@ def lib():
         L.cpo_gen_moving_extremum.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
         L.cpo_gen_double_gyre.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_void_p]
         L.cpo_gen_abc.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_void_p]
+        L.cpo_gen_tornado.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.cpo_cp_type_2d.restype = C.c_uint32
         L.cpo_cp_type_2d.argtypes = [C.c_void_p, C.c_int]
         L.cpo_cp_type_3d.restype = C.c_uint32
@@ -137,6 +138,12 @@ def abc_amplitude(k):
     return math.sqrt(3.0) + 0.5 * (float(k) / 64.0) * math.sin(math.pi * float(k) / 64.0)
 
 
+def gen_tornado(W, H, D, time):
+    out = np.empty((D, H, W, 3), np.float64)
+    lib().cpo_gen_tornado(W, H, D, int(time), _ptr(out))
+    return out
+
+
 def synthetic_series(name, dims, T, params=None):
     """Yield the T snapshots of a named reference generator (same time conventions as
     oracle/ref_harness.cpp)."""
@@ -160,6 +167,8 @@ def synthetic_series(name, dims, T, params=None):
             yield gen_double_gyre(dims[0], dims[1], k * P(0, 0.1))
         elif name == "abc":
             yield gen_abc(dims[0], dims[1], dims[2], abc_amplitude(k))
+        elif name == "tornado":
+            yield gen_tornado(dims[0], dims[1], dims[2], k)
         else:
             raise ValueError(name)
 
