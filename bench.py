@@ -481,7 +481,7 @@ def main():
             kname = "scan2d_build_kernel<1,true>" if cells else "scan2d_tile_kernel<true>"
         else:
             kname = "scan3d_build_kernel<1,true>" if cells else ("scan3d_fused_kernel<true>" if fused else "scan3d_kernel<true>")
-        if not cells:
+        if not cells and not (vector and os.environ.get("FTKB_VSCAN", "") != "twolayer"):
             traffic = None
         line = {
             "metric": METRIC, "value": per_step * K * world / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,

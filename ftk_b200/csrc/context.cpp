@@ -247,15 +247,24 @@ static int queue_resolution(ftkb_ctx *c, Layer &l, bool fused_in_gradient) {
 
 static int derive_layer(ftkb_ctx *c, Layer &l) {
   // slot <- all ones: above the bit pattern of every finite double, so the kernels' atomicMin on the
-  // bit patterns of |v| works unchanged and "nothing found" reads back as DBL_MAX (slot_value)
-  CK(cudaMemsetAsync(c->d_scalars + l.slot, 0xff, sizeof(unsigned long long), c->stream));
+  // bit patterns of |v| works unchanged and "nothing found" reads back as DBL_MAX (slot_value).
+  // Layers whose resolution the scan produces (res_pending) only mark the host mirror: the sweep's one
+  // host-to-device copy of the counter block resets the device slot (no separate memset per push).
   bool fused = false;
   if (!l.V && c->cfg.vector_source == FTKB_SOURCE_DERIVED && l.S && (c->n == 2 || (c->fused3d && (uintptr_t)l.S % 16 == 0))) {
     // the gradient is never materialised; the fused scan derives it on the fly and computes this
     // layer's resolution during the first sweep that reads it
     l.res_pending = true;
-    return check_launch(c, "derive");
+    c->h_scalars[l.slot] = ~0ull;
+    return FTKB_OK;
   }
+  if (l.V && c->cellsV && c->cfg.vector_source == FTKB_SOURCE_GIVEN && (uintptr_t)l.V % 16 == 0) {
+    // the range-cell scan streams this layer once and folds min non-zero |v| into that pass
+    l.res_pending = true;
+    c->h_scalars[l.slot] = ~0ull;
+    return FTKB_OK;
+  }
+  CK(cudaMemsetAsync(c->d_scalars + l.slot, 0xff, sizeof(unsigned long long), c->stream));
   if (!l.V && c->cfg.vector_source == FTKB_SOURCE_DERIVED && l.S) {
     int rc = take_buffer(c, c->freeV, c->nvert * c->n, &l.V);
     if (rc) return rc;
@@ -266,11 +275,6 @@ static int derive_layer(ftkb_ctx *c, Layer &l) {
     c->derive_timed = true;
     c->stats.kernel_launches++;
     fused = true;
-  }
-  if (l.V && !fused && c->cellsV && c->cfg.vector_source == FTKB_SOURCE_GIVEN && (uintptr_t)l.V % 16 == 0) {
-    // the range-cell scan streams this layer once and folds min non-zero |v| into that pass
-    l.res_pending = true;
-    return check_launch(c, "derive");
   }
   if (l.V) {
     int rc = queue_resolution(c, l, fused);
@@ -496,6 +500,7 @@ static bool rows_aligned16(const ftkb_ctx *c, const double *a, const double *b) 
 
 // resolution of a layer whose vector field is derived on the fly, outside a sweep (time-slab exchange)
 static int resolve_pending(ftkb_ctx *c, Layer &l) {
+  CK(cudaMemsetAsync(c->d_scalars + l.slot, 0xff, sizeof(unsigned long long), c->stream));   // (a pending layer's device slot is reset lazily)
   if (l.V) {          // vector input: the plain resolution pass
     l.res_pending = false;
     return queue_resolution(c, l, false);
@@ -684,7 +689,8 @@ extern "C" int ftkb_update_timestep(ftkb_ctx *c) {
     c->h_scalars[ftkb_ctx::SLOT_PT] = c->npts;
     c->h_scalars[ftkb_ctx::SLOT_UQ] = 0;
     c->h_scalars[ftkb_ctx::SLOT_POISON] = 0;
-    CK(cudaMemcpyAsync(c->d_scalars + ftkb_ctx::SLOT_WL, c->h_scalars + ftkb_ctx::SLOT_WL, 32, cudaMemcpyHostToDevice, c->stream));
+    // one copy resets the counters AND the resolution slots of the layers this sweep resolves (host mirror = all ones)
+    CK(cudaMemcpyAsync(c->d_scalars, c->h_scalars, 12 * sizeof(unsigned long long), cudaMemcpyHostToDevice, c->stream));
     CK(cudaEventRecord(c->ev[0], c->stream));
     if (vcells || (fused && ((c->n == 3 && c->cells3d) || (c->n == 2 && c->cells2d && p.bulk == 2)))) {
       // each layer is streamed once (the step that first sees it); everything else reads its 16-byte range cells
@@ -720,10 +726,11 @@ extern "C" int ftkb_update_timestep(ftkb_ctx *c) {
     c->stats.kernel_launches += 2;
     int rc = check_launch(c, "sweep");
     if (rc) return rc;
-    CK(cudaMemcpyAsync(c->h_scalars + ftkb_ctx::SLOT_WL, c->d_scalars + ftkb_ctx::SLOT_WL, 32, cudaMemcpyDeviceToHost, c->stream));
-    if (pending) {   // slots 0..7 hold the per-layer resolutions
-      CK(cudaMemcpyAsync(c->h_scalars, c->d_scalars, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    if (pending) {   // slots 0..7 hold the per-layer resolutions, 8..11 the counters: one copy
+      CK(cudaMemcpyAsync(c->h_scalars, c->d_scalars, 12 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
       c->stats.d2h_bytes += 64;
+    } else {
+      CK(cudaMemcpyAsync(c->h_scalars + ftkb_ctx::SLOT_WL, c->d_scalars + ftkb_ctx::SLOT_WL, 32, cudaMemcpyDeviceToHost, c->stream));
     }
     CK(cudaStreamSynchronize(c->stream));
     c->stats.d2h_bytes += 32;
