@@ -882,7 +882,7 @@ __device__ __forceinline__ size_t cells2d_index(const SweepParams &p, const int 
 // cold path: for every lane whose cell union failed (bit set in failmask), the WARP tests that lane's 2 x C2_R cubes,
 // one lane per cube: ranges over the vertices valid simplices can use (<= ub) from global memory, gradient exactly
 // as gradient2D indexes it (clamped at the array border); survivors are appended.
-__device__ __noinline__ void cells2d_slow_cubes(const SweepParams &p, unsigned failmask, const int c0, const int y0, const int nl) {
+__device__ __noinline__ void cells2d_slow_cubes(const SweepParams &p, unsigned failmask, const int c0, const int y0, const int nl, const int nrows) {
   static_assert(2 * C2_R <= 32, "one lane per cube");
   const int W = p.W, H = p.H;
   const int lane = threadIdx.x & 31;
@@ -893,7 +893,7 @@ __device__ __noinline__ void cells2d_slow_cubes(const SweepParams &p, unsigned f
     const int src = __ffs(failmask) - 1;
     failmask &= failmask - 1;
     const int x = c0 + 2 * src + q, y = y0 + r;
-    const bool in = lane < 2 * C2_R && x >= p.lb[0] && x <= p.ub[0] && y >= p.lb[1] && y <= p.ub[1];
+    const bool in = lane < 2 * nrows && x >= p.lb[0] && x <= p.ub[0] && y >= p.lb[1] && y <= p.ub[1];
     FRange rx{nanf_, nanf_}, ry{nanf_, nanf_};
 #pragma unroll
     for (int v = 0; v < 4; v++) {
@@ -917,7 +917,7 @@ __device__ __noinline__ void cells2d_slow_cubes(const SweepParams &p, unsigned f
 __device__ __forceinline__ void cells2d_decide(const SweepParams &p, const FRange ux, const FRange uy, const bool own, const int e, const int y0, const int nl) {
   const bool fail = own && !cube_excluded2_f(ux, uy, p.thrp_f, p.thr2_f, p.lim_f);
   const unsigned fm = __ballot_sync(0xffffffffu, fail);
-  if (fm) cells2d_slow_cubes(p, fm, e - 2 * (int)(threadIdx.x & 31), y0, nl);
+  if (fm) cells2d_slow_cubes(p, fm, e - 2 * (int)(threadIdx.x & 31), y0, nl, C2_R);
 }
 
 template <bool BORDER, int NPREV, bool TEST>
@@ -1092,9 +1092,15 @@ __global__ void __launch_bounds__(256) scan2d_cells_kernel(const __grid_constant
 
 static size_t c2_smem_bytes() { return (size_t)C2_NST * TL_SEG * 8 + (size_t)2 * C2_NST * 8; }
 
-size_t scan2d_cells_per_layer(const SweepParams &p) { return (size_t)p.nsx * C2_CW * (size_t)(p.H / C2_R + 2) * 32u; }
+size_t vscan2d_cells_per_layer(const SweepParams &p);
+void launch_scan2d_direct(const SweepParams &p, cudaStream_t s);
+size_t scan2d_cells_per_layer(const SweepParams &p) {
+  if (p.bulk == 3) return vscan2d_cells_per_layer(p);      // direct staging: strips x 8-row blocks
+  return (size_t)p.nsx * C2_CW * (size_t)(p.H / C2_R + 2) * 32u;
+}
 
 void launch_scan2d_cells(const SweepParams &p, cudaStream_t s) {
+  if (p.bulk == 3) { launch_scan2d_direct(p, s); return; }
   const unsigned grid = (unsigned)((i64)p.nsx * p.nsy);
   const int nstrips = (p.W + FB_STRIDE - 1) / FB_STRIDE, nblk = (p.H + C2_R - 1) / C2_R;
   const unsigned tgrid = (unsigned)(((i64)nstrips * nblk + 7) / 8);
@@ -1973,6 +1979,192 @@ __global__ void __launch_bounds__(256) vscan2d_cells_kernel(const __grid_constan
     ymn = fminf(ymn, __uint_as_float(c.z)); ymx = fmaxf(ymx, __uint_as_float(c.w));
   }
   vcells2d_decide(p, xmn, xmx, ymn, ymx, own, c0, y0, NL);
+}
+
+// ---- 2D, scalar input, range cells, direct loads ("direct" staging, the default) ------------------------------------
+// Same cells idea as scan2d_build_kernel, without shared memory: a warp owns a strip of 62 corner columns (64 vertex
+// columns, two per lane, one 16-byte load per lane and row) and marches along y eight rows at a time -- all eight loads
+// of a batch are issued before the first is used, so every thread keeps 128 B in flight; x neighbours come from warp
+// shuffles (lanes 0 and 31 load their one outside column), y neighbours from a two-row carry.  Ranges are kept on the
+// HIGH WORDS of the fp64 differences (monotone float keys, no conversion instruction in the row loop); a cell is four
+// such keys {min dx, max dx, min dy, max dy} per lane and 8-row block.  At block end the keys are widened outwards to
+// fp64, scaled by (W-1) / (H-1) like gradient2D does, rounded outwards to fp32, and go through cube_excluded2_f.
+__device__ __forceinline__ double key_bound_lo(const float k) {     // a double <= every value whose high word is k
+  const int h = __float_as_int(k);
+  return __hiloint2double(h, h < 0 ? (int)0xffffffffu : 0);
+}
+__device__ __forceinline__ double key_bound_hi(const float k) {     // a double >= every value whose high word is k
+  const int h = __float_as_int(k);
+  return __hiloint2double(h, h < 0 ? 0 : (int)0xffffffffu);
+}
+
+__device__ __forceinline__ void dcells2d_decide(const SweepParams &p, const float xmn, const float xmx, const float ymn, const float ymx,
+                                                const bool own, const int c0, const int y0, const int nl) {
+  const double cw = (double)(p.W - 1), ch = (double)(p.H - 1);
+  // NaN keys (no vertex) give NaN bounds: cube_excluded2_f then refuses and the cold path decides
+  const FRange x{__double2float_rd(key_bound_lo(xmn) * cw), __double2float_ru(key_bound_hi(xmx) * cw)};
+  const FRange y{__double2float_rd(key_bound_lo(ymn) * ch), __double2float_ru(key_bound_hi(ymx) * ch)};
+  const bool none = xmn != xmn || ymn != ymn;      // no vertex in the union: let the cold path look
+  const bool fail = own && (none || !cube_excluded2_f(x, y, p.thrp_f, p.thr2_f, p.lim_f));
+  const unsigned fm = __ballot_sync(0xffffffffu, fail);
+  if (fm) cells2d_slow_cubes(p, fm, c0, y0, nl, V2_R);
+}
+
+// min non-zero |v| of the layer, v = d (W-1) resp. d (H-1): the scale factors are constants >= 1, so the product is
+// monotone in |d| and never underflows to zero -- the kernel keeps the exact minimum of the non-zero |dx| and |dy| per
+// axis (with the float keys as a prefilter) and scales once at the end, which gives bit for bit the minimum that
+// res_update4 finds value by value.
+__device__ __forceinline__ void dmin_nz(double &m, float &mk, const bool in, const double d) {
+  const double a = fabs(d);
+  if (in && d != 0.0 && a < m) { m = a; mk = hikey(a); }      // NaN / Inf never compare below
+}
+
+template <bool BORDER, int NPREV, bool TEST>
+__device__ __forceinline__ void dcells2d_strip(const SweepParams &p, const int strip, const int cy, const int lane) {
+  const int W = p.W, H = p.H, B = p.build_layer;
+  const int c0 = strip * FB_STRIDE, e = c0 + 2 * lane;
+  const bool e_ok = !BORDER || e < W, o_ok = !BORDER || e + 1 < W, o1_ok = !BORDER || e + 2 < W;
+  const bool e_dom = e >= p.lb[0] && e <= p.ub[0], o_dom = e + 1 >= p.lb[0] && e + 1 <= p.ub[0];
+  const bool own_cols = lane <= 30 && (e_dom || o_dom);
+  const int r0 = cy * p.rows, r1 = min(r0 + p.rows - 1, H - 1), jl = min(r1 + 1, H - 1);
+  const double *__restrict__ S = p.L[B].S;
+  const bool want_res = p.res_slot[B] != nullptr;
+  const double cw = (double)(W - 1), ch = (double)(H - 1);
+  const float nanf_ = __int_as_float(KEYF_NAN), inff_ = __int_as_float(0x7F800000);
+  double mdx = DBL_MAX, mdy = DBL_MAX;       // min non-zero |dx|, |dy| seen by this thread
+  float tkx = inff_, tky = inff_;            // their high-word keys (prefilter)
+  const uint4 *sum_prev = NPREV ? p.sum_in[0] + vcells2d_index(p, strip, 0, lane) : nullptr;
+  uint4 *sum_out = p.sum_out + vcells2d_index(p, strip, 0, lane);
+  // the one column outside the strip that this lane supplies: lane 0 the left one, lane 31 the right one (index clamped like gradient2D)
+  const bool edge_lane = lane == 0 || lane == 31;
+  const int edge_col = lane == 0 ? max(c0 - 1, 0) : min(c0 + 64, W - 1);
+
+  auto load_row = [&](const int j, double2 &v, double &ed) {
+    const size_t row = (size_t)W * (size_t)min(max(j, 0), H - 1);
+    v = e_ok ? __ldg(reinterpret_cast<const double2 *>(S + row + e)) : make_double2(0.0, 0.0);
+    ed = edge_lane ? __ldg(S + row + edge_col) : 0.0;
+  };
+  auto finish_block = [&](const int kb, float xmn, float xmx, float ymn, float ymx, const uint4 prevc) {
+    xmn = fminf(xmn, __shfl_down_sync(0xffffffffu, xmn, 1)); xmx = fmaxf(xmx, __shfl_down_sync(0xffffffffu, xmx, 1));
+    ymn = fminf(ymn, __shfl_down_sync(0xffffffffu, ymn, 1)); ymx = fmaxf(ymx, __shfl_down_sync(0xffffffffu, ymx, 1));
+    sum_out[(size_t)kb * 32u] = make_uint4(__float_as_uint(xmn), __float_as_uint(xmx), __float_as_uint(ymn), __float_as_uint(ymx));
+    if (TEST) {
+      if (NPREV) {
+        xmn = fminf(xmn, __uint_as_float(prevc.x)); xmx = fmaxf(xmx, __uint_as_float(prevc.y));
+        ymn = fminf(ymn, __uint_as_float(prevc.z)); ymx = fmaxf(ymx, __uint_as_float(prevc.w));
+      }
+      const int y0 = kb * V2_R;
+      dcells2d_decide(p, xmn, xmx, ymn, ymx, own_cols && y0 <= p.ub[1] && y0 + V2_R - 1 >= p.lb[1], c0, y0, NPREV + 1);
+    }
+  };
+
+  // carry: vertex rows g-1 (m1) and g (c0v, with its edge value) of the next gradient row g
+  double2 m1, cv;
+  double m1e, cve;
+  load_row(r0 - 1, m1, m1e);
+  load_row(r0, cv, cve);
+  float bxmn = nanf_, bxmx = nanf_, bymn = nanf_, bymx = nanf_;
+  uint4 prevc = make_uint4(0x7FC00000u, 0x7FC00000u, 0x7FC00000u, 0x7FC00000u);
+  for (int g0 = r0; g0 <= jl; g0 += V2_R) {
+    // vertex rows g0+1 .. g0+8: the rows above the gradient rows g0 .. g0+7 of this batch
+    double2 a[V2_R];
+    double ae[V2_R];
+#pragma unroll
+    for (int k = 0; k < V2_R; k++) {
+      if (g0 + k <= jl) load_row(g0 + k + 1, a[k], ae[k]);
+      else { a[k] = make_double2(0.0, 0.0); ae[k] = 0.0; }
+    }
+    uint4 prevn = prevc;
+    if (NPREV) prevn = __ldg(sum_prev + (size_t)(g0 / V2_R) * 32u);     // the block this batch opens
+#pragma unroll
+    for (int k = 0; k < V2_R; k++) {
+      const int g = g0 + k;
+      if (g > jl) break;
+      const double2 up = a[k];
+      // x neighbours: column e-1 is the previous lane's second column, column e+2 the next lane's first
+      double left = __shfl_up_sync(0xffffffffu, cv.y, 1), right = __shfl_down_sync(0xffffffffu, cv.x, 1);
+      if (lane == 0) left = cve;
+      if (lane == 31) right = cve;
+      double mid_e = cv.y;
+      if (BORDER) {
+        if (!o_ok) mid_e = cv.x;          // x+1 clamped to W-1
+        if (!o1_ok) right = cv.y;
+      }
+      const double dxe = mid_e - left, dxo = right - cv.x, dye = up.x - m1.x, dyo = up.y - m1.y;
+      float kxe = hikey(dxe), kxo = hikey(dxo), kye = hikey(dye), kyo = hikey(dyo);
+      if (want_res) {
+        float ax = fminf(fabsf(kxe), fabsf(kxo)), ay = fminf(fabsf(kye), fabsf(kyo));
+        if (BORDER) {
+          ax = fminf(e_ok ? fabsf(kxe) : inff_, o_ok ? fabsf(kxo) : inff_);
+          ay = fminf(e_ok ? fabsf(kye) : inff_, o_ok ? fabsf(kyo) : inff_);
+        }
+        if (ax <= tkx) { dmin_nz(mdx, tkx, e_ok, dxe); dmin_nz(mdx, tkx, o_ok, dxo); }
+        if (ay <= tky) { dmin_nz(mdy, tky, e_ok, dye); dmin_nz(mdy, tky, o_ok, dyo); }
+      }
+      const bool dom_y = g >= p.lb[1] && g <= p.ub[1];
+      if (!(e_dom && dom_y)) { kxe = nanf_; kye = nanf_; }
+      if (!(o_dom && dom_y)) { kxo = nanf_; kyo = nanf_; }
+      const float rxmn = fminf(kxe, kxo), rxmx = fmaxf(kxe, kxo), rymn = fminf(kye, kyo), rymx = fmaxf(kye, kyo);
+      if (k == 0) {
+        // gradient row 8 k closes block k-1 and opens block k
+        if (g > r0) finish_block(g / V2_R - 1, fminf(bxmn, rxmn), fmaxf(bxmx, rxmx), fminf(bymn, rymn), fmaxf(bymx, rymx), prevc);
+        bxmn = rxmn; bxmx = rxmx; bymn = rymn; bymx = rymx;
+        prevc = prevn;
+      } else {
+        bxmn = fminf(bxmn, rxmn); bxmx = fmaxf(bxmx, rxmx); bymn = fminf(bymn, rymn); bymx = fmaxf(bymx, rymx);
+      }
+      m1 = cv; cv = up; cve = ae[k];
+    }
+  }
+  if (jl == H - 1) finish_block(jl / V2_R, bxmn, bxmx, bymn, bymx, prevc);     // the array's last block ends at row H-1
+  if (want_res) {
+    const double vx = mdx < DBL_MAX ? mdx * cw : DBL_MAX, vy = mdy < DBL_MAX ? mdy * ch : DBL_MAX;
+    warp_res_commit(fmin(vx, vy), p.res_slot[B]);
+  }
+}
+
+template <int NPREV, bool TEST>
+__global__ void __launch_bounds__(256, 2) scan2d_direct_kernel(const __grid_constant__ SweepParams p) {
+  const int lane = threadIdx.x & 31;
+  const i64 w = (i64)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int strip = (int)(w % p.nsx), cy = (int)(w / p.nsx);
+  if (cy >= p.nsy) return;
+  const int c0 = strip * FB_STRIDE;
+  if (c0 + 66 > p.W) dcells2d_strip<true, NPREV, TEST>(p, strip, cy, lane);        // the last strip clamps its columns
+  else dcells2d_strip<false, NPREV, TEST>(p, strip, cy, lane);
+}
+
+template <int NL>
+__global__ void __launch_bounds__(256) scan2d_direct_cells_kernel(const __grid_constant__ SweepParams p, const int nstrips, const int nblk_used) {
+  const int lane = threadIdx.x & 31;
+  const long long w = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (w >= (long long)nstrips * nblk_used) return;
+  const int strip = (int)(w / nblk_used), kb = (int)(w % nblk_used);
+  const int c0 = strip * FB_STRIDE, e = c0 + 2 * lane, y0 = kb * V2_R;
+  const bool own = lane <= 30 && ((e >= p.lb[0] && e <= p.ub[0]) || (e + 1 >= p.lb[0] && e + 1 <= p.ub[0])) && y0 <= p.ub[1] && y0 + V2_R - 1 >= p.lb[1];
+  if (!__any_sync(0xffffffffu, own)) return;
+  const float nanf_ = __int_as_float(KEYF_NAN);
+  float xmn = nanf_, xmx = nanf_, ymn = nanf_, ymx = nanf_;
+#pragma unroll
+  for (int L = 0; L < NL; L++) {
+    const uint4 c = __ldg(p.sum_in[L] + vcells2d_index(p, strip, kb, lane));
+    xmn = fminf(xmn, __uint_as_float(c.x)); xmx = fmaxf(xmx, __uint_as_float(c.y));
+    ymn = fminf(ymn, __uint_as_float(c.z)); ymx = fmaxf(ymx, __uint_as_float(c.w));
+  }
+  dcells2d_decide(p, xmn, xmx, ymn, ymx, own, c0, y0, NL);
+}
+
+void launch_scan2d_direct(const SweepParams &p, cudaStream_t s) {
+  const unsigned grid = (unsigned)(((i64)p.nsx * p.nsy + 7) / 8);
+  const int nblk = (p.H + V2_R - 1) / V2_R;
+  const unsigned tgrid = (unsigned)(((i64)p.nsx * nblk + 7) / 8);
+  switch (p.sum_mode) {
+    case SUM_BUILD: scan2d_direct_kernel<0, false><<<grid, 256, 0, s>>>(p); break;
+    case SUM_BUILD_TEST1: scan2d_direct_kernel<0, true><<<grid, 256, 0, s>>>(p); break;
+    case SUM_BUILD_TEST2: scan2d_direct_kernel<1, true><<<grid, 256, 0, s>>>(p); break;
+    case SUM_TEST1: scan2d_direct_cells_kernel<1><<<tgrid, 256, 0, s>>>(p, p.nsx, nblk); break;
+    default: scan2d_direct_cells_kernel<2><<<tgrid, 256, 0, s>>>(p, p.nsx, nblk); break;
+  }
 }
 
 // 3D: CTA = 8 warps over a tile of 62 x 32 corner columns, marching along a chunk of planes; per plane a thread reads
