@@ -2935,7 +2935,7 @@ __device__ bool check_simplex(const SweepParams &p, const DeviceMeshTables &mt, 
 }
 
 template <int ND>
-__global__ void __launch_bounds__(128) test_kernel(const SweepParams p) {
+__global__ void __launch_bounds__(128) test_kernel(const __grid_constant__ SweepParams p) {
   const DeviceMeshTables &mt = c_mesh[ND - 2];
   const int ntypes = ND == 2 ? 12 : 60;
   u64 ncubes = *p.wl_count;
