@@ -309,7 +309,34 @@ def main():
     tr = make()
     ptrs = [int(l.data_ptr()) for l in layers]     # resident layers are borrowed in place through the C ABI
     push_ptr(tr, ptrs[tri(g0, NL)])
-    for i in range(W):
+    # N > 1, halo through NVLink peer memory (default; FTKB_HALO=nccl copies the layer with ncclSend/Recv instead): the slab
+    # below needs this rank's first layer only for its last sweep, and of it only the 16-byte range cells and the vertices
+    # around the surviving cubes -- the owner exports IPC handles of the layer and of its cells, the neighbour maps them and
+    # pushes the layer as a remote snapshot (ftkb_push_snapshot_remote): nothing is copied.  Handle exchange and mapping are
+    # set-up (once per run), like NCCL's channel set-up; they stay outside the timed region.
+    peer = None
+    first_done = False
+    if dist and os.environ.get("FTKB_HALO", "peer") == "peer":
+        mine = None
+        try:
+            push_ptr(tr, ptrs[tri(g0 + 1, NL)])
+            tr.update_timestep()                         # the sweep that builds the cells of this rank's first layer
+            cptr, cbytes, cres = tr.export_layer_cells(0)
+            mine = (_lib.ipc_export(ptrs[tri(g0, NL)]), _lib.ipc_export(cptr), cres)
+        except _lib.FTKBError:
+            mine = None
+        tr.advance_timestep()                            # warm-up step 0 completes (repeated sweep from the cells, layer popped)
+        first_done = True
+        allh = [None] * world
+        dist.all_gather_object(allh, mine)
+        if all(h is not None for h in allh):
+            if rank < world - 1:
+                lh, ch, cres = allh[rank + 1]
+                peer = (_lib.ipc_import(lh, local), _lib.ipc_import(ch, local), cres)
+            else:
+                peer = ()
+    use_peer = peer is not None
+    for i in range(1 if first_done else 0, W):
         push_ptr(tr, ptrs[tri(g0 + i + 1, NL)])
         tr.advance_timestep()
     halo = None
@@ -329,10 +356,11 @@ def main():
     if dist:
         # untimed: NCCL sets its peer-to-peer channels up lazily on first use (hundreds of ms); the timed exchange
         # below then moves the halo over warm channels, as every exchange after the first would in a long run
-        if rank < world - 1:
-            halo = torch.empty_like(layers[0])
-        for r in exchange_halo():
-            r.wait()
+        if not use_peer:
+            if rank < world - 1:
+                halo = torch.empty_like(layers[0])
+            for r in exchange_halo():
+                r.wait()
         warm = torch.zeros(1, dtype=torch.float64, device=dev)
         dist.all_gather([torch.empty_like(warm) for _ in range(world)], warm)
         dist.all_reduce(warm, op=dist.ReduceOp.MAX)
@@ -341,12 +369,24 @@ def main():
     tr.reset_stats()
     sampler.start()
     tr.timer_start()
-    reqs = exchange_halo() if dist else []     # inside the timed region
+    reqs = exchange_halo() if (dist and not use_peer) else []     # inside the timed region
     res_layers, factors = [], []
     import ctypes as _C
     _L, _st = _lib, _lib.Stats()
     for i in range(W, W + K):
         nxt = ptrs[tri(g0 + i + 1, NL)]
+        if use_peer and peer and i == W + K - 1:
+            # the slab's last sweep: the next slab's first layer stays where it is, in the neighbour GPU's memory
+            if vector:
+                tr.push_remote_snapshot(vector=peer[0], cells=peer[1], resolution=peer[2])
+            else:
+                tr.push_remote_snapshot(scalar=peer[0], cells=peer[1], resolution=peer[2])
+            tr.advance_timestep()
+            if dist:
+                _L.lib().ftkb_get_stats(tr._h, _C.byref(_st))
+                res_layers.append(_st.resolution)
+                factors.append(_st.scaling_factor)
+            continue
         if halo is not None and i == W + K - 1:
             for r in reqs:
                 r.wait()
@@ -490,6 +530,8 @@ def main():
             "config": {"workload": label, "simplices_per_step_per_gpu": per_step, "layers_resident": NL,
                        "l2": "inputs larger than L2 (each fp64 layer >= 0.5 GB; no flush needed)",
                        "parallelism": f"time-slab x{world}" if world > 1 else "single GPU",
+                       "halo": (("nvlink peer memory: the next slab's first layer is read in place (range cells + sparse vertices), nothing copied"
+                                 if use_peer else "ncclSend/ncclRecv of the next slab's first layer, inside the timed region") if world > 1 else None),
                        "step": "one advance_timestep: gradient + min|v| + range cells + exact sign early-out (fused scan kernel) + per-simplex test kernel" if fused else
                                "one advance_timestep: derive(gradient+resolution) + scan + per-simplex test"},
             "roofline": {"bound": "hbm", "kernel": kname,

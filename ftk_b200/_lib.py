@@ -28,6 +28,10 @@ class Config(C.Structure):
     ]
 
 
+class IpcHandle(C.Structure):
+    _fields_ = [("bytes", C.c_uint8 * 64), ("offset", C.c_uint64)]
+
+
 class Stats(C.Structure):
     _fields_ = [
         ("simplices_tested", C.c_uint64), ("cells_scanned", C.c_uint64), ("cells_refined", C.c_uint64), ("points", C.c_uint64),
@@ -68,6 +72,7 @@ EXPORTS = [
     "ftkb_mesh_sides", "ftkb_mesh_side_of",
     "ftkb_curveset_create", "ftkb_get_curveset", "ftkb_curveset_destroy", "ftkb_curveset_post_process", "ftkb_curveset_size",
     "ftkb_curveset_get", "ftkb_curveset_last_error", "ftkb_curveset_slice",
+    "ftkb_ipc_export", "ftkb_ipc_import", "ftkb_ipc_close", "ftkb_export_layer_cells", "ftkb_push_snapshot_remote",
 ]
 
 _lib = None
@@ -123,7 +128,31 @@ def lib():
     L.ftkb_curveset_size.argtypes = [vp, u64p, u64p]
     L.ftkb_curveset_get.argtypes = [vp, vp, vp]
     L.ftkb_curveset_slice.argtypes = [vp, C.c_int32, vp, C.c_uint64, u64p]
+    L.ftkb_ipc_export.argtypes = [vp, C.POINTER(IpcHandle)]
+    L.ftkb_ipc_import.argtypes = [C.POINTER(IpcHandle), C.c_int, C.POINTER(vp)]
+    L.ftkb_ipc_close.argtypes = [vp, C.POINTER(IpcHandle)]
+    L.ftkb_export_layer_cells.argtypes = [vp, C.c_int, C.POINTER(vp), u64p, C.POINTER(C.c_double)]
+    L.ftkb_push_snapshot_remote.argtypes = [vp, vp, vp, vp, C.c_double]
     L.ftkb_curveset_last_error.argtypes = [vp]
     L.ftkb_curveset_last_error.restype = C.c_char_p
     _lib = L
     return L
+
+
+def ipc_export(dev_ptr):
+    """bytes of an ftkb_ipc_handle for a device pointer of this process (send it to a peer process of the same node)"""
+    h = IpcHandle()
+    rc = lib().ftkb_ipc_export(C.c_void_p(int(dev_ptr)), C.byref(h))
+    if rc:
+        raise FTKBError(rc, "ipc_export failed (memory not allocated with cudaMalloc?)")
+    return bytes(h)
+
+
+def ipc_import(handle_bytes, device):
+    """map a peer process's allocation; returns the device pointer (int) valid in this process"""
+    h = IpcHandle.from_buffer_copy(handle_bytes)
+    out = C.c_void_p()
+    rc = lib().ftkb_ipc_import(C.byref(h), int(device), C.byref(out))
+    if rc:
+        raise FTKBError(rc, "ipc_import failed")
+    return int(out.value)

@@ -31,8 +31,9 @@ struct Layer {
   bool ownS = false, ownV = false, ownJ = false;
   int slot = 0;                  // resolution slot
   bool res_pending = false;      // min non-zero |v| not computed yet: the fused scan produces it
-  uint4 *cells = nullptr;        // fused 3D scan: this layer's range cells (kernels.cu, "range summaries")
+  uint4 *cells = nullptr;        // this layer's range cells (kernels.cu, "range cells")
   bool cells_valid = false;
+  bool cells_foreign = false;    // the cells belong to a peer process (remote snapshot) or were exported: never recycled
 };
 
 }  // namespace
@@ -62,6 +63,7 @@ struct ftkb_ctx {
   bool cells2d = true;           // same for the fused 2D tile scan; FTKB_SCAN2D=twolayer re-reads both layers every step
   bool cells3d = true;           // fused 3D scan streams each layer once and keeps its range cells; FTKB_SCAN3D=twolayer re-reads both layers every step
   std::vector<uint4 *> freeCells;
+  std::vector<uint4 *> exportedCells;   // handed to a peer process (ftkb_export_layer_cells): freed at destroy only
   size_t ncells = 0;             // cells per layer (fixed by the dims)
   bool fused3d = false;          // 3D scalar input: gradient fused into the scan (TMA-staged); FTKB_SCAN3D=plain materialises the gradient instead
 
@@ -130,7 +132,7 @@ static void release_layer(ftkb_ctx *c, Layer &l) {
   if (l.ownS && l.S) c->freeS.push_back(l.S);
   if (l.ownV && l.V) c->freeV.push_back(l.V);
   if (l.ownJ && l.J) c->freeJ.push_back(l.J);
-  if (l.cells) c->freeCells.push_back(l.cells);
+  if (l.cells && !l.cells_foreign) c->freeCells.push_back(l.cells);
   l = Layer();
 }
 
@@ -143,6 +145,7 @@ extern "C" void ftkb_destroy(ftkb_ctx *c) {
   for (auto *p : c->freeV) cudaFree(p);
   for (auto *p : c->freeJ) cudaFree(p);
   for (auto *p : c->freeCells) cudaFree(p);
+  for (auto *p : c->exportedCells) cudaFree(p);
   cudaFree(c->d_scalars);
   if (c->h_scalars) cudaFreeHost(c->h_scalars);
   cudaFree(c->d_wl);
@@ -1032,6 +1035,86 @@ extern "C" int ftkb_get_trajectories(ftkb_ctx *c, uint64_t *offsets, uint64_t *p
   std::memcpy(offsets, c->traj_off.data(), 8 * c->traj_off.size());
   if (point_idx && !c->traj_idx.empty()) std::memcpy(point_idx, c->traj_idx.data(), 8 * c->traj_idx.size());
   if (loop && !c->traj_loop.empty()) std::memcpy(loop, c->traj_loop.data(), c->traj_loop.size());
+  return FTKB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// time-slab halo through peer memory
+// ------------------------------------------------------------------------------------------------
+extern "C" int ftkb_ipc_export(const void *dev_ptr, ftkb_ipc_handle *out) {
+  if (!dev_ptr || !out) return FTKB_ERR_INVALID;
+  typedef CUresult (*RangeFn)(CUdeviceptr *, size_t *, CUdeviceptr);
+  static RangeFn range = nullptr;
+  if (!range) {
+    void *fp = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &fp, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) { cudaGetLastError(); return FTKB_ERR_CUDA; }
+    range = reinterpret_cast<RangeFn>(fp);
+  }
+  CUdeviceptr base = 0;
+  size_t size = 0;
+  if (range(&base, &size, (CUdeviceptr)(uintptr_t)dev_ptr) != CUDA_SUCCESS) return FTKB_ERR_CUDA;
+  cudaIpcMemHandle_t h;
+  if (cudaIpcGetMemHandle(&h, reinterpret_cast<void *>(base)) != cudaSuccess) { cudaGetLastError(); return FTKB_ERR_CUDA; }
+  static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  std::memcpy(out->bytes, &h, 64);
+  out->offset = (uint64_t)((uintptr_t)dev_ptr - (uintptr_t)base);
+  return FTKB_OK;
+}
+
+extern "C" int ftkb_ipc_import(const ftkb_ipc_handle *h, int device, void **dev_ptr) {
+  if (!h || !dev_ptr) return FTKB_ERR_INVALID;
+  if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return FTKB_ERR_NO_DEVICE; }
+  cudaIpcMemHandle_t ih;
+  std::memcpy(&ih, h->bytes, 64);
+  void *base = nullptr;
+  if (cudaIpcOpenMemHandle(&base, ih, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); return FTKB_ERR_CUDA; }
+  *dev_ptr = static_cast<char *>(base) + h->offset;
+  return FTKB_OK;
+}
+
+extern "C" int ftkb_ipc_close(void *dev_ptr, const ftkb_ipc_handle *h) {
+  if (!dev_ptr || !h) return FTKB_ERR_INVALID;
+  if (cudaIpcCloseMemHandle(static_cast<char *>(dev_ptr) - h->offset) != cudaSuccess) { cudaGetLastError(); return FTKB_ERR_CUDA; }
+  return FTKB_OK;
+}
+
+extern "C" int ftkb_export_layer_cells(ftkb_ctx *c, int index, void **cells, uint64_t *bytes, double *resolution) {
+  if (!c || !cells || !bytes) return FTKB_ERR_INVALID;
+  if (index < 0 || (size_t)index >= c->layers.size()) return fail(c, FTKB_ERR_INVALID, "export_layer_cells: no such resident layer");
+  Layer &l = c->layers[index];
+  if (!l.cells || !l.cells_valid) return fail(c, FTKB_ERR_INVALID, "export_layer_cells: the layer has no range cells yet (a sweep must have read it)");
+  CK(cudaSetDevice(c->cfg.device));
+  CK(cudaStreamSynchronize(c->stream));
+  if (!l.cells_foreign) { l.cells_foreign = true; c->exportedCells.push_back(l.cells); }
+  *cells = l.cells;
+  *bytes = (uint64_t)c->ncells * sizeof(uint4);
+  if (resolution) *resolution = l.res_pending ? DBL_MAX : slot_value(c, l.slot);
+  return FTKB_OK;
+}
+
+extern "C" int ftkb_push_snapshot_remote(ftkb_ctx *c, const double *scalar, const double *vector, const void *cells, double resolution) {
+  if (!c || !cells || (!scalar && !vector)) return FTKB_ERR_INVALID;
+  if (c->cfg.jacobian_source == FTKB_SOURCE_GIVEN) return fail(c, FTKB_ERR_INVALID, "push_snapshot_remote: a GIVEN jacobian cannot be remote");
+  if (c->cfg.vector_source == FTKB_SOURCE_GIVEN ? !vector : !scalar) return fail(c, FTKB_ERR_INVALID, "push_snapshot_remote: the field the sweep reads is missing");
+  CK(cudaSetDevice(c->cfg.device));
+  Layer l;
+  int rc = new_layer(c, l);
+  if (rc) return rc;
+  l.S = const_cast<double *>(scalar);
+  l.V = const_cast<double *>(vector);
+  l.cells = reinterpret_cast<uint4 *>(const_cast<void *>(cells));
+  l.cells_valid = true;
+  l.cells_foreign = true;
+  l.res_pending = false;
+  // the owner's min non-zero |v| of this layer, as the sweep would have produced it
+  unsigned long long bits;
+  const double r = resolution > 0 ? resolution : DBL_MAX;
+  std::memcpy(&bits, &r, 8);
+  if (!(resolution > 0) || resolution >= DBL_MAX) bits = ~0ull;
+  c->h_scalars[l.slot] = bits;
+  CK(cudaMemcpyAsync(c->d_scalars + l.slot, c->h_scalars + l.slot, sizeof(unsigned long long), cudaMemcpyHostToDevice, c->stream));
+  c->layers.push_back(l);
   return FTKB_OK;
 }
 

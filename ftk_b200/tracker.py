@@ -219,6 +219,18 @@ class _RegularTracker:
         valid and unchanged until two advance_timestep() calls later."""
         self._check(L.lib().ftkb_push_snapshot(self._h, scalar or None, vector or None, jacobian or None, L.MEM_DEVICE_BORROW))
 
+    def export_layer_cells(self, index=0):
+        """(device pointer, bytes, min non-zero |v|) of the range cells of resident layer `index`; the buffer stays alive until
+        close() so that a neighbouring time slab can read it through NVLink peer memory (ftkb_export_layer_cells)"""
+        ptr, nbytes, res = C.c_void_p(), C.c_uint64(), C.c_double()
+        self._check(L.lib().ftkb_export_layer_cells(self._h, int(index), C.byref(ptr), C.byref(nbytes), C.byref(res)))
+        return int(ptr.value), int(nbytes.value), float(res.value)
+
+    def push_remote_snapshot(self, scalar=0, vector=0, cells=0, resolution=0.0):
+        """a layer that lives in a peer process's memory (pointers from _lib.ipc_import) together with its range cells and
+        its min non-zero |v|: the sweep reads the cells and the sparse vertices it needs over NVLink, nothing is copied"""
+        self._check(L.lib().ftkb_push_snapshot_remote(self._h, scalar or None, vector or None, cells or None, float(resolution)))
+
     def push_scalar_field_snapshot(self, scalar, borrow=False):
         self.push_field_data_snapshot(scalar=scalar, borrow=borrow)
 

@@ -149,6 +149,27 @@ int ftkb_get_points(ftkb_ctx *, ftkb_point *out, uint64_t cap);
 /* add punctured simplices found elsewhere (another time slab) before ftkb_finalize */
 int ftkb_import_points(ftkb_ctx *, const ftkb_point *pts, uint64_t n);
 
+/* ---- time-slab halo through NVLink peer memory -------------------------------------------------
+ * The slab below needs the first layer of the slab above only for its last sweep, and of that layer only (a) the
+ * 16-byte range cells and (b) the vertices around the handful of surviving cubes.  Instead of copying
+ * the layer (ncclSend/Recv of 25.8 GB on the 1024^3 vector field), the owner exports IPC handles of the layer and of
+ * its cells; the neighbour process maps them and pushes the layer as a REMOTE snapshot: its last sweep reads the cells
+ * and the sparse vertices straight from the peer's HBM over NVLink / NVSwitch.  Replaces the MPI ghost exchange of
+ * regular_tracker.hh:120-151 for the time-slab decomposition.
+ *
+ * ftkb_ipc_export: handle of the allocation that holds dev_ptr (cudaIpcGetMemHandle) + the pointer's offset in it.
+ * ftkb_ipc_import: map it in another process of the same node (peer access enabled lazily); ftkb_ipc_close unmaps.
+ * ftkb_export_layer_cells: device pointer / size of the range cells of resident layer `index` (0 = current); the
+ *   buffer is pinned to the context (not recycled) until ftkb_destroy.  The cells exist once a sweep has read the layer.
+ * ftkb_push_snapshot_remote: like ftkb_push_snapshot(.., FTKB_MEM_DEVICE_BORROW) for a layer whose cells and min non-zero
+ *   |v| (`resolution`, from the owner's ftkb_last_layer_resolution) come with it; nothing is copied or streamed. */
+typedef struct ftkb_ipc_handle { uint8_t bytes[64]; uint64_t offset; } ftkb_ipc_handle;
+int ftkb_ipc_export(const void *dev_ptr, ftkb_ipc_handle *out);
+int ftkb_ipc_import(const ftkb_ipc_handle *h, int device, void **dev_ptr);
+int ftkb_ipc_close(void *dev_ptr, const ftkb_ipc_handle *h);
+int ftkb_export_layer_cells(ftkb_ctx *, int index, void **cells, uint64_t *bytes, double *resolution /* the layer's min non-zero |v| */);
+int ftkb_push_snapshot_remote(ftkb_ctx *, const double *scalar, const double *vector, const void *cells, double resolution);
+
 /* after ftkb_finalize: trajectories as CSR over the sorted point array */
 int ftkb_num_trajectories(ftkb_ctx *, uint64_t *n);
 int ftkb_get_trajectories(ftkb_ctx *, uint64_t *offsets /* n+1 */, uint64_t *point_idx, uint8_t *loop /* n */);

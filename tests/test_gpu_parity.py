@@ -379,3 +379,100 @@ def test_time_slab_split_equals_single_run(ftk, oracle):
     P.assert_same_result(cuda_result(a), want, tol=0.0, what="time-slab merge")
     for t in (whole, a, b):
         t.close()
+
+
+# ---- time-slab halo through peer memory (two processes, IPC handles) --------------------------------------------
+def _upper_slab_worker(dims, field, snaps_upper, cut, res_init, q_out, q_in):
+    """process of the slab above: builds the range cells of its first layer, exports layer + cells, waits for the slab
+    below to finish its last sweep, then completes its own slab"""
+    import torch
+    import ftk_b200
+    from ftk_b200 import _lib
+    dev = torch.device("cuda", 0)
+    first = torch.from_numpy(np.ascontiguousarray(snaps_upper[0])).to(dev)       # stays alive while the neighbour reads it
+    tr = ftk_b200.make_tracker(dims, field=field, start_timestep=cut, resolution_init=res_init)
+    kw = "scalar" if field == "scalar" else "vector"
+    tr.push_device_pointers(**{kw: int(first.data_ptr())})
+    if field == "scalar":
+        tr.push_scalar_field_snapshot(snaps_upper[1])
+    else:
+        tr.push_vector_field_snapshot(snaps_upper[1])
+    tr.update_timestep()
+    cptr, _, cres = tr.export_layer_cells(0)
+    q_out.put((_lib.ipc_export(int(first.data_ptr())), _lib.ipc_export(cptr), cres))
+    assert q_in.get(timeout=120) == "done"
+    tr.advance_timestep()
+    for k in range(2, len(snaps_upper)):
+        if field == "scalar":
+            tr.push_scalar_field_snapshot(snaps_upper[k])
+        else:
+            tr.push_vector_field_snapshot(snaps_upper[k])
+        tr.advance_timestep()
+    tr.update_timestep()
+    q_out.put(tr.get_discrete_critical_points().tobytes())
+    tr.close()
+
+
+def _lower_slab_worker(dims, field, snaps_lower, q_from_upper, q_to_upper, q_out):
+    """process of the slab below: its last sweep reads the neighbour's first layer in place (cells + sparse vertices)"""
+    import ftk_b200
+    from ftk_b200 import _lib
+    lh, ch, cres = q_from_upper.get(timeout=120)
+    layer, cells = _lib.ipc_import(lh, 0), _lib.ipc_import(ch, 0)
+    tr = ftk_b200.make_tracker(dims, field=field)
+    for k, s in enumerate(snaps_lower):
+        if field == "scalar":
+            tr.push_scalar_field_snapshot(s)
+        else:
+            tr.push_vector_field_snapshot(s)
+        if k:
+            tr.advance_timestep()
+    kw = "scalar" if field == "scalar" else "vector"
+    tr.push_remote_snapshot(**{kw: layer, "cells": cells, "resolution": cres})
+    tr.advance_timestep()
+    q_out.put((tr.get_discrete_critical_points().tobytes(), tr.stats()["kernel_launches"]))
+    q_to_upper.put("done")
+    tr.close()
+
+
+@pytest.mark.parametrize("dims,field", [([70, 40], "scalar"), ([66, 36, 12], "scalar"), ([66, 36, 12], "vector"), ([70, 40], "vector")])
+def test_time_slab_halo_through_peer_memory(dims, field, ftk, oracle):
+    """two processes own the two time slabs; the lower one never receives the upper slab's first layer: it maps the
+    neighbour's layer and range cells (CUDA IPC; NVLink peer memory between GPUs) and sweeps them in place.
+    Merged result == one sequential run == the oracle."""
+    import multiprocessing as mp
+    from ftk_b200 import _lib
+    rng = np.random.default_rng(555 + len(dims))
+    T, cut = 6, 3
+    snaps = _rand_series(rng, dims, T, 1 if field == "scalar" else len(dims), "smooth")
+    whole = ftk.track(snaps, dims, field=field)
+    want = cuda_result(whole)
+    P.assert_same_result(want, P.oracle_result(oracle.track(snaps, dims, field=field)), tol=TOL, what="whole run")
+    # the running resolution the upper slab inherits (layers 0 .. cut)
+    probe = ftk.make_tracker(dims, field=field)
+    for k in range(cut + 1):
+        (probe.push_scalar_field_snapshot if field == "scalar" else probe.push_vector_field_snapshot)(snaps[k])
+        if k:
+            probe.advance_timestep()
+    res = probe.stats()["resolution"]
+    probe.close()
+    ctx = mp.get_context("spawn")
+    q_handles, q_done, q_up, q_lo = ctx.Queue(), ctx.Queue(), ctx.Queue(), ctx.Queue()
+    up = ctx.Process(target=_upper_slab_worker, args=(dims, field, snaps[cut:], cut, res, q_up, q_done))
+    up.start()
+    handles = q_up.get(timeout=180)
+    q_handles.put(handles)
+    lo = ctx.Process(target=_lower_slab_worker, args=(dims, field, snaps[:cut], q_handles, q_done, q_lo))
+    lo.start()
+    lo_pts, lo_launches = q_lo.get(timeout=180)
+    up_pts = q_up.get(timeout=180)
+    lo.join(60)
+    up.join(60)
+    assert lo.exitcode == 0 and up.exitcode == 0 and lo_launches > 0
+    merged = ftk.make_tracker(dims, field=field)
+    merged.import_points(np.frombuffer(lo_pts, dtype=_lib.POINT_DTYPE))
+    merged.import_points(np.frombuffer(up_pts, dtype=_lib.POINT_DTYPE))
+    merged.finalize()
+    P.assert_same_result(cuda_result(merged), want, tol=0.0, what="peer-memory halo")
+    for t in (whole, merged):
+        t.close()
