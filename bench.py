@@ -330,11 +330,18 @@ def main():
         allh = [None] * world
         dist.all_gather_object(allh, mine)
         if all(h is not None for h in allh):
-            if rank < world - 1:
-                lh, ch, cres = allh[rank + 1]
-                peer = (_lib.ipc_import(lh, local), _lib.ipc_import(ch, local), cres)
-            else:
-                peer = ()
+            try:
+                if rank < world - 1:
+                    lh, ch, cres = allh[rank + 1]
+                    peer = (_lib.ipc_import(lh, local), _lib.ipc_import(ch, local), cres)
+                else:
+                    peer = ()
+            except _lib.FTKBError:
+                peer = None
+        oks = [None] * world
+        dist.all_gather_object(oks, peer is not None)
+        if not all(oks):
+            peer = None          # some rank could not export / map: every rank copies the halo with NCCL instead
     use_peer = peer is not None
     for i in range(1 if first_done else 0, W):
         push_ptr(tr, ptrs[tri(g0 + i + 1, NL)])
