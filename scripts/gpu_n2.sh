@@ -1,7 +1,9 @@
 #!/bin/bash
+# N = 2 check of the default multi-GPU bench path (halo through peer memory) and of the NCCL copy
 mkdir -p gpurun_out
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 126 --warmup 3 2> gpurun_out/bench_n2.err | tee gpurun_out/bench_c2_n2.json
-tail -5 gpurun_out/bench_n2.err
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --config c3 --steps 31 --warmup 3 2> gpurun_out/bench_n2c3.err | tee gpurun_out/bench_c3_n2.json
-tail -5 gpurun_out/bench_n2c3.err
-timeout 600 python -m pytest tests -m gpu -q -x -k "shard or distrib or slab" 2>&1 | tail -4
+for halo in peer nccl; do
+FTKB_HALO=$halo timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 126 --warmup 3 2> gpurun_out/bench_n2.err | tee gpurun_out/bench_c2_n2_$halo.json | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); print('c2 n2 $halo', d['value'], d['ms_per_step'], d['trajectories'], d['punctured_simplices'], d['config']['halo'][:24])"
+grep -i "error\|Traceback" gpurun_out/bench_n2.err | head -3
+done
