@@ -11,6 +11,9 @@ timesteps [t0, t1) = slab_range(T, R, r):
               snapshot, json_interface.hh:699-706).  Nothing is swept twice, nothing is dropped.
   halo        one layer: the first layer of slab r+1, sent by its owner (send/recv: ncclSend/ncclRecv
               over NVLink for CUDA tensors).  Skipped when the source can produce any layer locally.
+              halo="peer" (CUDA tracker, ranks on one node): nothing is sent -- the owner exports CUDA IPC
+              handles of the layer and of its 16-byte range cells, the slab below maps them and sweeps the
+              layer in place through NVLink peer memory (ftkb_push_snapshot_remote).
   factor      the reference's quantisation factor is a RUNNING quantity (min non-zero |v| over every layer
               seen so far, critical_point_tracker.hh:850-864).  Every rank sweeps optimistically with the
               minimum of its own slab, then the slab minima are all-gathered; a rank whose factor would
@@ -74,12 +77,50 @@ def _res_factor(tr):
     return float(st["resolution"]), float(st["scaling_factor"])
 
 
-def track_time_sharded(layer, dims, T, field="scalar", group=None, tracker_factory=None, exchange_halo=True, trace=True, **kw):
+def _peer_sweep_slab(make, layer, push, t0, t1, T, field, resolution_init, exchange, keep):
+    """one pass over the slab with the halo read in place from the next rank (see track_time_sharded, halo="peer").
+    exchange(mine) -> handles of the next rank's first layer (or None for the last rank); called once, after this rank's
+    first sweep has built the range cells of its own first layer."""
+    import torch
+    tr = make(t0, resolution_init)
+    log = []
+    last = t1 == T
+    first = layer(t0)
+    if not torch.is_tensor(first) or not first.is_cuda:
+        first = torch.from_numpy(np.ascontiguousarray(first, dtype=np.float64)).cuda()
+    first = first.contiguous()
+    keep.append(first)                                     # the neighbour reads it in place: must outlive the sweep
+    kw = "scalar" if field == "scalar" else "vector"
+    tr.push_device_pointers(**{kw: int(first.data_ptr())})
+    push(tr, layer(t0 + 1))
+    tr.update_timestep()                                   # builds the cells of the first layer
+    cptr, _, cres = tr.export_layer_cells(0)
+    peer = exchange((L.ipc_export(int(first.data_ptr())), L.ipc_export(cptr), cres))
+    tr.advance_timestep()
+    log.append(_res_factor(tr))
+    for k in range(t0 + 2, t1):
+        push(tr, layer(k))
+        tr.advance_timestep()
+        log.append(_res_factor(tr))
+    if last:
+        tr.update_timestep()
+    else:
+        import torch.cuda
+        dev = torch.cuda.current_device()
+        tr.push_remote_snapshot(**{kw: L.ipc_import(peer[0], dev), "cells": L.ipc_import(peer[1], dev), "resolution": peer[2]})
+        tr.advance_timestep()
+    log.append(_res_factor(tr))
+    return tr, log
+
+
+def track_time_sharded(layer, dims, T, field="scalar", group=None, tracker_factory=None, exchange_halo=True, trace=True, halo="copy", **kw):
     """Run the tracker over T timesteps sharded into time slabs over the ranks of `group`.
 
     layer(k)         -> snapshot k in memory order (numpy array or CUDA tensor); called on the rank that owns
                         timestep k (and for the halo layer k = t1 when exchange_halo is False)
     tracker_factory  (dims, field, start_timestep, resolution_init, **kw) -> tracker; default: the CUDA tracker
+    halo             "copy": the halo layer is sent (send/recv); "peer": it is read in place through NVLink peer memory
+                     (CUDA tracker only, every slab at least two timesteps, all ranks on one node)
     Returns the rank-0 tracker holding every punctured simplex (finalized when trace=True) on rank 0 and the
     local slab's tracker elsewhere, plus a dict of bookkeeping (slab, halo bytes, repeated slabs)."""
     import torch
@@ -100,7 +141,49 @@ def track_time_sharded(layer, dims, T, field="scalar", group=None, tracker_facto
         else:
             tr.push_vector_field_snapshot(a)
 
-    info = {"rank": rank, "world": world, "slab": (t0, t1), "halo_bytes": 0, "slab_repeated": False}
+    info = {"rank": rank, "world": world, "slab": (t0, t1), "halo_bytes": 0, "slab_repeated": False, "halo": "copy"}
+    peer_mode = halo == "peer" and world > 1 and tracker_factory is None and all(b - a >= 2 for a, b in (slab_range(T, world, r) for r in range(world)))
+    if peer_mode:
+        info["halo"] = "peer"
+        keep, handles = [], {}
+
+        def exchange(mine):
+            # every rank contributes the handles of its first layer; a rank uses those of the rank above
+            if "all" not in handles:
+                allh = [None] * world
+                dist.all_gather_object(allh, mine, group=group)
+                handles["all"] = allh
+            return handles["all"][rank + 1] if rank < world - 1 else None
+
+        tr, log = _peer_sweep_slab(make, layer, push, t0, t1, T, field, 0.0, exchange, keep)
+        mine = torch.tensor([min(r for r, _ in log)], dtype=torch.float64)
+        dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+        mine = mine.to(dev)
+        allres = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allres, mine, group=group)
+        prefix = exclusive_prefix_min([float(a.item()) for a in allres], rank)
+        info["prefix_resolution"] = prefix
+        if prefix < float("inf") and any(float(1 << nbits_of(min(prefix, r))) != f for r, f in log):
+            # repeat with the inherited minimum; the first pass's tracker stays alive: the rank below may still read its cells
+            keep.append(tr)
+            tr, log = _peer_sweep_slab(make, layer, push, t0, t1, T, field, prefix, exchange, keep)
+            info["slab_repeated"] = True
+        info["factors"] = [f for _, f in log]
+        pts = tr.get_discrete_critical_points()
+        gathered = [None] * world if rank == 0 else None
+        dist.gather_object(pts.tobytes(), gathered, dst=0, group=group)
+        if rank == 0:
+            for b in gathered[1:]:
+                if len(b):
+                    tr.import_points(np.frombuffer(b, dtype=L.POINT_DTYPE))
+        dist.barrier(group=group)             # nobody releases a layer or its cells while a neighbour may still sweep them
+        for t in keep:
+            if hasattr(t, "close"):
+                t.close()
+        if rank == 0 and trace:
+            tr.finalize()
+        return tr, info
+
     # ---- halo: first layer of the next slab --------------------------------------------------------------
     halo = None
     first = None

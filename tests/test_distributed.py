@@ -90,7 +90,7 @@ def make_series(case):
     raise ValueError(case)
 
 
-def _worker(rank, world, port, case, use_cuda, out_path):
+def _worker(rank, world, port, case, use_cuda, out_path, halo="copy"):
     import torch.distributed as dist
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
     try:
@@ -102,7 +102,7 @@ def _worker(rank, world, port, case, use_cuda, out_path):
         def layer(k):
             calls.append(k)
             return snaps[k]
-        tr, info = D.track_time_sharded(layer, dims, T, field=field, tracker_factory=factory)
+        tr, info = D.track_time_sharded(layer, dims, T, field=field, tracker_factory=factory, halo=halo)
         t0, t1 = D.slab_range(T, world, rank)
         assert info["slab"] == (t0, t1)
         assert all(t0 <= k < t1 for k in calls), (calls, t0, t1)      # a rank only ever asks for its own layers: the halo is exchanged
@@ -117,10 +117,10 @@ def _worker(rank, world, port, case, use_cuda, out_path):
         dist.destroy_process_group()
 
 
-def _run(case, tmp_path, use_cuda=False, world=2):
+def _run(case, tmp_path, use_cuda=False, world=2, halo="copy"):
     import torch.multiprocessing as mp
     out = str(tmp_path / "res")
-    mp.spawn(_worker, args=(world, _free_port(), case, use_cuda, out), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), case, use_cuda, out, halo), nprocs=world, join=True)
     return [pickle.load(open(f"{out}.{r}", "rb")) for r in range(world)]
 
 
@@ -185,3 +185,17 @@ def test_two_slabs_cuda(case, tmp_path, oracle):
     want, _ = _sequential(case, oracle)
     res = _run(case, tmp_path, use_cuda=True)
     P.assert_same_result(res[0], want, tol=1e-9, what=f"CUDA time slabs x2 ({case})")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["woven", "resolution_prefix", "3d", "vector"])
+def test_two_slabs_cuda_peer_memory_halo(case, tmp_path, oracle):
+    """halo="peer": the upper slab's first layer is never sent; the lower slab maps it and its range cells (CUDA IPC, NVLink
+    peer memory between GPUs) and sweeps them in place -- including the slab that is repeated with an inherited resolution"""
+    import _parity as P
+    want, _ = _sequential(case, oracle)
+    res = _run(case, tmp_path, use_cuda=True, halo="peer")
+    assert all(r["info"]["halo"] == "peer" and r["info"]["halo_bytes"] == 0 for r in res)
+    if case == "resolution_prefix":
+        assert res[1]["info"]["slab_repeated"]
+    P.assert_same_result(res[0], want, tol=1e-9, what=f"CUDA time slabs x2, peer-memory halo ({case})")
