@@ -1,10 +1,7 @@
 #!/bin/bash
-# quick GPU check: parity tests + short C2/C3 bench lines
+# memcheck of the scan / build / test kernels on small parity cases (slow: a few minutes)
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -5 | tee gpurun_out/pytest_gpu.log
-timeout 300 python bench.py --steps 60 --no-cpu-baseline --e2e-steps 4 2> gpurun_out/bench.err | tee gpurun_out/bench_quick_c2.json | cut -c1-400
-tail -3 gpurun_out/bench.err
-timeout 300 python bench.py --config c3 --steps 31 --no-cpu-baseline --e2e-steps 4 2> gpurun_out/bench_c3.err | tee gpurun_out/bench_quick_c3.json | cut -c1-400
-tail -3 gpurun_out/bench_c3.err
-cp MEASURED_PEAKS.json gpurun_out/ 2>/dev/null
-nvidia-smi -L
+timeout 420 compute-sanitizer --tool memcheck --error-exitcode 3 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "range_cell_scan or direct_staging or matches_oracle_random or non_finite or single_snapshot or buffers_grow" > gpurun_out/memcheck.log 2>&1
+echo "memcheck rc=$?"
+grep -c "Invalid\|out of bounds" gpurun_out/memcheck.log; grep "ERROR SUMMARY\|passed\|failed" gpurun_out/memcheck.log | tail -5
+grep -B2 -A12 "Invalid" gpurun_out/memcheck.log | head -60
