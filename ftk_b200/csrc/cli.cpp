@@ -51,7 +51,7 @@ void usage() {
       "      --x0 a,b[,c]  --dir a,b[,c]   moving_extremum parameters;  --time-scale s (double_gyre)\n"
       "  -o, --output FILE                 result file\n"
       "      --output-type traced|discrete|sliced  (default traced; sliced: OUTPUT is a printf pattern, one text file per timestep)\n"
-      "      --output-format text|json         (default: by file name, .json -> json, else text)\n"
+      "      --output-format text|json|binary  (default: by file name, .json -> json, else text; binary = the reference's DIY archive)\n"
       "      --type-filter min|max|saddle|...  (2D; names joined with |)\n"
       "      --post-process OPS                smooth_types,rotate,split,discard_interval_points,reorder,adjust_time,derive_velocity,...\n"
       "      --compute-degrees  --no-robust-detection  --timing  -v/--verbose\n"
@@ -330,9 +330,11 @@ int main(int argc, char **argv) {
     std::string fmt = o.output_format;
     if (fmt == "auto") fmt = (o.output.size() > 5 && o.output.substr(o.output.size() - 5) == ".json") ? "json" : "text";
     if (o.output_type == "traced") {
-      if (fmt == "json") tr->write_traced_critical_points_json(o.output); else if (fmt == "text") tr->write_traced_critical_points_text(o.output); else die("unsupported --output-format " + fmt);
+      if (fmt == "json") tr->write_traced_critical_points_json(o.output); else if (fmt == "text") tr->write_traced_critical_points_text(o.output);
+      else if (fmt == "binary") tr->write_traced_critical_points_binary(o.output); else die("unsupported --output-format " + fmt);
     } else if (o.output_type == "discrete") {
-      if (fmt == "json") tr->write_critical_points_json(o.output); else if (fmt == "text") tr->write_critical_points_text(o.output); else die("unsupported --output-format " + fmt);
+      if (fmt == "json") tr->write_critical_points_json(o.output); else if (fmt == "text") tr->write_critical_points_text(o.output);
+      else if (fmt == "binary") tr->write_critical_points_binary(o.output); else die("unsupported --output-format " + fmt);
     } else if (o.output_type == "sliced") {       // json_interface.hh:805-811,584-592: one file per timestep, series_filename(pattern, k)
       if (fmt != "text") die("sliced output is written as text");
       if (o.output.find('%') == std::string::npos) die("--output-type sliced needs a printf pattern in --output (e.g. sliced-%03d.txt)");

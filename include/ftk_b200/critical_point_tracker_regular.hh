@@ -145,6 +145,30 @@ struct feature_point_t {
   }
 };
 
+// ---- binary archives: the byte layout of the reference's DIY serialization (little endian, no padding) ----------
+// feature_point.hh:160-188: x[3] t timestep(int) scalar[FTK_CP_MAX_NUM_VARS = 3] v[3] type(unsigned) ordinal(bool) tag id = 105 bytes
+namespace bin {
+template <typename T> inline void put(std::ostream &os, const T &v) { os.write(reinterpret_cast<const char *>(&v), sizeof(T)); }
+template <typename T> inline bool get(std::istream &is, T &v) { is.read(reinterpret_cast<char *>(&v), sizeof(T)); return (bool)is; }
+inline void put_point(std::ostream &os, const feature_point_t &p) {
+  for (double v : p.x) put(os, v);
+  put(os, p.t); put(os, (int)p.timestep);
+  for (double v : p.scalar) put(os, v);
+  for (double v : p.v) put(os, v);
+  put(os, (unsigned int)p.type); put(os, (unsigned char)(p.ordinal ? 1 : 0)); put(os, (unsigned long long)p.tag); put(os, (unsigned long long)p.id);
+}
+inline bool get_point(std::istream &is, feature_point_t &p) {
+  unsigned char o = 0;
+  for (double &v : p.x) get(is, v);
+  get(is, p.t); get(is, p.timestep);
+  for (double &v : p.scalar) get(is, v);
+  for (double &v : p.v) get(is, v);
+  get(is, p.type); get(is, o); get(is, p.tag);
+  p.ordinal = o != 0;
+  return get(is, p.id);
+}
+}  // namespace bin
+
 // one trajectory (ref: include/ftk/features/feature_curve.hh:8-54,145-184)
 struct feature_curve_t : public std::vector<feature_point_t> {
   int id = 0;
@@ -214,6 +238,45 @@ struct feature_curve_set_t : public std::multimap<int, feature_curve_t> {
       os << "loop=" << c.loop << std::endl;
       for (const auto &p : c) { os << "---"; p.print(os, scalar_components) << std::endl; }
     }
+  }
+
+  // the reference's binary archive: diy::save(bb, feature_curve_set_t) (feature_curve_set.hh:92-100) = count, then per curve
+  // its id and diy::Serialization<feature_curve_t>::save (feature_curve.hh:472-487): complete, max, min, persistence, bbmin, bbmax,
+  // tmin, tmax, consistent_type, size, points.  (The loop flag is not part of the reference's archive.)
+  void write_binary(std::ostream &os) const {
+    bin::put(os, (unsigned long long)size());
+    for (const auto &kv : *this) {
+      const auto &c = kv.second;
+      bin::put(os, (int)kv.first);
+      bin::put(os, (unsigned char)(c.complete ? 1 : 0));
+      for (const auto *a : {&c.max, &c.min, &c.persistence, &c.bbmin, &c.bbmax})
+        for (double v : *a) bin::put(os, v);
+      bin::put(os, c.tmin); bin::put(os, c.tmax); bin::put(os, (unsigned int)c.consistent_type);
+      bin::put(os, (unsigned long long)c.size());
+      for (const auto &p : c) bin::put_point(os, p);
+    }
+  }
+  bool read_binary(std::istream &is) {     // diy::load: every curve is relabelled with its id and inserted
+    unsigned long long n = 0;
+    if (!bin::get(is, n)) return false;
+    for (unsigned long long i = 0; i < n; i++) {
+      int id = 0;
+      unsigned char complete = 0;
+      feature_curve_t c;
+      bin::get(is, id); bin::get(is, complete);
+      c.complete = complete != 0;
+      for (auto *a : {&c.max, &c.min, &c.persistence, &c.bbmin, &c.bbmax})
+        for (double &v : *a) bin::get(is, v);
+      bin::get(is, c.tmin); bin::get(is, c.tmax); bin::get(is, c.consistent_type);
+      unsigned long long np = 0;
+      if (!bin::get(is, np)) return false;
+      c.resize(np);
+      for (auto &p : c)
+        if (!bin::get_point(is, p)) return false;
+      c.relabel(id);
+      insert(std::make_pair(id, c));
+    }
+    return true;
   }
 
   // keys of the reference's JSON archive (feature_curve_set.hh:79-89, feature_curve.hh:437-451, feature_point.hh:129-145)
@@ -355,8 +418,7 @@ class critical_point_tracker_regular {
     for (uint64_t i = 0; i < nt; i++) {
       feature_curve_t c;
       for (uint64_t k = off[i]; k < off[i + 1]; k++) c.push_back(points_[idx[k]]);
-      c.loop = loop[i] != 0;
-      c.complete = true;
+      c.loop = loop[i] != 0;          // (complete stays false: only the online tracer sets it, critical_point_tracker.hh:603)
       if (discard_interval_) c.discard_interval_points();
       if (discard_degenerate_) c.erase(std::remove_if(c.begin(), c.end(), [](const feature_point_t &p) { return p.type == 1; }), c.end());
       c.update_statistics();
@@ -409,6 +471,25 @@ class critical_point_tracker_regular {
   void write_traced_critical_points_text(std::ostream &os) const { traced_.write_text(os, scalar_components_); }
   void write_traced_critical_points_text(const std::string &f) const { std::ofstream o(f); write_traced_critical_points_text(o); }
   void write_traced_critical_points_json(const std::string &f) const { std::ofstream o(f); traced_.write_json(o); }
+  // critical_point_tracker.hh:339-364: diy::serializeToFile(get_critical_points() / traced_critical_points, filename)
+  void write_traced_critical_points_binary(const std::string &f) const { std::ofstream o(f, std::ios::binary); traced_.write_binary(o); }
+  bool read_traced_critical_points_binary(const std::string &f) { std::ifstream i(f, std::ios::binary); traced_.clear(); return i && traced_.read_binary(i); }
+  void write_critical_points_binary(const std::string &f) {
+    const std::vector<feature_point_t> pts = ctx_ ? get_critical_points() : points_;
+    std::ofstream o(f, std::ios::binary);
+    bin::put(o, (unsigned long long)pts.size());
+    for (const auto &p : pts) bin::put_point(o, p);
+  }
+  bool read_critical_points_binary(const std::string &f) {      // put_critical_points: the points become the tracker's discrete set
+    std::ifstream i(f, std::ios::binary);
+    unsigned long long n = 0;
+    if (!i || !bin::get(i, n)) return false;
+    points_.assign(n, feature_point_t());
+    for (auto &p : points_)
+      if (!bin::get_point(i, p)) return false;
+    points_valid_ = true;
+    return true;
+  }
 
   // ---- sliced output: critical_point_tracker.hh:819-835 (slice_traced_critical_points), :465-474 (text) ----
   void slice_traced_critical_points() {

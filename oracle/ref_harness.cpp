@@ -15,6 +15,7 @@
 //                  (--gen NAME [--p a b c ...] | --input raw.f64)
 //                  [--domain lb0 ub0 lb1 ub1 [lb2 ub2]] [--symmetric 0|1] [--nthreads N]
 //                  [--no-trace] [--out file.ftkg] [--dump-input raw.f64] [--quiet]
+//                  [--binary-discrete file] [--binary-traced file]   the reference's own binary archives (DIY serialization)
 //                  [--post OPS --out-curves file.ftkc]   trajectory post-processing by the reference's own curve code:
 //                  OPS as feature_curve_set_post_processor_t takes them, plus legacy[:thr[:discard[:velocity]]] = the
 //                  call sequence of json_interface::post_process() (json_interface.hh:758-800) on the same methods
@@ -38,7 +39,7 @@ struct args_t {
   int symmetric = -1;
   bool trace = true, quiet = false, have_domain = false;
   int dom[6] = {0, 0, 0, 0, 0, 0};
-  std::string gen, input, out, dump_input, post, out_curves;
+  std::string gen, input, out, dump_input, post, out_curves, bin_traced, bin_discrete;
   std::vector<double> p;
 };
 
@@ -141,6 +142,7 @@ static int run(const args_t &a)
   if (fin) fclose(fin);
   if (fdump) fclose(fdump);
 
+  if (!a.bin_discrete.empty()) tr.write_critical_points_binary(a.bin_discrete);
   // discrete critical points (std::map order == element operator<, x-first lexicographic)
   const auto pts = tr.get_discrete_critical_points(); // copy: finalize() may clear on non-root
   std::map<unsigned long long, size_t> tag2idx;
@@ -154,6 +156,7 @@ static int run(const args_t &a)
     tr.finalize();
     t_final = std::chrono::duration<double>(clk::now() - c0).count();
     if (!tags_unique) { fprintf(stderr, "tags not unique; cannot index trajectories\n"); return 3; }
+    if (!a.bin_traced.empty()) tr.write_traced_critical_points_binary(a.bin_traced);
     for (const auto &kv : tr.get_traced_critical_points()) {
       std::vector<size_t> idx;
       for (const auto &cp : kv.second) idx.push_back(tag2idx.at(cp.tag));
@@ -278,6 +281,8 @@ int main(int argc, char **argv)
     else if (s == "--symmetric") a.symmetric = atoi(next());
     else if (s == "--nthreads") a.nthreads = atoi(next());
     else if (s == "--no-trace") a.trace = false;
+    else if (s == "--binary-traced") a.bin_traced = next();      // tracker.write_traced_critical_points_binary (DIY archive)
+    else if (s == "--binary-discrete") a.bin_discrete = next();  // tracker.write_critical_points_binary
     else if (s == "--post") a.post = next();
     else if (s == "--out-curves") a.out_curves = next();
     else if (s == "--quiet") a.quiet = true;
