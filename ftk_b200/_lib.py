@@ -73,6 +73,8 @@ EXPORTS = [
     "ftkb_curveset_create", "ftkb_get_curveset", "ftkb_curveset_destroy", "ftkb_curveset_post_process", "ftkb_curveset_size",
     "ftkb_curveset_get", "ftkb_curveset_last_error", "ftkb_curveset_slice",
     "ftkb_ipc_export", "ftkb_ipc_import", "ftkb_ipc_close", "ftkb_export_layer_cells", "ftkb_push_snapshot_remote",
+    "ftkb_set_streaming_trajectories", "ftkb_get_trajectory_complete", "ftkb_online_create", "ftkb_online_destroy", "ftkb_online_grow",
+    "ftkb_online_size", "ftkb_online_get",
 ]
 
 _lib = None
@@ -134,6 +136,14 @@ def lib():
     L.ftkb_export_layer_cells.argtypes = [vp, C.c_int, C.POINTER(vp), u64p, C.POINTER(C.c_double)]
     L.ftkb_push_snapshot_remote.argtypes = [vp, vp, vp, vp, C.c_double]
     L.ftkb_curveset_last_error.argtypes = [vp]
+    L.ftkb_set_streaming_trajectories.argtypes = [vp, C.c_int]
+    L.ftkb_get_trajectory_complete.argtypes = [vp, vp]
+    L.ftkb_online_create.argtypes = [C.c_int, vp, vp, C.POINTER(vp)]
+    L.ftkb_online_destroy.argtypes = [vp]
+    L.ftkb_online_destroy.restype = None
+    L.ftkb_online_grow.argtypes = [vp, vp, C.c_uint64]
+    L.ftkb_online_size.argtypes = [vp, u64p, u64p]
+    L.ftkb_online_get.argtypes = [vp, vp, vp, vp, vp]
     L.ftkb_curveset_last_error.restype = C.c_char_p
     _lib = L
     return L

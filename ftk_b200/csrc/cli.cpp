@@ -29,7 +29,7 @@ struct Options {
   std::string type_filter, accelerator = "cuda", var, post_process;
   long width = -1, height = -1, depth = -1, timesteps = -1;
   int device = 0, nthreads = 0;
-  bool timing = false, compute_degrees = false, no_robust = false, verbose = false, device_generators = false, help = false;
+  bool timing = false, compute_degrees = false, no_robust = false, verbose = false, device_generators = false, help = false, stream = false;
   std::vector<double> x0, dir;
   double time_scale = 0.1;
 };
@@ -55,6 +55,7 @@ void usage() {
       "      --type-filter min|max|saddle|...  (2D; names joined with |)\n"
       "      --post-process OPS                smooth_types,rotate,split,discard_interval_points,reorder,adjust_time,derive_velocity,...\n"
       "      --compute-degrees  --no-robust-detection  --timing  -v/--verbose\n"
+      "      --stream                          streaming trajectories: grown after every timestep (trace_critical_points_online)\n"
       "  -a, --accelerator cuda            (the only back end)   --device ID   --nthreads N (ignored)\n"
       "      --device-generators           synthesise inputs on the GPU (CUDA libm; not bit-identical to the host generators)");
 }
@@ -104,7 +105,7 @@ Options parse(int argc, char **argv) {
     else if (a == "-v" || a == "--verbose") o.verbose = true;
     else if (a == "--help") o.help = true;
     else if (a == "--post-process") o.post_process = need(i);      // src/cli/ftk.cpp:253-257, :971
-    else if (a == "--stream") die(a + " is not implemented (SURVEY.md 8 f4)");
+    else if (a == "--stream") o.stream = true;                      // src/cli/ftk.cpp:47,202-203: enable_streaming_trajectories
     else die("unknown option " + a);
   }
   return o;
@@ -287,6 +288,7 @@ int main(int argc, char **argv) {
     tr->set_device_ids({o.device});
     if (!o.type_filter.empty()) tr->set_type_filter(parse_type_filter(o.type_filter));
     if (o.compute_degrees) tr->set_enable_computing_degrees(true);
+    if (o.stream) tr->set_enable_streaming_trajectories(true);      // json_interface.hh:324-325
     if (o.no_robust) tr->set_enable_robust_detection(false);
     tr->initialize();
     const double t_init = now();

@@ -18,7 +18,10 @@
 #include <string>
 #include <vector>
 
+#include <memory>
 #include "kernels.h"
+#include "online.h"
+#include "curves.h"
 
 using namespace ftkb;
 
@@ -86,7 +89,13 @@ struct ftkb_ctx {
   std::vector<uint64_t> labels;
   std::vector<int32_t> deg;
   std::vector<uint64_t> traj_off, traj_idx;
-  std::vector<uint8_t> traj_loop;
+  std::vector<uint8_t> traj_loop, traj_complete;
+
+  // streaming trajectories (critical_point_tracker.hh:38,522-641): grown on the host after every interval sweep
+  bool streaming = false;
+  std::unique_ptr<ftkb::OnlineTracer> online;
+  uint64_t grown = 0;            // d_pts[0 .. grown) have been through a grow step
+  std::vector<ftkb_point> batch;
 
   ftkb_stats stats{};
 };
@@ -583,6 +592,34 @@ static int resolve_pending(ftkb_ctx *c, Layer &l) {
 }
 
 // ref: critical_point_tracker_{2d,3d}_regular::update_timestep (xl == NONE branch)
+// grow(), critical_point_tracker_2d_regular.hh:288-329 / ..._3d_regular.hh:173-200: the punctured simplices found since
+// the last grow step (the reference clears discrete_critical_points after each) go to the host-side online tracer
+static int grow_trajectories(ftkb_ctx *c) {
+  const uint64_t n = c->npts - c->grown;
+  if (n >= 0xffffffffull) return fail(c, FTKB_ERR_OVERFLOW, "more than 2^32 punctured simplices in one step");
+  c->batch.resize(n);
+  if (n) {
+    CK(cudaMemcpyAsync(c->batch.data(), c->d_pts + c->grown, sizeof(ftkb_point) * n, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->stats.d2h_bytes += sizeof(ftkb_point) * n;
+  }
+  const auto t0 = std::chrono::steady_clock::now();
+  c->online->grow(c->batch.data(), n);
+  c->stats.ms_finalize_host += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  c->grown = c->npts;
+  c->traced = false;
+  return FTKB_OK;
+}
+
+extern "C" int ftkb_set_streaming_trajectories(ftkb_ctx *c, int enable) {
+  if (!c) return FTKB_ERR_INVALID;
+  if (c->stats.scan_launches || c->npts) return fail(c, FTKB_ERR_INVALID, "set_streaming_trajectories: call it before the first update_timestep");
+  c->streaming = enable != 0;
+  c->online.reset(c->streaming ? new ftkb::OnlineTracer(c->n, c->cfg.lb, c->cfg.ub) : nullptr);
+  c->grown = 0;
+  return FTKB_OK;
+}
+
 extern "C" int ftkb_update_timestep(ftkb_ctx *c) {
   if (!c) return FTKB_ERR_INVALID;
   if (c->layers.empty()) return fail(c, FTKB_ERR_INVALID, "update_timestep: no snapshot has been pushed");
@@ -807,6 +844,7 @@ extern "C" int ftkb_update_timestep(ftkb_ctx *c) {
     if (npt != c->npts) { c->sorted = false; c->traced = false; }
     c->npts = npt;
     c->stats.points = npt;
+    if (c->streaming && has_next) { const int rc2 = grow_trajectories(c); if (rc2) return rc2; }
     return FTKB_OK;
   }
   return fail(c, FTKB_ERR_CUDA, "update_timestep: buffers kept overflowing");
@@ -908,6 +946,7 @@ extern "C" int ftkb_get_points(ftkb_ctx *c, ftkb_point *out, uint64_t cap) {
 
 extern "C" int ftkb_import_points(ftkb_ctx *c, const ftkb_point *pts, uint64_t n) {
   if (!c || (!pts && n)) return FTKB_ERR_INVALID;
+  if (c->streaming) return fail(c, FTKB_ERR_INVALID, "import_points: not available with streaming trajectories");
   if (!n) return FTKB_OK;
   CK(cudaSetDevice(c->cfg.device));
   if (c->npts + n > c->pt_cap) {
@@ -936,6 +975,29 @@ extern "C" int ftkb_finalize(ftkb_ctx *c) {
   c->traj_off.assign(1, 0);
   c->traj_idx.clear();
   c->traj_loop.clear();
+  c->traj_complete.clear();
+  if (c->streaming) {
+    // "done" (critical_point_tracker_2d_regular.hh:150-151): publish the grown trajectories, in id order, as CSR over
+    // the sorted points; the component labels / degrees of the offline trace are not computed
+    const auto t0 = std::chrono::steady_clock::now();
+    std::vector<uint64_t> keys(n);
+    for (uint64_t i = 0; i < n; i++) c->online->key_of(c->pts_sorted[i], keys[i]);
+    for (const ftkb::OnlineCurve &cv : c->online->curves()) {
+      for (const ftkb_point &p : cv.pts) {
+        uint64_t key = 0;
+        c->online->key_of(p, key);
+        const auto it = std::lower_bound(keys.begin(), keys.end(), key);
+        if (it == keys.end() || *it != key) return fail(c, FTKB_ERR_INVALID, "finalize: a streamed point is missing from the sorted points");
+        c->traj_idx.push_back((uint64_t)(it - keys.begin()));
+      }
+      c->traj_loop.push_back(cv.loop);
+      c->traj_complete.push_back(cv.complete);
+      c->traj_off.push_back(c->traj_idx.size());
+    }
+    c->stats.ms_finalize_host += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    c->traced = true;
+    return FTKB_OK;
+  }
   if (n == 0) { c->traced = true; return FTKB_OK; }
 
   // device: neighbour search among punctured simplices + union-find (all nodes / ordinary nodes)
@@ -1026,6 +1088,13 @@ extern "C" int ftkb_num_trajectories(ftkb_ctx *c, uint64_t *n) {
   if (!c || !n) return FTKB_ERR_INVALID;
   if (!c->traced) return fail(c, FTKB_ERR_INVALID, "num_trajectories: call finalize first");
   *n = c->traj_loop.size();
+  return FTKB_OK;
+}
+
+extern "C" int ftkb_get_trajectory_complete(ftkb_ctx *c, uint8_t *complete) {
+  if (!c || !complete) return FTKB_ERR_INVALID;
+  if (!c->traced) return fail(c, FTKB_ERR_INVALID, "get_trajectory_complete: call finalize first");
+  for (size_t k = 0; k < c->traj_loop.size(); k++) complete[k] = k < c->traj_complete.size() ? c->traj_complete[k] : 0;
   return FTKB_OK;
 }
 
@@ -1123,8 +1192,11 @@ extern "C" int ftkb_get_curveset(ftkb_ctx *c, ftkb_curveset **out) {
   if (!c->traced) return fail(c, FTKB_ERR_INVALID, "get_curveset: call finalize first");
   const uint64_t ntraj = c->traj_off.empty() ? 0 : c->traj_off.size() - 1;
   static const uint64_t zero = 0;
-  return ftkb_curveset_create(c->pts_sorted.data(), c->pts_sorted.size(), ntraj ? c->traj_off.data() : &zero, c->traj_idx.data(),
-                              c->traj_loop.data(), ntraj, out);
+  const int rc = ftkb_curveset_create(c->pts_sorted.data(), c->pts_sorted.size(), ntraj ? c->traj_off.data() : &zero, c->traj_idx.data(),
+                                      c->traj_loop.data(), ntraj, out);
+  if (rc == FTKB_OK)   // streaming: feature_curve_t::complete as the grow steps left it (curves are in id order)
+    for (size_t k = 0; k < c->traj_complete.size() && k < (*out)->curves.size(); k++) (*out)->curves[k].complete = c->traj_complete[k] != 0;
+  return rc;
 }
 
 extern "C" int ftkb_get_component_labels(ftkb_ctx *c, uint64_t *labels) {

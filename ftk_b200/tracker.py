@@ -75,6 +75,7 @@ class _RegularTracker:
         self._type_filter = None
         self._start_timestep = 0
         self._resolution_init = 0.0
+        self._streaming = False
         self._keep = []   # borrowed device arrays stay referenced while resident
 
     # ---- configuration (same names as the reference) ------------------------------------------
@@ -104,6 +105,10 @@ class _RegularTracker:
 
     def set_type_filter(self, f):
         self._type_filter = int(f)
+
+    def set_enable_streaming_trajectories(self, b):
+        """ref: critical_point_tracker.hh:38 -- trajectories grown after every interval sweep (hh:522-641)"""
+        self._streaming = bool(b)
 
     def set_start_timestep(self, t):
         self._start_timestep = int(t)
@@ -157,6 +162,8 @@ class _RegularTracker:
             raise L.FTKBError(rc, L.lib().ftkb_last_error(None).decode())
         self._h = h
         self._dims = list(dims)
+        if self._streaming:
+            self._check(L.lib().ftkb_set_streaming_trajectories(self._h, 1))
 
     def reset(self):
         self.close()
@@ -294,6 +301,14 @@ class _RegularTracker:
         self._check(L.lib().ftkb_get_trajectories(self._h, off.ctypes.data, idx.ctypes.data, loop.ctypes.data))
         return [(idx[int(off[i]):int(off[i + 1])].astype(np.int64), bool(loop[i])) for i in range(nt.value)]
 
+    def get_trajectory_complete(self):
+        """feature_curve_t::complete of every trajectory (set by the streaming grow step; all False otherwise)"""
+        nt = C.c_uint64()
+        self._check(L.lib().ftkb_num_trajectories(self._h, C.byref(nt)))
+        out = np.zeros(max(nt.value, 1), np.uint8)
+        self._check(L.lib().ftkb_get_trajectory_complete(self._h, out.ctypes.data))
+        return out[:nt.value].astype(bool)
+
     def get_traced_critical_points(self):
         """list of trajectories, each a structured array of points in trace order (with .loop in the
         second tuple member); the counterpart of feature_curve_set_t"""
@@ -347,7 +362,7 @@ class critical_point_tracker_3d_regular(_RegularTracker):
 
 def make_tracker(dims, field="scalar", lb=None, ub=None, jacobian_symmetric=None, robust=True, compute_degrees=False,
                  type_filter=None, start_timestep=0, device=0, resolution_init=0.0,
-                 scalar_source=None, vector_source=None, jacobian_source=None):
+                 scalar_source=None, vector_source=None, jacobian_source=None, streaming=False):
     """Configure a tracker the way the reference's front ends do (json_interface.hh:634-656):
     scalar input -> lattice({2,..}, {D-3,..}) = [2, D-2], derived gradient/Hessian, symmetric;
     vector input -> lattice({1,..}, {D-2,..}) = [1, D-2], derived Jacobian, non-symmetric."""
@@ -371,6 +386,7 @@ def make_tracker(dims, field="scalar", lb=None, ub=None, jacobian_symmetric=None
     tr.set_array_domain(Lattice([0] * nd, dims))
     tr.set_start_timestep(start_timestep)
     tr.set_initial_resolution(resolution_init)
+    tr.set_enable_streaming_trajectories(streaming)
     tr.initialize()
     return tr
 

@@ -329,7 +329,8 @@ class critical_point_tracker_regular {
   void set_type_filter(unsigned int f) { use_type_filter_ = true; type_filter_ = f; }
   void set_enable_robust_detection(bool b) { robust_ = b; }
   void set_enable_computing_degrees(bool b) { degrees_ = b; }
-  void set_enable_streaming_trajectories(bool b) { if (b) throw std::runtime_error("ftk_b200: streaming trajectories are not implemented (SURVEY.md 8 f4)"); }
+  // critical_point_tracker.hh:38; trajectories then grow after every interval sweep (trace_critical_points_online, hh:522-641)
+  void set_enable_streaming_trajectories(bool b) { streaming_ = b; }
   void set_enable_discarding_interval_points(bool b) { discard_interval_ = b; }
   void set_enable_discarding_degenerate_points(bool b) { discard_degenerate_ = b; }
   void set_scalar_components(const std::vector<std::string> &c) { scalar_components_ = c; }
@@ -367,6 +368,7 @@ class critical_point_tracker_regular {
     cfg.start_timestep = start_timestep_; cfg.device = device_; cfg.resolution_init = resolution_init_;
     const int rc = ftkb_create(&cfg, &ctx_);
     if (rc != FTKB_OK) throw std::runtime_error(std::string("ftkb_create: ") + ftkb_last_error(nullptr));
+    if (streaming_) check(ftkb_set_streaming_trajectories(ctx_, 1));
   }
 
   void reset() {
@@ -414,11 +416,14 @@ class critical_point_tracker_regular {
     std::vector<uint64_t> off(nt + 1), idx(points_.size() ? points_.size() : 1);
     std::vector<uint8_t> loop(nt ? nt : 1);
     check(ftkb_get_trajectories(ctx_, off.data(), idx.data(), loop.data()));
+    std::vector<uint8_t> complete(nt ? nt : 1);
+    check(ftkb_get_trajectory_complete(ctx_, complete.data()));
     traced_.clear();
     for (uint64_t i = 0; i < nt; i++) {
       feature_curve_t c;
       for (uint64_t k = off[i]; k < off[i + 1]; k++) c.push_back(points_[idx[k]]);
-      c.loop = loop[i] != 0;          // (complete stays false: only the online tracer sets it, critical_point_tracker.hh:603)
+      c.loop = loop[i] != 0;
+      c.complete = complete[i] != 0;  // only the online tracer sets it (critical_point_tracker.hh:603)
       if (discard_interval_) c.discard_interval_points();
       if (discard_degenerate_) c.erase(std::remove_if(c.begin(), c.end(), [](const feature_point_t &p) { return p.type == 1; }), c.end());
       c.update_statistics();
@@ -561,7 +566,7 @@ class critical_point_tracker_regular {
   ftkb_ctx *ctx_ = nullptr;
   lattice domain_, array_domain_;
   int scalar_source_ = SOURCE_NONE, vector_source_ = SOURCE_NONE, jacobian_source_ = SOURCE_NONE;
-  bool symmetric_ = false, robust_ = true, degrees_ = false, use_type_filter_ = false, discard_interval_ = false, discard_degenerate_ = false;
+  bool symmetric_ = false, robust_ = true, degrees_ = false, use_type_filter_ = false, discard_interval_ = false, discard_degenerate_ = false, streaming_ = false;
   unsigned int type_filter_ = 0;
   int start_timestep_ = 0, device_ = 0;
   double resolution_init_ = 0.0;

@@ -178,6 +178,25 @@ int ftkb_get_trajectories(ftkb_ctx *, uint64_t *offsets /* n+1 */, uint64_t *poi
 int ftkb_get_component_labels(ftkb_ctx *, uint64_t *labels);
 int ftkb_get_degrees(ftkb_ctx *, int32_t *deg);
 
+/* ---- streaming trajectories --------------------------------------------------------------------
+ * set_enable_streaming_trajectories (critical_point_tracker.hh:38): with streaming on, every ftkb_update_timestep that
+ * sweeps an interval (two resident snapshots) ends with the reference's grow step, trace_critical_points_online
+ * (critical_point_tracker.hh:522-641): the punctured simplices found since the last grow step are copied to the host,
+ * existing trajectories claim their neighbours greedily, and what is left starts new trajectories.  ftkb_finalize then
+ * only publishes them ("done", critical_point_tracker_2d_regular.hh:150-151): the CSR of ftkb_get_trajectories is in
+ * trajectory-id order, and -- as in the reference -- the punctured simplices of the last ordinal sweep belong to no
+ * trajectory.  Must be called before the first ftkb_update_timestep.  ftkb_get_trajectory_complete: 1 for a trajectory
+ * that a grow step found nothing to add to (feature_curve_t::complete); all 0 without streaming. */
+int ftkb_set_streaming_trajectories(ftkb_ctx *, int enable);
+int ftkb_get_trajectory_complete(ftkb_ctx *, uint8_t *complete /* n */);
+/* the grow step by itself (host code, no device): feed it the punctured simplices of one step at a time */
+typedef struct ftkb_online ftkb_online;
+int ftkb_online_create(int nd, const int32_t *lb /* nd */, const int32_t *ub /* nd, inclusive */, ftkb_online **out);
+void ftkb_online_destroy(ftkb_online *);
+int ftkb_online_grow(ftkb_online *, const ftkb_point *pts, uint64_t n);
+int ftkb_online_size(const ftkb_online *, uint64_t *ntraj, uint64_t *npoints);
+int ftkb_online_get(const ftkb_online *, uint64_t *offsets /* ntraj+1 */, ftkb_point *pts /* npoints */, uint8_t *loop, uint8_t *complete);
+
 /* ---- trajectory post-processing (host code) ----------------------------------------------------
  * A curve set holds the traced trajectories as mutable curves -- the reference's feature_curve_set_t, a multimap
  * keyed by curve id (include/ftk/features/feature_curve_set.hh:21-70, :447-532) -- and applies the reference's

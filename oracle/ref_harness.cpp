@@ -16,6 +16,8 @@
 //                  [--domain lb0 ub0 lb1 ub1 [lb2 ub2]] [--symmetric 0|1] [--nthreads N]
 //                  [--no-trace] [--out file.ftkg] [--dump-input raw.f64] [--quiet]
 //                  [--binary-discrete file] [--binary-traced file]   the reference's own binary archives (DIY serialization)
+//                  [--out-stream file]   trajectories of a second tracker run with streaming trajectories
+//                                        (trace_critical_points_online per step), as indices into the punctured simplices
 //                  [--post OPS --out-curves file.ftkc]   trajectory post-processing by the reference's own curve code:
 //                  OPS as feature_curve_set_post_processor_t takes them, plus legacy[:thr[:discard[:velocity]]] = the
 //                  call sequence of json_interface::post_process() (json_interface.hh:758-800) on the same methods
@@ -39,7 +41,7 @@ struct args_t {
   int symmetric = -1;
   bool trace = true, quiet = false, have_domain = false;
   int dom[6] = {0, 0, 0, 0, 0, 0};
-  std::string gen, input, out, dump_input, post, out_curves, bin_traced, bin_discrete;
+  std::string gen, input, out, dump_input, post, out_curves, bin_traced, bin_discrete, out_stream;
   std::vector<double> p;
 };
 
@@ -118,6 +120,23 @@ static int run(const args_t &a)
   tr.set_array_domain(ftk::lattice(ast, asz));
   tr.initialize();
 
+  tracker_t trs(comm);           // streaming twin: same configuration, trajectories grown online after every step
+  const bool streaming = !a.out_stream.empty();
+  if (streaming) {
+    if (a.nthreads > 0) trs.set_number_of_threads(a.nthreads);
+    trs.set_enable_streaming_trajectories(true);
+    if (scalar) {
+      trs.set_scalar_field_source(ftk::SOURCE_GIVEN); trs.set_vector_field_source(ftk::SOURCE_DERIVED); trs.set_jacobian_field_source(ftk::SOURCE_DERIVED);
+      trs.set_jacobian_symmetric(a.symmetric < 0 ? true : a.symmetric != 0);
+    } else {
+      trs.set_scalar_field_source(ftk::SOURCE_NONE); trs.set_vector_field_source(ftk::SOURCE_GIVEN); trs.set_jacobian_field_source(ftk::SOURCE_DERIVED);
+      trs.set_jacobian_symmetric(a.symmetric < 0 ? false : a.symmetric != 0);
+    }
+    trs.set_domain(ftk::lattice(dst, dsz));
+    trs.set_array_domain(ftk::lattice(ast, asz));
+    trs.initialize();
+  }
+
   FILE *fin = NULL, *fdump = NULL;
   if (!a.input.empty()) { fin = fopen(a.input.c_str(), "rb"); if (!fin) { perror("input"); return 2; } }
   if (!a.dump_input.empty()) { fdump = fopen(a.dump_input.c_str(), "wb"); if (!fdump) { perror("dump"); return 2; } }
@@ -135,6 +154,11 @@ static int run(const args_t &a)
     if (k != 0) tr.advance_timestep();
     if (k == a.T - 1) tr.update_timestep();
     auto c3 = clk::now();
+    if (streaming) {
+      if (scalar) trs.push_scalar_field_snapshot(s); else trs.push_vector_field_snapshot(s);
+      if (k != 0) trs.advance_timestep();
+      if (k == a.T - 1) trs.update_timestep();
+    }
     t_gen += std::chrono::duration<double>(c1 - c0).count();
     t_push += std::chrono::duration<double>(c2 - c1).count();
     t_sweep += std::chrono::duration<double>(c3 - c2).count();
@@ -227,6 +251,20 @@ static int run(const args_t &a)
     fclose(fc);
   }
 
+  if (streaming) {
+    trs.finalize();
+    FILE *fs = fopen(a.out_stream.c_str(), "wb"); if (!fs) { perror("out-stream"); return 2; }
+    const auto &set = trs.get_traced_critical_points();
+    const uint64_t nt = set.size();
+    fwrite(&nt, 8, 1, fs);
+    for (const auto &kv : set) {
+      const uint64_t h[4] = {(uint64_t)kv.first, kv.second.size(), kv.second.loop ? 1u : 0u, kv.second.complete ? 1u : 0u};
+      fwrite(h, 8, 4, fs);
+      for (const auto &cp : kv.second) { const uint64_t idx = tag2idx.at(cp.tag); fwrite(&idx, 8, 1, fs); }
+    }
+    fclose(fs);
+  }
+
   // simplices enumerated: N_core * (n_ord * T + n_int * (T-1))   
   double ncore = 1; for (int i = 0; i < nd; i ++) ncore *= double(dsz[i]);
   const int n_ord = nd == 2 ? 2 : 6, n_int = nd == 2 ? 10 : 54;
@@ -283,6 +321,7 @@ int main(int argc, char **argv)
     else if (s == "--no-trace") a.trace = false;
     else if (s == "--binary-traced") a.bin_traced = next();      // tracker.write_traced_critical_points_binary (DIY archive)
     else if (s == "--binary-discrete") a.bin_discrete = next();  // tracker.write_critical_points_binary
+    else if (s == "--out-stream") a.out_stream = next();         // a second tracker with set_enable_streaming_trajectories(true)
     else if (s == "--post") a.post = next();
     else if (s == "--out-curves") a.out_curves = next();
     else if (s == "--quiet") a.quiet = true;

@@ -1,0 +1,159 @@
+"""Streaming trajectories: trace_critical_points_online, critical_point_tracker.hh:522-641.
+
+tests/golden/stream/<case>.npz hold the trajectories the UNMODIFIED reference grew with
+set_enable_streaming_trajectories(true) (made by tests/golden/make_golden_stream.py), as CSR over the sorted points
+of tests/golden/<case>.npz, in trajectory-id order with loop / complete flags.  Index work: everything is compared
+exactly, ORDER INCLUDED (ids decide who claims a shared neighbour in later steps).
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from _parity import GOLDEN_DIR, golden_snapshots, load_golden
+
+STREAM_DIR = os.path.join(GOLDEN_DIR, "stream")
+NAMES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(STREAM_DIR, "*.npz")))
+
+
+def load_stream(name):
+    z = np.load(os.path.join(STREAM_DIR, name + ".npz"))
+    off = z["traj_offsets"]
+    return [(z["traj_idx"][off[i]:off[i + 1]].astype(np.int64).tolist(), bool(z["traj_loop"][i]), bool(z["traj_complete"][i]))
+            for i in range(len(off) - 1)]
+
+
+@pytest.fixture(scope="module")
+def ftkb():
+    from ftk_b200 import _lib
+    _lib.lib()
+    return _lib
+
+
+def test_fixtures_present():
+    assert len(NAMES) >= 15
+    assert sum(len(load_stream(n)) for n in NAMES) > 700
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_oracle_matches_reference(name, oracle):
+    """the restatement (oracle/cp_online.py) reproduces the reference's streamed trajectories from its points"""
+    from oracle import cp_online
+    meta, gold, _ = load_golden(name)
+    p = gold["points"]
+    got = cp_online.trace_streaming(meta["nd"], p["corner"], p["simplex_type"], p["timestep"], meta["T"])
+    assert [(list(i), l, c) for i, l, c in got] == load_stream(name)
+
+
+def _domain(meta):
+    margin = 2 if meta["nv"] == 1 else 1          # json_interface.hh:634-656
+    return [margin] * meta["nd"], [d - 2 for d in meta["dims"]]
+
+
+def _index_of(points):
+    return {(tuple(int(v) for v in c), int(t)): i for i, (c, t) in enumerate(zip(points["corner"], points["simplex_type"]))}
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_host_grow_step_matches_reference(name, ftkb):
+    """the library's grow step (ftkb_online_*, host code) fed the reference's points one timestep at a time, in a
+    scrambled order within the step (the sweep appends hits in no particular order)"""
+    from ftk_b200.online import OnlineTracer
+    meta, gold, _ = load_golden(name)
+    p = np.zeros(len(gold["points"]), ftkb.POINT_DTYPE)
+    for f in p.dtype.names:
+        p[f] = gold["points"][f]
+    lb, ub = _domain(meta)
+    tr = OnlineTracer(lb, ub)
+    rng = np.random.default_rng(7)
+    for j in range(meta["T"] - 1):
+        batch = p[p["timestep"] == j]
+        tr.grow(batch[rng.permutation(len(batch))])
+    index = _index_of(p)
+    got = [([index[(tuple(int(v) for v in q["corner"]), int(q["simplex_type"]))] for q in pts], l, c) for pts, l, c in tr.trajectories()]
+    assert got == load_stream(name)
+
+
+def test_host_grow_step_duplicates_and_empty(ftkb):
+    """an element reported twice in one step is one map entry; empty steps complete every open trajectory"""
+    from ftk_b200.online import OnlineTracer
+    meta, gold, _ = load_golden("mx2d_11x13x20")
+    p = np.zeros(len(gold["points"]), ftkb.POINT_DTYPE)
+    for f in p.dtype.names:
+        p[f] = gold["points"][f]
+    lb, ub = _domain(meta)
+    a, b = OnlineTracer(lb, ub), OnlineTracer(lb, ub)
+    for j in range(5):
+        batch = p[p["timestep"] == j]
+        a.grow(batch)
+        b.grow(np.concatenate([batch, batch[::-1]]))
+    ta, tb = a.trajectories(), b.trajectories()
+    assert len(ta) == len(tb) == 1 and np.array_equal(ta[0][0], tb[0][0]) and not ta[0][2]
+    a.grow(p[:0])
+    assert a.trajectories()[0][2]                       # nothing to add: complete
+    a.grow(p[p["timestep"] == 5])
+    t = a.trajectories()
+    assert len(t) == 2 and np.array_equal(t[0][0], ta[0][0])   # a complete trajectory is never extended again
+
+
+def test_streaming_call_order_is_checked(ftkb):
+    import ctypes as C
+    assert ftkb.lib().ftkb_set_streaming_trajectories(None, 1) == 1          # FTKB_ERR_INVALID
+    h = C.c_void_p()
+    assert ftkb.lib().ftkb_online_create(4, None, None, C.byref(h)) != 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", NAMES)
+def test_gpu_streaming_matches_reference(name, oracle):
+    """the tracker with set_enable_streaming_trajectories(True): sweep on the device, grow step after every interval"""
+    from ftk_b200 import tracker as T
+    meta, gold, inp = load_golden(name)
+    field = "scalar" if meta["nv"] == 1 else "vector"
+    kw = {} if meta.get("symmetric") is None else {"jacobian_symmetric": bool(meta["symmetric"])}
+    tr = T.track(golden_snapshots(meta, inp, oracle), meta["dims"], field=field, streaming=True, **kw)
+    pts = tr.get_discrete_critical_points()
+    assert np.array_equal(pts["corner"], gold["points"]["corner"]) and np.array_equal(pts["simplex_type"], gold["points"]["simplex_type"])
+    complete = tr.get_trajectory_complete()
+    got = [(idx.tolist(), loop, bool(complete[i])) for i, (idx, loop) in enumerate(tr.get_trajectory_index())]
+    assert got == load_stream(name)
+    tr.close()
+
+
+@pytest.mark.gpu
+def test_gpu_streaming_equals_offline_partition_on_simple_case(oracle):
+    """moving extremum: one feature, so the streamed trajectory is the offline one minus the last ordinal sweep's point"""
+    from ftk_b200 import tracker as T
+    snaps = list(oracle.synthetic_series("moving_extremum", [21, 21], 32, None))
+    a = T.track(snaps, [21, 21], streaming=True)
+    b = T.track(snaps, [21, 21])
+    ia, ib = a.get_trajectory_index(), b.get_trajectory_index()
+    assert len(ia) == len(ib) == 1
+    assert set(ia[0][0].tolist()) <= set(ib[0][0].tolist()) and len(ib[0][0]) - len(ia[0][0]) == 1
+
+
+@pytest.mark.gpu
+def test_cli_stream_flag(tmp_path):
+    """`ftk -f cp --stream` (src/cli/ftk.cpp:47,202-203): traced text output holds the streamed trajectories, in id order"""
+    import subprocess
+    from ftk_b200 import build
+    build.build()
+    name = "woven_cli_31x37x32"
+    want = load_stream(name)
+    out = tmp_path / "traced.txt"
+    r = subprocess.run([build.CLI, "-f", "cp", "--synthetic", "woven", "--width", "31", "--height", "37", "--timesteps", "32", "--stream",
+                        "-o", str(out)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    text = open(out).read().splitlines()
+    assert text[0] == f"#trajectories={len(want)}"
+    lengths, cur = [], None
+    for line in text[1:]:
+        if line.startswith("--trajectory"):
+            if cur is not None:
+                lengths.append(cur)
+            cur = 0
+        elif line.startswith("---"):
+            cur += 1
+    lengths.append(cur)
+    assert lengths == [len(idx) for idx, _, _ in want]
