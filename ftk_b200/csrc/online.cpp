@@ -16,7 +16,6 @@
 
 #include <algorithm>
 #include <cstring>
-#include <map>
 #include <new>
 
 #include "kernels.h"
@@ -30,7 +29,29 @@ OnlineTracer::OnlineTracer(int nd, const int32_t lb[3], const int32_t ub[3]) : n
   }
   ny_ = ub_[1] - lb_[1] + 1;
   nz_ = ub_[2] - lb_[2] + 1;
-  fill_device_tables(nd + 1, &mt_);
+  DeviceMeshTables mt;
+  fill_device_tables(nd + 1, &mt);
+  for (int type = 0; type < mt.ntypes; type++) {
+    int cnt = 0;
+    Candidate self{};
+    self.type = (int8_t)type;
+    cand_[type][cnt++] = self;
+    for (int q = 0; q < mt.n_nb[type]; q++) {
+      Candidate c{};
+      c.off[0] = mt.nb_off[type][q][0];
+      c.off[1] = mt.nb_off[type][q][1];
+      c.off[2] = nd == 3 ? mt.nb_off[type][q][2] : 0;
+      c.off[3] = mt.nb_off[type][q][nd];
+      c.type = mt.nb_type[type][q];
+      cand_[type][cnt++] = c;
+    }
+    std::sort(cand_[type], cand_[type] + cnt, [](const Candidate &a, const Candidate &b) {
+      for (int j = 0; j < 4; j++) if (a.off[j] != b.off[j]) return a.off[j] < b.off[j];
+      return a.type < b.type;
+    });
+    for (int q = 0; q < cnt; q++) cand_[type][q].cell_delta = ((int64_t)cand_[type][q].off[0] * ny_ + cand_[type][q].off[1]) * nz_ + cand_[type][q].off[2];
+    ncand_[type] = cnt;
+  }
 }
 
 bool OnlineTracer::key_at(int x, int y, int z, int t, int type, uint64_t &key) const {
@@ -46,17 +67,17 @@ bool OnlineTracer::key_at(int x, int y, int z, int t, int type, uint64_t &key) c
 
 // neighbors(f) = every side of every cell f is a side of (critical_point_tracker_2d_regular.hh:292-300), f included
 int OnlineTracer::neighbor_keys(const ftkb_point &p, uint64_t out[9]) const {
-  int cnt = 0;
   const int type = p.simplex_type;
-  uint64_t key;
-  if (key_of(p, key)) out[cnt++] = key;
-  for (int q = 0; q < mt_.n_nb[type]; q++) {
-    const int x = p.corner[0] + mt_.nb_off[type][q][0], y = p.corner[1] + mt_.nb_off[type][q][1];
-    const int z = nd_ == 3 ? p.corner[2] + mt_.nb_off[type][q][2] : 0;
-    const int t = p.corner[3] + mt_.nb_off[type][q][nd_];
-    if (key_at(x, y, z, t, mt_.nb_type[type][q], key)) out[cnt++] = key;
+  if (type < 0 || type >= 60) return 0;
+  const int x0 = p.corner[0], y0 = p.corner[1], z0 = nd_ == 3 ? p.corner[2] : 0, t0 = p.corner[3];
+  const int64_t cell = ((int64_t)(x0 - lb_[0]) * ny_ + (y0 - lb_[1])) * nz_ + (z0 - lb_[2]);
+  int cnt = 0;
+  for (int q = 0; q < ncand_[type]; q++) {
+    const Candidate &c = cand_[type][q];
+    const int x = x0 + c.off[0], y = y0 + c.off[1], z = z0 + c.off[2], t = t0 + c.off[3];
+    if (x < lb_[0] || x > ub_[0] || y < lb_[1] || y > ub_[1] || z < lb_[2] || z > ub_[2] || t < 0 || t >= (1 << KEY_TIME_BITS)) continue;
+    out[cnt++] = ((((uint64_t)(cell + c.cell_delta) << KEY_TIME_BITS) | (uint64_t)t) << KEY_TYPE_BITS) | (uint64_t)c.type;
   }
-  std::sort(out, out + cnt);
   return cnt;
 }
 
@@ -93,58 +114,93 @@ struct RefUnionFind {
 };
 
 // algorithms/cca.hh:91-116: `nodes` ascending; nb(node) = its neighbours among `nodes` (ascending, itself included).
-// Components come back ordered by root, members ascending (union_find.hh:82-92).
+// Components come back ordered by root, members ascending (union_find.hh:82-92), as CSR: component g holds
+// members[start[g] .. start[g+1]).  `local` is scratch of the universe's size, all -1 on entry and on exit.
+struct Components {
+  std::vector<uint32_t> start, members;
+  size_t size() const { return start.size() - 1; }
+};
+
 template <class NB>
-std::vector<std::vector<uint32_t>> components_of(const std::vector<uint32_t> &nodes, uint32_t universe, NB nb) {
-  std::vector<int32_t> local(universe, -1);
-  for (size_t a = 0; a < nodes.size(); a++) local[nodes[a]] = (int32_t)a;
-  RefUnionFind uf(nodes.size());
+Components components_of(const std::vector<uint32_t> &nodes, std::vector<int32_t> &local, NB nb) {
+  const size_t m = nodes.size();
+  for (size_t a = 0; a < m; a++) local[nodes[a]] = (int32_t)a;
+  RefUnionFind uf(m);
   uint32_t tmp[9];
-  for (size_t a = 0; a < nodes.size(); a++) {
+  for (size_t a = 0; a < m; a++) {
     const int cnt = nb(nodes[a], tmp);
     for (int q = 0; q < cnt; q++)
       if (local[tmp[q]] >= 0) uf.unite((uint32_t)a, (uint32_t)local[tmp[q]]);
   }
-  std::map<uint32_t, std::vector<uint32_t>> root2set;
-  for (size_t a = 0; a < nodes.size(); a++) root2set[uf.find((uint32_t)a)].push_back(nodes[a]);
-  std::vector<std::vector<uint32_t>> out;
-  out.reserve(root2set.size());
-  for (auto &kv : root2set) out.push_back(std::move(kv.second));
+  // get_sets(): find() of every element in ascending order (it compresses paths as it goes), sets ordered by root
+  std::vector<uint32_t> root(m), rank(m, 0);
+  for (size_t a = 0; a < m; a++) { root[a] = uf.find((uint32_t)a); rank[root[a]] = 1; }
+  Components out;
+  uint32_t ngroups = 0;
+  for (size_t a = 0; a < m; a++) { const uint32_t is_root = rank[a]; rank[a] = ngroups; ngroups += is_root; }
+  out.start.assign(ngroups + 1, 0);
+  for (size_t a = 0; a < m; a++) out.start[rank[root[a]] + 1]++;
+  for (uint32_t g = 0; g < ngroups; g++) out.start[g + 1] += out.start[g];
+  out.members.resize(m);
+  std::vector<uint32_t> fill(out.start.begin(), out.start.end() - 1);
+  for (size_t a = 0; a < m; a++) out.members[fill[rank[root[a]]]++] = nodes[a];
+  for (size_t a = 0; a < m; a++) local[nodes[a]] = -1;
   return out;
 }
 
 }  // namespace
 
 void OnlineTracer::grow(const ftkb_point *pts_in, uint64_t n_in) {
-  // discrete_critical_points: std::map keyed by element (a later insert of the same element overwrites)
-  std::vector<std::pair<uint64_t, uint32_t>> order;
-  order.reserve(n_in);
-  for (uint64_t i = 0; i < n_in; i++) {
-    uint64_t key;
-    if (key_of(pts_in[i], key)) order.emplace_back(key, (uint32_t)i);
-  }
-  std::stable_sort(order.begin(), order.end(), [](const auto &a, const auto &b) { return a.first < b.first; });
+  // discrete_critical_points: std::map keyed by element (a later insert of the same element overwrites).  Most of a
+  // step's elements are claimed by existing trajectories through key lookups alone, so the batch is hashed, not
+  // sorted; only what is left for step 2 is put into element order.
+  size_t cap = 16;
+  while (cap < 2 * n_in + 2) cap <<= 1;
+  int shift = 64;
+  for (size_t c = cap; c > 1; c >>= 1) shift--;
+  // open addressing, hashed on the element's (corner, t) without the type: the neighbours of an element sit in a
+  // handful of adjacent cells, so their probes share cache lines; probes of one neighbour list are prefetched together
+  struct Entry { uint64_t key; uint32_t val, pad; };
+  std::vector<Entry> table(cap, Entry{~0ull, 0, 0});   // no element key is all ones (the type field is below 60)
   std::vector<uint64_t> keys;
   std::vector<ftkb_point> pts;
-  for (size_t a = 0; a < order.size(); a++) {
-    if (!keys.empty() && keys.back() == order[a].first) { pts.back() = pts_in[order[a].second]; continue; }
-    keys.push_back(order[a].first);
-    pts.push_back(pts_in[order[a].second]);
+  keys.reserve(n_in);
+  pts.reserve(n_in);
+  auto home_of = [&](uint64_t key) { return (size_t)(((key >> KEY_TYPE_BITS) * 0x9E3779B97F4A7C15ull) >> shift); };
+  auto slot_from = [&](size_t h, uint64_t key) {
+    while (table[h].key != ~0ull && table[h].key != key) h = (h + 1) & (cap - 1);
+    return h;
+  };
+  for (uint64_t i = 0; i < n_in; i++) {
+    uint64_t key;
+    if (!key_of(pts_in[i], key)) continue;
+    const size_t h = slot_from(home_of(key), key);
+    if (table[h].key == key) { pts[table[h].val] = pts_in[i]; continue; }
+    table[h].key = key;
+    table[h].val = (uint32_t)keys.size();
+    keys.push_back(key);
+    pts.push_back(pts_in[i]);
   }
   const uint32_t n = (uint32_t)keys.size();
   std::vector<uint8_t> alive(n, 1);
-  auto lookup = [&](uint64_t key) -> int64_t {
-    const auto it = std::lower_bound(keys.begin(), keys.end(), key);
-    return it != keys.end() && *it == key ? (int64_t)(it - keys.begin()) : -1;
+  // the punctured neighbours of an element, ascending: indices of those present in this step's batch
+  auto present_neighbors = [&](const ftkb_point &cur, int64_t out[9]) {
+    uint64_t nk[9];
+    size_t home[9];
+    const int cnt = neighbor_keys(cur, nk);
+    for (int q = 0; q < cnt; q++) { home[q] = home_of(nk[q]); __builtin_prefetch(&table[home[q]]); }
+    for (int q = 0; q < cnt; q++) {
+      const size_t h = slot_from(home[q], nk[q]);
+      out[q] = table[h].key == nk[q] ? (int64_t)table[h].val : -1;
+    }
+    return cnt;
   };
   // smallest unclaimed punctured neighbour of an element (critical_point_tracker.hh:555-572)
   auto claim_next = [&](const ftkb_point &cur) -> int64_t {
-    uint64_t nk[9];
-    const int cnt = neighbor_keys(cur, nk);
-    for (int q = 0; q < cnt; q++) {
-      const int64_t j = lookup(nk[q]);
-      if (j >= 0 && alive[j]) { alive[j] = 0; return j; }
-    }
+    int64_t nbr[9];
+    const int cnt = present_neighbors(cur, nbr);
+    for (int q = 0; q < cnt; q++)
+      if (nbr[q] >= 0 && alive[nbr[q]]) { alive[nbr[q]] = 0; return nbr[q]; }
     return -1;
   };
 
@@ -171,73 +227,89 @@ void OnlineTracer::grow(const ftkb_point *pts_in, uint64_t n_in) {
 
   // 2. new trajectories from what is left (critical_point_tracker.hh:611-640)
   std::vector<uint32_t> rest;
-  for (uint32_t i = 0; i < n; i++) if (alive[i]) rest.push_back(i);
-  if (rest.empty()) return;
-  std::vector<uint32_t> nb(9 * (size_t)n, 0);
+  {
+    std::vector<std::pair<uint64_t, uint32_t>> left;
+    for (uint32_t i = 0; i < n; i++) if (alive[i]) left.emplace_back(keys[i], i);
+    if (left.empty()) return;
+    std::sort(left.begin(), left.end());                 // std::set<element> order
+    rest.reserve(left.size());
+    for (const auto &kv : left) rest.push_back(kv.second);
+  }
+  std::vector<uint32_t> nb(9 * (size_t)n);
   std::vector<uint8_t> nnb(n, 0);
   for (uint32_t i : rest) {
-    uint64_t nk[9];
-    const int cnt = neighbor_keys(pts[i], nk);
-    for (int q = 0; q < cnt; q++) {
-      const int64_t j = lookup(nk[q]);
-      if (j >= 0 && alive[j]) nb[9 * (size_t)i + nnb[i]++] = (uint32_t)j;
-    }
+    int64_t nbr[9];
+    const int cnt = present_neighbors(pts[i], nbr);
+    for (int q = 0; q < cnt; q++)
+      if (nbr[q] >= 0 && alive[nbr[q]]) nb[9 * (size_t)i + nnb[i]++] = (uint32_t)nbr[q];
   }
   auto nb_all = [&](uint32_t i, uint32_t *out) { std::memcpy(out, &nb[9 * (size_t)i], 4 * nnb[i]); return (int)nnb[i]; };
-  const auto components = components_of(rest, n, nb_all);
+  std::vector<int32_t> scratch(n, -1);
+  const Components components = components_of(rest, scratch, nb_all);
 
+  // cc2curves.hh:19-31: a node with more than two punctured neighbours other than itself is special.  The reference
+  // splits every component into linear graphs on its own; unions never cross components and every component's
+  // ordinary nodes are visited in the same relative order, so one union-find over all ordinary nodes (cc2curves.hh:33-43)
+  // gives the same sets, and ordering them by (component, root) gives the reference's order of new trajectories.
   std::vector<uint8_t> special(n, 0), visited(n, 0);
+  std::vector<uint32_t> comp_of(n, 0), ordinary;
+  ordinary.reserve(rest.size());
+  for (uint32_t g = 0; g < components.size(); g++)
+    for (uint32_t k = components.start[g]; k < components.start[g + 1]; k++) comp_of[components.members[k]] = g;
+  for (uint32_t i : rest) {
+    int d = 0;
+    for (int q = 0; q < nnb[i]; q++) d += nb[9 * (size_t)i + q] != i;
+    special[i] = d > 2;
+    if (!special[i]) ordinary.push_back(i);
+  }
+  auto nb_ord = [&](uint32_t i, uint32_t *out) {
+    int cnt = 0;
+    for (int q = 0; q < nnb[i]; q++) { const uint32_t j = nb[9 * (size_t)i + q]; if (!special[j]) out[cnt++] = j; }
+    return cnt;
+  };
+  const Components linear = components_of(ordinary, scratch, nb_ord);
   std::vector<int32_t> member(n, -1);   // index of the linear graph a node belongs to
-  for (const auto &component : components) {
-    // cc2curves.hh:19-31: more than two punctured neighbours other than itself
-    std::vector<uint32_t> ordinary;
-    for (uint32_t i : component) {
-      int d = 0;
-      for (int q = 0; q < nnb[i]; q++) d += nb[9 * (size_t)i + q] != i;
-      special[i] = d > 2;
-      if (!special[i]) ordinary.push_back(i);
-    }
-    // cc2curves.hh:33-43
-    auto nb_ord = [&](uint32_t i, uint32_t *out) {
-      int cnt = 0;
-      for (int q = 0; q < nnb[i]; q++) { const uint32_t j = nb[9 * (size_t)i + q]; if (!special[j]) out[cnt++] = j; }
-      return cnt;
-    };
-    const auto linear = components_of(ordinary, n, nb_ord);
-    for (size_t g = 0; g < linear.size(); g++) for (uint32_t i : linear[g]) member[i] = (int32_t)g;
-    // cc2curves.hh:46-108
-    for (size_t g = 0; g < linear.size(); g++) {
-      const uint32_t seed = linear[g].front();
-      std::deque<uint32_t> trace;
-      visited[seed] = 1;
-      trace.push_back(seed);
-      uint32_t sn[9]; int nsn = 0;
-      for (int q = 0; q < nnb[seed]; q++) { const uint32_t j = nb[9 * (size_t)seed + q]; if (j != seed && !special[j]) sn[nsn++] = j; }
-      for (int dir = 0; dir < 2 && nsn > 0; dir++) {
-        uint32_t cur = dir == 0 ? sn[0] : sn[nsn - 1];
-        while (true) {
-          if (!visited[cur]) {
-            if (dir == 0) trace.push_back(cur); else trace.push_front(cur);
-            visited[cur] = 1;
-          }
-          bool found = false;
-          for (int q = 0; q < nnb[cur]; q++) {
-            const uint32_t j = nb[9 * (size_t)cur + q];
-            if (j != cur && !special[j] && member[j] == (int32_t)g && !visited[j]) { found = true; cur = j; break; }
-          }
-          if (!found) break;
+  std::vector<uint32_t> graph_order(linear.size());
+  for (uint32_t g = 0; g < linear.size(); g++) {
+    graph_order[g] = g;
+    for (uint32_t k = linear.start[g]; k < linear.start[g + 1]; k++) member[linear.members[k]] = (int32_t)g;
+  }
+  std::stable_sort(graph_order.begin(), graph_order.end(), [&](uint32_t a, uint32_t b) {
+    return comp_of[linear.members[linear.start[a]]] < comp_of[linear.members[linear.start[b]]];
+  });
+  // cc2curves.hh:46-108
+  std::vector<uint32_t> fwd, bwd;
+  for (const uint32_t g : graph_order) {
+    const uint32_t seed = linear.members[linear.start[g]];
+    fwd.clear();
+    bwd.clear();
+    visited[seed] = 1;
+    uint32_t sn[9]; int nsn = 0;
+    for (int q = 0; q < nnb[seed]; q++) { const uint32_t j = nb[9 * (size_t)seed + q]; if (j != seed && !special[j]) sn[nsn++] = j; }
+    for (int dir = 0; dir < 2 && nsn > 0; dir++) {
+      uint32_t cur = dir == 0 ? sn[0] : sn[nsn - 1];
+      while (true) {
+        if (!visited[cur]) {
+          (dir == 0 ? fwd : bwd).push_back(cur);
+          visited[cur] = 1;
         }
-        if (nsn == 1) break;
+        bool found = false;
+        for (int q = 0; q < nnb[cur]; q++) {
+          const uint32_t j = nb[9 * (size_t)cur + q];
+          if (j != cur && !special[j] && member[j] == (int32_t)g && !visited[j]) { found = true; cur = j; break; }
+        }
+        if (!found) break;
       }
-      OnlineCurve c;
-      if (trace.size() > 1) {   // is_loop, cc2curves.hh:113-122
-        const uint32_t front = trace.front(), back = trace.back();
-        for (int q = 0; q < nnb[front]; q++) c.loop = c.loop || nb[9 * (size_t)front + q] == back;
-      }
-      for (uint32_t i : trace) c.pts.push_back(pts[i]);
-      curves_.push_back(std::move(c));
+      if (nsn == 1) break;
     }
-    for (uint32_t i : component) member[i] = -1;
+    OnlineCurve c;
+    const uint32_t front = bwd.empty() ? seed : bwd.back(), back = fwd.empty() ? seed : fwd.back();
+    if (fwd.size() + bwd.size() > 0)   // is_loop, cc2curves.hh:113-122
+      for (int q = 0; q < nnb[front]; q++) c.loop = c.loop || nb[9 * (size_t)front + q] == back;
+    for (size_t k = bwd.size(); k > 0; k--) c.pts.push_back(pts[bwd[k - 1]]);
+    c.pts.push_back(pts[seed]);
+    for (uint32_t i : fwd) c.pts.push_back(pts[i]);
+    curves_.push_back(std::move(c));
   }
 }
 

@@ -32,7 +32,11 @@ class OnlineTracer {
   int nd_;
   int32_t lb_[3], ub_[3];
   int64_t ny_, nz_;
-  DeviceMeshTables mt_;
+  // neighbour candidates of every simplex type (the element itself included) in ascending element order: the order
+  // of (corner + offset, type) does not depend on the corner
+  struct Candidate { int8_t off[4]; int8_t type; int64_t cell_delta; };
+  Candidate cand_[60][9];
+  int ncand_[60];
   std::vector<OnlineCurve> curves_;
 };
 

@@ -113,7 +113,17 @@ def _peer_sweep_slab(make, layer, push, t0, t1, T, field, resolution_init, excha
     return tr, log
 
 
-def track_time_sharded(layer, dims, T, field="scalar", group=None, tracker_factory=None, exchange_halo=True, trace=True, halo="copy", **kw):
+def _streamed(tr, dims, field, T, kw):
+    """streaming=True on time slabs: rank 0 replays the reference's grow steps over the gathered punctured simplices"""
+    from .online import replay_streaming
+    margin = 2 if field == "scalar" else 1           # make_tracker's default domain (json_interface.hh:634-656)
+    lb = kw.get("lb") or [margin] * len(dims)
+    ub = kw.get("ub") or [d - 2 for d in dims]
+    return replay_streaming(tr.get_discrete_critical_points(), lb, ub, T)
+
+
+def track_time_sharded(layer, dims, T, field="scalar", group=None, tracker_factory=None, exchange_halo=True, trace=True, halo="copy",
+                       streaming=False, **kw):
     """Run the tracker over T timesteps sharded into time slabs over the ranks of `group`.
 
     layer(k)         -> snapshot k in memory order (numpy array or CUDA tensor); called on the rank that owns
@@ -121,6 +131,9 @@ def track_time_sharded(layer, dims, T, field="scalar", group=None, tracker_facto
     tracker_factory  (dims, field, start_timestep, resolution_init, **kw) -> tracker; default: the CUDA tracker
     halo             "copy": the halo layer is sent (send/recv); "peer": it is read in place through NVLink peer memory
                      (CUDA tracker only, every slab at least two timesteps, all ranks on one node)
+    streaming        True: instead of the offline trace, rank 0 replays the reference's streaming grow steps
+                     (trace_critical_points_online, critical_point_tracker.hh:522-641) over the gathered punctured simplices,
+                     timestep by timestep; the trajectories [(points, loop, complete)] are returned in info["streamed"]
     Returns the rank-0 tracker holding every punctured simplex (finalized when trace=True) on rank 0 and the
     local slab's tracker elsewhere, plus a dict of bookkeeping (slab, halo bytes, repeated slabs)."""
     import torch
@@ -180,7 +193,9 @@ def track_time_sharded(layer, dims, T, field="scalar", group=None, tracker_facto
         for t in keep:
             if hasattr(t, "close"):
                 t.close()
-        if rank == 0 and trace:
+        if rank == 0 and streaming:
+            info["streamed"] = _streamed(tr, dims, field, T, kw)
+        elif rank == 0 and trace:
             tr.finalize()
         return tr, info
 
@@ -237,6 +252,8 @@ def track_time_sharded(layer, dims, T, field="scalar", group=None, tracker_facto
             for b in gathered[1:]:
                 if len(b):
                     tr.import_points(np.frombuffer(b, dtype=L.POINT_DTYPE))
-    if rank == 0 and trace:
+    if rank == 0 and streaming:
+        info["streamed"] = _streamed(tr, dims, field, T, kw)
+    elif rank == 0 and trace:
         tr.finalize()
     return tr, info

@@ -50,3 +50,21 @@ class OnlineTracer:
         loop, complete = np.zeros(max(nt.value, 1), np.uint8), np.zeros(max(nt.value, 1), np.uint8)
         L.lib().ftkb_online_get(self._h, off.ctypes.data, pts.ctypes.data, loop.ctypes.data, complete.ctypes.data)
         return [(pts[int(off[i]):int(off[i + 1])], bool(loop[i]), bool(complete[i])) for i in range(nt.value)]
+
+
+def replay_streaming(points, lb, ub, T):
+    """Streaming trajectories of a finished run: the grow steps the reference runs after the sweeps of timesteps
+    0 .. T-2 (critical_point_tracker_2d_regular.hh:322-330; the last ordinal sweep, timestep T-1, is followed by none),
+    replayed over `points` (L.POINT_DTYPE, any order).  This is how the time-slab driver (distributed.py) serves
+    streaming=True: rank 0 holds every slab's punctured simplices after the gather, and the grow steps only depend on
+    which timestep's sweep found a point.  -> [(points in trace order, loop, complete)] in trajectory-id order."""
+    points = np.ascontiguousarray(points, dtype=L.POINT_DTYPE)
+    tr = OnlineTracer(lb, ub)
+    order = np.argsort(points["timestep"], kind="stable")
+    ts = points["timestep"][order]
+    for j in range(int(T) - 1):
+        a, b = np.searchsorted(ts, j, "left"), np.searchsorted(ts, j, "right")
+        tr.grow(points[order[a:b]])
+    out = tr.trajectories()
+    tr.close()
+    return out

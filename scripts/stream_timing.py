@@ -7,8 +7,11 @@ loop plus finalize (the grow step is host work between sweeps, so device events 
 JSON line per mode.  Not a bench.py number: bench.py's metric stays the offline path.
 """
 import json
+import os
 import sys
 import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 from ftk_b200 import _lib as L
 from ftk_b200 import tracker as T

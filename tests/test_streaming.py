@@ -157,3 +157,37 @@ def test_cli_stream_flag(tmp_path):
             cur += 1
     lengths.append(cur)
     assert lengths == [len(idx) for idx, _, _ in want]
+
+
+@pytest.mark.parametrize("nd,density,seed", [(2, 0.08, 1), (2, 0.3, 2), (2, 0.7, 3), (3, 0.02, 4), (3, 0.1, 5), (3, 0.35, 6)])
+def test_host_grow_step_matches_oracle_on_random_sets(nd, density, seed, ftkb, oracle):
+    """random punctured sets, sparse to dense: branching (special) nodes, components of special nodes only, components
+    large enough that union_find's doubled sizes wrap around 2^64 -- the library's grow step against the restatement"""
+    from oracle import cp_online
+    from ftk_b200.online import OnlineTracer
+    rng = np.random.default_rng(seed)
+    ntypes = 12 if nd == 2 else 60
+    side, T = (7, 5) if nd == 2 else (4, 4)
+    lb, ub = [0] * nd, [side + 1] * nd
+    elems = []
+    for t in range(T):
+        for idx in np.ndindex(*([side] * nd)):
+            for ty in range(ntypes):
+                if rng.random() < density:
+                    c = [int(v) + 1 for v in idx]                      # away from the border: every vertex in the domain
+                    elems.append((c[0], c[1], c[2] if nd == 3 else 0, t, ty))
+    assert len(elems) > 50
+    p = np.zeros(len(elems), ftkb.POINT_DTYPE)
+    p["corner"] = [e[:4] for e in elems]
+    p["simplex_type"] = [e[4] for e in elems]
+    p["timestep"] = p["corner"][:, 3]
+    a, b = cp_online.OnlineTracer(nd), OnlineTracer(lb, ub)
+    for t in range(T):
+        sel = p[p["timestep"] == t]
+        a.grow([tuple(int(v) for v in q["corner"]) + (int(q["simplex_type"]),) for q in sel])
+        b.grow(sel[rng.permutation(len(sel))])
+    want = [(t["elements"], t["loop"], t["complete"]) for t in a.trajectories]
+    got = [([tuple(int(v) for v in q["corner"]) + (int(q["simplex_type"]),) for q in pts], l, c) for pts, l, c in b.trajectories()]
+    assert got == want
+    if density >= 0.3:
+        assert sum(len(e) for e, _, _ in want) < len(elems)               # branching nodes were dropped, as in the reference
