@@ -191,3 +191,45 @@ def test_host_grow_step_matches_oracle_on_random_sets(nd, density, seed, ftkb, o
     assert got == want
     if density >= 0.3:
         assert sum(len(e) for e, _, _ in want) < len(elems)               # branching nodes were dropped, as in the reference
+
+
+# ---- time slabs (world_size 2, gloo): streaming=True replays the grow steps on rank 0 ----------------------------------
+def _slab_worker(rank, world, port, case, out_path):
+    import pickle
+    import torch.distributed as dist
+    import test_distributed as TD
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        from ftk_b200 import distributed as D
+        dims, T, field, snaps = TD.make_series(case)
+        tr, info = D.track_time_sharded(lambda k: snaps[k], dims, T, field=field, streaming=True,
+                                        tracker_factory=lambda d, f, s, r, **kw: TD.OracleSlabTracker(d, f, s, r, **kw))
+        if rank == 0:
+            pts = tr.get_discrete_critical_points()
+            index = _index_of(pts)
+            got = [([index[(tuple(int(v) for v in q["corner"]), int(q["simplex_type"]))] for q in p], l, c) for p, l, c in info["streamed"]]
+            with open(out_path, "wb") as f:
+                pickle.dump({"points": pts, "streamed": got}, f)
+        else:
+            assert "streamed" not in info
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("case", ["woven", "vector", "3d"])
+def test_two_slabs_streaming_equals_sequential_streaming(case, tmp_path, oracle):
+    """two time slabs over gloo (the oracle stands in for the sweep): rank 0's replay of the grow steps over the gathered
+    punctured simplices == the restatement's streamed trajectories of the sequential run"""
+    import pickle
+    import torch.multiprocessing as mp
+    import test_distributed as TD
+    from oracle import cp_online
+    out = str(tmp_path / "res")
+    mp.spawn(_slab_worker, args=(2, TD._free_port(), case, out), nprocs=2, join=True)
+    res = pickle.load(open(out, "rb"))
+    dims, T, field, snaps = TD.make_series(case)
+    seq = oracle.track(snaps, dims, field=field, trace=False).points()
+    assert np.array_equal(res["points"]["corner"], seq["corner"]) and np.array_equal(res["points"]["simplex_type"], seq["simplex_type"])
+    want = cp_online.trace_streaming(len(dims), seq["corner"], seq["simplex_type"], seq["timestep"], T)
+    assert len(want) > 0 and res["streamed"] == [(list(i), l, c) for i, l, c in want]
