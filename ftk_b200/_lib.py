@@ -15,6 +15,7 @@ ABI_VERSION = 1
 OK, ERR_INVALID, ERR_NO_DEVICE, ERR_CUDA, ERR_NOMEM, ERR_OVERFLOW = range(6)
 SOURCE_NONE, SOURCE_GIVEN, SOURCE_DERIVED = 0, 1, 2
 MEM_HOST, MEM_DEVICE, MEM_DEVICE_BORROW = 0, 1, 2
+COORDS_SIMPLE, COORDS_BOUNDS, COORDS_RECTILINEAR, COORDS_EXPLICIT = range(4)
 SYN_MOVING_EXTREMUM, SYN_WOVEN, SYN_DOUBLE_GYRE, SYN_ABC, SYN_MERGER, SYN_TORNADO = range(6)
 
 
@@ -74,7 +75,7 @@ EXPORTS = [
     "ftkb_curveset_get", "ftkb_curveset_last_error", "ftkb_curveset_slice",
     "ftkb_ipc_export", "ftkb_ipc_import", "ftkb_ipc_close", "ftkb_export_layer_cells", "ftkb_push_snapshot_remote",
     "ftkb_set_streaming_trajectories", "ftkb_get_trajectory_complete", "ftkb_online_create", "ftkb_online_destroy", "ftkb_online_grow",
-    "ftkb_online_size", "ftkb_online_get",
+    "ftkb_online_size", "ftkb_online_get", "ftkb_set_coords",
 ]
 
 _lib = None
@@ -137,6 +138,7 @@ def lib():
     L.ftkb_push_snapshot_remote.argtypes = [vp, vp, vp, vp, C.c_double]
     L.ftkb_curveset_last_error.argtypes = [vp]
     L.ftkb_set_streaming_trajectories.argtypes = [vp, C.c_int]
+    L.ftkb_set_coords.argtypes = [vp, C.c_int, vp, C.c_uint64]
     L.ftkb_get_trajectory_complete.argtypes = [vp, vp]
     L.ftkb_online_create.argtypes = [C.c_int, vp, vp, C.POINTER(vp)]
     L.ftkb_online_destroy.argtypes = [vp]

@@ -91,6 +91,11 @@ struct ftkb_ctx {
   std::vector<uint64_t> traj_off, traj_idx;
   std::vector<uint8_t> traj_loop, traj_complete;
 
+  // physical coordinates (regular_tracker.hh:38-40)
+  int coords_mode = 0, coords_ncomp = 0;
+  double coords_bounds[6] = {0, 0, 0, 0, 0, 0};
+  double *d_coords = nullptr;
+
   // streaming trajectories (critical_point_tracker.hh:38,522-641): grown on the host after every interval sweep
   bool streaming = false;
   std::unique_ptr<ftkb::OnlineTracer> online;
@@ -159,6 +164,7 @@ extern "C" void ftkb_destroy(ftkb_ctx *c) {
   if (c->h_scalars) cudaFreeHost(c->h_scalars);
   cudaFree(c->d_wl);
   cudaFree(c->d_pts);
+  cudaFree(c->d_coords);
   cudaFree(c->d_pts_sorted);
   cudaFree(c->d_keys_sorted);
   for (auto &e : c->ev) if (e) cudaEventDestroy(e);
@@ -414,7 +420,35 @@ static int nbits_of(double resolution) {
   return std::max(minbits, std::min(nbits, maxbits));
 }
 
+// set_coords_bounds / set_coords_rectilinear / set_coords_explicit (regular_tracker.hh:38-40): the coordinates the
+// per-simplex test interpolates (simplex_coordinates, critical_point_tracker_2d_regular.hh:494-526, ..._3d_regular.hh:343-379)
+extern "C" int ftkb_set_coords(ftkb_ctx *c, int mode, const double *data, uint64_t n) {
+  if (!c || mode < FTKB_COORDS_SIMPLE || mode > FTKB_COORDS_EXPLICIT || (mode != FTKB_COORDS_SIMPLE && !data)) return FTKB_ERR_INVALID;
+  CK(cudaSetDevice(c->cfg.device));
+  const uint64_t W = c->cfg.dims[0], H = c->cfg.dims[1], D = c->n == 3 ? c->cfg.dims[2] : 0;
+  if (mode == FTKB_COORDS_BOUNDS && n != 2u * c->n) return fail(c, FTKB_ERR_INVALID, "set_coords: bounds take 2 * nd values");
+  if (mode == FTKB_COORDS_RECTILINEAR && n != W + H + D) return fail(c, FTKB_ERR_INVALID, "set_coords: rectilinear coordinates take W + H [+ D] values");
+  if (mode == FTKB_COORDS_EXPLICIT && (n % (W * H) != 0 || n / (W * H) < (c->n == 3 ? 3u : 2u)))
+    return fail(c, FTKB_ERR_INVALID, "set_coords: explicit coordinates are (ncomp, W, H) with ncomp >= nd");
+  CK(cudaStreamSynchronize(c->stream));
+  cudaFree(c->d_coords);
+  c->d_coords = nullptr;
+  c->coords_mode = mode;
+  c->coords_ncomp = mode == FTKB_COORDS_EXPLICIT ? (int)(n / (W * H)) : 0;
+  if (mode == FTKB_COORDS_BOUNDS) for (uint64_t k = 0; k < n; k++) c->coords_bounds[k] = data[k];
+  if (mode == FTKB_COORDS_RECTILINEAR || mode == FTKB_COORDS_EXPLICIT) {
+    CK(cudaMalloc(&c->d_coords, 8 * n));
+    CK(cudaMemcpy(c->d_coords, data, 8 * n, cudaMemcpyHostToDevice));
+    c->stats.h2d_bytes += 8 * n;
+  }
+  return FTKB_OK;
+}
+
 static void fill_sweep_geometry(const ftkb_ctx *c, SweepParams &p) {
+  p.coords_mode = c->coords_mode;
+  p.coords_ncomp = c->coords_ncomp;
+  for (int k = 0; k < 6; k++) p.coords_bounds[k] = c->coords_bounds[k];
+  p.coords = c->d_coords;
   p.nd = c->n;
   p.W = c->cfg.dims[0]; p.H = c->cfg.dims[1]; p.D = c->n == 3 ? c->cfg.dims[2] : 1;
   for (int j = 0; j < 3; j++) {

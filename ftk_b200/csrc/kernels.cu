@@ -2743,6 +2743,34 @@ __device__ void jacobian3d_at(const SweepParams &p, const LayerPtrs &L, int i, i
   }
 }
 
+// physical coordinates of one vertex v = (x, y[, z], t) -> X = (x, y, z, t)
+// (ref: critical_point_tracker_2d_regular.hh:494-526, critical_point_tracker_3d_regular.hh:343-379; the array domain starts at 0).
+// The 3D explicit mode is the reference's as it stands: looked up by (x, y) only, and the time slot receives z.
+template <int ND>
+__device__ __forceinline__ void simplex_coordinates(const SweepParams &p, const int *v, double X[4]) {
+  const int dims[3] = {p.W, p.H, p.D};
+  if (p.coords_mode == 1) {
+#pragma unroll
+    for (int j = 0; j < ND; j++)
+      X[j] = ((double)v[j] / (double)(dims[j] - 1)) * (p.coords_bounds[2 * j + 1] - p.coords_bounds[2 * j]) + p.coords_bounds[2 * j];
+    if (ND == 2) X[2] = 0.0;
+    X[3] = (double)v[ND];
+  } else if (p.coords_mode == 2) {
+    int off = 0;
+#pragma unroll
+    for (int j = 0; j < ND; j++) { X[j] = __ldg(p.coords + off + v[j]); off += dims[j]; }
+    if (ND == 2) X[2] = 0.0;
+    X[3] = (double)v[ND];
+  } else {
+    const size_t nc = (size_t)p.coords_ncomp, k = (size_t)v[0] + (size_t)p.W * (size_t)v[1];
+    X[0] = __ldg(p.coords + nc * k);
+    X[1] = __ldg(p.coords + 1 + nc * k);
+    if (ND == 2) X[2] = nc > 2 ? __ldg(p.coords + 2 + nc * k) : 0.0;
+    else X[2] = __ldg(p.coords + 2 + nc * k);
+    X[3] = (double)v[2];
+  }
+}
+
 // SoS vertex rank: position in the mesh lattice (domain x time), uint64 truncated to int
 // (ref: regular_tracker.hh:188-194, lattice.hh:196-207)
 template <int ND>
@@ -2835,20 +2863,32 @@ __device__ bool check_simplex(const SweepParams &p, const DeviceMeshTables &mt, 
     clamp_barycentric<4>(mu);
   }
 
-  // position / time: lerp of the integer vertex coordinates (REGULAR_COORDS_SIMPLE), ref linear_interpolation.hh:81-99
+  // position / time: lerp of the vertex coordinates, ref linear_interpolation.hh:81-99
   double xo[4];
+  if (p.coords_mode == 0) {     // REGULAR_COORDS_SIMPLE: the integer vertex coordinates
 #pragma unroll
-  for (int q = 0; q < 4; q++) {
-    double acc;
-    if constexpr (ND == 2) {
-      const double c0 = q < 2 ? (double)vt[0][q] : (q == 2 ? 0.0 : (double)vt[0][2]);
-      const double c1 = q < 2 ? (double)vt[1][q] : (q == 2 ? 0.0 : (double)vt[1][2]);
-      const double c2 = q < 2 ? (double)vt[2][q] : (q == 2 ? 0.0 : (double)vt[2][2]);
-      acc = c0 * mu[0] + c1 * mu[1] + c2 * mu[2];
-    } else {
-      acc = (double)vt[0][q] * mu[0] + (double)vt[1][q] * mu[1] + (double)vt[2][q] * mu[2] + (double)vt[ND][q] * mu[ND];
+    for (int q = 0; q < 4; q++) {
+      double acc;
+      if constexpr (ND == 2) {
+        const double c0 = q < 2 ? (double)vt[0][q] : (q == 2 ? 0.0 : (double)vt[0][2]);
+        const double c1 = q < 2 ? (double)vt[1][q] : (q == 2 ? 0.0 : (double)vt[1][2]);
+        const double c2 = q < 2 ? (double)vt[2][q] : (q == 2 ? 0.0 : (double)vt[2][2]);
+        acc = c0 * mu[0] + c1 * mu[1] + c2 * mu[2];
+      } else {
+        acc = (double)vt[0][q] * mu[0] + (double)vt[1][q] * mu[1] + (double)vt[2][q] * mu[2] + (double)vt[ND][q] * mu[ND];
+      }
+      xo[q] = acc;
     }
-    xo[q] = acc;
+  } else {                      // bounds / rectilinear / explicit physical coordinates
+    double X[ND + 1][4];
+#pragma unroll
+    for (int k = 0; k <= ND; k++) simplex_coordinates<ND>(p, vt[k], X[k]);
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      double acc = X[0][q] * mu[0] + X[1][q] * mu[1] + X[2][q] * mu[2];
+      if constexpr (ND == 3) acc = acc + X[ND][q] * mu[ND];
+      xo[q] = acc;
+    }
   }
   cp.x[0] = xo[0]; cp.x[1] = xo[1]; cp.x[2] = xo[2]; cp.t = xo[3];
 

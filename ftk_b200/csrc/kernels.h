@@ -32,6 +32,10 @@ struct SweepParams {
   int32_t robust, compute_degrees, use_type_filter;
   uint32_t type_filter;
   LayerPtrs L[2];
+  // physical coordinates of the vertices (regular_tracker.hh:12-17,38-40): 0 grid units, 1 bounds, 2 rectilinear, 3 explicit
+  int32_t coords_mode, coords_ncomp;
+  double coords_bounds[6];
+  const double *coords;       // device: rectilinear x[W] y[H] [z[D]], or explicit (ncomp, W, H)
   // fused mode: the vector field is derived from the scalar layers on the fly (L[].V == nullptr)
   int32_t fused;
   int32_t aligned16;          // rows of S start 16-byte aligned (W even, base aligned): vector loads allowed

@@ -76,6 +76,7 @@ class _RegularTracker:
         self._start_timestep = 0
         self._resolution_init = 0.0
         self._streaming = False
+        self._coords = None
         self._keep = []   # borrowed device arrays stay referenced while resident
 
     # ---- configuration (same names as the reference) ------------------------------------------
@@ -105,6 +106,17 @@ class _RegularTracker:
 
     def set_type_filter(self, f):
         self._type_filter = int(f)
+
+    # physical coordinates (ref: regular_tracker.hh:38-40); applied at initialize()
+    def set_coords_bounds(self, bounds):
+        self._coords = (L.COORDS_BOUNDS, np.ascontiguousarray(bounds, np.float64).ravel())
+
+    def set_coords_rectilinear(self, arrays):
+        self._coords = (L.COORDS_RECTILINEAR, np.concatenate([np.ascontiguousarray(a, np.float64).ravel() for a in arrays]))
+
+    def set_coords_explicit(self, coords):
+        """coords in memory order: shape (H, W, ncomp)"""
+        self._coords = (L.COORDS_EXPLICIT, np.ascontiguousarray(coords, np.float64).ravel())
 
     def set_enable_streaming_trajectories(self, b):
         """ref: critical_point_tracker.hh:38 -- trajectories grown after every interval sweep (hh:522-641)"""
@@ -164,6 +176,9 @@ class _RegularTracker:
         self._dims = list(dims)
         if self._streaming:
             self._check(L.lib().ftkb_set_streaming_trajectories(self._h, 1))
+        if self._coords is not None:
+            mode, data = self._coords
+            self._check(L.lib().ftkb_set_coords(self._h, mode, data.ctypes.data, data.size))
 
     def reset(self):
         self.close()
@@ -362,7 +377,7 @@ class critical_point_tracker_3d_regular(_RegularTracker):
 
 def make_tracker(dims, field="scalar", lb=None, ub=None, jacobian_symmetric=None, robust=True, compute_degrees=False,
                  type_filter=None, start_timestep=0, device=0, resolution_init=0.0,
-                 scalar_source=None, vector_source=None, jacobian_source=None, streaming=False):
+                 scalar_source=None, vector_source=None, jacobian_source=None, streaming=False, coords=None):
     """Configure a tracker the way the reference's front ends do (json_interface.hh:634-656):
     scalar input -> lattice({2,..}, {D-3,..}) = [2, D-2], derived gradient/Hessian, symmetric;
     vector input -> lattice({1,..}, {D-2,..}) = [1, D-2], derived Jacobian, non-symmetric."""
@@ -387,6 +402,9 @@ def make_tracker(dims, field="scalar", lb=None, ub=None, jacobian_symmetric=None
     tr.set_start_timestep(start_timestep)
     tr.set_initial_resolution(resolution_init)
     tr.set_enable_streaming_trajectories(streaming)
+    if coords is not None:      # ("bounds" | "rectilinear" | "explicit", flat data in the reference's order)
+        tr._coords = ({"bounds": L.COORDS_BOUNDS, "rectilinear": L.COORDS_RECTILINEAR, "explicit": L.COORDS_EXPLICIT}[coords[0]],
+                      np.ascontiguousarray(coords[1], np.float64).ravel())
     tr.initialize()
     return tr
 

@@ -331,6 +331,14 @@ class critical_point_tracker_regular {
   void set_enable_computing_degrees(bool b) { degrees_ = b; }
   // critical_point_tracker.hh:38; trajectories then grow after every interval sweep (trace_critical_points_online, hh:522-641)
   void set_enable_streaming_trajectories(bool b) { streaming_ = b; }
+  // physical coordinates: regular_tracker.hh:38-40 (applied at initialize())
+  void set_coords_bounds(const std::vector<double> &bounds) { coords_mode_ = FTKB_COORDS_BOUNDS; coords_ = bounds; }
+  void set_coords_rectilinear(const std::vector<ndarray<double>> &rc) {
+    coords_mode_ = FTKB_COORDS_RECTILINEAR;
+    coords_.clear();
+    for (const auto &a : rc) coords_.insert(coords_.end(), a.data(), a.data() + a.nelem());
+  }
+  void set_coords_explicit(const ndarray<double> &e) { coords_mode_ = FTKB_COORDS_EXPLICIT; coords_.assign(e.data(), e.data() + e.nelem()); }
   void set_enable_discarding_interval_points(bool b) { discard_interval_ = b; }
   void set_enable_discarding_degenerate_points(bool b) { discard_degenerate_ = b; }
   void set_scalar_components(const std::vector<std::string> &c) { scalar_components_ = c; }
@@ -369,6 +377,7 @@ class critical_point_tracker_regular {
     const int rc = ftkb_create(&cfg, &ctx_);
     if (rc != FTKB_OK) throw std::runtime_error(std::string("ftkb_create: ") + ftkb_last_error(nullptr));
     if (streaming_) check(ftkb_set_streaming_trajectories(ctx_, 1));
+    if (coords_mode_ != FTKB_COORDS_SIMPLE) check(ftkb_set_coords(ctx_, coords_mode_, coords_.data(), coords_.size()));
   }
 
   void reset() {
@@ -567,6 +576,8 @@ class critical_point_tracker_regular {
   lattice domain_, array_domain_;
   int scalar_source_ = SOURCE_NONE, vector_source_ = SOURCE_NONE, jacobian_source_ = SOURCE_NONE;
   bool symmetric_ = false, robust_ = true, degrees_ = false, use_type_filter_ = false, discard_interval_ = false, discard_degenerate_ = false, streaming_ = false;
+  int coords_mode_ = FTKB_COORDS_SIMPLE;
+  std::vector<double> coords_;
   unsigned int type_filter_ = 0;
   int start_timestep_ = 0, device_ = 0;
   double resolution_init_ = 0.0;

@@ -132,6 +132,18 @@ int ftkb_push_snapshot(ftkb_ctx *, const double *scalar, const double *vector, c
 /* device-side generator for snapshot time `t` (benchmarks; no host data involved) */
 int ftkb_push_synthetic(ftkb_ctx *, int kind, const double *params, int nparams, double t);
 
+/* physical coordinates of the grid vertices, interpolated into ftkb_point.x by the per-simplex test
+ * (simplex_coordinates, critical_point_tracker_2d_regular.hh:494-526, ..._3d_regular.hh:343-379).  One entry point for the
+ * reference's three setters (regular_tracker.hh:38-40):
+ *   FTKB_COORDS_SIMPLE       grid units (default); data ignored
+ *   FTKB_COORDS_BOUNDS       set_coords_bounds: n = 2*nd values {x0, x1, y0, y1[, z0, z1]}
+ *   FTKB_COORDS_RECTILINEAR  set_coords_rectilinear: n = W + H [+ D] values, x[W] then y[H] [then z[D]]
+ *   FTKB_COORDS_EXPLICIT     set_coords_explicit: (ncomp, W, H) dim-0-fastest, ncomp = n / (W*H) >= nd.  As in the reference,
+ *                            3D trackers look the coordinates up by (x, y) only and report z in ftkb_point.t.
+ * data is host memory, copied before the call returns; applies to the sweeps that follow. */
+enum { FTKB_COORDS_SIMPLE = 0, FTKB_COORDS_BOUNDS = 1, FTKB_COORDS_RECTILINEAR = 2, FTKB_COORDS_EXPLICIT = 3 };
+int ftkb_set_coords(ftkb_ctx *, int mode, const double *data, uint64_t n);
+
 int ftkb_update_timestep(ftkb_ctx *);    /* critical_point_tracker_{2d,3d}_regular::update_timestep */
 int ftkb_advance_timestep(ftkb_ctx *);   /* critical_point_tracker.hh:841-848 */
 int ftkb_finalize(ftkb_ctx *);           /* trace_critical_points_offline, critical_point_tracker.hh:668-817 */

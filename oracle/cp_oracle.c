@@ -666,7 +666,49 @@ struct cpo_ctx {
   /* finalize results */
   uint64_t *labels; int32_t *deg;
   uint64_t ntraj; uint64_t *traj_off, *traj_idx; uint8_t *traj_loop;
+  /* physical coordinates, regular_tracker.hh:12-17,38-40,49-52 */
+  int coords_mode; double *coords; size_t ncoords;
 };
+
+/* set_coords_bounds (mode 1: 2*nd doubles) / set_coords_rectilinear (mode 2: x[W] y[H] [z[D]]) /
+ * set_coords_explicit (mode 3: (ncomp, W, H), ncomp = n / (W*H));  ref: regular_tracker.hh:38-40 */
+void cpo_set_coords(cpo_ctx *c, int mode, const double *data, uint64_t n)
+{
+  free(c->coords); c->coords = NULL;
+  c->coords_mode = mode; c->ncoords = n;
+  if (mode && n) { c->coords = (double *)malloc(sizeof(double) * n); memcpy(c->coords, data, sizeof(double) * n); }
+}
+
+/* simplex_coordinates: critical_point_tracker_2d_regular.hh:494-526, ..._3d_regular.hh:343-379.
+ * vt = vertex (x, y[, z], t); the array domain starts at 0.  Note the 3D explicit mode as the reference has it:
+ * coordinates looked up by (x, y) only and the time slot filled with z. */
+static void simplex_coordinates(const cpo_ctx *c, const int *vt, double X[4])
+{
+  const int n = c->n;
+  const int32_t *dims = c->cfg.dims;
+  if (c->coords_mode == 1) {
+    for (int j = 0; j < n; j ++)
+      X[j] = ((vt[j] - 0) / (double)(dims[j] - 1)) * (c->coords[2*j+1] - c->coords[2*j]) + c->coords[2*j];
+    if (n == 2) X[2] = 0.0;
+    X[3] = vt[n];
+  } else if (c->coords_mode == 2) {
+    size_t off = 0;
+    for (int j = 0; j < n; j ++) { X[j] = c->coords[off + vt[j]]; off += dims[j]; }
+    if (n == 2) X[2] = 0.0;
+    X[3] = vt[n];
+  } else if (c->coords_mode == 3) {
+    const size_t nc = c->ncoords / ((size_t)dims[0] * dims[1]);
+    const size_t k = (size_t)vt[0] + (size_t)dims[0] * vt[1];
+    X[0] = c->coords[0 + nc * k]; X[1] = c->coords[1 + nc * k];
+    if (n == 2) X[2] = nc > 2 ? c->coords[2 + nc * k] : 0.0;
+    else X[2] = c->coords[2 + nc * k];
+    X[3] = vt[2];
+  } else {
+    for (int j = 0; j < n; j ++) X[j] = vt[j];
+    if (n == 2) X[2] = 0.0;
+    X[3] = vt[n];
+  }
+}
 
 cpo_ctx *cpo_create(const cpo_config *cfg)
 {
@@ -685,6 +727,7 @@ static void free_snapshot(snapshot_t *s) { free(s->scalar); free(s->vector); fre
 
 void cpo_destroy(cpo_ctx *c)
 {
+  if (c) free(c->coords);
   if (!c) return;
   for (int i = 0; i < c->nsnaps; i ++) free_snapshot(&c->snaps[i]);
   free(c->pts); free(c->labels); free(c->deg); free(c->traj_off); free(c->traj_idx); free(c->traj_loop);
@@ -811,7 +854,7 @@ static int check_simplex_2d(const cpo_ctx *c, const int corner[3], int type, cpo
 
   /* simplex_coordinates (REGULAR_COORDS_SIMPLE) + lerp_s2v4: ref linear_interpolation.hh:81-89 */
   double X[3][4];
-  for (int i = 0; i < 3; i ++) { X[i][0] = vt[i][0]; X[i][1] = vt[i][1]; X[i][2] = 0.0; X[i][3] = vt[i][2]; }
+  for (int i = 0; i < 3; i ++) simplex_coordinates(c, vt[i], X[i]);
   double x[4];
   for (int k = 0; k < 4; k ++) x[k] = X[0][k] * mu[0] + X[1][k] * mu[1] + X[2][k] * mu[2];
   memset(cp, 0, sizeof(*cp));
@@ -888,9 +931,10 @@ static int check_simplex_3d(const cpo_ctx *c, const int corner[4], int type, cpo
   }
   clamp_barycentric(4, mu);
 
-  double x[4];
-  for (int k = 0; k < 4; k ++) /* lerp_s3v4 with X = integer vertex coordinates */
-    x[k] = (double)vt[0][k] * mu[0] + (double)vt[1][k] * mu[1] + (double)vt[2][k] * mu[2] + (double)vt[3][k] * mu[3];
+  double X[4][4], x[4];
+  for (int i = 0; i < 4; i ++) simplex_coordinates(c, vt[i], X[i]);
+  for (int k = 0; k < 4; k ++) /* lerp_s3v4 */
+    x[k] = X[0][k] * mu[0] + X[1][k] * mu[1] + X[2][k] * mu[2] + X[3][k] * mu[3];
   memset(cp, 0, sizeof(*cp));
   cp->x[0] = x[0]; cp->x[1] = x[1]; cp->x[2] = x[2]; cp->t = x[3];
 

@@ -49,6 +49,8 @@ void cpo_destroy(cpo_ctx *);
 /* any pointer may be NULL according to the *_source settings; arrays are dim-0-fastest
  * scalar (W,H[,D]); vector (n,W,H[,D]); jacobian (n,n,W,H[,D]) */
 int cpo_push_snapshot(cpo_ctx *, const double *scalar, const double *vector, const double *jacobian);
+/* physical coordinates (regular_tracker.hh:38-40): mode 0 grid units, 1 bounds, 2 rectilinear, 3 explicit */
+void cpo_set_coords(cpo_ctx *, int mode, const double *data, uint64_t n);
 int cpo_update_timestep(cpo_ctx *);
 int cpo_advance_timestep(cpo_ctx *);
 int cpo_finalize(cpo_ctx *);

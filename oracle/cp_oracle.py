@@ -64,6 +64,8 @@ def lib():
             getattr(L, name).argtypes = [C.c_void_p]
             getattr(L, name).restype = C.c_uint64
         L.cpo_get_points.argtypes = [C.c_void_p, C.c_void_p]
+        L.cpo_set_coords.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64]
+        L.cpo_set_coords.restype = None
         L.cpo_set_resolution.argtypes = [C.c_void_p, C.c_double]
         L.cpo_set_resolution.restype = None
         L.cpo_import_points.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
@@ -174,12 +176,15 @@ def synthetic_series(name, dims, T, params=None):
 
 
 # ---------------------------------------------------------------------------------------------
+COORDS_MODES = {"bounds": 1, "rectilinear": 2, "explicit": 3}
+
+
 class Tracker:
     """Oracle twin of ftk::critical_point_tracker_{2d,3d}_regular (CPU, non-GMP)."""
 
     def __init__(self, dims, lb=None, ub=None, field="scalar", jacobian_symmetric=None, robust=True,
                  compute_degrees=False, type_filter=None, start_timestep=0, nthreads=0,
-                 scalar_source=None, vector_source=None, jacobian_source=None):
+                 scalar_source=None, vector_source=None, jacobian_source=None, coords=None):
         nd = len(dims)
         cfg = Config()
         cfg.nd = nd
@@ -211,6 +216,10 @@ class Tracker:
         self._h = lib().cpo_create(C.byref(cfg))
         if not self._h:
             raise RuntimeError("cpo_create failed")
+        if coords is not None:      # (mode name, flat float64 data): regular_tracker.hh:38-40
+            mode, data = coords
+            data = np.ascontiguousarray(data, np.float64).ravel()
+            lib().cpo_set_coords(self._h, COORDS_MODES[mode], _ptr(data), data.size)
 
     def __del__(self):
         if getattr(self, "_h", None):
@@ -340,7 +349,7 @@ def canonical_trajectories(trajs):
 
 
 def run_reference(nd, nv, dims, T, gen=None, params=None, input_array=None, out=None, trace=True, domain=None,
-                  symmetric=None, nthreads=0, timeout=3600):
+                  symmetric=None, nthreads=0, timeout=3600, coords=None):
     """Run the unmodified reference binary (oracle/_ref).  Returns (stats dict, golden dict or None)."""
     import json
     import tempfile
@@ -365,6 +374,12 @@ def run_reference(nd, nv, dims, T, gen=None, params=None, input_array=None, out=
         cmd += ["--nthreads", str(nthreads)]
     if not trace:
         cmd += ["--no-trace"]
+    tmp_coords = None
+    if coords is not None:
+        tmp_coords = tempfile.NamedTemporaryFile(suffix=".f64", delete=False)
+        np.ascontiguousarray(coords[1], np.float64).ravel().tofile(tmp_coords)
+        tmp_coords.close()
+        cmd += ["--coords", coords[0], "--coords-file", tmp_coords.name]
     tmp_out = None
     if out is None:
         tmp_out = tempfile.NamedTemporaryFile(suffix=".ftkg", delete=False)
@@ -378,6 +393,8 @@ def run_reference(nd, nv, dims, T, gen=None, params=None, input_array=None, out=
     finally:
         if tmp_in is not None:
             os.unlink(tmp_in.name)
+        if tmp_coords is not None:
+            os.unlink(tmp_coords.name)
         if tmp_out is not None and os.path.exists(tmp_out.name):
             os.unlink(tmp_out.name)
     return stats, gold

@@ -41,7 +41,7 @@ struct args_t {
   int symmetric = -1;
   bool trace = true, quiet = false, have_domain = false;
   int dom[6] = {0, 0, 0, 0, 0, 0};
-  std::string gen, input, out, dump_input, post, out_curves, bin_traced, bin_discrete, out_stream;
+  std::string gen, input, out, dump_input, post, out_curves, bin_traced, bin_discrete, out_stream, coords, coords_file;
   std::vector<double> p;
 };
 
@@ -118,6 +118,25 @@ static int run(const args_t &a)
   }
   tr.set_domain(ftk::lattice(dst, dsz));
   tr.set_array_domain(ftk::lattice(ast, asz));
+  if (!a.coords.empty()) {   // regular_tracker.hh:38-40
+    FILE *fc = fopen(a.coords_file.c_str(), "rb"); if (!fc) { perror("coords-file"); return 2; }
+    std::vector<double> cd;
+    double tmp;
+    while (fread(&tmp, 8, 1, fc) == 1) cd.push_back(tmp);
+    fclose(fc);
+    if (a.coords == "bounds") tr.set_coords_bounds(cd);
+    else if (a.coords == "rectilinear") {
+      std::vector<ftk::ndarray<double>> rc;
+      size_t off = 0;
+      for (int i = 0; i < nd; i ++) { ftk::ndarray<double> r; r.reshape({dims[i]}); for (size_t k = 0; k < dims[i]; k ++) r[k] = cd[off + k]; off += dims[i]; rc.push_back(r); }
+      tr.set_coords_rectilinear(rc);
+    } else if (a.coords == "explicit") {
+      const size_t wh = dims[0] * dims[1], nc = cd.size() / wh;
+      ftk::ndarray<double> e; e.reshape({nc, dims[0], dims[1]});
+      for (size_t k = 0; k < nc * wh; k ++) e[k] = cd[k];
+      tr.set_coords_explicit(e);
+    } else { fprintf(stderr, "unknown --coords %s\n", a.coords.c_str()); return 2; }
+  }
   tr.initialize();
 
   tracker_t trs(comm);           // streaming twin: same configuration, trajectories grown online after every step
@@ -322,6 +341,8 @@ int main(int argc, char **argv)
     else if (s == "--binary-traced") a.bin_traced = next();      // tracker.write_traced_critical_points_binary (DIY archive)
     else if (s == "--binary-discrete") a.bin_discrete = next();  // tracker.write_critical_points_binary
     else if (s == "--out-stream") a.out_stream = next();         // a second tracker with set_enable_streaming_trajectories(true)
+    else if (s == "--coords") a.coords = next();
+    else if (s == "--coords-file") a.coords_file = next();
     else if (s == "--post") a.post = next();
     else if (s == "--out-curves") a.out_curves = next();
     else if (s == "--quiet") a.quiet = true;
