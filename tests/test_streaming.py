@@ -97,6 +97,14 @@ def test_host_grow_step_duplicates_and_empty(ftkb):
     assert len(t) == 2 and np.array_equal(t[0][0], ta[0][0])   # a complete trajectory is never extended again
 
 
+def test_cli_lists_stream_flag():
+    import subprocess
+    from ftk_b200 import build
+    build.build()
+    out = subprocess.run([build.CLI, "--help"], capture_output=True, text=True)
+    assert out.returncode == 0 and "--stream" in out.stdout
+
+
 def test_streaming_call_order_is_checked(ftkb):
     import ctypes as C
     assert ftkb.lib().ftkb_set_streaming_trajectories(None, 1) == 1          # FTKB_ERR_INVALID
