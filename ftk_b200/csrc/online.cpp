@@ -195,12 +195,17 @@ void OnlineTracer::grow(const ftkb_point *pts_in, uint64_t n_in) {
     }
     return cnt;
   };
-  // smallest unclaimed punctured neighbour of an element (critical_point_tracker.hh:555-572)
+  // smallest unclaimed punctured neighbour of an element (critical_point_tracker.hh:555-572): probe in ascending order,
+  // stop at the first hit
   auto claim_next = [&](const ftkb_point &cur) -> int64_t {
-    int64_t nbr[9];
-    const int cnt = present_neighbors(cur, nbr);
-    for (int q = 0; q < cnt; q++)
-      if (nbr[q] >= 0 && alive[nbr[q]]) { alive[nbr[q]] = 0; return nbr[q]; }
+    uint64_t nk[9];
+    size_t home[9];
+    const int cnt = neighbor_keys(cur, nk);
+    for (int q = 0; q < cnt; q++) { home[q] = home_of(nk[q]); __builtin_prefetch(&table[home[q]]); }
+    for (int q = 0; q < cnt; q++) {
+      const size_t h = slot_from(home[q], nk[q]);
+      if (table[h].key == nk[q] && alive[table[h].val]) { alive[table[h].val] = 0; return (int64_t)table[h].val; }
+    }
     return -1;
   };
 
