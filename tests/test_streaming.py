@@ -241,3 +241,44 @@ def test_two_slabs_streaming_equals_sequential_streaming(case, tmp_path, oracle)
     assert np.array_equal(res["points"]["corner"], seq["corner"]) and np.array_equal(res["points"]["simplex_type"], seq["simplex_type"])
     want = cp_online.trace_streaming(len(dims), seq["corner"], seq["simplex_type"], seq["timestep"], T)
     assert len(want) > 0 and res["streamed"] == [(list(i), l, c) for i, l, c in want]
+
+
+def test_host_grow_step_nothing_to_grow(ftkb):
+    """no grow step at all (a one-timestep run) and grow steps that receive nothing: no trajectories"""
+    from ftk_b200.online import OnlineTracer, replay_streaming
+    tr = OnlineTracer([2, 2], [10, 10])
+    assert tr.trajectories() == []
+    tr.grow(np.zeros(0, ftkb.POINT_DTYPE))
+    assert tr.trajectories() == []
+    meta, gold, _ = load_golden("mx2d_11x13x20")
+    p = np.zeros(len(gold["points"]), ftkb.POINT_DTYPE)
+    for f in p.dtype.names:
+        p[f] = gold["points"][f]
+    assert replay_streaming(p[p["timestep"] == 0], *_domain(meta), T=1) == []      # the only sweep is the last ordinal one
+    two = replay_streaming(p[p["timestep"] <= 1], *_domain(meta), T=2)
+    assert len(two) == 1 and len(two[0][0]) == int((p["timestep"] == 0).sum())
+
+
+@pytest.mark.gpu
+def test_gpu_streaming_edge_cases(oracle):
+    """one timestep (no grow step runs); finalize twice; complete flags reach the curve set; import_points is refused"""
+    from ftk_b200 import _lib, tracker as T
+    from ftk_b200.curves import CurveSet
+    snaps = list(oracle.synthetic_series("woven", [31, 37], 6, None))
+    one = T.track(snaps[:1], [31, 37], streaming=True)
+    assert one.get_trajectory_index() == [] and len(one.get_discrete_critical_points()) > 0
+    one.close()
+    tr = T.track(snaps, [31, 37], streaming=True)
+    a = [(i.tolist(), l) for i, l in tr.get_trajectory_index()]
+    tr.finalize()
+    assert [(i.tolist(), l) for i, l in tr.get_trajectory_index()] == a and len(a) > 0
+    complete = tr.get_trajectory_complete()
+    cs = CurveSet.from_tracker(tr)
+    infos, _ = cs.arrays()
+    assert [int(v) for v in infos["complete"]] == [int(v) for v in complete] and [int(v) for v in infos["id"]] == list(range(len(a)))
+    assert [int(v) for v in infos["count"]] == [len(i) for i, _ in a]
+    cs.close()
+    pts = tr.get_discrete_critical_points()
+    assert _lib.lib().ftkb_import_points(tr._h, pts.ctypes.data, 1) == 1            # FTKB_ERR_INVALID in streaming mode
+    assert _lib.lib().ftkb_set_streaming_trajectories(tr._h, 0) == 1                # too late: sweeps have run
+    tr.close()
