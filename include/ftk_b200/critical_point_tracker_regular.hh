@@ -554,6 +554,9 @@ class critical_point_tracker_regular {
     feature_point_t p;
     {
       p.x = {{r.x[0], r.x[1], r.x[2]}};
+      // the library works in array-relative vertex coordinates; the reference's grid-unit positions are absolute
+      // (simplex_coordinates, REGULAR_COORDS_SIMPLE: X = vertices).  Bounds coordinates are array-relative there too.
+      if (coords_mode_ == FTKB_COORDS_SIMPLE) for (int j = 0; j < nd_; j++) p.x[j] += (double)array_domain_.start(j);
       p.t = r.t;
       p.timestep = r.timestep;
       p.scalar = {{r.scalar, 0.0, 0.0}};
