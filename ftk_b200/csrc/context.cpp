@@ -18,6 +18,7 @@
 #include <string>
 #include <vector>
 
+#include <future>
 #include <memory>
 #include "kernels.h"
 #include "online.h"
@@ -100,7 +101,9 @@ struct ftkb_ctx {
   bool streaming = false;
   std::unique_ptr<ftkb::OnlineTracer> online;
   uint64_t grown = 0;            // d_pts[0 .. grown) have been through a grow step
-  std::vector<ftkb_point> batch;
+  // the grow step of sweep k runs on a worker while the caller produces / pushes snapshot k+2 and the device sweeps
+  // step k+1; at most one is in flight, and everything that reads `online` or the host-trace time joins it first
+  std::future<double> grow_task;
 
   ftkb_stats stats{};
 };
@@ -150,8 +153,11 @@ static void release_layer(ftkb_ctx *c, Layer &l) {
   l = Layer();
 }
 
+static void wait_grow(ftkb_ctx *c);
+
 extern "C" void ftkb_destroy(ftkb_ctx *c) {
   if (!c) return;
+  wait_grow(c);
   cudaSetDevice(c->cfg.device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   for (auto &l : c->layers) release_layer(c, l);
@@ -628,18 +634,28 @@ static int resolve_pending(ftkb_ctx *c, Layer &l) {
 // ref: critical_point_tracker_{2d,3d}_regular::update_timestep (xl == NONE branch)
 // grow(), critical_point_tracker_2d_regular.hh:288-329 / ..._3d_regular.hh:173-200: the punctured simplices found since
 // the last grow step (the reference clears discrete_critical_points after each) go to the host-side online tracer
+static void wait_grow(ftkb_ctx *c) {
+  if (!c->grow_task.valid()) return;
+  try { c->stats.ms_finalize_host += c->grow_task.get(); }
+  catch (const std::exception &e) { c->error = std::string("streaming grow step: ") + e.what(); }
+}
+
 static int grow_trajectories(ftkb_ctx *c) {
   const uint64_t n = c->npts - c->grown;
   if (n >= 0xffffffffull) return fail(c, FTKB_ERR_OVERFLOW, "more than 2^32 punctured simplices in one step");
-  c->batch.resize(n);
+  std::vector<ftkb_point> batch(n);
   if (n) {
-    CK(cudaMemcpyAsync(c->batch.data(), c->d_pts + c->grown, sizeof(ftkb_point) * n, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(batch.data(), c->d_pts + c->grown, sizeof(ftkb_point) * n, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     c->stats.d2h_bytes += sizeof(ftkb_point) * n;
   }
-  const auto t0 = std::chrono::steady_clock::now();
-  c->online->grow(c->batch.data(), n);
-  c->stats.ms_finalize_host += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  wait_grow(c);                  // grow steps run in order
+  ftkb::OnlineTracer *tracer = c->online.get();
+  c->grow_task = std::async(std::launch::async, [tracer](std::vector<ftkb_point> b) {
+    const auto t0 = std::chrono::steady_clock::now();
+    tracer->grow(b.data(), b.size());
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  }, std::move(batch));
   c->grown = c->npts;
   c->traced = false;
   return FTKB_OK;
@@ -648,6 +664,7 @@ static int grow_trajectories(ftkb_ctx *c) {
 extern "C" int ftkb_set_streaming_trajectories(ftkb_ctx *c, int enable) {
   if (!c) return FTKB_ERR_INVALID;
   if (c->stats.scan_launches || c->npts) return fail(c, FTKB_ERR_INVALID, "set_streaming_trajectories: call it before the first update_timestep");
+  wait_grow(c);
   c->streaming = enable != 0;
   c->online.reset(c->streaming ? new ftkb::OnlineTracer(c->n, c->cfg.lb, c->cfg.ub) : nullptr);
   c->grown = 0;
@@ -1011,6 +1028,7 @@ extern "C" int ftkb_finalize(ftkb_ctx *c) {
   c->traj_loop.clear();
   c->traj_complete.clear();
   if (c->streaming) {
+    wait_grow(c);
     // "done" (critical_point_tracker_2d_regular.hh:150-151): publish the grown trajectories, in id order, as CSR over
     // the sorted points; the component labels / degrees of the offline trace are not computed
     const auto t0 = std::chrono::steady_clock::now();
@@ -1260,6 +1278,7 @@ extern "C" int ftkb_get_last_worklist(ftkb_ctx *c, uint64_t *out, uint64_t cap, 
 
 extern "C" int ftkb_get_stats(ftkb_ctx *c, ftkb_stats *out) {
   if (!c || !out) return FTKB_ERR_INVALID;
+  wait_grow(c);
   c->stats.scaling_factor = c->factor;
   c->stats.resolution = c->resolution;
   *out = c->stats;
@@ -1268,6 +1287,7 @@ extern "C" int ftkb_get_stats(ftkb_ctx *c, ftkb_stats *out) {
 
 extern "C" int ftkb_reset_stats(ftkb_ctx *c) {
   if (!c) return FTKB_ERR_INVALID;
+  wait_grow(c);
   const uint64_t pts = c->stats.points;
   c->stats = ftkb_stats{};
   c->stats.points = pts;
@@ -1278,6 +1298,7 @@ extern "C" int ftkb_synchronize(ftkb_ctx *c) {
   if (!c) return FTKB_ERR_INVALID;
   CK(cudaSetDevice(c->cfg.device));
   CK(cudaStreamSynchronize(c->stream));
+  wait_grow(c);
   return FTKB_OK;
 }
 
