@@ -31,6 +31,7 @@ OnlineTracer::OnlineTracer(int nd, const int32_t lb[3], const int32_t ub[3]) : n
   nz_ = ub_[2] - lb_[2] + 1;
   DeviceMeshTables mt;
   fill_device_tables(nd + 1, &mt);
+  ntypes_ = mt.ntypes;
   for (int type = 0; type < mt.ntypes; type++) {
     int cnt = 0;
     Candidate self{};
@@ -57,6 +58,7 @@ OnlineTracer::OnlineTracer(int nd, const int32_t lb[3], const int32_t ub[3]) : n
 bool OnlineTracer::key_at(int x, int y, int z, int t, int type, uint64_t &key) const {
   if (x < lb_[0] || x > ub_[0] || y < lb_[1] || y > ub_[1] || t < 0 || t >= (1 << KEY_TIME_BITS)) return false;
   if (nd_ == 3 && (z < lb_[2] || z > ub_[2])) return false;
+  if (type < 0 || type >= ntypes_) return false;
   uint64_t k = (uint64_t)(x - lb_[0]);
   k = k * (uint64_t)ny_ + (uint64_t)(y - lb_[1]);
   k = k * (uint64_t)nz_ + (uint64_t)(nd_ == 3 ? z - lb_[2] : 0);
@@ -68,7 +70,7 @@ bool OnlineTracer::key_at(int x, int y, int z, int t, int type, uint64_t &key) c
 // neighbors(f) = every side of every cell f is a side of (critical_point_tracker_2d_regular.hh:292-300), f included
 int OnlineTracer::neighbor_keys(const ftkb_point &p, uint64_t out[9]) const {
   const int type = p.simplex_type;
-  if (type < 0 || type >= 60) return 0;
+  if (type < 0 || type >= ntypes_) return 0;
   const int x0 = p.corner[0], y0 = p.corner[1], z0 = nd_ == 3 ? p.corner[2] : 0, t0 = p.corner[3];
   const int64_t cell = ((int64_t)(x0 - lb_[0]) * ny_ + (y0 - lb_[1])) * nz_ + (z0 - lb_[2]);
   int cnt = 0;

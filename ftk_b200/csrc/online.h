@@ -36,7 +36,8 @@ class OnlineTracer {
   // of (corner + offset, type) does not depend on the corner
   struct Candidate { int8_t off[4]; int8_t type; int64_t cell_delta; };
   Candidate cand_[60][9];
-  int ncand_[60];
+  int ncand_[60] = {};
+  int ntypes_ = 0;             // 12 (2D+t) or 60 (3D+t); points with another simplex type are ignored
   std::vector<OnlineCurve> curves_;
 };
 

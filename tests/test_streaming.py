@@ -282,3 +282,15 @@ def test_gpu_streaming_edge_cases(oracle):
     assert _lib.lib().ftkb_import_points(tr._h, pts.ctypes.data, 1) == 1            # FTKB_ERR_INVALID in streaming mode
     assert _lib.lib().ftkb_set_streaming_trajectories(tr._h, 0) == 1                # too late: sweeps have run
     tr.close()
+
+
+def test_host_grow_step_ignores_foreign_points(ftkb):
+    """points outside the domain or with a simplex type the mesh does not have are not elements: ignored, not traced"""
+    from ftk_b200.online import OnlineTracer
+    p = np.zeros(4, ftkb.POINT_DTYPE)
+    p["corner"] = [[3, 3, 0, 0], [50, 3, 0, 0], [3, 3, 0, 0], [3, 3, 0, -1]]
+    p["simplex_type"] = [4, 4, 40, 4]                 # 2D+t mesh: 12 types
+    tr = OnlineTracer([2, 2], [10, 10])
+    tr.grow(p)
+    t = tr.trajectories()
+    assert len(t) == 1 and len(t[0][0]) == 1 and int(t[0][0]["simplex_type"][0]) == 4
