@@ -13,6 +13,12 @@ namespace ftkb {
 struct OnlineCurve {
   std::deque<ftkb_point> pts;
   bool loop = false, complete = false;
+  OnlineCurve() = default;
+  OnlineCurve(const OnlineCurve &) = default;
+  OnlineCurve &operator=(const OnlineCurve &) = default;
+  // noexcept so that a growing std::vector<OnlineCurve> moves its curves instead of copying every point
+  OnlineCurve(OnlineCurve &&o) noexcept : pts(std::move(o.pts)), loop(o.loop), complete(o.complete) {}
+  OnlineCurve &operator=(OnlineCurve &&o) noexcept { pts = std::move(o.pts); loop = o.loop; complete = o.complete; return *this; }
 };
 
 class OnlineTracer {
