@@ -101,8 +101,9 @@ struct ftkb_ctx {
   bool streaming = false;
   std::unique_ptr<ftkb::OnlineTracer> online;
   uint64_t grown = 0;            // d_pts[0 .. grown) have been through a grow step
-  // the grow step of sweep k runs on a worker while the caller produces / pushes snapshot k+2 and the device sweeps
-  // step k+1; at most one is in flight, and everything that reads `online` or the host-trace time joins it first
+  // FTKB_STREAM_GROW=async: the grow step of sweep k runs on a worker while the caller produces / pushes the next snapshot
+  // and the device sweeps step k+1; at most one is in flight, and everything that reads `online` or the host-trace time
+  // joins it first.  Default: inline.
   std::future<double> grow_task;
 
   ftkb_stats stats{};
@@ -651,11 +652,18 @@ static int grow_trajectories(ftkb_ctx *c) {
   }
   wait_grow(c);                  // grow steps run in order
   ftkb::OnlineTracer *tracer = c->online.get();
-  c->grow_task = std::async(std::launch::async, [tracer](std::vector<ftkb_point> b) {
+  auto work = [tracer](std::vector<ftkb_point> b) {
     const auto t0 = std::chrono::steady_clock::now();
     tracer->grow(b.data(), b.size());
     return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-  }, std::move(batch));
+  };
+  // FTKB_STREAM_GROW=async: the walk of step k runs on a worker thread behind the sweep of step k+1 and the caller's next
+  // push.  Default is inline: the two modes measured the same on the loop of scripts/stream_timing.py (the walk is the
+  // whole cost there) and one async run showed the sweeps' API calls stalling next to the busy worker
+  // (profiles/r01f_stream_timing.md), so async stays opt-in until that is understood.
+  static const bool async_grow = [] { const char *e = std::getenv("FTKB_STREAM_GROW"); return e && std::string(e) == "async"; }();
+  if (async_grow) c->grow_task = std::async(std::launch::async, work, std::move(batch));
+  else c->stats.ms_finalize_host += work(std::move(batch));
   c->grown = c->npts;
   c->traced = false;
   return FTKB_OK;
