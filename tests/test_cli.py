@@ -213,3 +213,25 @@ def test_cli_sliced_output(cli, tmp_path):
             assert all(f"timestep={t}, ordinal=1" in line for line in lines)
             got[t] = len(lines)
     assert got == want
+
+
+def test_shim_header_streaming_and_coords_compile(tmp_path):
+    """the shim's streaming switch and the three coordinate setters (regular_tracker.hh:38-40, critical_point_tracker.hh:38)"""
+    src = tmp_path / "caller2.cpp"
+    src.write_text(r'''
+#include "ftk_b200/critical_point_tracker_regular.hh"
+int run(const double *data, size_t DW, size_t DH, size_t DD, const double *xs, const double *ys, const double *xy) {
+  ftk_b200::critical_point_tracker_2d_regular t2;
+  t2.set_enable_streaming_trajectories(true);
+  t2.set_coords_bounds({0.0, 1.0, -1.0, 1.0});
+  t2.set_coords_rectilinear({ftk_b200::ndarray<double>::wrap(xs, {DW}), ftk_b200::ndarray<double>::wrap(ys, {DH})});
+  t2.set_coords_explicit(ftk_b200::ndarray<double>::wrap(xy, {2, DW, DH}));
+  ftk_b200::critical_point_tracker_3d_regular t3;
+  t3.set_coords_bounds({0.0, 1.0, 0.0, 1.0, 0.0, 1.0});
+  t3.set_enable_streaming_trajectories(true);
+  int n = 0;
+  for (const auto &kv : t2.get_traced_critical_points()) n += kv.second.complete ? 1 : 0;
+  return n + (int)(DD + (data != nullptr));
+}
+''')
+    subprocess.check_call(["g++", "-std=c++17", "-Wall", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), str(src)])
