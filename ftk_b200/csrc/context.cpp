@@ -65,16 +65,46 @@ struct ftkb_ctx {
                                  // (direct = no shared memory, 16-byte loads + shuffles: measured 0.259 ms vs 0.188 ms on C2)
   bool cellsV = true;            // same for vector input (field GIVEN); FTKB_VSCAN=twolayer re-reads both layers and runs the resolution pass
   bool cells2d = true;           // same for the fused 2D tile scan; FTKB_SCAN2D=twolayer re-reads both layers every step
+  bool keys2d = true;            // 2D scalar build kernel keeps high-word keys of the differences (no fp64->fp32 conversions);
+                                 // FTKB_SCAN2D=f32 (or a poisoned layer: NaN / Inf / >= 2^1000) selects the fp32-range build kernel
   bool cells3d = true;           // fused 3D scan streams each layer once and keeps its range cells; FTKB_SCAN3D=twolayer re-reads both layers every step
   std::vector<uint4 *> freeCells;
   std::vector<uint4 *> exportedCells;   // handed to a peer process (ftkb_export_layer_cells): freed at destroy only
   size_t ncells = 0;             // cells per layer (fixed by the dims)
   bool fused3d = false;          // 3D scalar input: gradient fused into the scan (TMA-staged); FTKB_SCAN3D=plain materialises the gradient instead
 
-  // device scalars: [0..7] per-layer resolution bits, [8] worklist count, [9] point count, [10] unique count
+  // device scalars: [0..7] per-layer resolution bits, [8] worklist count, [9] point count, [10] unique count, [11] poison,
+  // [12] the second worklist counter (deferred steps alternate), [13] ticket of the test kernel's blocks
   unsigned long long *d_scalars = nullptr;
   unsigned long long *h_scalars = nullptr;     // pinned mirror
-  static constexpr int SLOT_WL = 8, SLOT_PT = 9, SLOT_UQ = 10, SLOT_POISON = 11, NSLOTS = 16;
+  static constexpr int SLOT_WL = 8, SLOT_PT = 9, SLOT_UQ = 10, SLOT_POISON = 11, SLOT_WL2 = 12, SLOT_TICKET = 13, NSLOTS = 16;
+
+  // ---- deferred ("sync-free") steps ------------------------------------------------------------------------------
+  // ftkb_update_timestep enqueues scan + test and returns; the test kernel's last block publishes the counters into the
+  // mapped ring below and re-arms the device counters.  The step is confirmed -- counters read, statistics updated --
+  // AFTER the next step has been enqueued (or by any call that needs results: drain()).  A step that turns out to have
+  // run with a stale quantisation factor, or whose buffers overflowed, is replayed synchronously together with
+  // whatever was enqueued behind it.  Layers popped in between wait in `limbo`.
+  struct Pending {
+    int ring = 0, evset = 0, pops = 0, nbits = 0;
+    uint64_t seq = 0, npts_before = 0;
+    bool has_next = false;
+    int res_slots[2] = {-1, -1};     // resolution slots this step's scan fills
+  };
+  bool defer = true;                 // FTKB_DEFER=0: every step synchronous (the round-1 behaviour)
+  std::deque<Pending> pend;
+  std::deque<Layer> limbo;
+  unsigned long long *h_ring = nullptr;        // pinned + mapped: RING entries of 8 u64
+  static constexpr int RING = 4;
+  uint64_t step_seq = 0;
+  bool primed = false;               // the previous deferred step left the device counters armed for the next one
+  int wl_sel = 0;                    // worklist counter of the next deferred step: 0 = SLOT_WL, 1 = SLOT_WL2
+  cudaEvent_t dev[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
+  bool push_d2h_outstanding = false; // a push queued a resolution read-back the next sweep must wait for
+  uint64_t wl_hint = 1 << 16;        // surviving cubes expected by the next test kernel (sizes its grid)
+  cudaEvent_t ev_input = nullptr;    // orders device inputs after their producer stream (ftkb_set_producer_stream)
+  cudaStream_t producer = nullptr;
+  bool has_producer = false;
 
   unsigned long long *d_wl = nullptr;
   uint64_t wl_cap = 0, last_wl = 0;
@@ -105,6 +135,7 @@ struct ftkb_ctx {
   // and the device sweeps step k+1; at most one is in flight, and everything that reads `online` or the host-trace time
   // joins it first.  Default: inline.
   std::future<double> grow_task;
+  bool grow_failed = false;      // a grow step threw: every later call that depends on the trajectories reports it
 
   ftkb_stats stats{};
 };
@@ -154,14 +185,17 @@ static void release_layer(ftkb_ctx *c, Layer &l) {
   l = Layer();
 }
 
-static void wait_grow(ftkb_ctx *c);
+static int wait_grow(ftkb_ctx *c);
+static int drain(ftkb_ctx *c);
 
 extern "C" void ftkb_destroy(ftkb_ctx *c) {
   if (!c) return;
-  wait_grow(c);
+  (void)wait_grow(c);
   cudaSetDevice(c->cfg.device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   for (auto &l : c->layers) release_layer(c, l);
+  for (auto &l : c->limbo) release_layer(c, l);
+  c->limbo.clear();
   for (auto *p : c->freeS) cudaFree(p);
   for (auto *p : c->freeV) cudaFree(p);
   for (auto *p : c->freeJ) cudaFree(p);
@@ -169,6 +203,9 @@ extern "C" void ftkb_destroy(ftkb_ctx *c) {
   for (auto *p : c->exportedCells) cudaFree(p);
   cudaFree(c->d_scalars);
   if (c->h_scalars) cudaFreeHost(c->h_scalars);
+  if (c->h_ring) cudaFreeHost(c->h_ring);
+  for (auto &es : c->dev) for (auto &e : es) if (e) cudaEventDestroy(e);
+  if (c->ev_input) cudaEventDestroy(c->ev_input);
   cudaFree(c->d_wl);
   cudaFree(c->d_pts);
   cudaFree(c->d_coords);
@@ -217,6 +254,7 @@ extern "C" int ftkb_create(const ftkb_config *cfg, ftkb_ctx **out) {
                 !(ev && std::string(ev) == "twolayer");
     const char *e2 = std::getenv("FTKB_SCAN2D");
     c->cells2d = n == 2 && cfg->vector_source == FTKB_SOURCE_DERIVED && c->scan_mode >= 2 && !(e2 && std::string(e2) == "twolayer");
+    c->keys2d = !(e2 && std::string(e2) == "f32");
     if (n == 2 && c->scan_mode == 3 && !c->cells2d) c->scan_mode = 2;      // the direct staging exists as a cell scan only
   }
   c->n = n;
@@ -242,8 +280,17 @@ extern "C" int ftkb_create(const ftkb_config *cfg, ftkb_ctx **out) {
     if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail(std::string("cudaEventCreate: ") + cudaGetErrorString(e), FTKB_ERR_CUDA);
   if ((e = cudaMalloc(&c->d_scalars, sizeof(unsigned long long) * ftkb_ctx::NSLOTS)) != cudaSuccess) return bail("cudaMalloc(scalars) failed", FTKB_ERR_NOMEM);
   if ((e = cudaMallocHost(&c->h_scalars, sizeof(unsigned long long) * ftkb_ctx::NSLOTS)) != cudaSuccess) return bail("cudaMallocHost failed", FTKB_ERR_NOMEM);
+  std::memset(c->h_scalars, 0, sizeof(unsigned long long) * ftkb_ctx::NSLOTS);
+  if ((e = cudaHostAlloc(&c->h_ring, sizeof(unsigned long long) * 8 * ftkb_ctx::RING, cudaHostAllocMapped | cudaHostAllocPortable)) != cudaSuccess) return bail("cudaHostAlloc(ring) failed", FTKB_ERR_NOMEM);
+  std::memset(c->h_ring, 0xff, sizeof(unsigned long long) * 8 * ftkb_ctx::RING);
+  for (auto &es : c->dev)
+    for (auto &ev : es)
+      if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail(std::string("cudaEventCreate: ") + cudaGetErrorString(e), FTKB_ERR_CUDA);
+  if ((e = cudaEventCreateWithFlags(&c->ev_input, cudaEventDisableTiming)) != cudaSuccess) return bail(std::string("cudaEventCreate: ") + cudaGetErrorString(e), FTKB_ERR_CUDA);
+  if (const char *d = std::getenv("FTKB_DEFER")) c->defer = std::string(d) != "0";
   cudaMemsetAsync(c->d_scalars, 0, sizeof(unsigned long long) * ftkb_ctx::NSLOTS, c->stream);
   c->wl_cap = std::max<uint64_t>(1 << 16, c->ncore / 64);
+  if (const char *w = std::getenv("FTKB_WL_CAP")) c->wl_cap = std::max<uint64_t>(1, std::strtoull(w, nullptr, 10));   // tests: force the overflow path
   if ((e = cudaMalloc(&c->d_wl, sizeof(unsigned long long) * c->wl_cap)) != cudaSuccess) return bail("cudaMalloc(worklist) failed", FTKB_ERR_NOMEM);
   c->pt_cap = cfg->point_capacity ? cfg->point_capacity : (1 << 18);
   if ((e = cudaMalloc(&c->d_pts, sizeof(ftkb_point) * c->pt_cap)) != cudaSuccess) return bail("cudaMalloc(points) failed", FTKB_ERR_NOMEM);
@@ -269,6 +316,7 @@ static int queue_resolution(ftkb_ctx *c, Layer &l, bool fused_in_gradient) {
   c->stats.kernel_launches += fused_in_gradient ? 0 : 1;
   CK(cudaMemcpyAsync(c->h_scalars + l.slot, c->d_scalars + l.slot, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
   c->stats.d2h_bytes += 8;
+  c->push_d2h_outstanding = true;
   return check_launch(c, "resolution");
 }
 
@@ -325,9 +373,17 @@ extern "C" int ftkb_push_snapshot(ftkb_ctx *c, const double *scalar, const doubl
   if (c->cfg.vector_source == FTKB_SOURCE_DERIVED && !vector && !scalar) return fail(c, FTKB_ERR_INVALID, "push: vector field is DERIVED but no scalar array was passed");
   if (c->cfg.jacobian_source == FTKB_SOURCE_GIVEN && !jacobian) return fail(c, FTKB_ERR_INVALID, "push: jacobian is GIVEN but no jacobian array was passed");
   CK(cudaSetDevice(c->cfg.device));
+  for (const double *q : {scalar, vector, jacobian})
+    if ((uintptr_t)q % 8 != 0) return fail(c, FTKB_ERR_INVALID, "push: arrays must be 8-byte aligned");
   Layer l;
   int rc = new_layer(c, l);
   if (rc) return rc;
+  if (where != FTKB_MEM_HOST && c->has_producer) {
+    // device inputs are written by the caller's stream: everything this context enqueues from here on runs after the
+    // work queued there so far (the context's own stream is non-blocking: the legacy default stream orders nothing)
+    CK(cudaEventRecord(c->ev_input, c->producer));
+    CK(cudaStreamWaitEvent(c->stream, c->ev_input, 0));
+  }
   const size_t nS = c->nvert, nV = c->nvert * c->n, nJ = c->nvert * c->n * c->n;
   auto ingest = [&](const double *src, size_t count, std::vector<double *> &pool, double **dst, bool *own) -> int {
     if (!src) return FTKB_OK;
@@ -343,8 +399,16 @@ extern "C" int ftkb_push_snapshot(ftkb_ctx *c, const double *scalar, const doubl
   if ((rc = ingest(vector, nV, c->freeV, &l.V, &l.ownV))) { release_layer(c, l); return rc; }
   if ((rc = ingest(jacobian, nJ, c->freeJ, &l.J, &l.ownJ))) { release_layer(c, l); return rc; }
   if ((rc = derive_layer(c, l))) { release_layer(c, l); return rc; }
-  if (where == FTKB_MEM_HOST) CK(cudaStreamSynchronize(c->stream));   // host buffers are borrowed only until return
+  // copied inputs (host or device) are borrowed only until return: the caller may free or overwrite them right away
+  if (where != FTKB_MEM_DEVICE_BORROW) CK(cudaStreamSynchronize(c->stream));
   c->layers.push_back(l);
+  return FTKB_OK;
+}
+
+extern "C" int ftkb_set_producer_stream(ftkb_ctx *c, void *stream, int enable) {
+  if (!c) return FTKB_ERR_INVALID;
+  c->producer = reinterpret_cast<cudaStream_t>(stream);
+  c->has_producer = enable != 0;
   return FTKB_OK;
 }
 
@@ -364,7 +428,7 @@ extern "C" int ftkb_push_synthetic(ftkb_ctx *c, int kind, const double *params, 
   int rc = new_layer(c, l);
   if (rc) return rc;
   double **dst = vector_kind ? &l.V : &l.S;
-  if ((rc = take_buffer(c, vector_kind ? c->freeV : c->freeS, vector_kind ? c->nvert * c->n : c->nvert, dst))) return rc;
+  if ((rc = take_buffer(c, vector_kind ? c->freeV : c->freeS, vector_kind ? c->nvert * c->n : c->nvert, dst))) { release_layer(c, l); return rc; }
   (vector_kind ? l.ownV : l.ownS) = true;
   launch_synthetic(kind, c->n, c->cfg.dims[0], c->cfg.dims[1], c->n == 3 ? c->cfg.dims[2] : 1, p, t, *dst, c->stream);
   c->stats.kernel_launches++;
@@ -385,6 +449,7 @@ extern "C" int ftkb_last_layer_resolution(ftkb_ctx *c, double *res) {
   if (!c || !res) return FTKB_ERR_INVALID;
   if (c->layers.empty()) return fail(c, FTKB_ERR_INVALID, "last_layer_resolution: no resident snapshot");
   CK(cudaSetDevice(c->cfg.device));
+  { const int rc = drain(c); if (rc) return rc; }
   Layer &l = c->layers.back();
   if (l.res_pending) {
     const int rc = resolve_pending(c, l);
@@ -397,6 +462,11 @@ extern "C" int ftkb_last_layer_resolution(ftkb_ctx *c, double *res) {
 
 extern "C" int ftkb_set_resolution(ftkb_ctx *c, double res) {
   if (!c) return FTKB_ERR_INVALID;
+  if (!c->pend.empty()) {           // applies to the sweeps that follow, not to those in flight
+    cudaSetDevice(c->cfg.device);
+    const int rc = drain(c);
+    if (rc) return rc;
+  }
   if (res > 0 && res < c->resolution) c->resolution = res;
   return FTKB_OK;
 }
@@ -437,6 +507,7 @@ extern "C" int ftkb_set_coords(ftkb_ctx *c, int mode, const double *data, uint64
   if (mode == FTKB_COORDS_RECTILINEAR && n != W + H + D) return fail(c, FTKB_ERR_INVALID, "set_coords: rectilinear coordinates take W + H [+ D] values");
   if (mode == FTKB_COORDS_EXPLICIT && (n % (W * H) != 0 || n / (W * H) < (c->n == 3 ? 3u : 2u)))
     return fail(c, FTKB_ERR_INVALID, "set_coords: explicit coordinates are (ncomp, W, H) with ncomp >= nd");
+  { const int rc = drain(c); if (rc) return rc; }
   CK(cudaStreamSynchronize(c->stream));
   cudaFree(c->d_coords);
   c->d_coords = nullptr;
@@ -549,6 +620,7 @@ static int materialise_gradient(ftkb_ctx *c, Layer &l) {
   l.res_pending = false;
   CK(cudaMemcpyAsync(c->h_scalars + l.slot, c->d_scalars + l.slot, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
   c->stats.d2h_bytes += 8;
+  c->push_d2h_outstanding = true;
   return check_launch(c, "gradient");
 }
 
@@ -568,6 +640,7 @@ static bool rows_aligned16(const ftkb_ctx *c, const double *a, const double *b) 
 
 // resolution of a layer whose vector field is derived on the fly, outside a sweep (time-slab exchange)
 static int resolve_pending(ftkb_ctx *c, Layer &l) {
+  c->primed = false;
   CK(cudaMemsetAsync(c->d_scalars + l.slot, 0xff, sizeof(unsigned long long), c->stream));   // (a pending layer's device slot is reset lazily)
   if (l.V) {          // vector input: the plain resolution pass
     l.res_pending = false;
@@ -629,16 +702,19 @@ static int resolve_pending(ftkb_ctx *c, Layer &l) {
   CK(cudaMemcpyAsync(c->h_scalars + l.slot, c->d_scalars + l.slot, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
   c->stats.d2h_bytes += 8;
   l.res_pending = false;
+  c->push_d2h_outstanding = true;
   return check_launch(c, "resolution (fused)");
 }
 
 // ref: critical_point_tracker_{2d,3d}_regular::update_timestep (xl == NONE branch)
 // grow(), critical_point_tracker_2d_regular.hh:288-329 / ..._3d_regular.hh:173-200: the punctured simplices found since
 // the last grow step (the reference clears discrete_critical_points after each) go to the host-side online tracer
-static void wait_grow(ftkb_ctx *c) {
-  if (!c->grow_task.valid()) return;
+static int wait_grow(ftkb_ctx *c) {
+  if (!c->grow_task.valid()) return c->grow_failed ? FTKB_ERR_NOMEM : FTKB_OK;
   try { c->stats.ms_finalize_host += c->grow_task.get(); }
-  catch (const std::exception &e) { c->error = std::string("streaming grow step: ") + e.what(); }
+  catch (const std::bad_alloc &) { c->grow_failed = true; return fail(c, FTKB_ERR_NOMEM, "streaming grow step: out of memory (trajectories are incomplete)"); }
+  catch (const std::exception &e) { c->grow_failed = true; return fail(c, FTKB_ERR_INVALID, std::string("streaming grow step: ") + e.what()); }
+  return c->grow_failed ? FTKB_ERR_NOMEM : FTKB_OK;
 }
 
 static int grow_trajectories(ftkb_ctx *c) {
@@ -650,7 +726,7 @@ static int grow_trajectories(ftkb_ctx *c) {
     CK(cudaStreamSynchronize(c->stream));
     c->stats.d2h_bytes += sizeof(ftkb_point) * n;
   }
-  wait_grow(c);                  // grow steps run in order
+  { const int rc = wait_grow(c); if (rc) return rc; }                  // grow steps run in order
   ftkb::OnlineTracer *tracer = c->online.get();
   auto work = [tracer](std::vector<ftkb_point> b) {
     const auto t0 = std::chrono::steady_clock::now();
@@ -663,7 +739,11 @@ static int grow_trajectories(ftkb_ctx *c) {
   // (profiles/r01f_stream_timing.md), so async stays opt-in until that is understood.
   static const bool async_grow = [] { const char *e = std::getenv("FTKB_STREAM_GROW"); return e && std::string(e) == "async"; }();
   if (async_grow) c->grow_task = std::async(std::launch::async, work, std::move(batch));
-  else c->stats.ms_finalize_host += work(std::move(batch));
+  else {
+    try { c->stats.ms_finalize_host += work(std::move(batch)); }
+    catch (const std::bad_alloc &) { c->grow_failed = true; return fail(c, FTKB_ERR_NOMEM, "streaming grow step: out of memory (trajectories are incomplete)"); }
+    catch (const std::exception &e) { c->grow_failed = true; return fail(c, FTKB_ERR_INVALID, std::string("streaming grow step: ") + e.what()); }
+  }
   c->grown = c->npts;
   c->traced = false;
   return FTKB_OK;
@@ -672,17 +752,134 @@ static int grow_trajectories(ftkb_ctx *c) {
 extern "C" int ftkb_set_streaming_trajectories(ftkb_ctx *c, int enable) {
   if (!c) return FTKB_ERR_INVALID;
   if (c->stats.scan_launches || c->npts) return fail(c, FTKB_ERR_INVALID, "set_streaming_trajectories: call it before the first update_timestep");
-  wait_grow(c);
+  (void)wait_grow(c);
   c->streaming = enable != 0;
+  c->grow_failed = false;
   c->online.reset(c->streaming ? new ftkb::OnlineTracer(c->n, c->cfg.lb, c->cfg.ub) : nullptr);
   c->grown = 0;
   return FTKB_OK;
 }
 
+// ---- deferred steps: confirmation, replay ------------------------------------------------------------------------
+static int update_impl(ftkb_ctx *c, bool allow_defer);
+static int abandon_fused3d(ftkb_ctx *c);
+
+static void absorb_resolutions(ftkb_ctx *c, const ftkb_ctx::Pending &pd) {
+  const volatile unsigned long long *r = c->h_ring + 8 * pd.ring;
+  if (r[5] != pd.seq) return;
+  for (int k = 0; k < 2; k++)
+    if (pd.res_slots[k] >= 0) {
+      c->h_scalars[pd.res_slots[k]] = r[3 + k];
+      c->resolution = std::min(c->resolution, slot_value(c, pd.res_slots[k]));
+    }
+}
+
+// the oldest enqueued step failed (a buffer overflowed, or the scan met values its keys cannot order): everything that
+// was enqueued is discarded and redone synchronously, with the popped layers put back for the duration
+static int replay(ftkb_ctx *c, bool poison) {
+  CK(cudaStreamSynchronize(c->stream));
+  for (const auto &pd : c->pend) absorb_resolutions(c, pd);      // a scan's min |v| is valid whatever happened to the counters
+  std::vector<int> pops;
+  for (const auto &pd : c->pend) pops.push_back(pd.pops);
+  const uint64_t npts0 = c->pend.front().npts_before;
+  c->pend.clear();
+  c->primed = false;
+  while (!c->limbo.empty()) {
+    c->layers.push_front(c->limbo.back());
+    c->limbo.pop_back();
+    c->current_timestep--;
+  }
+  c->npts = npts0;
+  c->stats.points = npts0;
+  c->sorted = false;
+  c->traced = false;
+  if (poison) {
+    if (c->cfg.vector_source == FTKB_SOURCE_GIVEN) {
+      c->cellsV = false;
+      for (Layer &l : c->layers) l.cells_valid = false;
+    } else if (c->n == 3) {
+      const int rc = abandon_fused3d(c);
+      if (rc) return rc;
+    } else {
+      c->keys2d = false;
+      for (Layer &l : c->layers) l.cells_valid = false;
+    }
+  }
+  c->stats.sweeps_repeated += pops.size();
+  for (size_t i = 0; i < pops.size(); i++) {
+    const int rc = update_impl(c, false);
+    if (rc) return rc;
+    for (int j = 0; j < pops[i] && !c->layers.empty(); j++) {
+      release_layer(c, c->layers.front());
+      c->layers.pop_front();
+      c->current_timestep++;
+    }
+  }
+  return FTKB_OK;
+}
+
+static int confirm_front(ftkb_ctx *c) {
+  const ftkb_ctx::Pending pd = c->pend.front();
+  CK(cudaEventSynchronize(c->dev[pd.evset][2]));
+  const volatile unsigned long long *r = c->h_ring + 8 * pd.ring;
+  if (r[5] != pd.seq) return fail(c, FTKB_ERR_CUDA, "deferred step: the test kernel did not publish its counters");
+  const uint64_t nwl = r[0], npt = r[1];
+  const bool poison = r[2] != 0;
+  c->stats.d2h_bytes += 48;
+  absorb_resolutions(c, pd);
+  // the step ran with the factor known when it was enqueued; the layers it resolved may have lowered the running minimum
+  // (critical_point_tracker.hh:850-864) -- then it, and whatever was enqueued behind it, is redone with the right factor
+  const bool stale = nbits_of(c->resolution) != pd.nbits;
+  if (poison || stale || nwl > c->wl_cap || npt > c->pt_cap) return replay(c, poison);
+  c->nbits = pd.nbits;
+  c->factor = (double)(uint64_t)(1 << pd.nbits);
+  float ms_scan = 0, ms_test = 0;
+  CK(cudaEventElapsedTime(&ms_scan, c->dev[pd.evset][0], c->dev[pd.evset][1]));
+  CK(cudaEventElapsedTime(&ms_test, c->dev[pd.evset][1], c->dev[pd.evset][2]));
+  c->stats.ms_scan += ms_scan; c->stats.ms_test += ms_test; c->stats.last_ms_scan = ms_scan;
+  c->stats.scan_launches++;
+  c->stats.cells_scanned += c->ncore;
+  c->stats.cells_refined += nwl;
+  c->last_wl = nwl;
+  c->wl_hint = nwl;
+  c->stats.simplices_tested += c->ncore * (uint64_t)(c->n_ord + (pd.has_next ? c->n_int : 0));
+  if (npt != c->npts) { c->sorted = false; c->traced = false; }
+  c->npts = npt;
+  c->stats.points = npt;
+  for (int j = 0; j < pd.pops && !c->limbo.empty(); j++) {
+    release_layer(c, c->limbo.front());
+    c->limbo.pop_front();
+  }
+  c->pend.pop_front();
+  if (!c->pend.empty()) c->pend.front().npts_before = c->npts;
+  return FTKB_OK;
+}
+
+// confirm every enqueued step (any call that needs results, or that touches the stream's state, starts here)
+static int drain(ftkb_ctx *c) {
+  while (!c->pend.empty()) {
+    const int rc = confirm_front(c);
+    if (rc) return rc;
+  }
+  return FTKB_OK;
+}
+
+static int test_grid(const ftkb_ctx *c) {
+  const uint64_t ntypes = c->n == 2 ? 12 : 60;
+  const uint64_t want = ((c->wl_hint * 2 + 256) * ntypes + 127) / 128;
+  return (int)std::max<uint64_t>(8, std::min<uint64_t>(want, (uint64_t)c->sm_count * 8));
+}
+
 extern "C" int ftkb_update_timestep(ftkb_ctx *c) {
   if (!c) return FTKB_ERR_INVALID;
+  return update_impl(c, c->defer);
+}
+
+static int update_impl(ftkb_ctx *c, bool allow_defer) {
   if (c->layers.empty()) return fail(c, FTKB_ERR_INVALID, "update_timestep: no snapshot has been pushed");
   CK(cudaSetDevice(c->cfg.device));
+  bool may_defer = allow_defer && !c->streaming && !c->push_d2h_outstanding;
+  if (!may_defer) { const int rc = drain(c); if (rc) return rc; }
   if (c->n == 3 && c->fused3d && c->cfg.vector_source == FTKB_SOURCE_DERIVED) {
     // a layer whose pointer TMA cannot take was materialised at push time: the sweep cannot mix the two forms
     bool anyV = false, anyS = false;
@@ -693,14 +890,21 @@ extern "C" int ftkb_update_timestep(ftkb_ctx *c) {
     // layers pushed while the fused 3D path was still on (it was abandoned since): materialise their gradient
     bool any = false;
     for (Layer &l : c->layers)
-      if (!l.V && l.S && c->cfg.vector_source == FTKB_SOURCE_DERIVED) { const int rc = materialise_gradient(c, l); if (rc) return rc; any = true; }
-    if (any) CK(cudaStreamSynchronize(c->stream));
+      if (!l.V && l.S && c->cfg.vector_source == FTKB_SOURCE_DERIVED) {
+        int rc = drain(c);
+        if (!rc) rc = materialise_gradient(c, l);
+        if (rc) return rc;
+        any = true;
+      }
+    if (any) { CK(cudaStreamSynchronize(c->stream)); may_defer = false; }
   }
   const bool fused = !c->layers[0].V && c->layers[0].S && c->cfg.vector_source == FTKB_SOURCE_DERIVED && (c->n == 2 || c->fused3d);
   if (!c->layers[0].V && !fused) return fail(c, FTKB_ERR_INVALID, "update_timestep: the snapshot has no vector field");
   if (c->current_timestep + 1 >= (1 << KEY_TIME_BITS)) return fail(c, FTKB_ERR_OVERFLOW, "update_timestep: timestep exceeds the element id range");
-  CK(cudaSetDevice(c->cfg.device));
-  CK(cudaStreamSynchronize(c->stream));   // resolutions of layers derived at push time are on the host now
+  if (c->push_d2h_outstanding) {
+    CK(cudaStreamSynchronize(c->stream));   // resolutions of layers derived at push time are on the host now
+    c->push_d2h_outstanding = false;
+  }
   // derive timing of the most recent gradient launch
   if (c->derive_timed) {
     float ms = 0;
@@ -711,7 +915,7 @@ extern "C" int ftkb_update_timestep(ftkb_ctx *c) {
   const bool has_next = c->layers.size() >= 2;
   if (has_next && !c->layers[1].V && !(fused && c->layers[1].S)) return fail(c, FTKB_ERR_INVALID, "update_timestep: the next snapshot has no vector field");
   // vector input: the range-cell scan streams each layer once and produces its min |v|; layers it cannot take now
-  // (misaligned, or pushed further ahead than this sweep reads) get the plain resolution pass
+  // (pushed further ahead than this sweep reads) get the plain resolution pass
   bool vcells = !fused && c->cellsV && c->layers[0].V && c->cfg.vector_source == FTKB_SOURCE_GIVEN;
   for (size_t k = 0; vcells && k < (has_next ? 2u : 1u); k++)
     if (!c->layers[k].V || (uintptr_t)c->layers[k].V % 16 != 0) vcells = false;
@@ -719,9 +923,14 @@ extern "C" int ftkb_update_timestep(ftkb_ctx *c) {
     bool any = false;
     for (size_t k = 0; k < c->layers.size(); k++) {
       Layer &l = c->layers[k];
-      if (l.V && l.res_pending && !(vcells && k < 2)) { const int rc = resolve_pending(c, l); if (rc) return rc; any = true; }
+      if (l.V && l.res_pending && !(vcells && k < 2)) {
+        int rc = drain(c);
+        if (!rc) rc = resolve_pending(c, l);
+        if (rc) return rc;
+        any = true;
+      }
     }
-    if (any) CK(cudaStreamSynchronize(c->stream));
+    if (any) { CK(cudaStreamSynchronize(c->stream)); c->push_d2h_outstanding = false; may_defer = false; }
   }
   if (has_next && fused && c->layers[1].V) return fail(c, FTKB_ERR_INVALID, "update_timestep: resident snapshots mix derived and given vector fields");
   // ref: critical_point_tracker.hh:850-864 (running minimum over every resident snapshot, every sweep).
@@ -753,8 +962,9 @@ extern "C" int ftkb_update_timestep(ftkb_ctx *c) {
   p.poison = c->d_scalars + ftkb_ctx::SLOT_POISON;
   if (fused && c->n == 3) {
     if (!encode_scalar_tmap3d(lay[0]->S, p.W, p.H, p.D, &p.tmap[0]) || !encode_scalar_tmap3d(lay[1]->S, p.W, p.H, p.D, &p.tmap[1])) {
-      const int rc = abandon_fused3d(c);      // no TMA descriptor (driver entry point or alignment): unfused path
-      return rc ? rc : ftkb_update_timestep(c);
+      int rc = drain(c);
+      if (!rc) rc = abandon_fused3d(c);      // no TMA descriptor (driver entry point or alignment): unfused path
+      return rc ? rc : update_impl(c, allow_defer);
     }
     fused3d_decomposition(c, p);
   } else if (fused) {
@@ -783,8 +993,87 @@ extern "C" int ftkb_update_timestep(ftkb_ctx *c) {
       p.nsz = (p.nc[2] + p.rows - 1) / p.rows;
     }
   }
-  p.wl_count = c->d_scalars + ftkb_ctx::SLOT_WL;
+  p.keys2d = c->keys2d;
   p.pt_count = c->d_scalars + ftkb_ctx::SLOT_PT;
+  p.ticket = c->d_scalars + ftkb_ctx::SLOT_TICKET;
+  p.test_blocks = test_grid(c);
+  const bool cells_path = vcells || (fused && ((c->n == 3 && c->cells3d) || (c->n == 2 && c->cells2d && p.bulk >= 2)));
+  void (*launch_cells)(const SweepParams &, cudaStream_t) = vcells ? launch_vscan_cells : (c->n == 3 ? launch_scan3d_cells : launch_scan2d_cells);
+
+  // ---- deferred step: enqueue and return; the previous one is confirmed behind it ------------------------------------
+  if (may_defer && cells_path && lay[0]->cells_valid && !p.no_filter) {
+    if (has_next && !lay[1]->cells) {
+      const bool pool = !c->freeCells.empty();
+      if (!pool) { const int rc = drain(c); if (rc) return rc; }     // cudaMalloc would stall behind the queued work anyway
+      const int rc0 = ensure_cells(c, *lay[1], p);
+      if (rc0) return rc0;
+    }
+    p.nbits = nbits;
+    p.factor = (double)(uint64_t)(1 << nbits);
+    p.thrp_f = (float)((1.0 / p.factor) * (1.0 + 1.0 / 1048576.0));
+    p.thr2_f = (float)(2.0 / p.factor);
+    p.lim_f = (float)(0.999 * 4.5e18 / (p.factor * p.factor));
+    ftkb_ctx::Pending pd;
+    pd.seq = ++c->step_seq;
+    pd.ring = (int)(pd.seq % ftkb_ctx::RING);
+    pd.evset = (int)(pd.seq & 1);
+    pd.has_next = has_next;
+    pd.nbits = nbits;
+    pd.npts_before = c->npts;                 // exact for the oldest enqueued step (set again when it becomes the oldest)
+    p.res_slot[0] = p.res_slot[1] = nullptr;
+    for (int k = 0; k < (has_next ? 2 : 1); k++)
+      if (lay[k]->res_pending) {
+        p.res_slot[k] = c->d_scalars + lay[k]->slot;
+        pd.res_slots[k] = lay[k]->slot;
+        lay[k]->res_pending = false;          // this scan produces it; the value reaches the host at confirmation
+      }
+    p.wl = c->d_wl; p.wl_cap = c->wl_cap;
+    p.pts = c->d_pts; p.pt_cap = c->pt_cap;
+    p.wl_count = c->d_scalars + (c->wl_sel ? ftkb_ctx::SLOT_WL2 : ftkb_ctx::SLOT_WL);
+    p.wl_count_next = c->d_scalars + (c->wl_sel ? ftkb_ctx::SLOT_WL : ftkb_ctx::SLOT_WL2);
+    p.step_out = c->h_ring + 8 * pd.ring;     // pinned + mapped, unified addressing: the device writes it in place
+    p.step_seq = pd.seq;
+    // the layer the NEXT step resolves: resident already, or the next one to be pushed
+    const int next_slot = c->layers.size() >= 3 ? c->layers[2].slot : c->next_slot;
+    p.res_reset = c->d_scalars + next_slot;
+    if (!c->primed) {
+      // first deferred step after a synchronous one: arm the device counters once from the host mirror
+      c->h_scalars[ftkb_ctx::SLOT_WL] = 0;
+      c->h_scalars[ftkb_ctx::SLOT_WL2] = 0;
+      c->h_scalars[ftkb_ctx::SLOT_PT] = c->npts;
+      c->h_scalars[ftkb_ctx::SLOT_UQ] = 0;
+      c->h_scalars[ftkb_ctx::SLOT_POISON] = 0;
+      c->h_scalars[ftkb_ctx::SLOT_TICKET] = 0;
+      CK(cudaMemcpyAsync(c->d_scalars, c->h_scalars, 14 * sizeof(unsigned long long), cudaMemcpyHostToDevice, c->stream));
+    }
+    CK(cudaEventRecord(c->dev[pd.evset][0], c->stream));
+    p.sum_in[0] = lay[0]->cells; p.sum_in[1] = lay[1]->cells;
+    if (has_next && !lay[1]->cells_valid) {
+      p.sum_mode = SUM_BUILD_TEST2; p.build_layer = 1; p.sum_out = lay[1]->cells;
+      lay[1]->cells_valid = true;
+    } else {
+      p.sum_mode = has_next ? SUM_TEST2 : SUM_TEST1;
+    }
+    launch_cells(p, c->stream);
+    CK(cudaEventRecord(c->dev[pd.evset][1], c->stream));
+    launch_test(p, c->stream);
+    CK(cudaEventRecord(c->dev[pd.evset][2], c->stream));
+    c->stats.kernel_launches += 2;
+    const int rc = check_launch(c, "sweep");
+    if (rc) return rc;
+    c->pend.push_back(pd);
+    c->primed = true;
+    c->wl_sel ^= 1;
+    while (c->pend.size() > 1) {
+      const int rc2 = confirm_front(c);
+      if (rc2) return rc2;
+    }
+    return FTKB_OK;
+  }
+  { const int rc = drain(c); if (rc) return rc; }
+  c->primed = false;
+  p.wl_count = c->d_scalars + ftkb_ctx::SLOT_WL;
+  p.step_out = nullptr;
 
   for (int attempt = 0; attempt < 12; attempt++) {
     p.nbits = nbits;
@@ -799,16 +1088,18 @@ extern "C" int ftkb_update_timestep(ftkb_ctx *c) {
         if (lay[k]->res_pending) { p.res_slot[k] = c->d_scalars + lay[k]->slot; pending = true; }
     p.wl = c->d_wl; p.wl_cap = c->wl_cap;
     p.pts = c->d_pts; p.pt_cap = c->pt_cap;
+    p.test_blocks = test_grid(c);
     c->h_scalars[ftkb_ctx::SLOT_WL] = 0;
     c->h_scalars[ftkb_ctx::SLOT_PT] = c->npts;
     c->h_scalars[ftkb_ctx::SLOT_UQ] = 0;
     c->h_scalars[ftkb_ctx::SLOT_POISON] = 0;
+    c->h_scalars[ftkb_ctx::SLOT_WL2] = 0;
+    c->h_scalars[ftkb_ctx::SLOT_TICKET] = 0;
     // one copy resets the counters AND the resolution slots of the layers this sweep resolves (host mirror = all ones)
-    CK(cudaMemcpyAsync(c->d_scalars, c->h_scalars, 12 * sizeof(unsigned long long), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->d_scalars, c->h_scalars, 14 * sizeof(unsigned long long), cudaMemcpyHostToDevice, c->stream));
     CK(cudaEventRecord(c->ev[0], c->stream));
-    if (vcells || (fused && ((c->n == 3 && c->cells3d) || (c->n == 2 && c->cells2d && p.bulk >= 2)))) {
+    if (cells_path) {
       // each layer is streamed once (the step that first sees it); everything else reads its 16-byte range cells
-      void (*launch_cells)(const SweepParams &, cudaStream_t) = vcells ? launch_vscan_cells : (c->n == 3 ? launch_scan3d_cells : launch_scan2d_cells);
       int rc0 = ensure_cells(c, *lay[0], p);
       if (!rc0 && has_next) rc0 = ensure_cells(c, *lay[1], p);
       if (rc0) return rc0;
@@ -853,13 +1144,20 @@ extern "C" int ftkb_update_timestep(ftkb_ctx *c) {
       c->stats.sweeps_repeated++;
       c->cellsV = false;
       for (Layer &l : c->layers) l.cells_valid = false;
-      return ftkb_update_timestep(c);
+      return update_impl(c, false);
     }
     if (fused && c->n == 3 && c->h_scalars[ftkb_ctx::SLOT_POISON]) {
       // a scalar was NaN / Inf / >= 2^1000: the fused scan's keys cannot bracket such values; redo the step unfused
       c->stats.sweeps_repeated++;
       const int rc2 = abandon_fused3d(c);
-      return rc2 ? rc2 : ftkb_update_timestep(c);
+      return rc2 ? rc2 : update_impl(c, false);
+    }
+    if (fused && c->n == 2 && c->h_scalars[ftkb_ctx::SLOT_POISON]) {
+      // 2D key scan: a scalar was NaN / Inf / >= 2^1000; the fp32-range build kernel handles those (slower)
+      c->stats.sweeps_repeated++;
+      c->keys2d = false;
+      for (Layer &l : c->layers) l.cells_valid = false;
+      return update_impl(c, false);
     }
     float ms_scan = 0, ms_test = 0;
     CK(cudaEventElapsedTime(&ms_scan, c->ev[0], c->ev[1]));
@@ -880,11 +1178,13 @@ extern "C" int ftkb_update_timestep(ftkb_ctx *c) {
       }
     }
     const uint64_t nwl = c->h_scalars[ftkb_ctx::SLOT_WL], npt = c->h_scalars[ftkb_ctx::SLOT_PT];
+    c->wl_hint = std::min<uint64_t>(nwl, c->wl_cap);
     if (nwl > c->wl_cap) {           // worklist overflow: grow and redo the step (inputs are still resident)
       cudaFree(c->d_wl);
       c->d_wl = nullptr;
       c->wl_cap = nwl + nwl / 8 + 1024;
       CK(cudaMalloc(&c->d_wl, sizeof(unsigned long long) * c->wl_cap));
+      c->wl_hint = nwl;
       c->stats.sweeps_repeated++;
       continue;
     }
@@ -914,7 +1214,13 @@ extern "C" int ftkb_advance_timestep(ftkb_ctx *c) {
   const int rc = ftkb_update_timestep(c);
   if (rc) return rc;
   if (!c->layers.empty()) {
-    release_layer(c, c->layers.front());
+    if (!c->pend.empty()) {
+      // an enqueued step still reads this layer: it is released when that step has been confirmed
+      c->limbo.push_back(c->layers.front());
+      c->pend.back().pops++;
+    } else {
+      release_layer(c, c->layers.front());
+    }
     c->layers.pop_front();
   }
   c->current_timestep++;
@@ -938,8 +1244,9 @@ static void fill_trace_params(const ftkb_ctx *c, TraceParams &tp) {
 // sort the punctured simplices by element order and drop duplicates (std::map semantics of the
 // reference's discrete_critical_points, critical_point_tracker_regular.hh:13-38)
 static int ensure_sorted(ftkb_ctx *c) {
-  if (c->sorted) return FTKB_OK;
   CK(cudaSetDevice(c->cfg.device));
+  { const int rc = drain(c); if (rc) return rc; }
+  if (c->sorted) return FTKB_OK;
   cudaFree(c->d_pts_sorted); c->d_pts_sorted = nullptr;
   cudaFree(c->d_keys_sorted); c->d_keys_sorted = nullptr;
   c->pts_sorted.clear();
@@ -1008,6 +1315,8 @@ extern "C" int ftkb_import_points(ftkb_ctx *c, const ftkb_point *pts, uint64_t n
   if (c->streaming) return fail(c, FTKB_ERR_INVALID, "import_points: not available with streaming trajectories");
   if (!n) return FTKB_OK;
   CK(cudaSetDevice(c->cfg.device));
+  { const int rc = drain(c); if (rc) return rc; }
+  c->primed = false;
   if (c->npts + n > c->pt_cap) {
     const int rc = grow_points(c, c->npts + n);
     if (rc) return rc;
@@ -1025,8 +1334,10 @@ extern "C" int ftkb_import_points(ftkb_ctx *c, const ftkb_point *pts, uint64_t n
 // ref: critical_point_tracker.hh:668-817 trace_critical_points_offline; cc2curves.hh:10-122
 extern "C" int ftkb_finalize(ftkb_ctx *c) {
   if (!c) return FTKB_ERR_INVALID;
+  int rc = drain(c);
+  if (rc) return rc;
   if (c->traced) return FTKB_OK;
-  int rc = ensure_sorted(c);
+  rc = ensure_sorted(c);
   if (rc) return rc;
   const uint64_t n = c->nsorted;
   c->labels.assign(n, 0);
@@ -1036,7 +1347,7 @@ extern "C" int ftkb_finalize(ftkb_ctx *c) {
   c->traj_loop.clear();
   c->traj_complete.clear();
   if (c->streaming) {
-    wait_grow(c);
+    { const int rc2 = wait_grow(c); if (rc2) return rc2; }
     // "done" (critical_point_tracker_2d_regular.hh:150-151): publish the grown trajectories, in id order, as CSR over
     // the sorted points; the component labels / degrees of the offline trace are not computed
     const auto t0 = std::chrono::steady_clock::now();
@@ -1211,6 +1522,8 @@ extern "C" int ftkb_ipc_close(void *dev_ptr, const ftkb_ipc_handle *h) {
 extern "C" int ftkb_export_layer_cells(ftkb_ctx *c, int index, void **cells, uint64_t *bytes, double *resolution) {
   if (!c || !cells || !bytes) return FTKB_ERR_INVALID;
   if (index < 0 || (size_t)index >= c->layers.size()) return fail(c, FTKB_ERR_INVALID, "export_layer_cells: no such resident layer");
+  { const int rc = drain(c); if (rc) return rc; }
+  if ((size_t)index >= c->layers.size()) return fail(c, FTKB_ERR_INVALID, "export_layer_cells: no such resident layer");
   Layer &l = c->layers[index];
   if (!l.cells || !l.cells_valid) return fail(c, FTKB_ERR_INVALID, "export_layer_cells: the layer has no range cells yet (a sweep must have read it)");
   CK(cudaSetDevice(c->cfg.device));
@@ -1227,6 +1540,8 @@ extern "C" int ftkb_push_snapshot_remote(ftkb_ctx *c, const double *scalar, cons
   if (c->cfg.jacobian_source == FTKB_SOURCE_GIVEN) return fail(c, FTKB_ERR_INVALID, "push_snapshot_remote: a GIVEN jacobian cannot be remote");
   if (c->cfg.vector_source == FTKB_SOURCE_GIVEN ? !vector : !scalar) return fail(c, FTKB_ERR_INVALID, "push_snapshot_remote: the field the sweep reads is missing");
   CK(cudaSetDevice(c->cfg.device));
+  if ((uintptr_t)scalar % 8 != 0 || (uintptr_t)vector % 8 != 0 || (uintptr_t)cells % 16 != 0)
+    return fail(c, FTKB_ERR_INVALID, "push_snapshot_remote: arrays must be 8-byte aligned, cells 16-byte aligned");
   Layer l;
   int rc = new_layer(c, l);
   if (rc) return rc;
@@ -1276,6 +1591,7 @@ extern "C" int ftkb_get_degrees(ftkb_ctx *c, int32_t *deg) {
 extern "C" int ftkb_get_last_worklist(ftkb_ctx *c, uint64_t *out, uint64_t cap, uint64_t *n) {
   if (!c || !n || (!out && cap)) return FTKB_ERR_INVALID;
   CK(cudaSetDevice(c->cfg.device));
+  { const int rc = drain(c); if (rc) return rc; }
   CK(cudaStreamSynchronize(c->stream));
   const uint64_t have = std::min<uint64_t>(c->last_wl, c->wl_cap);
   *n = have;
@@ -1286,7 +1602,12 @@ extern "C" int ftkb_get_last_worklist(ftkb_ctx *c, uint64_t *out, uint64_t cap, 
 
 extern "C" int ftkb_get_stats(ftkb_ctx *c, ftkb_stats *out) {
   if (!c || !out) return FTKB_ERR_INVALID;
-  wait_grow(c);
+  if (!c->pend.empty()) {
+    cudaSetDevice(c->cfg.device);
+    const int rc = drain(c);
+    if (rc) return rc;
+  }
+  { const int rc = wait_grow(c); if (rc) return rc; }
   c->stats.scaling_factor = c->factor;
   c->stats.resolution = c->resolution;
   *out = c->stats;
@@ -1295,7 +1616,12 @@ extern "C" int ftkb_get_stats(ftkb_ctx *c, ftkb_stats *out) {
 
 extern "C" int ftkb_reset_stats(ftkb_ctx *c) {
   if (!c) return FTKB_ERR_INVALID;
-  wait_grow(c);
+  if (!c->pend.empty()) {
+    cudaSetDevice(c->cfg.device);
+    const int rc = drain(c);
+    if (rc) return rc;
+  }
+  { const int rc = wait_grow(c); if (rc) return rc; }
   const uint64_t pts = c->stats.points;
   c->stats = ftkb_stats{};
   c->stats.points = pts;
@@ -1305,9 +1631,9 @@ extern "C" int ftkb_reset_stats(ftkb_ctx *c) {
 extern "C" int ftkb_synchronize(ftkb_ctx *c) {
   if (!c) return FTKB_ERR_INVALID;
   CK(cudaSetDevice(c->cfg.device));
+  { const int rc = drain(c); if (rc) return rc; }
   CK(cudaStreamSynchronize(c->stream));
-  wait_grow(c);
-  return FTKB_OK;
+  return wait_grow(c);
 }
 
 extern "C" int ftkb_timer_start(ftkb_ctx *c) {

@@ -134,6 +134,13 @@ __global__ void __launch_bounds__(256) scan2d_kernel(const SweepParams p) {
   const int nbits20 = p.nbits << 20;
   const int4 *__restrict__ V0 = reinterpret_cast<const int4 *>(p.L[0].V);
   const int4 *__restrict__ V1 = reinterpret_cast<const int4 *>(p.L[1].V);
+  // a borrowed layer may be 8-byte aligned only: such a launch reads the two high words with 4-byte loads
+  const bool al16 = (((uintptr_t)p.L[0].V | (uintptr_t)p.L[1].V) & 15) == 0;
+  auto load_hi = [&](const int4 *V, const size_t i) -> int2 {
+    if (al16) { const int4 a = __ldg(V + i); return make_int2(a.y, a.w); }
+    const int *q = reinterpret_cast<const int *>(V) + 4 * i;
+    return make_int2(__ldg(q + 1), __ldg(q + 3));
+  };
 
   KeyRange px = neutral_range(), py = neutral_range();   // previous row, already merged over t and x..x+1
 #pragma unroll 2
@@ -141,13 +148,13 @@ __global__ void __launch_bounds__(256) scan2d_kernel(const SweepParams p) {
     KeyRange rx = neutral_range(), ry = neutral_range();
     if (col_ok && y <= p.vmax[1]) {
       const size_t i = (size_t)x + (size_t)p.W * (size_t)y;
-      const int4 a = __ldg(V0 + i);
-      rx = vertex_range(a.y, nbits20);
-      ry = vertex_range(a.w, nbits20);
+      const int2 a = load_hi(V0, i);
+      rx = vertex_range(a.x, nbits20);
+      ry = vertex_range(a.y, nbits20);
       if (HAS_NEXT) {
-        const int4 b = __ldg(V1 + i);
-        rx = merge(rx, vertex_range(b.y, nbits20));
-        ry = merge(ry, vertex_range(b.w, nbits20));
+        const int2 b = load_hi(V1, i);
+        rx = merge(rx, vertex_range(b.x, nbits20));
+        ry = merge(ry, vertex_range(b.y, nbits20));
       }
     }
     rx = merge(rx, shfl_down1(rx));
@@ -3012,11 +3019,32 @@ __global__ void __launch_bounds__(128) test_kernel(const __grid_constant__ Sweep
       }
     }
   }
+  if (p.step_out == nullptr) return;
+  // deferred step: the last block to finish publishes the counters to the host (mapped memory) and re-arms the
+  // device-side counters for the next step -- no copy, memset or host round trip sits between two sweeps
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  __threadfence();
+  if (atomicAdd(p.ticket, 1ull) != (u64)gridDim.x - 1) return;
+  __threadfence();
+  volatile unsigned long long *out = p.step_out;
+  out[0] = *(volatile unsigned long long *)p.wl_count;
+  out[1] = *(volatile unsigned long long *)p.pt_count;
+  out[2] = *(volatile unsigned long long *)p.poison;
+  out[3] = p.res_slot[0] ? *(volatile unsigned long long *)p.res_slot[0] : ~0ull;
+  out[4] = p.res_slot[1] ? *(volatile unsigned long long *)p.res_slot[1] : ~0ull;
+  out[5] = p.step_seq;
+  *p.ticket = 0;
+  *p.poison = 0;
+  *p.wl_count_next = 0;
+  if (p.res_reset) *p.res_reset = ~0ull;
+  __threadfence_system();
 }
 
 void launch_test(const SweepParams &p, cudaStream_t s) {
-  // the number of surviving cubes is only known on the device: fixed grid, grid-stride loop
-  const unsigned grid = 148 * 8;
+  // the number of surviving cubes is only known on the device: grid sized by the caller from the previous step's count,
+  // grid-stride loop over whatever the scan really left
+  const unsigned grid = (unsigned)(p.test_blocks > 0 ? p.test_blocks : 148 * 8);
   if (p.nd == 2) test_kernel<2><<<grid, 128, 0, s>>>(p);
   else test_kernel<3><<<grid, 128, 0, s>>>(p);
 }

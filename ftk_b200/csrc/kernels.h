@@ -39,6 +39,7 @@ struct SweepParams {
   // fused mode: the vector field is derived from the scalar layers on the fly (L[].V == nullptr)
   int32_t fused;
   int32_t aligned16;          // rows of S start 16-byte aligned (W even, base aligned): vector loads allowed
+  int32_t keys2d;             // 2D scalar build: high-word keys of the differences instead of fp32 ranges (scan2d_keys_build_kernel)
   int32_t bulk;               // row staging with cp.async.bulk + mbarrier (needs aligned16): 2 = CTA-wide ring + producer warp, 1 = per-warp rings, 0 = registers
   float thrp_f;               // 2^-nbits (1 + 2^-20): approx(v) >= thrp_f  =>  |quantised v| >= 1
   float thr2_f;               // 2^(1-nbits)
@@ -65,6 +66,15 @@ struct SweepParams {
   unsigned long long *pt_count;
   unsigned long long pt_cap;
   ftkb_point *pts;
+  // deferred step (context.cpp, "sync-free step"): the test kernel's last block publishes the step's counters into
+  // mapped host memory and re-arms the device counters for the next step, so that the host never has to touch the
+  // stream between two sweeps.  step_out == nullptr: the host resets / reads the counters itself (synchronous step).
+  unsigned long long *step_out;      // mapped pinned host memory: {worklist count, point count, poison, res[0], res[1], sequence}
+  unsigned long long step_seq;
+  unsigned long long *ticket;        // blocks of the test kernel that are done
+  unsigned long long *wl_count_next; // the next step's worklist counter (zeroed here)
+  unsigned long long *res_reset;     // resolution slot of the layer the next step resolves (set to all ones), or nullptr
+  int32_t test_blocks;               // grid of the test kernel (grid-stride: any worklist size is covered)
 };
 
 void upload_mesh_tables(const DeviceMeshTables &t2, const DeviceMeshTables &t3);

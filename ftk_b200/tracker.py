@@ -77,6 +77,7 @@ class _RegularTracker:
         self._resolution_init = 0.0
         self._streaming = False
         self._coords = None
+        self._point_capacity = 0
         self._keep = []   # borrowed device arrays stay referenced while resident
 
     # ---- configuration (same names as the reference) ------------------------------------------
@@ -167,7 +168,7 @@ class _RegularTracker:
         cfg.start_timestep = self._start_timestep
         cfg.device = self._device
         cfg.resolution_init = self._resolution_init
-        cfg.point_capacity = 0
+        cfg.point_capacity = int(self._point_capacity)
         h = C.c_void_p()
         rc = L.lib().ftkb_create(C.byref(cfg), C.byref(h))
         if rc:
@@ -232,13 +233,30 @@ class _RegularTracker:
             where = kind
         if where == L.MEM_DEVICE_BORROW:
             self._keep.append(hold)
-            self._keep = self._keep[-4:]
+            self._keep = self._keep[-6:]          # a borrowed layer is read until its sweeps are confirmed (ftkb200.h)
+        if where in (L.MEM_DEVICE, L.MEM_DEVICE_BORROW):
+            self._order_after_producer(hold)
+        # copied arrays (host, or device without borrow) are consumed before the call returns; `hold` lives until then
         self._check(L.lib().ftkb_push_snapshot(self._h, ptrs[0], ptrs[1], ptrs[2], where if where is not None else L.MEM_HOST))
 
-    def push_device_pointers(self, scalar=0, vector=0, jacobian=0):
+    def _order_after_producer(self, arrays):
+        """device inputs: make the context's stream wait for the stream that (may still be) writing them -- torch's current
+        stream for torch tensors (ftkb_set_producer_stream); other producers synchronise before pushing"""
+        stream = None
+        for a in arrays:
+            if getattr(a, "is_cuda", False) and hasattr(a, "data_ptr"):
+                import torch
+                stream = int(torch.cuda.current_stream(a.device).cuda_stream)
+        if stream is not None:
+            self._check(L.lib().ftkb_set_producer_stream(self._h, C.c_void_p(stream), 1))
+
+    def push_device_pointers(self, scalar=0, vector=0, jacobian=0, stream=None):
         """Raw device pointers (ints), used in place (FTKB_MEM_DEVICE_BORROW): the thinnest wrapper over
         ftkb_push_snapshot for callers that keep their time series resident in HBM.  The arrays must stay
-        valid and unchanged until two advance_timestep() calls later."""
+        valid and unchanged until three advance_timestep() calls later (or synchronize()).  stream: the CUDA stream
+        (int handle) that produced them, if it has not been synchronised."""
+        if stream is not None:
+            self._check(L.lib().ftkb_set_producer_stream(self._h, C.c_void_p(int(stream)), 1))
         self._check(L.lib().ftkb_push_snapshot(self._h, scalar or None, vector or None, jacobian or None, L.MEM_DEVICE_BORROW))
 
     def export_layer_cells(self, index=0):
@@ -297,12 +315,27 @@ class _RegularTracker:
         out = np.zeros(n.value, L.POINT_DTYPE)
         if n.value:
             self._check(L.lib().ftkb_get_points(self._h, out.ctypes.data, n.value))
+        starts = self._array_domain.starts if self._array_domain is not None else []
+        if n.value and any(starts):
+            # the library works in array-relative indices; the reference's positions are absolute
+            # (regular_tracker.hh:24-30; the C++ shim does the same in to_feature_point)
+            for j, s0 in enumerate(starts):
+                out["corner"][:, j] += s0
+                if self._coords is None:
+                    out["x"][:, j] += float(s0)
         return out
 
     get_critical_points = get_discrete_critical_points
 
     def import_points(self, pts):
         pts = np.ascontiguousarray(pts, dtype=L.POINT_DTYPE)
+        starts = self._array_domain.starts if self._array_domain is not None else []
+        if len(pts) and any(starts):          # back to the library's array-relative indices (see get_discrete_critical_points)
+            pts = pts.copy()
+            for j, s0 in enumerate(starts):
+                pts["corner"][:, j] -= s0
+                if self._coords is None:
+                    pts["x"][:, j] -= float(s0)
         self._check(L.lib().ftkb_import_points(self._h, pts.ctypes.data, len(pts)))
 
     def get_trajectory_index(self):
@@ -377,7 +410,7 @@ class critical_point_tracker_3d_regular(_RegularTracker):
 
 def make_tracker(dims, field="scalar", lb=None, ub=None, jacobian_symmetric=None, robust=True, compute_degrees=False,
                  type_filter=None, start_timestep=0, device=0, resolution_init=0.0,
-                 scalar_source=None, vector_source=None, jacobian_source=None, streaming=False, coords=None):
+                 scalar_source=None, vector_source=None, jacobian_source=None, streaming=False, coords=None, point_capacity=0):
     """Configure a tracker the way the reference's front ends do (json_interface.hh:634-656):
     scalar input -> lattice({2,..}, {D-3,..}) = [2, D-2], derived gradient/Hessian, symmetric;
     vector input -> lattice({1,..}, {D-2,..}) = [1, D-2], derived Jacobian, non-symmetric."""
@@ -402,6 +435,7 @@ def make_tracker(dims, field="scalar", lb=None, ub=None, jacobian_symmetric=None
     tr.set_start_timestep(start_timestep)
     tr.set_initial_resolution(resolution_init)
     tr.set_enable_streaming_trajectories(streaming)
+    tr._point_capacity = int(point_capacity)      # initial size of the punctured-simplex buffer (grows on demand)
     if coords is not None:      # ("bounds" | "rectilinear" | "explicit", flat data in the reference's order)
         tr._coords = ({"bounds": L.COORDS_BOUNDS, "rectilinear": L.COORDS_RECTILINEAR, "explicit": L.COORDS_EXPLICIT}[coords[0]],
                       np.ascontiguousarray(coords[1], np.float64).ravel())

@@ -52,10 +52,17 @@ enum { FTKB_SOURCE_NONE = 0, FTKB_SOURCE_GIVEN = 1, FTKB_SOURCE_DERIVED = 2 };
 /* where the pointers handed to ftkb_push_snapshot live */
 enum {
   FTKB_MEM_HOST = 0,          /* host memory; copied to the device before the call returns */
-  FTKB_MEM_DEVICE = 1,        /* device memory on the context's device; copied (D2D) */
-  FTKB_MEM_DEVICE_BORROW = 2  /* device memory used in place: must stay valid and unchanged until the
-                                 layer has been popped (two ftkb_advance_timestep calls later) */
+  FTKB_MEM_DEVICE = 1,        /* device memory on the context's device; copied (D2D) before the call returns */
+  FTKB_MEM_DEVICE_BORROW = 2  /* device memory used in place: must stay valid and unchanged until the sweeps that
+                                 read the layer have been confirmed -- three ftkb_advance_timestep calls after the
+                                 push, or the next ftkb_synchronize / ftkb_get_stats / result getter (steps are
+                                 enqueued without a host round trip, see ftkb_update_timestep) */
 };
+/* Device inputs and streams.  The context runs on its own non-blocking stream.  A device array handed to
+ * ftkb_push_snapshot must be complete when the context reads it: either the caller synchronises the stream that wrote
+ * it before the push, or it names that stream once with ftkb_set_producer_stream(ctx, stream, 1) -- every device push
+ * then records an event there and makes the context's stream wait for it (stream = NULL with enable = 1 is the legacy
+ * default stream).  enable = 0 turns the ordering off again.  Arrays must be 8-byte aligned. */
 
 /* synthetic generators of ftkb_push_synthetic (ref: include/ftk/ndarray/synthetic.hh) */
 enum {
@@ -129,6 +136,7 @@ const char *ftkb_last_error(const ftkb_ctx *);   /* ctx may be NULL: last create
  * Arrays are dim-0-fastest: scalar (W,H[,D]); vector (n,W,H[,D]); jacobian (n,n,W,H[,D]).
  * A pointer may be NULL when its source is NONE or DERIVED. */
 int ftkb_push_snapshot(ftkb_ctx *, const double *scalar, const double *vector, const double *jacobian, int where);
+int ftkb_set_producer_stream(ftkb_ctx *, void *cuda_stream, int enable);
 /* device-side generator for snapshot time `t` (benchmarks; no host data involved) */
 int ftkb_push_synthetic(ftkb_ctx *, int kind, const double *params, int nparams, double t);
 
@@ -144,6 +152,12 @@ int ftkb_push_synthetic(ftkb_ctx *, int kind, const double *params, int nparams,
 enum { FTKB_COORDS_SIMPLE = 0, FTKB_COORDS_BOUNDS = 1, FTKB_COORDS_RECTILINEAR = 2, FTKB_COORDS_EXPLICIT = 3 };
 int ftkb_set_coords(ftkb_ctx *, int mode, const double *data, uint64_t n);
 
+/* Sync-free steps: ftkb_update_timestep only ENQUEUES the sweep and returns; its counters are published by the device
+ * into mapped host memory and read when the NEXT step has been enqueued, or by any call that needs results
+ * (ftkb_get_stats, ftkb_synchronize, ftkb_finalize, the getters).  A step that ran with a stale quantisation factor
+ * (the layer it resolved lowered the running minimum, critical_point_tracker.hh:850-864) or whose buffers overflowed
+ * is replayed synchronously, so results never depend on the mode.  Streaming trajectories, non-robust 3D detection and
+ * the two-layer scans run every step synchronously; FTKB_DEFER=0 in the environment does so for all. */
 int ftkb_update_timestep(ftkb_ctx *);    /* critical_point_tracker_{2d,3d}_regular::update_timestep */
 int ftkb_advance_timestep(ftkb_ctx *);   /* critical_point_tracker.hh:841-848 */
 int ftkb_finalize(ftkb_ctx *);           /* trace_critical_points_offline, critical_point_tracker.hh:668-817 */

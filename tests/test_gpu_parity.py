@@ -476,3 +476,47 @@ def test_time_slab_halo_through_peer_memory(dims, field, ftk, oracle):
     P.assert_same_result(cuda_result(merged), want, tol=0.0, what="peer-memory halo")
     for t in (whole, merged):
         t.close()
+
+
+# ---- sync-free (deferred) steps: results never depend on the mode -------------------------------------------------
+def _woven_series(oracle, dims, T):
+    return list(oracle.synthetic_series("woven", dims, T, None))
+
+
+@pytest.mark.parametrize("mode", ["deferred", "sync"])
+def test_deferred_steps_equal_synchronous_steps(mode, ftk, oracle, monkeypatch):
+    """FTKB_DEFER=0 confirms every step before returning; the default enqueues step k+1 before reading step k"""
+    monkeypatch.setenv("FTKB_DEFER", "0" if mode == "sync" else "1")
+    dims, T = [96, 80], 7
+    snaps = _woven_series(oracle, dims, T)
+    want = P.oracle_result(oracle.track(snaps, dims, field="scalar"))
+    tr = ftk.track(snaps, dims, field="scalar")
+    P.assert_same_result(cuda_result(tr), want, tol=TOL, what=f"woven {mode}")
+    st = tr.stats()
+    assert st["scan_launches"] >= T and st["simplices_tested"] == (94 * 78) * (12 * (T - 1) + 2)
+    tr.close()
+
+
+@pytest.mark.parametrize("what", ["points", "worklist"])
+def test_deferred_step_overflow_is_replayed(what, ftk, oracle, monkeypatch):
+    """a step whose output buffers overflow while the next one is already enqueued: both are discarded and redone"""
+    if what == "worklist":
+        monkeypatch.setenv("FTKB_WL_CAP", "5")
+    dims, T = [96, 80], 6
+    snaps = _woven_series(oracle, dims, T)
+    want = P.oracle_result(oracle.track(snaps, dims, field="scalar"))
+    tr = ftk.track(snaps, dims, field="scalar", point_capacity=7 if what == "points" else 0)
+    P.assert_same_result(cuda_result(tr), want, tol=TOL, what=f"overflow {what}")
+    assert tr.stats()["sweeps_repeated"] > 0
+    tr.close()
+
+
+def test_deferred_steps_3d_and_vector(ftk, oracle):
+    rng = np.random.default_rng(77)
+    for dims, T, field in (([34, 20, 12], 5, "scalar"), ([40, 36], 6, "vector"), ([18, 16, 10], 4, "vector")):
+        nv = 1 if field == "scalar" else len(dims)
+        snaps = _rand_series(rng, dims, T, nv, "smooth")
+        c, o = _both(ftk, oracle, snaps, dims, field)
+        P.assert_same_result(cuda_result(c), P.oracle_result(o), tol=TOL, what=f"deferred {dims} {field}")
+        assert c.stats()["scaling_factor"] == o.scaling_factor
+        c.close()
