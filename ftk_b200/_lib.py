@@ -75,7 +75,7 @@ EXPORTS = [
     "ftkb_curveset_get", "ftkb_curveset_last_error", "ftkb_curveset_slice",
     "ftkb_ipc_export", "ftkb_ipc_import", "ftkb_ipc_close", "ftkb_export_layer_cells", "ftkb_push_snapshot_remote",
     "ftkb_set_streaming_trajectories", "ftkb_get_trajectory_complete", "ftkb_online_create", "ftkb_online_destroy", "ftkb_online_grow",
-    "ftkb_online_size", "ftkb_online_get", "ftkb_set_coords", "ftkb_set_producer_stream",
+    "ftkb_online_size", "ftkb_online_get", "ftkb_set_coords", "ftkb_set_producer_stream", "ftkb_get_layer",
 ]
 
 _lib = None
@@ -140,6 +140,7 @@ def lib():
     L.ftkb_set_streaming_trajectories.argtypes = [vp, C.c_int]
     L.ftkb_set_coords.argtypes = [vp, C.c_int, vp, C.c_uint64]
     L.ftkb_set_producer_stream.argtypes = [vp, vp, C.c_int]
+    L.ftkb_get_layer.argtypes = [vp, C.c_int, vp, vp]
     L.ftkb_get_trajectory_complete.argtypes = [vp, vp]
     L.ftkb_online_create.argtypes = [C.c_int, vp, vp, C.POINTER(vp)]
     L.ftkb_online_destroy.argtypes = [vp]

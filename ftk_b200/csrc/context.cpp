@@ -74,10 +74,10 @@ struct ftkb_ctx {
   bool fused3d = false;          // 3D scalar input: gradient fused into the scan (TMA-staged); FTKB_SCAN3D=plain materialises the gradient instead
 
   // device scalars: [0..7] per-layer resolution bits, [8] worklist count, [9] point count, [10] unique count, [11] poison,
-  // [12] the second worklist counter (deferred steps alternate), [13] ticket of the test kernel's blocks
+  // [12] the second worklist counter (deferred steps alternate), [13] ticket of the test kernel's blocks, [14] second poison flag
   unsigned long long *d_scalars = nullptr;
   unsigned long long *h_scalars = nullptr;     // pinned mirror
-  static constexpr int SLOT_WL = 8, SLOT_PT = 9, SLOT_UQ = 10, SLOT_POISON = 11, SLOT_WL2 = 12, SLOT_TICKET = 13, NSLOTS = 16;
+  static constexpr int SLOT_WL = 8, SLOT_PT = 9, SLOT_UQ = 10, SLOT_POISON = 11, SLOT_WL2 = 12, SLOT_TICKET = 13, SLOT_POISON2 = 14, NSLOTS = 16;
 
   // ---- deferred ("sync-free") steps ------------------------------------------------------------------------------
   // ftkb_update_timestep enqueues scan + test and returns; the test kernel's last block publishes the counters into the
@@ -86,7 +86,7 @@ struct ftkb_ctx {
   // run with a stale quantisation factor, or whose buffers overflowed, is replayed synchronously together with
   // whatever was enqueued behind it.  Layers popped in between wait in `limbo`.
   struct Pending {
-    int ring = 0, evset = 0, pops = 0, nbits = 0;
+    int ring = 0, evset = 0, pops = 0, nbits = 0, wl_sel = 0;
     uint64_t seq = 0, npts_before = 0;
     bool has_next = false;
     int res_slots[2] = {-1, -1};     // resolution slots this step's scan fills
@@ -104,9 +104,14 @@ struct ftkb_ctx {
   uint64_t wl_hint = 1 << 16;        // surviving cubes expected by the next test kernel (sizes its grid)
   cudaEvent_t ev_input = nullptr;    // orders device inputs after their producer stream (ftkb_set_producer_stream)
   cudaStream_t producer = nullptr;
+  cudaStream_t stream2 = nullptr;    // deferred steps: the test kernels' stream
+  cudaEvent_t ev_join = nullptr;
+  bool overlap_test = true;          // FTKB_TEST_OVERLAP=0: test kernels stay on the sweep's stream
   bool has_producer = false;
 
-  unsigned long long *d_wl = nullptr;
+  unsigned long long *d_wl = nullptr;          // worklist of the synchronous steps and of the even deferred ones
+  unsigned long long *d_wl2 = nullptr;         // worklist of the odd deferred steps (a test kernel overlaps the next scan)
+  int last_wl_sel = 0;
   uint64_t wl_cap = 0, last_wl = 0;
   ftkb_point *d_pts = nullptr;
   uint64_t pt_cap = 0, npts = 0;
@@ -207,6 +212,9 @@ extern "C" void ftkb_destroy(ftkb_ctx *c) {
   for (auto &es : c->dev) for (auto &e : es) if (e) cudaEventDestroy(e);
   if (c->ev_input) cudaEventDestroy(c->ev_input);
   cudaFree(c->d_wl);
+  cudaFree(c->d_wl2);
+  if (c->stream2) { cudaStreamSynchronize(c->stream2); cudaStreamDestroy(c->stream2); }
+  if (c->ev_join) cudaEventDestroy(c->ev_join);
   cudaFree(c->d_pts);
   cudaFree(c->d_coords);
   cudaFree(c->d_pts_sorted);
@@ -292,6 +300,15 @@ extern "C" int ftkb_create(const ftkb_config *cfg, ftkb_ctx **out) {
   c->wl_cap = std::max<uint64_t>(1 << 16, c->ncore / 64);
   if (const char *w = std::getenv("FTKB_WL_CAP")) c->wl_cap = std::max<uint64_t>(1, std::strtoull(w, nullptr, 10));   // tests: force the overflow path
   if ((e = cudaMalloc(&c->d_wl, sizeof(unsigned long long) * c->wl_cap)) != cudaSuccess) return bail("cudaMalloc(worklist) failed", FTKB_ERR_NOMEM);
+  if ((e = cudaMalloc(&c->d_wl2, sizeof(unsigned long long) * c->wl_cap)) != cudaSuccess) return bail("cudaMalloc(worklist) failed", FTKB_ERR_NOMEM);
+  {
+    // the exact tests of deferred step k run on their own (high-priority) stream next to the scan of step k+1
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    if ((e = cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, hi)) != cudaSuccess) return bail(std::string("cudaStreamCreate: ") + cudaGetErrorString(e), FTKB_ERR_CUDA);
+    if ((e = cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming)) != cudaSuccess) return bail(std::string("cudaEventCreate: ") + cudaGetErrorString(e), FTKB_ERR_CUDA);
+    if (const char *o = std::getenv("FTKB_TEST_OVERLAP")) c->overlap_test = std::string(o) != "0";
+  }
   c->pt_cap = cfg->point_capacity ? cfg->point_capacity : (1 << 18);
   if ((e = cudaMalloc(&c->d_pts, sizeof(ftkb_point) * c->pt_cap)) != cudaSuccess) return bail("cudaMalloc(points) failed", FTKB_ERR_NOMEM);
   DeviceMeshTables t2, t3;
@@ -305,6 +322,11 @@ extern "C" int ftkb_create(const ftkb_config *cfg, ftkb_ctx **out) {
 }
 
 static int take_buffer(ftkb_ctx *c, std::vector<double *> &pool, size_t count, double **out) {
+  if (pool.empty() && !c->pend.empty()) {
+    // buffers of layers that enqueued steps still read come back once those steps are confirmed
+    const int rc = drain(c);
+    if (rc) return rc;
+  }
   if (!pool.empty()) { *out = pool.back(); pool.pop_back(); return FTKB_OK; }
   CK(cudaMalloc(out, sizeof(double) * count));
   return FTKB_OK;
@@ -778,6 +800,7 @@ static void absorb_resolutions(ftkb_ctx *c, const ftkb_ctx::Pending &pd) {
 // was enqueued is discarded and redone synchronously, with the popped layers put back for the duration
 static int replay(ftkb_ctx *c, bool poison) {
   CK(cudaStreamSynchronize(c->stream));
+  CK(cudaStreamSynchronize(c->stream2));
   for (const auto &pd : c->pend) absorb_resolutions(c, pd);      // a scan's min |v| is valid whatever happened to the counters
   std::vector<int> pops;
   for (const auto &pd : c->pend) pops.push_back(pd.pops);
@@ -841,6 +864,7 @@ static int confirm_front(ftkb_ctx *c) {
   c->stats.cells_scanned += c->ncore;
   c->stats.cells_refined += nwl;
   c->last_wl = nwl;
+  c->last_wl_sel = pd.wl_sel;
   c->wl_hint = nwl;
   c->stats.simplices_tested += c->ncore * (uint64_t)(c->n_ord + (pd.has_next ? c->n_int : 0));
   if (npt != c->npts) { c->sorted = false; c->traced = false; }
@@ -1027,15 +1051,20 @@ static int update_impl(ftkb_ctx *c, bool allow_defer) {
         pd.res_slots[k] = lay[k]->slot;
         lay[k]->res_pending = false;          // this scan produces it; the value reaches the host at confirmation
       }
-    p.wl = c->d_wl; p.wl_cap = c->wl_cap;
+    pd.wl_sel = c->wl_sel;
+    p.wl = c->wl_sel ? c->d_wl2 : c->d_wl; p.wl_cap = c->wl_cap;
     p.pts = c->d_pts; p.pt_cap = c->pt_cap;
+    // worklist, its counter and the poison flag alternate between two sets: the test kernel of this step may still run
+    // (on stream2) while the scan of the next step fills the other set; each test kernel re-arms its own set when done
     p.wl_count = c->d_scalars + (c->wl_sel ? ftkb_ctx::SLOT_WL2 : ftkb_ctx::SLOT_WL);
-    p.wl_count_next = c->d_scalars + (c->wl_sel ? ftkb_ctx::SLOT_WL : ftkb_ctx::SLOT_WL2);
+    p.poison = c->d_scalars + (c->wl_sel ? ftkb_ctx::SLOT_POISON2 : ftkb_ctx::SLOT_POISON);
     p.step_out = c->h_ring + 8 * pd.ring;     // pinned + mapped, unified addressing: the device writes it in place
     p.step_seq = pd.seq;
-    // the layer the NEXT step resolves: resident already, or the next one to be pushed
-    const int next_slot = c->layers.size() >= 3 ? c->layers[2].slot : c->next_slot;
-    p.res_reset = c->d_scalars + next_slot;
+    // resolution slots are handed out in push order: the layer the scan of step k+1 / k+2 resolves sits 2 / 3 places
+    // behind the current front, resident already or still to be pushed.  This step's test kernel re-arms the slot for
+    // step k+2 (step k+1's scan may already be running by then; its slot was re-armed by the previous test kernel).
+    auto slot_at = [&](size_t idx) { return idx < c->layers.size() ? c->layers[idx].slot : (int)((c->next_slot + (idx - c->layers.size())) % 8); };
+    p.res_reset = c->d_scalars + slot_at(3);
     if (!c->primed) {
       // first deferred step after a synchronous one: arm the device counters once from the host mirror
       c->h_scalars[ftkb_ctx::SLOT_WL] = 0;
@@ -1043,8 +1072,10 @@ static int update_impl(ftkb_ctx *c, bool allow_defer) {
       c->h_scalars[ftkb_ctx::SLOT_PT] = c->npts;
       c->h_scalars[ftkb_ctx::SLOT_UQ] = 0;
       c->h_scalars[ftkb_ctx::SLOT_POISON] = 0;
+      c->h_scalars[ftkb_ctx::SLOT_POISON2] = 0;
       c->h_scalars[ftkb_ctx::SLOT_TICKET] = 0;
-      CK(cudaMemcpyAsync(c->d_scalars, c->h_scalars, 14 * sizeof(unsigned long long), cudaMemcpyHostToDevice, c->stream));
+      if (c->layers.size() < 3) c->h_scalars[slot_at(2)] = ~0ull;      // the layer the next step's scan resolves (not pushed yet)
+      CK(cudaMemcpyAsync(c->d_scalars, c->h_scalars, 15 * sizeof(unsigned long long), cudaMemcpyHostToDevice, c->stream));
     }
     CK(cudaEventRecord(c->dev[pd.evset][0], c->stream));
     p.sum_in[0] = lay[0]->cells; p.sum_in[1] = lay[1]->cells;
@@ -1056,8 +1087,10 @@ static int update_impl(ftkb_ctx *c, bool allow_defer) {
     }
     launch_cells(p, c->stream);
     CK(cudaEventRecord(c->dev[pd.evset][1], c->stream));
-    launch_test(p, c->stream);
-    CK(cudaEventRecord(c->dev[pd.evset][2], c->stream));
+    cudaStream_t ts = c->overlap_test ? c->stream2 : c->stream;
+    if (c->overlap_test) CK(cudaStreamWaitEvent(c->stream2, c->dev[pd.evset][1], 0));
+    launch_test(p, ts);
+    CK(cudaEventRecord(c->dev[pd.evset][2], ts));
     c->stats.kernel_launches += 2;
     const int rc = check_launch(c, "sweep");
     if (rc) return rc;
@@ -1096,7 +1129,8 @@ static int update_impl(ftkb_ctx *c, bool allow_defer) {
     c->h_scalars[ftkb_ctx::SLOT_WL2] = 0;
     c->h_scalars[ftkb_ctx::SLOT_TICKET] = 0;
     // one copy resets the counters AND the resolution slots of the layers this sweep resolves (host mirror = all ones)
-    CK(cudaMemcpyAsync(c->d_scalars, c->h_scalars, 14 * sizeof(unsigned long long), cudaMemcpyHostToDevice, c->stream));
+    c->h_scalars[ftkb_ctx::SLOT_POISON2] = 0;
+    CK(cudaMemcpyAsync(c->d_scalars, c->h_scalars, 15 * sizeof(unsigned long long), cudaMemcpyHostToDevice, c->stream));
     CK(cudaEventRecord(c->ev[0], c->stream));
     if (cells_path) {
       // each layer is streamed once (the step that first sees it); everything else reads its 16-byte range cells
@@ -1180,10 +1214,11 @@ static int update_impl(ftkb_ctx *c, bool allow_defer) {
     const uint64_t nwl = c->h_scalars[ftkb_ctx::SLOT_WL], npt = c->h_scalars[ftkb_ctx::SLOT_PT];
     c->wl_hint = std::min<uint64_t>(nwl, c->wl_cap);
     if (nwl > c->wl_cap) {           // worklist overflow: grow and redo the step (inputs are still resident)
-      cudaFree(c->d_wl);
-      c->d_wl = nullptr;
+      cudaFree(c->d_wl); cudaFree(c->d_wl2);
+      c->d_wl = c->d_wl2 = nullptr;
       c->wl_cap = nwl + nwl / 8 + 1024;
       CK(cudaMalloc(&c->d_wl, sizeof(unsigned long long) * c->wl_cap));
+      CK(cudaMalloc(&c->d_wl2, sizeof(unsigned long long) * c->wl_cap));
       c->wl_hint = nwl;
       c->stats.sweeps_repeated++;
       continue;
@@ -1199,6 +1234,7 @@ static int update_impl(ftkb_ctx *c, bool allow_defer) {
     c->stats.cells_scanned += c->ncore;
     c->stats.cells_refined += nwl;
     c->last_wl = nwl;
+    c->last_wl_sel = 0;
     c->stats.simplices_tested += c->ncore * (uint64_t)(c->n_ord + (has_next ? c->n_int : 0));
     if (npt != c->npts) { c->sorted = false; c->traced = false; }
     c->npts = npt;
@@ -1596,7 +1632,21 @@ extern "C" int ftkb_get_last_worklist(ftkb_ctx *c, uint64_t *out, uint64_t cap, 
   const uint64_t have = std::min<uint64_t>(c->last_wl, c->wl_cap);
   *n = have;
   const uint64_t m = std::min(have, cap);
-  if (m) CK(cudaMemcpy(out, c->d_wl, sizeof(uint64_t) * m, cudaMemcpyDeviceToHost));
+  if (m) CK(cudaMemcpy(out, c->last_wl_sel ? c->d_wl2 : c->d_wl, sizeof(uint64_t) * m, cudaMemcpyDeviceToHost));
+  return FTKB_OK;
+}
+
+extern "C" int ftkb_get_layer(ftkb_ctx *c, int index, double *scalar, double *vector) {
+  if (!c || (!scalar && !vector)) return FTKB_ERR_INVALID;
+  CK(cudaSetDevice(c->cfg.device));
+  { const int rc = drain(c); if (rc) return rc; }
+  if (index < 0 || (size_t)index >= c->layers.size()) return fail(c, FTKB_ERR_INVALID, "get_layer: no such resident snapshot");
+  const Layer &l = c->layers[index];
+  if ((scalar && !l.S) || (vector && !l.V)) return fail(c, FTKB_ERR_INVALID, "get_layer: the snapshot does not hold that field");
+  CK(cudaStreamSynchronize(c->stream));
+  if (scalar) CK(cudaMemcpy(scalar, l.S, sizeof(double) * c->nvert, cudaMemcpyDeviceToHost));
+  if (vector) CK(cudaMemcpy(vector, l.V, sizeof(double) * c->nvert * c->n, cudaMemcpyDeviceToHost));
+  c->stats.d2h_bytes += sizeof(double) * c->nvert * ((scalar ? 1 : 0) + (vector ? c->n : 0));
   return FTKB_OK;
 }
 
@@ -1633,6 +1683,7 @@ extern "C" int ftkb_synchronize(ftkb_ctx *c) {
   CK(cudaSetDevice(c->cfg.device));
   { const int rc = drain(c); if (rc) return rc; }
   CK(cudaStreamSynchronize(c->stream));
+  CK(cudaStreamSynchronize(c->stream2));
   return wait_grow(c);
 }
 
@@ -1646,6 +1697,8 @@ extern "C" int ftkb_timer_start(ftkb_ctx *c) {
 extern "C" int ftkb_timer_stop(ftkb_ctx *c, double *ms) {
   if (!c || !ms) return FTKB_ERR_INVALID;
   CK(cudaSetDevice(c->cfg.device));
+  CK(cudaEventRecord(c->ev_join, c->stream2));      // the last test kernel belongs to the timed work
+  CK(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
   CK(cudaEventRecord(c->ev[7], c->stream));
   CK(cudaEventSynchronize(c->ev[7]));
   float f = 0;

@@ -250,6 +250,12 @@ __global__ void __launch_bounds__(32 * SCAN3_BY) scan3d_kernel(const SweepParams
 // over the WHOLE array -- which is why strips cover the array and not only the tracker's domain.
 struct FRange { float mn, mx; };
 
+// raw high word of an fp64 value read as fp32: an order-preserving key (sign | 11 exponent bits | 20 mantissa bits) for
+// magnitudes below 2^1017; FMNMX orders such keys like the values, NaN patterns (>= 2^1017, Inf, NaN) drop out
+constexpr int KEYF_BIG = 0x7E700000;     // high word of 2^1000
+constexpr int KEYF_NAN = 0x7FC00000;
+__device__ __forceinline__ float hikey(double d) { return __int_as_float(__double2hiint(d)); }
+
 __device__ __forceinline__ FRange fmerge(FRange a, FRange b) { return FRange{fminf(a.mn, b.mn), fmaxf(a.mx, b.mx)}; }
 __device__ __forceinline__ FRange fshfl_down1(FRange a) {
   return FRange{__shfl_down_sync(0xffffffffu, a.mn, 1), __shfl_down_sync(0xffffffffu, a.mx, 1)};
@@ -1097,6 +1103,251 @@ __global__ void __launch_bounds__(256) scan2d_cells_kernel(const __grid_constant
   cells2d_decide(p, ux, uy, own, e, y0, NL);
 }
 
+// ---- 2D, scalar input, range cells from high-word keys (default build kernel) -----------------------------------------
+// Same cells, same geometry and the same consumers as scan2d_build_kernel (cells kernel, cold path, peer export), but the
+// hot loop never converts fp64 to fp32: the raw high word of each fp64 difference d = S(x+1) - S(x-1) (not yet scaled by
+// W-1) is used as an order-preserving fp32 key (sign | 11 exponent bits | 20 mantissa bits read as a float: monotone in d
+// for |d| < 2^1017), so a row costs four DADD and four three-input FMNMX per lane.  Keys become conservative fp32 ranges of
+// v = d (W-1) once per cell block of 9 rows: a key truncates |d| towards zero, so bounds that must move away from zero take
+// the next key; key x (W-1) is exact in fp64 (21 x 31 significant bits), the final rounding is directed outwards.
+// Staging: ring of K2_NST stages of K2_R = 3 rows each (cp.async.bulk + full/empty mbarriers, one producer warp); a consumer
+// warp moves a whole stage into registers (3 x LDS.128 + 6 x LDS.64 through explicit shared-space loads) and releases it at
+// once, so a stage is busy for a few dozen cycles and the ring is almost always in flight.
+// Scalars >= 2^1000 / Inf / NaN cannot be ordered by the keys: they raise p.poison and the context redoes the step with
+// scan2d_build_kernel (fp32 ranges, handles them).
+constexpr int K2_R = 3;                                // rows per stage
+constexpr int K2_NST = 8;                              // ring stages (power of two); 85 KB per CTA, two CTAs per SM
+constexpr uint32_t K2_ROW_BYTES = TL_SEG * 8;
+constexpr uint32_t K2_STAGE_BYTES = K2_R * K2_ROW_BYTES;
+static_assert(C2_R % K2_R == 0 && (K2_NST & (K2_NST - 1)) == 0, "cell block = whole stages; ring index by mask");
+
+__device__ __forceinline__ double2 lds128_f64(uint32_t a) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ double lds64_f64(uint32_t a) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+  return v;
+}
+// max that keeps a NaN once it has seen one (FMNMX.NAN): the "magnitude too large for float keys" accumulator
+__device__ __forceinline__ float fmax_nan(float a, float b) {
+  float r;
+  asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+  return r;
+}
+
+struct K2Res { double m; float kx, ky; };   // running signed value of smallest non-zero magnitude + the key filters per component
+
+// exact (cold) update of the running min non-zero |v| with the four gradient values of one row, v = d * (W-1 | H-1) in fp64
+// as gradient2D computes them (grad.hh:24-27); afterwards kx / ky are keys no difference below the new minimum can exceed
+__device__ __noinline__ K2Res k2_res_update(K2Res r, bool e_in, bool o_in, double dxe, double dye, double dxo, double dyo, double cw, double ch) {
+  const double vxe = dxe * cw, vye = dye * ch, vxo = dxo * cw, vyo = dyo * ch;
+  double m = r.m;
+  if (e_in) {
+    if (vxe != 0.0 && fabs(vxe) < fabs(m)) m = vxe;     // NaN / Inf never compare below
+    if (vye != 0.0 && fabs(vye) < fabs(m)) m = vye;
+  }
+  if (o_in) {
+    if (vxo != 0.0 && fabs(vxo) < fabs(m)) m = vxo;
+    if (vyo != 0.0 && fabs(vyo) < fabs(m)) m = vyo;
+  }
+  K2Res out;
+  out.m = m;
+  if (fabs(m) < DBL_MAX) {
+    // |d| (W-1) < |m|  =>  |d| <= |m| / (W-1) (1 + 2^-52)  =>  hi(|d|) <= hi(|m| / (W-1)) + 1
+    out.kx = __int_as_float(__double2hiint(fabs(m) / cw) + 1);
+    out.ky = __int_as_float(__double2hiint(fabs(m) / ch) + 1);
+  } else {
+    out.kx = out.ky = __int_as_float(0x7F800000);       // nothing found yet: every key is a candidate
+  }
+  return out;
+}
+
+// conservative fp32 range of v = d * c over the values whose keys lie in [kmn, kmx]
+__device__ __forceinline__ FRange k2_vrange(float kmn, float kmx, double c) {
+  const int a = __float_as_int(kmn), b = __float_as_int(kmx);
+  const double lo = __hiloint2double(a < 0 ? a + 1 : a, 0);     // negative: the truncated key is too close to zero
+  const double hi = __hiloint2double(b < 0 ? b : b + 1, 0);     // positive: likewise
+  return FRange{__double2float_rd(lo * c), __double2float_ru(hi * c)};
+}
+
+template <bool BORDER, int NPREV, bool TEST>
+__device__ __forceinline__ void keys2d_strip(const SweepParams &p, const int c0, const int r0, const int r1, const int lane,
+                                             const uint32_t tile_u32 /* smem address of this warp's column c0-2, stage 0, row 0 */,
+                                             const uint32_t full0, const uint32_t empty0, const int strip) {
+  const int W = p.W, H = p.H, B = p.build_layer;
+  const int e = c0 + 2 * lane, o = e + 1;
+  const bool e_in = !BORDER || e < W, o_in = !BORDER || o < W, o1_in = !BORDER || o + 1 < W;
+  const bool own_cols = lane <= 30 && ((e >= p.lb[0] && e <= p.ub[0]) || (o >= p.lb[0] && o <= p.ub[0]));
+  const int jl = r1 + 1;                              // last gradient row visited
+  const int nrows = jl - r0 + 1;                      // gradient rows r0 .. jl; ring rows 0 .. nrows+1 hold array rows r0-1 .. jl+1
+  const int ngroups = (nrows + K2_R - 1) / K2_R, nstages = (nrows + 2 + K2_R - 1) / K2_R;
+  const double cw = (double)(W - 1), ch = (double)(H - 1);
+  const bool want_res = p.res_slot[B] != nullptr;
+  K2Res res{DBL_MAX, __int_as_float(0x7F800000), __int_as_float(0x7F800000)};
+  float big = 0.f;
+  const float inff_ = __int_as_float(0x7F800000);
+  const uint4 *sum_prev = NPREV ? p.sum_in[0] + cells2d_index(p, strip, 0, lane) : nullptr;
+  uint4 *sum_out = p.sum_out + cells2d_index(p, strip, 0, lane);
+  const uint32_t lane_u32 = tile_u32 + (uint32_t)lane * 16u;    // +8: column e-1, +16: e, o, +32: o+1
+
+  // a block of C2_R corner rows is complete: x-neighbour merge on the keys, keys -> fp32 ranges of v, store the cell, test
+  auto finish_block = [&](const int kb, float xmn, float xmx, float ymn, float ymx, const uint4 prevc) {
+    xmn = fminf(xmn, __shfl_down_sync(0xffffffffu, xmn, 1)); xmx = fmaxf(xmx, __shfl_down_sync(0xffffffffu, xmx, 1));
+    ymn = fminf(ymn, __shfl_down_sync(0xffffffffu, ymn, 1)); ymx = fmaxf(ymx, __shfl_down_sync(0xffffffffu, ymx, 1));
+    FRange bx = k2_vrange(xmn, xmx, cw), by = k2_vrange(ymn, ymx, ch);
+    sum_out[(size_t)kb * 32u] = make_uint4(__float_as_uint(bx.mn), __float_as_uint(bx.mx), __float_as_uint(by.mn), __float_as_uint(by.mx));
+    if (TEST) {
+      if (NPREV) {
+        bx = fmerge(bx, FRange{__uint_as_float(prevc.x), __uint_as_float(prevc.y)});
+        by = fmerge(by, FRange{__uint_as_float(prevc.z), __uint_as_float(prevc.w)});
+      }
+      const int y0 = kb * C2_R;
+      const bool own = own_cols && y0 <= p.ub[1] && y0 + C2_R - 1 >= p.lb[1];
+      cells2d_decide(p, bx, by, own, e, y0, NPREV + 1);
+    }
+  };
+
+  // two register sets of one stage each: centre columns (e, o) and x neighbours (e-1, o+1) of its three rows
+  double C[2][K2_R][2], N[2][K2_R][2];
+  auto load_stage = [&](auto PC, const int s) {
+    constexpr int P = decltype(PC)::value;
+    const uint32_t slot = (uint32_t)s & (K2_NST - 1);
+    mbar_wait(full0 + 8u * slot, (uint32_t)(s / K2_NST) & 1u);
+    const uint32_t base = lane_u32 + slot * K2_STAGE_BYTES;
+#pragma unroll
+    for (int i = 0; i < K2_R; i++) {
+      const double2 c = lds128_f64(base + (uint32_t)i * K2_ROW_BYTES + 16u);
+      C[P][i][0] = c.x; C[P][i][1] = c.y;
+      N[P][i][0] = lds64_f64(base + (uint32_t)i * K2_ROW_BYTES + 8u);
+      N[P][i][1] = lds64_f64(base + (uint32_t)i * K2_ROW_BYTES + 32u);
+    }
+#pragma unroll
+    for (int i = 0; i < K2_R; i++) {
+      const float ke = fabsf(hikey(C[P][i][0])), ko = fabsf(hikey(C[P][i][1]));
+      big = fmax_nan(big, BORDER ? (e_in ? ke : 0.f) : ke);
+      big = fmax_nan(big, BORDER ? (o_in ? ko : 0.f) : ko);
+    }
+    __syncwarp();
+    if (elect_one()) mbar_arrive(empty0 + 8u * slot);   // the stage lives in registers now
+  };
+
+  float bxmn = 0.f, bxmx = 0.f, bymn = 0.f, bymx = 0.f;
+  uint4 prevc = make_uint4(0x7FC00000u, 0x7FC00000u, 0x7FC00000u, 0x7FC00000u);
+  int kb = r0 / C2_R;                                  // the block the next row with K == 0 opens
+
+  // group g = gradient rows r0 + 3 g + {0, 1, 2}; ring row q holds array row r0 - 1 + q, gradient row r0 + q reads ring rows
+  // q (below), q + 1 (centre, x neighbours), q + 2 (above).  PC: register set of stage g; KC: (3 g) mod 9.
+  auto group = [&](auto PC, auto KC, const int g) {
+    constexpr int P = decltype(PC)::value, K0 = decltype(KC)::value;
+    if (g + 1 < nstages) load_stage(IC<1 - P>{}, g + 1);
+#pragma unroll
+    for (int i = 0; i < K2_R; i++) {
+      const int j = r0 + K2_R * g + i;
+      if (j > jl) break;
+      constexpr int dummy = 0; (void)dummy;
+      const double *m1 = C[P][i];
+      const double *cv = i + 1 < K2_R ? C[P][i + 1] : C[1 - P][i + 1 - K2_R];
+      const double *nb = i + 1 < K2_R ? N[P][i + 1] : N[1 - P][i + 1 - K2_R];
+      const double *p1 = i + 2 < K2_R ? C[P][i + 2] : C[1 - P][i + 2 - K2_R];
+      double left = nb[0], right = nb[1], mid_e = cv[1];
+      if (BORDER) {
+        if (e == 0) left = cv[0];
+        if (!o_in) mid_e = cv[0];
+        if (!o1_in) right = cv[1];
+      }
+      const double dxe = mid_e - left, dxo = right - cv[0], dye = p1[0] - m1[0], dyo = p1[1] - m1[1];
+      const float kxe = hikey(dxe), kxo = hikey(dxo), kye = hikey(dye), kyo = hikey(dyo);
+      if (want_res && j < H) {
+        float ax = fminf(fabsf(kxe), fabsf(kxo)), ay = fminf(fabsf(kye), fabsf(kyo));
+        if (BORDER) {
+          ax = fminf(e_in ? fabsf(kxe) : inff_, o_in ? fabsf(kxo) : inff_);
+          ay = fminf(e_in ? fabsf(kye) : inff_, o_in ? fabsf(kyo) : inff_);
+        }
+        if (ax <= res.kx || ay <= res.ky) res = k2_res_update(res, e_in, o_in, dxe, dye, dxo, dyo, cw, ch);
+      }
+      if ((K0 + i) % C2_R == 0) {
+        // gradient row C2_R k closes block k-1 and opens block k
+        const float rxmn = fminf(kxe, kxo), rxmx = fmaxf(kxe, kxo), rymn = fminf(kye, kyo), rymx = fmaxf(kye, kyo);
+        if (j > r0) finish_block(kb - 1, fminf(bxmn, rxmn), fmaxf(bxmx, rxmx), fminf(bymn, rymn), fmaxf(bymx, rymx), prevc);
+        bxmn = rxmn; bxmx = rxmx; bymn = rymn; bymx = rymx;
+        if (NPREV && j < jl) prevc = __ldg(sum_prev + (size_t)kb * 32u);
+        kb++;
+      } else {
+        bxmn = fminf(fminf(bxmn, kxe), kxo); bxmx = fmaxf(fmaxf(bxmx, kxe), kxo);
+        bymn = fminf(fminf(bymn, kye), kyo); bymx = fmaxf(fmaxf(bymx, kye), kyo);
+      }
+    }
+  };
+
+  load_stage(IC<0>{}, 0);
+  for (int g = 0; g < ngroups; g += 6) {
+    group(IC<0>{}, IC<0>{}, g);
+    if (g + 1 < ngroups) group(IC<1>{}, IC<3>{}, g + 1);
+    if (g + 2 < ngroups) group(IC<0>{}, IC<6>{}, g + 2);
+    if (g + 3 < ngroups) group(IC<1>{}, IC<0>{}, g + 3);
+    if (g + 4 < ngroups) group(IC<0>{}, IC<3>{}, g + 4);
+    if (g + 5 < ngroups) group(IC<1>{}, IC<6>{}, g + 5);
+  }
+  if (jl % C2_R != 0) finish_block(jl / C2_R, bxmn, bxmx, bymn, bymx, prevc);     // the array's last, partial block
+  if (want_res) warp_res_commit(fabs(res.m), p.res_slot[B]);
+  if (!(big < __int_as_float(KEYF_BIG))) atomicExch(p.poison, 1ull);
+}
+
+template <int NPREV, bool TEST>
+__global__ void __launch_bounds__((C2_CW + 1) * 32, 2) scan2d_keys_build_kernel(const __grid_constant__ SweepParams p) {
+  extern __shared__ __align__(128) unsigned char fb_smem[];
+  const int lane = threadIdx.x & 31;
+  const int wib = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);     // warp-uniform by construction
+  const uint32_t ring0 = smem_u32(fb_smem);
+  const uint32_t full0 = ring0 + (uint32_t)K2_NST * K2_STAGE_BYTES, empty0 = full0 + 8u * K2_NST;
+  const int W = p.W, H = p.H;
+  const int bx = blockIdx.x % p.nsx, cy = blockIdx.x / p.nsx;
+  const int C0 = bx * (C2_CW * FB_STRIDE);
+  const int nactive = min(C2_CW, (W - C0 + FB_STRIDE - 1) / FB_STRIDE);     // consumer warps whose strip starts inside the array
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int q = 0; q < K2_NST; q++) { mbar_init(full0 + 8u * q, 1); mbar_init(empty0 + 8u * q, (uint32_t)nactive); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  const int r0 = cy * p.rows;                        // p.rows is a multiple of C2_R
+  const int r1 = min(r0 + p.rows - 1, H - 1);
+  const int nstages = ((r1 + 1) - r0 + 1 + 2 + K2_R - 1) / K2_R;
+  if (wib == C2_CW) {
+    // producer: one elected lane walks the rows with the array's index clamp and keeps the ring full; a stage always gets
+    // K2_R rows (rows past the chunk's last one repeat the clamp: valid data, never used)
+    if (elect_one()) {
+      const double *S = p.L[p.build_layer].S;
+      const int col_lo = max(C0 - 2, 0), col_hi = min(C0 - 2 + TL_SEG, W);
+      const uint32_t seg_bytes = (uint32_t)(col_hi - col_lo) * 8u;
+      const uint32_t dst0 = ring0 + (uint32_t)(col_lo - (C0 - 2)) * 8u;
+      for (int s = 0; s < nstages; s++) {
+        const uint32_t slot = (uint32_t)s & (K2_NST - 1);
+        if (s >= K2_NST) mbar_wait(empty0 + 8u * slot, (uint32_t)((s / K2_NST - 1) & 1));
+        mbar_expect_tx(full0 + 8u * slot, seg_bytes * K2_R);
+#pragma unroll
+        for (int i = 0; i < K2_R; i++) {
+          const size_t off = (size_t)W * (size_t)clampi(r0 - 1 + K2_R * s + i, H) + (size_t)col_lo;
+          bulk_g2s(dst0 + slot * K2_STAGE_BYTES + (uint32_t)i * K2_ROW_BYTES, S + off, seg_bytes, full0 + 8u * slot);
+        }
+      }
+    }
+    return;
+  }
+  if (wib >= nactive) return;
+  const int c0 = C0 + wib * FB_STRIDE;
+  const uint32_t tile_u32 = ring0 + (uint32_t)(wib * FB_STRIDE) * 8u;
+  const bool border = c0 == 0 || c0 + FB_SEG - 2 > W;      // strips that touch the array's left / right edge clamp their columns
+  if (border) keys2d_strip<true, NPREV, TEST>(p, c0, r0, r1, lane, tile_u32, full0, empty0, bx * C2_CW + wib);
+  else keys2d_strip<false, NPREV, TEST>(p, c0, r0, r1, lane, tile_u32, full0, empty0, bx * C2_CW + wib);
+}
+
+static size_t k2_smem_bytes() { return (size_t)K2_NST * K2_STAGE_BYTES + (size_t)2 * K2_NST * 8; }
+
 static size_t c2_smem_bytes() { return (size_t)C2_NST * TL_SEG * 8 + (size_t)2 * C2_NST * 8; }
 
 size_t vscan2d_cells_per_layer(const SweepParams &p);
@@ -1111,6 +1362,14 @@ void launch_scan2d_cells(const SweepParams &p, cudaStream_t s) {
   const unsigned grid = (unsigned)((i64)p.nsx * p.nsy);
   const int nstrips = (p.W + FB_STRIDE - 1) / FB_STRIDE, nblk = (p.H + C2_R - 1) / C2_R;
   const unsigned tgrid = (unsigned)(((i64)nstrips * nblk + 7) / 8);
+  if (p.keys2d && p.sum_mode <= SUM_BUILD_TEST2) {
+    switch (p.sum_mode) {
+      case SUM_BUILD: scan2d_keys_build_kernel<0, false><<<grid, (C2_CW + 1) * 32, k2_smem_bytes(), s>>>(p); break;
+      case SUM_BUILD_TEST1: scan2d_keys_build_kernel<0, true><<<grid, (C2_CW + 1) * 32, k2_smem_bytes(), s>>>(p); break;
+      default: scan2d_keys_build_kernel<1, true><<<grid, (C2_CW + 1) * 32, k2_smem_bytes(), s>>>(p); break;
+    }
+    return;
+  }
   switch (p.sum_mode) {
     case SUM_BUILD: scan2d_build_kernel<0, false><<<grid, (C2_CW + 1) * 32, c2_smem_bytes(), s>>>(p); break;
     case SUM_BUILD_TEST1: scan2d_build_kernel<0, true><<<grid, (C2_CW + 1) * 32, c2_smem_bytes(), s>>>(p); break;
@@ -1147,15 +1406,12 @@ void launch_scan2d_cells(const SweepParams &p, cudaStream_t s) {
 constexpr int F3_LAYER_BYTES = ((F3_ROWS * F3_COLS * 8 + 127) / 128) * 128;   // one staged plane of one layer
 constexpr int F3_LAYER_DOUBLES = F3_LAYER_BYTES / 8;
 constexpr uint32_t F3_BOX_BYTES = F3_ROWS * F3_COLS * 8;
-constexpr int KEYF_BIG = 0x7E700000;     // high word of 2^1000
-constexpr int KEYF_NAN = 0x7FC00000;
 
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *tm, int c0, int c1, int c2, uint32_t bar) {
   asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
                ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
 }
 
-__device__ __forceinline__ float hikey(double d) { return __int_as_float(__double2hiint(d)); }
 
 // cold path: for every lane whose union failed (bit set in failmask), the WARP tests that lane's 2 x F3_RW cubes of
 // plane z: four lanes per cube, two vertices each (ranges over the vertices valid simplices can use, <= ub, read from
@@ -2372,6 +2628,9 @@ void init_kernel_attributes() {
   cudaFuncSetAttribute(scan3d_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused3d_smem_bytes(true));
   cudaFuncSetAttribute(scan3d_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused3d_smem_bytes(false));
   cudaFuncSetAttribute(scan2d_build_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c2_smem_bytes());
+  cudaFuncSetAttribute(scan2d_keys_build_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2_smem_bytes());
+  cudaFuncSetAttribute(scan2d_keys_build_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2_smem_bytes());
+  cudaFuncSetAttribute(scan2d_keys_build_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2_smem_bytes());
   cudaFuncSetAttribute(scan2d_build_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c2_smem_bytes());
   cudaFuncSetAttribute(scan2d_build_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c2_smem_bytes());
   cudaFuncSetAttribute(scan3d_build_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s3_smem_bytes());
@@ -3034,9 +3293,10 @@ __global__ void __launch_bounds__(128) test_kernel(const __grid_constant__ Sweep
   out[3] = p.res_slot[0] ? *(volatile unsigned long long *)p.res_slot[0] : ~0ull;
   out[4] = p.res_slot[1] ? *(volatile unsigned long long *)p.res_slot[1] : ~0ull;
   out[5] = p.step_seq;
+  // re-arm this step's set (the other set belongs to the next step, whose scan may be running already)
   *p.ticket = 0;
   *p.poison = 0;
-  *p.wl_count_next = 0;
+  *p.wl_count = 0;
   if (p.res_reset) *p.res_reset = ~0ull;
   __threadfence_system();
 }

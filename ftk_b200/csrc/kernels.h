@@ -72,8 +72,7 @@ struct SweepParams {
   unsigned long long *step_out;      // mapped pinned host memory: {worklist count, point count, poison, res[0], res[1], sequence}
   unsigned long long step_seq;
   unsigned long long *ticket;        // blocks of the test kernel that are done
-  unsigned long long *wl_count_next; // the next step's worklist counter (zeroed here)
-  unsigned long long *res_reset;     // resolution slot of the layer the next step resolves (set to all ones), or nullptr
+  unsigned long long *res_reset;     // resolution slot to re-arm (all ones) for the step after next, or nullptr
   int32_t test_blocks;               // grid of the test kernel (grid-stride: any worklist size is covered)
 };
 

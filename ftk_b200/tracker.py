@@ -383,6 +383,21 @@ class _RegularTracker:
         self._check(L.lib().ftkb_get_last_worklist(self._h, out.ctypes.data, n.value, C.byref(n)))
         return out[:n.value]
 
+    def get_layer(self, index=0):
+        """diagnostic: resident snapshot `index` (0 = current) copied to the host, in memory order -> (scalar, vector), None
+        for a field the snapshot does not hold (what ftkb_push_synthetic generated on the device)"""
+        n = self.ND
+        out = []
+        for trailing, src in (((), self._scalar_source), ((n,), self._vector_source)):
+            if src != SOURCE_GIVEN:
+                out.append(None)
+                continue
+            a = np.zeros(self._shape(trailing), np.float64)
+            args = (a.ctypes.data, None) if not trailing else (None, a.ctypes.data)
+            self._check(L.lib().ftkb_get_layer(self._h, int(index), *args))
+            out.append(a)
+        return tuple(out)
+
     def stats(self):
         s = L.Stats()
         self._check(L.lib().ftkb_get_stats(self._h, C.byref(s)))

@@ -268,6 +268,10 @@ const char *ftkb_curveset_last_error(const ftkb_curveset *);
  * scan kernel left for the exact test; *n receives the count, at most cap entries are copied */
 int ftkb_get_last_worklist(ftkb_ctx *, uint64_t *out, uint64_t cap, uint64_t *n);
 
+/* diagnostic: copy resident snapshot `index` (0 = current) to host memory -- what a device-side generator
+ * (ftkb_push_synthetic) produced; either pointer may be NULL */
+int ftkb_get_layer(ftkb_ctx *, int index, double *scalar, double *vector);
+
 int ftkb_get_stats(ftkb_ctx *, ftkb_stats *out);
 int ftkb_reset_stats(ftkb_ctx *);
 /* block until all work queued on the context's stream is complete */

@@ -493,7 +493,7 @@ def test_deferred_steps_equal_synchronous_steps(mode, ftk, oracle, monkeypatch):
     tr = ftk.track(snaps, dims, field="scalar")
     P.assert_same_result(cuda_result(tr), want, tol=TOL, what=f"woven {mode}")
     st = tr.stats()
-    assert st["scan_launches"] >= T and st["simplices_tested"] == (94 * 78) * (12 * (T - 1) + 2)
+    assert st["scan_launches"] >= T and st["simplices_tested"] == (93 * 77) * (12 * (T - 1) + 2)
     tr.close()
 
 
@@ -520,3 +520,100 @@ def test_deferred_steps_3d_and_vector(ftk, oracle):
         P.assert_same_result(cuda_result(c), P.oracle_result(o), tol=TOL, what=f"deferred {dims} {field}")
         assert c.stats()["scaling_factor"] == o.scaling_factor
         c.close()
+
+
+# ---- SURVEY.md 8(c) sizes: the reduced extents of the benchmark generators, compared with the oracle -------------
+def _ref_series(oracle, gen, dims, T, params=None):
+    return list(oracle.synthetic_series(gen, dims, T, params))
+
+
+@pytest.mark.parametrize("gen,dims,T,field,params", [
+    ("woven", [512, 512], 16, "scalar", None),
+    ("double_gyre", [512, 256], 16, "vector", None),
+    ("moving_extremum", [96, 96, 96], 6, "scalar", [48.3, 47.7, 48.1, 0.1, 0.11, 0.1]),
+    ("abc", [96, 96, 96], 6, "vector", None),                      # unsteady ABC: A(k) as in the C4 benchmark
+])
+def test_survey_8c_sizes_match_oracle(gen, dims, T, field, params, ftk, oracle):
+    snaps = _ref_series(oracle, gen, dims, T, params)
+    c, o = _both(ftk, oracle, snaps, dims, field)
+    got, want = cuda_result(c), P.oracle_result(o)
+    assert len(want["points"]) > 0
+    P.assert_same_result(got, want, tol=TOL, what=f"{gen} {dims}x{T}")
+    assert np.array_equal(c.get_component_labels(), o.component_labels())
+    assert c.stats()["scaling_factor"] == o.scaling_factor
+    c.close()
+
+
+def test_scalar_2d_nonfinite_and_huge_values(ftk, oracle):
+    """NaN / Inf / 2^1010 scalars cannot be ordered by the high-word keys of the default 2D build kernel: the layer is
+    poisoned and the step redone with the fp32-range kernel; results equal the oracle's either way"""
+    rng = np.random.default_rng(5)
+    dims, T = [140, 90], 4
+    snaps = [rng.standard_normal((90, 140)) for _ in range(T)]
+    snaps[1][40, 70] = np.nan
+    snaps[2][10:12, 100] = np.inf
+    snaps[2][60, 20] = -2.0 ** 1010
+    c, o = _both(ftk, oracle, snaps, dims, "scalar")
+    P.assert_same_result(cuda_result(c), P.oracle_result(o), tol=TOL, what="non-finite 2D scalar")
+    assert c.stats()["sweeps_repeated"] > 0
+    c.close()
+
+
+# ---- device-side generators (SURVEY.md 8f1): values against the reference's closed forms, and the tracker on exactly the
+# field the device produced against the oracle on that same field --------------------------------------------------------
+GENERATORS = [
+    # kind, name, dims, field, params handed to ftkb_push_synthetic, time of snapshot k, host twin
+    (0, "moving_extremum_2d", [64, 48], "scalar", [30.3, 21.7, 0.4, 0.3], lambda k, T: float(k)),
+    (0, "moving_extremum_3d", [24, 20, 18], "scalar", [11.3, 9.7, 8.1, 0.3, 0.21, 0.1], lambda k, T: float(k)),
+    (1, "woven", [96, 72], "scalar", [], lambda k, T: float(k) / (T - 1) + 1e-4),
+    (2, "double_gyre", [96, 48], "vector", [0.1, 2 * np.pi, 0.25], lambda k, T: 0.1 * k),
+    (3, "abc", [24, 22, 20], "vector", None, lambda k, T: 0.0),
+    (4, "merger", [48, 40], "scalar", [], lambda k, T: 0.1 * k),
+    (5, "tornado", [20, 18, 16], "vector", [], lambda k, T: float(k)),
+]
+
+
+def _host_twin(oracle, name, dims, params, t, k):
+    if name.startswith("moving_extremum"):
+        nd = len(dims)
+        return oracle.gen_moving_extremum(dims, params[:nd], params[nd:], t)
+    if name == "woven":
+        return oracle.gen_woven(dims[0], dims[1], t)
+    if name == "double_gyre":
+        return oracle.gen_double_gyre(dims[0], dims[1], t, *params)
+    if name == "abc":
+        return oracle.gen_abc(dims[0], dims[1], dims[2], oracle.abc_amplitude(k))
+    if name == "merger":
+        return oracle.gen_merger(dims[0], dims[1], t)
+    return oracle.gen_tornado(dims[0], dims[1], dims[2], int(t))
+
+
+@pytest.mark.parametrize("case", range(len(GENERATORS)), ids=[g[1] for g in GENERATORS])
+def test_device_generators(case, ftk, oracle):
+    kind, name, dims, field, params, time_of = GENERATORS[case]
+    T = 5
+    tr = ftk.make_tracker(dims, field=field)
+    device_fields = []
+    for k in range(T):
+        t = time_of(k, T)
+        prm = [oracle.abc_amplitude(k), np.sqrt(2.0), 1.0] if name == "abc" else params
+        tr.push_synthetic_snapshot(kind, prm, t)
+        s, v = tr.get_layer(1 if k else 0)
+        dev = s if field == "scalar" else v
+        host = _host_twin(oracle, name, dims, prm, t, k)
+        # the closed forms of include/ftk/ndarray/synthetic.hh: exact where they are pure arithmetic, within a few ulp of the
+        # value scale where sin / cos / exp / sqrt of the device's libm round differently from the host's
+        scale = max(1.0, float(np.abs(host).max()))
+        if name.startswith("moving_extremum"):
+            assert np.array_equal(dev, host), f"{name}: device generator differs from synthetic.hh"
+        else:
+            assert np.abs(dev - host).max() <= 64 * np.finfo(np.float64).eps * scale, f"{name}: max |d| = {np.abs(dev - host).max()}"
+        device_fields.append(dev.copy())
+        if k:
+            tr.advance_timestep()
+        if k == T - 1:
+            tr.update_timestep()
+    tr.finalize()
+    o = oracle.track(device_fields, dims, field=field)           # the oracle on exactly what the device generated
+    P.assert_same_result(cuda_result(tr), P.oracle_result(o), tol=TOL, what=f"generator {name}")
+    tr.close()
