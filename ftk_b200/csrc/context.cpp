@@ -106,6 +106,8 @@ struct ftkb_ctx {
   cudaStream_t producer = nullptr;
   cudaStream_t stream2 = nullptr;    // deferred steps: the test kernels' stream
   cudaEvent_t ev_join = nullptr;
+  bool debug_timing = false;         // FTKB_DEBUG_TIMING=1: report the sweep stream's idle time between scans at destroy
+  double gap_ms = 0; uint64_t gap_n = 0, last_confirmed_seq = 0;
   bool overlap_test = true;          // FTKB_TEST_OVERLAP=0: test kernels stay on the sweep's stream
   bool has_producer = false;
 
@@ -196,6 +198,9 @@ static int drain(ftkb_ctx *c);
 extern "C" void ftkb_destroy(ftkb_ctx *c) {
   if (!c) return;
   (void)wait_grow(c);
+  if (c->debug_timing && c->gap_n)
+    std::fprintf(stderr, "[ftkb] sweep stream idle between scans: %.2f us avg over %llu steps (scan %.1f us, test %.1f us avg)\n", 1e3 * c->gap_ms / c->gap_n,
+                 (unsigned long long)c->gap_n, 1e3 * c->stats.ms_scan / std::max<uint64_t>(1, c->stats.scan_launches), 1e3 * c->stats.ms_test / std::max<uint64_t>(1, c->stats.scan_launches));
   cudaSetDevice(c->cfg.device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   for (auto &l : c->layers) release_layer(c, l);
@@ -308,6 +313,7 @@ extern "C" int ftkb_create(const ftkb_config *cfg, ftkb_ctx **out) {
     if ((e = cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, hi)) != cudaSuccess) return bail(std::string("cudaStreamCreate: ") + cudaGetErrorString(e), FTKB_ERR_CUDA);
     if ((e = cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming)) != cudaSuccess) return bail(std::string("cudaEventCreate: ") + cudaGetErrorString(e), FTKB_ERR_CUDA);
     if (const char *o = std::getenv("FTKB_TEST_OVERLAP")) c->overlap_test = std::string(o) != "0";
+    if (const char *o = std::getenv("FTKB_DEBUG_TIMING")) c->debug_timing = std::string(o) == "1";
   }
   c->pt_cap = cfg->point_capacity ? cfg->point_capacity : (1 << 18);
   if ((e = cudaMalloc(&c->d_pts, sizeof(ftkb_point) * c->pt_cap)) != cudaSuccess) return bail("cudaMalloc(points) failed", FTKB_ERR_NOMEM);
@@ -860,6 +866,13 @@ static int confirm_front(ftkb_ctx *c) {
   CK(cudaEventElapsedTime(&ms_scan, c->dev[pd.evset][0], c->dev[pd.evset][1]));
   CK(cudaEventElapsedTime(&ms_test, c->dev[pd.evset][1], c->dev[pd.evset][2]));
   c->stats.ms_scan += ms_scan; c->stats.ms_test += ms_test; c->stats.last_ms_scan = ms_scan;
+  if (c->debug_timing && c->last_confirmed_seq + 1 == pd.seq) {
+    // idle time of the sweep's stream between the previous step's scan and this one's (diagnostic, FTKB_DEBUG_TIMING=1)
+    float gap = 0;
+    if (cudaEventElapsedTime(&gap, c->dev[1 - pd.evset][1], c->dev[pd.evset][0]) == cudaSuccess) { c->gap_ms += gap; c->gap_n++; }
+    else cudaGetLastError();
+  }
+  c->last_confirmed_seq = pd.seq;
   c->stats.scan_launches++;
   c->stats.cells_scanned += c->ncore;
   c->stats.cells_refined += nwl;

@@ -16,6 +16,8 @@
 #include "kernels.h"
 
 #include <cfloat>
+#include <cstdlib>
+#include <string>
 #include <climits>
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_select.cuh>
@@ -1138,31 +1140,14 @@ __device__ __forceinline__ float fmax_nan(float a, float b) {
   return r;
 }
 
-struct K2Res { double m; float kx, ky; };   // running signed value of smallest non-zero magnitude + the key filters per component
-
-// exact (cold) update of the running min non-zero |v| with the four gradient values of one row, v = d * (W-1 | H-1) in fp64
-// as gradient2D computes them (grad.hh:24-27); afterwards kx / ky are keys no difference below the new minimum can exceed
-__device__ __noinline__ K2Res k2_res_update(K2Res r, bool e_in, bool o_in, double dxe, double dye, double dxo, double dyo, double cw, double ch) {
-  const double vxe = dxe * cw, vye = dye * ch, vxo = dxo * cw, vyo = dyo * ch;
-  double m = r.m;
-  if (e_in) {
-    if (vxe != 0.0 && fabs(vxe) < fabs(m)) m = vxe;     // NaN / Inf never compare below
-    if (vye != 0.0 && fabs(vye) < fabs(m)) m = vye;
-  }
-  if (o_in) {
-    if (vxo != 0.0 && fabs(vxo) < fabs(m)) m = vxo;
-    if (vyo != 0.0 && fabs(vyo) < fabs(m)) m = vyo;
-  }
-  K2Res out;
-  out.m = m;
-  if (fabs(m) < DBL_MAX) {
-    // |d| (W-1) < |m|  =>  |d| <= |m| / (W-1) (1 + 2^-52)  =>  hi(|d|) <= hi(|m| / (W-1)) + 1
-    out.kx = __int_as_float(__double2hiint(fabs(m) / cw) + 1);
-    out.ky = __int_as_float(__double2hiint(fabs(m) / ch) + 1);
-  } else {
-    out.kx = out.ky = __int_as_float(0x7F800000);       // nothing found yet: every key is a candidate
-  }
-  return out;
+// running minimum of the non-zero magnitudes, branch-free (two DSETP + select per value): the moving-extremum fields are
+// adversarial for a filtered slow path -- |dS/dy| shrinks row by row towards the extremum, so every row is a new minimum
+__device__ __forceinline__ double nzmin(double m, double d) {     // m, d signed: |.| folds into the compare's operand modifiers
+  double r;                                                      // (|d| < |m| && d != 0) ? d : m -- NaN compares false, Inf never below
+  asm("{\n\t.reg .pred p, q;\n\t.reg .f64 ad, am;\n\tabs.f64 ad, %2;\n\tabs.f64 am, %1;\n\t"
+      "setp.neu.f64 q, %2, 0d0000000000000000;\n\tsetp.lt.and.f64 p, ad, am, q;\n\tselp.f64 %0, %2, %1, p;\n\t}"
+      : "=d"(r) : "d"(m), "d"(d));
+  return r;
 }
 
 // conservative fp32 range of v = d * c over the values whose keys lie in [kmn, kmx]
@@ -1186,9 +1171,9 @@ __device__ __forceinline__ void keys2d_strip(const SweepParams &p, const int c0,
   const int ngroups = (nrows + K2_R - 1) / K2_R, nstages = (nrows + 2 + K2_R - 1) / K2_R;
   const double cw = (double)(W - 1), ch = (double)(H - 1);
   const bool want_res = p.res_slot[B] != nullptr;
-  K2Res res{DBL_MAX, __int_as_float(0x7F800000), __int_as_float(0x7F800000)};
+  double mdx = DBL_MAX, mdy = DBL_MAX;                // exact min non-zero |d| per component; scaled by (W-1), (H-1) at the end:
+                                                      // v = fl(d c) is monotone in |d|, so min |v| = fl(min |d| c) (grad.hh:24-27)
   float big = 0.f;
-  const float inff_ = __int_as_float(0x7F800000);
   const uint4 *sum_prev = NPREV ? p.sum_in[0] + cells2d_index(p, strip, 0, lane) : nullptr;
   uint4 *sum_out = p.sum_out + cells2d_index(p, strip, 0, lane);
   const uint32_t lane_u32 = tile_u32 + (uint32_t)lane * 16u;    // +8: column e-1, +16: e, o, +32: o+1
@@ -1261,12 +1246,8 @@ __device__ __forceinline__ void keys2d_strip(const SweepParams &p, const int c0,
       const double dxe = mid_e - left, dxo = right - cv[0], dye = p1[0] - m1[0], dyo = p1[1] - m1[1];
       const float kxe = hikey(dxe), kxo = hikey(dxo), kye = hikey(dye), kyo = hikey(dyo);
       if (want_res && j < H) {
-        float ax = fminf(fabsf(kxe), fabsf(kxo)), ay = fminf(fabsf(kye), fabsf(kyo));
-        if (BORDER) {
-          ax = fminf(e_in ? fabsf(kxe) : inff_, o_in ? fabsf(kxo) : inff_);
-          ay = fminf(e_in ? fabsf(kye) : inff_, o_in ? fabsf(kyo) : inff_);
-        }
-        if (ax <= res.kx || ay <= res.ky) res = k2_res_update(res, e_in, o_in, dxe, dye, dxo, dyo, cw, ch);
+        if (e_in) { mdx = nzmin(mdx, dxe); mdy = nzmin(mdy, dye); }
+        if (o_in) { mdx = nzmin(mdx, dxo); mdy = nzmin(mdy, dyo); }
       }
       if ((K0 + i) % C2_R == 0) {
         // gradient row C2_R k closes block k-1 and opens block k
@@ -1292,7 +1273,11 @@ __device__ __forceinline__ void keys2d_strip(const SweepParams &p, const int c0,
     if (g + 5 < ngroups) group(IC<1>{}, IC<6>{}, g + 5);
   }
   if (jl % C2_R != 0) finish_block(jl / C2_R, bxmn, bxmx, bymn, bymx, prevc);     // the array's last, partial block
-  if (want_res) warp_res_commit(fabs(res.m), p.res_slot[B]);
+  if (want_res) {
+    const double ax = fabs(mdx), ay = fabs(mdy);
+    const double vx = ax < DBL_MAX ? ax * cw : DBL_MAX, vy = ay < DBL_MAX ? ay * ch : DBL_MAX;      // W - 1, H - 1 >= 1: no underflow to zero
+    warp_res_commit(fmin(vx > 0.0 ? vx : DBL_MAX, vy > 0.0 ? vy : DBL_MAX), p.res_slot[B]);
+  }
   if (!(big < __int_as_float(KEYF_BIG))) atomicExch(p.poison, 1ull);
 }
 
@@ -2620,7 +2605,9 @@ static size_t bulk_smem_bytes(bool has_next) {
   return (size_t)FB_WARPS * FB_NST * (has_next ? 2 : 1) * FB_SEG * 8 + (size_t)FB_WARPS * FB_NST * 8;
 }
 
+static void init_carveouts();
 void init_kernel_attributes() {
+  init_carveouts();
   cudaFuncSetAttribute(scan2d_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem_bytes(true));
   cudaFuncSetAttribute(scan2d_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem_bytes(false));
   cudaFuncSetAttribute(scan2d_bulk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bulk_smem_bytes(true));
@@ -3307,6 +3294,25 @@ void launch_test(const SweepParams &p, cudaStream_t s) {
   const unsigned grid = (unsigned)(p.test_blocks > 0 ? p.test_blocks : 148 * 8);
   if (p.nd == 2) test_kernel<2><<<grid, 128, 0, s>>>(p);
   else test_kernel<3><<<grid, 128, 0, s>>>(p);
+}
+
+// Kernels of one step that ask for different shared-memory / L1 splits cannot share an SM, and an SM has to drain before its
+// split changes: the scan kernels take most of the 228 KB as shared memory, so every kernel of the step loop asks for the same
+// split -- then the test kernel's few blocks slot in next to the next scan's CTAs.  FTKB_CARVEOUT=0 leaves the driver's choice.
+static void init_carveouts() {
+  if (const char *e = std::getenv("FTKB_CARVEOUT")) if (std::string(e) == "0") return;
+  const int co = cudaSharedmemCarveoutMaxShared;
+#define CARVE(k) cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, co)
+  CARVE(test_kernel<2>); CARVE(test_kernel<3>);
+  CARVE((scan2d_keys_build_kernel<0, false>)); CARVE((scan2d_keys_build_kernel<0, true>)); CARVE((scan2d_keys_build_kernel<1, true>));
+  CARVE((scan2d_build_kernel<0, false>)); CARVE((scan2d_build_kernel<0, true>)); CARVE((scan2d_build_kernel<1, true>));
+  CARVE((scan3d_build_kernel<0, false>)); CARVE((scan3d_build_kernel<0, true>)); CARVE((scan3d_build_kernel<1, true>));
+  CARVE((vscan2d_build_kernel<0, false>)); CARVE((vscan2d_build_kernel<0, true>)); CARVE((vscan2d_build_kernel<1, true>));
+  CARVE((vscan3d_build_kernel<0, false>)); CARVE((vscan3d_build_kernel<0, true>)); CARVE((vscan3d_build_kernel<1, true>));
+  CARVE(scan2d_cells_kernel<1>); CARVE(scan2d_cells_kernel<2>); CARVE(scan3d_cells_kernel<1>); CARVE(scan3d_cells_kernel<2>);
+  CARVE(vscan2d_cells_kernel<1>); CARVE(vscan2d_cells_kernel<2>);
+#undef CARVE
+  cudaGetLastError();
 }
 
 // =============================================================================================
