@@ -108,6 +108,7 @@ struct ftkb_ctx {
   cudaEvent_t ev_join = nullptr;
   bool debug_timing = false;         // FTKB_DEBUG_TIMING=1: report the sweep stream's idle time between scans at destroy
   double gap_ms = 0; uint64_t gap_n = 0, last_confirmed_seq = 0;
+  std::vector<float> gaps;
   bool overlap_test = true;          // FTKB_TEST_OVERLAP=0: test kernels stay on the sweep's stream
   bool has_producer = false;
 
@@ -198,9 +199,12 @@ static int drain(ftkb_ctx *c);
 extern "C" void ftkb_destroy(ftkb_ctx *c) {
   if (!c) return;
   (void)wait_grow(c);
-  if (c->debug_timing && c->gap_n)
-    std::fprintf(stderr, "[ftkb] sweep stream idle between scans: %.2f us avg over %llu steps (scan %.1f us, test %.1f us avg)\n", 1e3 * c->gap_ms / c->gap_n,
+  if (c->debug_timing && c->gap_n) {
+    std::sort(c->gaps.begin(), c->gaps.end());
+    std::fprintf(stderr, "[ftkb] sweep stream idle between scans: median %.2f us, min %.2f, p90 %.2f over %llu steps (scan %.1f us, test %.1f us avg)\n",
+                 1e3 * c->gaps[c->gaps.size() / 2], 1e3 * c->gaps.front(), 1e3 * c->gaps[c->gaps.size() * 9 / 10],
                  (unsigned long long)c->gap_n, 1e3 * c->stats.ms_scan / std::max<uint64_t>(1, c->stats.scan_launches), 1e3 * c->stats.ms_test / std::max<uint64_t>(1, c->stats.scan_launches));
+  }
   cudaSetDevice(c->cfg.device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   for (auto &l : c->layers) release_layer(c, l);
@@ -556,6 +560,7 @@ static void fill_sweep_geometry(const ftkb_ctx *c, SweepParams &p) {
   for (int k = 0; k < 6; k++) p.coords_bounds[k] = c->coords_bounds[k];
   p.coords = c->d_coords;
   p.nd = c->n;
+  p.sm_count = c->sm_count;
   p.W = c->cfg.dims[0]; p.H = c->cfg.dims[1]; p.D = c->n == 3 ? c->cfg.dims[2] : 1;
   for (int j = 0; j < 3; j++) {
     const bool used = j < c->n;
@@ -869,7 +874,7 @@ static int confirm_front(ftkb_ctx *c) {
   if (c->debug_timing && c->last_confirmed_seq + 1 == pd.seq) {
     // idle time of the sweep's stream between the previous step's scan and this one's (diagnostic, FTKB_DEBUG_TIMING=1)
     float gap = 0;
-    if (cudaEventElapsedTime(&gap, c->dev[1 - pd.evset][1], c->dev[pd.evset][0]) == cudaSuccess) { c->gap_ms += gap; c->gap_n++; }
+    if (cudaEventElapsedTime(&gap, c->dev[1 - pd.evset][1], c->dev[pd.evset][0]) == cudaSuccess) { c->gap_ms += gap; c->gap_n++; c->gaps.push_back(gap); }
     else cudaGetLastError();
   }
   c->last_confirmed_seq = pd.seq;

@@ -15,6 +15,7 @@
 //   gradient2d/3d, resolution, synthetic generators, element keys, neighbour search, union-find.
 #include "kernels.h"
 
+#include <algorithm>
 #include <cfloat>
 #include <cstdlib>
 #include <string>
@@ -1158,10 +1159,20 @@ __device__ __forceinline__ FRange k2_vrange(float kmn, float kmx, double c) {
   return FRange{__double2float_rd(lo * c), __double2float_ru(hi * c)};
 }
 
+__device__ __forceinline__ void prefetch_l2(const void *q) { asm volatile("prefetch.global.L2 [%0];" ::"l"(q)); }
+
+struct K2Acc { double mdx, mdy; float big; };     // per-lane accumulators carried across the segments of a persistent CTA
+
+// one segment of one strip; a function of its own (not inlined) so that the hot loop gets the whole register file and the
+// persistent loop's bookkeeping is saved once per segment, not kept live across it
 template <bool BORDER, int NPREV, bool TEST>
-__device__ __forceinline__ void keys2d_strip(const SweepParams &p, const int c0, const int r0, const int r1, const int lane,
-                                             const uint32_t tile_u32 /* smem address of this warp's column c0-2, stage 0, row 0 */,
-                                             const uint32_t full0, const uint32_t empty0, const int strip) {
+__device__ __noinline__ K2Acc keys2d_strip(const SweepParams &p, const int c0, const int r0, const int r1, const int lane,
+                                           const uint32_t tile_u32 /* smem address of this warp's column c0-2, stage 0, row 0 */,
+                                           const uint32_t full0, const uint32_t empty0, const int strip,
+                                           const uint32_t sbase /* ring stages this CTA has consumed before this segment */,
+                                           const K2Acc acc) {
+  double mdx = acc.mdx, mdy = acc.mdy;
+  float big = acc.big;
   const int W = p.W, H = p.H, B = p.build_layer;
   const int e = c0 + 2 * lane, o = e + 1;
   const bool e_in = !BORDER || e < W, o_in = !BORDER || o < W, o1_in = !BORDER || o + 1 < W;
@@ -1171,12 +1182,11 @@ __device__ __forceinline__ void keys2d_strip(const SweepParams &p, const int c0,
   const int ngroups = (nrows + K2_R - 1) / K2_R, nstages = (nrows + 2 + K2_R - 1) / K2_R;
   const double cw = (double)(W - 1), ch = (double)(H - 1);
   const bool want_res = p.res_slot[B] != nullptr;
-  double mdx = DBL_MAX, mdy = DBL_MAX;                // exact min non-zero |d| per component; scaled by (W-1), (H-1) at the end:
-                                                      // v = fl(d c) is monotone in |d|, so min |v| = fl(min |d| c) (grad.hh:24-27)
-  float big = 0.f;
   const uint4 *sum_prev = NPREV ? p.sum_in[0] + cells2d_index(p, strip, 0, lane) : nullptr;
   uint4 *sum_out = p.sum_out + cells2d_index(p, strip, 0, lane);
   const uint32_t lane_u32 = tile_u32 + (uint32_t)lane * 16u;    // +8: column e-1, +16: e, o, +32: o+1
+  const int kb0 = r0 / C2_R;                          // first block of the segment (a segment has at most 64 blocks)
+  unsigned long long failbits = 0;
 
   // a block of C2_R corner rows is complete: x-neighbour merge on the keys, keys -> fp32 ranges of v, store the cell, test
   auto finish_block = [&](const int kb, float xmn, float xmx, float ymn, float ymx, const uint4 prevc) {
@@ -1191,42 +1201,68 @@ __device__ __forceinline__ void keys2d_strip(const SweepParams &p, const int c0,
       }
       const int y0 = kb * C2_R;
       const bool own = own_cols && y0 <= p.ub[1] && y0 + C2_R - 1 >= p.lb[1];
-      cells2d_decide(p, bx, by, own, e, y0, NPREV + 1);
+      // a union that does not prove its 18 cubes excluded is only noted here (one bit per block of the segment): the per-cube
+      // refinement runs after the row loop, so the hot loop contains no call and keeps its registers
+      if (own && !cube_excluded2_f(bx, by, p.thrp_f, p.thr2_f, p.lim_f)) failbits |= 1ull << (kb - kb0);
     }
   };
 
-  // two register sets of one stage each: centre columns (e, o) and x neighbours (e-1, o+1) of its three rows
-  double C[2][K2_R][2], N[2][K2_R][2];
+  // two register sets of one stage each: the centre columns (e, o) of its three rows, and the keys of their x differences --
+  // d/dx only involves the row itself, so it is formed (and its exact minimum taken) while the stage is unloaded and only
+  // the two 32-bit keys stay live
+  double C[2][K2_R][2];
+  float KX[2][K2_R][2];
   auto load_stage = [&](auto PC, const int s) {
     constexpr int P = decltype(PC)::value;
-    const uint32_t slot = (uint32_t)s & (K2_NST - 1);
-    mbar_wait(full0 + 8u * slot, (uint32_t)(s / K2_NST) & 1u);
+    const uint32_t gs = sbase + (uint32_t)s, slot = gs & (K2_NST - 1);
+    mbar_wait(full0 + 8u * slot, (gs / K2_NST) & 1u);
     const uint32_t base = lane_u32 + slot * K2_STAGE_BYTES;
+    double nl[K2_R], nr[K2_R];
 #pragma unroll
     for (int i = 0; i < K2_R; i++) {
       const double2 c = lds128_f64(base + (uint32_t)i * K2_ROW_BYTES + 16u);
       C[P][i][0] = c.x; C[P][i][1] = c.y;
-      N[P][i][0] = lds64_f64(base + (uint32_t)i * K2_ROW_BYTES + 8u);
-      N[P][i][1] = lds64_f64(base + (uint32_t)i * K2_ROW_BYTES + 32u);
+      nl[i] = lds64_f64(base + (uint32_t)i * K2_ROW_BYTES + 8u);
+      nr[i] = lds64_f64(base + (uint32_t)i * K2_ROW_BYTES + 32u);
     }
+    __syncwarp();
+    if (elect_one()) mbar_arrive(empty0 + 8u * slot);   // the stage lives in registers now
 #pragma unroll
     for (int i = 0; i < K2_R; i++) {
       const float ke = fabsf(hikey(C[P][i][0])), ko = fabsf(hikey(C[P][i][1]));
       big = fmax_nan(big, BORDER ? (e_in ? ke : 0.f) : ke);
       big = fmax_nan(big, BORDER ? (o_in ? ko : 0.f) : ko);
+      double left = nl[i], right = nr[i], mid_e = C[P][i][1];
+      if (BORDER) {
+        if (e == 0) left = C[P][i][0];
+        if (!o_in) mid_e = C[P][i][0];
+        if (!o1_in) right = C[P][i][1];
+      }
+      const double dxe = mid_e - left, dxo = right - C[P][i][0];
+      KX[P][i][0] = hikey(dxe); KX[P][i][1] = hikey(dxo);
+      const int j = r0 + K2_R * s + i - 1;              // the gradient row this ring row is the centre of
+      if (want_res && j >= r0 && j <= jl && j < H) {
+        if (e_in) mdx = nzmin(mdx, dxe);
+        if (o_in) mdx = nzmin(mdx, dxo);
+      }
     }
-    __syncwarp();
-    if (elect_one()) mbar_arrive(empty0 + 8u * slot);   // the stage lives in registers now
   };
 
   float bxmn = 0.f, bxmx = 0.f, bymn = 0.f, bymx = 0.f;
-  uint4 prevc = make_uint4(0x7FC00000u, 0x7FC00000u, 0x7FC00000u, 0x7FC00000u);
+  const uint4 nanc = make_uint4(0x7FC00000u, 0x7FC00000u, 0x7FC00000u, 0x7FC00000u);
   int kb = r0 / C2_R;                                  // the block the next row with K == 0 opens
+  const int kb_end = (jl + C2_R - 1) / C2_R;           // blocks kb .. kb_end-1 are closed by this segment
+  // the other layer's cells are requested into L2 two blocks ahead of their use (a DRAM miss each: ~1 us) and loaded one
+  // block ahead
+  uint4 prevc = nanc;
+  if (NPREV && kb < kb_end) prefetch_l2(sum_prev + (size_t)kb * 32u);
+  if (NPREV && kb + 1 < kb_end) prefetch_l2(sum_prev + (size_t)(kb + 1) * 32u);
 
   // group g = gradient rows r0 + 3 g + {0, 1, 2}; ring row q holds array row r0 - 1 + q, gradient row r0 + q reads ring rows
-  // q (below), q + 1 (centre, x neighbours), q + 2 (above).  PC: register set of stage g; KC: (3 g) mod 9.
-  auto group = [&](auto PC, auto KC, const int g) {
-    constexpr int P = decltype(PC)::value, K0 = decltype(KC)::value;
+  // q (below), q + 1 (centre, x neighbours), q + 2 (above).  PC: register set of stage g; phase: rows since the last block opened.
+  int phase = 0;
+  auto group = [&](auto PC, const int g) {
+    constexpr int P = decltype(PC)::value;
     if (g + 1 < nstages) load_stage(IC<1 - P>{}, g + 1);
 #pragma unroll
     for (int i = 0; i < K2_R; i++) {
@@ -1234,28 +1270,24 @@ __device__ __forceinline__ void keys2d_strip(const SweepParams &p, const int c0,
       if (j > jl) break;
       constexpr int dummy = 0; (void)dummy;
       const double *m1 = C[P][i];
-      const double *cv = i + 1 < K2_R ? C[P][i + 1] : C[1 - P][i + 1 - K2_R];
-      const double *nb = i + 1 < K2_R ? N[P][i + 1] : N[1 - P][i + 1 - K2_R];
+      const float *kx = i + 1 < K2_R ? KX[P][i + 1] : KX[1 - P][i + 1 - K2_R];
       const double *p1 = i + 2 < K2_R ? C[P][i + 2] : C[1 - P][i + 2 - K2_R];
-      double left = nb[0], right = nb[1], mid_e = cv[1];
-      if (BORDER) {
-        if (e == 0) left = cv[0];
-        if (!o_in) mid_e = cv[0];
-        if (!o1_in) right = cv[1];
-      }
-      const double dxe = mid_e - left, dxo = right - cv[0], dye = p1[0] - m1[0], dyo = p1[1] - m1[1];
-      const float kxe = hikey(dxe), kxo = hikey(dxo), kye = hikey(dye), kyo = hikey(dyo);
+      const double dye = p1[0] - m1[0], dyo = p1[1] - m1[1];
+      const float kxe = kx[0], kxo = kx[1], kye = hikey(dye), kyo = hikey(dyo);
       if (want_res && j < H) {
-        if (e_in) { mdx = nzmin(mdx, dxe); mdy = nzmin(mdy, dye); }
-        if (o_in) { mdx = nzmin(mdx, dxo); mdy = nzmin(mdy, dyo); }
+        if (e_in) mdy = nzmin(mdy, dye);
+        if (o_in) mdy = nzmin(mdy, dyo);
       }
-      if ((K0 + i) % C2_R == 0) {
+      const bool opens = phase == 0;                    // warp-uniform
+      phase = phase + 1 == C2_R ? 0 : phase + 1;
+      if (opens) {
         // gradient row C2_R k closes block k-1 and opens block k
         const float rxmn = fminf(kxe, kxo), rxmx = fmaxf(kxe, kxo), rymn = fminf(kye, kyo), rymx = fmaxf(kye, kyo);
         if (j > r0) finish_block(kb - 1, fminf(bxmn, rxmn), fmaxf(bxmx, rxmx), fminf(bymn, rymn), fmaxf(bymx, rymx), prevc);
         bxmn = rxmn; bxmx = rxmx; bymn = rymn; bymx = rymx;
-        if (NPREV && j < jl) prevc = __ldg(sum_prev + (size_t)kb * 32u);
+        if (NPREV && kb < kb_end) prevc = __ldg(sum_prev + (size_t)kb * 32u);     // cells of the block this row opens (in L2 by now)
         kb++;
+        if (NPREV && kb + 1 < kb_end) prefetch_l2(sum_prev + (size_t)(kb + 1) * 32u);
       } else {
         bxmn = fminf(fminf(bxmn, kxe), kxo); bxmx = fmaxf(fmaxf(bxmx, kxe), kxo);
         bymn = fminf(fminf(bymn, kye), kyo); bymx = fmaxf(fmaxf(bymx, kye), kyo);
@@ -1264,23 +1296,27 @@ __device__ __forceinline__ void keys2d_strip(const SweepParams &p, const int c0,
   };
 
   load_stage(IC<0>{}, 0);
-  for (int g = 0; g < ngroups; g += 6) {
-    group(IC<0>{}, IC<0>{}, g);
-    if (g + 1 < ngroups) group(IC<1>{}, IC<3>{}, g + 1);
-    if (g + 2 < ngroups) group(IC<0>{}, IC<6>{}, g + 2);
-    if (g + 3 < ngroups) group(IC<1>{}, IC<0>{}, g + 3);
-    if (g + 4 < ngroups) group(IC<0>{}, IC<3>{}, g + 4);
-    if (g + 5 < ngroups) group(IC<1>{}, IC<6>{}, g + 5);
+#pragma unroll 1
+  for (int g = 0; g < ngroups; g += 2) {
+    group(IC<0>{}, g);
+    if (g + 1 < ngroups) group(IC<1>{}, g + 1);
   }
   if (jl % C2_R != 0) finish_block(jl / C2_R, bxmn, bxmx, bymn, bymx, prevc);     // the array's last, partial block
-  if (want_res) {
-    const double ax = fabs(mdx), ay = fabs(mdy);
-    const double vx = ax < DBL_MAX ? ax * cw : DBL_MAX, vy = ay < DBL_MAX ? ay * ch : DBL_MAX;      // W - 1, H - 1 >= 1: no underflow to zero
-    warp_res_commit(fmin(vx > 0.0 ? vx : DBL_MAX, vy > 0.0 ? vy : DBL_MAX), p.res_slot[B]);
+  if (TEST) {
+    // cold path: per-cube refinement of the blocks whose cell union failed (rows re-read through L2)
+    for (int b = 0; b < 64; b++) {
+      if (!__any_sync(0xffffffffu, (failbits >> b) != 0)) break;
+      const unsigned fm = __ballot_sync(0xffffffffu, (failbits >> b) & 1ull);
+      if (fm) cells2d_slow_cubes(p, fm, c0, (kb0 + b) * C2_R, NPREV + 1, C2_R);
+    }
   }
-  if (!(big < __int_as_float(KEYF_BIG))) atomicExch(p.poison, 1ull);
+  return K2Acc{mdx, mdy, big};
 }
 
+// Persistent: the grid is two CTAs per SM, and CTA c owns the c-th equal share of all (tile, 9-row block) pairs, in tile-major
+// order -- one or two long vertical segments.  The producer warp streams the segments' rows back to back through the ring (the
+// ring is filled once per CTA, not once per chunk, and there is no tail of half-empty waves); consumer warps whose strip lies
+// outside the array still take part in the barrier protocol, so the ring's arrival counts are the same for every segment.
 template <int NPREV, bool TEST>
 __global__ void __launch_bounds__((C2_CW + 1) * 32, 2) scan2d_keys_build_kernel(const __grid_constant__ SweepParams p) {
   extern __shared__ __align__(128) unsigned char fb_smem[];
@@ -1289,46 +1325,71 @@ __global__ void __launch_bounds__((C2_CW + 1) * 32, 2) scan2d_keys_build_kernel(
   const uint32_t ring0 = smem_u32(fb_smem);
   const uint32_t full0 = ring0 + (uint32_t)K2_NST * K2_STAGE_BYTES, empty0 = full0 + 8u * K2_NST;
   const int W = p.W, H = p.H;
-  const int bx = blockIdx.x % p.nsx, cy = blockIdx.x / p.nsx;
-  const int C0 = bx * (C2_CW * FB_STRIDE);
-  const int nactive = min(C2_CW, (W - C0 + FB_STRIDE - 1) / FB_STRIDE);     // consumer warps whose strip starts inside the array
   if (threadIdx.x == 0) {
 #pragma unroll
-    for (int q = 0; q < K2_NST; q++) { mbar_init(full0 + 8u * q, 1); mbar_init(empty0 + 8u * q, (uint32_t)nactive); }
+    for (int q = 0; q < K2_NST; q++) { mbar_init(full0 + 8u * q, 1); mbar_init(empty0 + 8u * q, (uint32_t)C2_CW); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   __syncthreads();
-  const int r0 = cy * p.rows;                        // p.rows is a multiple of C2_R
-  const int r1 = min(r0 + p.rows - 1, H - 1);
-  const int nstages = ((r1 + 1) - r0 + 1 + 2 + K2_R - 1) / K2_R;
-  if (wib == C2_CW) {
-    // producer: one elected lane walks the rows with the array's index clamp and keeps the ring full; a stage always gets
-    // K2_R rows (rows past the chunk's last one repeat the clamp: valid data, never used)
-    if (elect_one()) {
-      const double *S = p.L[p.build_layer].S;
-      const int col_lo = max(C0 - 2, 0), col_hi = min(C0 - 2 + TL_SEG, W);
-      const uint32_t seg_bytes = (uint32_t)(col_hi - col_lo) * 8u;
-      const uint32_t dst0 = ring0 + (uint32_t)(col_lo - (C0 - 2)) * 8u;
-      for (int s = 0; s < nstages; s++) {
-        const uint32_t slot = (uint32_t)s & (K2_NST - 1);
-        if (s >= K2_NST) mbar_wait(empty0 + 8u * slot, (uint32_t)((s / K2_NST - 1) & 1));
-        mbar_expect_tx(full0 + 8u * slot, seg_bytes * K2_R);
+  const i64 nblk = (H + C2_R - 1) / C2_R;                                   // 9-row blocks per tile column
+  const i64 total = (i64)p.nsx * nblk;
+  const i64 w0 = total * (i64)blockIdx.x / (i64)gridDim.x, w1 = total * ((i64)blockIdx.x + 1) / (i64)gridDim.x;
+  K2Acc acc{DBL_MAX, DBL_MAX, 0.f};                   // exact min non-zero |d| per component; scaled by (W-1), (H-1) at the end:
+                                                      // v = fl(d c) is monotone in |d|, so min |v| = fl(min |d| c) (grad.hh:24-27)
+  uint32_t sbase = 0;
+  for (i64 w = w0; w < w1;) {
+    const int bx = (int)(w / nblk), b0 = (int)(w % nblk);
+    const int b1 = (int)min(min((i64)nblk, (i64)b0 + (w1 - w)), (i64)b0 + 64);   // blocks b0 .. b1-1 of tile column bx (one fail bit each)
+    w += b1 - b0;
+    const int C0 = bx * (C2_CW * FB_STRIDE);
+    const int nactive = min(C2_CW, (W - C0 + FB_STRIDE - 1) / FB_STRIDE);   // consumer warps whose strip starts inside the array
+    const int r0 = b0 * C2_R, r1 = min(b1 * C2_R - 1, H - 1);
+    const int nstages = ((r1 + 1) - r0 + 1 + 2 + K2_R - 1) / K2_R;
+    if (wib == C2_CW) {
+      // producer: one elected lane walks the rows with the array's index clamp and keeps the ring full; a stage always gets
+      // K2_R rows (rows past the segment's last one repeat the clamp: valid data, never used)
+      if (elect_one()) {
+        const double *S = p.L[p.build_layer].S;
+        const int col_lo = max(C0 - 2, 0), col_hi = min(C0 - 2 + TL_SEG, W);
+        const uint32_t seg_bytes = (uint32_t)(col_hi - col_lo) * 8u;
+        const uint32_t dst0 = ring0 + (uint32_t)(col_lo - (C0 - 2)) * 8u;
+        for (int s = 0; s < nstages; s++) {
+          const uint32_t gs = sbase + (uint32_t)s, slot = gs & (K2_NST - 1);
+          if (gs >= K2_NST) mbar_wait(empty0 + 8u * slot, ((gs / K2_NST) - 1u) & 1u);
+          mbar_expect_tx(full0 + 8u * slot, seg_bytes * K2_R);
 #pragma unroll
-        for (int i = 0; i < K2_R; i++) {
-          const size_t off = (size_t)W * (size_t)clampi(r0 - 1 + K2_R * s + i, H) + (size_t)col_lo;
-          bulk_g2s(dst0 + slot * K2_STAGE_BYTES + (uint32_t)i * K2_ROW_BYTES, S + off, seg_bytes, full0 + 8u * slot);
+          for (int i = 0; i < K2_R; i++) {
+            const size_t off = (size_t)W * (size_t)clampi(r0 - 1 + K2_R * s + i, H) + (size_t)col_lo;
+            bulk_g2s(dst0 + slot * K2_STAGE_BYTES + (uint32_t)i * K2_ROW_BYTES, S + off, seg_bytes, full0 + 8u * slot);
+          }
         }
       }
+    } else if (wib >= nactive) {
+      // no strip of this warp inside the array in this tile column: keep the ring's arrival counts whole
+      for (int s = 0; s < nstages; s++) {
+        const uint32_t gs = sbase + (uint32_t)s, slot = gs & (K2_NST - 1);
+        mbar_wait(full0 + 8u * slot, (gs / K2_NST) & 1u);
+        __syncwarp();
+        if (elect_one()) mbar_arrive(empty0 + 8u * slot);
+      }
+    } else {
+      const int c0 = C0 + wib * FB_STRIDE;
+      const uint32_t tile_u32 = ring0 + (uint32_t)(wib * FB_STRIDE) * 8u;
+      const bool border = c0 == 0 || c0 + FB_SEG - 2 > W;      // strips that touch the array's left / right edge clamp their columns
+      if (border) acc = keys2d_strip<true, NPREV, TEST>(p, c0, r0, r1, lane, tile_u32, full0, empty0, bx * C2_CW + wib, sbase, acc);
+      else acc = keys2d_strip<false, NPREV, TEST>(p, c0, r0, r1, lane, tile_u32, full0, empty0, bx * C2_CW + wib, sbase, acc);
     }
-    return;
+    sbase += (uint32_t)nstages;
   }
-  if (wib >= nactive) return;
-  const int c0 = C0 + wib * FB_STRIDE;
-  const uint32_t tile_u32 = ring0 + (uint32_t)(wib * FB_STRIDE) * 8u;
-  const bool border = c0 == 0 || c0 + FB_SEG - 2 > W;      // strips that touch the array's left / right edge clamp their columns
-  if (border) keys2d_strip<true, NPREV, TEST>(p, c0, r0, r1, lane, tile_u32, full0, empty0, bx * C2_CW + wib);
-  else keys2d_strip<false, NPREV, TEST>(p, c0, r0, r1, lane, tile_u32, full0, empty0, bx * C2_CW + wib);
+  if (wib >= C2_CW) return;
+  if (p.res_slot[p.build_layer] != nullptr) {
+    const double cw = (double)(W - 1), ch = (double)(H - 1);
+    const double ax = fabs(acc.mdx), ay = fabs(acc.mdy);
+    const double vx = ax < DBL_MAX ? ax * cw : DBL_MAX, vy = ay < DBL_MAX ? ay * ch : DBL_MAX;      // W - 1, H - 1 >= 1: no underflow to zero
+    warp_res_commit(fmin(vx > 0.0 ? vx : DBL_MAX, vy > 0.0 ? vy : DBL_MAX), p.res_slot[p.build_layer]);
+  }
+  if (!(acc.big < __int_as_float(KEYF_BIG))) atomicExch(p.poison, 1ull);
 }
 
 static size_t k2_smem_bytes() { return (size_t)K2_NST * K2_STAGE_BYTES + (size_t)2 * K2_NST * 8; }
@@ -1348,10 +1409,13 @@ void launch_scan2d_cells(const SweepParams &p, cudaStream_t s) {
   const int nstrips = (p.W + FB_STRIDE - 1) / FB_STRIDE, nblk = (p.H + C2_R - 1) / C2_R;
   const unsigned tgrid = (unsigned)(((i64)nstrips * nblk + 7) / 8);
   if (p.keys2d && p.sum_mode <= SUM_BUILD_TEST2) {
+    // persistent: two CTAs per SM, never more CTAs than 9-row blocks
+    const i64 total = (i64)p.nsx * ((p.H + C2_R - 1) / C2_R);
+    const unsigned pgrid = (unsigned)std::max<i64>(1, std::min<i64>(total, 2 * (i64)(p.sm_count > 0 ? p.sm_count : 148)));
     switch (p.sum_mode) {
-      case SUM_BUILD: scan2d_keys_build_kernel<0, false><<<grid, (C2_CW + 1) * 32, k2_smem_bytes(), s>>>(p); break;
-      case SUM_BUILD_TEST1: scan2d_keys_build_kernel<0, true><<<grid, (C2_CW + 1) * 32, k2_smem_bytes(), s>>>(p); break;
-      default: scan2d_keys_build_kernel<1, true><<<grid, (C2_CW + 1) * 32, k2_smem_bytes(), s>>>(p); break;
+      case SUM_BUILD: scan2d_keys_build_kernel<0, false><<<pgrid, (C2_CW + 1) * 32, k2_smem_bytes(), s>>>(p); break;
+      case SUM_BUILD_TEST1: scan2d_keys_build_kernel<0, true><<<pgrid, (C2_CW + 1) * 32, k2_smem_bytes(), s>>>(p); break;
+      default: scan2d_keys_build_kernel<1, true><<<pgrid, (C2_CW + 1) * 32, k2_smem_bytes(), s>>>(p); break;
     }
     return;
   }
@@ -3298,9 +3362,10 @@ void launch_test(const SweepParams &p, cudaStream_t s) {
 
 // Kernels of one step that ask for different shared-memory / L1 splits cannot share an SM, and an SM has to drain before its
 // split changes: the scan kernels take most of the 228 KB as shared memory, so every kernel of the step loop asks for the same
-// split -- then the test kernel's few blocks slot in next to the next scan's CTAs.  FTKB_CARVEOUT=0 leaves the driver's choice.
+// split -- then the test kernel's few blocks slot in next to the next scan's CTAs.  Opt-in (FTKB_CARVEOUT=1): it costs the scans L1.
 static void init_carveouts() {
-  if (const char *e = std::getenv("FTKB_CARVEOUT")) if (std::string(e) == "0") return;
+  const char *e = std::getenv("FTKB_CARVEOUT");      // off by default: measured 174 us (driver's split) against 183 us on the C2 scan
+  if (!e || std::string(e) != "1") return;
   const int co = cudaSharedmemCarveoutMaxShared;
 #define CARVE(k) cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, co)
   CARVE(test_kernel<2>); CARVE(test_kernel<3>);

@@ -74,6 +74,7 @@ struct SweepParams {
   unsigned long long *ticket;        // blocks of the test kernel that are done
   unsigned long long *res_reset;     // resolution slot to re-arm (all ones) for the step after next, or nullptr
   int32_t test_blocks;               // grid of the test kernel (grid-stride: any worklist size is covered)
+  int32_t sm_count;                  // SMs of the device (persistent kernels size their grid by it)
 };
 
 void upload_mesh_tables(const DeviceMeshTables &t2, const DeviceMeshTables &t3);

@@ -37,7 +37,7 @@ using ftk::ndarray;
 typedef ftk::simplicial_regular_mesh_element element_t;
 
 struct args_t {
-  int nd = 2, nv = 1, W = 0, H = 0, D = 1, T = 0, nthreads = 0;
+  int nd = 2, nv = 1, W = 0, H = 0, D = 1, T = 0, nthreads = 0, start_timestep = 0;
   int symmetric = -1;
   bool trace = true, quiet = false, have_domain = false;
   int dom[6] = {0, 0, 0, 0, 0, 0};
@@ -138,6 +138,7 @@ static int run(const args_t &a)
     } else { fprintf(stderr, "unknown --coords %s\n", a.coords.c_str()); return 2; }
   }
   tr.initialize();
+  if (a.start_timestep) tr.set_current_timestep(a.start_timestep);   // tracker.hh:40 (a time slab, or a run resumed at t > 0)
 
   tracker_t trs(comm);           // streaming twin: same configuration, trajectories grown online after every step
   const bool streaming = !a.out_stream.empty();
@@ -331,6 +332,7 @@ int main(int argc, char **argv)
     else if (s == "--nv") a.nv = atoi(next());
     else if (s == "--dims") { a.W = atoi(next()); a.H = atoi(next()); if (a.nd == 3) a.D = atoi(next()); }
     else if (s == "--nt") a.T = atoi(next());
+    else if (s == "--start-timestep") a.start_timestep = atoi(next());
     else if (s == "--gen") a.gen = next();
     else if (s == "--input") a.input = next();
     else if (s == "--out") a.out = next();
