@@ -109,6 +109,7 @@ struct ftkb_ctx {
   bool debug_timing = false;         // FTKB_DEBUG_TIMING=1: report the sweep stream's idle time between scans at destroy
   double gap_ms = 0; uint64_t gap_n = 0, last_confirmed_seq = 0;
   std::vector<float> gaps;
+  double host_wait_us = 0, host_enq_us = 0; uint64_t host_wait_n = 0, host_enq_n = 0;
   bool overlap_test = true;          // FTKB_TEST_OVERLAP=0: test kernels stay on the sweep's stream
   bool has_producer = false;
 
@@ -204,6 +205,9 @@ extern "C" void ftkb_destroy(ftkb_ctx *c) {
     std::fprintf(stderr, "[ftkb] sweep stream idle between scans: median %.2f us, min %.2f, p90 %.2f over %llu steps (scan %.1f us, test %.1f us avg)\n",
                  1e3 * c->gaps[c->gaps.size() / 2], 1e3 * c->gaps.front(), 1e3 * c->gaps[c->gaps.size() * 9 / 10],
                  (unsigned long long)c->gap_n, 1e3 * c->stats.ms_scan / std::max<uint64_t>(1, c->stats.scan_launches), 1e3 * c->stats.ms_test / std::max<uint64_t>(1, c->stats.scan_launches));
+    std::fprintf(stderr, "[ftkb] host: %.1f us to enqueue a step, %.1f us blocked per confirmation (avg over %llu / %llu)\n",
+                 c->host_enq_us / std::max<uint64_t>(1, c->host_enq_n), c->host_wait_us / std::max<uint64_t>(1, c->host_wait_n),
+                 (unsigned long long)c->host_enq_n, (unsigned long long)c->host_wait_n);
   }
   cudaSetDevice(c->cfg.device);
   if (c->stream) cudaStreamSynchronize(c->stream);
@@ -606,6 +610,7 @@ static void fused2d_decomposition(const ftkb_ctx *c, SweepParams &p) {
     p.rows = std::max(2 * R, (int)((p.H + want - 1) / want));
     p.rows = (p.rows + R - 1) / R * R;      // chunks start on cell-block boundaries
     if (const char *e = std::getenv("FTKB_C2_ROWS")) p.rows = std::max(R, std::atoi(e) / R * R);   // A/B measurements
+    p.rows = std::min(p.rows, 64 * R);      // the key kernel keeps one fail bit per block of a chunk
   }
   p.nsy = (p.H + p.rows - 1) / p.rows;
   p.nsz = 1;
@@ -854,7 +859,9 @@ static int replay(ftkb_ctx *c, bool poison) {
 
 static int confirm_front(ftkb_ctx *c) {
   const ftkb_ctx::Pending pd = c->pend.front();
+  const auto tw0 = std::chrono::steady_clock::now();
   CK(cudaEventSynchronize(c->dev[pd.evset][2]));
+  if (c->debug_timing) { c->host_wait_us += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - tw0).count(); c->host_wait_n++; }
   const volatile unsigned long long *r = c->h_ring + 8 * pd.ring;
   if (r[5] != pd.seq) return fail(c, FTKB_ERR_CUDA, "deferred step: the test kernel did not publish its counters");
   const uint64_t nwl = r[0], npt = r[1];
@@ -1055,6 +1062,7 @@ static int update_impl(ftkb_ctx *c, bool allow_defer) {
     p.thrp_f = (float)((1.0 / p.factor) * (1.0 + 1.0 / 1048576.0));
     p.thr2_f = (float)(2.0 / p.factor);
     p.lim_f = (float)(0.999 * 4.5e18 / (p.factor * p.factor));
+    const auto te0 = std::chrono::steady_clock::now();
     ftkb_ctx::Pending pd;
     pd.seq = ++c->step_seq;
     pd.ring = (int)(pd.seq % ftkb_ctx::RING);
@@ -1115,6 +1123,7 @@ static int update_impl(ftkb_ctx *c, bool allow_defer) {
     c->pend.push_back(pd);
     c->primed = true;
     c->wl_sel ^= 1;
+    if (c->debug_timing) { c->host_enq_us += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - te0).count(); c->host_enq_n++; }
     while (c->pend.size() > 1) {
       const int rc2 = confirm_front(c);
       if (rc2) return rc2;

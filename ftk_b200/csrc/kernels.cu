@@ -1119,10 +1119,12 @@ __global__ void __launch_bounds__(256) scan2d_cells_kernel(const __grid_constant
 // Scalars >= 2^1000 / Inf / NaN cannot be ordered by the keys: they raise p.poison and the context redoes the step with
 // scan2d_build_kernel (fp32 ranges, handles them).
 constexpr int K2_R = 3;                                // rows per stage
-constexpr int K2_NST = 8;                              // ring stages (power of two); 85 KB per CTA, two CTAs per SM
+// CTAs per SM (a launch-bounds variant each; FTKB_K2_CTAS selects, default 3): the ring has 8 stages at two CTAs per SM
+// (85 KB per CTA) and 4 stages (42 KB) at three or four
+__host__ __device__ constexpr int k2_nst(int ctas) { return ctas >= 3 ? 4 : 8; }
 constexpr uint32_t K2_ROW_BYTES = TL_SEG * 8;
 constexpr uint32_t K2_STAGE_BYTES = K2_R * K2_ROW_BYTES;
-static_assert(C2_R % K2_R == 0 && (K2_NST & (K2_NST - 1)) == 0, "cell block = whole stages; ring index by mask");
+static_assert(C2_R % K2_R == 0, "cell block = whole stages");
 
 __device__ __forceinline__ double2 lds128_f64(uint32_t a) {
   double2 v;
@@ -1165,8 +1167,8 @@ struct K2Acc { double mdx, mdy; float big; };     // per-lane accumulators carri
 
 // one segment of one strip; a function of its own (not inlined) so that the hot loop gets the whole register file and the
 // persistent loop's bookkeeping is saved once per segment, not kept live across it
-template <bool BORDER, int NPREV, bool TEST>
-__device__ __noinline__ K2Acc keys2d_strip(const SweepParams &p, const int c0, const int r0, const int r1, const int lane,
+template <bool BORDER, int NPREV, bool TEST, int K2_NST>
+__device__ __forceinline__ K2Acc keys2d_strip(const SweepParams &p, const int c0, const int r0, const int r1, const int lane,
                                            const uint32_t tile_u32 /* smem address of this warp's column c0-2, stage 0, row 0 */,
                                            const uint32_t full0, const uint32_t empty0, const int strip,
                                            const uint32_t sbase /* ring stages this CTA has consumed before this segment */,
@@ -1313,76 +1315,58 @@ __device__ __noinline__ K2Acc keys2d_strip(const SweepParams &p, const int c0, c
   return K2Acc{mdx, mdy, big};
 }
 
-// Persistent: the grid is two CTAs per SM, and CTA c owns the c-th equal share of all (tile, 9-row block) pairs, in tile-major
-// order -- one or two long vertical segments.  The producer warp streams the segments' rows back to back through the ring (the
-// ring is filled once per CTA, not once per chunk, and there is no tail of half-empty waves); consumer warps whose strip lies
-// outside the array still take part in the barrier protocol, so the ring's arrival counts are the same for every segment.
-template <int NPREV, bool TEST>
-__global__ void __launch_bounds__((C2_CW + 1) * 32, 2) scan2d_keys_build_kernel(const __grid_constant__ SweepParams p) {
+// One CTA per (tile of C2_CW strips, chunk of p.rows corner rows); K2_CTAS CTAs per SM.
+template <int NPREV, bool TEST, int K2_CTAS>
+__global__ void __launch_bounds__((C2_CW + 1) * 32, K2_CTAS) scan2d_keys_build_kernel(const __grid_constant__ SweepParams p) {
+  constexpr int K2_NST = k2_nst(K2_CTAS);
   extern __shared__ __align__(128) unsigned char fb_smem[];
   const int lane = threadIdx.x & 31;
   const int wib = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);     // warp-uniform by construction
   const uint32_t ring0 = smem_u32(fb_smem);
   const uint32_t full0 = ring0 + (uint32_t)K2_NST * K2_STAGE_BYTES, empty0 = full0 + 8u * K2_NST;
   const int W = p.W, H = p.H;
+  const int bx = blockIdx.x % p.nsx, cy = blockIdx.x / p.nsx;
+  const int C0 = bx * (C2_CW * FB_STRIDE);
+  const int nactive = min(C2_CW, (W - C0 + FB_STRIDE - 1) / FB_STRIDE);     // consumer warps whose strip starts inside the array
   if (threadIdx.x == 0) {
 #pragma unroll
-    for (int q = 0; q < K2_NST; q++) { mbar_init(full0 + 8u * q, 1); mbar_init(empty0 + 8u * q, (uint32_t)C2_CW); }
+    for (int q = 0; q < K2_NST; q++) { mbar_init(full0 + 8u * q, 1); mbar_init(empty0 + 8u * q, (uint32_t)nactive); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   __syncthreads();
-  const i64 nblk = (H + C2_R - 1) / C2_R;                                   // 9-row blocks per tile column
-  const i64 total = (i64)p.nsx * nblk;
-  const i64 w0 = total * (i64)blockIdx.x / (i64)gridDim.x, w1 = total * ((i64)blockIdx.x + 1) / (i64)gridDim.x;
-  K2Acc acc{DBL_MAX, DBL_MAX, 0.f};                   // exact min non-zero |d| per component; scaled by (W-1), (H-1) at the end:
-                                                      // v = fl(d c) is monotone in |d|, so min |v| = fl(min |d| c) (grad.hh:24-27)
-  uint32_t sbase = 0;
-  for (i64 w = w0; w < w1;) {
-    const int bx = (int)(w / nblk), b0 = (int)(w % nblk);
-    const int b1 = (int)min(min((i64)nblk, (i64)b0 + (w1 - w)), (i64)b0 + 64);   // blocks b0 .. b1-1 of tile column bx (one fail bit each)
-    w += b1 - b0;
-    const int C0 = bx * (C2_CW * FB_STRIDE);
-    const int nactive = min(C2_CW, (W - C0 + FB_STRIDE - 1) / FB_STRIDE);   // consumer warps whose strip starts inside the array
-    const int r0 = b0 * C2_R, r1 = min(b1 * C2_R - 1, H - 1);
-    const int nstages = ((r1 + 1) - r0 + 1 + 2 + K2_R - 1) / K2_R;
-    if (wib == C2_CW) {
-      // producer: one elected lane walks the rows with the array's index clamp and keeps the ring full; a stage always gets
-      // K2_R rows (rows past the segment's last one repeat the clamp: valid data, never used)
-      if (elect_one()) {
-        const double *S = p.L[p.build_layer].S;
-        const int col_lo = max(C0 - 2, 0), col_hi = min(C0 - 2 + TL_SEG, W);
-        const uint32_t seg_bytes = (uint32_t)(col_hi - col_lo) * 8u;
-        const uint32_t dst0 = ring0 + (uint32_t)(col_lo - (C0 - 2)) * 8u;
-        for (int s = 0; s < nstages; s++) {
-          const uint32_t gs = sbase + (uint32_t)s, slot = gs & (K2_NST - 1);
-          if (gs >= K2_NST) mbar_wait(empty0 + 8u * slot, ((gs / K2_NST) - 1u) & 1u);
-          mbar_expect_tx(full0 + 8u * slot, seg_bytes * K2_R);
+  const int r0 = cy * p.rows;                        // p.rows is a multiple of C2_R, at most 64 blocks (one fail bit each)
+  const int r1 = min(r0 + p.rows - 1, H - 1);
+  const int nstages = ((r1 + 1) - r0 + 1 + 2 + K2_R - 1) / K2_R;
+  if (wib == C2_CW) {
+    // producer: one elected lane walks the rows with the array's index clamp and keeps the ring full; a stage always gets
+    // K2_R rows (rows past the chunk's last one repeat the clamp: valid data, never used)
+    if (elect_one()) {
+      const double *S = p.L[p.build_layer].S;
+      const int col_lo = max(C0 - 2, 0), col_hi = min(C0 - 2 + TL_SEG, W);
+      const uint32_t seg_bytes = (uint32_t)(col_hi - col_lo) * 8u;
+      const uint32_t dst0 = ring0 + (uint32_t)(col_lo - (C0 - 2)) * 8u;
+      for (int s = 0; s < nstages; s++) {
+        const uint32_t slot = (uint32_t)s & (K2_NST - 1);
+        if (s >= K2_NST) mbar_wait(empty0 + 8u * slot, (uint32_t)((s / K2_NST - 1) & 1));
+        mbar_expect_tx(full0 + 8u * slot, seg_bytes * K2_R);
 #pragma unroll
-          for (int i = 0; i < K2_R; i++) {
-            const size_t off = (size_t)W * (size_t)clampi(r0 - 1 + K2_R * s + i, H) + (size_t)col_lo;
-            bulk_g2s(dst0 + slot * K2_STAGE_BYTES + (uint32_t)i * K2_ROW_BYTES, S + off, seg_bytes, full0 + 8u * slot);
-          }
+        for (int i = 0; i < K2_R; i++) {
+          const size_t off = (size_t)W * (size_t)clampi(r0 - 1 + K2_R * s + i, H) + (size_t)col_lo;
+          bulk_g2s(dst0 + slot * K2_STAGE_BYTES + (uint32_t)i * K2_ROW_BYTES, S + off, seg_bytes, full0 + 8u * slot);
         }
       }
-    } else if (wib >= nactive) {
-      // no strip of this warp inside the array in this tile column: keep the ring's arrival counts whole
-      for (int s = 0; s < nstages; s++) {
-        const uint32_t gs = sbase + (uint32_t)s, slot = gs & (K2_NST - 1);
-        mbar_wait(full0 + 8u * slot, (gs / K2_NST) & 1u);
-        __syncwarp();
-        if (elect_one()) mbar_arrive(empty0 + 8u * slot);
-      }
-    } else {
-      const int c0 = C0 + wib * FB_STRIDE;
-      const uint32_t tile_u32 = ring0 + (uint32_t)(wib * FB_STRIDE) * 8u;
-      const bool border = c0 == 0 || c0 + FB_SEG - 2 > W;      // strips that touch the array's left / right edge clamp their columns
-      if (border) acc = keys2d_strip<true, NPREV, TEST>(p, c0, r0, r1, lane, tile_u32, full0, empty0, bx * C2_CW + wib, sbase, acc);
-      else acc = keys2d_strip<false, NPREV, TEST>(p, c0, r0, r1, lane, tile_u32, full0, empty0, bx * C2_CW + wib, sbase, acc);
     }
-    sbase += (uint32_t)nstages;
+    return;
   }
-  if (wib >= C2_CW) return;
+  if (wib >= nactive) return;
+  const int c0 = C0 + wib * FB_STRIDE;
+  const uint32_t tile_u32 = ring0 + (uint32_t)(wib * FB_STRIDE) * 8u;
+  const bool border = c0 == 0 || c0 + FB_SEG - 2 > W;      // strips that touch the array's left / right edge clamp their columns
+  K2Acc acc{DBL_MAX, DBL_MAX, 0.f};                   // exact min non-zero |d| per component; scaled by (W-1), (H-1) at the end:
+                                                      // v = fl(d c) is monotone in |d|, so min |v| = fl(min |d| c) (grad.hh:24-27)
+  if (border) acc = keys2d_strip<true, NPREV, TEST, K2_NST>(p, c0, r0, r1, lane, tile_u32, full0, empty0, bx * C2_CW + wib, 0u, acc);
+  else acc = keys2d_strip<false, NPREV, TEST, K2_NST>(p, c0, r0, r1, lane, tile_u32, full0, empty0, bx * C2_CW + wib, 0u, acc);
   if (p.res_slot[p.build_layer] != nullptr) {
     const double cw = (double)(W - 1), ch = (double)(H - 1);
     const double ax = fabs(acc.mdx), ay = fabs(acc.mdy);
@@ -1392,7 +1376,27 @@ __global__ void __launch_bounds__((C2_CW + 1) * 32, 2) scan2d_keys_build_kernel(
   if (!(acc.big < __int_as_float(KEYF_BIG))) atomicExch(p.poison, 1ull);
 }
 
-static size_t k2_smem_bytes() { return (size_t)K2_NST * K2_STAGE_BYTES + (size_t)2 * K2_NST * 8; }
+static size_t k2_smem_bytes(int ctas) { return (size_t)k2_nst(ctas) * K2_STAGE_BYTES + (size_t)2 * k2_nst(ctas) * 8; }
+static int k2_ctas() {
+  static const int v = [] { const char *e = std::getenv("FTKB_K2_CTAS"); const int n = e ? std::atoi(e) : 3; return n >= 2 && n <= 4 ? n : 3; }();
+  return v;
+}
+template <int CTAS>
+static void k2_launch(const SweepParams &p, unsigned grid, cudaStream_t s) {
+  const size_t sm = k2_smem_bytes(CTAS);
+  switch (p.sum_mode) {
+    case SUM_BUILD: scan2d_keys_build_kernel<0, false, CTAS><<<grid, (C2_CW + 1) * 32, sm, s>>>(p); break;
+    case SUM_BUILD_TEST1: scan2d_keys_build_kernel<0, true, CTAS><<<grid, (C2_CW + 1) * 32, sm, s>>>(p); break;
+    default: scan2d_keys_build_kernel<1, true, CTAS><<<grid, (C2_CW + 1) * 32, sm, s>>>(p); break;
+  }
+}
+template <int CTAS>
+static void k2_attrs() {
+  const int sm = (int)k2_smem_bytes(CTAS);
+  cudaFuncSetAttribute(scan2d_keys_build_kernel<0, false, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+  cudaFuncSetAttribute(scan2d_keys_build_kernel<0, true, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+  cudaFuncSetAttribute(scan2d_keys_build_kernel<1, true, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+}
 
 static size_t c2_smem_bytes() { return (size_t)C2_NST * TL_SEG * 8 + (size_t)2 * C2_NST * 8; }
 
@@ -1409,13 +1413,10 @@ void launch_scan2d_cells(const SweepParams &p, cudaStream_t s) {
   const int nstrips = (p.W + FB_STRIDE - 1) / FB_STRIDE, nblk = (p.H + C2_R - 1) / C2_R;
   const unsigned tgrid = (unsigned)(((i64)nstrips * nblk + 7) / 8);
   if (p.keys2d && p.sum_mode <= SUM_BUILD_TEST2) {
-    // persistent: two CTAs per SM, never more CTAs than 9-row blocks
-    const i64 total = (i64)p.nsx * ((p.H + C2_R - 1) / C2_R);
-    const unsigned pgrid = (unsigned)std::max<i64>(1, std::min<i64>(total, 2 * (i64)(p.sm_count > 0 ? p.sm_count : 148)));
-    switch (p.sum_mode) {
-      case SUM_BUILD: scan2d_keys_build_kernel<0, false><<<pgrid, (C2_CW + 1) * 32, k2_smem_bytes(), s>>>(p); break;
-      case SUM_BUILD_TEST1: scan2d_keys_build_kernel<0, true><<<pgrid, (C2_CW + 1) * 32, k2_smem_bytes(), s>>>(p); break;
-      default: scan2d_keys_build_kernel<1, true><<<pgrid, (C2_CW + 1) * 32, k2_smem_bytes(), s>>>(p); break;
+    switch (k2_ctas()) {
+      case 2: k2_launch<2>(p, grid, s); break;
+      case 4: k2_launch<4>(p, grid, s); break;
+      default: k2_launch<3>(p, grid, s); break;
     }
     return;
   }
@@ -2679,9 +2680,7 @@ void init_kernel_attributes() {
   cudaFuncSetAttribute(scan3d_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused3d_smem_bytes(true));
   cudaFuncSetAttribute(scan3d_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused3d_smem_bytes(false));
   cudaFuncSetAttribute(scan2d_build_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c2_smem_bytes());
-  cudaFuncSetAttribute(scan2d_keys_build_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2_smem_bytes());
-  cudaFuncSetAttribute(scan2d_keys_build_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2_smem_bytes());
-  cudaFuncSetAttribute(scan2d_keys_build_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2_smem_bytes());
+  k2_attrs<2>(); k2_attrs<3>(); k2_attrs<4>();
   cudaFuncSetAttribute(scan2d_build_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c2_smem_bytes());
   cudaFuncSetAttribute(scan2d_build_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c2_smem_bytes());
   cudaFuncSetAttribute(scan3d_build_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s3_smem_bytes());
@@ -3369,7 +3368,7 @@ static void init_carveouts() {
   const int co = cudaSharedmemCarveoutMaxShared;
 #define CARVE(k) cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, co)
   CARVE(test_kernel<2>); CARVE(test_kernel<3>);
-  CARVE((scan2d_keys_build_kernel<0, false>)); CARVE((scan2d_keys_build_kernel<0, true>)); CARVE((scan2d_keys_build_kernel<1, true>));
+  CARVE((scan2d_keys_build_kernel<0, false, 3>)); CARVE((scan2d_keys_build_kernel<0, true, 3>)); CARVE((scan2d_keys_build_kernel<1, true, 3>));
   CARVE((scan2d_build_kernel<0, false>)); CARVE((scan2d_build_kernel<0, true>)); CARVE((scan2d_build_kernel<1, true>));
   CARVE((scan3d_build_kernel<0, false>)); CARVE((scan3d_build_kernel<0, true>)); CARVE((scan3d_build_kernel<1, true>));
   CARVE((vscan2d_build_kernel<0, false>)); CARVE((vscan2d_build_kernel<0, true>)); CARVE((vscan2d_build_kernel<1, true>));

@@ -349,7 +349,7 @@ def canonical_trajectories(trajs):
 
 
 def run_reference(nd, nv, dims, T, gen=None, params=None, input_array=None, out=None, trace=True, domain=None,
-                  symmetric=None, nthreads=0, timeout=3600, coords=None):
+                  symmetric=None, nthreads=0, timeout=3600, coords=None, start_timestep=0):
     """Run the unmodified reference binary (oracle/_ref).  Returns (stats dict, golden dict or None)."""
     import json
     import tempfile
@@ -372,6 +372,8 @@ def run_reference(nd, nv, dims, T, gen=None, params=None, input_array=None, out=
         cmd += ["--symmetric", str(int(symmetric))]
     if nthreads:
         cmd += ["--nthreads", str(nthreads)]
+    if start_timestep:
+        cmd += ["--start-timestep", str(int(start_timestep))]
     if not trace:
         cmd += ["--no-trace"]
     tmp_coords = None
