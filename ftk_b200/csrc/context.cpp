@@ -628,6 +628,7 @@ static void fused3d_decomposition(const ftkb_ctx *c, SweepParams &p, bool cells 
     const int64_t nsz = std::max<int64_t>(1, std::min<int64_t>((6 * slots + tiles - 1) / tiles, std::max(1, p.D / 16)));
     p.rows = (int)((p.D + nsz - 1) / nsz);
     if (const char *e = std::getenv("FTKB_S3_ROWS")) p.rows = std::max(1, std::min(p.D, std::atoi(e)));   // A/B measurements
+    p.rows = std::min(p.rows, 63);       // the build kernels keep one fail bit per corner plane of a chunk
     p.nsz = (p.D + p.rows - 1) / p.rows;
     return;
   }

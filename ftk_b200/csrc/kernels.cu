@@ -1779,6 +1779,18 @@ __device__ __noinline__ bool s3_union_excluded_precise(const float mn0, const fl
   return cube_excluded3(x, y, z);
 }
 
+// exponent-level part of s3_test: true = every cube of the block is excluded (see s3_test for the bound)
+__device__ __forceinline__ bool s3_excluded_level1(const S3Thresholds &T, const float (&cmn)[3], const float (&cmx)[3]) {
+  bool sided = false;
+  int esum = 0;
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    sided = sided || cmn[c] >= T.kthr || cmx[c] <= -T.kthr;
+    esum += (__float_as_int(fmaxf(fmaxf(fabsf(cmn[c]), fabsf(cmx[c])), T.kfloor)) >> 20);
+  }
+  return sided && esum <= T.esum_max && !(cmn[0] != cmn[0]);
+}
+
 // decide corner plane zc of this lane's 2 x S3_RW cubes from the union of the cells of planes zc, zc+1 (all layers)
 __device__ __forceinline__ void s3_test(const SweepParams &p, const S3Thresholds &T, const float (&cmn)[3], const float (&cmx)[3],
                                         const bool own_any, const int e, const int y0, const int zc, const int nl) {
@@ -1810,6 +1822,22 @@ __device__ __forceinline__ void s3_test(const SweepParams &p, const S3Thresholds
 
 __device__ __forceinline__ size_t s3_cell_index(const SweepParams &p, const int tile, const int wib, const int z, const int lane) {
   return (((size_t)tile * F3_CW + (size_t)wib) * (size_t)(p.D + 1) + (size_t)z) * 32u + (size_t)lane;
+}
+
+// cold path of the build kernels: corner plane zc of one warp's blocks, decided from the cells in memory (those of the layer
+// being built were written by these very threads: plain loads; the other layer's cells are read-only here)
+__device__ __noinline__ void s3_retest_plane(const SweepParams &p, const uint4 *built, const uint4 *other, const bool fail, const bool vec,
+                                             const int e, const int y0, const int zc, const int zc0) {
+  if (!__any_sync(0xffffffffu, fail)) return;
+  const S3Thresholds T = s3_thresholds(p.nbits, vec);
+  const float nanf_ = __int_as_float(KEYF_NAN);
+  float cmn[3] = {nanf_, nanf_, nanf_}, cmx[3] = {nanf_, nanf_, nanf_};
+#pragma unroll
+  for (int dz = 0; dz < 2; dz++) {
+    merge_cell(cmn, cmx, built[(size_t)(zc - zc0 + dz) * 32u]);
+    if (other) merge_cell(cmn, cmx, __ldg(other + (size_t)(zc - zc0 + dz) * 32u));
+  }
+  s3_test(p, T, cmn, cmx, fail, e, y0, zc, other ? 2 : 1);
 }
 
 // exact (cold) part of the running min non-zero |v|: entered only when a key of this row undercuts the best so far
@@ -1857,6 +1885,7 @@ struct S3Build {
   uint32_t pcell[3];         // previous plane's merged cell (packed like a stored cell)
   int st_c, st_p;
   uint32_t par_p;
+  unsigned long long failbits;   // bit (zc - zc0): corner plane zc of this lane's block failed the exponent-level test (decided after the loop)
   const uint4 *sum_prev;     // cells of the current layer at the plane being processed (this warp, this lane)
   uint4 *sum_out;            // cells of the layer being built, likewise
 
@@ -1926,7 +1955,8 @@ struct S3Build {
           // (no key of this row is below rkey here, so none of the six values is zero)
           if (!go) go = fabs(dxe) < r2 || fabs(dye) < r2 || fabs(dze) < r2 || fabs(dxo) < r2 || fabs(dyo) < r2 || fabs(dzo) < r2;
           if (go) {
-            rmin = s3_res_row(rmin, in_e, in_o, dxe, dye, dze, dxo, dyo, dzo);
+            res_update3(rmin, in_e, dxe, dye, dze);       // inline: a call here would cost the plane loop its registers
+            res_update3(rmin, in_o, dxo, dyo, dzo);
             r2 = 2.0 * fabs(rmin);
             rkey = rmin == DBL_MAX ? inff_ : hikey(r2);      // nothing found yet: keep accepting every key
           }
@@ -1973,7 +2003,9 @@ struct S3Build {
         if (zc_ >= p.lb[2] && zc_ <= p.ub[2]) {
           float cmn[3] = {umin[0], umin[1], umin[2]}, cmx[3] = {umax[0], umax[1], umax[2]};
           merge_cell(cmn, cmx, make_uint4(pcell[0], pcell[1], pcell[2], 0u));
-          s3_test(p, T, cmn, cmx, own_any, e, y0, zc_, NPREV + 1);
+          // only the exponent-level test runs here; a union it cannot exclude is noted (one bit per corner plane of the chunk) and
+          // decided after the plane loop from the stored cells -- the hot loop contains no call and keeps its registers
+          if (own_any && !s3_excluded_level1(T, cmn, cmx)) failbits |= 1ull << (zc_ - zc0);
         }
       }
 #pragma unroll
@@ -2021,6 +2053,7 @@ __device__ __forceinline__ void s3_consume(const SweepParams &p, const uint32_t 
   s.rkey = __int_as_float(0x7F800000);
 #pragma unroll
   for (int c = 0; c < 3; c++) s.pcell[c] = 0x7FC07FC0u;
+  s.failbits = 0;
   const size_t cell0 = s3_cell_index(p, tile, wib, zc0, lane);
   s.sum_prev = NPREV ? p.sum_in[0] + cell0 : nullptr;
   s.sum_out = p.sum_out + cell0;
@@ -2041,6 +2074,15 @@ __device__ __forceinline__ void s3_consume(const SweepParams &p, const uint32_t 
   }
   if (s.want_res) warp_res_commit(fabs(s.rmin), p.res_slot[B]);
   if (s.bad) atomicExch(p.poison, 1ull);
+  if (TEST) {
+    // cold path: the corner planes whose cell union the exponent-level test could not exclude (a chunk has at most 64 planes)
+    const unsigned long long fb = s.failbits;
+    const int e = s.e, y0 = s.y0;
+    for (int b = 0; b <= zc1 - zc0; b++) {
+      if (!__any_sync(0xffffffffu, (fb >> b) != 0)) break;
+      s3_retest_plane(p, p.sum_out + cell0, NPREV ? p.sum_in[0] + cell0 : nullptr, (fb >> b) & 1ull, false, e, y0, zc0 + b, zc0);
+    }
+  }
 }
 
 template <int NPREV, bool TEST>
