@@ -108,7 +108,8 @@ struct ftkb_ctx {
   cudaEvent_t ev_join = nullptr;
   bool debug_timing = false;         // FTKB_DEBUG_TIMING=1: report the sweep stream's idle time between scans at destroy
   double gap_ms = 0; uint64_t gap_n = 0, last_confirmed_seq = 0;
-  std::vector<float> gaps;
+  std::vector<float> gaps, tl_scan_end, tl_test_end;
+  cudaEvent_t dbg_prev = nullptr; bool dbg_prev_valid = false;
   double host_wait_us = 0, host_enq_us = 0; uint64_t host_wait_n = 0, host_enq_n = 0;
   bool overlap_test = true;          // FTKB_TEST_OVERLAP=0: test kernels stay on the sweep's stream
   bool has_producer = false;
@@ -200,11 +201,10 @@ static int drain(ftkb_ctx *c);
 extern "C" void ftkb_destroy(ftkb_ctx *c) {
   if (!c) return;
   (void)wait_grow(c);
-  if (c->debug_timing && c->gap_n) {
-    std::sort(c->gaps.begin(), c->gaps.end());
-    std::fprintf(stderr, "[ftkb] sweep stream idle between scans: median %.2f us, min %.2f, p90 %.2f over %llu steps (scan %.1f us, test %.1f us avg)\n",
-                 1e3 * c->gaps[c->gaps.size() / 2], 1e3 * c->gaps.front(), 1e3 * c->gaps[c->gaps.size() * 9 / 10],
-                 (unsigned long long)c->gap_n, 1e3 * c->stats.ms_scan / std::max<uint64_t>(1, c->stats.scan_launches), 1e3 * c->stats.ms_test / std::max<uint64_t>(1, c->stats.scan_launches));
+  if (c->debug_timing && c->gaps.size() > 8) {
+    auto med = [](std::vector<float> v) { std::sort(v.begin(), v.end()); return 1e3 * v[v.size() / 2]; };
+    std::fprintf(stderr, "[ftkb] deferred steps, relative to the previous scan's end (medians over %zu): scan starts +%.1f us, ends +%.1f us, test ends +%.1f us\n",
+                 c->gaps.size(), med(c->gaps), med(c->tl_scan_end), med(c->tl_test_end));
     std::fprintf(stderr, "[ftkb] host: %.1f us to enqueue a step, %.1f us blocked per confirmation (avg over %llu / %llu)\n",
                  c->host_enq_us / std::max<uint64_t>(1, c->host_enq_n), c->host_wait_us / std::max<uint64_t>(1, c->host_wait_n),
                  (unsigned long long)c->host_enq_n, (unsigned long long)c->host_wait_n);
@@ -224,6 +224,7 @@ extern "C" void ftkb_destroy(ftkb_ctx *c) {
   if (c->h_ring) cudaFreeHost(c->h_ring);
   for (auto &es : c->dev) for (auto &e : es) if (e) cudaEventDestroy(e);
   if (c->ev_input) cudaEventDestroy(c->ev_input);
+  if (c->dbg_prev) cudaEventDestroy(c->dbg_prev);
   cudaFree(c->d_wl);
   cudaFree(c->d_wl2);
   if (c->stream2) { cudaStreamSynchronize(c->stream2); cudaStreamDestroy(c->stream2); }
@@ -322,6 +323,7 @@ extern "C" int ftkb_create(const ftkb_config *cfg, ftkb_ctx **out) {
     if ((e = cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming)) != cudaSuccess) return bail(std::string("cudaEventCreate: ") + cudaGetErrorString(e), FTKB_ERR_CUDA);
     if (const char *o = std::getenv("FTKB_TEST_OVERLAP")) c->overlap_test = std::string(o) != "0";
     if (const char *o = std::getenv("FTKB_DEBUG_TIMING")) c->debug_timing = std::string(o) == "1";
+    if (c->debug_timing) cudaEventCreate(&c->dbg_prev);
   }
   c->pt_cap = cfg->point_capacity ? cfg->point_capacity : (1 << 18);
   if ((e = cudaMalloc(&c->d_pts, sizeof(ftkb_point) * c->pt_cap)) != cudaSuccess) return bail("cudaMalloc(points) failed", FTKB_ERR_NOMEM);
@@ -879,13 +881,20 @@ static int confirm_front(ftkb_ctx *c) {
   CK(cudaEventElapsedTime(&ms_scan, c->dev[pd.evset][0], c->dev[pd.evset][1]));
   CK(cudaEventElapsedTime(&ms_test, c->dev[pd.evset][1], c->dev[pd.evset][2]));
   c->stats.ms_scan += ms_scan; c->stats.ms_test += ms_test; c->stats.last_ms_scan = ms_scan;
-  if (c->debug_timing && c->last_confirmed_seq + 1 == pd.seq) {
-    // idle time of the sweep's stream between the previous step's scan and this one's (diagnostic, FTKB_DEBUG_TIMING=1)
-    float gap = 0;
-    if (cudaEventElapsedTime(&gap, c->dev[1 - pd.evset][1], c->dev[pd.evset][0]) == cudaSuccess) { c->gap_ms += gap; c->gap_n++; c->gaps.push_back(gap); }
-    else cudaGetLastError();
+  if (c->debug_timing) {
+    // timeline of the deferred steps (diagnostic, FTKB_DEBUG_TIMING=1): scan start / scan end / test end relative to the
+    // previous confirmed step's scan end
+    float s0 = 0, s1 = 0, s2 = 0;
+    if (c->dbg_prev_valid && cudaEventElapsedTime(&s0, c->dbg_prev, c->dev[pd.evset][0]) == cudaSuccess &&
+        cudaEventElapsedTime(&s1, c->dbg_prev, c->dev[pd.evset][1]) == cudaSuccess && cudaEventElapsedTime(&s2, c->dbg_prev, c->dev[pd.evset][2]) == cudaSuccess) {
+      c->gaps.push_back(s0);
+      c->tl_scan_end.push_back(s1);
+      c->tl_test_end.push_back(s2);
+    } else cudaGetLastError();
+    // keep this step's scan-end time in an event of its own (the per-step events are re-recorded two steps later)
+    std::swap(c->dbg_prev, c->dev[pd.evset][1]);
+    c->dbg_prev_valid = true;
   }
-  c->last_confirmed_seq = pd.seq;
   c->stats.scan_launches++;
   c->stats.cells_scanned += c->ncore;
   c->stats.cells_refined += nwl;
