@@ -76,6 +76,8 @@ EXPORTS = [
     "ftkb_ipc_export", "ftkb_ipc_import", "ftkb_ipc_close", "ftkb_export_layer_cells", "ftkb_push_snapshot_remote",
     "ftkb_set_streaming_trajectories", "ftkb_get_trajectory_complete", "ftkb_online_create", "ftkb_online_destroy", "ftkb_online_grow",
     "ftkb_online_size", "ftkb_online_get", "ftkb_set_coords", "ftkb_set_producer_stream", "ftkb_get_layer",
+    "ftkb_group_create", "ftkb_group_destroy", "ftkb_group_last_error", "ftkb_group_push_snapshot", "ftkb_group_push_synthetic",
+    "ftkb_group_advance_timestep", "ftkb_group_update_timestep", "ftkb_group_finalize", "ftkb_group_get_stats",
 ]
 
 _lib = None
@@ -141,6 +143,17 @@ def lib():
     L.ftkb_set_coords.argtypes = [vp, C.c_int, vp, C.c_uint64]
     L.ftkb_set_producer_stream.argtypes = [vp, vp, C.c_int]
     L.ftkb_get_layer.argtypes = [vp, C.c_int, vp, vp]
+    L.ftkb_group_create.argtypes = [C.POINTER(Config), C.POINTER(C.c_int32), C.c_int32, C.c_int32, C.POINTER(vp)]
+    L.ftkb_group_destroy.argtypes = [vp]
+    L.ftkb_group_destroy.restype = None
+    L.ftkb_group_last_error.argtypes = [vp]
+    L.ftkb_group_last_error.restype = C.c_char_p
+    L.ftkb_group_push_snapshot.argtypes = [vp, vp, vp, vp]
+    L.ftkb_group_push_synthetic.argtypes = [vp, C.c_int, C.POINTER(C.c_double), C.c_int, C.c_double]
+    L.ftkb_group_advance_timestep.argtypes = [vp]
+    L.ftkb_group_update_timestep.argtypes = [vp]
+    L.ftkb_group_finalize.argtypes = [vp, C.POINTER(vp)]
+    L.ftkb_group_get_stats.argtypes = [vp, C.POINTER(Stats), C.POINTER(C.c_int32)]
     L.ftkb_get_trajectory_complete.argtypes = [vp, vp]
     L.ftkb_online_create.argtypes = [C.c_int, vp, vp, C.POINTER(vp)]
     L.ftkb_online_destroy.argtypes = [vp]

@@ -14,11 +14,11 @@ LIB = os.path.join(HERE, "libftkb200.so")
 CLI = os.path.join(HERE, "bin", "ftkb200")          # `ftk -f cp` front end (C++ host code over the C ABI)
 CLI_SOURCES = [os.path.join(CSRC, "cli.cpp"), os.path.join(HERE, "..", "include", "ftk_b200", "critical_point_tracker_regular.hh"),
                os.path.join(HERE, "..", "include", "ftkb200.h")]
-SOURCES = ["kernels.cu", "context.cpp", "mesh_tables.cpp", "curves.cpp", "online.cpp"]
+SOURCES = ["kernels.cu", "context.cpp", "mesh_tables.cpp", "curves.cpp", "online.cpp", "group.cpp"]
 HEADERS = ["kernels.h", "mesh_tables.h", "curves.h", "online.h", os.path.join("..", "..", "include", "ftkb200.h")]
 # -fmad=false: the parity target is the reference's x86-64 CPU path (no FMA contraction)
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-fmad=false",
-              "-Xcompiler", "-fPIC,-O2,-Wall,-Wno-unused-function", "-shared", "--cudart", "static"]
+              "-Xcompiler", "-fPIC,-O2,-Wall,-Wno-unused-function", "-shared", "--cudart", "static", "-Xcompiler", "-pthread"]
 
 
 def nvcc():

@@ -28,7 +28,8 @@ struct Options {
   std::string feature = "cp", input, input_format = "float64", synthetic, output, output_type = "traced", output_format = "auto";
   std::string type_filter, accelerator = "cuda", var, post_process;
   long width = -1, height = -1, depth = -1, timesteps = -1;
-  int device = 0, nthreads = 0;
+  int device = 0, nthreads = 0, time_chunk = 8;
+  std::vector<int> devices;
   bool timing = false, compute_degrees = false, no_robust = false, verbose = false, device_generators = false, help = false, stream = false;
   std::vector<double> x0, dir;
   double time_scale = 0.1;
@@ -56,7 +57,8 @@ void usage() {
       "      --post-process OPS                smooth_types,rotate,split,discard_interval_points,reorder,adjust_time,derive_velocity,...\n"
       "      --compute-degrees  --no-robust-detection  --timing  -v/--verbose\n"
       "      --stream                          streaming trajectories: grown after every timestep (trace_critical_points_online)\n"
-      "  -a, --accelerator cuda            (the only back end)   --device ID   --nthreads N (ignored)\n"
+      "  -a, --accelerator cuda            (the only back end)   --device ID[,ID...]   --time-chunk N (timesteps per device turn, default 8)\n"
+      "      --nthreads N                  (ignored)\n"
       "      --device-generators           synthesise inputs on the GPU (CUDA libm; not bit-identical to the host generators)");
 }
 
@@ -98,7 +100,20 @@ Options parse(int argc, char **argv) {
     else if (a == "--affinity" || a == "--async") {}
     else if (a == "--timing") o.timing = true;
     else if (a == "-a" || a == "--accelerator") o.accelerator = need(i);
-    else if (a == "--device") o.device = std::atoi(need(i).c_str());
+    else if (a == "--device") {        // one id, or a comma-separated list: the tracker then runs on all of them (filter.hh:47-51)
+      o.devices.clear();
+      std::string v = need(i);
+      for (size_t pos = 0; pos <= v.size();) {
+        const size_t q = v.find(',', pos);
+        const std::string tok = v.substr(pos, q == std::string::npos ? std::string::npos : q - pos);
+        if (!tok.empty()) o.devices.push_back(std::atoi(tok.c_str()));
+        if (q == std::string::npos) break;
+        pos = q + 1;
+      }
+      if (o.devices.empty()) die("--device needs an id or a list of ids");
+      o.device = o.devices[0];
+    }
+    else if (a == "--time-chunk") o.time_chunk = std::atoi(need(i).c_str());
     else if (a == "--compute-degrees") o.compute_degrees = true;
     else if (a == "--no-robust-detection") o.no_robust = true;
     else if (a == "--device-generators") o.device_generators = true;
@@ -285,7 +300,8 @@ int main(int argc, char **argv) {
     }
     tr->set_number_of_threads(o.nthreads);
     tr->use_accelerator(o.accelerator);
-    tr->set_device_ids({o.device});
+    tr->set_device_ids(o.devices.empty() ? std::vector<int>{o.device} : o.devices);
+    tr->set_time_chunk(o.time_chunk);
     if (!o.type_filter.empty()) tr->set_type_filter(parse_type_filter(o.type_filter));
     if (o.compute_degrees) tr->set_enable_computing_degrees(true);
     if (o.stream) tr->set_enable_streaming_trajectories(true);      // json_interface.hh:324-325

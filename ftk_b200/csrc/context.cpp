@@ -338,7 +338,7 @@ extern "C" int ftkb_create(const ftkb_config *cfg, ftkb_ctx **out) {
 }
 
 static int take_buffer(ftkb_ctx *c, std::vector<double *> &pool, size_t count, double **out) {
-  if (pool.empty() && !c->pend.empty()) {
+  if (pool.empty() && !c->pend.empty() && c->layers.size() + c->limbo.size() >= 4) {
     // buffers of layers that enqueued steps still read come back once those steps are confirmed
     const int rc = drain(c);
     if (rc) return rc;
@@ -1062,8 +1062,8 @@ static int update_impl(ftkb_ctx *c, bool allow_defer) {
   // ---- deferred step: enqueue and return; the previous one is confirmed behind it ------------------------------------
   if (may_defer && cells_path && lay[0]->cells_valid && !p.no_filter) {
     if (has_next && !lay[1]->cells) {
-      const bool pool = !c->freeCells.empty();
-      if (!pool) { const int rc = drain(c); if (rc) return rc; }     // cudaMalloc would stall behind the queued work anyway
+      // (an empty pool means one more buffer: with a step in flight four layers hold cells -- the one in limbo, the two being
+      // swept and the one being built; confirming the step in flight first would serialise the steps again)
       const int rc0 = ensure_cells(c, *lay[1], p);
       if (rc0) return rc0;
     }

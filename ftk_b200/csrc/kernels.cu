@@ -1214,13 +1214,6 @@ __device__ __forceinline__ K2Acc keys2d_strip(const SweepParams &p, const int c0
   // the two 32-bit keys stay live
   double C[2][K2_R][2];
   float KX[2][K2_R][2];
-  // Exact running minima of the non-zero |d|, filtered by key: a difference can only undercut a minimum if its high word does
-  // not exceed the minimum's, so a stage / group first takes the smallest key of its six values (three FMNMX3) and runs the
-  // exact update (two DSETP + select per value) only when that key reaches the filter.  On the moving-extremum fields
-  // |dS/dy| shrinks row by row towards the extremum -- the y filter fires for half the rows -- while |dS/dx| never does.
-  const float inff_ = __int_as_float(0x7F800000);
-  float fkx = mdx == DBL_MAX ? inff_ : hikey(fabs(mdx)), fky = mdy == DBL_MAX ? inff_ : hikey(fabs(mdy));
-  const int jres = min(jl, H - 1);                    // last gradient row that counts for min |v|
   auto load_stage = [&](auto PC, const int s) {
     constexpr int P = decltype(PC)::value;
     const uint32_t gs = sbase + (uint32_t)s, slot = gs & (K2_NST - 1);
@@ -1236,7 +1229,6 @@ __device__ __forceinline__ K2Acc keys2d_strip(const SweepParams &p, const int c0
     }
     __syncwarp();
     if (elect_one()) mbar_arrive(empty0 + 8u * slot);   // the stage lives in registers now
-    double dxe[K2_R], dxo[K2_R];
 #pragma unroll
     for (int i = 0; i < K2_R; i++) {
       const float ke = fabsf(hikey(C[P][i][0])), ko = fabsf(hikey(C[P][i][1]));
@@ -1248,36 +1240,19 @@ __device__ __forceinline__ K2Acc keys2d_strip(const SweepParams &p, const int c0
         if (!o_in) mid_e = C[P][i][0];
         if (!o1_in) right = C[P][i][1];
       }
-      dxe[i] = mid_e - left; dxo[i] = right - C[P][i][0];
-      KX[P][i][0] = hikey(dxe[i]); KX[P][i][1] = hikey(dxo[i]);
-    }
-    if (!want_res) return;
-    const int j0 = r0 + K2_R * s - 1;                   // ring row i of this stage is the centre of gradient row j0 + i
-    if (!BORDER && s >= 1 && j0 + K2_R - 1 <= jres) {   // (warp-uniform) every row counts, every column is inside the array
-      const float a = fminf(fminf(fminf(fabsf(KX[P][0][0]), fabsf(KX[P][0][1])), fminf(fabsf(KX[P][1][0]), fabsf(KX[P][1][1]))),
-                            fminf(fabsf(KX[P][2][0]), fabsf(KX[P][2][1])));
-      static_assert(K2_R == 3, "three rows per stage");
-      if (a <= fkx) {
-#pragma unroll
-        for (int i = 0; i < K2_R; i++) { mdx = nzmin(mdx, dxe[i]); mdx = nzmin(mdx, dxo[i]); }
-        fkx = mdx == DBL_MAX ? inff_ : hikey(fabs(mdx));
+      const double dxe = mid_e - left, dxo = right - C[P][i][0];
+      KX[P][i][0] = hikey(dxe); KX[P][i][1] = hikey(dxo);
+      const int j = r0 + K2_R * s + i - 1;              // the gradient row this ring row is the centre of
+      if (want_res && j >= r0 && j <= jl && j < H) {
+        if (e_in) mdx = nzmin(mdx, dxe);
+        if (o_in) mdx = nzmin(mdx, dxo);
       }
-    } else {
-#pragma unroll
-      for (int i = 0; i < K2_R; i++) {
-        const int j = j0 + i;
-        if (j >= r0 && j <= jres) {
-          if (e_in) mdx = nzmin(mdx, dxe[i]);
-          if (o_in) mdx = nzmin(mdx, dxo[i]);
-        }
-      }
-      fkx = mdx == DBL_MAX ? inff_ : hikey(fabs(mdx));
     }
   };
 
   float bxmn = 0.f, bxmx = 0.f, bymn = 0.f, bymx = 0.f;
   const uint4 nanc = make_uint4(0x7FC00000u, 0x7FC00000u, 0x7FC00000u, 0x7FC00000u);
-  int kb = r0 / C2_R;                                  // the block the next opening row opens
+  int kb = r0 / C2_R;                                  // the block the next row with K == 0 opens
   const int kb_end = (jl + C2_R - 1) / C2_R;           // blocks kb .. kb_end-1 are closed by this segment
   // the other layer's cells are requested into L2 two blocks ahead of their use (a DRAM miss each: ~1 us) and loaded one
   // block ahead
@@ -1286,57 +1261,41 @@ __device__ __forceinline__ K2Acc keys2d_strip(const SweepParams &p, const int c0
   if (NPREV && kb + 1 < kb_end) prefetch_l2(sum_prev + (size_t)(kb + 1) * 32u);
 
   // group g = gradient rows r0 + 3 g + {0, 1, 2}; ring row q holds array row r0 - 1 + q, gradient row r0 + q reads ring rows
-  // q (below), q + 1 (centre, x neighbours), q + 2 (above).  PC: register set of stage g.  r0 is a multiple of C2_R = 9 = three
-  // groups, so only the first row of every third group opens a block (gphase counts groups since the last one).
+  // q (below), q + 1 (centre, x neighbours), q + 2 (above).  PC: register set of stage g; phase: rows since the last block opened.
+  // r0 is a multiple of C2_R = 9 = three groups: only the first row of every third group opens a block (gphase counts groups)
   int gphase = 0;
+  static_assert(C2_R == 3 * K2_R, "a cell block is three groups");
   auto group = [&](auto PC, const int g) {
     constexpr int P = decltype(PC)::value;
     if (g + 1 < nstages) load_stage(IC<1 - P>{}, g + 1);
-    const int j0 = r0 + K2_R * g;
-    const bool opens = gphase == 0;                     // warp-uniform
+    const bool opens_group = gphase == 0;               // warp-uniform
     gphase = gphase == 2 ? 0 : gphase + 1;
-    static_assert(C2_R == 3 * K2_R, "a cell block is three groups");
-    float kye[K2_R], kyo[K2_R];
-    auto dy = [&](const int i, const int q) {           // exact d/dy of gradient row j0 + i, column e + q
-      return (i + 2 < K2_R ? C[P][i + 2 < K2_R ? i + 2 : 0][q] : C[1 - P][i + 2 >= K2_R ? i + 2 - K2_R : 0][q]) - C[P][i][q];
-    };
-#pragma unroll
-    for (int i = 0; i < K2_R; i++) { kye[i] = hikey(dy(i, 0)); kyo[i] = hikey(dy(i, 1)); }
-    const bool full = j0 + K2_R - 1 <= jl;              // (warp-uniform) all three rows belong to the segment
-    if (want_res) {
-      if (!BORDER && j0 + K2_R - 1 <= jres) {
-        const float a = fminf(fminf(fminf(fabsf(kye[0]), fabsf(kyo[0])), fminf(fabsf(kye[1]), fabsf(kyo[1]))), fminf(fabsf(kye[2]), fabsf(kyo[2])));
-        if (a <= fky) {                                   // (the six differences are formed again: two registers each would stay live otherwise)
-#pragma unroll
-          for (int i = 0; i < K2_R; i++) { mdy = nzmin(mdy, dy(i, 0)); mdy = nzmin(mdy, dy(i, 1)); }
-          fky = mdy == DBL_MAX ? inff_ : hikey(fabs(mdy));
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < K2_R; i++)
-          if (j0 + i <= jres) {
-            if (e_in) mdy = nzmin(mdy, dy(i, 0));
-            if (o_in) mdy = nzmin(mdy, dy(i, 1));
-          }
-        fky = mdy == DBL_MAX ? inff_ : hikey(fabs(mdy));
-      }
-    }
+    const int j0 = r0 + K2_R * g;
+    const bool full = j0 + K2_R - 1 <= min(jl, H - 1);  // (warp-uniform) all three rows exist and count for min |v|
 #pragma unroll
     for (int i = 0; i < K2_R; i++) {
-      if (!full && j0 + i > jl) break;
+      const int j = j0 + i;
+      if (!full && j > jl) break;
+      const double *m1 = C[P][i];
       const float *kx = i + 1 < K2_R ? KX[P][i + 1] : KX[1 - P][i + 1 - K2_R];
-      const float kxe = kx[0], kxo = kx[1];
-      if (i == 0 && opens) {
+      const double *p1 = i + 2 < K2_R ? C[P][i + 2] : C[1 - P][i + 2 - K2_R];
+      const double dye = p1[0] - m1[0], dyo = p1[1] - m1[1];
+      const float kxe = kx[0], kxo = kx[1], kye = hikey(dye), kyo = hikey(dyo);
+      if (want_res && (full || j < H)) {
+        if (e_in) mdy = nzmin(mdy, dye);
+        if (o_in) mdy = nzmin(mdy, dyo);
+      }
+      if (i == 0 && opens_group) {
         // gradient row C2_R k closes block k-1 and opens block k
-        const float rxmn = fminf(kxe, kxo), rxmx = fmaxf(kxe, kxo), rymn = fminf(kye[0], kyo[0]), rymx = fmaxf(kye[0], kyo[0]);
-        if (j0 > r0) finish_block(kb - 1, fminf(bxmn, rxmn), fmaxf(bxmx, rxmx), fminf(bymn, rymn), fmaxf(bymx, rymx), prevc);
+        const float rxmn = fminf(kxe, kxo), rxmx = fmaxf(kxe, kxo), rymn = fminf(kye, kyo), rymx = fmaxf(kye, kyo);
+        if (j > r0) finish_block(kb - 1, fminf(bxmn, rxmn), fmaxf(bxmx, rxmx), fminf(bymn, rymn), fmaxf(bymx, rymx), prevc);
         bxmn = rxmn; bxmx = rxmx; bymn = rymn; bymx = rymx;
         if (NPREV && kb < kb_end) prevc = __ldg(sum_prev + (size_t)kb * 32u);     // cells of the block this row opens (in L2 by now)
         kb++;
         if (NPREV && kb + 1 < kb_end) prefetch_l2(sum_prev + (size_t)(kb + 1) * 32u);
       } else {
         bxmn = fminf(fminf(bxmn, kxe), kxo); bxmx = fmaxf(fmaxf(bxmx, kxe), kxo);
-        bymn = fminf(fminf(bymn, kye[i]), kyo[i]); bymx = fmaxf(fmaxf(bymx, kye[i]), kyo[i]);
+        bymn = fminf(fminf(bymn, kye), kyo); bymx = fmaxf(fmaxf(bymx, kye), kyo);
       }
     }
   };

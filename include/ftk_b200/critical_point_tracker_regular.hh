@@ -349,7 +349,10 @@ class critical_point_tracker_regular {
       throw std::runtime_error("ftk_b200 runs on CUDA sm_100a only; there is no CPU or other back end");
   }
   void use_accelerator(int) {}
-  void set_device_ids(const std::vector<int> &ids) { if (!ids.empty()) device_ = ids[0]; }
+  // filter.hh:47-51: one id = that device; several = the tracker is served by all of them (ftkb_group: time chunks of
+  // set_time_chunk() timesteps go round the devices; results equal the one-device run)
+  void set_device_ids(const std::vector<int> &ids) { device_ids_ = ids; if (!ids.empty()) device_ = ids[0]; }
+  void set_time_chunk(int timesteps) { time_chunk_ = timesteps > 0 ? timesteps : 8; }
   void set_start_timestep(int t) { start_timestep_ = t; }
   void set_current_timestep(int t) { start_timestep_ = t; }
   // time-slab sharding: running min non-zero |v| inherited from the slabs before this one
@@ -374,6 +377,14 @@ class critical_point_tracker_regular {
     cfg.jacobian_symmetric = symmetric_; cfg.robust_detection = robust_; cfg.compute_degrees = degrees_;
     cfg.use_type_filter = use_type_filter_; cfg.type_filter = type_filter_;
     cfg.start_timestep = start_timestep_; cfg.device = device_; cfg.resolution_init = resolution_init_;
+    if (device_ids_.size() > 1) {
+      if (streaming_) throw std::runtime_error("ftk_b200: streaming trajectories are not available on several devices");
+      if (coords_mode_ != FTKB_COORDS_SIMPLE) throw std::runtime_error("ftk_b200: physical coordinates are not available on several devices yet");
+      std::vector<int32_t> ids(device_ids_.begin(), device_ids_.end());
+      const int rcg = ftkb_group_create(&cfg, ids.data(), (int32_t)ids.size(), time_chunk_, &group_);
+      if (rcg != FTKB_OK) throw std::runtime_error("ftkb_group_create failed (device ids?)");
+      return;
+    }
     const int rc = ftkb_create(&cfg, &ctx_);
     if (rc != FTKB_OK) throw std::runtime_error(std::string("ftkb_create: ") + ftkb_last_error(nullptr));
     if (streaming_) check(ftkb_set_streaming_trajectories(ctx_, 1));
@@ -381,6 +392,7 @@ class critical_point_tracker_regular {
   }
 
   void reset() {
+    if (group_) { ftkb_group_destroy(group_); group_ = nullptr; ctx_ = nullptr; }       // (the group owns its root context)
     if (ctx_) { ftkb_destroy(ctx_); ctx_ = nullptr; }
     traced_.clear();
     points_valid_ = false;
@@ -398,6 +410,10 @@ class critical_point_tracker_regular {
     };
     const double *s = ptr(scalar, nvert, "scalar"), *v = ptr(vector, nvert * nd_, "vector"), *j = ptr(jacobian, nvert * nd_ * nd_, "jacobian");
     const bool dev = scalar.on_device() || vector.on_device() || jacobian.on_device();
+    if (group_) {
+      if (dev) throw std::runtime_error("ftk_b200: a tracker on several devices takes host snapshots");
+      gcheck(ftkb_group_push_snapshot(group_, s, v, j));
+    } else
     check(ftkb_push_snapshot(ctx_, s, v, j, dev ? FTKB_MEM_DEVICE : FTKB_MEM_HOST));
     points_valid_ = false;
   }
@@ -406,18 +422,21 @@ class critical_point_tracker_regular {
   // device-side generator (no host data): FTKB_SYN_* kinds of ftkb200.h
   void push_synthetic_snapshot(int kind, const std::vector<double> &params, double t) {
     need();
+    if (group_) gcheck(ftkb_group_push_synthetic(group_, kind, params.data(), (int)params.size(), t));
+    else
     check(ftkb_push_synthetic(ctx_, kind, params.data(), (int)params.size(), t));
     points_valid_ = false;
   }
 
   // ---- stepping: critical_point_tracker.hh:841-848, *_regular.hh update_timestep ------------------
-  void update_timestep() { need(); check(ftkb_update_timestep(ctx_)); points_valid_ = false; }
-  bool advance_timestep() { need(); check(ftkb_advance_timestep(ctx_)); points_valid_ = false; return true; }
+  void update_timestep() { need(); if (group_) gcheck(ftkb_group_update_timestep(group_)); else check(ftkb_update_timestep(ctx_)); points_valid_ = false; }
+  bool advance_timestep() { need(); if (group_) gcheck(ftkb_group_advance_timestep(group_)); else check(ftkb_advance_timestep(ctx_)); points_valid_ = false; return true; }
   int get_current_timestep() const { int32_t t = start_timestep_; if (ctx_) ftkb_current_timestep(ctx_, &t); return t; }
 
   // ---- finalize: critical_point_tracker_2d_regular.hh:143-225, critical_point_tracker.hh:668-817 --
   void finalize() {
     need();
+    ensure_root();     // several devices: merged into one context on the first device, traced there
     check(ftkb_finalize(ctx_));
     fetch_points();
     uint64_t nt = 0;
@@ -531,16 +550,26 @@ class critical_point_tracker_regular {
     o << "]" << std::endl;
   }
 
-  ftkb_stats stats() { need(); ftkb_stats s; check(ftkb_get_stats(ctx_, &s)); return s; }
+  ftkb_stats stats() {
+    need();
+    ftkb_stats s;
+    if (group_) { ensure_root(); gcheck(ftkb_group_get_stats(group_, &s, nullptr)); }     // sums over the chunks of all devices
+    else check(ftkb_get_stats(ctx_, &s));
+    return s;
+  }
   ftkb_ctx *handle() { return ctx_; }
 
  protected:
-  void need() const { if (!ctx_) throw std::runtime_error("ftk_b200: initialize() has not been called"); }
+  void need() const { if (!ctx_ && !group_) throw std::runtime_error("ftk_b200: initialize() has not been called"); }
+  // several devices: every result getter works on the merged context (ftkb_group_finalize)
+  void ensure_root() { if (group_ && !ctx_) gcheck(ftkb_group_finalize(group_, &ctx_)); }
+  void gcheck(int rc) const { if (rc != FTKB_OK) throw std::runtime_error(std::string("ftk_b200: ") + ftkb_group_last_error(group_)); }
   void check(int rc) const { if (rc != FTKB_OK) throw std::runtime_error(std::string("ftk_b200: ") + ftkb_last_error(ctx_)); }
 
   void fetch_points() {
     if (points_valid_) return;
     uint64_t n = 0;
+    ensure_root();
     check(ftkb_num_points(ctx_, &n));
     std::vector<ftkb_point> raw(n ? n : 1);
     if (n) check(ftkb_get_points(ctx_, raw.data(), n));
@@ -576,6 +605,9 @@ class critical_point_tracker_regular {
 
   int nd_;
   ftkb_ctx *ctx_ = nullptr;
+  ftkb_group *group_ = nullptr;        // several devices: ctx_ is the group's root context once finalize() has run
+  std::vector<int> device_ids_;
+  int time_chunk_ = 8;
   lattice domain_, array_domain_;
   int scalar_source_ = SOURCE_NONE, vector_source_ = SOURCE_NONE, jacobian_source_ = SOURCE_NONE;
   bool symmetric_ = false, robust_ = true, degrees_ = false, use_type_filter_ = false, discard_interval_ = false, discard_degenerate_ = false, streaming_ = false;

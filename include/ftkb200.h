@@ -196,6 +196,29 @@ int ftkb_ipc_close(void *dev_ptr, const ftkb_ipc_handle *h);
 int ftkb_export_layer_cells(ftkb_ctx *, int index, void **cells, uint64_t *bytes, double *resolution /* the layer's min non-zero |v| */);
 int ftkb_push_snapshot_remote(ftkb_ctx *, const double *scalar, const double *vector, const void *cells, double resolution);
 
+/* ---- several GPUs behind one tracker (the reference's filter::set_device_ids, filter.hh:47-51) ---------------
+ * One process, one caller thread, N devices.  Timesteps are cut into chunks of `chunk_timesteps`; chunk c is swept by a context
+ * of its own on device_ids[c mod n_devices] (a simplex belongs to the chunk that owns its corner time; the first layer of the
+ * next chunk is pushed to both: a one-layer halo), one host thread per device executes that device's pushes and sweeps in
+ * order, so the devices work on their chunks concurrently while the caller hands snapshots over in time order.  A chunk
+ * inherits the running minimum of min non-zero |v| (the quantisation factor is a running quantity) from its predecessor; it
+ * starts early once the minimum known so far saturates the factor, otherwise when the predecessor has finished -- results equal
+ * the one-device run bit for bit.  ftkb_group_finalize merges the punctured simplices of all chunks into one context on
+ * device_ids[0] and traces there; *root stays owned by the group and serves every getter (ftkb_get_points, ftkb_get_trajectories,
+ * ftkb_get_curveset ...).  cfg->device is ignored; streaming trajectories are not available on a group.
+ * ftkb_group_push_snapshot takes HOST memory (borrowed until return); ftkb_group_push_synthetic generates on the devices. */
+typedef struct ftkb_group ftkb_group;
+int ftkb_group_create(const ftkb_config *cfg, const int32_t *device_ids, int32_t n_devices, int32_t chunk_timesteps, ftkb_group **out);
+void ftkb_group_destroy(ftkb_group *);
+const char *ftkb_group_last_error(const ftkb_group *);
+int ftkb_group_push_snapshot(ftkb_group *, const double *scalar, const double *vector, const double *jacobian);
+int ftkb_group_push_synthetic(ftkb_group *, int kind, const double *params, int nparams, double t);
+int ftkb_group_advance_timestep(ftkb_group *);
+int ftkb_group_update_timestep(ftkb_group *);
+int ftkb_group_finalize(ftkb_group *, ftkb_ctx **root);
+/* sums over the chunks that have finished so far (scaling_factor / resolution: the latest finished chunk's) */
+int ftkb_group_get_stats(ftkb_group *, ftkb_stats *sum, int32_t *chunks_done);
+
 /* after ftkb_finalize: trajectories as CSR over the sorted point array */
 int ftkb_num_trajectories(ftkb_ctx *, uint64_t *n);
 int ftkb_get_trajectories(ftkb_ctx *, uint64_t *offsets /* n+1 */, uint64_t *point_idx, uint8_t *loop /* n */);
