@@ -41,6 +41,7 @@ class Stats(C.Structure):
         ("ms_finalize_host", C.c_double), ("last_ms_scan", C.c_double), ("last_ms_derive", C.c_double),
         ("scaling_factor", C.c_double), ("resolution", C.c_double),
         ("scan_launches", C.c_uint64), ("sweeps_repeated", C.c_uint64),
+        ("ms_sort_wall", C.c_double), ("ms_trace_wall", C.c_double),
     ]
 
     def as_dict(self):
@@ -78,6 +79,7 @@ EXPORTS = [
     "ftkb_online_size", "ftkb_online_get", "ftkb_set_coords", "ftkb_set_producer_stream", "ftkb_get_layer",
     "ftkb_group_create", "ftkb_group_destroy", "ftkb_group_last_error", "ftkb_group_push_snapshot", "ftkb_group_push_synthetic",
     "ftkb_group_advance_timestep", "ftkb_group_update_timestep", "ftkb_group_finalize", "ftkb_group_get_stats",
+    "ftkb_host_alloc", "ftkb_host_free",
 ]
 
 _lib = None
@@ -154,6 +156,9 @@ def lib():
     L.ftkb_group_update_timestep.argtypes = [vp]
     L.ftkb_group_finalize.argtypes = [vp, C.POINTER(vp)]
     L.ftkb_group_get_stats.argtypes = [vp, C.POINTER(Stats), C.POINTER(C.c_int32)]
+    L.ftkb_host_alloc.argtypes = [C.c_uint64, C.POINTER(vp)]
+    L.ftkb_host_free.argtypes = [vp]
+    L.ftkb_host_free.restype = None
     L.ftkb_get_trajectory_complete.argtypes = [vp, vp]
     L.ftkb_online_create.argtypes = [C.c_int, vp, vp, C.POINTER(vp)]
     L.ftkb_online_destroy.argtypes = [vp]

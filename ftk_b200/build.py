@@ -40,7 +40,7 @@ def build_cli(force=False):
     if not force and os.path.exists(CLI) and all(os.path.getmtime(f) <= os.path.getmtime(CLI) for f in CLI_SOURCES + [LIB]):
         return CLI
     os.makedirs(os.path.dirname(CLI), exist_ok=True)
-    cmd = ["g++", "-O2", "-std=c++17", "-Wall", CLI_SOURCES[0], "-o", CLI, "-L" + HERE, "-lftkb200", "-Wl,-rpath,$ORIGIN/.."]
+    cmd = ["g++", "-O2", "-std=c++17", "-Wall", "-pthread", CLI_SOURCES[0], "-o", CLI, "-L" + HERE, "-lftkb200", "-Wl,-rpath,$ORIGIN/.."]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)

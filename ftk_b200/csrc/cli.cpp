@@ -9,6 +9,10 @@
 // C ABI of libftkb200.so; every per-simplex computation runs on the GPU.  Without a B200 the
 // program fails with the library's error message -- there is no CPU path.
 #include <chrono>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
+#include <thread>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -247,6 +251,58 @@ double now() { return std::chrono::duration<double>(std::chrono::steady_clock::n
 
 }  // namespace
 
+// Double-buffered source of host snapshots: a reader thread fills page-locked buffers ahead of the consumer.
+struct Feed {
+  static constexpr int NB = 2;
+  double *buf[NB] = {nullptr, nullptr};
+  std::thread th;
+  std::mutex m;
+  std::condition_variable cv;
+  long produced = 0, consumed = 0, total = 0;
+  bool pinned = false, failed = false;
+  std::string error;
+  ~Feed() {
+    { std::lock_guard<std::mutex> lk(m); consumed = total; }
+    cv.notify_all();
+    if (th.joinable()) th.join();
+    for (double *b : buf) { if (pinned) ftkb_host_free(b); else std::free(b); }
+  }
+  void start(long T, size_t count, std::function<void(long, double *)> fill) {
+    total = T;
+    pinned = true;
+    for (int i = 0; i < NB; i++) {
+      void *p = nullptr;
+      if (ftkb_host_alloc(count * sizeof(double), &p) != FTKB_OK) { pinned = false; break; }
+      buf[i] = static_cast<double *>(p);
+    }
+    if (!pinned)      // no device / no pinned memory: plain buffers (the tracker will fail loudly later if there is no device)
+      for (int i = 0; i < NB; i++) { if (buf[i]) ftkb_host_free(buf[i]); buf[i] = static_cast<double *>(std::malloc(count * sizeof(double))); }
+    th = std::thread([this, fill] {
+      for (long k = 0; k < total; k++) {
+        {
+          std::unique_lock<std::mutex> lk(m);
+          cv.wait(lk, [&] { return k - consumed < NB || consumed >= total; });
+          if (consumed >= total) return;
+        }
+        try { fill(k, buf[k % NB]); }
+        catch (const std::exception &e) { std::lock_guard<std::mutex> lk(m); failed = true; error = e.what(); }
+        { std::lock_guard<std::mutex> lk(m); produced = k + 1; }
+        cv.notify_all();
+      }
+    });
+  }
+  double *get(long k) {
+    std::unique_lock<std::mutex> lk(m);
+    cv.wait(lk, [&] { return produced > k || failed; });
+    if (failed) throw std::runtime_error(error);
+    return buf[k % NB];
+  }
+  void release(long k) {
+    { std::lock_guard<std::mutex> lk(m); consumed = k + 1; }
+    cv.notify_all();
+  }
+};
+
 int main(int argc, char **argv) {
   Options o = parse(argc, argv);
   if (o.help || argc == 1) { usage(); return 0; }
@@ -311,10 +367,22 @@ int main(int argc, char **argv) {
 
     size_t nvert = 1;
     for (int i = 0; i < nd; i++) nvert *= (size_t)dims[i];
-    std::vector<double> buf(nvert * nv);
     std::vector<size_t> shape;
     if (nv > 1) shape.push_back(nv);
     for (int i = 0; i < nd; i++) shape.push_back((size_t)dims[i]);
+    // host-side sources (files, host generators): two page-locked buffers and a reader thread -- snapshot k+1 is read (or
+    // generated) and converted while snapshot k travels to the device and is swept (the reference overlaps I/O and compute the
+    // same way, ndarray/stream.hh:1607-1699)
+    Feed feed;
+    if (!(syn >= 0 && o.device_generators))
+      feed.start(T, nvert * nv, [&](long k, double *dst) {
+        if (syn == FTKB_SYN_WOVEN) gen_woven(dims[0], dims[1], T == 1 ? 0.0 : double(k) / (T - 1), dst);        // stream.hh:1468-1480
+        else if (syn == FTKB_SYN_MERGER) gen_merger(dims[0], dims[1], double(k) * 0.1, dst);                   // stream.hh:1540
+        else if (syn == FTKB_SYN_DOUBLE_GYRE) gen_double_gyre(dims[0], dims[1], k * o.time_scale, dst);        // stream.hh:1542-1555
+        else if (syn == FTKB_SYN_TORNADO) gen_tornado(dims[0], dims[1], dims[2], (int)k, dst);                  // stream.hh:1560-1567
+        else if (syn == FTKB_SYN_MOVING_EXTREMUM) gen_moving_extremum(nd, dims, o.x0.data(), o.dir.data(), double(k), dst);
+        else read_raw(o, k, nvert * nv, o.input_format == "float32", dst);
+      });
     for (long k = 0; k < T; k++) {
       if (o.verbose) std::fprintf(stderr, "current_timestep=%ld\n", k);
       if (syn >= 0 && o.device_generators) {
@@ -326,14 +394,10 @@ int main(int argc, char **argv) {
         else { p = o.x0; p.insert(p.end(), o.dir.begin(), o.dir.end()); }
         tr->push_synthetic_snapshot(syn, p, t);
       } else {
-        if (syn == FTKB_SYN_WOVEN) gen_woven(dims[0], dims[1], T == 1 ? 0.0 : double(k) / (T - 1), buf.data());        // stream.hh:1468-1480
-        else if (syn == FTKB_SYN_MERGER) gen_merger(dims[0], dims[1], double(k) * 0.1, buf.data());                   // stream.hh:1540
-        else if (syn == FTKB_SYN_DOUBLE_GYRE) gen_double_gyre(dims[0], dims[1], k * o.time_scale, buf.data());        // stream.hh:1542-1555
-        else if (syn == FTKB_SYN_TORNADO) gen_tornado(dims[0], dims[1], dims[2], (int)k, buf.data());                  // stream.hh:1560-1567
-        else if (syn == FTKB_SYN_MOVING_EXTREMUM) gen_moving_extremum(nd, dims, o.x0.data(), o.dir.data(), double(k), buf.data());
-        else read_raw(o, k, nvert * nv, o.input_format == "float32", buf.data());
-        const ndarray<double> a = ndarray<double>::wrap(buf.data(), shape);
+        double *buf = feed.get(k);                   // filled by the reader thread while the previous snapshot was pushed and swept
+        const ndarray<double> a = ndarray<double>::wrap(buf, shape);
         if (nv == 1) tr->push_scalar_field_snapshot(a); else tr->push_vector_field_snapshot(a);
+        feed.release(k);                             // (the push copies before it returns)
       }
       if (k != 0) tr->advance_timestep();          // json_interface.hh:699-706
       if (k == T - 1) tr->update_timestep();

@@ -121,6 +121,10 @@ struct ftkb_ctx {
   ftkb_point *d_pts = nullptr;
   uint64_t pt_cap = 0, npts = 0;
 
+  // finalize scratch (sort keys / indices, cub temp storage, neighbour lists, union-find parents): kept between calls, grown on demand
+  struct Scratch { void *p = nullptr; size_t cap = 0; };
+  Scratch fz[9];
+
   // sorted / traced results (host)
   bool sorted = false, traced = false;
   std::vector<ftkb_point> pts_sorted;
@@ -163,6 +167,20 @@ static int fail(ftkb_ctx *c, int code, const std::string &msg) {
   if (c) c->error = msg;
   else g_create_error = msg;
   return code;
+}
+
+// pooled device scratch of ensure_sorted / ftkb_finalize: slot i holds at least `bytes`
+static int scratch(ftkb_ctx *c, int i, size_t bytes, void **out) {
+  ftkb_ctx::Scratch &s = c->fz[i];
+  if (s.cap < bytes) {
+    cudaFree(s.p);
+    s.p = nullptr; s.cap = 0;
+    const size_t want = bytes + bytes / 4 + 256;
+    if (cudaMalloc(&s.p, want) != cudaSuccess) { cudaGetLastError(); c->error = "finalize: out of device memory"; return FTKB_ERR_NOMEM; }
+    s.cap = want;
+  }
+  *out = s.p;
+  return FTKB_OK;
 }
 
 static int check_launch(ftkb_ctx *c, const char *what) {
@@ -233,6 +251,7 @@ extern "C" void ftkb_destroy(ftkb_ctx *c) {
   cudaFree(c->d_coords);
   cudaFree(c->d_pts_sorted);
   cudaFree(c->d_keys_sorted);
+  for (auto &s : c->fz) cudaFree(s.p);
   for (auto &e : c->ev) if (e) cudaEventDestroy(e);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
@@ -1329,24 +1348,27 @@ static int ensure_sorted(ftkb_ctx *c) {
   if (n >= 0xffffffffull) return fail(c, FTKB_ERR_OVERFLOW, "more than 2^32 punctured simplices");
   TraceParams tp{};
   fill_trace_params(c, tp);
+  const auto tw0 = std::chrono::steady_clock::now();
   unsigned long long *k0 = nullptr, *k1 = nullptr;
   uint32_t *i0 = nullptr, *i1 = nullptr;
   void *temp = nullptr;
-  auto cleanup = [&]() { cudaFree(k0); cudaFree(k1); cudaFree(i0); cudaFree(i1); cudaFree(temp); };
-#define CKC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); c->error = std::string(#call) + ": " + cudaGetErrorString(e_); return FTKB_ERR_CUDA; } } while (0)
-  CKC(cudaMalloc(&k0, 8 * n)); CKC(cudaMalloc(&k1, 8 * n)); CKC(cudaMalloc(&i0, 4 * n)); CKC(cudaMalloc(&i1, 4 * n));
+#define CKC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { c->error = std::string(#call) + ": " + cudaGetErrorString(e_); return FTKB_ERR_CUDA; } } while (0)
+  { int rs = scratch(c, 0, 8 * n, (void **)&k0); if (!rs) rs = scratch(c, 1, 8 * n, (void **)&k1); if (!rs) rs = scratch(c, 2, 4 * n, (void **)&i0);
+    if (!rs) rs = scratch(c, 3, 4 * n, (void **)&i1); if (rs) return rs; }
   CKC(cudaEventRecord(c->ev[0], c->stream));
   launch_point_keys(c->d_pts, n, tp, k0, i0, c->stream);
   size_t tb = std::max(sort_pairs_u64(nullptr, 0, k0, k1, i0, i1, n, c->stream),
                        unique_by_key_u64(nullptr, 0, k1, i1, k0, i0, c->d_scalars + ftkb_ctx::SLOT_UQ, n, c->stream));
-  CKC(cudaMalloc(&temp, tb));
+  { const int rs = scratch(c, 4, tb, &temp); if (rs) return rs; }
   sort_pairs_u64(temp, tb, k0, k1, i0, i1, n, c->stream);
   unique_by_key_u64(temp, tb, k1, i1, k0, i0, c->d_scalars + ftkb_ctx::SLOT_UQ, n, c->stream);
   CKC(cudaMemcpyAsync(c->h_scalars + ftkb_ctx::SLOT_UQ, c->d_scalars + ftkb_ctx::SLOT_UQ, 8, cudaMemcpyDeviceToHost, c->stream));
   CKC(cudaStreamSynchronize(c->stream));
   const uint64_t nu = c->h_scalars[ftkb_ctx::SLOT_UQ];
   CKC(cudaMalloc(&c->d_pts_sorted, sizeof(ftkb_point) * nu));
+  CKC(cudaMalloc(&c->d_keys_sorted, 8 * nu));
   launch_gather_points(c->d_pts, i0, nu, c->d_pts_sorted, c->stream);
+  CKC(cudaMemcpyAsync(c->d_keys_sorted, k0, 8 * nu, cudaMemcpyDeviceToDevice, c->stream));      // unique sorted keys
   CKC(cudaEventRecord(c->ev[1], c->stream));
   c->pts_sorted.resize(nu);
   CKC(cudaMemcpyAsync(c->pts_sorted.data(), c->d_pts_sorted, sizeof(ftkb_point) * nu, cudaMemcpyDeviceToHost, c->stream));
@@ -1357,10 +1379,8 @@ static int ensure_sorted(ftkb_ctx *c) {
   c->stats.ms_finalize_device += ms;
   c->stats.kernel_launches += 4;
   c->stats.d2h_bytes += sizeof(ftkb_point) * nu;
-  c->d_keys_sorted = k0;   // unique sorted keys
-  k0 = nullptr;
   c->nsorted = nu;
-  cleanup();
+  c->stats.ms_sort_wall += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tw0).count();
 #undef CKC
   c->sorted = true;
   return FTKB_OK;
@@ -1450,11 +1470,12 @@ extern "C" int ftkb_finalize(ftkb_ctx *c) {
   tp.n = n;
   tp.keys = c->d_keys_sorted;
   tp.pts = c->d_pts_sorted;
+  const auto tw0 = std::chrono::steady_clock::now();
   uint32_t *d_nb = nullptr, *d_pa = nullptr, *d_po = nullptr;
   int32_t *d_deg = nullptr;
-  auto cleanup = [&]() { cudaFree(d_nb); cudaFree(d_pa); cudaFree(d_po); cudaFree(d_deg); };
-#define CKC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); c->error = std::string(#call) + ": " + cudaGetErrorString(e_); return FTKB_ERR_CUDA; } } while (0)
-  CKC(cudaMalloc(&d_nb, 4 * 8 * n)); CKC(cudaMalloc(&d_pa, 4 * n)); CKC(cudaMalloc(&d_po, 4 * n)); CKC(cudaMalloc(&d_deg, 4 * n));
+#define CKC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { c->error = std::string(#call) + ": " + cudaGetErrorString(e_); return FTKB_ERR_CUDA; } } while (0)
+  { int rs = scratch(c, 5, 4 * 8 * n, (void **)&d_nb); if (!rs) rs = scratch(c, 6, 4 * n, (void **)&d_pa); if (!rs) rs = scratch(c, 7, 4 * n, (void **)&d_po);
+    if (!rs) rs = scratch(c, 8, 4 * n, (void **)&d_deg); if (rs) return rs; }
   tp.nb = d_nb; tp.deg = d_deg; tp.parent_all = d_pa; tp.parent_ord = d_po;
   CKC(cudaEventRecord(c->ev[0], c->stream));
   launch_neighbors(tp, c->stream);
@@ -1472,7 +1493,6 @@ extern "C" int ftkb_finalize(ftkb_ctx *c) {
   CKC(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]));
   c->stats.ms_finalize_device += ms;
   c->stats.d2h_bytes += 4 * 11 * n;
-  cleanup();
 #undef CKC
 
   // host: order every trajectory with the reference's deterministic walk (cc2curves.hh:46-108)
@@ -1524,6 +1544,7 @@ extern "C" int ftkb_finalize(ftkb_ctx *c) {
     c->traj_off.push_back(c->traj_idx.size());
   }
   c->stats.ms_finalize_host += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  c->stats.ms_trace_wall += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tw0).count();
   c->traced = true;
   return FTKB_OK;
 }
@@ -1685,6 +1706,19 @@ extern "C" int ftkb_get_layer(ftkb_ctx *c, int index, double *scalar, double *ve
   if (vector) CK(cudaMemcpy(vector, l.V, sizeof(double) * c->nvert * c->n, cudaMemcpyDeviceToHost));
   c->stats.d2h_bytes += sizeof(double) * c->nvert * ((scalar ? 1 : 0) + (vector ? c->n : 0));
   return FTKB_OK;
+}
+
+// page-locked host memory for callers that feed snapshots from files or generators: copies from it run at full PCIe speed and
+// do not go through the driver's staging buffers (the CLI's double-buffered reader, stream.hh:1607-1699 in the reference)
+extern "C" int ftkb_host_alloc(uint64_t bytes, void **out) {
+  if (!out || !bytes) return FTKB_ERR_INVALID;
+  *out = nullptr;
+  if (cudaHostAlloc(out, bytes, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return FTKB_ERR_NOMEM; }
+  return FTKB_OK;
+}
+
+extern "C" void ftkb_host_free(void *p) {
+  if (p && cudaFreeHost(p) != cudaSuccess) cudaGetLastError();
 }
 
 extern "C" int ftkb_get_stats(ftkb_ctx *c, ftkb_stats *out) {

@@ -1119,9 +1119,8 @@ __global__ void __launch_bounds__(256) scan2d_cells_kernel(const __grid_constant
 // Scalars >= 2^1000 / Inf / NaN cannot be ordered by the keys: they raise p.poison and the context redoes the step with
 // scan2d_build_kernel (fp32 ranges, handles them).
 constexpr int K2_R = 3;                                // rows per stage
-// CTAs per SM (a launch-bounds variant each; FTKB_K2_CTAS selects, default 3): the ring has 8 stages at two CTAs per SM
-// (85 KB per CTA) and 4 stages (42 KB) at three or four
-__host__ __device__ constexpr int k2_nst(int ctas) { return ctas >= 3 ? 4 : 8; }
+// CTAs per SM and ring stages are launch variants (FTKB_K2_CTAS / FTKB_K2_NST, see k2_variant): 8 stages (85 KB per CTA) at two
+// CTAs per SM, 4 - 6 stages (42 - 64 KB) at three, 4 at four
 constexpr uint32_t K2_ROW_BYTES = TL_SEG * 8;
 constexpr uint32_t K2_STAGE_BYTES = K2_R * K2_ROW_BYTES;
 static_assert(C2_R % K2_R == 0, "cell block = whole stages");
@@ -1216,7 +1215,7 @@ __device__ __forceinline__ K2Acc keys2d_strip(const SweepParams &p, const int c0
   float KX[2][K2_R][2];
   auto load_stage = [&](auto PC, const int s) {
     constexpr int P = decltype(PC)::value;
-    const uint32_t gs = sbase + (uint32_t)s, slot = gs & (K2_NST - 1);
+    const uint32_t gs = sbase + (uint32_t)s, slot = gs % K2_NST;
     mbar_wait(full0 + 8u * slot, (gs / K2_NST) & 1u);
     const uint32_t base = lane_u32 + slot * K2_STAGE_BYTES;
     double nl[K2_R], nr[K2_R];
@@ -1319,9 +1318,8 @@ __device__ __forceinline__ K2Acc keys2d_strip(const SweepParams &p, const int c0
 }
 
 // One CTA per (tile of C2_CW strips, chunk of p.rows corner rows); K2_CTAS CTAs per SM.
-template <int NPREV, bool TEST, int K2_CTAS>
+template <int NPREV, bool TEST, int K2_CTAS, int K2_NST>
 __global__ void __launch_bounds__((C2_CW + 1) * 32, K2_CTAS) scan2d_keys_build_kernel(const __grid_constant__ SweepParams p) {
-  constexpr int K2_NST = k2_nst(K2_CTAS);
   extern __shared__ __align__(128) unsigned char fb_smem[];
   const int lane = threadIdx.x & 31;
   const int wib = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);     // warp-uniform by construction
@@ -1350,7 +1348,7 @@ __global__ void __launch_bounds__((C2_CW + 1) * 32, K2_CTAS) scan2d_keys_build_k
       const uint32_t seg_bytes = (uint32_t)(col_hi - col_lo) * 8u;
       const uint32_t dst0 = ring0 + (uint32_t)(col_lo - (C0 - 2)) * 8u;
       for (int s = 0; s < nstages; s++) {
-        const uint32_t slot = (uint32_t)s & (K2_NST - 1);
+        const uint32_t slot = (uint32_t)s % K2_NST;
         if (s >= K2_NST) mbar_wait(empty0 + 8u * slot, (uint32_t)((s / K2_NST - 1) & 1));
         mbar_expect_tx(full0 + 8u * slot, seg_bytes * K2_R);
 #pragma unroll
@@ -1379,26 +1377,33 @@ __global__ void __launch_bounds__((C2_CW + 1) * 32, K2_CTAS) scan2d_keys_build_k
   if (!(acc.big < __int_as_float(KEYF_BIG))) atomicExch(p.poison, 1ull);
 }
 
-static size_t k2_smem_bytes(int ctas) { return (size_t)k2_nst(ctas) * K2_STAGE_BYTES + (size_t)2 * k2_nst(ctas) * 8; }
-static int k2_ctas() {
-  static const int v = [] { const char *e = std::getenv("FTKB_K2_CTAS"); const int n = e ? std::atoi(e) : 3; return n >= 2 && n <= 4 ? n : 3; }();
+static size_t k2_smem_bytes(int nst) { return (size_t)nst * K2_STAGE_BYTES + (size_t)2 * nst * 8; }
+// FTKB_K2_CTAS (CTAs per SM: 2 | 3 | 4, default 3) and FTKB_K2_NST (ring stages at three CTAs per SM: 4 | 5 | 6, default 4)
+static int k2_variant() {
+  static const int v = [] {
+    const char *e = std::getenv("FTKB_K2_CTAS"), *n = std::getenv("FTKB_K2_NST");
+    const int ctas = e ? std::atoi(e) : 3, nst = n ? std::atoi(n) : 4;
+    if (ctas == 2) return 28;
+    if (ctas == 4) return 44;
+    return nst == 5 ? 35 : (nst == 6 ? 36 : 34);
+  }();
   return v;
 }
-template <int CTAS>
+template <int CTAS, int NST>
 static void k2_launch(const SweepParams &p, unsigned grid, cudaStream_t s) {
-  const size_t sm = k2_smem_bytes(CTAS);
+  const size_t sm = k2_smem_bytes(NST);
   switch (p.sum_mode) {
-    case SUM_BUILD: scan2d_keys_build_kernel<0, false, CTAS><<<grid, (C2_CW + 1) * 32, sm, s>>>(p); break;
-    case SUM_BUILD_TEST1: scan2d_keys_build_kernel<0, true, CTAS><<<grid, (C2_CW + 1) * 32, sm, s>>>(p); break;
-    default: scan2d_keys_build_kernel<1, true, CTAS><<<grid, (C2_CW + 1) * 32, sm, s>>>(p); break;
+    case SUM_BUILD: scan2d_keys_build_kernel<0, false, CTAS, NST><<<grid, (C2_CW + 1) * 32, sm, s>>>(p); break;
+    case SUM_BUILD_TEST1: scan2d_keys_build_kernel<0, true, CTAS, NST><<<grid, (C2_CW + 1) * 32, sm, s>>>(p); break;
+    default: scan2d_keys_build_kernel<1, true, CTAS, NST><<<grid, (C2_CW + 1) * 32, sm, s>>>(p); break;
   }
 }
-template <int CTAS>
+template <int CTAS, int NST>
 static void k2_attrs() {
-  const int sm = (int)k2_smem_bytes(CTAS);
-  cudaFuncSetAttribute(scan2d_keys_build_kernel<0, false, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
-  cudaFuncSetAttribute(scan2d_keys_build_kernel<0, true, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
-  cudaFuncSetAttribute(scan2d_keys_build_kernel<1, true, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+  const int sm = (int)k2_smem_bytes(NST);
+  cudaFuncSetAttribute(scan2d_keys_build_kernel<0, false, CTAS, NST>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+  cudaFuncSetAttribute(scan2d_keys_build_kernel<0, true, CTAS, NST>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+  cudaFuncSetAttribute(scan2d_keys_build_kernel<1, true, CTAS, NST>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
 }
 
 static size_t c2_smem_bytes() { return (size_t)C2_NST * TL_SEG * 8 + (size_t)2 * C2_NST * 8; }
@@ -1416,10 +1421,12 @@ void launch_scan2d_cells(const SweepParams &p, cudaStream_t s) {
   const int nstrips = (p.W + FB_STRIDE - 1) / FB_STRIDE, nblk = (p.H + C2_R - 1) / C2_R;
   const unsigned tgrid = (unsigned)(((i64)nstrips * nblk + 7) / 8);
   if (p.keys2d && p.sum_mode <= SUM_BUILD_TEST2) {
-    switch (k2_ctas()) {
-      case 2: k2_launch<2>(p, grid, s); break;
-      case 4: k2_launch<4>(p, grid, s); break;
-      default: k2_launch<3>(p, grid, s); break;
+    switch (k2_variant()) {
+      case 28: k2_launch<2, 8>(p, grid, s); break;
+      case 44: k2_launch<4, 4>(p, grid, s); break;
+      case 35: k2_launch<3, 5>(p, grid, s); break;
+      case 36: k2_launch<3, 6>(p, grid, s); break;
+      default: k2_launch<3, 4>(p, grid, s); break;
     }
     return;
   }
@@ -2729,7 +2736,7 @@ void init_kernel_attributes() {
   cudaFuncSetAttribute(scan3d_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused3d_smem_bytes(true));
   cudaFuncSetAttribute(scan3d_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused3d_smem_bytes(false));
   cudaFuncSetAttribute(scan2d_build_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c2_smem_bytes());
-  k2_attrs<2>(); k2_attrs<3>(); k2_attrs<4>();
+  k2_attrs<2, 8>(); k2_attrs<3, 4>(); k2_attrs<3, 5>(); k2_attrs<3, 6>(); k2_attrs<4, 4>();
   cudaFuncSetAttribute(scan2d_build_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c2_smem_bytes());
   cudaFuncSetAttribute(scan2d_build_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c2_smem_bytes());
   cudaFuncSetAttribute(scan3d_build_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s3_smem_bytes());
@@ -3417,7 +3424,7 @@ static void init_carveouts() {
   const int co = cudaSharedmemCarveoutMaxShared;
 #define CARVE(k) cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, co)
   CARVE(test_kernel<2>); CARVE(test_kernel<3>);
-  CARVE((scan2d_keys_build_kernel<0, false, 3>)); CARVE((scan2d_keys_build_kernel<0, true, 3>)); CARVE((scan2d_keys_build_kernel<1, true, 3>));
+  CARVE((scan2d_keys_build_kernel<0, false, 3, 4>)); CARVE((scan2d_keys_build_kernel<0, true, 3, 4>)); CARVE((scan2d_keys_build_kernel<1, true, 3, 4>));
   CARVE((scan2d_build_kernel<0, false>)); CARVE((scan2d_build_kernel<0, true>)); CARVE((scan2d_build_kernel<1, true>));
   CARVE((scan3d_build_kernel<0, false>)); CARVE((scan3d_build_kernel<0, true>)); CARVE((scan3d_build_kernel<1, true>));
   CARVE((vscan2d_build_kernel<0, false>)); CARVE((vscan2d_build_kernel<0, true>)); CARVE((vscan2d_build_kernel<1, true>));

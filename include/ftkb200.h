@@ -120,6 +120,8 @@ typedef struct ftkb_stats {
   double resolution;          /* running min non-zero |v| */
   uint64_t scan_launches;     /* scan kernel launches (one per sweep, repeated sweeps included) */
   uint64_t sweeps_repeated;   /* sweeps run again: stale quantisation factor or output buffers grown */
+  double ms_sort_wall;        /* host wall clock of sort + dedup + copy of the punctured simplices (ensure_sorted), accumulated */
+  double ms_trace_wall;       /* host wall clock of ftkb_finalize after the sort: neighbour search, union-find, copies, ordering walk */
 } ftkb_stats;
 
 typedef struct ftkb_ctx ftkb_ctx;
@@ -294,6 +296,11 @@ int ftkb_get_last_worklist(ftkb_ctx *, uint64_t *out, uint64_t cap, uint64_t *n)
 /* diagnostic: copy resident snapshot `index` (0 = current) to host memory -- what a device-side generator
  * (ftkb_push_synthetic) produced; either pointer may be NULL */
 int ftkb_get_layer(ftkb_ctx *, int index, double *scalar, double *vector);
+
+/* page-locked (pinned, portable) host memory for snapshot buffers: ftkb_push_snapshot(FTKB_MEM_HOST) then copies at full
+ * PCIe speed.  The CLI reads file series through two such buffers (one being read while the other is pushed and swept). */
+int ftkb_host_alloc(uint64_t bytes, void **out);
+void ftkb_host_free(void *p);
 
 int ftkb_get_stats(ftkb_ctx *, ftkb_stats *out);
 int ftkb_reset_stats(ftkb_ctx *);
