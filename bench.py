@@ -471,7 +471,9 @@ def run_config(env, config, K, W, e2e_steps, sample_clocks):
         ntraj = len(tr.get_trajectory_index())
         npts_total = len(tr.get_discrete_critical_points())
         after = tr.stats()
-        fin = {"device": after["ms_finalize_device"] - before["ms_finalize_device"], "host": after["ms_finalize_host"] - before["ms_finalize_host"]}
+        fin = {"device": after["ms_finalize_device"] - before["ms_finalize_device"], "host": after["ms_finalize_host"] - before["ms_finalize_host"],
+               # wall clock inside the library: sort + dedup + copy of the punctured simplices, then neighbour search + union-find + ordering
+               "library": after["ms_sort_wall"] + after["ms_trace_wall"]}
     finalize_ms = 1e3 * (time.perf_counter() - t0)
     tr.close()
 
@@ -588,7 +590,7 @@ def run_config(env, config, K, W, e2e_steps, sample_clocks):
                  "api": "ftkb_push_snapshot(host) + ftkb_advance_timestep"} if E else None),
         "gpu_launches": int(st["kernel_launches"]),
         "clocks": sampler.result() if sample_clocks else None,
-        "finalize_ms": finalize_ms, "finalize_ms_device": fin.get("device"), "finalize_ms_host": fin.get("host"),
+        "finalize_ms": finalize_ms, "finalize_ms_library": fin.get("library"), "finalize_ms_device": fin.get("device"), "finalize_ms_host": fin.get("host"),
         "trajectories": ntraj, "punctured_simplices": int(npts_total),
         "cells_refined_per_step": st["cells_refined"] / K, "slab_refactor_steps": redo,
         "slab_epilogue_ms": epilogue_ms if world > 1 else None,
@@ -598,7 +600,7 @@ def run_config(env, config, K, W, e2e_steps, sample_clocks):
 
 def sub_record(line):
     """what a scaling sub-record keeps of a full line"""
-    keep = ("value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "trajectories", "punctured_simplices", "finalize_ms",
+    keep = ("value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "trajectories", "punctured_simplices", "finalize_ms", "finalize_ms_library",
             "slab_epilogue_ms", "slab_refactor_steps", "cells_refined_per_step")
     out = {k: line[k] for k in keep}
     out["workload"] = line["config"]["workload"]
@@ -690,7 +692,14 @@ def main():
     extras = {}
     if args.config == "c2" and not args.only_main:
         # the configurations north_star quotes its scaling targets on, at the same N, in the same driver-run line
-        budget_ok = lambda: time.perf_counter() - t_all < 420.0
+        def budget_ok():
+            # one decision for all ranks (rank 0's clock): a rank that skipped on its own would leave the others in a collective
+            ok = time.perf_counter() - t_all < 420.0
+            if env.dist:
+                flag = [ok]
+                env.dist.broadcast_object_list(flag, src=0)
+                ok = bool(flag[0])
+            return ok
         for key, cfg, k in (("scaling_c4", "c4", 8), ("scaling_c3", "c3", 12), ("dense_woven", "woven", 12)):
             if not budget_ok():
                 extras[key] = {"skipped": "time budget of the default run"}
