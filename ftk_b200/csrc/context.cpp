@@ -943,8 +943,8 @@ static int drain(ftkb_ctx *c) {
 }
 
 static int test_grid(const ftkb_ctx *c) {
-  const uint64_t ntypes = c->n == 2 ? 12 : 60;
-  const uint64_t want = ((c->wl_hint * 2 + 256) * ntypes + 127) / 128;
+  const uint64_t cpb = c->n == 2 ? 10 : 2;           // cubes per block and round of test_kernel
+  const uint64_t want = (c->wl_hint * 2 + 256 + cpb - 1) / cpb;
   return (int)std::max<uint64_t>(8, std::min<uint64_t>(want, (uint64_t)c->sm_count * 8));
 }
 

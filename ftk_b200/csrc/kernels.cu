@@ -904,12 +904,16 @@ __device__ __noinline__ void cells2d_slow_cubes(const SweepParams &p, unsigned f
   const int lane = threadIdx.x & 31;
   const float cwf = (float)(W - 1), chf = (float)(H - 1);
   const float nanf_ = __int_as_float(0x7FC00000);
-  const int r = lane >> 1, q = lane & 1;
-  while (failmask) {
-    const int src = __ffs(failmask) - 1;
-    failmask &= failmask - 1;
+  // the 2 x nrows cubes of every failing lane, packed 32 to a pass (a failing lane alone would keep 18 of 32 lanes busy)
+  const int per = 2 * nrows, total = per * __popc(failmask);
+  for (int q0 = 0; q0 < total; q0 += 32) {
+    const int qi = q0 + lane;
+    const bool live = qi < total;
+    const int which = live ? qi / per : 0, within = live ? qi % per : 0;
+    const int src = (int)__fns(failmask, 0, which + 1);       // the which-th failing lane
+    const int r = within >> 1, q = within & 1;
     const int x = c0 + 2 * src + q, y = y0 + r;
-    const bool in = lane < 2 * nrows && x >= p.lb[0] && x <= p.ub[0] && y >= p.lb[1] && y <= p.ub[1];
+    const bool in = live && x >= p.lb[0] && x <= p.ub[0] && y >= p.lb[1] && y <= p.ub[1];
     FRange rx{nanf_, nanf_}, ry{nanf_, nanf_};
 #pragma unroll
     for (int v = 0; v < 4; v++) {
@@ -3158,8 +3162,9 @@ __device__ __forceinline__ int sos_rank(const SweepParams &p, const int *v /* ND
   return (int)(unsigned)i;
 }
 
+// vcache: the cube's 2^(ND+1) vertex vectors, [vertex mask][component], gathered once per cube by the block (test_kernel)
 template <int ND>
-__device__ bool check_simplex(const SweepParams &p, const DeviceMeshTables &mt, const int corner[3], int type, ftkb_point &cp) {
+__device__ bool check_simplex(const SweepParams &p, const DeviceMeshTables &mt, const int corner[3], int type, ftkb_point &cp, const double *vcache) {
   constexpr int NV = ND + 1;
   int vt[NV][ND + 1];
   const LayerPtrs *L[NV];
@@ -3184,10 +3189,7 @@ __device__ bool check_simplex(const SweepParams &p, const DeviceMeshTables &mt, 
 #pragma unroll
   for (int k = 0; k < NV; k++)
 #pragma unroll
-    for (int c = 0; c < ND; c++) {
-      if constexpr (ND == 2) v[k][c] = vec2_at(p, *L[k], c, vt[k][0], vt[k][1]);
-      else v[k][c] = vec3_at(p, *L[k], c, vt[k][0], vt[k][1], vt[k][2]);
-    }
+    for (int c = 0; c < ND; c++) v[k][c] = vcache[mt.vmask[type][k] * ND + c];
 
   double mu[NV];
   bool inside = false;
@@ -3346,30 +3348,61 @@ __device__ bool check_simplex(const SweepParams &p, const DeviceMeshTables &mt, 
   return true;
 }
 
+// A block works on CPB surviving cubes per round: first the 2^(ND+1) vertices of every cube are gathered (the vector field
+// read or derived ONCE per vertex -- a vertex is shared by up to 9 / 36 simplices of its cube), then one thread per
+// (cube, simplex type) runs the exact test on the cached vectors.
 template <int ND>
 __global__ void __launch_bounds__(128) test_kernel(const __grid_constant__ SweepParams p) {
   const DeviceMeshTables &mt = c_mesh[ND - 2];
-  const int ntypes = ND == 2 ? 12 : 60;
+  constexpr int ntypes = ND == 2 ? 12 : 60;
+  constexpr int NVC = 1 << (ND + 1);                  // vertices of a space-time cube
+  constexpr int CPB = 128 / ntypes;                   // cubes per block and round (10 in 2D, 2 in 3D)
+  __shared__ double vcache[CPB][NVC * ND];
+  __shared__ int ccorner[CPB][3];
   u64 ncubes = *p.wl_count;
   if (ncubes > p.wl_cap) ncubes = p.wl_cap;
-  const u64 total = ncubes * ntypes;
-  const u64 stride = (u64)gridDim.x * blockDim.x;
-  const u64 rounds = (total + stride - 1) / stride;
+  const u64 stride = (u64)gridDim.x * CPB;
+  const u64 rounds = (ncubes + stride - 1) / stride;
   const int lane = threadIdx.x & 31;
   for (u64 r = 0; r < rounds; r++) {
-    const u64 i = r * stride + (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    bool hit = false;
-    ftkb_point cp;
-    if (i < total) {
-      const u64 lin = p.wl[i / ntypes];
-      const int type = (int)(i % ntypes);
-      if (p.has_next || mt.ordinal[type]) {
+    const u64 cube0 = r * stride + (u64)blockIdx.x * CPB;
+    // ---- gather: thread t -> (cube t / NVC, vertex mask t % NVC)
+    for (int t = threadIdx.x; t < CPB * NVC; t += blockDim.x) {
+      const int ci = t / NVC, m = t % NVC;
+      const u64 cube = cube0 + (u64)ci;
+      if (cube < ncubes) {
+        u64 q = p.wl[cube];
         int corner[3];
-        u64 q = lin;
         corner[0] = (int)(q % (u64)p.nc[0]) + p.lb[0]; q /= (u64)p.nc[0];
         corner[1] = (int)(q % (u64)p.nc[1]) + p.lb[1]; q /= (u64)p.nc[1];
         corner[2] = ND == 3 ? (int)q + p.lb[2] : 0;
-        hit = check_simplex<ND>(p, mt, corner, type, cp);
+        if (m == 0) { ccorner[ci][0] = corner[0]; ccorner[ci][1] = corner[1]; ccorner[ci][2] = corner[2]; }
+        int vx[3];
+        bool ok = true;
+#pragma unroll
+        for (int j = 0; j < ND; j++) { vx[j] = corner[j] + ((m >> j) & 1); ok = ok && vx[j] >= p.lb[j] && vx[j] <= p.ub[j]; }
+        const int dt = (m >> ND) & 1;
+        ok = ok && (p.has_next || dt == 0);           // (no second layer: the interval vertices belong to no simplex that is tested)
+#pragma unroll
+        for (int c = 0; c < ND; c++) {
+          double val = 0.0;                           // a vertex outside the domain belongs to no valid simplex: never read
+          if (ok) {
+            if constexpr (ND == 2) val = vec2_at(p, p.L[dt], c, vx[0], vx[1]);
+            else val = vec3_at(p, p.L[dt], c, vx[0], vx[1], vx[2]);
+          }
+          vcache[ci][m * ND + c] = val;
+        }
+      }
+    }
+    __syncthreads();
+    // ---- test: thread t -> (cube t / ntypes, type t % ntypes)
+    bool hit = false;
+    ftkb_point cp;
+    {
+      const int ci = threadIdx.x / ntypes, type = threadIdx.x % ntypes;
+      if (ci < CPB && cube0 + (u64)ci < ncubes && (p.has_next || mt.ordinal[type])) {
+        const int corner[3] = {ccorner[ci][0], ccorner[ci][1], ccorner[ci][2]};
+        hit = check_simplex<ND>(p, mt, corner, type, cp, vcache[ci]);
       }
     }
     const unsigned b = __ballot_sync(0xffffffffu, hit);
@@ -3383,6 +3416,7 @@ __global__ void __launch_bounds__(128) test_kernel(const __grid_constant__ Sweep
         if (o < p.pt_cap) p.pts[o] = cp;
       }
     }
+    __syncthreads();                                  // the cache is refilled by the next round
   }
   if (p.step_out == nullptr) return;
   // deferred step: the last block to finish publishes the counters to the host (mapped memory) and re-arms the
