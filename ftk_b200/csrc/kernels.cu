@@ -3162,8 +3162,10 @@ __device__ __forceinline__ int sos_rank(const SweepParams &p, const int *v /* ND
   return (int)(unsigned)i;
 }
 
-// vcache: the cube's 2^(ND+1) vertex vectors, [vertex mask][component], gathered once per cube by the block (test_kernel)
-template <int ND>
+// vcache: the cube's 2^(ND+1) vertex vectors, [vertex mask][component], gathered once per cube by the block (test_kernel).
+// PRETEST: only validity + quantisation + the cheap exact exclusion; true = the simplex needs the full test (the block then runs
+// the full test on the compacted survivors, so that the long SoS cascade is executed by full warps)
+template <int ND, bool PRETEST = false>
 __device__ bool check_simplex(const SweepParams &p, const DeviceMeshTables &mt, const int corner[3], int type, ftkb_point &cp, const double *vcache) {
   constexpr int NV = ND + 1;
   int vt[NV][ND + 1];
@@ -3190,6 +3192,26 @@ __device__ bool check_simplex(const SweepParams &p, const DeviceMeshTables &mt, 
   for (int k = 0; k < NV; k++)
 #pragma unroll
     for (int c = 0; c < ND; c++) v[k][c] = vcache[mt.vmask[type][k] * ND + c];
+
+  if constexpr (PRETEST) {
+    if (!(ND == 2 || p.robust)) return true;
+    const i64 lim = ND == 2 ? (1ll << 29) : (1ll << 19);
+    bool small = true, sided = false;
+#pragma unroll
+    for (int c = 0; c < ND; c++) {
+      bool pos = true, neg = true;
+#pragma unroll
+      for (int k = 0; k < NV; k++) {
+        if (isnan(v[k][c]) || isinf(v[k][c])) return false;
+        const i64 q = quantise(v[k][c], p.factor);
+        pos = pos && q > 0;
+        neg = neg && q < 0;
+        small = small && q < lim && q > -lim;
+      }
+      sided = sided || pos || neg;
+    }
+    return !(small && sided);
+  }
 
   double mu[NV];
   bool inside = false;
@@ -3359,6 +3381,8 @@ __global__ void __launch_bounds__(128) test_kernel(const __grid_constant__ Sweep
   constexpr int CPB = 128 / ntypes;                   // cubes per block and round (10 in 2D, 2 in 3D)
   __shared__ double vcache[CPB][NVC * ND];
   __shared__ int ccorner[CPB][3];
+  __shared__ unsigned short need_list[128];
+  __shared__ int need_count;
   u64 ncubes = *p.wl_count;
   if (ncubes > p.wl_cap) ncubes = p.wl_cap;
   const u64 stride = (u64)gridDim.x * CPB;
@@ -3366,6 +3390,7 @@ __global__ void __launch_bounds__(128) test_kernel(const __grid_constant__ Sweep
   const int lane = threadIdx.x & 31;
   for (u64 r = 0; r < rounds; r++) {
     const u64 cube0 = r * stride + (u64)blockIdx.x * CPB;
+    if (threadIdx.x == 0) need_count = 0;
     // ---- gather: thread t -> (cube t / NVC, vertex mask t % NVC)
     for (int t = threadIdx.x; t < CPB * NVC; t += blockDim.x) {
       const int ci = t / NVC, m = t % NVC;
@@ -3395,15 +3420,34 @@ __global__ void __launch_bounds__(128) test_kernel(const __grid_constant__ Sweep
       }
     }
     __syncthreads();
-    // ---- test: thread t -> (cube t / ntypes, type t % ntypes)
-    bool hit = false;
-    ftkb_point cp;
+    // ---- pretest: thread t -> (cube t / ntypes, type t % ntypes): validity, quantisation, cheap exact exclusion; what survives
+    // is compacted so that the long part (SoS cascade, interpolation, Jacobians) runs in full warps
     {
+      ftkb_point dummy;
       const int ci = threadIdx.x / ntypes, type = threadIdx.x % ntypes;
+      bool need = false;
       if (ci < CPB && cube0 + (u64)ci < ncubes && (p.has_next || mt.ordinal[type])) {
         const int corner[3] = {ccorner[ci][0], ccorner[ci][1], ccorner[ci][2]};
-        hit = check_simplex<ND>(p, mt, corner, type, cp, vcache[ci]);
+        need = check_simplex<ND, true>(p, mt, corner, type, dummy, vcache[ci]);
       }
+      const unsigned nb = __ballot_sync(0xffffffffu, need);
+      if (nb) {
+        int base = 0;
+        const int leader = __ffs(nb) - 1;
+        if (lane == leader) base = atomicAdd(&need_count, __popc(nb));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (need) need_list[base + __popc(nb & ((1u << lane) - 1))] = (unsigned short)threadIdx.x;
+      }
+    }
+    __syncthreads();
+    // ---- full test on the survivors
+    bool hit = false;
+    ftkb_point cp;
+    if ((int)threadIdx.x < need_count) {
+      const int t = need_list[threadIdx.x];
+      const int ci = t / ntypes, type = t % ntypes;
+      const int corner[3] = {ccorner[ci][0], ccorner[ci][1], ccorner[ci][2]};
+      hit = check_simplex<ND, false>(p, mt, corner, type, cp, vcache[ci]);
     }
     const unsigned b = __ballot_sync(0xffffffffu, hit);
     if (b) {

@@ -98,11 +98,18 @@ def _worker(rank, world, port, case, use_cuda, out_path, halo="copy"):
         dims, T, field, snaps = make_series(case)
         factory = None if use_cuda else (lambda d, f, s, r, **kw: OracleSlabTracker(d, f, s, r, **kw))
         calls = []
+        extra = {}
+        if use_cuda:
+            # one GPU per rank when the box has them (the halo then really crosses NVLink); both ranks on cuda:0 otherwise
+            import torch
+            dev = rank % max(1, torch.cuda.device_count())
+            torch.cuda.set_device(dev)
+            extra["device"] = dev
 
         def layer(k):
             calls.append(k)
             return snaps[k]
-        tr, info = D.track_time_sharded(layer, dims, T, field=field, tracker_factory=factory, halo=halo)
+        tr, info = D.track_time_sharded(layer, dims, T, field=field, tracker_factory=factory, halo=halo, **extra)
         t0, t1 = D.slab_range(T, world, rank)
         assert info["slab"] == (t0, t1)
         assert all(t0 <= k < t1 for k in calls), (calls, t0, t1)      # a rank only ever asks for its own layers: the halo is exchanged

@@ -388,9 +388,11 @@ def _upper_slab_worker(dims, field, snaps_upper, cut, res_init, q_out, q_in):
     import torch
     import ftk_b200
     from ftk_b200 import _lib
-    dev = torch.device("cuda", 0)
+    ndev = torch.cuda.device_count()
+    dev = torch.device("cuda", 1 if ndev >= 2 else 0)      # the upper slab on its own GPU when there is one: the halo then crosses NVLink
+    torch.cuda.set_device(dev)
     first = torch.from_numpy(np.ascontiguousarray(snaps_upper[0])).to(dev)       # stays alive while the neighbour reads it
-    tr = ftk_b200.make_tracker(dims, field=field, start_timestep=cut, resolution_init=res_init)
+    tr = ftk_b200.make_tracker(dims, field=field, start_timestep=cut, resolution_init=res_init, device=dev.index)
     kw = "scalar" if field == "scalar" else "vector"
     tr.push_device_pointers(**{kw: int(first.data_ptr())})
     if field == "scalar":
