@@ -11,7 +11,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libftkb200.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 OK, ERR_INVALID, ERR_NO_DEVICE, ERR_CUDA, ERR_NOMEM, ERR_OVERFLOW = range(6)
 SOURCE_NONE, SOURCE_GIVEN, SOURCE_DERIVED = 0, 1, 2
 MEM_HOST, MEM_DEVICE, MEM_DEVICE_BORROW = 0, 1, 2
@@ -26,6 +26,7 @@ class Config(C.Structure):
         ("jacobian_symmetric", C.c_int32), ("robust_detection", C.c_int32), ("compute_degrees", C.c_int32),
         ("use_type_filter", C.c_int32), ("type_filter", C.c_uint32), ("start_timestep", C.c_int32), ("device", C.c_int32),
         ("resolution_init", C.c_double), ("point_capacity", C.c_uint64),
+        ("slab_offset", C.c_int32), ("slab_global_dim", C.c_int32), ("slab_global_lb", C.c_int32), ("slab_global_ub", C.c_int32),
     ]
 
 

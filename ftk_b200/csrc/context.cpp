@@ -53,6 +53,7 @@ struct ftkb_ctx {
   bool derive_timed = false;
   std::string error;
 
+  bool slab = false;             // the context holds a z-slab of a larger array (cfg.slab_*)
   std::deque<Layer> layers;
   std::vector<double *> freeS, freeV, freeJ;   // buffer pools
   int current_timestep = 0;
@@ -280,8 +281,16 @@ extern "C" int ftkb_create(const ftkb_config *cfg, ftkb_ctx **out) {
   if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess || prop.major != 10)
     return fail(nullptr, FTKB_ERR_NO_DEVICE, "ftkb_create: device is not compute capability 10.x (kernels are built for sm_100a only)");
 
+  if (cfg->slab_global_dim != 0) {
+    if (n != 3) return fail(nullptr, FTKB_ERR_INVALID, "ftkb_create: spatial slabs are 3D (along z)");
+    if (cfg->slab_offset < 0 || cfg->slab_offset + cfg->dims[2] > cfg->slab_global_dim || cfg->slab_global_lb < 0 ||
+        cfg->slab_global_ub >= cfg->slab_global_dim || cfg->slab_global_lb > cfg->slab_global_ub ||
+        cfg->slab_offset + cfg->lb[2] < cfg->slab_global_lb || cfg->slab_offset + cfg->ub[2] > cfg->slab_global_ub)
+      return fail(nullptr, FTKB_ERR_INVALID, "ftkb_create: the slab does not lie inside the whole array / domain");
+  }
   ftkb_ctx *c = new ftkb_ctx();
   c->cfg = *cfg;
+  c->slab = cfg->slab_global_dim != 0;
   c->sm_count = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : 148;
   if (const char *e = std::getenv("FTKB_SCAN")) c->scan_mode = std::string(e) == "ldg" ? 0 : (std::string(e) == "warp" ? 1 : (std::string(e) == "direct" ? 3 : 2));
   {
@@ -305,7 +314,9 @@ extern "C" int ftkb_create(const ftkb_config *cfg, ftkb_ctx **out) {
   // element keys pack (x, y, z, t, type) into 64 bits
   {
     const long double cap = 18446744073709551616.0L / (long double)(1ull << (KEY_TIME_BITS + KEY_TYPE_BITS));
-    if ((long double)c->ncore >= cap) { delete c; return fail(nullptr, FTKB_ERR_OVERFLOW, "ftkb_create: domain too large for 64-bit element ids"); }
+    long double key_cells = (long double)c->ncore;
+    if (c->slab) key_cells = key_cells / (long double)(cfg->ub[2] - cfg->lb[2] + 1) * (long double)(cfg->slab_global_ub - cfg->slab_global_lb + 1);
+    if (key_cells >= cap) { delete c; return fail(nullptr, FTKB_ERR_OVERFLOW, "ftkb_create: domain too large for 64-bit element ids"); }
   }
   const MeshTables &mt = mesh_tables(n + 1);
   c->n_ord = (int)mt.ordinal_types[n].size();
@@ -487,7 +498,8 @@ extern "C" int ftkb_push_synthetic(ftkb_ctx *c, int kind, const double *params, 
   double **dst = vector_kind ? &l.V : &l.S;
   if ((rc = take_buffer(c, vector_kind ? c->freeV : c->freeS, vector_kind ? c->nvert * c->n : c->nvert, dst))) { release_layer(c, l); return rc; }
   (vector_kind ? l.ownV : l.ownS) = true;
-  launch_synthetic(kind, c->n, c->cfg.dims[0], c->cfg.dims[1], c->n == 3 ? c->cfg.dims[2] : 1, p, t, *dst, c->stream);
+  launch_synthetic(kind, c->n, c->cfg.dims[0], c->cfg.dims[1], c->n == 3 ? c->cfg.dims[2] : 1, p, t, *dst, c->stream,
+                   c->slab ? c->cfg.slab_offset : 0, c->slab ? c->cfg.slab_global_dim : 0);
   c->stats.kernel_launches++;
   if ((rc = derive_layer(c, l))) { release_layer(c, l); return rc; }
   c->layers.push_back(l);
@@ -558,6 +570,7 @@ static int nbits_of(double resolution) {
 // per-simplex test interpolates (simplex_coordinates, critical_point_tracker_2d_regular.hh:494-526, ..._3d_regular.hh:343-379)
 extern "C" int ftkb_set_coords(ftkb_ctx *c, int mode, const double *data, uint64_t n) {
   if (!c || mode < FTKB_COORDS_SIMPLE || mode > FTKB_COORDS_EXPLICIT || (mode != FTKB_COORDS_SIMPLE && !data)) return FTKB_ERR_INVALID;
+  if (c->slab && mode != FTKB_COORDS_SIMPLE) return fail(c, FTKB_ERR_INVALID, "set_coords: physical coordinates are not available on a spatial slab");
   CK(cudaSetDevice(c->cfg.device));
   const uint64_t W = c->cfg.dims[0], H = c->cfg.dims[1], D = c->n == 3 ? c->cfg.dims[2] : 0;
   if (mode == FTKB_COORDS_BOUNDS && n != 2u * c->n) return fail(c, FTKB_ERR_INVALID, "set_coords: bounds take 2 * nd values");
@@ -593,6 +606,12 @@ static void fill_sweep_geometry(const ftkb_ctx *c, SweepParams &p) {
     p.ub[j] = used ? c->cfg.ub[j] : 0;
     p.nc[j] = p.ub[j] - p.lb[j] + 1;
     p.vmax[j] = p.ub[j];   // vertices outside the domain belong to no valid simplex: keep them out of the cube ranges
+    p.voff[j] = 0; p.rank_lb[j] = p.lb[j]; p.rank_nc[j] = p.nc[j];
+  }
+  if (c->slab) {           // a z-slab of a larger array: ranks / positions / corners in the whole lattice's frame
+    p.voff[2] = c->cfg.slab_offset;
+    p.rank_lb[2] = c->cfg.slab_global_lb;
+    p.rank_nc[2] = c->cfg.slab_global_ub - c->cfg.slab_global_lb + 1;
   }
 }
 
@@ -812,6 +831,7 @@ static int grow_trajectories(ftkb_ctx *c) {
 extern "C" int ftkb_set_streaming_trajectories(ftkb_ctx *c, int enable) {
   if (!c) return FTKB_ERR_INVALID;
   if (c->stats.scan_launches || c->npts) return fail(c, FTKB_ERR_INVALID, "set_streaming_trajectories: call it before the first update_timestep");
+  if (c->slab && enable) return fail(c, FTKB_ERR_INVALID, "set_streaming_trajectories: not available on a spatial slab");
   (void)wait_grow(c);
   c->streaming = enable != 0;
   c->grow_failed = false;
@@ -1329,6 +1349,7 @@ static void fill_trace_params(const ftkb_ctx *c, TraceParams &tp) {
     tp.lb[j] = used ? c->cfg.lb[j] : 0;
     tp.ub[j] = used ? c->cfg.ub[j] : 0;
   }
+  if (c->slab) { tp.lb[2] = c->cfg.slab_global_lb; tp.ub[2] = c->cfg.slab_global_ub; }    // the points carry whole-array corners
   tp.ny = tp.ub[1] - tp.lb[1] + 1;
   tp.nz = tp.ub[2] - tp.lb[2] + 1;
 }

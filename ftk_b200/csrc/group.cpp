@@ -17,6 +17,7 @@
 //   merge         ftkb_group_finalize collects the (sparse) punctured simplices of every chunk into one context on the first
 //                 device and runs the union-find + ordering there: components that cross chunk boundaries are united by
 //                 the same neighbour search that unites them inside a chunk.
+#include <algorithm>
 #include <atomic>
 #include <cfloat>
 #include <cmath>
@@ -100,10 +101,22 @@ int nbits_of(double res) {
 
 }  // namespace
 
+// spatial mode (chunk_timesteps == 0, 3D): device s holds planes [a0, a1] of every snapshot -- its corner planes plus the ghost
+// planes its stencils reach (the reference's spatial decomposition, regular_tracker.hh:126-149)
+struct Slab {
+  int device = 0, a0 = 0, a1 = 0;
+  ftkb_ctx *ctx = nullptr;
+  std::vector<ftkb_point> points;
+  ftkb_stats stats{};
+};
+
 struct ftkb_group {
   ftkb_config cfg{};
   std::vector<int> devices;
   int B = 8;
+  bool spatial = false;
+  std::vector<Slab> slabs;
+  double running = DBL_MAX;                        // spatial mode: running minimum of min non-zero |v| over the whole array
   std::vector<std::unique_ptr<Worker>> workers;
   std::deque<std::unique_ptr<Chunk>> chunks;       // by index
   std::mutex m;                                    // protects chunk state shared between workers
@@ -177,7 +190,7 @@ struct ftkb_group {
 extern "C" const char *ftkb_group_last_error(const ftkb_group *g) { return g ? g->error.c_str() : "null group"; }
 
 extern "C" int ftkb_group_create(const ftkb_config *cfg, const int32_t *device_ids, int32_t n_devices, int32_t chunk_timesteps, ftkb_group **out) {
-  if (!cfg || !out || !device_ids || n_devices < 1 || n_devices > 64 || chunk_timesteps < 1) return FTKB_ERR_INVALID;
+  if (!cfg || !out || !device_ids || n_devices < 1 || n_devices > 64 || chunk_timesteps < 0) return FTKB_ERR_INVALID;
   *out = nullptr;
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return FTKB_ERR_NO_DEVICE; }
@@ -187,6 +200,40 @@ extern "C" int ftkb_group_create(const ftkb_config *cfg, const int32_t *device_i
   g->cfg = *cfg;
   g->devices.assign(device_ids, device_ids + n_devices);
   g->B = chunk_timesteps;
+  g->spatial = chunk_timesteps == 0;
+  if (g->spatial) {
+    // z-slabs: the domain's corner planes are split evenly; slab s also sweeps the corner plane above its last one (the flat
+    // simplices of that plane are found twice and merged as one), and its array reaches two planes past every vertex it uses
+    // (gradient of the Jacobian's neighbours); the first / last slab hold the array's end planes so that min non-zero |v|
+    // still covers the whole array
+    const int D = cfg->dims[2], glb = cfg->lb[2], gub = cfg->ub[2], nplanes = gub - glb + 1;
+    if (cfg->nd != 3 || nplanes < 2 * n_devices) { delete g; return FTKB_ERR_INVALID; }
+    g->running = cfg->resolution_init > 0 ? cfg->resolution_init : DBL_MAX;
+    for (int s = 0; s < n_devices; s++) {
+      Slab sl;
+      sl.device = device_ids[s];
+      const int c0 = glb + (int)((long long)nplanes * s / n_devices), c1 = glb + (int)((long long)nplanes * (s + 1) / n_devices) - 1;
+      const int vtop = std::min(c1 + 1, gub);
+      sl.a0 = s == 0 ? 0 : std::max(0, c0 - 2);
+      sl.a1 = s == n_devices - 1 ? D - 1 : std::min(D - 1, vtop + 2);
+      ftkb_config c = *cfg;
+      c.device = sl.device;
+      c.dims[2] = sl.a1 - sl.a0 + 1;
+      c.lb[2] = c0 - sl.a0;
+      c.ub[2] = vtop - sl.a0;
+      c.slab_offset = sl.a0;
+      c.slab_global_dim = D;
+      c.slab_global_lb = glb;
+      c.slab_global_ub = gub;
+      const int rc = ftkb_create(&c, &sl.ctx);
+      if (rc) {
+        for (auto &x : g->slabs) ftkb_destroy(x.ctx);
+        delete g;
+        return rc;
+      }
+      g->slabs.push_back(sl);
+    }
+  }
   for (int i = 0; i < n_devices; i++) {
     g->workers.emplace_back(new Worker());
     g->workers.back()->start();
@@ -200,8 +247,54 @@ extern "C" void ftkb_group_destroy(ftkb_group *g) {
   g->fail(FTKB_ERR_INVALID, "group destroyed");            // releases workers that wait for a predecessor
   for (auto &w : g->workers) w->join();
   for (auto &ch : g->chunks) if (ch->ctx) ftkb_destroy(ch->ctx);
+  for (auto &sl : g->slabs) if (sl.ctx) ftkb_destroy(sl.ctx);
   if (g->root) ftkb_destroy(g->root);
   delete g;
+}
+
+// ---- spatial mode: every device works on every step ------------------------------------------------------------------------
+// run f(slab) on every device's worker and wait for all
+static int on_all_slabs(ftkb_group *g, std::function<int(Slab &)> f, const char *what) {
+  std::vector<std::shared_ptr<Done>> waits;
+  for (size_t s = 0; s < g->slabs.size(); s++) {
+    std::shared_ptr<Done> d(new Done());
+    waits.push_back(d);
+    Slab *sl = &g->slabs[s];
+    g->workers[s]->post([g, sl, f, d, what] {
+      int rc = g->failed.load();
+      if (!rc) {
+        rc = f(*sl);
+        if (rc) g->fail(rc, std::string(what) + ": " + ftkb_last_error(sl->ctx));
+      }
+      d->set(rc);
+    });
+  }
+  int rc = FTKB_OK;
+  for (auto &d : waits) { const int r = d->wait(); if (r && !rc) rc = r; }
+  return rc;
+}
+
+// The quantisation factor must be the undivided run's on every slab: until the running minimum saturates it, the slabs
+// resolve the new layer first (a cells-only build for scalar input, a reduction for vector input), the minima are combined
+// and handed back before anyone sweeps.  Once saturated (nbits = 21) nothing can change the factor and the step is skipped.
+static int spatial_sync_resolution(ftkb_group *g) {
+  if (nbits_of(g->running) == 21) return FTKB_OK;
+  std::vector<double> res(g->slabs.size(), DBL_MAX);
+  int rc = on_all_slabs(g, [&](Slab &sl) { return ftkb_last_layer_resolution(sl.ctx, &res[&sl - g->slabs.data()]); }, "resolution");
+  if (rc) return rc;
+  for (double r : res) if (r > 0 && r < g->running) g->running = r;
+  if (g->running < DBL_MAX) {
+    const double run = g->running;
+    rc = on_all_slabs(g, [run](Slab &sl) { return ftkb_set_resolution(sl.ctx, run); }, "set_resolution");
+  }
+  return rc;
+}
+
+static int spatial_push(ftkb_group *g, std::function<int(Slab &)> push) {
+  int rc = on_all_slabs(g, push, "push");
+  if (!rc) rc = spatial_sync_resolution(g);
+  g->npushed++;
+  return rc;
 }
 
 // hand one snapshot to chunk c's context (runs on that device's worker)
@@ -241,6 +334,14 @@ struct Staged { double *S = nullptr, *V = nullptr, *J = nullptr; };
 extern "C" int ftkb_group_push_snapshot(ftkb_group *g, const double *scalar, const double *vector, const double *jacobian) {
   if (!g) return FTKB_ERR_INVALID;
   if (g->failed.load()) return g->failed.load();
+  if (g->spatial) {
+    // every device copies its planes (ghost planes included) over its own PCIe link, concurrently
+    const size_t plane = (size_t)g->cfg.dims[0] * (size_t)g->cfg.dims[1];
+    return spatial_push(g, [=](Slab &sl) {
+      const size_t o = plane * (size_t)sl.a0;
+      return ftkb_push_snapshot(sl.ctx, scalar ? scalar + o : nullptr, vector ? vector + 3 * o : nullptr, jacobian ? jacobian + 9 * o : nullptr, FTKB_MEM_HOST);
+    });
+  }
   const int k = g->npushed;
   if (k % g->B != 0 || k == 0)
     // host memory, borrowed until return: wait for the copy
@@ -286,6 +387,7 @@ extern "C" int ftkb_group_push_snapshot(ftkb_group *g, const double *scalar, con
 extern "C" int ftkb_group_push_synthetic(ftkb_group *g, int kind, const double *params, int nparams, double t) {
   if (!g || nparams < 0 || nparams > 8 || (nparams && !params)) return FTKB_ERR_INVALID;
   std::vector<double> p(params, params + nparams);
+  if (g->spatial) return spatial_push(g, [=](Slab &sl) { return ftkb_push_synthetic(sl.ctx, kind, p.data(), (int)p.size(), t); });
   return push_layer(g, [=](ftkb_ctx *c) { return ftkb_push_synthetic(c, kind, p.data(), (int)p.size(), t); }, false);
 }
 
@@ -310,18 +412,40 @@ static int post_sweep(ftkb_group *g, int step, bool advance) {
 extern "C" int ftkb_group_advance_timestep(ftkb_group *g) {
   if (!g) return FTKB_ERR_INVALID;
   if (g->npushed < g->nadvanced + 2) { g->error = "advance_timestep: two snapshots are needed"; return FTKB_ERR_INVALID; }
+  if (g->spatial) { g->nadvanced++; return on_all_slabs(g, [](Slab &sl) { return ftkb_advance_timestep(sl.ctx); }, "sweep"); }
   return post_sweep(g, g->nadvanced++, true);
 }
 
 extern "C" int ftkb_group_update_timestep(ftkb_group *g) {
   if (!g) return FTKB_ERR_INVALID;
   if (g->npushed < g->nadvanced + 1) { g->error = "update_timestep: no snapshot has been pushed"; return FTKB_ERR_INVALID; }
+  if (g->spatial) return on_all_slabs(g, [](Slab &sl) { return ftkb_update_timestep(sl.ctx); }, "sweep");
   return post_sweep(g, g->nadvanced, false);
 }
 
 extern "C" int ftkb_group_finalize(ftkb_group *g, ftkb_ctx **root) {
   if (!g || !root) return FTKB_ERR_INVALID;
   *root = nullptr;
+  if (g->spatial) {
+    int rc = on_all_slabs(g, [](Slab &sl) {
+      uint64_t n = 0;
+      int r = ftkb_get_stats(sl.ctx, &sl.stats);
+      if (!r) r = ftkb_num_points(sl.ctx, &n);
+      if (!r) { sl.points.resize(n); r = ftkb_get_points(sl.ctx, sl.points.data(), n); }
+      return r;
+    }, "collect");
+    if (rc) return rc;
+    if (g->root) { ftkb_destroy(g->root); g->root = nullptr; }
+    ftkb_config c = g->cfg;
+    c.device = g->devices[0];
+    if ((rc = ftkb_create(&c, &g->root))) { g->error = ftkb_last_error(nullptr); return rc; }
+    // (the flat simplices of a cut plane were found by both neighbours: the root's sort drops the duplicates)
+    for (auto &sl : g->slabs)
+      if (!sl.points.empty() && (rc = ftkb_import_points(g->root, sl.points.data(), sl.points.size()))) { g->error = ftkb_last_error(g->root); return rc; }
+    if ((rc = ftkb_finalize(g->root))) { g->error = ftkb_last_error(g->root); return rc; }
+    *root = g->root;
+    return FTKB_OK;
+  }
   // wait for every device's queue to drain
   std::vector<std::shared_ptr<Done>> waits;
   for (auto &w : g->workers) {
@@ -352,6 +476,15 @@ extern "C" int ftkb_group_get_stats(ftkb_group *g, ftkb_stats *sum, int32_t *chu
   std::lock_guard<std::mutex> lk(g->m);
   ftkb_stats s{};
   int done = 0;
+  for (auto &sl : g->slabs) {          // spatial mode: as collected by ftkb_group_finalize
+    const ftkb_stats &t = sl.stats;
+    s.simplices_tested += t.simplices_tested; s.cells_scanned += t.cells_scanned; s.cells_refined += t.cells_refined;
+    s.points += t.points; s.kernel_launches += t.kernel_launches; s.h2d_bytes += t.h2d_bytes; s.d2h_bytes += t.d2h_bytes;
+    s.ms_derive += t.ms_derive; s.ms_scan += t.ms_scan; s.ms_test += t.ms_test;
+    s.scan_launches += t.scan_launches; s.sweeps_repeated += t.sweeps_repeated;
+    s.scaling_factor = t.scaling_factor; s.resolution = t.resolution;
+    done++;
+  }
   for (auto &ch : g->chunks) {
     if (!ch->finished) continue;
     done++;

@@ -3154,18 +3154,16 @@ __device__ __forceinline__ int sos_rank(const SweepParams &p, const int *v /* ND
   u64 prod = 1, i = 0;
 #pragma unroll
   for (int j = 0; j <= ND; j++) {
-    const int lbj = j < ND ? p.lb[j] : 0;
-    const u64 d = (u64)(i64)(v[j] - lbj);
+    // (the whole lattice's frame: a spatial slab ranks its vertices as the undivided domain would)
+    const u64 d = j < ND ? (u64)(i64)(v[j] + p.voff[j] - p.rank_lb[j]) : (u64)(i64)v[j];
     i += d * prod;
-    if (j < ND) prod *= (u64)(p.ub[j] - p.lb[j] + 1);
+    if (j < ND) prod *= (u64)p.rank_nc[j];
   }
   return (int)(unsigned)i;
 }
 
-// vcache: the cube's 2^(ND+1) vertex vectors, [vertex mask][component], gathered once per cube by the block (test_kernel).
-// PRETEST: only validity + quantisation + the cheap exact exclusion; true = the simplex needs the full test (the block then runs
-// the full test on the compacted survivors, so that the long SoS cascade is executed by full warps)
-template <int ND, bool PRETEST = false>
+// vcache: the cube's 2^(ND+1) vertex vectors, [vertex mask][component], gathered once per cube by the block (test_kernel)
+template <int ND>
 __device__ bool check_simplex(const SweepParams &p, const DeviceMeshTables &mt, const int corner[3], int type, ftkb_point &cp, const double *vcache) {
   constexpr int NV = ND + 1;
   int vt[NV][ND + 1];
@@ -3192,26 +3190,6 @@ __device__ bool check_simplex(const SweepParams &p, const DeviceMeshTables &mt, 
   for (int k = 0; k < NV; k++)
 #pragma unroll
     for (int c = 0; c < ND; c++) v[k][c] = vcache[mt.vmask[type][k] * ND + c];
-
-  if constexpr (PRETEST) {
-    if (!(ND == 2 || p.robust)) return true;
-    const i64 lim = ND == 2 ? (1ll << 29) : (1ll << 19);
-    bool small = true, sided = false;
-#pragma unroll
-    for (int c = 0; c < ND; c++) {
-      bool pos = true, neg = true;
-#pragma unroll
-      for (int k = 0; k < NV; k++) {
-        if (isnan(v[k][c]) || isinf(v[k][c])) return false;
-        const i64 q = quantise(v[k][c], p.factor);
-        pos = pos && q > 0;
-        neg = neg && q < 0;
-        small = small && q < lim && q > -lim;
-      }
-      sided = sided || pos || neg;
-    }
-    return !(small && sided);
-  }
 
   double mu[NV];
   bool inside = false;
@@ -3266,12 +3244,13 @@ __device__ bool check_simplex(const SweepParams &p, const DeviceMeshTables &mt, 
     for (int q = 0; q < 4; q++) {
       double acc;
       if constexpr (ND == 2) {
-        const double c0 = q < 2 ? (double)vt[0][q] : (q == 2 ? 0.0 : (double)vt[0][2]);
-        const double c1 = q < 2 ? (double)vt[1][q] : (q == 2 ? 0.0 : (double)vt[1][2]);
-        const double c2 = q < 2 ? (double)vt[2][q] : (q == 2 ? 0.0 : (double)vt[2][2]);
+        const double c0 = q < 2 ? (double)(vt[0][q] + p.voff[q]) : (q == 2 ? 0.0 : (double)vt[0][2]);
+        const double c1 = q < 2 ? (double)(vt[1][q] + p.voff[q]) : (q == 2 ? 0.0 : (double)vt[1][2]);
+        const double c2 = q < 2 ? (double)(vt[2][q] + p.voff[q]) : (q == 2 ? 0.0 : (double)vt[2][2]);
         acc = c0 * mu[0] + c1 * mu[1] + c2 * mu[2];
       } else {
-        acc = (double)vt[0][q] * mu[0] + (double)vt[1][q] * mu[1] + (double)vt[2][q] * mu[2] + (double)vt[ND][q] * mu[ND];
+        const int og = q < ND ? p.voff[q < ND ? q : 0] : 0;      // a slab reports positions in the whole array's frame
+        acc = (double)(vt[0][q] + og) * mu[0] + (double)(vt[1][q] + og) * mu[1] + (double)(vt[2][q] + og) * mu[2] + (double)(vt[ND][q] + og) * mu[ND];
       }
       xo[q] = acc;
     }
@@ -3294,8 +3273,8 @@ __device__ bool check_simplex(const SweepParams &p, const DeviceMeshTables &mt, 
     if constexpr (ND == 3) acc = acc + __ldg(L[ND]->S + vi[ND]) * mu[ND];
     cp.scalar = acc;
   }
-  cp.corner[0] = corner[0]; cp.corner[1] = corner[1];
-  cp.corner[2] = ND == 3 ? corner[2] : 0;
+  cp.corner[0] = corner[0] + p.voff[0]; cp.corner[1] = corner[1] + p.voff[1];
+  cp.corner[2] = ND == 3 ? corner[2] + p.voff[2] : 0;
   cp.corner[3] = p.t;
   cp.simplex_type = type;
   cp.ordinal = mt.ordinal[type];
@@ -3381,8 +3360,6 @@ __global__ void __launch_bounds__(128) test_kernel(const __grid_constant__ Sweep
   constexpr int CPB = 128 / ntypes;                   // cubes per block and round (10 in 2D, 2 in 3D)
   __shared__ double vcache[CPB][NVC * ND];
   __shared__ int ccorner[CPB][3];
-  __shared__ unsigned short need_list[128];
-  __shared__ int need_count;
   u64 ncubes = *p.wl_count;
   if (ncubes > p.wl_cap) ncubes = p.wl_cap;
   const u64 stride = (u64)gridDim.x * CPB;
@@ -3390,7 +3367,6 @@ __global__ void __launch_bounds__(128) test_kernel(const __grid_constant__ Sweep
   const int lane = threadIdx.x & 31;
   for (u64 r = 0; r < rounds; r++) {
     const u64 cube0 = r * stride + (u64)blockIdx.x * CPB;
-    if (threadIdx.x == 0) need_count = 0;
     // ---- gather: thread t -> (cube t / NVC, vertex mask t % NVC)
     for (int t = threadIdx.x; t < CPB * NVC; t += blockDim.x) {
       const int ci = t / NVC, m = t % NVC;
@@ -3420,34 +3396,15 @@ __global__ void __launch_bounds__(128) test_kernel(const __grid_constant__ Sweep
       }
     }
     __syncthreads();
-    // ---- pretest: thread t -> (cube t / ntypes, type t % ntypes): validity, quantisation, cheap exact exclusion; what survives
-    // is compacted so that the long part (SoS cascade, interpolation, Jacobians) runs in full warps
-    {
-      ftkb_point dummy;
-      const int ci = threadIdx.x / ntypes, type = threadIdx.x % ntypes;
-      bool need = false;
-      if (ci < CPB && cube0 + (u64)ci < ncubes && (p.has_next || mt.ordinal[type])) {
-        const int corner[3] = {ccorner[ci][0], ccorner[ci][1], ccorner[ci][2]};
-        need = check_simplex<ND, true>(p, mt, corner, type, dummy, vcache[ci]);
-      }
-      const unsigned nb = __ballot_sync(0xffffffffu, need);
-      if (nb) {
-        int base = 0;
-        const int leader = __ffs(nb) - 1;
-        if (lane == leader) base = atomicAdd(&need_count, __popc(nb));
-        base = __shfl_sync(0xffffffffu, base, leader);
-        if (need) need_list[base + __popc(nb & ((1u << lane) - 1))] = (unsigned short)threadIdx.x;
-      }
-    }
-    __syncthreads();
-    // ---- full test on the survivors
+    // ---- test: thread t -> (cube t / ntypes, type t % ntypes)
     bool hit = false;
     ftkb_point cp;
-    if ((int)threadIdx.x < need_count) {
-      const int t = need_list[threadIdx.x];
-      const int ci = t / ntypes, type = t % ntypes;
-      const int corner[3] = {ccorner[ci][0], ccorner[ci][1], ccorner[ci][2]};
-      hit = check_simplex<ND, false>(p, mt, corner, type, cp, vcache[ci]);
+    {
+      const int ci = threadIdx.x / ntypes, type = threadIdx.x % ntypes;
+      if (ci < CPB && cube0 + (u64)ci < ncubes && (p.has_next || mt.ordinal[type])) {
+        const int corner[3] = {ccorner[ci][0], ccorner[ci][1], ccorner[ci][2]};
+        hit = check_simplex<ND>(p, mt, corner, type, cp, vcache[ci]);
+      }
     }
     const unsigned b = __ballot_sync(0xffffffffu, hit);
     if (b) {
@@ -3600,10 +3557,11 @@ void launch_fill_u64(unsigned long long *p, unsigned long long v, cudaStream_t s
 // =============================================================================================
 struct SynParams { double p[8]; };
 
-__global__ void __launch_bounds__(256) synthetic_kernel(int kind, int nd, int W, int H, int D, SynParams sp, double t, double *__restrict__ out) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y * blockDim.y + threadIdx.y, k = blockIdx.z;
+__global__ void __launch_bounds__(256) synthetic_kernel(int kind, int nd, int W, int H, int Dg, SynParams sp, double t, double *__restrict__ out, int zoff) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y * blockDim.y + threadIdx.y, kl = blockIdx.z;
   if (i >= W || j >= H) return;
-  const size_t idx = (size_t)i + (size_t)W * ((size_t)j + (size_t)H * k);
+  const size_t idx = (size_t)i + (size_t)W * ((size_t)j + (size_t)H * kl);
+  const int k = kl + zoff, D = Dg;          // a slab generates its planes of the whole array
   const double kPi = 3.14159265358979323846;
   switch (kind) {
     case FTKB_SYN_MOVING_EXTREMUM: {   // synthetic.hh:332-354; pow(d, 2) is the correctly rounded square
@@ -3663,11 +3621,11 @@ __global__ void __launch_bounds__(256) synthetic_kernel(int kind, int nd, int W,
   }
 }
 
-void launch_synthetic(int kind, int nd, int W, int H, int D, const double *params, double t, double *out, cudaStream_t s) {
+void launch_synthetic(int kind, int nd, int W, int H, int D, const double *params, double t, double *out, cudaStream_t s, int zoff, int Dg) {
   SynParams sp;
   for (int i = 0; i < 8; i++) sp.p[i] = params[i];
   const dim3 block(64, 4), grid((W + 63) / 64, (H + 3) / 4, D);
-  synthetic_kernel<<<grid, block, 0, s>>>(kind, nd, W, H, D, sp, t, out);
+  synthetic_kernel<<<grid, block, 0, s>>>(kind, nd, W, H, Dg > 0 ? Dg : D, sp, t, out, zoff);
 }
 
 // =============================================================================================

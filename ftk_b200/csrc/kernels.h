@@ -22,6 +22,9 @@ struct SweepParams {
   int32_t lb[3], ub[3];       // domain (inclusive)
   int32_t nc[3];              // corners per dimension = ub - lb + 1 (1 for the unused dim)
   int32_t vmax[3];            // last vertex that enters a cube's value range per dim (= ub)
+  // global frame of a spatial slab (all zero / equal to lb, nc when the context is not a slab): offset of the local array in
+  // the whole one, and the whole domain's lower bound / extent -- SoS vertex rank, interpolated position, reported corner
+  int32_t voff[3], rank_lb[3], rank_nc[3];
   int32_t t;                  // current timestep (time of layer 0)
   int32_t has_next;           // layer 1 present -> interval simplices are swept too
   int32_t nbits;              // factor = 2^nbits
@@ -119,7 +122,8 @@ void launch_resolution(const double *p, uint64_t n, unsigned long long *res_bits
 void launch_fill_u64(unsigned long long *p, unsigned long long v, cudaStream_t s);
 
 // synthetic generators (ref: include/ftk/ndarray/synthetic.hh); out is S (scalar kinds) or V (vector kinds)
-void launch_synthetic(int kind, int nd, int W, int H, int D, const double *params, double t, double *out, cudaStream_t s);
+// zoff / Dg: the slab's first plane and the whole array's depth (3D; zoff = 0, Dg = D when the context is not a slab)
+void launch_synthetic(int kind, int nd, int W, int H, int D, const double *params, double t, double *out, cudaStream_t s, int zoff = 0, int Dg = 0);
 
 // finalize
 struct TraceParams {

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define FTKB_ABI_VERSION 1
+#define FTKB_ABI_VERSION 2
 
 enum {
   FTKB_OK = 0,
@@ -90,6 +90,14 @@ typedef struct ftkb_config {
   double  resolution_init;    /* running min non-zero |v| inherited from earlier time slabs; <= 0: DBL_MAX
                                  (critical_point_tracker.hh:850-864 keeps a running minimum over all sweeps) */
   uint64_t point_capacity;    /* initial capacity of the punctured-simplex buffer; 0: default (grows on demand) */
+  /* ABI 2 -- spatial slab of a larger array (3D: slabs along z, the reference's spatial decomposition with ghost layers,
+   * regular_tracker.hh:126-149).  The context holds planes [slab_offset, slab_offset + dims[2]) of an array of slab_global_dim
+   * planes; lb / ub stay relative to the slab.  Everything that depends on a vertex's position in the WHOLE lattice uses the
+   * global frame: the SoS vertex rank (regular_tracker.hh:188-194), the interpolated position, the reported corner, the element
+   * key, the device generators.  slab_global_dim = 0: not a slab (the defaults below are then ignored). */
+  int32_t slab_offset;
+  int32_t slab_global_dim;
+  int32_t slab_global_lb, slab_global_ub;   /* bounds of the whole tracker domain along z, in the whole array's indices */
 } ftkb_config;
 
 /* one punctured simplex; same 72-byte layout the parity oracle uses */

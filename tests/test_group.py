@@ -109,3 +109,67 @@ def test_cli_device_list_equals_one_device(tmp_path):
     assert len(outs[0]) > 0
     for o in outs[1:]:
         assert o == outs[0]
+
+
+# ---- spatial decomposition: z-slabs with ghost planes (chunk = 0; the reference's decomposition, regular_tracker.hh:126-149) ------
+def _slab_lists():
+    n = _ndev()
+    out = [[0, 0], [0, 0, 0]]
+    if n >= 2:
+        out.append([0, 1])
+    if n >= 4:
+        out.append([0, 1, 2, 3])
+    return out
+
+
+@pytest.mark.parametrize("field,kind", [("scalar", "smooth"), ("vector", "smooth"), ("scalar", "int"), ("vector", "int")])
+def test_z_slabs_equal_one_device(field, kind, oracle):
+    """every device holds a z-slab (plus ghost planes) of every snapshot and sweeps every step; SoS ranks, positions, corners and
+    the quantisation factor are those of the undivided domain, so the merged result equals the one-device run bit for bit"""
+    import ftk_b200
+    from ftk_b200.group import track_on_devices
+    from test_gpu_parity import _rand_series
+    rng = np.random.default_rng(91)
+    dims, T = [36, 30, 26], 4
+    nv = 1 if field == "scalar" else 3
+    snaps = _rand_series(rng, dims, T, nv, kind)
+    one = ftk_b200.track(snaps, dims, field=field)
+    want = P.oracle_result(oracle.track(snaps, dims, field=field))
+    assert len(want["points"]) > 0
+    for ids in _slab_lists():
+        g, root = track_on_devices(snaps, dims, ids, field=field, chunk=0)
+        _same(root, one, f"z-slabs {ids} {field} {kind}")
+        P.assert_same_result({"points": root.get_discrete_critical_points(), "trajectories": root.get_trajectory_index()}, want, tol=TOL, what="vs oracle")
+        assert root.stats()["points"] == len(want["points"])
+        g.close()
+    one.close()
+
+
+def test_z_slabs_moving_extremum_and_generators(oracle):
+    """a feature that crosses the cuts (moving extremum through z), and device-side generators that depend on the global z"""
+    import ftk_b200
+    from ftk_b200.group import GroupTracker, track_on_devices
+    dims, T = [32, 28, 40], 6
+    x0, d = [15.3, 13.7, 10.1], [0.2, 0.1, 3.7]        # moves 3.7 planes per step: through every cut of 2 and 3 slabs
+    snaps = [oracle.gen_moving_extremum(dims, x0, d, float(k)) for k in range(T)]
+    one = ftk_b200.track(snaps, dims, field="scalar")
+    assert len(one.get_trajectory_index()) == 1
+    for ids in _slab_lists():
+        g, root = track_on_devices(snaps, dims, ids, field="scalar", chunk=0)
+        _same(root, one, f"z-slabs {ids} moving extremum")
+        g.close()
+    one.close()
+    for kind, prm, field, dims in ((3, [np.sqrt(3.0), np.sqrt(2.0), 1.0], "vector", [24, 22, 30]), (5, [], "vector", [20, 18, 24])):
+        one = ftk_b200.make_tracker(dims, field=field)
+        g = GroupTracker(dims, _slab_lists()[-1], field=field, chunk=0)
+        for tr in (one, g):
+            for k in range(4):
+                tr.push_synthetic_snapshot(kind, prm, float(k))
+                if k:
+                    tr.advance_timestep()
+                if k == 3:
+                    tr.update_timestep()
+        one.finalize()
+        _same(g.finalize(), one, f"z-slabs generator {kind}")
+        g.close()
+        one.close()
