@@ -64,7 +64,7 @@ void usage() {
       "      --post-process OPS                smooth_types,rotate,split,discard_interval_points,reorder,adjust_time,derive_velocity,...\n"
       "      --compute-degrees  --no-robust-detection  --timing  -v/--verbose\n"
       "      --stream                          streaming trajectories: grown after every timestep (trace_critical_points_online)\n"
-      "  -a, --accelerator cuda            (the only back end)   --device ID[,ID...]   --time-chunk N (timesteps per device turn, default 8)\n"
+      "  -a, --accelerator cuda            (the only back end)   --device ID[,ID...]   --time-chunk N (timesteps per device turn, default 8; 0 = z-slabs, 3D)\n"
       "      --nthreads N                  (ignored)\n"
       "      --device-generators           synthesise inputs on the GPU (CUDA libm; not bit-identical to the host generators)");
 }

@@ -352,7 +352,7 @@ class critical_point_tracker_regular {
   // filter.hh:47-51: one id = that device; several = the tracker is served by all of them (ftkb_group: time chunks of
   // set_time_chunk() timesteps go round the devices; results equal the one-device run)
   void set_device_ids(const std::vector<int> &ids) { device_ids_ = ids; if (!ids.empty()) device_ = ids[0]; }
-  void set_time_chunk(int timesteps) { time_chunk_ = timesteps > 0 ? timesteps : 8; }
+  void set_time_chunk(int timesteps) { time_chunk_ = timesteps >= 0 ? timesteps : 8; }     // 0: z-slabs (3D) instead of time chunks
   void set_start_timestep(int t) { start_timestep_ = t; }
   void set_current_timestep(int t) { start_timestep_ = t; }
   // time-slab sharding: running min non-zero |v| inherited from the slabs before this one

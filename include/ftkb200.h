@@ -216,7 +216,15 @@ int ftkb_push_snapshot_remote(ftkb_ctx *, const double *scalar, const double *ve
  * the one-device run bit for bit.  ftkb_group_finalize merges the punctured simplices of all chunks into one context on
  * device_ids[0] and traces there; *root stays owned by the group and serves every getter (ftkb_get_points, ftkb_get_trajectories,
  * ftkb_get_curveset ...).  cfg->device is ignored; streaming trajectories are not available on a group.
- * ftkb_group_push_snapshot takes HOST memory (borrowed until return); ftkb_group_push_synthetic generates on the devices. */
+ * ftkb_group_push_snapshot takes HOST memory (borrowed until return); ftkb_group_push_synthetic generates on the devices.
+ *
+ * chunk_timesteps = 0 selects the SPATIAL decomposition instead (3D only; the reference's own, regular_tracker.hh:126-149):
+ * device s holds a z-slab of every snapshot -- its share of the domain's corner planes, the corner plane above (whose flat
+ * simplices both neighbours find; the merge drops the duplicates) and two ghost planes beyond every vertex it uses -- and every
+ * device sweeps every step, so a host snapshot travels in N pieces over N PCIe links at once.  SoS vertex ranks, interpolated
+ * positions, reported corners and the device generators use the whole array's frame (ftkb_config.slab_*); until the running
+ * minimum of min non-zero |v| saturates the quantisation factor, the slabs' minima are combined before every sweep, so every
+ * slab quantises exactly as the undivided run does. */
 typedef struct ftkb_group ftkb_group;
 int ftkb_group_create(const ftkb_config *cfg, const int32_t *device_ids, int32_t n_devices, int32_t chunk_timesteps, ftkb_group **out);
 void ftkb_group_destroy(ftkb_group *);
