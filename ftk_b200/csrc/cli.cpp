@@ -231,7 +231,8 @@ void gen_double_gyre(long W, long H, double time, double *out) {      // synthet
 // raw input: snapshot k from one big file (offset k * bytes) or from sprintf(pattern, k).  The byte range is read by several
 // threads at once (pread on disjoint slices, float32 converted slice by slice): one thread copying out of the page cache
 // delivers about 5 GB/s, a fifth of what the PCIe link behind it takes.
-void read_raw(const Options &o, long k, size_t count, bool f32, double *out) {
+// (keep_f32: the float32 bytes are delivered as they are -- `out` then holds `count` floats -- and widened on the device)
+void read_raw(const Options &o, long k, size_t count, bool f32, double *out, bool keep_f32 = false) {
   std::string path = o.input;
   long offset = 0;
   if (o.input.find('%') != std::string::npos) {
@@ -253,17 +254,18 @@ void read_raw(const Options &o, long k, size_t count, bool f32, double *out) {
       const size_t e0 = count * t / nthr, e1 = count * (t + 1) / nthr;
       std::vector<float> tmp;
       const size_t chunk = 1u << 22;                       // elements per pread
-      if (f32) tmp.resize(std::min(chunk, e1 - e0));
+      if (f32 && !keep_f32) tmp.resize(std::min(chunk, e1 - e0));
       for (size_t e = e0; e < e1;) {
         const size_t n = std::min(chunk, e1 - e);
-        char *dst = f32 ? reinterpret_cast<char *>(tmp.data()) : reinterpret_cast<char *>(out + e);
+        char *dst = keep_f32 ? reinterpret_cast<char *>(reinterpret_cast<float *>(out) + e)
+                             : f32 ? reinterpret_cast<char *>(tmp.data()) : reinterpret_cast<char *>(out + e);
         size_t got = 0;
         while (got < n * esz) {
           const ssize_t r = ::pread(fd, dst + got, n * esz - got, (off_t)(offset + (long)(e * esz + got)));
           if (r <= 0) { bad[t] = 1; return; }
           got += (size_t)r;
         }
-        if (f32) for (size_t i = 0; i < n; i++) out[e + i] = (double)tmp[i];
+        if (f32 && !keep_f32) for (size_t i = 0; i < n; i++) out[e + i] = (double)tmp[i];
         e += n;
       }
     });
@@ -399,6 +401,8 @@ int main(int argc, char **argv) {
     // generated) and converted while snapshot k travels to the device and is swept (the reference overlaps I/O and compute the
     // same way, ndarray/stream.hh:1607-1699)
     Feed feed;
+    // raw float32 series on one device: the bytes go to the device as they are (half the PCIe traffic) and are widened there
+    const bool raw_f32 = syn < 0 && o.input_format == "float32" && o.devices.size() <= 1;
     if (!(syn >= 0 && o.device_generators))
       feed.start(T, nvert * nv, [&](long k, double *dst) {
         if (syn == FTKB_SYN_WOVEN) gen_woven(dims[0], dims[1], T == 1 ? 0.0 : double(k) / (T - 1), dst);        // stream.hh:1468-1480
@@ -406,7 +410,7 @@ int main(int argc, char **argv) {
         else if (syn == FTKB_SYN_DOUBLE_GYRE) gen_double_gyre(dims[0], dims[1], k * o.time_scale, dst);        // stream.hh:1542-1555
         else if (syn == FTKB_SYN_TORNADO) gen_tornado(dims[0], dims[1], dims[2], (int)k, dst);                  // stream.hh:1560-1567
         else if (syn == FTKB_SYN_MOVING_EXTREMUM) gen_moving_extremum(nd, dims, o.x0.data(), o.dir.data(), double(k), dst);
-        else read_raw(o, k, nvert * nv, o.input_format == "float32", dst);
+        else read_raw(o, k, nvert * nv, o.input_format == "float32", dst, raw_f32);
       });
     for (long k = 0; k < T; k++) {
       if (o.verbose) std::fprintf(stderr, "current_timestep=%ld\n", k);
@@ -420,8 +424,13 @@ int main(int argc, char **argv) {
         tr->push_synthetic_snapshot(syn, p, t);
       } else {
         double *buf = feed.get(k);                   // filled by the reader thread while the previous snapshot was pushed and swept
-        const ndarray<double> a = ndarray<double>::wrap(buf, shape);
-        if (nv == 1) tr->push_scalar_field_snapshot(a); else tr->push_vector_field_snapshot(a);
+        if (raw_f32) {
+          const ndarray<float> a = ndarray<float>::wrap(reinterpret_cast<const float *>(buf), shape);
+          if (nv == 1) tr->push_scalar_field_snapshot(a); else tr->push_vector_field_snapshot(a);
+        } else {
+          const ndarray<double> a = ndarray<double>::wrap(buf, shape);
+          if (nv == 1) tr->push_scalar_field_snapshot(a); else tr->push_vector_field_snapshot(a);
+        }
         feed.release(k);                             // (the push copies before it returns)
       }
       if (k != 0) tr->advance_timestep();          // json_interface.hh:699-706

@@ -16,6 +16,8 @@
 #include <cstring>
 #include <deque>
 #include <string>
+#include <thread>
+#include <atomic>
 #include <vector>
 
 #include <future>
@@ -54,6 +56,8 @@ struct ftkb_ctx {
   std::string error;
 
   bool slab = false;             // the context holds a z-slab of a larger array (cfg.slab_*)
+  void *d_f32 = nullptr;         // staging of float32 snapshots (ftkb_push_snapshot_f32)
+  size_t f32_cap = 0;
   std::deque<Layer> layers;
   std::vector<double *> freeS, freeV, freeJ;   // buffer pools
   int current_timestep = 0;
@@ -250,6 +254,7 @@ extern "C" void ftkb_destroy(ftkb_ctx *c) {
   if (c->ev_join) cudaEventDestroy(c->ev_join);
   cudaFree(c->d_pts);
   cudaFree(c->d_coords);
+  cudaFree(c->d_f32);
   cudaFree(c->d_pts_sorted);
   cudaFree(c->d_keys_sorted);
   for (auto &s : c->fz) cudaFree(s.p);
@@ -473,6 +478,46 @@ extern "C" int ftkb_push_snapshot(ftkb_ctx *c, const double *scalar, const doubl
   return FTKB_OK;
 }
 
+// A snapshot that exists as float32 (raw float32 file series: the reference widens them on the host, ndarray.hh read_binary_file):
+// it travels over PCIe as float32 and is widened on the device, into the same resident fp64 layer the other pushes produce.
+extern "C" int ftkb_push_snapshot_f32(ftkb_ctx *c, const float *scalar, const float *vector) {
+  if (!c) return FTKB_ERR_INVALID;
+  if (c->cfg.jacobian_source == FTKB_SOURCE_GIVEN) return fail(c, FTKB_ERR_INVALID, "push_snapshot_f32: a GIVEN jacobian has no float32 form");
+  if (c->cfg.scalar_source == FTKB_SOURCE_GIVEN && !scalar) return fail(c, FTKB_ERR_INVALID, "push: scalar field is GIVEN but no scalar array was passed");
+  if (c->cfg.vector_source == FTKB_SOURCE_GIVEN && !vector) return fail(c, FTKB_ERR_INVALID, "push: vector field is GIVEN but no vector array was passed");
+  if (c->cfg.vector_source == FTKB_SOURCE_DERIVED && !vector && !scalar) return fail(c, FTKB_ERR_INVALID, "push: vector field is DERIVED but no scalar array was passed");
+  if ((uintptr_t)scalar % 4 != 0 || (uintptr_t)vector % 4 != 0) return fail(c, FTKB_ERR_INVALID, "push: arrays must be 4-byte aligned");
+  CK(cudaSetDevice(c->cfg.device));
+  Layer l;
+  int rc = new_layer(c, l);
+  if (rc) return rc;
+  const size_t nS = c->nvert, nV = c->nvert * c->n;
+  const size_t need = 4 * std::max(scalar ? nS : 0, vector ? nV : 0) + 16;
+  if (c->f32_cap < need) {
+    cudaFree(c->d_f32);
+    c->d_f32 = nullptr; c->f32_cap = 0;
+    CK(cudaMalloc(&c->d_f32, need));
+    c->f32_cap = need;
+  }
+  auto ingest = [&](const float *src, size_t count, std::vector<double *> &pool, double **dst, bool *own) -> int {
+    if (!src) return FTKB_OK;
+    const int r = take_buffer(c, pool, count, dst);
+    if (r) return r;
+    *own = true;
+    CK(cudaMemcpyAsync(c->d_f32, src, 4 * count, cudaMemcpyHostToDevice, c->stream));
+    launch_widen_f32(static_cast<const float *>(c->d_f32), *dst, count, c->stream);
+    c->stats.h2d_bytes += 4 * count;
+    c->stats.kernel_launches++;
+    return check_launch(c, "widen");
+  };
+  if ((rc = ingest(scalar, nS, c->freeS, &l.S, &l.ownS))) { release_layer(c, l); return rc; }
+  if ((rc = ingest(vector, nV, c->freeV, &l.V, &l.ownV))) { release_layer(c, l); return rc; }
+  if ((rc = derive_layer(c, l))) { release_layer(c, l); return rc; }
+  CK(cudaStreamSynchronize(c->stream));      // the host buffer is borrowed only until return
+  c->layers.push_back(l);
+  return FTKB_OK;
+}
+
 extern "C" int ftkb_set_producer_stream(ftkb_ctx *c, void *stream, int enable) {
   if (!c) return FTKB_ERR_INVALID;
   c->producer = reinterpret_cast<cudaStream_t>(stream);
@@ -678,6 +723,19 @@ static void fused3d_decomposition(const ftkb_ctx *c, SweepParams &p, bool cells 
   p.nsz = (p.D + p.rows - 1) / p.rows;
 }
 
+// vector input, range-cell scan: warps = strips of 62 corner columns x row chunks (2D), tiles x plane chunks (3D)
+static void vcells_decomposition(const ftkb_ctx *c, SweepParams &p) {
+  if (c->n == 3) { fused3d_decomposition(c, p, true); return; }
+  // two CTAs of 8 warps per SM, about six waves; chunks are multiples of the cell block
+  const int R = VSCAN2D_CELL_ROWS;
+  p.nsx = std::max(1, (p.W + 61) / 62);
+  const int64_t want = std::max<int64_t>(1, (6 * (int64_t)c->sm_count * 16) / p.nsx);
+  p.rows = std::max(2 * R, (int)((p.H + want - 1) / want));
+  p.rows = (p.rows + R - 1) / R * R;
+  p.nsy = (p.H + p.rows - 1) / p.rows;
+  p.nsz = 1;
+}
+
 static int ensure_cells(ftkb_ctx *c, Layer &l, const SweepParams &p) {
   if (l.cells) return FTKB_OK;
   if (!c->ncells) c->ncells = c->n == 3 ? scan3d_cells_per_layer(p) : (p.fused ? scan2d_cells_per_layer(p) : vscan2d_cells_per_layer(p));
@@ -721,7 +779,42 @@ static bool rows_aligned16(const ftkb_ctx *c, const double *a, const double *b) 
 static int resolve_pending(ftkb_ctx *c, Layer &l) {
   c->primed = false;
   CK(cudaMemsetAsync(c->d_scalars + l.slot, 0xff, sizeof(unsigned long long), c->stream));   // (a pending layer's device slot is reset lazily)
-  if (l.V) {          // vector input: the plain resolution pass
+  if (l.V) {
+    if (c->cellsV && c->cfg.vector_source == FTKB_SOURCE_GIVEN && (uintptr_t)l.V % 16 == 0 && !l.cells_valid) {
+      // vector input: stream the layer once -- its range cells and min |v|; no cube is tested (the sweeps then read the cells)
+      SweepParams p{};
+      fill_sweep_geometry(c, p);
+      p.fused = 0;
+      p.has_next = 0;
+      p.nbits = c->nbits ? c->nbits : 8;
+      p.L[0].V = l.V; p.L[1].V = l.V;
+      p.res_slot[0] = c->d_scalars + l.slot;
+      p.poison = c->d_scalars + ftkb_ctx::SLOT_POISON;
+      p.wl_count = c->d_scalars + ftkb_ctx::SLOT_WL;
+      p.wl = c->d_wl; p.wl_cap = 0;
+      vcells_decomposition(c, p);
+      const int rc = ensure_cells(c, l, p);
+      if (rc) return rc;
+      CK(cudaMemsetAsync(p.poison, 0, sizeof(unsigned long long), c->stream));
+      p.sum_mode = SUM_BUILD; p.build_layer = 0; p.sum_out = l.cells;
+      launch_vscan_cells(p, c->stream);
+      c->stats.kernel_launches++;
+      CK(cudaMemcpyAsync(c->h_scalars + l.slot, c->d_scalars + l.slot, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+      CK(cudaMemcpyAsync(c->h_scalars + ftkb_ctx::SLOT_POISON, p.poison, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+      c->stats.d2h_bytes += 16;
+      const int rl = check_launch(c, "resolution (vector cells)");
+      if (rl) return rl;
+      CK(cudaStreamSynchronize(c->stream));
+      if (!c->h_scalars[ftkb_ctx::SLOT_POISON]) {
+        l.cells_valid = true;
+        l.res_pending = false;
+        return FTKB_OK;
+      }
+      // magnitudes the float keys cannot order: fall back to the plain pass (and the two-layer scans)
+      c->cellsV = false;
+      for (Layer &x : c->layers) x.cells_valid = false;
+      CK(cudaMemsetAsync(c->d_scalars + l.slot, 0xff, sizeof(unsigned long long), c->stream));
+    }
     l.res_pending = false;
     return queue_resolution(c, l, false);
   }
@@ -1068,17 +1161,8 @@ static int update_impl(ftkb_ctx *c, bool allow_defer) {
   } else if (fused) {
     p.aligned16 = rows_aligned16(c, lay[0]->S, lay[1]->S);
     fused2d_decomposition(c, p);
-  } else if (vcells && c->n == 3) {
-    fused3d_decomposition(c, p, true);
   } else if (vcells) {
-    // warps = strips of 62 corner columns x row chunks (a multiple of the cell block); two CTAs of 8 warps per SM, about six waves
-    const int R = VSCAN2D_CELL_ROWS;
-    p.nsx = std::max(1, (p.W + 61) / 62);
-    const int64_t want = std::max<int64_t>(1, (6 * (int64_t)c->sm_count * 16) / p.nsx);
-    p.rows = std::max(2 * R, (int)((p.H + want - 1) / want));
-    p.rows = (p.rows + R - 1) / R * R;
-    p.nsy = (p.H + p.rows - 1) / p.rows;
-    p.nsz = 1;
+    vcells_decomposition(c, p);
   } else {
     p.nsx = (p.nc[0] + 30) / 31;
     if (c->n == 2) {
@@ -1520,7 +1604,6 @@ extern "C" int ftkb_finalize(ftkb_ctx *c) {
   const auto t0 = std::chrono::steady_clock::now();
   for (uint64_t i = 0; i < n; i++) c->labels[i] = pa[i];
   std::vector<uint8_t> visited(n, 0);
-  std::vector<uint32_t> fwd, bwd;
   auto ordinary = [&](uint32_t i) { return c->deg[i] <= 2; };
   auto next_unvisited = [&](uint32_t cur, uint32_t &out) {
     for (int q = 0; q < 8; q++) {
@@ -1530,38 +1613,70 @@ extern "C" int ftkb_finalize(ftkb_ctx *c) {
     }
     return false;
   };
-  c->traj_idx.reserve(n);
-  for (uint64_t seed = 0; seed < n; seed++) {
-    if (!ordinary((uint32_t)seed) || po[seed] != seed) continue;   // the smallest member starts the walk
-    fwd.clear(); bwd.clear();
-    visited[seed] = 1;
-    uint32_t sn[8]; int nsn = 0;
-    for (int q = 0; q < 8; q++) {
-      const uint32_t j = nb[seed * 8 + q];
-      if (j == 0xffffffffu) break;
-      if (ordinary(j)) sn[nsn++] = j;
-    }
-    for (int dir = 0; dir < 2 && nsn > 0; dir++) {
-      uint32_t cur = dir == 0 ? sn[0] : sn[nsn - 1];
-      while (true) {
-        if (!visited[cur]) { (dir == 0 ? fwd : bwd).push_back(cur); visited[cur] = 1; }
-        uint32_t nx;
-        if (!next_unvisited(cur, nx)) break;
-        cur = nx;
+  // The walks of different trajectories touch disjoint nodes (a trajectory is one connected component of the ordinary nodes),
+  // so they run on several host threads; the trajectories are then laid out in seed order, as the serial walk would.
+  std::vector<uint32_t> seeds;
+  for (uint64_t seed = 0; seed < n; seed++)
+    if (ordinary((uint32_t)seed) && po[seed] == seed) seeds.push_back((uint32_t)seed);   // the smallest member starts the walk
+  const size_t S = seeds.size();
+  struct Piece { uint32_t thread; uint64_t off, len; uint8_t loop; };
+  std::vector<Piece> pieces(S);
+  const unsigned hw = std::thread::hardware_concurrency();
+  const size_t nthr = std::max<size_t>(1, std::min<size_t>({(size_t)16, (size_t)(hw ? hw : 1), (size_t)(n / 65536 + 1)}));
+  std::vector<std::vector<uint32_t>> bufs(nthr);
+  std::atomic<size_t> next{0};
+  auto work = [&](const uint32_t tid) {
+    std::vector<uint32_t> &out = bufs[tid];
+    std::vector<uint32_t> fwd, bwd;
+    for (;;) {
+      const size_t s0 = next.fetch_add(64), s1 = std::min(S, s0 + 64);
+      if (s0 >= S) break;
+      for (size_t si = s0; si < s1; si++) {
+        const uint32_t seed = seeds[si];
+        fwd.clear(); bwd.clear();
+        visited[seed] = 1;
+        uint32_t sn[8]; int nsn = 0;
+        for (int q = 0; q < 8; q++) {
+          const uint32_t j = nb[(size_t)seed * 8 + q];
+          if (j == 0xffffffffu) break;
+          if (ordinary(j)) sn[nsn++] = j;
+        }
+        for (int dir = 0; dir < 2 && nsn > 0; dir++) {
+          uint32_t cur = dir == 0 ? sn[0] : sn[nsn - 1];
+          while (true) {
+            if (!visited[cur]) { (dir == 0 ? fwd : bwd).push_back(cur); visited[cur] = 1; }
+            uint32_t nx;
+            if (!next_unvisited(cur, nx)) break;
+            cur = nx;
+          }
+          if (nsn == 1) break;
+        }
+        const uint64_t start = out.size();
+        for (size_t k = bwd.size(); k > 0; k--) out.push_back(bwd[k - 1]);
+        out.push_back(seed);
+        for (uint32_t v : fwd) out.push_back(v);
+        const uint64_t len = out.size() - start;
+        bool loop = false;
+        if (len > 1) {   // is_loop: the back is a neighbour of the front (cc2curves.hh:113-122)
+          const uint64_t front = out[start], back = out.back();
+          for (int q = 0; q < 8; q++) loop = loop || nb[front * 8 + q] == back;
+        }
+        pieces[si] = Piece{tid, start, len, (uint8_t)loop};
       }
-      if (nsn == 1) break;
     }
-    const uint64_t start = c->traj_idx.size();
-    for (size_t k = bwd.size(); k > 0; k--) c->traj_idx.push_back(bwd[k - 1]);
-    c->traj_idx.push_back(seed);
-    for (uint32_t v : fwd) c->traj_idx.push_back(v);
-    const uint64_t len = c->traj_idx.size() - start;
-    bool loop = false;
-    if (len > 1) {   // is_loop: the back is a neighbour of the front (cc2curves.hh:113-122)
-      const uint64_t front = c->traj_idx[start], back = c->traj_idx.back();
-      for (int q = 0; q < 8; q++) loop = loop || nb[front * 8 + q] == back;
-    }
-    c->traj_loop.push_back(loop);
+  };
+  if (nthr == 1) work(0);
+  else {
+    std::vector<std::thread> pool;
+    for (uint32_t t = 0; t < nthr; t++) pool.emplace_back(work, t);
+    for (auto &th : pool) th.join();
+  }
+  c->traj_idx.reserve(n);
+  for (size_t si = 0; si < S; si++) {
+    const Piece &pc = pieces[si];
+    const uint32_t *src = bufs[pc.thread].data() + pc.off;
+    c->traj_idx.insert(c->traj_idx.end(), src, src + pc.len);
+    c->traj_loop.push_back(pc.loop);
     c->traj_off.push_back(c->traj_idx.size());
   }
   c->stats.ms_finalize_host += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();

@@ -3549,6 +3549,21 @@ void launch_resolution(const double *p, uint64_t n, unsigned long long *res_bits
   resolution_kernel<<<grid, 256, 0, s>>>(p, n, res_bits);
 }
 
+// float32 -> float64 widening of a snapshot that travelled as float32 (raw float32 file series: half the PCIe bytes)
+__global__ void __launch_bounds__(256) widen_f32_kernel(const float4 *__restrict__ in, double *__restrict__ out, u64 n4, const float *__restrict__ tail_in, u64 n) {
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (u64)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(in + i);
+    reinterpret_cast<double2 *>(out)[2 * i] = make_double2((double)v.x, (double)v.y);
+    reinterpret_cast<double2 *>(out)[2 * i + 1] = make_double2((double)v.z, (double)v.w);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) out[4 * n4 + threadIdx.x] = (double)tail_in[4 * n4 + threadIdx.x];
+}
+void launch_widen_f32(const float *in, double *out, uint64_t n, cudaStream_t s) {
+  const u64 n4 = n / 4;
+  const unsigned grid = (unsigned)std::max<u64>(1, std::min<u64>((n4 + 255) / 256, 148ull * 16));
+  widen_f32_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const float4 *>(in), out, n4, in, n);
+}
+
 __global__ void fill_u64_kernel(unsigned long long *p, unsigned long long v) { *p = v; }
 void launch_fill_u64(unsigned long long *p, unsigned long long v, cudaStream_t s) { fill_u64_kernel<<<1, 1, 0, s>>>(p, v); }
 

@@ -120,6 +120,7 @@ void launch_test(const SweepParams &p, cudaStream_t s);
 void launch_gradient(int nd, const double *S, double *V, int W, int H, int D, unsigned long long *res_bits, cudaStream_t s);
 void launch_resolution(const double *p, uint64_t n, unsigned long long *res_bits, cudaStream_t s);
 void launch_fill_u64(unsigned long long *p, unsigned long long v, cudaStream_t s);
+void launch_widen_f32(const float *in, double *out, uint64_t n, cudaStream_t s);   // in, out 16-byte aligned
 
 // synthetic generators (ref: include/ftk/ndarray/synthetic.hh); out is S (scalar kinds) or V (vector kinds)
 // zoff / Dg: the slab's first plane and the whole array's depth (3D; zoff = 0, Dg = D when the context is not a slab)

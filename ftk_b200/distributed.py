@@ -92,11 +92,11 @@ def _peer_sweep_slab(make, layer, push, t0, t1, T, field, resolution_init, excha
     keep.append(first)                                     # the neighbour reads it in place: must outlive the sweep
     kw = "scalar" if field == "scalar" else "vector"
     tr.push_device_pointers(**{kw: int(first.data_ptr())})
-    push(tr, layer(t0 + 1))
-    tr.update_timestep()                                   # builds the cells of the first layer
+    tr.last_layer_resolution()                             # streams the first layer once: its range cells and min |v|, no sweep
     cptr, _, cres = tr.export_layer_cells(0)
     peer = exchange((L.ipc_export(int(first.data_ptr())), L.ipc_export(cptr), cres))
-    tr.advance_timestep()
+    push(tr, layer(t0 + 1))
+    tr.advance_timestep()                                  # every step of the slab is swept exactly once
     log.append(_res_factor(tr))
     for k in range(t0 + 2, t1):
         push(tr, layer(k))
@@ -107,8 +107,11 @@ def _peer_sweep_slab(make, layer, push, t0, t1, T, field, resolution_init, excha
     else:
         import torch.cuda
         dev = torch.cuda.current_device()
-        tr.push_remote_snapshot(**{kw: L.ipc_import(peer[0], dev), "cells": L.ipc_import(peer[1], dev), "resolution": peer[2]})
+        mapped = [(L.ipc_import(peer[0], dev), peer[0]), (L.ipc_import(peer[1], dev), peer[1])]
+        tr.push_remote_snapshot(**{kw: mapped[0][0], "cells": mapped[1][0], "resolution": peer[2]})
         tr.advance_timestep()
+        tr.synchronize()
+        keep.append(("ipc", mapped))                       # unmapped once nobody sweeps any more (after the barrier)
     log.append(_res_factor(tr))
     return tr, log
 
@@ -191,7 +194,13 @@ def track_time_sharded(layer, dims, T, field="scalar", group=None, tracker_facto
                     tr.import_points(np.frombuffer(b, dtype=L.POINT_DTYPE))
         dist.barrier(group=group)             # nobody releases a layer or its cells while a neighbour may still sweep them
         for t in keep:
-            if hasattr(t, "close"):
+            if isinstance(t, tuple) and t and t[0] == "ipc":
+                for ptr, handle in t[1]:
+                    try:
+                        L.ipc_close(ptr, handle)
+                    except L.FTKBError:
+                        pass
+            elif hasattr(t, "close"):
                 t.close()
         if rank == 0 and streaming:
             info["streamed"] = _streamed(tr, dims, field, T, kw)

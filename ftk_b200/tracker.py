@@ -208,6 +208,21 @@ class _RegularTracker:
         """ref: critical_point_tracker.hh:202-213.  Host numpy arrays are copied; CUDA tensors are
         copied device-to-device, or used in place with borrow=True."""
         n = self.ND
+        given = [a for a in (scalar, vector, jacobian) if a is not None]
+        if jacobian is None and given and all(isinstance(a, np.ndarray) and a.dtype == np.float32 for a in given):
+            # float32 host arrays travel as float32 and are widened on the device (same values as widening here first)
+            ptrs, hold = [], []
+            for a, trailing in ((scalar, ()), (vector, (n,))):
+                if a is None:
+                    ptrs.append(None)
+                    continue
+                h = np.ascontiguousarray(a)
+                if h.size != int(np.prod(self._shape(trailing))):
+                    raise ValueError(f"array has {h.size} elements, expected {int(np.prod(self._shape(trailing)))}")
+                ptrs.append(h.ctypes.data)
+                hold.append(h)
+            self._check(L.lib().ftkb_push_snapshot_f32(self._h, ptrs[0], ptrs[1]))
+            return
         ptrs, where, hold = [], None, []
         for a, trailing in ((scalar, ()), (vector, (n,)), (jacobian, (n, n))):
             if a is None:

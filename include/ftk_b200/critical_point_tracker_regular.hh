@@ -419,6 +419,24 @@ class critical_point_tracker_regular {
   }
   void push_scalar_field_snapshot(const ndarray<double> &scalar) { push_field_data_snapshot(scalar, ndarray<double>(), ndarray<double>()); }
   void push_vector_field_snapshot(const ndarray<double> &vector) { push_field_data_snapshot(ndarray<double>(), vector, ndarray<double>()); }
+  // float32 host snapshots (raw float32 series; the reference's streams widen them on the host): they travel as float32 and are
+  // widened on the device.  Several devices: widened here, then pushed like any host snapshot.
+  void push_field_data_snapshot(const ndarray<float> &scalar, const ndarray<float> &vector) {
+    need();
+    size_t nvert = 1;
+    for (int i = 0; i < nd_; i++) nvert *= (size_t)array_domain_.size(i);
+    if (!scalar.empty() && scalar.nelem() != nvert) throw std::runtime_error("ftk_b200: scalar snapshot has the wrong number of elements");
+    if (!vector.empty() && vector.nelem() != nvert * nd_) throw std::runtime_error("ftk_b200: vector snapshot has the wrong number of elements");
+    if (scalar.on_device() || vector.on_device()) throw std::runtime_error("ftk_b200: float32 snapshots are host arrays");
+    if (group_) {
+      std::vector<double> s(scalar.data(), scalar.data() + scalar.nelem()), v(vector.data(), vector.data() + vector.nelem());
+      gcheck(ftkb_group_push_snapshot(group_, s.empty() ? nullptr : s.data(), v.empty() ? nullptr : v.data(), nullptr));
+    } else
+    check(ftkb_push_snapshot_f32(ctx_, scalar.empty() ? nullptr : scalar.data(), vector.empty() ? nullptr : vector.data()));
+    points_valid_ = false;
+  }
+  void push_scalar_field_snapshot(const ndarray<float> &scalar) { push_field_data_snapshot(scalar, ndarray<float>()); }
+  void push_vector_field_snapshot(const ndarray<float> &vector) { push_field_data_snapshot(ndarray<float>(), vector); }
   // device-side generator (no host data): FTKB_SYN_* kinds of ftkb200.h
   void push_synthetic_snapshot(int kind, const std::vector<double> &params, double t) {
     need();

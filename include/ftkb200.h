@@ -147,6 +147,9 @@ const char *ftkb_last_error(const ftkb_ctx *);   /* ctx may be NULL: last create
  * A pointer may be NULL when its source is NONE or DERIVED. */
 int ftkb_push_snapshot(ftkb_ctx *, const double *scalar, const double *vector, const double *jacobian, int where);
 int ftkb_set_producer_stream(ftkb_ctx *, void *cuda_stream, int enable);
+/* host snapshot that exists as float32 (raw float32 file series): travels as float32, widened to the resident fp64 layer on the
+ * device -- bit-identical to widening on the host first (ndarray.hh read_binary_file + push), half the PCIe bytes */
+int ftkb_push_snapshot_f32(ftkb_ctx *, const float *scalar, const float *vector);
 /* device-side generator for snapshot time `t` (benchmarks; no host data involved) */
 int ftkb_push_synthetic(ftkb_ctx *, int kind, const double *params, int nparams, double t);
 

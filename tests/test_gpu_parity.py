@@ -619,3 +619,17 @@ def test_device_generators(case, ftk, oracle):
     o = oracle.track(device_fields, dims, field=field)           # the oracle on exactly what the device generated
     P.assert_same_result(cuda_result(tr), P.oracle_result(o), tol=TOL, what=f"generator {name}")
     tr.close()
+
+
+@pytest.mark.parametrize("dims,field", [([19, 13], "scalar"), ([17, 11], "vector"), ([11, 9, 7], "scalar")])
+def test_float32_snapshots_are_widened_on_the_device(dims, field, ftk, oracle):
+    """float32 host arrays travel as float32 (ftkb_push_snapshot_f32) and are widened on the device: same result as widening
+    on the host first, sizes that are not a multiple of four elements included"""
+    rng = np.random.default_rng(77)
+    nv = 1 if field == "scalar" else len(dims)
+    snaps32 = [s.astype(np.float32) for s in _rand_series(rng, dims, 4, nv, "smooth")]
+    o = oracle.track([s.astype(np.float64) for s in snaps32], dims, field=field)
+    c = ftk.track(snaps32, dims, field=field)
+    assert c.stats()["h2d_bytes"] == sum(s.nbytes for s in snaps32)
+    P.assert_same_result(cuda_result(c), P.oracle_result(o), tol=TOL, what=f"float32 {field} {dims}")
+    c.close()
