@@ -678,6 +678,8 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the engine has no CPU fallback")
     torch.cuda.set_device(local)
+    # one rank per GPU: run on the CPUs next to it, so the pinned host snapshots of the e2e leg live in that socket's memory
+    numa_cpus = _lib.lib().ftkb_bind_thread_to_device(local)
     env = Env()
     env.rank, env.world, env.local = rank, world, local
     env.dev = torch.device("cuda", local)
@@ -689,6 +691,8 @@ def main():
 
     t_all = time.perf_counter()
     line = run_config(env, args.config, args.steps, args.warmup, args.e2e_steps, sample_clocks=True)
+    if line is not None:
+        line["config"]["host_cpus_bound_per_rank"] = int(numa_cpus)     # CPUs next to the rank's GPU (0: affinity left alone)
     extras = {}
     if args.config == "c2" and not args.only_main:
         # the configurations north_star quotes its scaling targets on, at the same N, in the same driver-run line

@@ -80,7 +80,7 @@ EXPORTS = [
     "ftkb_online_size", "ftkb_online_get", "ftkb_set_coords", "ftkb_set_producer_stream", "ftkb_get_layer",
     "ftkb_group_create", "ftkb_group_destroy", "ftkb_group_last_error", "ftkb_group_push_snapshot", "ftkb_group_push_synthetic",
     "ftkb_group_advance_timestep", "ftkb_group_update_timestep", "ftkb_group_finalize", "ftkb_group_get_stats",
-    "ftkb_host_alloc", "ftkb_host_free", "ftkb_push_snapshot_f32",
+    "ftkb_host_alloc", "ftkb_host_free", "ftkb_push_snapshot_f32", "ftkb_bind_thread_to_device",
 ]
 
 _lib = None
@@ -160,6 +160,7 @@ def lib():
     L.ftkb_host_alloc.argtypes = [C.c_uint64, C.POINTER(vp)]
     L.ftkb_host_free.argtypes = [vp]
     L.ftkb_push_snapshot_f32.argtypes = [vp, vp, vp]
+    L.ftkb_bind_thread_to_device.argtypes = [C.c_int]
     L.ftkb_host_free.restype = None
     L.ftkb_get_trajectory_complete.argtypes = [vp, vp]
     L.ftkb_online_create.argtypes = [C.c_int, vp, vp, C.POINTER(vp)]

@@ -294,16 +294,16 @@ struct Feed {
     if (th.joinable()) th.join();
     for (double *b : buf) { if (pinned) ftkb_host_free(b); else std::free(b); }
   }
-  void start(long T, size_t count, std::function<void(long, double *)> fill) {
+  void start(long T, size_t bytes, std::function<void(long, double *)> fill) {
     total = T;
     pinned = true;
     for (int i = 0; i < NB; i++) {
       void *p = nullptr;
-      if (ftkb_host_alloc(count * sizeof(double), &p) != FTKB_OK) { pinned = false; break; }
+      if (ftkb_host_alloc(bytes, &p) != FTKB_OK) { pinned = false; break; }
       buf[i] = static_cast<double *>(p);
     }
     if (!pinned)      // no device / no pinned memory: plain buffers (the tracker will fail loudly later if there is no device)
-      for (int i = 0; i < NB; i++) { if (buf[i]) ftkb_host_free(buf[i]); buf[i] = static_cast<double *>(std::malloc(count * sizeof(double))); }
+      for (int i = 0; i < NB; i++) { if (buf[i]) ftkb_host_free(buf[i]); buf[i] = static_cast<double *>(std::malloc(bytes)); }
     th = std::thread([this, fill] {
       for (long k = 0; k < total; k++) {
         {
@@ -403,8 +403,9 @@ int main(int argc, char **argv) {
     Feed feed;
     // raw float32 series on one device: the bytes go to the device as they are (half the PCIe traffic) and are widened there
     const bool raw_f32 = syn < 0 && o.input_format == "float32" && o.devices.size() <= 1;
+    double t_wait = 0, t_push = 0, t_step = 0;
     if (!(syn >= 0 && o.device_generators))
-      feed.start(T, nvert * nv, [&](long k, double *dst) {
+      feed.start(T, nvert * nv * (raw_f32 ? sizeof(float) : sizeof(double)), [&](long k, double *dst) {
         if (syn == FTKB_SYN_WOVEN) gen_woven(dims[0], dims[1], T == 1 ? 0.0 : double(k) / (T - 1), dst);        // stream.hh:1468-1480
         else if (syn == FTKB_SYN_MERGER) gen_merger(dims[0], dims[1], double(k) * 0.1, dst);                   // stream.hh:1540
         else if (syn == FTKB_SYN_DOUBLE_GYRE) gen_double_gyre(dims[0], dims[1], k * o.time_scale, dst);        // stream.hh:1542-1555
@@ -412,6 +413,7 @@ int main(int argc, char **argv) {
         else if (syn == FTKB_SYN_MOVING_EXTREMUM) gen_moving_extremum(nd, dims, o.x0.data(), o.dir.data(), double(k), dst);
         else read_raw(o, k, nvert * nv, o.input_format == "float32", dst, raw_f32);
       });
+    const double t_feed_ready = now();              // page-locked buffers allocated, reader thread running
     for (long k = 0; k < T; k++) {
       if (o.verbose) std::fprintf(stderr, "current_timestep=%ld\n", k);
       if (syn >= 0 && o.device_generators) {
@@ -423,7 +425,10 @@ int main(int argc, char **argv) {
         else { p = o.x0; p.insert(p.end(), o.dir.begin(), o.dir.end()); }
         tr->push_synthetic_snapshot(syn, p, t);
       } else {
+        const double t0 = now();
         double *buf = feed.get(k);                   // filled by the reader thread while the previous snapshot was pushed and swept
+        const double t1 = now();
+        t_wait += t1 - t0;
         if (raw_f32) {
           const ndarray<float> a = ndarray<float>::wrap(reinterpret_cast<const float *>(buf), shape);
           if (nv == 1) tr->push_scalar_field_snapshot(a); else tr->push_vector_field_snapshot(a);
@@ -432,11 +437,15 @@ int main(int argc, char **argv) {
           if (nv == 1) tr->push_scalar_field_snapshot(a); else tr->push_vector_field_snapshot(a);
         }
         feed.release(k);                             // (the push copies before it returns)
+        t_push += now() - t1;
       }
+      const double t2 = now();
       if (k != 0) tr->advance_timestep();          // json_interface.hh:699-706
       if (k == T - 1) tr->update_timestep();
+      t_step += now() - t2;
     }
     const double t_compute = now();
+    const double t_feed_alloc = t_feed_ready - t_init;
     if (o.output_type == "traced" || o.output_type == "sliced") {
       tr->finalize();
       if (!o.post_process.empty()) tr->post_process(o.post_process);     // feature_curve_set_post_processor_t(ops).filter(trajs)
@@ -465,6 +474,7 @@ int main(int argc, char **argv) {
     if (o.timing) {   // same line as json_interface.hh:718-723, plus the device-side split
       const ftkb_stats st = tr->stats();
       std::fprintf(stderr, "t_init=%f, t_compute=%f, t_finalize=%f\n", t_init - t_start, t_compute - t_init, t_final - t_compute);
+      std::fprintf(stderr, "t_input_buffers=%f, t_wait_input=%f, t_push=%f, t_step=%f (inside t_compute; %ld snapshots)\n", t_feed_alloc, t_wait, t_push, t_step, T);
       std::fprintf(stderr, "simplices_tested=%llu, punctured=%llu, kernel_launches=%llu, ms_scan=%f, ms_test=%f, ms_derive=%f, h2d_bytes=%llu\n",
                    (unsigned long long)st.simplices_tested, (unsigned long long)st.points, (unsigned long long)st.kernel_launches, st.ms_scan, st.ms_test, st.ms_derive,
                    (unsigned long long)st.h2d_bytes);

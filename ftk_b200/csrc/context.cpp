@@ -1438,6 +1438,24 @@ static void fill_trace_params(const ftkb_ctx *c, TraceParams &tp) {
   tp.nz = tp.ub[2] - tp.lb[2] + 1;
 }
 
+// FTKB_DEBUG_TIMING=1: wall-clock laps of the finalize phases on stderr
+struct Laps {
+  bool on;
+  const char *what;
+  std::chrono::steady_clock::time_point t;
+  std::string line;
+  Laps(bool enabled, const char *w) : on(enabled), what(w), t(std::chrono::steady_clock::now()) {}
+  void lap(const char *name) {
+    if (!on) return;
+    const auto now = std::chrono::steady_clock::now();
+    char buf[96];
+    std::snprintf(buf, sizeof(buf), " %s=%.2f", name, std::chrono::duration<double, std::milli>(now - t).count());
+    line += buf;
+    t = now;
+  }
+  ~Laps() { if (on) std::fprintf(stderr, "[ftkb timing] %s (ms):%s\n", what, line.c_str()); }
+};
+
 // sort the punctured simplices by element order and drop duplicates (std::map semantics of the
 // reference's discrete_critical_points, critical_point_tracker_regular.hh:13-38)
 static int ensure_sorted(ftkb_ctx *c) {
@@ -1454,6 +1472,7 @@ static int ensure_sorted(ftkb_ctx *c) {
   TraceParams tp{};
   fill_trace_params(c, tp);
   const auto tw0 = std::chrono::steady_clock::now();
+  Laps laps(c->debug_timing, "sort");
   unsigned long long *k0 = nullptr, *k1 = nullptr;
   uint32_t *i0 = nullptr, *i1 = nullptr;
   void *temp = nullptr;
@@ -1470,14 +1489,18 @@ static int ensure_sorted(ftkb_ctx *c) {
   CKC(cudaMemcpyAsync(c->h_scalars + ftkb_ctx::SLOT_UQ, c->d_scalars + ftkb_ctx::SLOT_UQ, 8, cudaMemcpyDeviceToHost, c->stream));
   CKC(cudaStreamSynchronize(c->stream));
   const uint64_t nu = c->h_scalars[ftkb_ctx::SLOT_UQ];
+  laps.lap("sort+unique");
   CKC(cudaMalloc(&c->d_pts_sorted, sizeof(ftkb_point) * nu));
   CKC(cudaMalloc(&c->d_keys_sorted, 8 * nu));
   launch_gather_points(c->d_pts, i0, nu, c->d_pts_sorted, c->stream);
   CKC(cudaMemcpyAsync(c->d_keys_sorted, k0, 8 * nu, cudaMemcpyDeviceToDevice, c->stream));      // unique sorted keys
   CKC(cudaEventRecord(c->ev[1], c->stream));
+  laps.lap("malloc+gather");
   c->pts_sorted.resize(nu);
+  laps.lap("host_resize");
   CKC(cudaMemcpyAsync(c->pts_sorted.data(), c->d_pts_sorted, sizeof(ftkb_point) * nu, cudaMemcpyDeviceToHost, c->stream));
   CKC(cudaStreamSynchronize(c->stream));
+  laps.lap("d2h_points");
   CKC(cudaGetLastError());
   float ms = 0;
   CKC(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]));
@@ -1538,6 +1561,7 @@ extern "C" int ftkb_finalize(ftkb_ctx *c) {
   rc = ensure_sorted(c);
   if (rc) return rc;
   const uint64_t n = c->nsorted;
+  Laps laps(c->debug_timing, "trace");
   c->labels.assign(n, 0);
   c->deg.assign(n, 0);
   c->traj_off.assign(1, 0);
@@ -1582,12 +1606,14 @@ extern "C" int ftkb_finalize(ftkb_ctx *c) {
   { int rs = scratch(c, 5, 4 * 8 * n, (void **)&d_nb); if (!rs) rs = scratch(c, 6, 4 * n, (void **)&d_pa); if (!rs) rs = scratch(c, 7, 4 * n, (void **)&d_po);
     if (!rs) rs = scratch(c, 8, 4 * n, (void **)&d_deg); if (rs) return rs; }
   tp.nb = d_nb; tp.deg = d_deg; tp.parent_all = d_pa; tp.parent_ord = d_po;
+  laps.lap("host_assign+scratch");
   CKC(cudaEventRecord(c->ev[0], c->stream));
   launch_neighbors(tp, c->stream);
   launch_union_find(tp, c->stream);
   CKC(cudaEventRecord(c->ev[1], c->stream));
   c->stats.kernel_launches += 3;
   std::vector<uint32_t> nb(8 * n), pa(n), po(n);
+  laps.lap("host_vectors");
   CKC(cudaMemcpyAsync(nb.data(), d_nb, 4 * 8 * n, cudaMemcpyDeviceToHost, c->stream));
   CKC(cudaMemcpyAsync(pa.data(), d_pa, 4 * n, cudaMemcpyDeviceToHost, c->stream));
   CKC(cudaMemcpyAsync(po.data(), d_po, 4 * n, cudaMemcpyDeviceToHost, c->stream));
@@ -1598,6 +1624,7 @@ extern "C" int ftkb_finalize(ftkb_ctx *c) {
   CKC(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]));
   c->stats.ms_finalize_device += ms;
   c->stats.d2h_bytes += 4 * 11 * n;
+  laps.lap("kernels+d2h");
 #undef CKC
 
   // host: order every trajectory with the reference's deterministic walk (cc2curves.hh:46-108)
@@ -1619,17 +1646,19 @@ extern "C" int ftkb_finalize(ftkb_ctx *c) {
   for (uint64_t seed = 0; seed < n; seed++)
     if (ordinary((uint32_t)seed) && po[seed] == seed) seeds.push_back((uint32_t)seed);   // the smallest member starts the walk
   const size_t S = seeds.size();
+  laps.lap("seeds");
   struct Piece { uint32_t thread; uint64_t off, len; uint8_t loop; };
   std::vector<Piece> pieces(S);
   const unsigned hw = std::thread::hardware_concurrency();
   const size_t nthr = std::max<size_t>(1, std::min<size_t>({(size_t)16, (size_t)(hw ? hw : 1), (size_t)(n / 65536 + 1)}));
   std::vector<std::vector<uint32_t>> bufs(nthr);
   std::atomic<size_t> next{0};
+  const size_t batch = std::max<size_t>(1, std::min<size_t>(64, S / (nthr * 8)));      // few long trajectories: one seed at a time
   auto work = [&](const uint32_t tid) {
     std::vector<uint32_t> &out = bufs[tid];
     std::vector<uint32_t> fwd, bwd;
     for (;;) {
-      const size_t s0 = next.fetch_add(64), s1 = std::min(S, s0 + 64);
+      const size_t s0 = next.fetch_add(batch), s1 = std::min(S, s0 + batch);
       if (s0 >= S) break;
       for (size_t si = s0; si < s1; si++) {
         const uint32_t seed = seeds[si];
@@ -1671,6 +1700,7 @@ extern "C" int ftkb_finalize(ftkb_ctx *c) {
     for (uint32_t t = 0; t < nthr; t++) pool.emplace_back(work, t);
     for (auto &th : pool) th.join();
   }
+  laps.lap("walk");
   c->traj_idx.reserve(n);
   for (size_t si = 0; si < S; si++) {
     const Piece &pc = pieces[si];
@@ -1679,6 +1709,7 @@ extern "C" int ftkb_finalize(ftkb_ctx *c) {
     c->traj_loop.push_back(pc.loop);
     c->traj_off.push_back(c->traj_idx.size());
   }
+  laps.lap("layout");
   c->stats.ms_finalize_host += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
   c->stats.ms_trace_wall += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tw0).count();
   c->traced = true;
@@ -1846,10 +1877,55 @@ extern "C" int ftkb_get_layer(ftkb_ctx *c, int index, double *scalar, double *ve
 
 // page-locked host memory for callers that feed snapshots from files or generators: copies from it run at full PCIe speed and
 // do not go through the driver's staging buffers (the CLI's double-buffered reader, stream.hh:1607-1699 in the reference)
+// CPUs on the socket the device's PCIe root hangs off (sysfs local_cpulist), restricted to what the thread may run on
+static bool device_local_cpus(int device, cpu_set_t *set) {
+  char bus[32] = {0};
+  if (cudaDeviceGetPCIBusId(bus, sizeof(bus) - 1, device) != cudaSuccess) { cudaGetLastError(); return false; }
+  for (char *q = bus; *q; q++) *q = (char)std::tolower((unsigned char)*q);
+  FILE *f = std::fopen((std::string("/sys/bus/pci/devices/") + bus + "/local_cpulist").c_str(), "r");
+  if (!f) return false;
+  char line[4096];
+  const bool got = std::fgets(line, sizeof(line), f) != nullptr;
+  std::fclose(f);
+  cpu_set_t allowed;
+  if (!got || sched_getaffinity(0, sizeof(allowed), &allowed) != 0) return false;
+  CPU_ZERO(set);
+  int n = 0;
+  for (const char *q = line; *q && *q != '\n';) {          // "0-31,64-95"
+    char *e = nullptr;
+    long a = std::strtol(q, &e, 10), b = a;
+    if (e == q) break;
+    if (*e == '-') { q = e + 1; b = std::strtol(q, &e, 10); }
+    for (long i = a; i <= b && i < CPU_SETSIZE; i++)
+      if (CPU_ISSET(i, &allowed)) { CPU_SET(i, set); n++; }
+    if (*e != ',') break;
+    q = e + 1;
+  }
+  return n > 0;
+}
+
+// The calling thread (and the threads it creates afterwards) run on the CPUs next to `device` from here on: page-locked
+// buffers it allocates and the driver's staging copies then live in that socket's memory, so host<->device copies of several
+// devices do not all cross the inter-socket link or drain one socket's DRAM (e2e at 4 and 8 ranks).
+extern "C" int ftkb_bind_thread_to_device(int device) {
+  cpu_set_t set;
+  if (!device_local_cpus(device, &set)) return 0;
+  if (sched_setaffinity(0, sizeof(set), &set) != 0) return 0;
+  return CPU_COUNT(&set);
+}
+
 extern "C" int ftkb_host_alloc(uint64_t bytes, void **out) {
   if (!out || !bytes) return FTKB_ERR_INVALID;
   *out = nullptr;
-  if (cudaHostAlloc(out, bytes, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return FTKB_ERR_NOMEM; }
+  // pages are placed where the allocating thread runs: next to the current device for the duration of the call
+  cpu_set_t before, local;
+  int device = 0;
+  bool moved = false;
+  if (cudaGetDevice(&device) == cudaSuccess && sched_getaffinity(0, sizeof(before), &before) == 0 && device_local_cpus(device, &local))
+    moved = sched_setaffinity(0, sizeof(local), &local) == 0;
+  const cudaError_t e = cudaHostAlloc(out, bytes, cudaHostAllocPortable);
+  if (moved) sched_setaffinity(0, sizeof(before), &before);
+  if (e != cudaSuccess) { cudaGetLastError(); return FTKB_ERR_NOMEM; }
   return FTKB_OK;
 }
 

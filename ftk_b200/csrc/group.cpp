@@ -43,8 +43,9 @@ struct Worker {
   std::condition_variable cv, cv_space;
   std::deque<std::function<void()>> q;
   bool stop = false;
-  void start() {
-    th = std::thread([this] {
+  void start(int device) {
+    th = std::thread([this, device] {
+      ftkb_bind_thread_to_device(device);      // host-side staging of this device's snapshots stays in the socket next to it
       for (;;) {
         std::function<void()> f;
         {
@@ -236,7 +237,7 @@ extern "C" int ftkb_group_create(const ftkb_config *cfg, const int32_t *device_i
   }
   for (int i = 0; i < n_devices; i++) {
     g->workers.emplace_back(new Worker());
-    g->workers.back()->start();
+    g->workers.back()->start(device_ids[i]);
   }
   *out = g;
   return FTKB_OK;

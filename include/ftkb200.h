@@ -318,7 +318,10 @@ int ftkb_get_layer(ftkb_ctx *, int index, double *scalar, double *vector);
 
 /* page-locked (pinned, portable) host memory for snapshot buffers: ftkb_push_snapshot(FTKB_MEM_HOST) then copies at full
  * PCIe speed.  The CLI reads file series through two such buffers (one being read while the other is pushed and swept). */
-int ftkb_host_alloc(uint64_t bytes, void **out);
+int ftkb_host_alloc(uint64_t bytes, void **out);   /* placed in the memory of the socket next to the current device */
+/* run the calling thread (and threads it creates later) on the CPUs next to `device` (sysfs local_cpulist): host buffers it
+ * allocates afterwards are local to that device's PCIe root.  Returns the number of CPUs bound to, 0 if nothing was changed. */
+int ftkb_bind_thread_to_device(int device);
 void ftkb_host_free(void *p);
 
 int ftkb_get_stats(ftkb_ctx *, ftkb_stats *out);

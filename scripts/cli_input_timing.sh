@@ -17,7 +17,7 @@ for fmt in float64 float32; do
   ext=f64; [ $fmt == float32 ] && ext=f32
   for rep in 1 2; do    # the second pass reads from the page cache
     ./ftk_b200/bin/ftkb200 -f cp --input "$D/me_%03d.$ext" --input-format $fmt --width 8192 --height 8192 --timesteps 12 --timing \
-        --output-type discrete -o $D/out_$ext.txt 2>&1 | tail -2 | sed "s/^/$fmt pass $rep: /" | tee -a $OUT/${TAG:-r02i}_cli_input_timing.log
+        --output-type discrete -o $D/out_$ext.txt 2>&1 | tail -3 | sed "s/^/$fmt pass $rep: /" | tee -a $OUT/${TAG:-r02i}_cli_input_timing.log
   done
 done
 wc -l $D/out_f64.txt $D/out_f32.txt | tee -a $OUT/${TAG:-r02i}_cli_input_timing.log
