@@ -689,9 +689,11 @@ static void fused2d_decomposition(const ftkb_ctx *c, SweepParams &p) {
   nsy = std::max<int64_t>(1, std::min<int64_t>(nsy, (p.H + 31) / 32));
   p.rows = (int)((p.H + nsy - 1) / nsy);
   if (p.bulk == 2 && c->cells2d) {
-    // about six waves of CTAs (costs differ: border strips, cold paths), at least two cell blocks per chunk
+    // just under eight waves of CTAs (costs differ: border strips, cold paths; the last, partly filled wave runs at low occupancy:
+    // measured on C2, rows 36 / 45 / 54 / 63 / 90 = 9.8 / 7.8 / 6.5 / 5.6 / 3.9 waves: 0.153 / 0.145 / 0.148 / 0.150 / 0.163 ms),
+    // at least two cell blocks per chunk
     const int R = SCAN2D_CELL_ROWS;
-    const int64_t want = std::max<int64_t>(1, (6 * (int64_t)c->sm_count * 3) / p.nsx);
+    const int64_t want = std::max<int64_t>(1, (8 * (int64_t)c->sm_count * 3) / p.nsx);
     p.rows = std::max(2 * R, (int)((p.H + want - 1) / want));
     p.rows = (p.rows + R - 1) / R * R;      // chunks start on cell-block boundaries
     if (const char *e = std::getenv("FTKB_C2_ROWS")) p.rows = std::max(R, std::atoi(e) / R * R);   // A/B measurements
@@ -732,6 +734,7 @@ static void vcells_decomposition(const ftkb_ctx *c, SweepParams &p) {
   const int64_t want = std::max<int64_t>(1, (6 * (int64_t)c->sm_count * 16) / p.nsx);
   p.rows = std::max(2 * R, (int)((p.H + want - 1) / want));
   p.rows = (p.rows + R - 1) / R * R;
+  if (const char *e = std::getenv("FTKB_V2_ROWS")) p.rows = std::max(R, std::atoi(e) / R * R);   // A/B measurements
   p.nsy = (p.H + p.rows - 1) / p.rows;
   p.nsz = 1;
 }
@@ -1575,10 +1578,11 @@ extern "C" int ftkb_finalize(ftkb_ctx *c) {
     const auto t0 = std::chrono::steady_clock::now();
     std::vector<uint64_t> keys(n);
     for (uint64_t i = 0; i < n; i++) c->online->key_of(c->pts_sorted[i], keys[i]);
+    const std::vector<ftkb_point> &streamed = c->online->points();
     for (const ftkb::OnlineCurve &cv : c->online->curves()) {
-      for (const ftkb_point &p : cv.pts) {
+      for (const uint32_t g : cv.idx) {
         uint64_t key = 0;
-        c->online->key_of(p, key);
+        c->online->key_of(streamed[g], key);
         const auto it = std::lower_bound(keys.begin(), keys.end(), key);
         if (it == keys.end() || *it != key) return fail(c, FTKB_ERR_INVALID, "finalize: a streamed point is missing from the sorted points");
         c->traj_idx.push_back((uint64_t)(it - keys.begin()));

@@ -17,6 +17,7 @@
 #include <algorithm>
 #include <cstring>
 #include <new>
+#include <stdexcept>
 
 #include "kernels.h"
 
@@ -50,7 +51,12 @@ OnlineTracer::OnlineTracer(int nd, const int32_t lb[3], const int32_t ub[3]) : n
       for (int j = 0; j < 4; j++) if (a.off[j] != b.off[j]) return a.off[j] < b.off[j];
       return a.type < b.type;
     });
-    for (int q = 0; q < cnt; q++) cand_[type][q].cell_delta = ((int64_t)cand_[type][q].off[0] * ny_ + cand_[type][q].off[1]) * nz_ + cand_[type][q].off[2];
+    for (int q = 0; q < cnt; q++) {
+      Candidate &c = cand_[type][q];
+      c.cell_delta = ((int64_t)c.off[0] * ny_ + c.off[1]) * nz_ + c.off[2];
+      // key = ((cell << TIME) | t) << TYPE | type is linear in (cell, t, type) as long as no field leaves its range
+      c.key_delta = c.cell_delta * ((int64_t)1 << (KEY_TIME_BITS + KEY_TYPE_BITS)) + (int64_t)c.off[3] * ((int64_t)1 << KEY_TYPE_BITS) + ((int64_t)c.type - type);
+    }
     ncand_[type] = cnt;
   }
 }
@@ -73,6 +79,13 @@ int OnlineTracer::neighbor_keys(const ftkb_point &p, uint64_t out[9]) const {
   if (type < 0 || type >= ntypes_) return 0;
   const int x0 = p.corner[0], y0 = p.corner[1], z0 = nd_ == 3 ? p.corner[2] : 0, t0 = p.corner[3];
   const int64_t cell = ((int64_t)(x0 - lb_[0]) * ny_ + (y0 - lb_[1])) * nz_ + (z0 - lb_[2]);
+  if (x0 > lb_[0] && x0 < ub_[0] && y0 > lb_[1] && y0 < ub_[1] && (nd_ == 2 || (z0 > lb_[2] && z0 < ub_[2])) && t0 > 0 && t0 < (1 << KEY_TIME_BITS) - 1) {
+    // away from the domain's faces every candidate exists (offsets are -1, 0, 1): its key is the element's plus a constant
+    const uint64_t self = ((((uint64_t)cell << KEY_TIME_BITS) | (uint64_t)t0) << KEY_TYPE_BITS) | (uint64_t)type;
+    const int n = ncand_[type];
+    for (int q = 0; q < n; q++) out[q] = self + (uint64_t)cand_[type][q].key_delta;
+    return n;
+  }
   int cnt = 0;
   for (int q = 0; q < ncand_[type]; q++) {
     const Candidate &c = cand_[type][q];
@@ -85,7 +98,7 @@ int OnlineTracer::neighbor_keys(const ftkb_point &p, uint64_t out[9]) const {
 
 uint64_t OnlineTracer::npoints() const {
   uint64_t n = 0;
-  for (const OnlineCurve &c : curves_) n += c.pts.size();
+  for (const OnlineCurve &c : curves_) n += c.idx.size();
   return n;
 }
 
@@ -165,9 +178,9 @@ void OnlineTracer::grow(const ftkb_point *pts_in, uint64_t n_in) {
   struct Entry { uint64_t key; uint32_t val, pad; };
   std::vector<Entry> table(cap, Entry{~0ull, 0, 0});   // no element key is all ones (the type field is below 60)
   std::vector<uint64_t> keys;
-  std::vector<ftkb_point> pts;
   keys.reserve(n_in);
-  pts.reserve(n_in);
+  const size_t base = all_.size();
+  all_.reserve(base + n_in);
   auto home_of = [&](uint64_t key) { return (size_t)(((key >> KEY_TYPE_BITS) * 0x9E3779B97F4A7C15ull) >> shift); };
   auto slot_from = [&](size_t h, uint64_t key) {
     while (table[h].key != ~0ull && table[h].key != key) h = (h + 1) & (cap - 1);
@@ -177,80 +190,132 @@ void OnlineTracer::grow(const ftkb_point *pts_in, uint64_t n_in) {
     uint64_t key;
     if (!key_of(pts_in[i], key)) continue;
     const size_t h = slot_from(home_of(key), key);
-    if (table[h].key == key) { pts[table[h].val] = pts_in[i]; continue; }
+    if (table[h].key == key) { all_[base + table[h].val] = pts_in[i]; continue; }
     table[h].key = key;
     table[h].val = (uint32_t)keys.size();
     keys.push_back(key);
-    pts.push_back(pts_in[i]);
+    all_.push_back(pts_in[i]);
   }
-  const uint32_t n = (uint32_t)keys.size();
-  std::vector<uint8_t> alive(n, 1);
-  // the punctured neighbours of an element, ascending: indices of those present in this step's batch
-  auto present_neighbors = [&](const ftkb_point &cur, int64_t out[9]) {
-    uint64_t nk[9];
-    size_t home[9];
-    const int cnt = neighbor_keys(cur, nk);
-    for (int q = 0; q < cnt; q++) { home[q] = home_of(nk[q]); __builtin_prefetch(&table[home[q]]); }
-    for (int q = 0; q < cnt; q++) {
-      const size_t h = slot_from(home[q], nk[q]);
-      out[q] = table[h].key == nk[q] ? (int64_t)table[h].val : -1;
+  // the punctured neighbours of an element, ascending (the candidate order), as batch indices; looked up when needed
+  struct Source {
+    OnlineTracer *self; size_t base; const std::vector<Entry> *table; size_t cap; int shift;
+    size_t home_of(uint64_t key) const { return (size_t)(((key >> KEY_TYPE_BITS) * 0x9E3779B97F4A7C15ull) >> shift); }
+    size_t slot_from(size_t h, uint64_t key) const {
+      const Entry *t = table->data();
+      while (t[h].key != ~0ull && t[h].key != key) h = (h + 1) & (cap - 1);
+      return h;
     }
-    return cnt;
+    int64_t find(uint64_t key) const {
+      const size_t h = slot_from(home_of(key), key);
+      return (*table)[h].key == key ? (int64_t)(*table)[h].val : -1;
+    }
+    int list(uint32_t i, uint32_t out[9]) const {
+      uint64_t nk[9];
+      size_t home[9];
+      const int m = self->neighbor_keys(self->all_[base + i], nk);
+      for (int q = 0; q < m; q++) { home[q] = home_of(nk[q]); __builtin_prefetch(table->data() + home[q]); }
+      int cnt = 0;
+      for (int q = 0; q < m; q++) {
+        const size_t h = slot_from(home[q], nk[q]);
+        if ((*table)[h].key == nk[q]) out[cnt++] = (*table)[h].val;
+      }
+      return cnt;
+    }
+    // first live entry of the list: probing stops at the first hit
+    int64_t first_alive(uint32_t i, const uint8_t *alive) const {
+      uint64_t nk[9];
+      size_t home[9];
+      const int m = self->neighbor_keys(self->all_[base + i], nk);
+      for (int q = 0; q < m; q++) { home[q] = home_of(nk[q]); __builtin_prefetch(table->data() + home[q]); }
+      for (int q = 0; q < m; q++) {
+        const size_t h = slot_from(home[q], nk[q]);
+        if ((*table)[h].key == nk[q] && alive[(*table)[h].val]) return (int64_t)(*table)[h].val;
+      }
+      return -1;
+    }
   };
-  // smallest unclaimed punctured neighbour of an element (critical_point_tracker.hh:555-572): probe in ascending order,
-  // stop at the first hit
-  auto claim_next = [&](const ftkb_point &cur) -> int64_t {
+  walk((uint32_t)keys.size(), keys.data(), false, Source{this, base, &table, cap, shift});
+}
+
+void OnlineTracer::grow_sorted(const ftkb_point *pts, const uint64_t *keys, uint32_t n, const uint32_t *nb, const uint8_t *cnt) {
+  all_.insert(all_.end(), pts, pts + n);
+  struct Source {
+    const uint64_t *keys; uint32_t n; const uint32_t *nb; const uint8_t *cnt;
+    int64_t find(uint64_t key) const {
+      const uint64_t *it = std::lower_bound(keys, keys + n, key);
+      return it != keys + n && *it == key ? (int64_t)(it - keys) : -1;
+    }
+    int list(uint32_t i, uint32_t out[9]) const { std::memcpy(out, nb + 9 * (size_t)i, 4 * cnt[i]); return cnt[i]; }
+    int64_t first_alive(uint32_t i, const uint8_t *alive) const {
+      const uint32_t *l = nb + 9 * (size_t)i;
+      for (int q = 0; q < cnt[i]; q++) if (alive[l[q]]) return (int64_t)l[q];
+      return -1;
+    }
+  };
+  walk(n, keys, true, Source{keys, n, nb, cnt});
+}
+
+// The batch is the last n elements of all_.
+template <class Source>
+void OnlineTracer::walk(uint32_t n, const uint64_t *keys, bool sorted, Source src) {
+  if (all_.size() >= 0xffffffffull) throw std::length_error("more than 2^32 punctured simplices");
+  const uint32_t base = (uint32_t)(all_.size() - n);
+  std::vector<uint8_t> alive(n, 1);
+  // smallest unclaimed punctured neighbour of an element (critical_point_tracker.hh:555-572): the first live entry of its
+  // ascending neighbour list.  An element of this batch has its list ready; a trajectory's end from an earlier step looks
+  // its candidates up by key (only the first claim of an end does).
+  auto claim_next = [&](uint32_t g) -> int64_t {
+    if (g >= base) {
+      const int64_t j = src.first_alive(g - base, alive.data());
+      if (j >= 0) alive[j] = 0;
+      return j;
+    }
+    if (n == 0) return -1;
     uint64_t nk[9];
-    size_t home[9];
-    const int cnt = neighbor_keys(cur, nk);
-    for (int q = 0; q < cnt; q++) { home[q] = home_of(nk[q]); __builtin_prefetch(&table[home[q]]); }
-    for (int q = 0; q < cnt; q++) {
-      const size_t h = slot_from(home[q], nk[q]);
-      if (table[h].key == nk[q] && alive[table[h].val]) { alive[table[h].val] = 0; return (int64_t)table[h].val; }
+    const int m = neighbor_keys(all_[g], nk);
+    for (int q = 0; q < m; q++) {
+      const int64_t j = src.find(nk[q]);
+      if (j >= 0 && alive[j]) { alive[j] = 0; return j; }
     }
     return -1;
   };
 
   // 1. continue existing trajectories, in id order (critical_point_tracker.hh:540-609)
   for (OnlineCurve &c : curves_) {
-    if (c.complete || c.pts.empty()) continue;
+    if (c.complete || c.idx.empty()) continue;
     bool continued = false;
-    for (ftkb_point cur = c.pts.back();;) {
+    for (uint32_t cur = c.idx.back();;) {
       const int64_t j = claim_next(cur);
       if (j < 0) break;
-      c.pts.push_back(pts[j]);
-      cur = pts[j];
+      cur = base + (uint32_t)j;
+      c.idx.push_back(cur);
       continued = true;
     }
-    for (ftkb_point cur = c.pts.front();;) {
+    for (uint32_t cur = c.idx.front();;) {
       const int64_t j = claim_next(cur);
       if (j < 0) break;
-      c.pts.push_front(pts[j]);
-      cur = pts[j];
+      cur = base + (uint32_t)j;
+      c.idx.push_front(cur);
       continued = true;
     }
     if (!continued) c.complete = true;
   }
 
-  // 2. new trajectories from what is left (critical_point_tracker.hh:611-640)
+  // 2. new trajectories from what is left (critical_point_tracker.hh:611-640), in std::set<element> order
   std::vector<uint32_t> rest;
-  {
-    std::vector<std::pair<uint64_t, uint32_t>> left;
-    for (uint32_t i = 0; i < n; i++) if (alive[i]) left.emplace_back(keys[i], i);
-    if (left.empty()) return;
-    std::sort(left.begin(), left.end());                 // std::set<element> order
-    rest.reserve(left.size());
-    for (const auto &kv : left) rest.push_back(kv.second);
-  }
-  std::vector<uint32_t> nb(9 * (size_t)n);
+  for (uint32_t i = 0; i < n; i++) if (alive[i]) rest.push_back(i);
+  if (rest.empty()) return;
+  if (!sorted) std::sort(rest.begin(), rest.end(), [&](uint32_t a, uint32_t b) { return keys[a] < keys[b]; });
+  // neighbour lists restricted to what is left
+  std::vector<uint32_t> lnb(9 * (size_t)n);
   std::vector<uint8_t> nnb(n, 0);
   for (uint32_t i : rest) {
-    int64_t nbr[9];
-    const int cnt = present_neighbors(pts[i], nbr);
-    for (int q = 0; q < cnt; q++)
-      if (nbr[q] >= 0 && alive[nbr[q]]) nb[9 * (size_t)i + nnb[i]++] = (uint32_t)nbr[q];
+    uint32_t l[9];
+    const int m = src.list(i, l);
+    for (int q = 0; q < m; q++)
+      if (alive[l[q]]) lnb[9 * (size_t)i + nnb[i]++] = l[q];
   }
-  auto nb_all = [&](uint32_t i, uint32_t *out) { std::memcpy(out, &nb[9 * (size_t)i], 4 * nnb[i]); return (int)nnb[i]; };
+  auto nb_all = [&](uint32_t i, uint32_t *out) { std::memcpy(out, &lnb[9 * (size_t)i], 4 * nnb[i]); return (int)nnb[i]; };
   std::vector<int32_t> scratch(n, -1);
   const Components components = components_of(rest, scratch, nb_all);
 
@@ -265,14 +330,14 @@ void OnlineTracer::grow(const ftkb_point *pts_in, uint64_t n_in) {
     for (uint32_t k = components.start[g]; k < components.start[g + 1]; k++) comp_of[components.members[k]] = g;
   for (uint32_t i : rest) {
     int d = 0;
-    for (int q = 0; q < nnb[i]; q++) d += nb[9 * (size_t)i + q] != i;
+    for (int q = 0; q < nnb[i]; q++) d += lnb[9 * (size_t)i + q] != i;
     special[i] = d > 2;
     if (!special[i]) ordinary.push_back(i);
   }
   auto nb_ord = [&](uint32_t i, uint32_t *out) {
-    int cnt = 0;
-    for (int q = 0; q < nnb[i]; q++) { const uint32_t j = nb[9 * (size_t)i + q]; if (!special[j]) out[cnt++] = j; }
-    return cnt;
+    int m = 0;
+    for (int q = 0; q < nnb[i]; q++) { const uint32_t j = lnb[9 * (size_t)i + q]; if (!special[j]) out[m++] = j; }
+    return m;
   };
   const Components linear = components_of(ordinary, scratch, nb_ord);
   std::vector<int32_t> member(n, -1);   // index of the linear graph a node belongs to
@@ -292,7 +357,7 @@ void OnlineTracer::grow(const ftkb_point *pts_in, uint64_t n_in) {
     bwd.clear();
     visited[seed] = 1;
     uint32_t sn[9]; int nsn = 0;
-    for (int q = 0; q < nnb[seed]; q++) { const uint32_t j = nb[9 * (size_t)seed + q]; if (j != seed && !special[j]) sn[nsn++] = j; }
+    for (int q = 0; q < nnb[seed]; q++) { const uint32_t j = lnb[9 * (size_t)seed + q]; if (j != seed && !special[j]) sn[nsn++] = j; }
     for (int dir = 0; dir < 2 && nsn > 0; dir++) {
       uint32_t cur = dir == 0 ? sn[0] : sn[nsn - 1];
       while (true) {
@@ -302,7 +367,7 @@ void OnlineTracer::grow(const ftkb_point *pts_in, uint64_t n_in) {
         }
         bool found = false;
         for (int q = 0; q < nnb[cur]; q++) {
-          const uint32_t j = nb[9 * (size_t)cur + q];
+          const uint32_t j = lnb[9 * (size_t)cur + q];
           if (j != cur && !special[j] && member[j] == (int32_t)g && !visited[j]) { found = true; cur = j; break; }
         }
         if (!found) break;
@@ -312,10 +377,10 @@ void OnlineTracer::grow(const ftkb_point *pts_in, uint64_t n_in) {
     OnlineCurve c;
     const uint32_t front = bwd.empty() ? seed : bwd.back(), back = fwd.empty() ? seed : fwd.back();
     if (fwd.size() + bwd.size() > 0)   // is_loop, cc2curves.hh:113-122
-      for (int q = 0; q < nnb[front]; q++) c.loop = c.loop || nb[9 * (size_t)front + q] == back;
-    for (size_t k = bwd.size(); k > 0; k--) c.pts.push_back(pts[bwd[k - 1]]);
-    c.pts.push_back(pts[seed]);
-    for (uint32_t i : fwd) c.pts.push_back(pts[i]);
+      for (int q = 0; q < nnb[front]; q++) c.loop = c.loop || lnb[9 * (size_t)front + q] == back;
+    for (size_t k = bwd.size(); k > 0; k--) c.idx.push_back(base + bwd[k - 1]);
+    c.idx.push_back(base + seed);
+    for (uint32_t i : fwd) c.idx.push_back(base + i);
     curves_.push_back(std::move(c));
   }
 }
@@ -356,8 +421,9 @@ extern "C" int ftkb_online_get(const ftkb_online *o, uint64_t *offsets, ftkb_poi
   if (!o || !offsets) return FTKB_ERR_INVALID;
   uint64_t pos = 0, k = 0;
   offsets[0] = 0;
+  const std::vector<ftkb_point> &all = o->tracer.points();
   for (const ftkb::OnlineCurve &c : o->tracer.curves()) {
-    if (pts) for (const ftkb_point &p : c.pts) pts[pos++] = p; else pos += c.pts.size();
+    if (pts) for (const uint32_t g : c.idx) pts[pos++] = all[g]; else pos += c.idx.size();
     if (loop) loop[k] = c.loop;
     if (complete) complete[k] = c.complete;
     offsets[++k] = pos;
