@@ -76,7 +76,7 @@ EXPORTS = [
     "ftkb_curveset_create", "ftkb_get_curveset", "ftkb_curveset_destroy", "ftkb_curveset_post_process", "ftkb_curveset_size",
     "ftkb_curveset_get", "ftkb_curveset_last_error", "ftkb_curveset_slice",
     "ftkb_ipc_export", "ftkb_ipc_import", "ftkb_ipc_close", "ftkb_export_layer_cells", "ftkb_push_snapshot_remote",
-    "ftkb_set_streaming_trajectories", "ftkb_get_trajectory_complete", "ftkb_online_create", "ftkb_online_destroy", "ftkb_online_grow",
+    "ftkb_set_streaming_trajectories", "ftkb_get_trajectory_complete", "ftkb_online_create", "ftkb_online_destroy", "ftkb_online_grow", "ftkb_online_grow_prepared",
     "ftkb_online_size", "ftkb_online_get", "ftkb_set_coords", "ftkb_set_producer_stream", "ftkb_get_layer",
     "ftkb_group_create", "ftkb_group_destroy", "ftkb_group_last_error", "ftkb_group_push_snapshot", "ftkb_group_push_synthetic",
     "ftkb_group_advance_timestep", "ftkb_group_update_timestep", "ftkb_group_finalize", "ftkb_group_get_stats",
@@ -167,6 +167,7 @@ def lib():
     L.ftkb_online_destroy.argtypes = [vp]
     L.ftkb_online_destroy.restype = None
     L.ftkb_online_grow.argtypes = [vp, vp, C.c_uint64]
+    L.ftkb_online_grow_prepared.argtypes = [vp, vp, C.c_uint64]
     L.ftkb_online_size.argtypes = [vp, u64p, u64p]
     L.ftkb_online_get.argtypes = [vp, vp, vp, vp, vp]
     L.ftkb_curveset_last_error.restype = C.c_char_p

@@ -128,7 +128,9 @@ struct ftkb_ctx {
 
   // finalize scratch (sort keys / indices, cub temp storage, neighbour lists, union-find parents): kept between calls, grown on demand
   struct Scratch { void *p = nullptr; size_t cap = 0; };
-  Scratch fz[9];
+  Scratch fz[12];          // 10, 11: the streaming grow step's neighbour lists and counts
+  void *grow_stage = nullptr;   // page-locked staging of a grow step's batch
+  size_t grow_stage_cap = 0;
 
   // sorted / traced results (host)
   bool sorted = false, traced = false;
@@ -219,6 +221,7 @@ static void release_layer(ftkb_ctx *c, Layer &l) {
 }
 
 static int wait_grow(ftkb_ctx *c);
+static void fill_trace_params(const ftkb_ctx *c, TraceParams &tp);
 static int drain(ftkb_ctx *c);
 
 extern "C" void ftkb_destroy(ftkb_ctx *c) {
@@ -244,6 +247,7 @@ extern "C" void ftkb_destroy(ftkb_ctx *c) {
   for (auto *p : c->exportedCells) cudaFree(p);
   cudaFree(c->d_scalars);
   if (c->h_scalars) cudaFreeHost(c->h_scalars);
+  if (c->grow_stage) cudaFreeHost(c->grow_stage);
   if (c->h_ring) cudaFreeHost(c->h_ring);
   for (auto &es : c->dev) for (auto &e : es) if (e) cudaEventDestroy(e);
   if (c->ev_input) cudaEventDestroy(c->ev_input);
@@ -895,27 +899,77 @@ static int wait_grow(ftkb_ctx *c) {
 static int grow_trajectories(ftkb_ctx *c) {
   const uint64_t n = c->npts - c->grown;
   if (n >= 0xffffffffull) return fail(c, FTKB_ERR_OVERFLOW, "more than 2^32 punctured simplices in one step");
-  std::vector<ftkb_point> batch(n);
-  if (n) {
-    CK(cudaMemcpyAsync(batch.data(), c->d_pts + c->grown, sizeof(ftkb_point) * n, cudaMemcpyDeviceToHost, c->stream));
+  { const int rc = wait_grow(c); if (rc) return rc; }                  // grow steps run in order; the staging buffer is free again
+  // The device prepares the batch (FTKB_STREAM_PREP=host: the host hashes the raw batch instead): element keys -> radix sort ->
+  // unique -> for every element the batch indices of its punctured neighbours, itself included (the same binary search as the
+  // offline trace).  The host walk then only chases index lists (OnlineTracer::grow_sorted).
+  static const bool host_prep = [] { const char *e = std::getenv("FTKB_STREAM_PREP"); return e && std::string(e) == "host"; }();
+  // staging: the raw records (host preparation), or {keys, nine neighbour indices, count} per element -- the records themselves stay on
+  // the device: finalize maps the trajectories' keys onto the sorted points
+  const size_t per = host_prep ? sizeof(ftkb_point) : 8 + 4 * 9 + 1;
+  if (n && c->grow_stage_cap < per * n) {
+    if (c->grow_stage) cudaFreeHost(c->grow_stage);
+    c->grow_stage = nullptr; c->grow_stage_cap = 0;
+    const size_t want = per * (n + n / 2 + 1024);
+    if (cudaMallocHost(&c->grow_stage, want) != cudaSuccess) { cudaGetLastError(); return fail(c, FTKB_ERR_NOMEM, "streaming grow step: out of page-locked memory"); }
+    c->grow_stage_cap = want;
+  }
+  ftkb_point *h_pts = (ftkb_point *)c->grow_stage;
+  uint64_t *h_keys = (uint64_t *)c->grow_stage;
+  uint32_t *h_nb = (uint32_t *)(h_keys + n);
+  uint8_t *h_cnt = (uint8_t *)(h_nb + 9 * n);
+  uint64_t nu = n;
+  if (n && host_prep) {
+    CK(cudaMemcpyAsync(h_pts, c->d_pts + c->grown, sizeof(ftkb_point) * n, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     c->stats.d2h_bytes += sizeof(ftkb_point) * n;
+  } else if (n) {
+    TraceParams tp{};
+    fill_trace_params(c, tp);
+    unsigned long long *k0 = nullptr, *k1 = nullptr;
+    uint32_t *i0 = nullptr, *i1 = nullptr, *d_nb = nullptr;
+    uint8_t *d_cnt = nullptr;
+    void *temp = nullptr;
+    unsigned long long *d_nu = c->d_scalars + ftkb_ctx::SLOT_UQ;
+    { int rs = scratch(c, 0, 8 * n, (void **)&k0); if (!rs) rs = scratch(c, 1, 8 * n, (void **)&k1); if (!rs) rs = scratch(c, 2, 4 * n, (void **)&i0);
+      if (!rs) rs = scratch(c, 3, 4 * n, (void **)&i1);
+      if (!rs) rs = scratch(c, 10, 4 * 9 * n, (void **)&d_nb); if (!rs) rs = scratch(c, 11, n, (void **)&d_cnt); if (rs) return rs; }
+    CK(cudaEventRecord(c->ev[0], c->stream));
+    launch_point_keys(c->d_pts + c->grown, n, tp, k0, i0, c->stream);
+    const size_t tb = std::max(sort_pairs_u64(nullptr, 0, k0, k1, i0, i1, n, c->stream), unique_by_key_u64(nullptr, 0, k1, i1, k0, i0, d_nu, n, c->stream));
+    { const int rs = scratch(c, 4, tb, &temp); if (rs) return rs; }
+    sort_pairs_u64(temp, tb, k0, k1, i0, i1, n, c->stream);
+    unique_by_key_u64(temp, tb, k1, i1, k0, i0, d_nu, n, c->stream);
+    tp.keys = k0;
+    launch_batch_neighbors(tp, d_nu, n, c->d_pts + c->grown, i0, nullptr, d_nb, d_cnt, c->stream);
+    CK(cudaEventRecord(c->ev[1], c->stream));
+    CK(cudaMemcpyAsync(c->h_scalars + ftkb_ctx::SLOT_UQ, d_nu, 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(h_keys, k0, 8 * n, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(h_nb, d_nb, 4 * 9 * n, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(h_cnt, d_cnt, n, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    { const int rc = check_launch(c, "streaming grow step (batch preparation)"); if (rc) return rc; }
+    nu = c->h_scalars[ftkb_ctx::SLOT_UQ];
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]));
+    c->stats.ms_finalize_device += ms;
+    c->stats.kernel_launches += 4;
+    c->stats.d2h_bytes += per * n + 8;
   }
-  { const int rc = wait_grow(c); if (rc) return rc; }                  // grow steps run in order
   ftkb::OnlineTracer *tracer = c->online.get();
-  auto work = [tracer](std::vector<ftkb_point> b) {
+  const bool prepared = n && !host_prep;
+  auto work = [tracer, prepared, h_pts, h_keys, h_nb, h_cnt, n, nu]() {
     const auto t0 = std::chrono::steady_clock::now();
-    tracer->grow(b.data(), b.size());
+    if (prepared) tracer->grow_sorted(nullptr, h_keys, (uint32_t)nu, h_nb, h_cnt);
+    else tracer->grow(h_pts, n);
     return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
   };
   // FTKB_STREAM_GROW=async: the walk of step k runs on a worker thread behind the sweep of step k+1 and the caller's next
-  // push.  Default is inline: the two modes measured the same on the loop of scripts/stream_timing.py (the walk is the
-  // whole cost there) and one async run showed the sweeps' API calls stalling next to the busy worker
-  // (profiles/r01f_stream_timing.md), so async stays opt-in until that is understood.
+  // push (it reads the staging buffer, which the next grow step reuses only after joining it).  Default is inline.
   static const bool async_grow = [] { const char *e = std::getenv("FTKB_STREAM_GROW"); return e && std::string(e) == "async"; }();
-  if (async_grow) c->grow_task = std::async(std::launch::async, work, std::move(batch));
+  if (async_grow) c->grow_task = std::async(std::launch::async, work);
   else {
-    try { c->stats.ms_finalize_host += work(std::move(batch)); }
+    try { c->stats.ms_finalize_host += work(); }
     catch (const std::bad_alloc &) { c->grow_failed = true; return fail(c, FTKB_ERR_NOMEM, "streaming grow step: out of memory (trajectories are incomplete)"); }
     catch (const std::exception &e) { c->grow_failed = true; return fail(c, FTKB_ERR_INVALID, std::string("streaming grow step: ") + e.what()); }
   }
@@ -1578,11 +1632,10 @@ extern "C" int ftkb_finalize(ftkb_ctx *c) {
     const auto t0 = std::chrono::steady_clock::now();
     std::vector<uint64_t> keys(n);
     for (uint64_t i = 0; i < n; i++) c->online->key_of(c->pts_sorted[i], keys[i]);
-    const std::vector<ftkb_point> &streamed = c->online->points();
+    const std::vector<uint64_t> &streamed = c->online->keys();
     for (const ftkb::OnlineCurve &cv : c->online->curves()) {
       for (const uint32_t g : cv.idx) {
-        uint64_t key = 0;
-        c->online->key_of(streamed[g], key);
+        const uint64_t key = streamed[g];
         const auto it = std::lower_bound(keys.begin(), keys.end(), key);
         if (it == keys.end() || *it != key) return fail(c, FTKB_ERR_INVALID, "finalize: a streamed point is missing from the sorted points");
         c->traj_idx.push_back((uint64_t)(it - keys.begin()));

@@ -3717,6 +3717,45 @@ void launch_neighbors(const TraceParams &tp, cudaStream_t s) {
   if (tp.n) neighbors_kernel<<<(unsigned)((tp.n + 127) / 128), 128, 0, s>>>(tp);
 }
 
+// streaming grow step (online.cpp: OnlineTracer::grow_sorted): the step's batch, sorted and unique; thread i moves point
+// idx[i] into place (dst != nullptr) and lists the batch indices of its punctured neighbours in ascending element order, ITSELF INCLUDED
+// (the reference unites an element with itself, which is visible in its union-find sizes).  *n_ptr = unique elements.
+__global__ void batch_neighbors_kernel(TraceParams tp, const u64 *__restrict__ n_ptr, const ftkb_point *__restrict__ src,
+                                       const uint32_t *__restrict__ idx, ftkb_point *dst, uint32_t *nb9, uint8_t *cnt_out) {
+  const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  const u64 n = *n_ptr;
+  if (i >= n) return;
+  const DeviceMeshTables &mt = c_mesh[tp.nd - 2];
+  const ftkb_point &pt = src[idx[i]];
+  if (dst) dst[i] = pt;
+  const int type = pt.simplex_type;
+  uint32_t found[9];
+  int cnt = 0;
+  found[cnt++] = (uint32_t)i;
+  for (int q = 0; q < mt.n_nb[type]; q++) {
+    const int x = pt.corner[0] + mt.nb_off[type][q][0], y = pt.corner[1] + mt.nb_off[type][q][1];
+    const int z = tp.nd == 3 ? pt.corner[2] + mt.nb_off[type][q][2] : 0;
+    const int t = pt.corner[3] + mt.nb_off[type][q][tp.nd];
+    u64 key;
+    if (!element_key(tp, x, y, z, t, mt.nb_type[type][q], key)) continue;
+    u64 lo = 0, hi = n;
+    while (lo < hi) {
+      const u64 mid = (lo + hi) >> 1;
+      if (tp.keys[mid] < key) lo = mid + 1; else hi = mid;
+    }
+    if (lo < n && tp.keys[lo] == key) found[cnt++] = (uint32_t)lo;
+  }
+  for (int a = 1; a < cnt; a++)
+    for (int b = a; b > 0 && found[b - 1] > found[b]; b--) { const uint32_t t = found[b]; found[b] = found[b - 1]; found[b - 1] = t; }
+  for (int q = 0; q < 9; q++) nb9[i * 9 + q] = q < cnt ? found[q] : 0xffffffffu;
+  cnt_out[i] = (uint8_t)cnt;
+}
+
+void launch_batch_neighbors(const TraceParams &tp, const unsigned long long *n_ptr, uint64_t n_max, const ftkb_point *src, const uint32_t *idx,
+                            ftkb_point *dst, uint32_t *nb9, uint8_t *cnt, cudaStream_t s) {
+  if (n_max) batch_neighbors_kernel<<<(unsigned)((n_max + 127) / 128), 128, 0, s>>>(tp, n_ptr, src, idx, dst, nb9, cnt);
+}
+
 // union-find with atomicMin hooking: the larger root is hooked under the smaller one, so the root of
 // every tree is its smallest member (the reference's duf hooks the same way, basic/duf.hh:41-72)
 __device__ __forceinline__ uint32_t uf_find(uint32_t *parent, uint32_t i) {

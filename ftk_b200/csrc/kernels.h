@@ -146,6 +146,10 @@ void launch_point_keys(const ftkb_point *pts, uint64_t n, const TraceParams &tp,
 void launch_gather_points(const ftkb_point *src, const uint32_t *idx, uint64_t n, ftkb_point *dst, cudaStream_t s);
 void launch_neighbors(const TraceParams &tp, cudaStream_t s);
 void launch_union_find(const TraceParams &tp, cudaStream_t s);
+// streaming grow step: tp.keys = the batch's sorted unique keys, *n_ptr of them (n_max bounds the grid); writes the sorted points (dst may be nullptr),
+// nine neighbour indices per element (ascending, itself included, 0xffffffff padded) and how many
+void launch_batch_neighbors(const TraceParams &tp, const unsigned long long *n_ptr, uint64_t n_max, const ftkb_point *src, const uint32_t *idx,
+                            ftkb_point *dst, uint32_t *nb9, uint8_t *cnt, cudaStream_t s);
 
 // cub wrappers (sort by key, then drop duplicate keys); return bytes of temp storage needed when temp == nullptr
 size_t sort_pairs_u64(void *temp, size_t temp_bytes, const unsigned long long *kin, unsigned long long *kout,

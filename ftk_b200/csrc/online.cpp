@@ -15,6 +15,9 @@
 #include "online.h"
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <stdexcept>
@@ -73,15 +76,16 @@ bool OnlineTracer::key_at(int x, int y, int z, int t, int type, uint64_t &key) c
   return true;
 }
 
-// neighbors(f) = every side of every cell f is a side of (critical_point_tracker_2d_regular.hh:292-300), f included
-int OnlineTracer::neighbor_keys(const ftkb_point &p, uint64_t out[9]) const {
-  const int type = p.simplex_type;
-  if (type < 0 || type >= ntypes_) return 0;
-  const int x0 = p.corner[0], y0 = p.corner[1], z0 = nd_ == 3 ? p.corner[2] : 0, t0 = p.corner[3];
-  const int64_t cell = ((int64_t)(x0 - lb_[0]) * ny_ + (y0 - lb_[1])) * nz_ + (z0 - lb_[2]);
+// neighbors(f) = every side of every cell f is a side of (critical_point_tracker_2d_regular.hh:292-300), f included;
+// computed on the element's key alone
+int OnlineTracer::neighbor_keys(const uint64_t self, uint64_t out[9]) const {
+  const int type = (int)(self & ((1u << KEY_TYPE_BITS) - 1));
+  if (type >= ntypes_) return 0;
+  const int t0 = (int)((self >> KEY_TYPE_BITS) & ((1u << KEY_TIME_BITS) - 1));
+  const int64_t cell = (int64_t)(self >> (KEY_TYPE_BITS + KEY_TIME_BITS));
+  const int z0 = (int)(cell % nz_) + lb_[2], y0 = (int)((cell / nz_) % ny_) + lb_[1], x0 = (int)(cell / (nz_ * ny_)) + lb_[0];
   if (x0 > lb_[0] && x0 < ub_[0] && y0 > lb_[1] && y0 < ub_[1] && (nd_ == 2 || (z0 > lb_[2] && z0 < ub_[2])) && t0 > 0 && t0 < (1 << KEY_TIME_BITS) - 1) {
     // away from the domain's faces every candidate exists (offsets are -1, 0, 1): its key is the element's plus a constant
-    const uint64_t self = ((((uint64_t)cell << KEY_TIME_BITS) | (uint64_t)t0) << KEY_TYPE_BITS) | (uint64_t)type;
     const int n = ncand_[type];
     for (int q = 0; q < n; q++) out[q] = self + (uint64_t)cand_[type][q].key_delta;
     return n;
@@ -94,6 +98,11 @@ int OnlineTracer::neighbor_keys(const ftkb_point &p, uint64_t out[9]) const {
     out[cnt++] = ((((uint64_t)(cell + c.cell_delta) << KEY_TIME_BITS) | (uint64_t)t) << KEY_TYPE_BITS) | (uint64_t)c.type;
   }
   return cnt;
+}
+
+const ftkb_point &OnlineTracer::point(uint32_t g) const {
+  const size_t b = (size_t)(std::upper_bound(batch_base_.begin(), batch_base_.end(), g) - batch_base_.begin()) - 1;
+  return batches_[b][g - batch_base_[b]];
 }
 
 uint64_t OnlineTracer::npoints() const {
@@ -179,8 +188,8 @@ void OnlineTracer::grow(const ftkb_point *pts_in, uint64_t n_in) {
   std::vector<Entry> table(cap, Entry{~0ull, 0, 0});   // no element key is all ones (the type field is below 60)
   std::vector<uint64_t> keys;
   keys.reserve(n_in);
-  const size_t base = all_.size();
-  all_.reserve(base + n_in);
+  std::vector<ftkb_point> batch;
+  batch.reserve(n_in);
   auto home_of = [&](uint64_t key) { return (size_t)(((key >> KEY_TYPE_BITS) * 0x9E3779B97F4A7C15ull) >> shift); };
   auto slot_from = [&](size_t h, uint64_t key) {
     while (table[h].key != ~0ull && table[h].key != key) h = (h + 1) & (cap - 1);
@@ -190,15 +199,15 @@ void OnlineTracer::grow(const ftkb_point *pts_in, uint64_t n_in) {
     uint64_t key;
     if (!key_of(pts_in[i], key)) continue;
     const size_t h = slot_from(home_of(key), key);
-    if (table[h].key == key) { all_[base + table[h].val] = pts_in[i]; continue; }
+    if (table[h].key == key) { batch[table[h].val] = pts_in[i]; continue; }
     table[h].key = key;
     table[h].val = (uint32_t)keys.size();
     keys.push_back(key);
-    all_.push_back(pts_in[i]);
+    batch.push_back(pts_in[i]);
   }
   // the punctured neighbours of an element, ascending (the candidate order), as batch indices; looked up when needed
   struct Source {
-    OnlineTracer *self; size_t base; const std::vector<Entry> *table; size_t cap; int shift;
+    const OnlineTracer *self; const uint64_t *keys; const std::vector<Entry> *table; size_t cap; int shift;
     size_t home_of(uint64_t key) const { return (size_t)(((key >> KEY_TYPE_BITS) * 0x9E3779B97F4A7C15ull) >> shift); }
     size_t slot_from(size_t h, uint64_t key) const {
       const Entry *t = table->data();
@@ -212,7 +221,7 @@ void OnlineTracer::grow(const ftkb_point *pts_in, uint64_t n_in) {
     int list(uint32_t i, uint32_t out[9]) const {
       uint64_t nk[9];
       size_t home[9];
-      const int m = self->neighbor_keys(self->all_[base + i], nk);
+      const int m = self->neighbor_keys(keys[i], nk);
       for (int q = 0; q < m; q++) { home[q] = home_of(nk[q]); __builtin_prefetch(table->data() + home[q]); }
       int cnt = 0;
       for (int q = 0; q < m; q++) {
@@ -225,7 +234,7 @@ void OnlineTracer::grow(const ftkb_point *pts_in, uint64_t n_in) {
     int64_t first_alive(uint32_t i, const uint8_t *alive) const {
       uint64_t nk[9];
       size_t home[9];
-      const int m = self->neighbor_keys(self->all_[base + i], nk);
+      const int m = self->neighbor_keys(keys[i], nk);
       for (int q = 0; q < m; q++) { home[q] = home_of(nk[q]); __builtin_prefetch(table->data() + home[q]); }
       for (int q = 0; q < m; q++) {
         const size_t h = slot_from(home[q], nk[q]);
@@ -234,11 +243,22 @@ void OnlineTracer::grow(const ftkb_point *pts_in, uint64_t n_in) {
       return -1;
     }
   };
-  walk((uint32_t)keys.size(), keys.data(), false, Source{this, base, &table, cap, shift});
+  store_batch(keys.data(), (uint32_t)keys.size(), std::move(batch));
+  walk((uint32_t)keys.size(), keys.data(), false, Source{this, keys.data(), &table, cap, shift});
+}
+
+// every element handed to a grow step: its key (the walk needs nothing else of an earlier step's element) and, for callers that
+// read trajectories back as points, the batch's records -- one array per batch, never copied again
+void OnlineTracer::store_batch(const uint64_t *keys, uint32_t n, std::vector<ftkb_point> &&pts) {
+  if (keys_.size() + n >= 0xffffffffull) throw std::length_error("more than 2^32 punctured simplices");
+  batch_base_.push_back((uint32_t)keys_.size());
+  keys_.insert(keys_.end(), keys, keys + n);
+  batches_.push_back(std::move(pts));
 }
 
 void OnlineTracer::grow_sorted(const ftkb_point *pts, const uint64_t *keys, uint32_t n, const uint32_t *nb, const uint8_t *cnt) {
-  all_.insert(all_.end(), pts, pts + n);
+  if (!pts && n) have_points_ = false;
+  store_batch(keys, n, pts ? std::vector<ftkb_point>(pts, pts + n) : std::vector<ftkb_point>());
   struct Source {
     const uint64_t *keys; uint32_t n; const uint32_t *nb; const uint8_t *cnt;
     int64_t find(uint64_t key) const {
@@ -255,11 +275,10 @@ void OnlineTracer::grow_sorted(const ftkb_point *pts, const uint64_t *keys, uint
   walk(n, keys, true, Source{keys, n, nb, cnt});
 }
 
-// The batch is the last n elements of all_.
+// The batch is the last n stored elements.
 template <class Source>
 void OnlineTracer::walk(uint32_t n, const uint64_t *keys, bool sorted, Source src) {
-  if (all_.size() >= 0xffffffffull) throw std::length_error("more than 2^32 punctured simplices");
-  const uint32_t base = (uint32_t)(all_.size() - n);
+  const uint32_t base = (uint32_t)(keys_.size() - n);
   std::vector<uint8_t> alive(n, 1);
   // smallest unclaimed punctured neighbour of an element (critical_point_tracker.hh:555-572): the first live entry of its
   // ascending neighbour list.  An element of this batch has its list ready; a trajectory's end from an earlier step looks
@@ -272,7 +291,7 @@ void OnlineTracer::walk(uint32_t n, const uint64_t *keys, bool sorted, Source sr
     }
     if (n == 0) return -1;
     uint64_t nk[9];
-    const int m = neighbor_keys(all_[g], nk);
+    const int m = neighbor_keys(keys_[g], nk);
     for (int q = 0; q < m; q++) {
       const int64_t j = src.find(nk[q]);
       if (j >= 0 && alive[j]) { alive[j] = 0; return j; }
@@ -410,6 +429,44 @@ extern "C" int ftkb_online_grow(ftkb_online *o, const ftkb_point *pts, uint64_t 
   return FTKB_OK;
 }
 
+// the same step through grow_sorted: the preparation the tracker does on the device (sort by element key, one entry per
+// element, neighbour lists by binary search, the element itself included) restated on the host, so that the index-list walk is
+// tested without a device
+extern "C" int ftkb_online_grow_prepared(ftkb_online *o, const ftkb_point *pts, uint64_t n) {
+  if (!o || (!pts && n) || n >= 0xffffffffull) return FTKB_ERR_INVALID;
+  std::vector<std::pair<uint64_t, uint32_t>> order;
+  order.reserve(n);
+  for (uint64_t i = 0; i < n; i++) {
+    uint64_t key;
+    if (o->tracer.key_of(pts[i], key)) order.emplace_back(key, (uint32_t)i);
+  }
+  std::stable_sort(order.begin(), order.end(), [](const std::pair<uint64_t, uint32_t> &a, const std::pair<uint64_t, uint32_t> &b) { return a.first < b.first; });
+  std::vector<ftkb_point> sorted;
+  std::vector<uint64_t> keys;
+  for (size_t k = 0; k < order.size(); k++)
+    if (k == 0 || order[k].first != order[k - 1].first) { keys.push_back(order[k].first); sorted.push_back(pts[order[k].second]); }
+  const uint32_t m = (uint32_t)keys.size();
+  std::vector<uint32_t> nb(9 * (size_t)m, 0xffffffffu);
+  std::vector<uint8_t> cnt(m, 0);
+  for (uint32_t i = 0; i < m; i++) {
+    uint64_t nk[9];
+    const int c = o->tracer.neighbor_keys(keys[i], nk);     // ascending
+    for (int q = 0; q < c; q++) {
+      const auto it = std::lower_bound(keys.begin(), keys.end(), nk[q]);
+      if (it != keys.end() && *it == nk[q]) nb[9 * (size_t)i + cnt[i]++] = (uint32_t)(it - keys.begin());
+    }
+  }
+  static const bool timing = std::getenv("FTKB_DEBUG_TIMING") != nullptr;
+  const auto t0 = std::chrono::steady_clock::now();
+  o->tracer.grow_sorted(sorted.data(), keys.data(), m, nb.data(), cnt.data());
+  if (timing) {
+    static double total = 0;
+    total += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    std::fprintf(stderr, "[ftkb timing] grow_sorted walk alone: %.3f ms so far\n", total);
+  }
+  return FTKB_OK;
+}
+
 extern "C" int ftkb_online_size(const ftkb_online *o, uint64_t *ntraj, uint64_t *npoints) {
   if (!o) return FTKB_ERR_INVALID;
   if (ntraj) *ntraj = o->tracer.curves().size();
@@ -421,9 +478,9 @@ extern "C" int ftkb_online_get(const ftkb_online *o, uint64_t *offsets, ftkb_poi
   if (!o || !offsets) return FTKB_ERR_INVALID;
   uint64_t pos = 0, k = 0;
   offsets[0] = 0;
-  const std::vector<ftkb_point> &all = o->tracer.points();
+  if (pts && !o->tracer.has_points()) return FTKB_ERR_INVALID;
   for (const ftkb::OnlineCurve &c : o->tracer.curves()) {
-    if (pts) for (const uint32_t g : c.idx) pts[pos++] = all[g]; else pos += c.idx.size();
+    if (pts) for (const uint32_t g : c.idx) pts[pos++] = o->tracer.point(g); else pos += c.idx.size();
     if (loop) loop[k] = c.loop;
     if (complete) complete[k] = c.complete;
     offsets[++k] = pos;

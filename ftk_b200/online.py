@@ -34,10 +34,12 @@ class OnlineTracer:
         except Exception:
             pass
 
-    def grow(self, pts):
-        """pts: structured array (L.POINT_DTYPE) of the punctured simplices found since the last call"""
+    def grow(self, pts, prepared=False):
+        """pts: structured array (L.POINT_DTYPE) of the punctured simplices found since the last call; prepared: walk over
+        sorted neighbour lists (what the tracker's device-side preparation produces) instead of a hash of the batch"""
         pts = np.ascontiguousarray(pts, dtype=L.POINT_DTYPE)
-        rc = L.lib().ftkb_online_grow(self._h, pts.ctypes.data, len(pts))
+        f = L.lib().ftkb_online_grow_prepared if prepared else L.lib().ftkb_online_grow
+        rc = f(self._h, pts.ctypes.data, len(pts))
         if rc:
             raise L.FTKBError(rc, "ftkb_online_grow failed")
 

@@ -264,6 +264,9 @@ typedef struct ftkb_online ftkb_online;
 int ftkb_online_create(int nd, const int32_t *lb /* nd */, const int32_t *ub /* nd, inclusive */, ftkb_online **out);
 void ftkb_online_destroy(ftkb_online *);
 int ftkb_online_grow(ftkb_online *, const ftkb_point *pts, uint64_t n);
+/* the same step over sorted neighbour lists -- the form the tracker's device-side preparation hands to the walk -- built here on
+ * the host; results are identical to ftkb_online_grow */
+int ftkb_online_grow_prepared(ftkb_online *, const ftkb_point *pts, uint64_t n);
 int ftkb_online_size(const ftkb_online *, uint64_t *ntraj, uint64_t *npoints);
 int ftkb_online_get(const ftkb_online *, uint64_t *offsets /* ntraj+1 */, ftkb_point *pts /* npoints */, uint8_t *loop, uint8_t *complete);
 

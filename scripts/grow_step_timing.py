@@ -26,13 +26,14 @@ except Exception:
     np.save(cache, pts)
     print(f"oracle: {len(pts)} points in {time.time() - t0:.1f} s", file=sys.stderr)
 steps = [np.ascontiguousarray(pts[pts["corner"][:, 3] == t]) for t in range(T)]   # the sweep of interval t emits corner time t
-best = 1e9
-for r in range(reps):
-    tr = OnlineTracer([2, 2], [W - 2, W - 2])
-    t0 = time.perf_counter()
-    for s in steps:
-        tr.grow(s)
-    dt = time.perf_counter() - t0
-    best = min(best, dt)
 n = sum(len(s) for s in steps)
-print(f"{W}x{W}x{T}: {n} points, {len(tr.trajectories())} trajectories, grow {best * 1e3:.2f} ms = {best / n * 1e9:.0f} ns/point")
+for prepared in (False, True):      # True includes the host-side stand-in for the device preparation (sort + binary searches)
+    best = 1e9
+    for r in range(reps):
+        tr = OnlineTracer([2, 2], [W - 2, W - 2])
+        t0 = time.perf_counter()
+        for s in steps:
+            tr.grow(s, prepared=prepared)
+        dt = time.perf_counter() - t0
+        best = min(best, dt)
+    print(f"{W}x{W}x{T} prepared={prepared}: {n} points, {len(tr.trajectories())} trajectories, grow {best * 1e3:.2f} ms = {best / n * 1e9:.0f} ns/point")

@@ -55,8 +55,9 @@ def _index_of(points):
     return {(tuple(int(v) for v in c), int(t)): i for i, (c, t) in enumerate(zip(points["corner"], points["simplex_type"]))}
 
 
+@pytest.mark.parametrize("prepared", [False, True])
 @pytest.mark.parametrize("name", NAMES)
-def test_host_grow_step_matches_reference(name, ftkb):
+def test_host_grow_step_matches_reference(name, prepared, ftkb):
     """the library's grow step (ftkb_online_*, host code) fed the reference's points one timestep at a time, in a
     scrambled order within the step (the sweep appends hits in no particular order)"""
     from ftk_b200.online import OnlineTracer
@@ -69,13 +70,14 @@ def test_host_grow_step_matches_reference(name, ftkb):
     rng = np.random.default_rng(7)
     for j in range(meta["T"] - 1):
         batch = p[p["timestep"] == j]
-        tr.grow(batch[rng.permutation(len(batch))])
+        tr.grow(batch[rng.permutation(len(batch))], prepared=prepared)
     index = _index_of(p)
     got = [([index[(tuple(int(v) for v in q["corner"]), int(q["simplex_type"]))] for q in pts], l, c) for pts, l, c in tr.trajectories()]
     assert got == load_stream(name)
 
 
-def test_host_grow_step_duplicates_and_empty(ftkb):
+@pytest.mark.parametrize("prepared", [False, True])
+def test_host_grow_step_duplicates_and_empty(prepared, ftkb):
     """an element reported twice in one step is one map entry; empty steps complete every open trajectory"""
     from ftk_b200.online import OnlineTracer
     meta, gold, _ = load_golden("mx2d_11x13x20")
@@ -86,13 +88,13 @@ def test_host_grow_step_duplicates_and_empty(ftkb):
     a, b = OnlineTracer(lb, ub), OnlineTracer(lb, ub)
     for j in range(5):
         batch = p[p["timestep"] == j]
-        a.grow(batch)
-        b.grow(np.concatenate([batch, batch[::-1]]))
+        a.grow(batch, prepared=prepared)
+        b.grow(np.concatenate([batch, batch[::-1]]), prepared=prepared)
     ta, tb = a.trajectories(), b.trajectories()
     assert len(ta) == len(tb) == 1 and np.array_equal(ta[0][0], tb[0][0]) and not ta[0][2]
-    a.grow(p[:0])
+    a.grow(p[:0], prepared=prepared)
     assert a.trajectories()[0][2]                       # nothing to add: complete
-    a.grow(p[p["timestep"] == 5])
+    a.grow(p[p["timestep"] == 5], prepared=prepared)
     t = a.trajectories()
     assert len(t) == 2 and np.array_equal(t[0][0], ta[0][0])   # a complete trajectory is never extended again
 
@@ -167,8 +169,9 @@ def test_cli_stream_flag(tmp_path):
     assert lengths == [len(idx) for idx, _, _ in want]
 
 
+@pytest.mark.parametrize("prepared", [False, True])
 @pytest.mark.parametrize("nd,density,seed", [(2, 0.08, 1), (2, 0.3, 2), (2, 0.7, 3), (3, 0.02, 4), (3, 0.1, 5), (3, 0.35, 6)])
-def test_host_grow_step_matches_oracle_on_random_sets(nd, density, seed, ftkb, oracle):
+def test_host_grow_step_matches_oracle_on_random_sets(nd, density, seed, prepared, ftkb, oracle):
     """random punctured sets, sparse to dense: branching (special) nodes, components of special nodes only, components
     large enough that union_find's doubled sizes wrap around 2^64 -- the library's grow step against the restatement"""
     from oracle import cp_online
@@ -193,7 +196,7 @@ def test_host_grow_step_matches_oracle_on_random_sets(nd, density, seed, ftkb, o
     for t in range(T):
         sel = p[p["timestep"] == t]
         a.grow([tuple(int(v) for v in q["corner"]) + (int(q["simplex_type"]),) for q in sel])
-        b.grow(sel[rng.permutation(len(sel))])
+        b.grow(sel[rng.permutation(len(sel))], prepared=prepared)
     want = [(t["elements"], t["loop"], t["complete"]) for t in a.trajectories]
     got = [([tuple(int(v) for v in q["corner"]) + (int(q["simplex_type"]),) for q in pts], l, c) for pts, l, c in b.trajectories()]
     assert got == want
