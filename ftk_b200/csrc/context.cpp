@@ -657,6 +657,11 @@ static void fill_sweep_geometry(const ftkb_ctx *c, SweepParams &p) {
     p.vmax[j] = p.ub[j];   // vertices outside the domain belong to no valid simplex: keep them out of the cube ranges
     p.voff[j] = 0; p.rank_lb[j] = p.lb[j]; p.rank_nc[j] = p.nc[j];
   }
+  // scalar build kernels: key filter of the layer's min non-zero |v| against the running minimum known now (kernels.h);
+  // gradient2D scales the differences by W - 1 / H - 1 (grad.hh:24-27), gradient3D halves them (grad.hh:140-144)
+  static const bool res_filter = [] { const char *e = std::getenv("FTKB_RES_FILTER"); return !(e && std::string(e) == "0"); }();
+  for (int j = 0; j < 3; j++)
+    p.res_thr[j] = !res_filter ? __builtin_inff() : res_threshold_key(c->resolution, c->n == 2 ? (double)(c->cfg.dims[j < 2 ? j : 0] - 1) : 0.5);
   if (c->slab) {           // a z-slab of a larger array: ranks / positions / corners in the whole lattice's frame
     p.voff[2] = c->cfg.slab_offset;
     p.rank_lb[2] = c->cfg.slab_global_lb;

@@ -1139,6 +1139,7 @@ __device__ __forceinline__ double lds64_f64(uint32_t a) {
   asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
   return v;
 }
+__device__ __forceinline__ void sts64_f64(uint32_t a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
 // max that keeps a NaN once it has seen one (FMNMX.NAN): the "magnitude too large for float keys" accumulator
 __device__ __forceinline__ float fmax_nan(float a, float b) {
   float r;
@@ -1175,8 +1176,8 @@ __device__ __forceinline__ K2Acc keys2d_strip(const SweepParams &p, const int c0
                                            const uint32_t tile_u32 /* smem address of this warp's column c0-2, stage 0, row 0 */,
                                            const uint32_t full0, const uint32_t empty0, const int strip,
                                            const uint32_t sbase /* ring stages this CTA has consumed before this segment */,
+                                           const uint32_t res_u32 /* smem: this thread's {min dx, min dy}; only the rare exact path touches them */,
                                            const K2Acc acc) {
-  double mdx = acc.mdx, mdy = acc.mdy;
   float big = acc.big;
   const int W = p.W, H = p.H, B = p.build_layer;
   const int e = c0 + 2 * lane, o = e + 1;
@@ -1187,6 +1188,7 @@ __device__ __forceinline__ K2Acc keys2d_strip(const SweepParams &p, const int c0
   const int ngroups = (nrows + K2_R - 1) / K2_R, nstages = (nrows + 2 + K2_R - 1) / K2_R;
   const double cw = (double)(W - 1), ch = (double)(H - 1);
   const bool want_res = p.res_slot[B] != nullptr;
+  const float thrx = p.res_thr[0], thry = p.res_thr[1];
   const uint4 *sum_prev = NPREV ? p.sum_in[0] + cells2d_index(p, strip, 0, lane) : nullptr;
   uint4 *sum_out = p.sum_out + cells2d_index(p, strip, 0, lane);
   const uint32_t lane_u32 = tile_u32 + (uint32_t)lane * 16u;    // +8: column e-1, +16: e, o, +32: o+1
@@ -1230,8 +1232,7 @@ __device__ __forceinline__ K2Acc keys2d_strip(const SweepParams &p, const int c0
       nl[i] = lds64_f64(base + (uint32_t)i * K2_ROW_BYTES + 8u);
       nr[i] = lds64_f64(base + (uint32_t)i * K2_ROW_BYTES + 32u);
     }
-    __syncwarp();
-    if (elect_one()) mbar_arrive(empty0 + 8u * slot);   // the stage lives in registers now
+    float ax = __int_as_float(0x7F800000);
 #pragma unroll
     for (int i = 0; i < K2_R; i++) {
       const float ke = fabsf(hikey(C[P][i][0])), ko = fabsf(hikey(C[P][i][1]));
@@ -1245,12 +1246,31 @@ __device__ __forceinline__ K2Acc keys2d_strip(const SweepParams &p, const int c0
       }
       const double dxe = mid_e - left, dxo = right - C[P][i][0];
       KX[P][i][0] = hikey(dxe); KX[P][i][1] = hikey(dxo);
-      const int j = r0 + K2_R * s + i - 1;              // the gradient row this ring row is the centre of
-      if (want_res && j >= r0 && j <= jl && j < H) {
-        if (e_in) mdx = nzmin(mdx, dxe);
-        if (o_in) mdx = nzmin(mdx, dxo);
-      }
+      ax = fminf(ax, fminf(fabsf(KX[P][i][0]), fabsf(KX[P][i][1])));
     }
+    // exact minimum of the non-zero |d|: only values whose key does not exceed the running minimum's (known when the step was
+    // enqueued; +inf until a layer has been resolved) can lower it -- one vote per stage instead of two DSETP + select per value.
+    // The rare path reads the x neighbours again (the stage is released after it) so that the differences need not stay live.
+    if (want_res && __any_sync(0xffffffffu, ax <= thrx)) {
+      double mdx = lds64_f64(res_u32);
+#pragma unroll
+      for (int i = 0; i < K2_R; i++) {
+        const int j = r0 + K2_R * s + i - 1;              // the gradient row this ring row is the centre of
+        if (j >= r0 && j <= jl && j < H) {
+          double left = lds64_f64(base + (uint32_t)i * K2_ROW_BYTES + 8u), right = lds64_f64(base + (uint32_t)i * K2_ROW_BYTES + 32u), mid_e = C[P][i][1];
+          if (BORDER) {
+            if (e == 0) left = C[P][i][0];
+            if (!o_in) mid_e = C[P][i][0];
+            if (!o1_in) right = C[P][i][1];
+          }
+          if (e_in) mdx = nzmin(mdx, mid_e - left);
+          if (o_in) mdx = nzmin(mdx, right - C[P][i][0]);
+        }
+      }
+      sts64_f64(res_u32, mdx);
+    }
+    __syncwarp();
+    if (elect_one()) mbar_arrive(empty0 + 8u * slot);   // the stage lives in registers now
   };
 
   float bxmn = 0.f, bxmx = 0.f, bymn = 0.f, bymx = 0.f;
@@ -1275,6 +1295,7 @@ __device__ __forceinline__ K2Acc keys2d_strip(const SweepParams &p, const int c0
     gphase = gphase == 2 ? 0 : gphase + 1;
     const int j0 = r0 + K2_R * g;
     const bool full = j0 + K2_R - 1 <= min(jl, H - 1);  // (warp-uniform) all three rows exist and count for min |v|
+    float ay = __int_as_float(0x7F800000);
 #pragma unroll
     for (int i = 0; i < K2_R; i++) {
       const int j = j0 + i;
@@ -1284,10 +1305,7 @@ __device__ __forceinline__ K2Acc keys2d_strip(const SweepParams &p, const int c0
       const double *p1 = i + 2 < K2_R ? C[P][i + 2] : C[1 - P][i + 2 - K2_R];
       const double dye = p1[0] - m1[0], dyo = p1[1] - m1[1];
       const float kxe = kx[0], kxo = kx[1], kye = hikey(dye), kyo = hikey(dyo);
-      if (want_res && (full || j < H)) {
-        if (e_in) mdy = nzmin(mdy, dye);
-        if (o_in) mdy = nzmin(mdy, dyo);
-      }
+      ay = fminf(ay, fminf(fabsf(kye), fabsf(kyo)));
       if (i == 0 && opens_group) {
         // gradient row C2_R k closes block k-1 and opens block k
         const float rxmn = fminf(kxe, kxo), rxmx = fmaxf(kxe, kxo), rymn = fminf(kye, kyo), rymx = fmaxf(kye, kyo);
@@ -1300,6 +1318,19 @@ __device__ __forceinline__ K2Acc keys2d_strip(const SweepParams &p, const int c0
         bxmn = fminf(fminf(bxmn, kxe), kxo); bxmx = fmaxf(fmaxf(bxmx, kxe), kxo);
         bymn = fminf(fminf(bymn, kye), kyo); bymx = fmaxf(fmaxf(bymx, kye), kyo);
       }
+    }
+    if (want_res && __any_sync(0xffffffffu, ay <= thry)) {     // see load_stage: the rows of this group are still in registers
+      double mdy = lds64_f64(res_u32 + 8u);
+#pragma unroll
+      for (int i = 0; i < K2_R; i++) {
+        const int j = j0 + i;
+        if (!full && (j > jl || j >= H)) break;
+        const double *m1 = C[P][i];
+        const double *p1 = i + 2 < K2_R ? C[P][i + 2] : C[1 - P][i + 2 - K2_R];
+        if (e_in) mdy = nzmin(mdy, p1[0] - m1[0]);
+        if (o_in) mdy = nzmin(mdy, p1[1] - m1[1]);
+      }
+      sts64_f64(res_u32 + 8u, mdy);
     }
   };
 
@@ -1318,7 +1349,7 @@ __device__ __forceinline__ K2Acc keys2d_strip(const SweepParams &p, const int c0
       if (fm) cells2d_slow_cubes(p, fm, c0, (kb0 + b) * C2_R, NPREV + 1, C2_R);
     }
   }
-  return K2Acc{mdx, mdy, big};
+  return K2Acc{lds64_f64(res_u32), lds64_f64(res_u32 + 8u), big};
 }
 
 // One CTA per (tile of C2_CW strips, chunk of p.rows corner rows); K2_CTAS CTAs per SM.
@@ -1329,6 +1360,7 @@ __global__ void __launch_bounds__((C2_CW + 1) * 32, K2_CTAS) scan2d_keys_build_k
   const int wib = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);     // warp-uniform by construction
   const uint32_t ring0 = smem_u32(fb_smem);
   const uint32_t full0 = ring0 + (uint32_t)K2_NST * K2_STAGE_BYTES, empty0 = full0 + 8u * K2_NST;
+  const uint32_t res_u32 = empty0 + 8u * K2_NST + 16u * threadIdx.x;
   const int W = p.W, H = p.H;
   const int bx = blockIdx.x % p.nsx, cy = blockIdx.x / p.nsx;
   const int C0 = bx * (C2_CW * FB_STRIDE);
@@ -1370,8 +1402,9 @@ __global__ void __launch_bounds__((C2_CW + 1) * 32, K2_CTAS) scan2d_keys_build_k
   const bool border = c0 == 0 || c0 + FB_SEG - 2 > W;      // strips that touch the array's left / right edge clamp their columns
   K2Acc acc{DBL_MAX, DBL_MAX, 0.f};                   // exact min non-zero |d| per component; scaled by (W-1), (H-1) at the end:
                                                       // v = fl(d c) is monotone in |d|, so min |v| = fl(min |d| c) (grad.hh:24-27)
-  if (border) acc = keys2d_strip<true, NPREV, TEST, K2_NST>(p, c0, r0, r1, lane, tile_u32, full0, empty0, bx * C2_CW + wib, 0u, acc);
-  else acc = keys2d_strip<false, NPREV, TEST, K2_NST>(p, c0, r0, r1, lane, tile_u32, full0, empty0, bx * C2_CW + wib, 0u, acc);
+  sts64_f64(res_u32, DBL_MAX); sts64_f64(res_u32 + 8u, DBL_MAX);
+  if (border) acc = keys2d_strip<true, NPREV, TEST, K2_NST>(p, c0, r0, r1, lane, tile_u32, full0, empty0, bx * C2_CW + wib, 0u, res_u32, acc);
+  else acc = keys2d_strip<false, NPREV, TEST, K2_NST>(p, c0, r0, r1, lane, tile_u32, full0, empty0, bx * C2_CW + wib, 0u, res_u32, acc);
   if (p.res_slot[p.build_layer] != nullptr) {
     const double cw = (double)(W - 1), ch = (double)(H - 1);
     const double ax = fabs(acc.mdx), ay = fabs(acc.mdy);
@@ -1381,7 +1414,7 @@ __global__ void __launch_bounds__((C2_CW + 1) * 32, K2_CTAS) scan2d_keys_build_k
   if (!(acc.big < __int_as_float(KEYF_BIG))) atomicExch(p.poison, 1ull);
 }
 
-static size_t k2_smem_bytes(int nst) { return (size_t)nst * K2_STAGE_BYTES + (size_t)2 * nst * 8; }
+static size_t k2_smem_bytes(int nst) { return (size_t)nst * K2_STAGE_BYTES + (size_t)2 * nst * 8 + (size_t)16 * (C2_CW + 1) * 32; }
 // FTKB_K2_CTAS (CTAs per SM: 2 | 3 | 4, default 3) and FTKB_K2_NST (ring stages at three CTAs per SM: 4 | 5 | 6, default 4)
 static int k2_variant() {
   static const int v = [] {
@@ -1896,6 +1929,8 @@ struct S3Build {
   unsigned masks;
   double rmin, r2;           // signed value of smallest magnitude so far; 2 |rmin| (the differences are 2 v)
   float rkey;                // high word of r2
+  double r2cap;              // what r2 / rkey start from: just above twice the running minimum of the earlier layers, or +inf
+  float kcap;
   uint32_t pcell[3];         // previous plane's merged cell (packed like a stored cell)
   int st_c, st_p;
   uint32_t par_p;
@@ -1974,8 +2009,12 @@ struct S3Build {
           if (go) {
             res_update3(rmin, in_e, dxe, dye, dze);       // inline: a call here would cost the plane loop its registers
             res_update3(rmin, in_o, dxo, dyo, dzo);
-            r2 = 2.0 * fabs(rmin);
-            rkey = rmin == DBL_MAX ? inff_ : hikey(r2);      // nothing found yet: keep accepting every key
+            // nothing found yet: back to the cap -- the running minimum known when the step was enqueued (SweepParams::res_thr;
+            // +inf accepts every key)
+            const double n2 = 2.0 * fabs(rmin);
+            const bool capped = !(n2 < r2cap);
+            r2 = capped ? r2cap : n2;
+            rkey = capped ? kcap : hikey(n2);
           }
         }
       }
@@ -2066,8 +2105,10 @@ __device__ __forceinline__ void s3_consume(const SweepParams &p, const uint32_t 
     s.touches = ((dom_e & ~in_e) | (dom_o & ~in_o)) != 0u;
   }
   s.rmin = DBL_MAX;
-  s.r2 = __hiloint2double(0x7FF00000, 0);
-  s.rkey = __int_as_float(0x7F800000);
+  s.kcap = p.res_thr[0];
+  s.r2cap = s.kcap < __int_as_float(0x7F800000) ? __hiloint2double(__float_as_int(s.kcap), 0) : __hiloint2double(0x7FF00000, 0);
+  s.r2 = s.r2cap;
+  s.rkey = s.kcap;
 #pragma unroll
   for (int c = 0; c < 3; c++) s.pcell[c] = 0x7FC07FC0u;
   s.failbits = 0;
@@ -3163,8 +3204,12 @@ __device__ __forceinline__ int sos_rank(const SweepParams &p, const int *v /* ND
 }
 
 // vcache: the cube's 2^(ND+1) vertex vectors, [vertex mask][component], gathered once per cube by the block (test_kernel)
-template <int ND>
-__device__ bool check_simplex(const SweepParams &p, const DeviceMeshTables &mt, const int corner[3], int type, ftkb_point &cp, const double *vcache) {
+// STAGE 0: validity + cheap exact exclusion ("does the simplex need the predicate at all"); STAGE 1: the predicate (exact
+// origin-in-simplex, or the non-robust barycentric test); STAGE 2: interpolation, Jacobian, type -> the record (assumes 0 and 1
+// passed).  vin: the simplex's vertex vectors, vin[k * ND + c].  The stages recompute the few quantities they share (vertex
+// coordinates, quantised values, SoS ranks): cheaper than carrying them through the block's queues.
+template <int ND, int STAGE>
+__device__ bool check_simplex(const SweepParams &p, const DeviceMeshTables &mt, const int corner[3], int type, ftkb_point &cp, const double *vin) {
   constexpr int NV = ND + 1;
   int vt[NV][ND + 1];
   const LayerPtrs *L[NV];
@@ -3189,11 +3234,11 @@ __device__ bool check_simplex(const SweepParams &p, const DeviceMeshTables &mt, 
 #pragma unroll
   for (int k = 0; k < NV; k++)
 #pragma unroll
-    for (int c = 0; c < ND; c++) v[k][c] = vcache[mt.vmask[type][k] * ND + c];
+    for (int c = 0; c < ND; c++) v[k][c] = vin[k * ND + c];
 
   double mu[NV];
   bool inside = false;
-  if constexpr (ND == 3) inside = inverse_lerp3(v, mu);
+  if constexpr (ND == 3) { if (STAGE != 0) inside = inverse_lerp3(v, mu); }
 
   i64 vf[NV][ND];
   int rank[NV];
@@ -3205,11 +3250,13 @@ __device__ bool check_simplex(const SweepParams &p, const DeviceMeshTables &mt, 
         if (isnan(v[k][c]) || isinf(v[k][c])) return false;
         vf[k][c] = quantise(v[k][c], p.factor);
       }
+    if (STAGE != 0) {
 #pragma unroll
-    for (int k = 0; k < NV; k++) rank[k] = sos_rank<ND>(p, vt[k]);
+      for (int k = 0; k < NV; k++) rank[k] = sos_rank<ND>(p, vt[k]);
+    }
     // cheap exact exclusion on the quantised integers before the full cascade: one strictly
     // signed component, with magnitudes small enough that no determinant can leave int64
-    {
+    if (STAGE == 0) {
       const i64 lim = ND == 2 ? (1ll << 29) : (1ll << 19);
       bool small = true, sided = false;
 #pragma unroll
@@ -3223,11 +3270,12 @@ __device__ bool check_simplex(const SweepParams &p, const DeviceMeshTables &mt, 
         }
         sided = sided || pos || neg;
       }
-      if (small && sided) return false;
+      return !(small && sided);
     }
-    if (!origin_in_simplex<NV, ND>(vf, rank)) return false;
+    if (STAGE == 1) return origin_in_simplex<NV, ND>(vf, rank);
   } else {
-    if (!inside) return false;
+    if (STAGE == 0) return true;
+    if (STAGE == 1) return inside;
   }
 
   if constexpr (ND == 2) {
@@ -3351,20 +3399,88 @@ __device__ bool check_simplex(const SweepParams &p, const DeviceMeshTables &mt, 
 
 // A block works on CPB surviving cubes per round: first the 2^(ND+1) vertices of every cube are gathered (the vector field
 // read or derived ONCE per vertex -- a vertex is shared by up to 9 / 36 simplices of its cube), then one thread per
-// (cube, simplex type) runs the exact test on the cached vectors.
+// (cube, simplex type) runs the cheap exclusion (stage 0).  What survives goes into a shared-memory queue (the simplex's vertex
+// vectors, corner, type); whenever a queue holds a block's worth of entries the next stage runs on it with every lane busy:
+// stage 1 = the exact predicate, stage 2 = interpolation / Jacobian / type of the punctured simplices.  On feature-dense fields
+// (1e6 surviving cubes per step) a warp of 32 (cube, type) pairs almost always holds one that needs the long path; without the
+// queues all 32 lanes would walk it.
+template <int ND>
+struct TestQueueEntry {
+  double v[(ND + 1) * ND];
+  int corner[3];
+  int type;
+};
+// the long stages as functions of their own: the kernel's register budget is then the largest stage's, not the sum
+template <int ND, int STAGE>
+__device__ __noinline__ bool test_stage(const SweepParams &p, const TestQueueEntry<ND> *e, ftkb_point *cp) {
+  return check_simplex<ND, STAGE>(p, c_mesh[ND - 2], e->corner, e->type, *cp, e->v);
+}
+
 template <int ND>
 __global__ void __launch_bounds__(128) test_kernel(const __grid_constant__ SweepParams p) {
   const DeviceMeshTables &mt = c_mesh[ND - 2];
   constexpr int ntypes = ND == 2 ? 12 : 60;
+  constexpr int NV = ND + 1;
   constexpr int NVC = 1 << (ND + 1);                  // vertices of a space-time cube
   constexpr int CPB = 128 / ntypes;                   // cubes per block and round (10 in 2D, 2 in 3D)
+  constexpr int QT = ND == 2 ? 128 : 64;              // a queue is drained in batches of up to 128 while it holds at least QT entries
+  constexpr int QCAP = QT + 128;                      // (at most QT - 1 left behind + at most 128 pushed by one batch of the stage before)
+  using Entry = TestQueueEntry<ND>;
   __shared__ double vcache[CPB][NVC * ND];
   __shared__ int ccorner[CPB][3];
+  __shared__ Entry q1[QCAP], q2[QCAP];
+  __shared__ int qn[2], qhead[2];                     // entries / first entry of q1, q2 (rings)
   u64 ncubes = *p.wl_count;
   if (ncubes > p.wl_cap) ncubes = p.wl_cap;
   const u64 stride = (u64)gridDim.x * CPB;
   const u64 rounds = (ncubes + stride - 1) / stride;
   const int lane = threadIdx.x & 31;
+  if (threadIdx.x < 2) { qn[threadIdx.x] = 0; qhead[threadIdx.x] = 0; }
+  __syncthreads();
+
+  // append `e` to queue q (ring of QCAP entries) for the lanes with `push`
+  auto push_entry = [&](Entry *q, const int which, const bool push, const Entry &e) {
+    const unsigned b = __ballot_sync(0xffffffffu, push);
+    if (!b) return;
+    int base = 0;
+    const int leader = __ffs(b) - 1;
+    if (lane == leader) base = atomicAdd(&qn[which], __popc(b));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (push) q[(qhead[which] + base + __popc(b & ((1u << lane) - 1))) % QCAP] = e;
+  };
+  // stage 2 on up to 128 entries of q2: the records of punctured simplices
+  auto run_stage2 = [&]() {
+    const int n2 = min(qn[1], 128), h2 = qhead[1];
+    bool hit = false;
+    ftkb_point cp;
+    if ((int)threadIdx.x < n2) hit = test_stage<ND, 2>(p, &q2[(h2 + (int)threadIdx.x) % QCAP], &cp);
+    const unsigned b = __ballot_sync(0xffffffffu, hit);
+    if (b) {
+      u64 base = 0;
+      const int leader = __ffs(b) - 1;
+      if (lane == leader) base = atomicAdd(p.pt_count, (u64)__popc(b));
+      base = __shfl_sync(0xffffffffu, base, leader);
+      if (hit) {
+        const u64 o = base + __popc(b & ((1u << lane) - 1));
+        if (o < p.pt_cap) p.pts[o] = cp;
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { qn[1] -= n2; qhead[1] = (h2 + n2) % QCAP; }
+    __syncthreads();
+  };
+  // stage 1 on up to 128 entries of q1: the exact predicate; punctured simplices move on to q2
+  auto run_stage1 = [&]() {
+    const int n1 = min(qn[0], 128), h1 = qhead[0];
+    bool inside = false;
+    const Entry *src = &q1[(h1 + (int)threadIdx.x) % QCAP];
+    if ((int)threadIdx.x < n1) inside = test_stage<ND, 1>(p, src, nullptr);
+    push_entry(q2, 1, inside, *src);
+    __syncthreads();
+    if (threadIdx.x == 0) { qn[0] -= n1; qhead[0] = (h1 + n1) % QCAP; }
+    __syncthreads();
+  };
+
   for (u64 r = 0; r < rounds; r++) {
     const u64 cube0 = r * stride + (u64)blockIdx.x * CPB;
     // ---- gather: thread t -> (cube t / NVC, vertex mask t % NVC)
@@ -3396,28 +3512,30 @@ __global__ void __launch_bounds__(128) test_kernel(const __grid_constant__ Sweep
       }
     }
     __syncthreads();
-    // ---- test: thread t -> (cube t / ntypes, type t % ntypes)
-    bool hit = false;
-    ftkb_point cp;
+    // ---- stage 0: thread t -> (cube t / ntypes, type t % ntypes)
     {
       const int ci = threadIdx.x / ntypes, type = threadIdx.x % ntypes;
+      bool need = false;
+      Entry e;
       if (ci < CPB && cube0 + (u64)ci < ncubes && (p.has_next || mt.ordinal[type])) {
-        const int corner[3] = {ccorner[ci][0], ccorner[ci][1], ccorner[ci][2]};
-        hit = check_simplex<ND>(p, mt, corner, type, cp, vcache[ci]);
+#pragma unroll
+        for (int k = 0; k < NV; k++)
+#pragma unroll
+          for (int c = 0; c < ND; c++) e.v[k * ND + c] = vcache[ci][mt.vmask[type][k] * ND + c];
+        e.corner[0] = ccorner[ci][0]; e.corner[1] = ccorner[ci][1]; e.corner[2] = ccorner[ci][2];
+        e.type = type;
+        ftkb_point dummy;
+        need = check_simplex<ND, 0>(p, mt, e.corner, type, dummy, e.v);
       }
+      push_entry(q1, 0, need, e);
     }
-    const unsigned b = __ballot_sync(0xffffffffu, hit);
-    if (b) {
-      u64 base = 0;
-      const int leader = __ffs(b) - 1;
-      if (lane == leader) base = atomicAdd(p.pt_count, (u64)__popc(b));
-      base = __shfl_sync(0xffffffffu, base, leader);
-      if (hit) {
-        const u64 o = base + __popc(b & ((1u << lane) - 1));
-        if (o < p.pt_cap) p.pts[o] = cp;
-      }
+    __syncthreads();                                  // the queue counters are settled; the cache may be refilled
+    const bool last = r + 1 == rounds;
+    while (qn[0] >= QT || (last && qn[0] > 0)) {      // (block-uniform: the counters only change between barriers)
+      run_stage1();
+      while (qn[1] >= QT) run_stage2();
     }
-    __syncthreads();                                  // the cache is refilled by the next round
+    if (last) while (qn[1] > 0) run_stage2();
   }
   if (p.step_out == nullptr) return;
   // deferred step: the last block to finish publishes the counters to the host (mapped memory) and re-arms the

@@ -48,6 +48,11 @@ struct SweepParams {
   float thr2_f;               // 2^(1-nbits)
   float lim_f;                // 0.999 * 4.5e18 / factor^2 (determinant magnitude bound, field units)
   unsigned long long *res_slot[2];   // non-null: accumulate min non-zero |v| of that layer during the scan
+  // key filter of that accumulation (scalar build kernels): a difference d (v = d * scale of the component) whose high-word key
+  // exceeds res_thr[component] cannot lower the running minimum known when the step was enqueued; +inf: nothing is known yet.
+  // What the slot then receives is the minimum over the values under the threshold -- equal to the layer's own minimum whenever
+  // that one would lower the running minimum, which is all the tracker uses it for.
+  float res_thr[3];
   unsigned long long *poison;        // fused 3D scan: set non-zero when a scalar is NaN / Inf / >= 2^1000 (the sweep is redone unfused)
   // fused 3D scan: TMA descriptors of the two scalar layers (box = one tile plane incl. halo)
   alignas(64) CUtensorMap tmap[2];
@@ -79,6 +84,18 @@ struct SweepParams {
   int32_t test_blocks;               // grid of the test kernel (grid-stride: any worklist size is covered)
   int32_t sm_count;                  // SMs of the device (persistent kernels size their grid by it)
 };
+
+// threshold key for SweepParams::res_thr: R = running minimum of the non-zero |v| (DBL_MAX: unknown), v = d * scale
+inline float res_threshold_key(double R, double scale) {
+  if (!(R < 0x1p1000) || !(scale > 0.0)) return __builtin_inff();
+  const double T = R / scale;
+  unsigned long long bits;
+  __builtin_memcpy(&bits, &T, 8);
+  const int hi = (int)(bits >> 32) + 2;     // two key units (2^-19 relative) above T: far beyond the rounding of T and of d * scale
+  float f;
+  __builtin_memcpy(&f, &hi, 4);
+  return f;
+}
 
 void upload_mesh_tables(const DeviceMeshTables &t2, const DeviceMeshTables &t3);
 void init_kernel_attributes();   // opt-in shared memory sizes; once per device
