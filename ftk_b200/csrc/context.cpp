@@ -82,7 +82,7 @@ struct ftkb_ctx {
   // [12] the second worklist counter (deferred steps alternate), [13] ticket of the test kernel's blocks, [14] second poison flag
   unsigned long long *d_scalars = nullptr;
   unsigned long long *h_scalars = nullptr;     // pinned mirror
-  static constexpr int SLOT_WL = 8, SLOT_PT = 9, SLOT_UQ = 10, SLOT_POISON = 11, SLOT_WL2 = 12, SLOT_TICKET = 13, SLOT_POISON2 = 14, NSLOTS = 16;
+  static constexpr int SLOT_WL = 8, SLOT_PT = 9, SLOT_UQ = 10, SLOT_POISON = 11, SLOT_WL2 = 12, SLOT_TICKET = 13, SLOT_POISON2 = 14, SLOT_WORK = 15, NSLOTS = 16;
 
   // ---- deferred ("sync-free") steps ------------------------------------------------------------------------------
   // ftkb_update_timestep enqueues scan + test and returns; the test kernel's last block publishes the counters into the
@@ -92,7 +92,7 @@ struct ftkb_ctx {
   // whatever was enqueued behind it.  Layers popped in between wait in `limbo`.
   struct Pending {
     int ring = 0, evset = 0, pops = 0, nbits = 0, wl_sel = 0;
-    uint64_t seq = 0, npts_before = 0;
+    uint64_t seq = 0, npts_before = 0, pt_cap = 0;     // pt_cap: the point buffer's capacity this step ran with
     bool has_next = false;
     int res_slots[2] = {-1, -1};     // resolution slots this step's scan fills
   };
@@ -125,6 +125,8 @@ struct ftkb_ctx {
   uint64_t wl_cap = 0, last_wl = 0;
   ftkb_point *d_pts = nullptr;
   uint64_t pt_cap = 0, npts = 0;
+  uint64_t max_step_points = 0;          // most points one confirmed step has produced (sizes the buffer ahead of deferred steps)
+  std::vector<ftkb_point *> retired_pts; // point buffers replaced while steps were in flight; freed once nothing is
 
   // finalize scratch (sort keys / indices, cub temp storage, neighbour lists, union-find parents): kept between calls, grown on demand
   struct Scratch { void *p = nullptr; size_t cap = 0; };
@@ -248,6 +250,7 @@ extern "C" void ftkb_destroy(ftkb_ctx *c) {
   cudaFree(c->d_scalars);
   if (c->h_scalars) cudaFreeHost(c->h_scalars);
   if (c->grow_stage) cudaFreeHost(c->grow_stage);
+  for (ftkb_point *q : c->retired_pts) cudaFree(q);
   if (c->h_ring) cudaFreeHost(c->h_ring);
   for (auto &es : c->dev) for (auto &e : es) if (e) cudaEventDestroy(e);
   if (c->ev_input) cudaEventDestroy(c->ev_input);
@@ -648,6 +651,7 @@ static void fill_sweep_geometry(const ftkb_ctx *c, SweepParams &p) {
   p.coords = c->d_coords;
   p.nd = c->n;
   p.sm_count = c->sm_count;
+  p.work_counter = c->d_scalars + ftkb_ctx::SLOT_WORK;
   p.W = c->cfg.dims[0]; p.H = c->cfg.dims[1]; p.D = c->n == 3 ? c->cfg.dims[2] : 1;
   for (int j = 0; j < 3; j++) {
     const bool used = j < c->n;
@@ -914,6 +918,7 @@ static int grow_trajectories(ftkb_ctx *c) {
   const size_t per = host_prep ? sizeof(ftkb_point) : 8 + 4 * 9 + 1;
   if (n && c->grow_stage_cap < per * n) {
     if (c->grow_stage) cudaFreeHost(c->grow_stage);
+  for (ftkb_point *q : c->retired_pts) cudaFree(q);
     c->grow_stage = nullptr; c->grow_stage_cap = 0;
     const size_t want = per * (n + n / 2 + 1024);
     if (cudaMallocHost(&c->grow_stage, want) != cudaSuccess) { cudaGetLastError(); return fail(c, FTKB_ERR_NOMEM, "streaming grow step: out of page-locked memory"); }
@@ -1068,7 +1073,7 @@ static int confirm_front(ftkb_ctx *c) {
   // the step ran with the factor known when it was enqueued; the layers it resolved may have lowered the running minimum
   // (critical_point_tracker.hh:850-864) -- then it, and whatever was enqueued behind it, is redone with the right factor
   const bool stale = nbits_of(c->resolution) != pd.nbits;
-  if (poison || stale || nwl > c->wl_cap || npt > c->pt_cap) return replay(c, poison);
+  if (poison || stale || nwl > c->wl_cap || npt > pd.pt_cap) return replay(c, poison);
   c->nbits = pd.nbits;
   c->factor = (double)(uint64_t)(1 << pd.nbits);
   float ms_scan = 0, ms_test = 0;
@@ -1097,6 +1102,7 @@ static int confirm_front(ftkb_ctx *c) {
   c->wl_hint = nwl;
   c->stats.simplices_tested += c->ncore * (uint64_t)(c->n_ord + (pd.has_next ? c->n_int : 0));
   if (npt != c->npts) { c->sorted = false; c->traced = false; }
+  if (npt > c->npts) c->max_step_points = std::max(c->max_step_points, npt - c->npts);
   c->npts = npt;
   c->stats.points = npt;
   for (int j = 0; j < pd.pops && !c->limbo.empty(); j++) {
@@ -1114,6 +1120,32 @@ static int drain(ftkb_ctx *c) {
     const int rc = confirm_front(c);
     if (rc) return rc;
   }
+  if (!c->retired_pts.empty()) {
+    CK(cudaStreamSynchronize(c->stream));          // the copy out of a retired buffer is stream-ordered
+    for (ftkb_point *q : c->retired_pts) cudaFree(q);
+    c->retired_pts.clear();
+  }
+  return FTKB_OK;
+}
+
+// Deferred steps: grow the point buffer BEFORE a step can overflow it -- an overflow is only noticed one step later and costs a
+// drain and a replay of everything in flight.  The steps in flight keep the old buffer; the copy into the new one is ordered
+// behind their test kernels, the old buffer is freed at the next drain (cudaFree would synchronise the device here).
+static int grow_points_ahead(ftkb_ctx *c) {
+  const uint64_t per = c->max_step_points;
+  if (!per) return FTKB_OK;
+  const uint64_t need = c->npts + (c->pend.size() + 2) * (per + per / 2);
+  if (need <= c->pt_cap) return FTKB_OK;
+  uint64_t cap = c->pt_cap;
+  while (cap < need) cap *= 2;
+  if (cap >= 0xffffffffull) return FTKB_OK;          // (the overflow path reports it)
+  ftkb_point *np = nullptr;
+  if (cudaMalloc(&np, sizeof(ftkb_point) * cap) != cudaSuccess) { cudaGetLastError(); return FTKB_OK; }   // the overflow path will say so if it matters
+  if (!c->pend.empty()) CK(cudaStreamWaitEvent(c->stream, c->dev[c->pend.back().evset][2], 0));
+  CK(cudaMemcpyAsync(np, c->d_pts, sizeof(ftkb_point) * c->pt_cap, cudaMemcpyDeviceToDevice, c->stream));
+  c->retired_pts.push_back(c->d_pts);
+  c->d_pts = np;
+  c->pt_cap = cap;
   return FTKB_OK;
 }
 
@@ -1274,7 +1306,9 @@ static int update_impl(ftkb_ctx *c, bool allow_defer) {
       }
     pd.wl_sel = c->wl_sel;
     p.wl = c->wl_sel ? c->d_wl2 : c->d_wl; p.wl_cap = c->wl_cap;
+    { const int rcg = grow_points_ahead(c); if (rcg) return rcg; }
     p.pts = c->d_pts; p.pt_cap = c->pt_cap;
+    pd.pt_cap = c->pt_cap;
     // worklist, its counter and the poison flag alternate between two sets: the test kernel of this step may still run
     // (on stream2) while the scan of the next step fills the other set; each test kernel re-arms its own set when done
     p.wl_count = c->d_scalars + (c->wl_sel ? ftkb_ctx::SLOT_WL2 : ftkb_ctx::SLOT_WL);

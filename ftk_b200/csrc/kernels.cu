@@ -1414,7 +1414,113 @@ __global__ void __launch_bounds__((C2_CW + 1) * 32, K2_CTAS) scan2d_keys_build_k
   if (!(acc.big < __int_as_float(KEYF_BIG))) atomicExch(p.poison, 1ull);
 }
 
-static size_t k2_smem_bytes(int nst) { return (size_t)nst * K2_STAGE_BYTES + (size_t)2 * nst * 8 + (size_t)16 * (C2_CW + 1) * 32; }
+// Persistent variant (FTKB_K2_PERSIST=1): K2_CTAS CTAs per SM for the whole launch; the producer warp draws (tile, chunk) items
+// from a device counter (same order as the grid of the kernel above, so CTAs that run together still read neighbouring pieces of
+// the same rows) and streams their rows back to back through the ring -- the ring never drains between chunks and nobody waits
+// for a last, partly filled wave.  The first stage of every item carries the item's number (stage_item[slot], written before the
+// stage is armed); a negative number ends the consumers.  Consumer warps whose strip lies outside the array still take part in
+// the barrier protocol, so the ring's arrival counts are the same for every item.  The last CTA out re-arms the counter.
+template <int NPREV, bool TEST, int K2_CTAS, int K2_NST>
+__global__ void __launch_bounds__((C2_CW + 1) * 32, K2_CTAS) scan2d_keys_persist_kernel(const __grid_constant__ SweepParams p) {
+  extern __shared__ __align__(128) unsigned char fb_smem[];
+  const int lane = threadIdx.x & 31;
+  const int wib = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);     // warp-uniform by construction
+  const uint32_t ring0 = smem_u32(fb_smem);
+  const uint32_t full0 = ring0 + (uint32_t)K2_NST * K2_STAGE_BYTES, empty0 = full0 + 8u * K2_NST;
+  const uint32_t res_u32 = empty0 + 8u * K2_NST + 16u * threadIdx.x;
+  const uint32_t item0 = empty0 + 8u * K2_NST + 16u * (C2_CW + 1) * 32u;   // int stage_item[K2_NST]
+  const int W = p.W, H = p.H;
+  unsigned int *wc = reinterpret_cast<unsigned int *>(p.work_counter);     // [0] next item, [1] CTAs that are done
+  const int total = p.nsx * p.nsy;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int q = 0; q < K2_NST; q++) { mbar_init(full0 + 8u * q, 1); mbar_init(empty0 + 8u * q, (uint32_t)C2_CW); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  if (wib == C2_CW) {
+    if (elect_one()) {
+      const double *S = p.L[p.build_layer].S;
+      uint32_t gs = 0;
+      int item = (int)atomicAdd(&wc[0], 1u);
+      while (true) {
+        const uint32_t slot0 = gs % K2_NST;
+        if (gs >= K2_NST) mbar_wait(empty0 + 8u * slot0, ((gs / K2_NST) - 1u) & 1u);
+        if (item >= total) {
+          asm volatile("st.shared.s32 [%0], %1;" ::"r"(item0 + 4u * slot0), "r"(-1) : "memory");
+          mbar_arrive(full0 + 8u * slot0);
+          break;
+        }
+        asm volatile("st.shared.s32 [%0], %1;" ::"r"(item0 + 4u * slot0), "r"(item) : "memory");
+        const int bx = item % p.nsx, cy = item / p.nsx;
+        const int next = (int)atomicAdd(&wc[0], 1u);      // its latency hides behind this item's copies
+        const int C0 = bx * (C2_CW * FB_STRIDE);
+        const int r0 = cy * p.rows, r1 = min(r0 + p.rows - 1, H - 1);
+        const int nstages = ((r1 + 1) - r0 + 1 + 2 + K2_R - 1) / K2_R;
+        const int col_lo = max(C0 - 2, 0), col_hi = min(C0 - 2 + TL_SEG, W);
+        const uint32_t seg_bytes = (uint32_t)(col_hi - col_lo) * 8u;
+        const uint32_t dst0 = ring0 + (uint32_t)(col_lo - (C0 - 2)) * 8u;
+        for (int st = 0; st < nstages; st++, gs++) {
+          const uint32_t slot = gs % K2_NST;
+          if (st > 0 && gs >= K2_NST) mbar_wait(empty0 + 8u * slot, ((gs / K2_NST) - 1u) & 1u);
+          mbar_expect_tx(full0 + 8u * slot, seg_bytes * K2_R);
+#pragma unroll
+          for (int i = 0; i < K2_R; i++) {
+            const size_t off = (size_t)W * (size_t)clampi(r0 - 1 + K2_R * st + i, H) + (size_t)col_lo;
+            bulk_g2s(dst0 + slot * K2_STAGE_BYTES + (uint32_t)i * K2_ROW_BYTES, S + off, seg_bytes, full0 + 8u * slot);
+          }
+        }
+        item = next;
+      }
+    }
+    return;
+  }
+  K2Acc acc{DBL_MAX, DBL_MAX, 0.f};
+  sts64_f64(res_u32, DBL_MAX); sts64_f64(res_u32 + 8u, DBL_MAX);
+  uint32_t gs = 0;
+  while (true) {
+    const uint32_t slot = gs % K2_NST;
+    mbar_wait(full0 + 8u * slot, (gs / K2_NST) & 1u);
+    int item;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(item) : "r"(item0 + 4u * slot) : "memory");
+    if (item < 0) break;
+    const int bx = item % p.nsx, cy = item / p.nsx;
+    const int C0 = bx * (C2_CW * FB_STRIDE);
+    const int r0 = cy * p.rows, r1 = min(r0 + p.rows - 1, H - 1);
+    const int nstages = ((r1 + 1) - r0 + 1 + 2 + K2_R - 1) / K2_R;
+    const int nactive = min(C2_CW, (W - C0 + FB_STRIDE - 1) / FB_STRIDE);
+    if (wib >= nactive) {
+      for (int st = 0; st < nstages; st++) {
+        const uint32_t g2 = gs + (uint32_t)st, sl = g2 % K2_NST;
+        mbar_wait(full0 + 8u * sl, (g2 / K2_NST) & 1u);
+        __syncwarp();
+        if (elect_one()) mbar_arrive(empty0 + 8u * sl);
+      }
+    } else {
+      const int c0 = C0 + wib * FB_STRIDE;
+      const uint32_t tile_u32 = ring0 + (uint32_t)(wib * FB_STRIDE) * 8u;
+      const bool border = c0 == 0 || c0 + FB_SEG - 2 > W;
+      if (border) acc = keys2d_strip<true, NPREV, TEST, K2_NST>(p, c0, r0, r1, lane, tile_u32, full0, empty0, bx * C2_CW + wib, gs, res_u32, acc);
+      else acc = keys2d_strip<false, NPREV, TEST, K2_NST>(p, c0, r0, r1, lane, tile_u32, full0, empty0, bx * C2_CW + wib, gs, res_u32, acc);
+    }
+    gs += (uint32_t)nstages;
+  }
+  if (p.res_slot[p.build_layer] != nullptr) {
+    const double cw = (double)(W - 1), ch = (double)(H - 1);
+    const double ax = fabs(acc.mdx), ay = fabs(acc.mdy);
+    const double vx = ax < DBL_MAX ? ax * cw : DBL_MAX, vy = ay < DBL_MAX ? ay * ch : DBL_MAX;
+    warp_res_commit(fmin(vx > 0.0 ? vx : DBL_MAX, vy > 0.0 ? vy : DBL_MAX), p.res_slot[p.build_layer]);
+  }
+  if (!(acc.big < __int_as_float(KEYF_BIG))) atomicExch(p.poison, 1ull);
+  if (threadIdx.x == 0) {
+    // every CTA's producer has drawn its last item before its consumers saw the end marker: the last CTA out may re-arm
+    __threadfence();
+    if (atomicAdd(&wc[1], 1u) == gridDim.x - 1) { wc[0] = 0u; wc[1] = 0u; __threadfence(); }
+  }
+}
+
+static size_t k2_smem_bytes(int nst) { return (size_t)nst * K2_STAGE_BYTES + (size_t)2 * nst * 8 + (size_t)16 * (C2_CW + 1) * 32 + (size_t)4 * nst; }
 // FTKB_K2_CTAS (CTAs per SM: 2 | 3 | 4, default 3) and FTKB_K2_NST (ring stages at three CTAs per SM: 4 | 5 | 6, default 4)
 static int k2_variant() {
   static const int v = [] {
@@ -1426,9 +1532,22 @@ static int k2_variant() {
   }();
   return v;
 }
+static bool k2_persistent() {
+  static const bool v = [] { const char *e = std::getenv("FTKB_K2_PERSIST"); return e && std::atoi(e) != 0; }();
+  return v;
+}
 template <int CTAS, int NST>
 static void k2_launch(const SweepParams &p, unsigned grid, cudaStream_t s) {
   const size_t sm = k2_smem_bytes(NST);
+  if (CTAS == 3 && NST == 4 && k2_persistent() && p.work_counter) {
+    const unsigned pgrid = std::min<unsigned>(grid, (unsigned)(CTAS * (p.sm_count > 0 ? p.sm_count : 148)));
+    switch (p.sum_mode) {
+      case SUM_BUILD: scan2d_keys_persist_kernel<0, false, 3, 4><<<pgrid, (C2_CW + 1) * 32, sm, s>>>(p); break;
+      case SUM_BUILD_TEST1: scan2d_keys_persist_kernel<0, true, 3, 4><<<pgrid, (C2_CW + 1) * 32, sm, s>>>(p); break;
+      default: scan2d_keys_persist_kernel<1, true, 3, 4><<<pgrid, (C2_CW + 1) * 32, sm, s>>>(p); break;
+    }
+    return;
+  }
   switch (p.sum_mode) {
     case SUM_BUILD: scan2d_keys_build_kernel<0, false, CTAS, NST><<<grid, (C2_CW + 1) * 32, sm, s>>>(p); break;
     case SUM_BUILD_TEST1: scan2d_keys_build_kernel<0, true, CTAS, NST><<<grid, (C2_CW + 1) * 32, sm, s>>>(p); break;
@@ -1441,6 +1560,11 @@ static void k2_attrs() {
   cudaFuncSetAttribute(scan2d_keys_build_kernel<0, false, CTAS, NST>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
   cudaFuncSetAttribute(scan2d_keys_build_kernel<0, true, CTAS, NST>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
   cudaFuncSetAttribute(scan2d_keys_build_kernel<1, true, CTAS, NST>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+  if (CTAS == 3 && NST == 4) {
+    cudaFuncSetAttribute(scan2d_keys_persist_kernel<0, false, 3, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+    cudaFuncSetAttribute(scan2d_keys_persist_kernel<0, true, 3, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+    cudaFuncSetAttribute(scan2d_keys_persist_kernel<1, true, 3, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+  }
 }
 
 static size_t c2_smem_bytes() { return (size_t)C2_NST * TL_SEG * 8 + (size_t)2 * C2_NST * 8; }
@@ -3204,12 +3328,8 @@ __device__ __forceinline__ int sos_rank(const SweepParams &p, const int *v /* ND
 }
 
 // vcache: the cube's 2^(ND+1) vertex vectors, [vertex mask][component], gathered once per cube by the block (test_kernel)
-// STAGE 0: validity + cheap exact exclusion ("does the simplex need the predicate at all"); STAGE 1: the predicate (exact
-// origin-in-simplex, or the non-robust barycentric test); STAGE 2: interpolation, Jacobian, type -> the record (assumes 0 and 1
-// passed).  vin: the simplex's vertex vectors, vin[k * ND + c].  The stages recompute the few quantities they share (vertex
-// coordinates, quantised values, SoS ranks): cheaper than carrying them through the block's queues.
-template <int ND, int STAGE>
-__device__ bool check_simplex(const SweepParams &p, const DeviceMeshTables &mt, const int corner[3], int type, ftkb_point &cp, const double *vin) {
+template <int ND>
+__device__ bool check_simplex(const SweepParams &p, const DeviceMeshTables &mt, const int corner[3], int type, ftkb_point &cp, const double *vcache) {
   constexpr int NV = ND + 1;
   int vt[NV][ND + 1];
   const LayerPtrs *L[NV];
@@ -3234,11 +3354,11 @@ __device__ bool check_simplex(const SweepParams &p, const DeviceMeshTables &mt, 
 #pragma unroll
   for (int k = 0; k < NV; k++)
 #pragma unroll
-    for (int c = 0; c < ND; c++) v[k][c] = vin[k * ND + c];
+    for (int c = 0; c < ND; c++) v[k][c] = vcache[mt.vmask[type][k] * ND + c];
 
   double mu[NV];
   bool inside = false;
-  if constexpr (ND == 3) { if (STAGE != 0) inside = inverse_lerp3(v, mu); }
+  if constexpr (ND == 3) inside = inverse_lerp3(v, mu);
 
   i64 vf[NV][ND];
   int rank[NV];
@@ -3250,13 +3370,11 @@ __device__ bool check_simplex(const SweepParams &p, const DeviceMeshTables &mt, 
         if (isnan(v[k][c]) || isinf(v[k][c])) return false;
         vf[k][c] = quantise(v[k][c], p.factor);
       }
-    if (STAGE != 0) {
 #pragma unroll
-      for (int k = 0; k < NV; k++) rank[k] = sos_rank<ND>(p, vt[k]);
-    }
+    for (int k = 0; k < NV; k++) rank[k] = sos_rank<ND>(p, vt[k]);
     // cheap exact exclusion on the quantised integers before the full cascade: one strictly
     // signed component, with magnitudes small enough that no determinant can leave int64
-    if (STAGE == 0) {
+    {
       const i64 lim = ND == 2 ? (1ll << 29) : (1ll << 19);
       bool small = true, sided = false;
 #pragma unroll
@@ -3270,12 +3388,11 @@ __device__ bool check_simplex(const SweepParams &p, const DeviceMeshTables &mt, 
         }
         sided = sided || pos || neg;
       }
-      return !(small && sided);
+      if (small && sided) return false;
     }
-    if (STAGE == 1) return origin_in_simplex<NV, ND>(vf, rank);
+    if (!origin_in_simplex<NV, ND>(vf, rank)) return false;
   } else {
-    if (STAGE == 0) return true;
-    if (STAGE == 1) return inside;
+    if (!inside) return false;
   }
 
   if constexpr (ND == 2) {
@@ -3399,88 +3516,20 @@ __device__ bool check_simplex(const SweepParams &p, const DeviceMeshTables &mt, 
 
 // A block works on CPB surviving cubes per round: first the 2^(ND+1) vertices of every cube are gathered (the vector field
 // read or derived ONCE per vertex -- a vertex is shared by up to 9 / 36 simplices of its cube), then one thread per
-// (cube, simplex type) runs the cheap exclusion (stage 0).  What survives goes into a shared-memory queue (the simplex's vertex
-// vectors, corner, type); whenever a queue holds a block's worth of entries the next stage runs on it with every lane busy:
-// stage 1 = the exact predicate, stage 2 = interpolation / Jacobian / type of the punctured simplices.  On feature-dense fields
-// (1e6 surviving cubes per step) a warp of 32 (cube, type) pairs almost always holds one that needs the long path; without the
-// queues all 32 lanes would walk it.
-template <int ND>
-struct TestQueueEntry {
-  double v[(ND + 1) * ND];
-  int corner[3];
-  int type;
-};
-// the long stages as functions of their own: the kernel's register budget is then the largest stage's, not the sum
-template <int ND, int STAGE>
-__device__ __noinline__ bool test_stage(const SweepParams &p, const TestQueueEntry<ND> *e, ftkb_point *cp) {
-  return check_simplex<ND, STAGE>(p, c_mesh[ND - 2], e->corner, e->type, *cp, e->v);
-}
-
+// (cube, simplex type) runs the exact test on the cached vectors.
 template <int ND>
 __global__ void __launch_bounds__(128) test_kernel(const __grid_constant__ SweepParams p) {
   const DeviceMeshTables &mt = c_mesh[ND - 2];
   constexpr int ntypes = ND == 2 ? 12 : 60;
-  constexpr int NV = ND + 1;
   constexpr int NVC = 1 << (ND + 1);                  // vertices of a space-time cube
   constexpr int CPB = 128 / ntypes;                   // cubes per block and round (10 in 2D, 2 in 3D)
-  constexpr int QT = ND == 2 ? 128 : 64;              // a queue is drained in batches of up to 128 while it holds at least QT entries
-  constexpr int QCAP = QT + 128;                      // (at most QT - 1 left behind + at most 128 pushed by one batch of the stage before)
-  using Entry = TestQueueEntry<ND>;
   __shared__ double vcache[CPB][NVC * ND];
   __shared__ int ccorner[CPB][3];
-  __shared__ Entry q1[QCAP], q2[QCAP];
-  __shared__ int qn[2], qhead[2];                     // entries / first entry of q1, q2 (rings)
   u64 ncubes = *p.wl_count;
   if (ncubes > p.wl_cap) ncubes = p.wl_cap;
   const u64 stride = (u64)gridDim.x * CPB;
   const u64 rounds = (ncubes + stride - 1) / stride;
   const int lane = threadIdx.x & 31;
-  if (threadIdx.x < 2) { qn[threadIdx.x] = 0; qhead[threadIdx.x] = 0; }
-  __syncthreads();
-
-  // append `e` to queue q (ring of QCAP entries) for the lanes with `push`
-  auto push_entry = [&](Entry *q, const int which, const bool push, const Entry &e) {
-    const unsigned b = __ballot_sync(0xffffffffu, push);
-    if (!b) return;
-    int base = 0;
-    const int leader = __ffs(b) - 1;
-    if (lane == leader) base = atomicAdd(&qn[which], __popc(b));
-    base = __shfl_sync(0xffffffffu, base, leader);
-    if (push) q[(qhead[which] + base + __popc(b & ((1u << lane) - 1))) % QCAP] = e;
-  };
-  // stage 2 on up to 128 entries of q2: the records of punctured simplices
-  auto run_stage2 = [&]() {
-    const int n2 = min(qn[1], 128), h2 = qhead[1];
-    bool hit = false;
-    ftkb_point cp;
-    if ((int)threadIdx.x < n2) hit = test_stage<ND, 2>(p, &q2[(h2 + (int)threadIdx.x) % QCAP], &cp);
-    const unsigned b = __ballot_sync(0xffffffffu, hit);
-    if (b) {
-      u64 base = 0;
-      const int leader = __ffs(b) - 1;
-      if (lane == leader) base = atomicAdd(p.pt_count, (u64)__popc(b));
-      base = __shfl_sync(0xffffffffu, base, leader);
-      if (hit) {
-        const u64 o = base + __popc(b & ((1u << lane) - 1));
-        if (o < p.pt_cap) p.pts[o] = cp;
-      }
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) { qn[1] -= n2; qhead[1] = (h2 + n2) % QCAP; }
-    __syncthreads();
-  };
-  // stage 1 on up to 128 entries of q1: the exact predicate; punctured simplices move on to q2
-  auto run_stage1 = [&]() {
-    const int n1 = min(qn[0], 128), h1 = qhead[0];
-    bool inside = false;
-    const Entry *src = &q1[(h1 + (int)threadIdx.x) % QCAP];
-    if ((int)threadIdx.x < n1) inside = test_stage<ND, 1>(p, src, nullptr);
-    push_entry(q2, 1, inside, *src);
-    __syncthreads();
-    if (threadIdx.x == 0) { qn[0] -= n1; qhead[0] = (h1 + n1) % QCAP; }
-    __syncthreads();
-  };
-
   for (u64 r = 0; r < rounds; r++) {
     const u64 cube0 = r * stride + (u64)blockIdx.x * CPB;
     // ---- gather: thread t -> (cube t / NVC, vertex mask t % NVC)
@@ -3512,30 +3561,28 @@ __global__ void __launch_bounds__(128) test_kernel(const __grid_constant__ Sweep
       }
     }
     __syncthreads();
-    // ---- stage 0: thread t -> (cube t / ntypes, type t % ntypes)
+    // ---- test: thread t -> (cube t / ntypes, type t % ntypes)
+    bool hit = false;
+    ftkb_point cp;
     {
       const int ci = threadIdx.x / ntypes, type = threadIdx.x % ntypes;
-      bool need = false;
-      Entry e;
       if (ci < CPB && cube0 + (u64)ci < ncubes && (p.has_next || mt.ordinal[type])) {
-#pragma unroll
-        for (int k = 0; k < NV; k++)
-#pragma unroll
-          for (int c = 0; c < ND; c++) e.v[k * ND + c] = vcache[ci][mt.vmask[type][k] * ND + c];
-        e.corner[0] = ccorner[ci][0]; e.corner[1] = ccorner[ci][1]; e.corner[2] = ccorner[ci][2];
-        e.type = type;
-        ftkb_point dummy;
-        need = check_simplex<ND, 0>(p, mt, e.corner, type, dummy, e.v);
+        const int corner[3] = {ccorner[ci][0], ccorner[ci][1], ccorner[ci][2]};
+        hit = check_simplex<ND>(p, mt, corner, type, cp, vcache[ci]);
       }
-      push_entry(q1, 0, need, e);
     }
-    __syncthreads();                                  // the queue counters are settled; the cache may be refilled
-    const bool last = r + 1 == rounds;
-    while (qn[0] >= QT || (last && qn[0] > 0)) {      // (block-uniform: the counters only change between barriers)
-      run_stage1();
-      while (qn[1] >= QT) run_stage2();
+    const unsigned b = __ballot_sync(0xffffffffu, hit);
+    if (b) {
+      u64 base = 0;
+      const int leader = __ffs(b) - 1;
+      if (lane == leader) base = atomicAdd(p.pt_count, (u64)__popc(b));
+      base = __shfl_sync(0xffffffffu, base, leader);
+      if (hit) {
+        const u64 o = base + __popc(b & ((1u << lane) - 1));
+        if (o < p.pt_cap) p.pts[o] = cp;
+      }
     }
-    if (last) while (qn[1] > 0) run_stage2();
+    __syncthreads();                                  // the cache is refilled by the next round
   }
   if (p.step_out == nullptr) return;
   // deferred step: the last block to finish publishes the counters to the host (mapped memory) and re-arms the
