@@ -117,6 +117,7 @@ struct ftkb_ctx {
   cudaEvent_t dbg_prev = nullptr; bool dbg_prev_valid = false;
   double host_wait_us = 0, host_enq_us = 0; uint64_t host_wait_n = 0, host_enq_n = 0;
   bool overlap_test = true;          // FTKB_TEST_OVERLAP=0: test kernels stay on the sweep's stream
+  bool last_test_overlapped = false; // where the previous deferred step's test kernel went
   bool has_producer = false;
 
   unsigned long long *d_wl = nullptr;          // worklist of the synchronous steps and of the even deferred ones
@@ -1342,8 +1343,15 @@ static int update_impl(ftkb_ctx *c, bool allow_defer) {
     }
     launch_cells(p, c->stream);
     CK(cudaEventRecord(c->dev[pd.evset][1], c->stream));
-    cudaStream_t ts = c->overlap_test ? c->stream2 : c->stream;
-    if (c->overlap_test) CK(cudaStreamWaitEvent(c->stream2, c->dev[pd.evset][1], 0));
+    // a test kernel with a GPU's worth of work (feature-dense fields: 1e5 .. 1e6 surviving cubes) gains nothing next to the
+    // following scan -- the two take turns on the SMs, measured 0.90 .. 1.64 ms per step against 0.95 in a row -- so only
+    // the small, latency-bound ones go to the second stream
+    const bool overlap = c->overlap_test && c->wl_hint < 100000;
+    if (!overlap && c->last_test_overlapped && !c->pend.empty())
+      CK(cudaStreamWaitEvent(c->stream, c->dev[c->pend.back().evset][2], 0));     // test kernels share one ticket counter: never two at once
+    c->last_test_overlapped = overlap;
+    cudaStream_t ts = overlap ? c->stream2 : c->stream;
+    if (overlap) CK(cudaStreamWaitEvent(c->stream2, c->dev[pd.evset][1], 0));
     launch_test(p, ts);
     CK(cudaEventRecord(c->dev[pd.evset][2], ts));
     c->stats.kernel_launches += 2;

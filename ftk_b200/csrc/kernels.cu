@@ -122,6 +122,41 @@ __device__ __forceinline__ void append_survivors(const SweepParams &p, bool surv
   }
 }
 
+// Survivors staged per warp in shared memory and appended WL_STAGE_CAP at a time: on feature-dense fields (1e6 surviving cubes per
+// step) one atomicAdd per pass of the cold path -- all on the same counter -- is what the scan waits for.
+// stage (shared-memory address, 8-byte aligned): u32 count, pad, then WL_STAGE_CAP u64 entries; one per warp.
+constexpr int WL_STAGE_CAP = 64;
+constexpr uint32_t WL_STAGE_BYTES = 8u + 8u * WL_STAGE_CAP;
+__device__ __forceinline__ void flush_survivors(const SweepParams &p, const uint32_t stage) {
+  const int lane = threadIdx.x & 31;
+  int cnt;
+  asm volatile("ld.shared.s32 %0, [%1];" : "=r"(cnt) : "r"(stage) : "memory");
+  if (cnt == 0) return;                                         // (warp-uniform)
+  u64 base = 0;
+  if (lane == 0) base = atomicAdd(p.wl_count, (u64)cnt);
+  base = __shfl_sync(0xffffffffu, base, 0);
+  for (int i = lane; i < cnt; i += 32) {
+    u64 lin;
+    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(lin) : "r"(stage + 8u + 8u * (uint32_t)i) : "memory");
+    if (base + (u64)i < p.wl_cap) p.wl[base + (u64)i] = lin;
+  }
+  __syncwarp();
+  if (lane == 0) asm volatile("st.shared.s32 [%0], %1;" ::"r"(stage), "r"(0) : "memory");
+  __syncwarp();
+}
+__device__ __forceinline__ void stage_survivors(const SweepParams &p, const uint32_t stage, const bool surv, const u64 lin) {
+  const unsigned b = __ballot_sync(0xffffffffu, surv);
+  if (b == 0) return;
+  const int lane = threadIdx.x & 31, n = __popc(b);
+  int cnt;
+  asm volatile("ld.shared.s32 %0, [%1];" : "=r"(cnt) : "r"(stage) : "memory");
+  if (cnt + n > WL_STAGE_CAP) { flush_survivors(p, stage); cnt = 0; }
+  if (surv) asm volatile("st.shared.u64 [%0], %1;" ::"r"(stage + 8u + 8u * (uint32_t)(cnt + __popc(b & ((1u << lane) - 1)))), "l"(lin) : "memory");
+  __syncwarp();
+  if (lane == 0) asm volatile("st.shared.s32 [%0], %1;" ::"r"(stage), "r"(cnt + n) : "memory");
+  __syncwarp();
+}
+
 // ---- 2D: one warp owns a strip of 32 vertex columns (31 corners) and marches along y -------------
 template <bool HAS_NEXT>
 __global__ void __launch_bounds__(256) scan2d_kernel(const SweepParams p) {
@@ -898,7 +933,8 @@ __device__ __forceinline__ size_t cells2d_index(const SweepParams &p, const int 
 // cold path: for every lane whose cell union failed (bit set in failmask), the WARP tests that lane's 2 x C2_R cubes,
 // one lane per cube: ranges over the vertices valid simplices can use (<= ub) from global memory, gradient exactly
 // as gradient2D indexes it (clamped at the array border); survivors are appended.
-__device__ __noinline__ void cells2d_slow_cubes(const SweepParams &p, unsigned failmask, const int c0, const int y0, const int nl, const int nrows) {
+template <int NL>
+__device__ __forceinline__ void cells2d_slow_cubes_t(const SweepParams &p, unsigned failmask, const int c0, const int y0, const int nrows, const uint32_t stage) {
   static_assert(2 * C2_R <= 32, "one lane per cube");
   const int W = p.W, H = p.H;
   const int lane = threadIdx.x & 31;
@@ -914,23 +950,48 @@ __device__ __noinline__ void cells2d_slow_cubes(const SweepParams &p, unsigned f
     const int r = within >> 1, q = within & 1;
     const int x = c0 + 2 * src + q, y = y0 + r;
     const bool in = live && x >= p.lb[0] && x <= p.ub[0] && y >= p.lb[1] && y <= p.ub[1];
+    // the cube's 3 x 3 (+ corners unused) stencil footprint: columns x-1 .. x+2, rows y-1 .. y+2, clamped like gradient2D clamps
+    // them; every load of a layer is issued before the first one is used (a pass is one round trip to L2 per layer, not sixteen)
+    const int xs[4] = {clampi(x - 1, W), clampi(x, W), clampi(x + 1, W), clampi(x + 2, W)};
+    size_t rows_[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) rows_[k] = (size_t)W * (size_t)clampi(y - 1 + k, H);
     FRange rx{nanf_, nanf_}, ry{nanf_, nanf_};
 #pragma unroll
-    for (int v = 0; v < 4; v++) {
-      const int vx = x + (v & 1), vy = y + (v >> 1);
-      if (!in || vx > p.ub[0] || vy > p.ub[1]) continue;
-      const size_t row = (size_t)W * (size_t)vy;
-      for (int L = 0; L < nl; L++) {
-        const double *S = p.L[L].S;
-        const double dx = __ldg(S + row + clampi(vx + 1, W)) - __ldg(S + row + clampi(vx - 1, W));
-        const double dy = __ldg(S + (size_t)W * (size_t)clampi(vy + 1, H) + vx) - __ldg(S + (size_t)W * (size_t)clampi(vy - 1, H) + vx);
+    for (int L = 0; L < NL; L++) {
+      const double *S = p.L[L].S;
+      // h[j][k] = S(clamp(x - 1 + k), clamp(y + j)), lo / hi[i] = S(clamp(x + i), clamp(y - 1)) / S(clamp(x + i), clamp(y + 2)):
+      // d/dx at vertex (x + i, y + j) = h[j][i + 2] - h[j][i], d/dy = (row y + j + 1) - (row y + j - 1) at column x + i
+      double h[2][4], lo[2], hi[2];
+#pragma unroll
+      for (int j = 0; j < 2; j++)
+#pragma unroll
+        for (int k = 0; k < 4; k++) h[j][k] = __ldg(S + rows_[1 + j] + xs[k]);
+#pragma unroll
+      for (int i = 0; i < 2; i++) { lo[i] = __ldg(S + rows_[0] + xs[1 + i]); hi[i] = __ldg(S + rows_[3] + xs[1 + i]); }
+#pragma unroll
+      for (int v = 0; v < 4; v++) {
+        const int i = v & 1, j = v >> 1;
+        if (!in || x + i > p.ub[0] || y + j > p.ub[1]) continue;
+        const double dx = h[j][i + 2] - h[j][i];
+        const double dy = (j == 0 ? h[1][i + 1] : hi[i]) - (j == 0 ? lo[i] : h[0][i + 1]);
         const float fx = __double2float_rn(dx) * cwf, fy = __double2float_rn(dy) * chf;
         rx = fmerge(rx, FRange{fx, fx}); ry = fmerge(ry, FRange{fy, fy});
       }
     }
     const bool surv = in && !cube_excluded2_f(rx, ry, p.thrp_f, p.thr2_f, p.lim_f);
-    append_survivors(p, surv, (u64)(x - p.lb[0]) + (u64)p.nc[0] * (u64)(y - p.lb[1]));
+    const u64 lin = (u64)(x - p.lb[0]) + (u64)p.nc[0] * (u64)(y - p.lb[1]);
+    if (stage) stage_survivors(p, stage, surv, lin);          // (warp-uniform)
+    else append_survivors(p, surv, lin);
   }
+}
+// cold path: for every lane whose cell union failed (bit set in failmask), the WARP tests that lane's 2 x C2_R cubes,
+// one lane per cube: ranges over the vertices valid simplices can use (<= ub) from global memory, gradient exactly
+// as gradient2D indexes it (clamped at the array border); survivors are appended.
+// stage: shared-memory staging of this warp's survivors (flushed by the caller at the end), or 0: append directly
+__device__ __noinline__ void cells2d_slow_cubes(const SweepParams &p, unsigned failmask, const int c0, const int y0, const int nl, const int nrows, const uint32_t stage = 0) {
+  if (nl == 1) cells2d_slow_cubes_t<1>(p, failmask, c0, y0, nrows, stage);
+  else cells2d_slow_cubes_t<2>(p, failmask, c0, y0, nrows, stage);
 }
 
 // union of the cells of all layers for one block -> excluded, or the cold path
@@ -1177,6 +1238,7 @@ __device__ __forceinline__ K2Acc keys2d_strip(const SweepParams &p, const int c0
                                            const uint32_t full0, const uint32_t empty0, const int strip,
                                            const uint32_t sbase /* ring stages this CTA has consumed before this segment */,
                                            const uint32_t res_u32 /* smem: this thread's {min dx, min dy}; only the rare exact path touches them */,
+                                           const uint32_t wl_stage /* smem: this warp's survivor staging (empty on entry and on exit) */,
                                            const K2Acc acc) {
   float big = acc.big;
   const int W = p.W, H = p.H, B = p.build_layer;
@@ -1346,8 +1408,9 @@ __device__ __forceinline__ K2Acc keys2d_strip(const SweepParams &p, const int c0
     for (int b = 0; b < 64; b++) {
       if (!__any_sync(0xffffffffu, (failbits >> b) != 0)) break;
       const unsigned fm = __ballot_sync(0xffffffffu, (failbits >> b) & 1ull);
-      if (fm) cells2d_slow_cubes(p, fm, c0, (kb0 + b) * C2_R, NPREV + 1, C2_R);
+      if (fm) cells2d_slow_cubes(p, fm, c0, (kb0 + b) * C2_R, NPREV + 1, C2_R, wl_stage);
     }
+    flush_survivors(p, wl_stage);
   }
   return K2Acc{lds64_f64(res_u32), lds64_f64(res_u32 + 8u), big};
 }
@@ -1361,6 +1424,7 @@ __global__ void __launch_bounds__((C2_CW + 1) * 32, K2_CTAS) scan2d_keys_build_k
   const uint32_t ring0 = smem_u32(fb_smem);
   const uint32_t full0 = ring0 + (uint32_t)K2_NST * K2_STAGE_BYTES, empty0 = full0 + 8u * K2_NST;
   const uint32_t res_u32 = empty0 + 8u * K2_NST + 16u * threadIdx.x;
+  const uint32_t wl_stage = empty0 + 8u * K2_NST + 16u * (C2_CW + 1) * 32u + 32u + WL_STAGE_BYTES * (uint32_t)wib;
   const int W = p.W, H = p.H;
   const int bx = blockIdx.x % p.nsx, cy = blockIdx.x / p.nsx;
   const int C0 = bx * (C2_CW * FB_STRIDE);
@@ -1403,8 +1467,10 @@ __global__ void __launch_bounds__((C2_CW + 1) * 32, K2_CTAS) scan2d_keys_build_k
   K2Acc acc{DBL_MAX, DBL_MAX, 0.f};                   // exact min non-zero |d| per component; scaled by (W-1), (H-1) at the end:
                                                       // v = fl(d c) is monotone in |d|, so min |v| = fl(min |d| c) (grad.hh:24-27)
   sts64_f64(res_u32, DBL_MAX); sts64_f64(res_u32 + 8u, DBL_MAX);
-  if (border) acc = keys2d_strip<true, NPREV, TEST, K2_NST>(p, c0, r0, r1, lane, tile_u32, full0, empty0, bx * C2_CW + wib, 0u, res_u32, acc);
-  else acc = keys2d_strip<false, NPREV, TEST, K2_NST>(p, c0, r0, r1, lane, tile_u32, full0, empty0, bx * C2_CW + wib, 0u, res_u32, acc);
+  if (lane == 0) asm volatile("st.shared.s32 [%0], %1;" ::"r"(wl_stage), "r"(0) : "memory");
+  __syncwarp();
+  if (border) acc = keys2d_strip<true, NPREV, TEST, K2_NST>(p, c0, r0, r1, lane, tile_u32, full0, empty0, bx * C2_CW + wib, 0u, res_u32, wl_stage, acc);
+  else acc = keys2d_strip<false, NPREV, TEST, K2_NST>(p, c0, r0, r1, lane, tile_u32, full0, empty0, bx * C2_CW + wib, 0u, res_u32, wl_stage, acc);
   if (p.res_slot[p.build_layer] != nullptr) {
     const double cw = (double)(W - 1), ch = (double)(H - 1);
     const double ax = fabs(acc.mdx), ay = fabs(acc.mdy);
@@ -1429,6 +1495,7 @@ __global__ void __launch_bounds__((C2_CW + 1) * 32, K2_CTAS) scan2d_keys_persist
   const uint32_t full0 = ring0 + (uint32_t)K2_NST * K2_STAGE_BYTES, empty0 = full0 + 8u * K2_NST;
   const uint32_t res_u32 = empty0 + 8u * K2_NST + 16u * threadIdx.x;
   const uint32_t item0 = empty0 + 8u * K2_NST + 16u * (C2_CW + 1) * 32u;   // int stage_item[K2_NST]
+  const uint32_t wl_stage = item0 + 32u + WL_STAGE_BYTES * (uint32_t)wib;
   const int W = p.W, H = p.H;
   unsigned int *wc = reinterpret_cast<unsigned int *>(p.work_counter);     // [0] next item, [1] CTAs that are done
   const int total = p.nsx * p.nsy;
@@ -1478,6 +1545,8 @@ __global__ void __launch_bounds__((C2_CW + 1) * 32, K2_CTAS) scan2d_keys_persist
   }
   K2Acc acc{DBL_MAX, DBL_MAX, 0.f};
   sts64_f64(res_u32, DBL_MAX); sts64_f64(res_u32 + 8u, DBL_MAX);
+  if (lane == 0) asm volatile("st.shared.s32 [%0], %1;" ::"r"(wl_stage), "r"(0) : "memory");
+  __syncwarp();
   uint32_t gs = 0;
   while (true) {
     const uint32_t slot = gs % K2_NST;
@@ -1501,8 +1570,8 @@ __global__ void __launch_bounds__((C2_CW + 1) * 32, K2_CTAS) scan2d_keys_persist
       const int c0 = C0 + wib * FB_STRIDE;
       const uint32_t tile_u32 = ring0 + (uint32_t)(wib * FB_STRIDE) * 8u;
       const bool border = c0 == 0 || c0 + FB_SEG - 2 > W;
-      if (border) acc = keys2d_strip<true, NPREV, TEST, K2_NST>(p, c0, r0, r1, lane, tile_u32, full0, empty0, bx * C2_CW + wib, gs, res_u32, acc);
-      else acc = keys2d_strip<false, NPREV, TEST, K2_NST>(p, c0, r0, r1, lane, tile_u32, full0, empty0, bx * C2_CW + wib, gs, res_u32, acc);
+      if (border) acc = keys2d_strip<true, NPREV, TEST, K2_NST>(p, c0, r0, r1, lane, tile_u32, full0, empty0, bx * C2_CW + wib, gs, res_u32, wl_stage, acc);
+      else acc = keys2d_strip<false, NPREV, TEST, K2_NST>(p, c0, r0, r1, lane, tile_u32, full0, empty0, bx * C2_CW + wib, gs, res_u32, wl_stage, acc);
     }
     gs += (uint32_t)nstages;
   }
@@ -1520,7 +1589,7 @@ __global__ void __launch_bounds__((C2_CW + 1) * 32, K2_CTAS) scan2d_keys_persist
   }
 }
 
-static size_t k2_smem_bytes(int nst) { return (size_t)nst * K2_STAGE_BYTES + (size_t)2 * nst * 8 + (size_t)16 * (C2_CW + 1) * 32 + (size_t)4 * nst; }
+static size_t k2_smem_bytes(int nst) { return (size_t)nst * K2_STAGE_BYTES + (size_t)2 * nst * 8 + (size_t)16 * (C2_CW + 1) * 32 + 32 + (size_t)WL_STAGE_BYTES * C2_CW; }
 // FTKB_K2_CTAS (CTAs per SM: 2 | 3 | 4, default 3) and FTKB_K2_NST (ring stages at three CTAs per SM: 4 | 5 | 6, default 4)
 static int k2_variant() {
   static const int v = [] {
@@ -3068,7 +3137,7 @@ __device__ int oriented_sign(const i64 Xin[NV][NC], const int idx_in[NV]) {
 // origin (rank -1) inside the simplex: the orientation must not change when any one row is
 // replaced by the origin (sign_det.hh:360-414, critical_point_test.hh:22-34)
 template <int NV, int NC>
-__device__ bool origin_in_simplex(const i64 X[NV][NC], const int idx[NV]) {
+__device__ __noinline__ bool origin_in_simplex(const i64 X[NV][NC], const int idx[NV]) {
   const int s = oriented_sign<NV, NC>(X, idx);
 #pragma unroll 1
   for (int i = 0; i < NV; i++) {
@@ -3084,6 +3153,50 @@ __device__ bool origin_in_simplex(const i64 X[NV][NC], const int idx[NV]) {
     if (oriented_sign<NV, NC>(Y, my) != s) return false;
   }
   return true;
+}
+
+// Fast paths of origin_in_simplex.  The reference sorts the rows by vertex rank and multiplies the sign by the parity of the
+// swaps; the determinant is an alternating polynomial of the rows, and the arithmetic is mod 2^64 (a ring), so
+// det(sorted) = (-1)^swaps det(unsorted) exactly -- whenever a determinant is neither 0 (the symbolic cascade decides) nor
+// -2^63 (the one value whose negation has the same sign) the sorted, parity-corrected sign IS the sign of the unsorted
+// determinant.  A row replaced by the origin leaves a minor: expanding along the column of ones, det = sum of the replaced
+// determinants D_i.  All D_i and their sum usable -> compare signs; anything else -> the full cascade above.
+__device__ __forceinline__ bool usable_det(i64 v) { return v != 0 && v != LLONG_MIN; }
+
+__device__ __forceinline__ bool origin_in_simplex_fast(const i64 X[3][2], const int idx[3]) {
+  const u64 a0 = U(X[0][0]), a1 = U(X[0][1]), b0 = U(X[1][0]), b1 = U(X[1][1]), c0 = U(X[2][0]), c1 = U(X[2][1]);
+  const i64 Da = (i64)(b0 * c1 - b1 * c0);      // det3_h with row 0 = origin
+  const i64 Db = (i64)(a1 * c0 - a0 * c1);      // row 1 = origin
+  const i64 Dc = (i64)(a0 * b1 - a1 * b0);      // row 2 = origin
+  const i64 D = (i64)(U(Da) + U(Db) + U(Dc));   // det3_h of the simplex itself
+  if (usable_det(D) && usable_det(Da) && usable_det(Db) && usable_det(Dc)) {
+    const bool pos = D > 0;
+    return (Da > 0) == pos && (Db > 0) == pos && (Dc > 0) == pos;
+  }
+  return origin_in_simplex<3, 2>(X, idx);
+}
+
+__device__ __forceinline__ u64 det3_rows(const u64 r0[3], const u64 r1[3], const u64 r2[3]) {
+  return r0[0] * (r1[1] * r2[2] - r1[2] * r2[1]) - r0[1] * (r1[0] * r2[2] - r1[2] * r2[0]) + r0[2] * (r1[0] * r2[1] - r1[1] * r2[0]);
+}
+
+__device__ __forceinline__ bool origin_in_simplex_fast(const i64 X[4][3], const int idx[4]) {
+  u64 r[4][3];
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) r[i][j] = U(X[i][j]);
+  // det of rows (x, y, z, 1) with row i replaced by (0, 0, 0, 1): (-1)^(i+3) times the minor of the other rows
+  const i64 D0 = (i64)(0 - det3_rows(r[1], r[2], r[3]));
+  const i64 D1 = (i64)det3_rows(r[0], r[2], r[3]);
+  const i64 D2 = (i64)(0 - det3_rows(r[0], r[1], r[3]));
+  const i64 D3 = (i64)det3_rows(r[0], r[1], r[2]);
+  const i64 D = (i64)(U(D0) + U(D1) + U(D2) + U(D3));
+  if (usable_det(D) && usable_det(D0) && usable_det(D1) && usable_det(D2) && usable_det(D3)) {
+    const bool pos = D > 0;
+    return (D0 > 0) == pos && (D1 > 0) == pos && (D2 > 0) == pos && (D3 > 0) == pos;
+  }
+  return origin_in_simplex<4, 3>(X, idx);
 }
 
 // =============================================================================================
@@ -3390,7 +3503,7 @@ __device__ bool check_simplex(const SweepParams &p, const DeviceMeshTables &mt, 
       }
       if (small && sided) return false;
     }
-    if (!origin_in_simplex<NV, ND>(vf, rank)) return false;
+    if (!origin_in_simplex_fast(vf, rank)) return false;
   } else {
     if (!inside) return false;
   }
