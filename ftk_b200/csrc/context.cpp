@@ -1137,7 +1137,7 @@ static int grow_points_ahead(ftkb_ctx *c) {
   if (!per) return FTKB_OK;
   const uint64_t need = c->npts + (c->pend.size() + 2) * (per + per / 2);
   if (need <= c->pt_cap) return FTKB_OK;
-  uint64_t cap = c->pt_cap;
+  uint64_t cap = 4 * c->pt_cap;                      // in big steps: every growth costs a cudaMalloc in the middle of the step loop
   while (cap < need) cap *= 2;
   if (cap >= 0xffffffffull) return FTKB_OK;          // (the overflow path reports it)
   ftkb_point *np = nullptr;

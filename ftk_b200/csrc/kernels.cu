@@ -3627,61 +3627,128 @@ __device__ bool check_simplex(const SweepParams &p, const DeviceMeshTables &mt, 
   return true;
 }
 
-// A block works on CPB surviving cubes per round: first the 2^(ND+1) vertices of every cube are gathered (the vector field
+// A block works on CPB surviving cubes per round: the 2^(ND+1) vertices of every cube are gathered (the vector field
 // read or derived ONCE per vertex -- a vertex is shared by up to 9 / 36 simplices of its cube), then one thread per
-// (cube, simplex type) runs the exact test on the cached vectors.
+// (cube, simplex type) runs the exact test on the cached vectors.  The gather is software-pipelined: while round r is
+// tested, the loads of round r + 1 are in flight (their results sit in registers until the test is over and then go into
+// the other half of the cache), and the worklist entry of round r + 2 is on its way -- one barrier per round, and neither
+// the worklist read nor the dependent field reads are waited for.
 template <int ND>
-__global__ void __launch_bounds__(128) test_kernel(const __grid_constant__ SweepParams p) {
+struct VertexLoads {
+  double a[ND], b[ND];        // component c = finish(a[c], b[c]): the value itself (vector input) or the two ends of a difference
+  int corner[3];
+  bool item, ok;              // this thread holds a (cube, vertex) item of the round / the vertex is one valid simplices use
+};
+
+template <int ND>
+__device__ __forceinline__ void vertex_loads_issue(const SweepParams &p, const LayerPtrs &L, const int *vx, VertexLoads<ND> &g) {
+  const int W = p.W, H = p.H;
+  if constexpr (ND == 2) {
+    const int i = clampi(vx[0], W), j = clampi(vx[1], H);
+    if (L.V) {
+      const double *v = L.V + 2 * ((size_t)i + (size_t)W * j);      // (8-byte loads: a borrowed layer need not be 16-byte aligned)
+      g.a[0] = __ldg(v); g.a[1] = __ldg(v + 1); g.b[0] = g.b[1] = 0.0;
+      return;
+    }
+#define SF(ii, jj) __ldg(L.S + (size_t)clampi(ii, W) + (size_t)W * clampi(jj, H))
+    g.a[0] = SF(i + 1, j); g.b[0] = SF(i - 1, j);
+    g.a[1] = SF(i, j + 1); g.b[1] = SF(i, j - 1);
+#undef SF
+  } else {
+    const int D = p.D, i = vx[0], j = vx[1], k = vx[2];
+    const size_t idx = (size_t)i + (size_t)W * ((size_t)j + (size_t)H * (size_t)k);
+    if (L.V) {
+#pragma unroll
+      for (int c = 0; c < 3; c++) { g.a[c] = __ldg(L.V + c + 3 * idx); g.b[c] = 0.0; }
+      return;
+    }
+    const bool interior = i >= 1 && i < W - 1 && j >= 1 && j < H - 1 && k >= 1 && k < D - 1;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      const size_t st = c == 0 ? 1 : (c == 1 ? (size_t)W : (size_t)W * H);
+      g.a[c] = interior ? __ldg(L.S + idx + st) : 0.0;
+      g.b[c] = interior ? __ldg(L.S + idx - st) : 0.0;
+    }
+  }
+}
+
+// the arithmetic of vec2_at / vec3_at on the loaded values (same operations, same order)
+template <int ND>
+__device__ __forceinline__ double vertex_loads_finish(const SweepParams &p, const LayerPtrs &L, const VertexLoads<ND> &g, const int c) {
+  if (L.V) return g.a[c];
+  if constexpr (ND == 2) return (g.a[c] - g.b[c]) * (c == 0 ? p.W - 1 : p.H - 1);
+  else return 0.5 * (g.a[c] - g.b[c]);
+}
+
+template <int ND>
+__global__ void __launch_bounds__(128, ND == 2 ? 5 : 3) test_kernel(const __grid_constant__ SweepParams p) {
   const DeviceMeshTables &mt = c_mesh[ND - 2];
   constexpr int ntypes = ND == 2 ? 12 : 60;
   constexpr int NVC = 1 << (ND + 1);                  // vertices of a space-time cube
   constexpr int CPB = 128 / ntypes;                   // cubes per block and round (10 in 2D, 2 in 3D)
-  __shared__ double vcache[CPB][NVC * ND];
-  __shared__ int ccorner[CPB][3];
+  static_assert(CPB * NVC <= 128, "one (cube, vertex) item per thread");
+  __shared__ double vcache[2][CPB][NVC * ND];
+  __shared__ int ccorner[2][CPB][3];
   u64 ncubes = *p.wl_count;
   if (ncubes > p.wl_cap) ncubes = p.wl_cap;
   const u64 stride = (u64)gridDim.x * CPB;
   const u64 rounds = (ncubes + stride - 1) / stride;
   const int lane = threadIdx.x & 31;
+  const int gci = threadIdx.x / NVC, gm = threadIdx.x % NVC;       // this thread's gather item: cube gci of the round, vertex mask gm
+  const bool gthread = (int)threadIdx.x < CPB * NVC;
+  const int gdt = (gm >> ND) & 1;
+  // worklist entry of this thread's cube in round r (all ones: none)
+  auto wl_entry = [&](const u64 r) -> u64 {
+    const u64 cube = r * stride + (u64)blockIdx.x * CPB + (u64)gci;
+    return (gthread && r < rounds && cube < ncubes) ? p.wl[cube] : ~0ull;
+  };
+  auto issue = [&](u64 q, VertexLoads<ND> &g) {
+    g.item = q != ~0ull;
+    g.ok = false;
+#pragma unroll
+    for (int c = 0; c < ND; c++) { g.a[c] = 0.0; g.b[c] = 0.0; }
+    if (!g.item) return;
+    g.corner[0] = (int)(q % (u64)p.nc[0]) + p.lb[0]; q /= (u64)p.nc[0];
+    g.corner[1] = (int)(q % (u64)p.nc[1]) + p.lb[1]; q /= (u64)p.nc[1];
+    g.corner[2] = ND == 3 ? (int)q + p.lb[2] : 0;
+    int vx[3] = {0, 0, 0};
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < ND; j++) { vx[j] = g.corner[j] + ((gm >> j) & 1); ok = ok && vx[j] >= p.lb[j] && vx[j] <= p.ub[j]; }
+    ok = ok && (p.has_next || gdt == 0);              // (no second layer: the interval vertices belong to no simplex that is tested)
+    g.ok = ok;
+    if (ok) vertex_loads_issue<ND>(p, p.L[gdt], vx, g);   // a vertex outside the domain belongs to no valid simplex: never read
+  };
+  auto commit = [&](const int buf, const VertexLoads<ND> &g) {
+    if (!g.item) return;
+    if (gm == 0) { ccorner[buf][gci][0] = g.corner[0]; ccorner[buf][gci][1] = g.corner[1]; ccorner[buf][gci][2] = g.corner[2]; }
+#pragma unroll
+    for (int c = 0; c < ND; c++) vcache[buf][gci][gm * ND + c] = g.ok ? vertex_loads_finish<ND>(p, p.L[gdt], g, c) : 0.0;
+  };
+
+  int cur = 0;
+  u64 qnext = ~0ull;
+  {
+    VertexLoads<ND> g0;
+    issue(wl_entry(0), g0);
+    qnext = wl_entry(1);
+    commit(0, g0);
+  }
+  __syncthreads();
   for (u64 r = 0; r < rounds; r++) {
     const u64 cube0 = r * stride + (u64)blockIdx.x * CPB;
-    // ---- gather: thread t -> (cube t / NVC, vertex mask t % NVC)
-    for (int t = threadIdx.x; t < CPB * NVC; t += blockDim.x) {
-      const int ci = t / NVC, m = t % NVC;
-      const u64 cube = cube0 + (u64)ci;
-      if (cube < ncubes) {
-        u64 q = p.wl[cube];
-        int corner[3];
-        corner[0] = (int)(q % (u64)p.nc[0]) + p.lb[0]; q /= (u64)p.nc[0];
-        corner[1] = (int)(q % (u64)p.nc[1]) + p.lb[1]; q /= (u64)p.nc[1];
-        corner[2] = ND == 3 ? (int)q + p.lb[2] : 0;
-        if (m == 0) { ccorner[ci][0] = corner[0]; ccorner[ci][1] = corner[1]; ccorner[ci][2] = corner[2]; }
-        int vx[3];
-        bool ok = true;
-#pragma unroll
-        for (int j = 0; j < ND; j++) { vx[j] = corner[j] + ((m >> j) & 1); ok = ok && vx[j] >= p.lb[j] && vx[j] <= p.ub[j]; }
-        const int dt = (m >> ND) & 1;
-        ok = ok && (p.has_next || dt == 0);           // (no second layer: the interval vertices belong to no simplex that is tested)
-#pragma unroll
-        for (int c = 0; c < ND; c++) {
-          double val = 0.0;                           // a vertex outside the domain belongs to no valid simplex: never read
-          if (ok) {
-            if constexpr (ND == 2) val = vec2_at(p, p.L[dt], c, vx[0], vx[1]);
-            else val = vec3_at(p, p.L[dt], c, vx[0], vx[1], vx[2]);
-          }
-          vcache[ci][m * ND + c] = val;
-        }
-      }
-    }
-    __syncthreads();
+    // ---- round r + 1: field loads issued now, worklist entry of round r + 2 requested
+    VertexLoads<ND> gn;
+    issue(qnext, gn);
+    qnext = wl_entry(r + 2);
     // ---- test: thread t -> (cube t / ntypes, type t % ntypes)
     bool hit = false;
     ftkb_point cp;
     {
       const int ci = threadIdx.x / ntypes, type = threadIdx.x % ntypes;
       if (ci < CPB && cube0 + (u64)ci < ncubes && (p.has_next || mt.ordinal[type])) {
-        const int corner[3] = {ccorner[ci][0], ccorner[ci][1], ccorner[ci][2]};
-        hit = check_simplex<ND>(p, mt, corner, type, cp, vcache[ci]);
+        const int corner[3] = {ccorner[cur][ci][0], ccorner[cur][ci][1], ccorner[cur][ci][2]};
+        hit = check_simplex<ND>(p, mt, corner, type, cp, vcache[cur][ci]);
       }
     }
     const unsigned b = __ballot_sync(0xffffffffu, hit);
@@ -3695,7 +3762,9 @@ __global__ void __launch_bounds__(128) test_kernel(const __grid_constant__ Sweep
         if (o < p.pt_cap) p.pts[o] = cp;
       }
     }
-    __syncthreads();                                  // the cache is refilled by the next round
+    commit(cur ^ 1, gn);
+    __syncthreads();                                  // round r + 1 is in the other half; this half is free again
+    cur ^= 1;
   }
   if (p.step_out == nullptr) return;
   // deferred step: the last block to finish publishes the counters to the host (mapped memory) and re-arms the
