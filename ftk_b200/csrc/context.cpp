@@ -44,6 +44,18 @@ struct Layer {
 
 }  // namespace
 
+// host arrays that are filled completely right after they are sized (by a device-to-host copy or a loop): no value-initialisation
+// pass over tens of megabytes first
+template <class T>
+struct NoInitAlloc : std::allocator<T> {
+  template <class U> struct rebind { using other = NoInitAlloc<U>; };
+  template <class U, class... A>
+  void construct(U *q, A &&...a) {
+    if constexpr (sizeof...(A) > 0) ::new ((void *)q) U(std::forward<A>(a)...);
+  }
+};
+template <class T> using RawVec = std::vector<T, NoInitAlloc<T>>;
+
 struct ftkb_ctx {
   ftkb_config cfg{};
   int n = 0;                     // spatial dims
@@ -137,12 +149,12 @@ struct ftkb_ctx {
 
   // sorted / traced results (host)
   bool sorted = false, traced = false;
-  std::vector<ftkb_point> pts_sorted;
+  RawVec<ftkb_point> pts_sorted;
   ftkb_point *d_pts_sorted = nullptr;          // device copy of the sorted unique points
   unsigned long long *d_keys_sorted = nullptr;
   uint64_t nsorted = 0;
-  std::vector<uint64_t> labels;
-  std::vector<int32_t> deg;
+  RawVec<uint64_t> labels;
+  RawVec<int32_t> deg;
   std::vector<uint64_t> traj_off, traj_idx;
   std::vector<uint8_t> traj_loop, traj_complete;
 
@@ -368,7 +380,7 @@ extern "C" int ftkb_create(const ftkb_config *cfg, ftkb_ctx **out) {
     if (const char *o = std::getenv("FTKB_DEBUG_TIMING")) c->debug_timing = std::string(o) == "1";
     if (c->debug_timing) cudaEventCreate(&c->dbg_prev);
   }
-  c->pt_cap = cfg->point_capacity ? cfg->point_capacity : (1 << 18);
+  c->pt_cap = cfg->point_capacity ? cfg->point_capacity : (1 << 20);      // 75 MB of 180 GB: growth (a cudaMalloc in the middle of the step loop) starts late
   if ((e = cudaMalloc(&c->d_pts, sizeof(ftkb_point) * c->pt_cap)) != cudaSuccess) return bail("cudaMalloc(points) failed", FTKB_ERR_NOMEM);
   DeviceMeshTables t2, t3;
   fill_device_tables(3, &t2);
@@ -1666,8 +1678,9 @@ extern "C" int ftkb_finalize(ftkb_ctx *c) {
   if (rc) return rc;
   const uint64_t n = c->nsorted;
   Laps laps(c->debug_timing, "trace");
-  c->labels.assign(n, 0);
-  c->deg.assign(n, 0);
+  c->labels.clear(); c->deg.clear();
+  if (c->streaming) { c->labels.assign(n, 0); c->deg.assign(n, 0); }     // (not computed: zeros)
+  else { c->labels.resize(n); c->deg.resize(n); }                       // every entry is written below
   c->traj_off.assign(1, 0);
   c->traj_idx.clear();
   c->traj_loop.clear();
@@ -1716,7 +1729,7 @@ extern "C" int ftkb_finalize(ftkb_ctx *c) {
   launch_union_find(tp, c->stream);
   CKC(cudaEventRecord(c->ev[1], c->stream));
   c->stats.kernel_launches += 3;
-  std::vector<uint32_t> nb(8 * n), pa(n), po(n);
+  RawVec<uint32_t> nb(8 * n), pa(n), po(n);
   laps.lap("host_vectors");
   CKC(cudaMemcpyAsync(nb.data(), d_nb, 4 * 8 * n, cudaMemcpyDeviceToHost, c->stream));
   CKC(cudaMemcpyAsync(pa.data(), d_pa, 4 * n, cudaMemcpyDeviceToHost, c->stream));
