@@ -3039,6 +3039,7 @@ void launch_scan(const SweepParams &p, cudaStream_t s) {
 // All integer arithmetic wraps mod 2^64 exactly like the reference's int64 (-fwrapv) evaluation;
 // the determinant expansions below are polynomial identities of the reference's, hence equal
 // mod 2^64 term order notwithstanding.
+// [host-testable: begin]  (tests/test_predicate_fast_path.py compiles the lines up to the matching end marker with g++)
 __device__ __forceinline__ int sgn(i64 v) { return (v > 0) - (v < 0); }
 __device__ __forceinline__ u64 U(i64 v) { return (u64)v; }
 
@@ -3198,6 +3199,7 @@ __device__ __forceinline__ bool origin_in_simplex_fast(const i64 X[4][3], const 
   }
   return origin_in_simplex<4, 3>(X, idx);
 }
+// [host-testable: end]
 
 // =============================================================================================
 // 3. floating-point leaves (literal operation order of the reference)
