@@ -1612,21 +1612,34 @@ static int ensure_sorted(ftkb_ctx *c) {
   CKC(cudaMemcpyAsync(c->d_keys_sorted, k0, 8 * nu, cudaMemcpyDeviceToDevice, c->stream));      // unique sorted keys
   CKC(cudaEventRecord(c->ev[1], c->stream));
   laps.lap("malloc+gather");
-  c->pts_sorted.resize(nu);
-  laps.lap("host_resize");
-  CKC(cudaMemcpyAsync(c->pts_sorted.data(), c->d_pts_sorted, sizeof(ftkb_point) * nu, cudaMemcpyDeviceToHost, c->stream));
+  // the sorted records stay on the device: ftkb_get_points copies them straight into the caller's array, and the few host-side
+  // users (curve sets) fetch them on demand (host_points) -- a copy of 72 bytes per record into fresh pageable memory costs more
+  // than the sort
   CKC(cudaStreamSynchronize(c->stream));
-  laps.lap("d2h_points");
+  laps.lap("sync");
   CKC(cudaGetLastError());
   float ms = 0;
   CKC(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]));
   c->stats.ms_finalize_device += ms;
   c->stats.kernel_launches += 4;
-  c->stats.d2h_bytes += sizeof(ftkb_point) * nu;
   c->nsorted = nu;
   c->stats.ms_sort_wall += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tw0).count();
 #undef CKC
   c->sorted = true;
+  return FTKB_OK;
+}
+
+// host copy of the sorted records, made when somebody on the host needs it
+static int host_points(ftkb_ctx *c) {
+  const int rc = ensure_sorted(c);
+  if (rc) return rc;
+  if (c->pts_sorted.size() == c->nsorted) return FTKB_OK;
+  c->pts_sorted.resize(c->nsorted);
+  if (c->nsorted) {
+    CK(cudaMemcpyAsync(c->pts_sorted.data(), c->d_pts_sorted, sizeof(ftkb_point) * c->nsorted, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->stats.d2h_bytes += sizeof(ftkb_point) * c->nsorted;
+  }
   return FTKB_OK;
 }
 
@@ -1643,7 +1656,12 @@ extern "C" int ftkb_get_points(ftkb_ctx *c, ftkb_point *out, uint64_t cap) {
   const int rc = ensure_sorted(c);
   if (rc) return rc;
   if (cap < c->nsorted) return fail(c, FTKB_ERR_INVALID, "get_points: output buffer too small");
-  if (c->nsorted) std::memcpy(out, c->pts_sorted.data(), sizeof(ftkb_point) * c->nsorted);
+  if (!c->nsorted) return FTKB_OK;
+  if (c->pts_sorted.size() == c->nsorted) { std::memcpy(out, c->pts_sorted.data(), sizeof(ftkb_point) * c->nsorted); return FTKB_OK; }
+  CK(cudaSetDevice(c->cfg.device));
+  CK(cudaMemcpyAsync(out, c->d_pts_sorted, sizeof(ftkb_point) * c->nsorted, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  c->stats.d2h_bytes += sizeof(ftkb_point) * c->nsorted;
   return FTKB_OK;
 }
 
@@ -1691,7 +1709,11 @@ extern "C" int ftkb_finalize(ftkb_ctx *c) {
     // the sorted points; the component labels / degrees of the offline trace are not computed
     const auto t0 = std::chrono::steady_clock::now();
     std::vector<uint64_t> keys(n);
-    for (uint64_t i = 0; i < n; i++) c->online->key_of(c->pts_sorted[i], keys[i]);
+    if (n) {      // the sorted points' element keys (the device sorted by them)
+      CK(cudaMemcpyAsync(keys.data(), c->d_keys_sorted, 8 * n, cudaMemcpyDeviceToHost, c->stream));
+      CK(cudaStreamSynchronize(c->stream));
+      c->stats.d2h_bytes += 8 * n;
+    }
     const std::vector<uint64_t> &streamed = c->online->keys();
     for (const ftkb::OnlineCurve &cv : c->online->curves()) {
       for (const uint32_t g : cv.idx) {
@@ -1945,6 +1967,7 @@ extern "C" int ftkb_get_curveset(ftkb_ctx *c, ftkb_curveset **out) {
   if (!c->traced) return fail(c, FTKB_ERR_INVALID, "get_curveset: call finalize first");
   const uint64_t ntraj = c->traj_off.empty() ? 0 : c->traj_off.size() - 1;
   static const uint64_t zero = 0;
+  { const int rch = host_points(c); if (rch) return rch; }
   const int rc = ftkb_curveset_create(c->pts_sorted.data(), c->pts_sorted.size(), ntraj ? c->traj_off.data() : &zero, c->traj_idx.data(),
                                       c->traj_loop.data(), ntraj, out);
   if (rc == FTKB_OK)   // streaming: feature_curve_t::complete as the grow steps left it (curves are in id order)

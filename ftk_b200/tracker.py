@@ -327,7 +327,7 @@ class _RegularTracker:
         """structured array (L.POINT_DTYPE) sorted by the reference's element order"""
         n = C.c_uint64()
         self._check(L.lib().ftkb_num_points(self._h, C.byref(n)))
-        out = np.zeros(n.value, L.POINT_DTYPE)
+        out = np.empty(n.value, L.POINT_DTYPE)       # filled completely by the copy below
         if n.value:
             self._check(L.lib().ftkb_get_points(self._h, out.ctypes.data, n.value))
         starts = self._array_domain.starts if self._array_domain is not None else []
@@ -357,7 +357,9 @@ class _RegularTracker:
         """-> list of (index array into get_discrete_critical_points(), loop flag)"""
         nt = C.c_uint64()
         self._check(L.lib().ftkb_num_trajectories(self._h, C.byref(nt)))
-        npts = len(self.get_discrete_critical_points())
+        n = C.c_uint64()
+        self._check(L.lib().ftkb_num_points(self._h, C.byref(n)))
+        npts = int(n.value)
         off = np.zeros(nt.value + 1, np.uint64)
         idx = np.zeros(max(npts, 1), np.uint64)
         loop = np.zeros(max(nt.value, 1), np.uint8)
