@@ -94,7 +94,7 @@ struct ftkb_ctx {
   // [12] the second worklist counter (deferred steps alternate), [13] ticket of the test kernel's blocks, [14] second poison flag
   unsigned long long *d_scalars = nullptr;
   unsigned long long *h_scalars = nullptr;     // pinned mirror
-  static constexpr int SLOT_WL = 8, SLOT_PT = 9, SLOT_UQ = 10, SLOT_POISON = 11, SLOT_WL2 = 12, SLOT_TICKET = 13, SLOT_POISON2 = 14, SLOT_WORK = 15, NSLOTS = 16;
+  static constexpr int SLOT_WL = 8, SLOT_PT = 9, SLOT_UQ = 10, SLOT_POISON = 11, SLOT_WL2 = 12, SLOT_TICKET = 13, SLOT_POISON2 = 14, NSLOTS = 16;
 
   // ---- deferred ("sync-free") steps ------------------------------------------------------------------------------
   // ftkb_update_timestep enqueues scan + test and returns; the test kernel's last block publishes the counters into the
@@ -664,7 +664,8 @@ static void fill_sweep_geometry(const ftkb_ctx *c, SweepParams &p) {
   p.coords = c->d_coords;
   p.nd = c->n;
   p.sm_count = c->sm_count;
-  p.work_counter = c->d_scalars + ftkb_ctx::SLOT_WORK;
+  static const int l2_hint = [] { const char *e = std::getenv("FTKB_K2_L2HINT"); return e ? std::atoi(e) : 0; }();
+  p.l2_hint = l2_hint;
   p.W = c->cfg.dims[0]; p.H = c->cfg.dims[1]; p.D = c->n == 3 ? c->cfg.dims[2] : 1;
   for (int j = 0; j < 3; j++) {
     const bool used = j < c->n;

@@ -482,6 +482,16 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+// the same copy with an L2 eviction policy (createpolicy): a layer is streamed once, so its lines may leave L2 first
+__device__ __forceinline__ unsigned long long l2_policy_evict_first() {
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void bulk_g2s_hint(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar, unsigned long long pol) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(pol) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done;
   do {
@@ -1256,15 +1266,19 @@ __device__ __forceinline__ K2Acc keys2d_strip(const SweepParams &p, const int c0
   const uint32_t lane_u32 = tile_u32 + (uint32_t)lane * 16u;    // +8: column e-1, +16: e, o, +32: o+1
   const int kb0 = r0 / C2_R;                          // first block of the segment (a segment has at most 64 blocks)
   unsigned long long failbits = 0;
+  const int kb_end = ((r1 + 1) + C2_R - 1) / C2_R;     // blocks up to kb_end-1 are closed by this segment
 
   // a block of C2_R corner rows is complete: x-neighbour merge on the keys, keys -> fp32 ranges of v, store the cell, test
-  auto finish_block = [&](const int kb, float xmn, float xmx, float ymn, float ymx, const uint4 prevc) {
+  auto finish_block = [&](const int kb, float xmn, float xmx, float ymn, float ymx) {
     xmn = fminf(xmn, __shfl_down_sync(0xffffffffu, xmn, 1)); xmx = fmaxf(xmx, __shfl_down_sync(0xffffffffu, xmx, 1));
     ymn = fminf(ymn, __shfl_down_sync(0xffffffffu, ymn, 1)); ymx = fmaxf(ymx, __shfl_down_sync(0xffffffffu, ymx, 1));
     FRange bx = k2_vrange(xmn, xmx, cw), by = k2_vrange(ymn, ymx, ch);
     sum_out[(size_t)kb * 32u] = make_uint4(__float_as_uint(bx.mn), __float_as_uint(bx.mx), __float_as_uint(by.mn), __float_as_uint(by.mx));
     if (TEST) {
-      if (NPREV) {
+      if (NPREV && kb < kb_end) {
+        // the other layer's cell of this block: requested into L2 two blocks ago (a DRAM miss: ~1 us), loaded only now -- four
+        // registers that are not live across the block's nine rows
+        const uint4 prevc = __ldg(sum_prev + (size_t)kb * 32u);
         bx = fmerge(bx, FRange{__uint_as_float(prevc.x), __uint_as_float(prevc.y)});
         by = fmerge(by, FRange{__uint_as_float(prevc.z), __uint_as_float(prevc.w)});
       }
@@ -1338,10 +1352,7 @@ __device__ __forceinline__ K2Acc keys2d_strip(const SweepParams &p, const int c0
   float bxmn = 0.f, bxmx = 0.f, bymn = 0.f, bymx = 0.f;
   const uint4 nanc = make_uint4(0x7FC00000u, 0x7FC00000u, 0x7FC00000u, 0x7FC00000u);
   int kb = r0 / C2_R;                                  // the block the next row with K == 0 opens
-  const int kb_end = (jl + C2_R - 1) / C2_R;           // blocks kb .. kb_end-1 are closed by this segment
-  // the other layer's cells are requested into L2 two blocks ahead of their use (a DRAM miss each: ~1 us) and loaded one
-  // block ahead
-  uint4 prevc = nanc;
+  // the other layer's cells are requested into L2 two blocks ahead of their use
   if (NPREV && kb < kb_end) prefetch_l2(sum_prev + (size_t)kb * 32u);
   if (NPREV && kb + 1 < kb_end) prefetch_l2(sum_prev + (size_t)(kb + 1) * 32u);
 
@@ -1371,9 +1382,8 @@ __device__ __forceinline__ K2Acc keys2d_strip(const SweepParams &p, const int c0
       if (i == 0 && opens_group) {
         // gradient row C2_R k closes block k-1 and opens block k
         const float rxmn = fminf(kxe, kxo), rxmx = fmaxf(kxe, kxo), rymn = fminf(kye, kyo), rymx = fmaxf(kye, kyo);
-        if (j > r0) finish_block(kb - 1, fminf(bxmn, rxmn), fmaxf(bxmx, rxmx), fminf(bymn, rymn), fmaxf(bymx, rymx), prevc);
+        if (j > r0) finish_block(kb - 1, fminf(bxmn, rxmn), fmaxf(bxmx, rxmx), fminf(bymn, rymn), fmaxf(bymx, rymx));
         bxmn = rxmn; bxmx = rxmx; bymn = rymn; bymx = rymx;
-        if (NPREV && kb < kb_end) prevc = __ldg(sum_prev + (size_t)kb * 32u);     // cells of the block this row opens (in L2 by now)
         kb++;
         if (NPREV && kb + 1 < kb_end) prefetch_l2(sum_prev + (size_t)(kb + 1) * 32u);
       } else {
@@ -1402,7 +1412,7 @@ __device__ __forceinline__ K2Acc keys2d_strip(const SweepParams &p, const int c0
     group(IC<0>{}, g);
     if (g + 1 < ngroups) group(IC<1>{}, g + 1);
   }
-  if (jl % C2_R != 0) finish_block(jl / C2_R, bxmn, bxmx, bymn, bymx, prevc);     // the array's last, partial block
+  if (jl % C2_R != 0) finish_block(jl / C2_R, bxmn, bxmx, bymn, bymx);     // the array's last, partial block
   if (TEST) {
     // cold path: per-cube refinement of the blocks whose cell union failed (rows re-read through L2)
     for (int b = 0; b < 64; b++) {
@@ -1447,6 +1457,8 @@ __global__ void __launch_bounds__((C2_CW + 1) * 32, K2_CTAS) scan2d_keys_build_k
       const int col_lo = max(C0 - 2, 0), col_hi = min(C0 - 2 + TL_SEG, W);
       const uint32_t seg_bytes = (uint32_t)(col_hi - col_lo) * 8u;
       const uint32_t dst0 = ring0 + (uint32_t)(col_lo - (C0 - 2)) * 8u;
+      const bool hint = p.l2_hint != 0;
+      const unsigned long long pol = hint ? l2_policy_evict_first() : 0ull;
       for (int s = 0; s < nstages; s++) {
         const uint32_t slot = (uint32_t)s % K2_NST;
         if (s >= K2_NST) mbar_wait(empty0 + 8u * slot, (uint32_t)((s / K2_NST - 1) & 1));
@@ -1454,7 +1466,8 @@ __global__ void __launch_bounds__((C2_CW + 1) * 32, K2_CTAS) scan2d_keys_build_k
 #pragma unroll
         for (int i = 0; i < K2_R; i++) {
           const size_t off = (size_t)W * (size_t)clampi(r0 - 1 + K2_R * s + i, H) + (size_t)col_lo;
-          bulk_g2s(dst0 + slot * K2_STAGE_BYTES + (uint32_t)i * K2_ROW_BYTES, S + off, seg_bytes, full0 + 8u * slot);
+          if (hint) bulk_g2s_hint(dst0 + slot * K2_STAGE_BYTES + (uint32_t)i * K2_ROW_BYTES, S + off, seg_bytes, full0 + 8u * slot, pol);
+          else bulk_g2s(dst0 + slot * K2_STAGE_BYTES + (uint32_t)i * K2_ROW_BYTES, S + off, seg_bytes, full0 + 8u * slot);
         }
       }
     }
@@ -1480,115 +1493,6 @@ __global__ void __launch_bounds__((C2_CW + 1) * 32, K2_CTAS) scan2d_keys_build_k
   if (!(acc.big < __int_as_float(KEYF_BIG))) atomicExch(p.poison, 1ull);
 }
 
-// Persistent variant (FTKB_K2_PERSIST=1): K2_CTAS CTAs per SM for the whole launch; the producer warp draws (tile, chunk) items
-// from a device counter (same order as the grid of the kernel above, so CTAs that run together still read neighbouring pieces of
-// the same rows) and streams their rows back to back through the ring -- the ring never drains between chunks and nobody waits
-// for a last, partly filled wave.  The first stage of every item carries the item's number (stage_item[slot], written before the
-// stage is armed); a negative number ends the consumers.  Consumer warps whose strip lies outside the array still take part in
-// the barrier protocol, so the ring's arrival counts are the same for every item.  The last CTA out re-arms the counter.
-template <int NPREV, bool TEST, int K2_CTAS, int K2_NST>
-__global__ void __launch_bounds__((C2_CW + 1) * 32, K2_CTAS) scan2d_keys_persist_kernel(const __grid_constant__ SweepParams p) {
-  extern __shared__ __align__(128) unsigned char fb_smem[];
-  const int lane = threadIdx.x & 31;
-  const int wib = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);     // warp-uniform by construction
-  const uint32_t ring0 = smem_u32(fb_smem);
-  const uint32_t full0 = ring0 + (uint32_t)K2_NST * K2_STAGE_BYTES, empty0 = full0 + 8u * K2_NST;
-  const uint32_t res_u32 = empty0 + 8u * K2_NST + 16u * threadIdx.x;
-  const uint32_t item0 = empty0 + 8u * K2_NST + 16u * (C2_CW + 1) * 32u;   // int stage_item[K2_NST]
-  const uint32_t wl_stage = item0 + 32u + WL_STAGE_BYTES * (uint32_t)wib;
-  const int W = p.W, H = p.H;
-  unsigned int *wc = reinterpret_cast<unsigned int *>(p.work_counter);     // [0] next item, [1] CTAs that are done
-  const int total = p.nsx * p.nsy;
-  if (threadIdx.x == 0) {
-#pragma unroll
-    for (int q = 0; q < K2_NST; q++) { mbar_init(full0 + 8u * q, 1); mbar_init(empty0 + 8u * q, (uint32_t)C2_CW); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  }
-  __syncthreads();
-  if (wib == C2_CW) {
-    if (elect_one()) {
-      const double *S = p.L[p.build_layer].S;
-      uint32_t gs = 0;
-      int item = (int)atomicAdd(&wc[0], 1u);
-      while (true) {
-        const uint32_t slot0 = gs % K2_NST;
-        if (gs >= K2_NST) mbar_wait(empty0 + 8u * slot0, ((gs / K2_NST) - 1u) & 1u);
-        if (item >= total) {
-          asm volatile("st.shared.s32 [%0], %1;" ::"r"(item0 + 4u * slot0), "r"(-1) : "memory");
-          mbar_arrive(full0 + 8u * slot0);
-          break;
-        }
-        asm volatile("st.shared.s32 [%0], %1;" ::"r"(item0 + 4u * slot0), "r"(item) : "memory");
-        const int bx = item % p.nsx, cy = item / p.nsx;
-        const int next = (int)atomicAdd(&wc[0], 1u);      // its latency hides behind this item's copies
-        const int C0 = bx * (C2_CW * FB_STRIDE);
-        const int r0 = cy * p.rows, r1 = min(r0 + p.rows - 1, H - 1);
-        const int nstages = ((r1 + 1) - r0 + 1 + 2 + K2_R - 1) / K2_R;
-        const int col_lo = max(C0 - 2, 0), col_hi = min(C0 - 2 + TL_SEG, W);
-        const uint32_t seg_bytes = (uint32_t)(col_hi - col_lo) * 8u;
-        const uint32_t dst0 = ring0 + (uint32_t)(col_lo - (C0 - 2)) * 8u;
-        for (int st = 0; st < nstages; st++, gs++) {
-          const uint32_t slot = gs % K2_NST;
-          if (st > 0 && gs >= K2_NST) mbar_wait(empty0 + 8u * slot, ((gs / K2_NST) - 1u) & 1u);
-          mbar_expect_tx(full0 + 8u * slot, seg_bytes * K2_R);
-#pragma unroll
-          for (int i = 0; i < K2_R; i++) {
-            const size_t off = (size_t)W * (size_t)clampi(r0 - 1 + K2_R * st + i, H) + (size_t)col_lo;
-            bulk_g2s(dst0 + slot * K2_STAGE_BYTES + (uint32_t)i * K2_ROW_BYTES, S + off, seg_bytes, full0 + 8u * slot);
-          }
-        }
-        item = next;
-      }
-    }
-    return;
-  }
-  K2Acc acc{DBL_MAX, DBL_MAX, 0.f};
-  sts64_f64(res_u32, DBL_MAX); sts64_f64(res_u32 + 8u, DBL_MAX);
-  if (lane == 0) asm volatile("st.shared.s32 [%0], %1;" ::"r"(wl_stage), "r"(0) : "memory");
-  __syncwarp();
-  uint32_t gs = 0;
-  while (true) {
-    const uint32_t slot = gs % K2_NST;
-    mbar_wait(full0 + 8u * slot, (gs / K2_NST) & 1u);
-    int item;
-    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(item) : "r"(item0 + 4u * slot) : "memory");
-    if (item < 0) break;
-    const int bx = item % p.nsx, cy = item / p.nsx;
-    const int C0 = bx * (C2_CW * FB_STRIDE);
-    const int r0 = cy * p.rows, r1 = min(r0 + p.rows - 1, H - 1);
-    const int nstages = ((r1 + 1) - r0 + 1 + 2 + K2_R - 1) / K2_R;
-    const int nactive = min(C2_CW, (W - C0 + FB_STRIDE - 1) / FB_STRIDE);
-    if (wib >= nactive) {
-      for (int st = 0; st < nstages; st++) {
-        const uint32_t g2 = gs + (uint32_t)st, sl = g2 % K2_NST;
-        mbar_wait(full0 + 8u * sl, (g2 / K2_NST) & 1u);
-        __syncwarp();
-        if (elect_one()) mbar_arrive(empty0 + 8u * sl);
-      }
-    } else {
-      const int c0 = C0 + wib * FB_STRIDE;
-      const uint32_t tile_u32 = ring0 + (uint32_t)(wib * FB_STRIDE) * 8u;
-      const bool border = c0 == 0 || c0 + FB_SEG - 2 > W;
-      if (border) acc = keys2d_strip<true, NPREV, TEST, K2_NST>(p, c0, r0, r1, lane, tile_u32, full0, empty0, bx * C2_CW + wib, gs, res_u32, wl_stage, acc);
-      else acc = keys2d_strip<false, NPREV, TEST, K2_NST>(p, c0, r0, r1, lane, tile_u32, full0, empty0, bx * C2_CW + wib, gs, res_u32, wl_stage, acc);
-    }
-    gs += (uint32_t)nstages;
-  }
-  if (p.res_slot[p.build_layer] != nullptr) {
-    const double cw = (double)(W - 1), ch = (double)(H - 1);
-    const double ax = fabs(acc.mdx), ay = fabs(acc.mdy);
-    const double vx = ax < DBL_MAX ? ax * cw : DBL_MAX, vy = ay < DBL_MAX ? ay * ch : DBL_MAX;
-    warp_res_commit(fmin(vx > 0.0 ? vx : DBL_MAX, vy > 0.0 ? vy : DBL_MAX), p.res_slot[p.build_layer]);
-  }
-  if (!(acc.big < __int_as_float(KEYF_BIG))) atomicExch(p.poison, 1ull);
-  if (threadIdx.x == 0) {
-    // every CTA's producer has drawn its last item before its consumers saw the end marker: the last CTA out may re-arm
-    __threadfence();
-    if (atomicAdd(&wc[1], 1u) == gridDim.x - 1) { wc[0] = 0u; wc[1] = 0u; __threadfence(); }
-  }
-}
-
 static size_t k2_smem_bytes(int nst) { return (size_t)nst * K2_STAGE_BYTES + (size_t)2 * nst * 8 + (size_t)16 * (C2_CW + 1) * 32 + 32 + (size_t)WL_STAGE_BYTES * C2_CW; }
 // FTKB_K2_CTAS (CTAs per SM: 2 | 3 | 4, default 3) and FTKB_K2_NST (ring stages at three CTAs per SM: 4 | 5 | 6, default 4)
 static int k2_variant() {
@@ -1601,22 +1505,9 @@ static int k2_variant() {
   }();
   return v;
 }
-static bool k2_persistent() {
-  static const bool v = [] { const char *e = std::getenv("FTKB_K2_PERSIST"); return e && std::atoi(e) != 0; }();
-  return v;
-}
 template <int CTAS, int NST>
 static void k2_launch(const SweepParams &p, unsigned grid, cudaStream_t s) {
   const size_t sm = k2_smem_bytes(NST);
-  if (CTAS == 3 && NST == 4 && k2_persistent() && p.work_counter) {
-    const unsigned pgrid = std::min<unsigned>(grid, (unsigned)(CTAS * (p.sm_count > 0 ? p.sm_count : 148)));
-    switch (p.sum_mode) {
-      case SUM_BUILD: scan2d_keys_persist_kernel<0, false, 3, 4><<<pgrid, (C2_CW + 1) * 32, sm, s>>>(p); break;
-      case SUM_BUILD_TEST1: scan2d_keys_persist_kernel<0, true, 3, 4><<<pgrid, (C2_CW + 1) * 32, sm, s>>>(p); break;
-      default: scan2d_keys_persist_kernel<1, true, 3, 4><<<pgrid, (C2_CW + 1) * 32, sm, s>>>(p); break;
-    }
-    return;
-  }
   switch (p.sum_mode) {
     case SUM_BUILD: scan2d_keys_build_kernel<0, false, CTAS, NST><<<grid, (C2_CW + 1) * 32, sm, s>>>(p); break;
     case SUM_BUILD_TEST1: scan2d_keys_build_kernel<0, true, CTAS, NST><<<grid, (C2_CW + 1) * 32, sm, s>>>(p); break;
@@ -1629,11 +1520,6 @@ static void k2_attrs() {
   cudaFuncSetAttribute(scan2d_keys_build_kernel<0, false, CTAS, NST>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
   cudaFuncSetAttribute(scan2d_keys_build_kernel<0, true, CTAS, NST>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
   cudaFuncSetAttribute(scan2d_keys_build_kernel<1, true, CTAS, NST>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
-  if (CTAS == 3 && NST == 4) {
-    cudaFuncSetAttribute(scan2d_keys_persist_kernel<0, false, 3, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
-    cudaFuncSetAttribute(scan2d_keys_persist_kernel<0, true, 3, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
-    cudaFuncSetAttribute(scan2d_keys_persist_kernel<1, true, 3, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
-  }
 }
 
 static size_t c2_smem_bytes() { return (size_t)C2_NST * TL_SEG * 8 + (size_t)2 * C2_NST * 8; }

@@ -53,7 +53,7 @@ struct SweepParams {
   // What the slot then receives is the minimum over the values under the threshold -- equal to the layer's own minimum whenever
   // that one would lower the running minimum, which is all the tracker uses it for.
   float res_thr[3];
-  unsigned long long *work_counter;  // persistent scan kernels: {next item, CTAs done} as two 32-bit words, zero between launches
+  int32_t l2_hint;                   // 2D key kernel: layer rows are copied with an L2 evict-first policy (FTKB_K2_L2HINT=1; measured alternative)
   unsigned long long *poison;        // fused 3D scan: set non-zero when a scalar is NaN / Inf / >= 2^1000 (the sweep is redone unfused)
   // fused 3D scan: TMA descriptors of the two scalar layers (box = one tile plane incl. halo)
   alignas(64) CUtensorMap tmap[2];
