@@ -1917,6 +1917,19 @@ __device__ __forceinline__ bool s3_excluded_level1(const S3Thresholds &T, const 
   return sided && esum <= T.esum_max && !(cmn[0] != cmn[0]);
 }
 
+// levels 2 and 3 of the determinant guard for a union that is one-sided in some component but failed the exponent-level bound
+// (large magnitudes: on a 512^3 moving extremum at factor 2^21 that is every sixth block).  A function of its own, entered behind a
+// warp vote, so that the plane loop pays a call only where it is needed and the blocks it clears never reach the retest after the loop.
+__device__ __noinline__ bool s3_excluded_levels23(const float mn0, const float mx0, const float mn1, const float mx1, const float mn2, const float mx2,
+                                                  const double half_factor, const int nbits20) {
+  const float mag[3] = {fmaxf(fabsf(mn0), fabsf(mx0)), fmaxf(fabsf(mn1), fabsf(mx1)), fmaxf(fabsf(mn2), fabsf(mx2))};
+  double P = 48.0;
+#pragma unroll
+  for (int c = 0; c < 3; c++) P *= fma(__hiloint2double((__float_as_int(mag[c]) | 0xFFFF) + 1, 0), half_factor, 1.0);
+  if (P < 9.0e18) return true;           // Inf / NaN magnitudes compare false
+  return s3_union_excluded_precise(mn0, mx0, mn1, mx1, mn2, mx2, nbits20);
+}
+
 // decide corner plane zc of this lane's 2 x S3_RW cubes from the union of the cells of planes zc, zc+1 (all layers)
 __device__ __forceinline__ void s3_test(const SweepParams &p, const S3Thresholds &T, const float (&cmn)[3], const float (&cmx)[3],
                                         const bool own_any, const int e, const int y0, const int zc, const int nl) {
@@ -2138,9 +2151,18 @@ struct S3Build {
         if (zc_ >= p.lb[2] && zc_ <= p.ub[2]) {
           float cmn[3] = {umin[0], umin[1], umin[2]}, cmx[3] = {umax[0], umax[1], umax[2]};
           merge_cell(cmn, cmx, make_uint4(pcell[0], pcell[1], pcell[2], 0u));
-          // only the exponent-level test runs here; a union it cannot exclude is noted (one bit per corner plane of the chunk) and
-          // decided after the plane loop from the stored cells -- the hot loop contains no call and keeps its registers
-          if (own_any && !s3_excluded_level1(T, cmn, cmx)) failbits |= 1ull << (zc_ - zc0);
+          // the exponent-level test runs here; a union it cannot exclude although some component is one-sided goes through
+          // the magnitude / range bounds behind a vote (s3_excluded_levels23); what is still open is noted (one bit per corner
+          // plane of the chunk) and decided after the plane loop from the stored cells
+          bool open_ = own_any && !s3_excluded_level1(T, cmn, cmx);
+          bool sided = false;
+#pragma unroll
+          for (int c = 0; c < 3; c++) sided = sided || cmn[c] >= T.kthr || cmx[c] <= -T.kthr;
+          const bool try23 = open_ && sided && !(cmn[0] != cmn[0]);
+          if (__any_sync(0xffffffffu, try23)) {
+            if (try23 && s3_excluded_levels23(cmn[0], cmx[0], cmn[1], cmx[1], cmn[2], cmx[2], T.half_factor, T.nbits20)) open_ = false;
+          }
+          if (open_) failbits |= 1ull << (zc_ - zc0);
         }
       }
 #pragma unroll
