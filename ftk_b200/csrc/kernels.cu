@@ -126,7 +126,7 @@ __device__ __forceinline__ void append_survivors(const SweepParams &p, bool surv
 // step) one atomicAdd per pass of the cold path -- all on the same counter -- is what the scan waits for.
 // stage (shared-memory address, 8-byte aligned): u32 count, pad, then WL_STAGE_CAP u64 entries; one per warp.
 constexpr int WL_STAGE_CAP = 64;
-constexpr uint32_t WL_STAGE_BYTES = 8u + 8u * WL_STAGE_CAP;
+constexpr uint32_t WL_STAGE_BYTES = 16u + 8u * WL_STAGE_CAP;     // (a multiple of 16: what follows the stagings is 16-byte aligned)
 __device__ __forceinline__ void flush_survivors(const SweepParams &p, const uint32_t stage) {
   const int lane = threadIdx.x & 31;
   int cnt;
@@ -1210,6 +1210,16 @@ __device__ __forceinline__ double lds64_f64(uint32_t a) {
   asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
   return v;
 }
+// 16 bytes global -> shared without a register (LDGSTS); completion: cp_async_wait_all of the issuing thread
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ uint4 lds128_u32(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+  return v;
+}
 __device__ __forceinline__ void sts64_f64(uint32_t a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
 // max that keeps a NaN once it has seen one (FMNMX.NAN): the "magnitude too large for float keys" accumulator
 __device__ __forceinline__ float fmax_nan(float a, float b) {
@@ -1249,6 +1259,7 @@ __device__ __forceinline__ K2Acc keys2d_strip(const SweepParams &p, const int c0
                                            const uint32_t sbase /* ring stages this CTA has consumed before this segment */,
                                            const uint32_t res_u32 /* smem: this thread's {min dx, min dy}; only the rare exact path touches them */,
                                            const uint32_t wl_stage /* smem: this warp's survivor staging (empty on entry and on exit) */,
+                                           const uint32_t cell_stage /* smem: this lane's two 16-byte slots (512 bytes apart) for the other layer's cells */,
                                            const K2Acc acc) {
   float big = acc.big;
   const int W = p.W, H = p.H, B = p.build_layer;
@@ -1276,9 +1287,11 @@ __device__ __forceinline__ K2Acc keys2d_strip(const SweepParams &p, const int c0
     sum_out[(size_t)kb * 32u] = make_uint4(__float_as_uint(bx.mn), __float_as_uint(bx.mx), __float_as_uint(by.mn), __float_as_uint(by.mx));
     if (TEST) {
       if (NPREV && kb < kb_end) {
-        // the other layer's cell of this block: requested into L2 two blocks ago (a DRAM miss: ~1 us), loaded only now -- four
-        // registers that are not live across the block's nine rows
-        const uint4 prevc = __ldg(sum_prev + (size_t)kb * 32u);
+        // the other layer's cell of this block: requested into L2 two blocks ago (a DRAM miss: ~1 us), copied into shared memory
+        // by cp.async when the block opened -- no register is live across the block's nine rows (four of them cost the loop six
+        // spilled scalars), and the L2 latency is not waited for here (a plain load at this point was 8 % of the warp samples)
+        cp_async_wait_all();
+        const uint4 prevc = lds128_u32(cell_stage + ((uint32_t)kb & 1u) * 512u);
         bx = fmerge(bx, FRange{__uint_as_float(prevc.x), __uint_as_float(prevc.y)});
         by = fmerge(by, FRange{__uint_as_float(prevc.z), __uint_as_float(prevc.w)});
       }
@@ -1384,6 +1397,7 @@ __device__ __forceinline__ K2Acc keys2d_strip(const SweepParams &p, const int c0
         const float rxmn = fminf(kxe, kxo), rxmx = fmaxf(kxe, kxo), rymn = fminf(kye, kyo), rymx = fmaxf(kye, kyo);
         if (j > r0) finish_block(kb - 1, fminf(bxmn, rxmn), fmaxf(bxmx, rxmx), fminf(bymn, rymn), fmaxf(bymx, rymx));
         bxmn = rxmn; bxmx = rxmx; bymn = rymn; bymx = rymx;
+        if (NPREV && kb < kb_end) cp_async16(cell_stage + ((uint32_t)kb & 1u) * 512u, sum_prev + (size_t)kb * 32u);     // the block this row opens
         kb++;
         if (NPREV && kb + 1 < kb_end) prefetch_l2(sum_prev + (size_t)(kb + 1) * 32u);
       } else {
@@ -1435,6 +1449,7 @@ __global__ void __launch_bounds__((C2_CW + 1) * 32, K2_CTAS) scan2d_keys_build_k
   const uint32_t full0 = ring0 + (uint32_t)K2_NST * K2_STAGE_BYTES, empty0 = full0 + 8u * K2_NST;
   const uint32_t res_u32 = empty0 + 8u * K2_NST + 16u * threadIdx.x;
   const uint32_t wl_stage = empty0 + 8u * K2_NST + 16u * (C2_CW + 1) * 32u + 32u + WL_STAGE_BYTES * (uint32_t)wib;
+  const uint32_t cell_stage = empty0 + 8u * K2_NST + 16u * (C2_CW + 1) * 32u + 32u + WL_STAGE_BYTES * (uint32_t)C2_CW + 1024u * (uint32_t)wib + 16u * (uint32_t)lane;
   const int W = p.W, H = p.H;
   const int bx = blockIdx.x % p.nsx, cy = blockIdx.x / p.nsx;
   const int C0 = bx * (C2_CW * FB_STRIDE);
@@ -1457,7 +1472,7 @@ __global__ void __launch_bounds__((C2_CW + 1) * 32, K2_CTAS) scan2d_keys_build_k
       const int col_lo = max(C0 - 2, 0), col_hi = min(C0 - 2 + TL_SEG, W);
       const uint32_t seg_bytes = (uint32_t)(col_hi - col_lo) * 8u;
       const uint32_t dst0 = ring0 + (uint32_t)(col_lo - (C0 - 2)) * 8u;
-      const bool hint = p.l2_hint != 0;
+      const bool hint = (p.l2_hint & 1) != 0;
       const unsigned long long pol = hint ? l2_policy_evict_first() : 0ull;
       for (int s = 0; s < nstages; s++) {
         const uint32_t slot = (uint32_t)s % K2_NST;
@@ -1482,8 +1497,8 @@ __global__ void __launch_bounds__((C2_CW + 1) * 32, K2_CTAS) scan2d_keys_build_k
   sts64_f64(res_u32, DBL_MAX); sts64_f64(res_u32 + 8u, DBL_MAX);
   if (lane == 0) asm volatile("st.shared.s32 [%0], %1;" ::"r"(wl_stage), "r"(0) : "memory");
   __syncwarp();
-  if (border) acc = keys2d_strip<true, NPREV, TEST, K2_NST>(p, c0, r0, r1, lane, tile_u32, full0, empty0, bx * C2_CW + wib, 0u, res_u32, wl_stage, acc);
-  else acc = keys2d_strip<false, NPREV, TEST, K2_NST>(p, c0, r0, r1, lane, tile_u32, full0, empty0, bx * C2_CW + wib, 0u, res_u32, wl_stage, acc);
+  if (border) acc = keys2d_strip<true, NPREV, TEST, K2_NST>(p, c0, r0, r1, lane, tile_u32, full0, empty0, bx * C2_CW + wib, 0u, res_u32, wl_stage, cell_stage, acc);
+  else acc = keys2d_strip<false, NPREV, TEST, K2_NST>(p, c0, r0, r1, lane, tile_u32, full0, empty0, bx * C2_CW + wib, 0u, res_u32, wl_stage, cell_stage, acc);
   if (p.res_slot[p.build_layer] != nullptr) {
     const double cw = (double)(W - 1), ch = (double)(H - 1);
     const double ax = fabs(acc.mdx), ay = fabs(acc.mdy);
@@ -1493,7 +1508,7 @@ __global__ void __launch_bounds__((C2_CW + 1) * 32, K2_CTAS) scan2d_keys_build_k
   if (!(acc.big < __int_as_float(KEYF_BIG))) atomicExch(p.poison, 1ull);
 }
 
-static size_t k2_smem_bytes(int nst) { return (size_t)nst * K2_STAGE_BYTES + (size_t)2 * nst * 8 + (size_t)16 * (C2_CW + 1) * 32 + 32 + (size_t)WL_STAGE_BYTES * C2_CW; }
+static size_t k2_smem_bytes(int nst) { return (size_t)nst * K2_STAGE_BYTES + (size_t)2 * nst * 8 + (size_t)16 * (C2_CW + 1) * 32 + 32 + (size_t)WL_STAGE_BYTES * C2_CW + (size_t)1024 * C2_CW; }
 // FTKB_K2_CTAS (CTAs per SM: 2 | 3 | 4, default 3) and FTKB_K2_NST (ring stages at three CTAs per SM: 4 | 5 | 6, default 4)
 static int k2_variant() {
   static const int v = [] {
