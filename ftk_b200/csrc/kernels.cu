@@ -2250,10 +2250,13 @@ __device__ __forceinline__ void s3_consume(const SweepParams &p, const uint32_t 
   s.st_c = 1; s.st_p = 2; s.par_p = 0; s.sidx = 1;
   const int zend = zc1 + 1;
   int zg = zc0;
+  // ONE copy of the plane step; the three-plane register window rotates by moves (20 per plane).  Three unrolled steps with the
+  // windows renamed (no moves) measured 2 % slower: the kernel is three times the code and 13 % of its warp samples were
+  // instruction fetch.
   while (true) {
     s.step(A, Bw, Cw, zg); if (++zg > zend) break;
-    s.step(Bw, Cw, A, zg); if (++zg > zend) break;
-    s.step(Cw, A, Bw, zg); if (++zg > zend) break;
+#pragma unroll
+    for (int r = 0; r < S3_WR; r++) { A[r] = Bw[r]; Bw[r] = Cw[r]; }
   }
   if (s.want_res) warp_res_commit(fabs(s.rmin), p.res_slot[B]);
   if (s.bad) atomicExch(p.poison, 1ull);
