@@ -142,7 +142,9 @@ struct ftkb_ctx {
   std::vector<ftkb_point *> retired_pts; // point buffers replaced while steps were in flight; freed once nothing is
 
   // finalize scratch (sort keys / indices, cub temp storage, neighbour lists, union-find parents): kept between calls, grown on demand
-  struct Scratch { void *p = nullptr; size_t cap = 0; };
+  struct Scratch { void *p = nullptr; size_t cap = 0; bool in_slab = false; };
+  void *fz_slab = nullptr;          // one allocation behind the slots a finalize plans together (scratch_plan)
+  size_t fz_slab_cap = 0;
   Scratch fz[12];          // 10, 11: the streaming grow step's neighbour lists and counts
   void *grow_stage = nullptr;   // page-locked staging of a grow step's batch
   size_t grow_stage_cap = 0;
@@ -192,10 +194,39 @@ static int fail(ftkb_ctx *c, int code, const std::string &msg) {
 }
 
 // pooled device scratch of ensure_sorted / ftkb_finalize: slot i holds at least `bytes`
+// Every cudaMalloc of a finalize showed up in its wall time (0.1 .. 30 ms each, depending on what the process freed before): the slots
+// one finalize needs are planned together and carved out of ONE allocation.  bytes[i] == 0: slot i is left alone.
+static int scratch_plan(ftkb_ctx *c, const size_t *bytes, int nslots) {
+  bool enough = true;
+  size_t total = 0;
+  for (int i = 0; i < nslots; i++)
+    if (bytes[i]) { enough = enough && c->fz[i].cap >= bytes[i]; total += (bytes[i] + bytes[i] / 4 + 511) / 256 * 256; }
+  if (enough) return FTKB_OK;
+  for (int i = 0; i < (int)(sizeof(c->fz) / sizeof(c->fz[0])); i++)
+    if (c->fz[i].in_slab) c->fz[i] = ftkb_ctx::Scratch{};
+  if (c->fz_slab_cap < total) {
+    cudaFree(c->fz_slab);
+    c->fz_slab = nullptr; c->fz_slab_cap = 0;
+    if (cudaMalloc(&c->fz_slab, total) != cudaSuccess) { cudaGetLastError(); c->error = "finalize: out of device memory"; return FTKB_ERR_NOMEM; }
+    c->fz_slab_cap = total;
+  }
+  size_t off = 0;
+  for (int i = 0; i < nslots; i++) {
+    if (!bytes[i]) continue;
+    ftkb_ctx::Scratch &s = c->fz[i];
+    if (s.p && !s.in_slab) cudaFree(s.p);
+    const size_t sz = (bytes[i] + bytes[i] / 4 + 511) / 256 * 256;
+    s.p = (char *)c->fz_slab + off; s.cap = sz; s.in_slab = true;
+    off += sz;
+  }
+  return FTKB_OK;
+}
+
 static int scratch(ftkb_ctx *c, int i, size_t bytes, void **out) {
   ftkb_ctx::Scratch &s = c->fz[i];
   if (s.cap < bytes) {
-    cudaFree(s.p);
+    if (!s.in_slab) cudaFree(s.p);
+    s.in_slab = false;
     s.p = nullptr; s.cap = 0;
     const size_t want = bytes + bytes / 4 + 256;
     if (cudaMalloc(&s.p, want) != cudaSuccess) { cudaGetLastError(); c->error = "finalize: out of device memory"; return FTKB_ERR_NOMEM; }
@@ -277,7 +308,8 @@ extern "C" void ftkb_destroy(ftkb_ctx *c) {
   cudaFree(c->d_f32);
   cudaFree(c->d_pts_sorted);
   cudaFree(c->d_keys_sorted);
-  for (auto &s : c->fz) cudaFree(s.p);
+  for (auto &s : c->fz) if (!s.in_slab) cudaFree(s.p);
+  cudaFree(c->fz_slab);
   for (auto &e : c->ev) if (e) cudaEventDestroy(e);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
@@ -1594,6 +1626,14 @@ static int ensure_sorted(ftkb_ctx *c) {
   uint32_t *i0 = nullptr, *i1 = nullptr;
   void *temp = nullptr;
 #define CKC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { c->error = std::string(#call) + ": " + cudaGetErrorString(e_); return FTKB_ERR_CUDA; } } while (0)
+  {
+    // everything this sort and the trace after it will ask for (the cub sizes are queries: nothing is launched)
+    const size_t tb0 = std::max(sort_pairs_u64(nullptr, 0, nullptr, nullptr, nullptr, nullptr, n, c->stream),
+                                unique_by_key_u64(nullptr, 0, nullptr, nullptr, nullptr, nullptr, c->d_scalars + ftkb_ctx::SLOT_UQ, n, c->stream));
+    const size_t plan[9] = {8 * n, 8 * n, 4 * n, 4 * n, tb0, c->streaming ? 0 : 4 * 8 * n, c->streaming ? 0 : 4 * n, c->streaming ? 0 : 4 * n, c->streaming ? 0 : 4 * n};
+    const int rp = scratch_plan(c, plan, 9);
+    if (rp) return rp;
+  }
   { int rs = scratch(c, 0, 8 * n, (void **)&k0); if (!rs) rs = scratch(c, 1, 8 * n, (void **)&k1); if (!rs) rs = scratch(c, 2, 4 * n, (void **)&i0);
     if (!rs) rs = scratch(c, 3, 4 * n, (void **)&i1); if (rs) return rs; }
   CKC(cudaEventRecord(c->ev[0], c->stream));

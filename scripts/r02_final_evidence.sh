@@ -1,7 +1,7 @@
 #!/bin/bash
 # round 2, final evidence session on one B200: parity tests, smoke, bench lines (C2 default with sub-records / CPU baseline / e2e, C3, C5,
 # dense woven, reference arm), launch lists, ncu --set full captures of the two scalar build kernels and of the dense test kernel.
-T=${TAG:-r02f}
+T=${TAG:-r02z}
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -4 | tee gpurun_out/${T}_pytest_gpu.log
 timeout 300 python __graft_entry__.py --smoke 2>&1 | tail -3 | tee gpurun_out/${T}_smoke.log
