@@ -1215,6 +1215,8 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ uint4 lds128_u32(uint32_t a) {
   uint4 v;
   asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
@@ -2042,7 +2044,7 @@ struct S3Build {
   int st_c, st_p;
   uint32_t par_p;
   unsigned long long failbits;   // bit (zc - zc0): corner plane zc of this lane's block failed the exponent-level test (decided after the loop)
-  uint4 prev_next;           // the other layer's cell of the next plane (in flight / loaded)
+  uint32_t cellring;         // shared memory: this lane's four 16-byte slots (512 bytes apart) for the other layer's cells
   int zlast;                 // last plane of the chunk's loop (zc1 + 1)
   const uint4 *sum_prev;     // cells of the current layer at the plane being processed (this warp, this lane)
   uint4 *sum_out;            // cells of the layer being built, likewise
@@ -2076,14 +2078,13 @@ struct S3Build {
   __device__ __forceinline__ void step(const double2 (&zm)[S3_WR], const double2 (&zc)[S3_WR], double2 (&zp)[S3_WR], const int zg) {
     const float nanf_ = __int_as_float(KEYF_NAN);
     const float inff_ = __int_as_float(0x7F800000);
-    // the other layer's cell of this plane was loaded one plane ago (prev_next); the one of the next plane is requested now and
-    // stays in flight for the whole step -- loaded at the top of its own step its 128-bit destination was reused as scratch by
-    // the row loop, whose first instruction then waited for the load (7.6 % of the warp samples, ncu source page)
-    uint4 prev = make_uint4(0x7FC07FC0u, 0x7FC07FC0u, 0x7FC07FC0u, 0u);
+    // the other layer's cells travel through a small shared-memory ring filled by cp.async three planes ahead (no register holds
+    // a cell in flight: as a 128-bit load one plane ahead it was still waited for -- 16 % of the warp samples -- because an L2 hit
+    // takes longer than a plane step while the TMA ring saturates the memory system); one commit group per plane
     if (NPREV) {
-      prev = prev_next;
-      if (zg < zlast) prev_next = __ldg(sum_prev + 32);
-      if (zg + 3 <= p.D) prefetch_l2(sum_prev + 3 * 32);      // a DRAM miss each, requested into L2 three planes ahead
+      if (zg + 3 <= zlast) cp_async16(cellring + (((uint32_t)zg + 3u) & 3u) * 512u, sum_prev + 3 * 32);
+      cp_async_commit();
+      if (zg + 5 <= p.D) prefetch_l2(sum_prev + 5 * 32);      // a DRAM miss each, requested into L2 five planes ahead
     }
     mbar_wait(full0 + 8u * st_p, par_p);
     load_plane(zp, st_p);
@@ -2166,7 +2167,10 @@ struct S3Build {
     sum_out += 32;
     if (NPREV) sum_prev += 32;
     if (TEST) {
-      if (NPREV) merge_cell(umin, umax, prev);
+      if (NPREV) {
+        cp_async_wait_group<3>();               // everything but the three newest groups: this plane's cell has landed
+        merge_cell(umin, umax, lds128_u32(cellring + ((uint32_t)zg & 3u) * 512u));
+      }
       if (zg > zc0) {
         const int zc_ = zg - 1;                   // corner plane decided now (warp-uniform)
         if (zc_ >= p.lb[2] && zc_ <= p.ub[2]) {
@@ -2194,7 +2198,7 @@ struct S3Build {
 };
 
 template <bool EDGE, int NPREV, bool TEST>
-__device__ __forceinline__ void s3_consume(const SweepParams &p, const uint32_t ring, const uint32_t full0, const uint32_t cnt,
+__device__ __forceinline__ void s3_consume(const SweepParams &p, const uint32_t ring, const uint32_t full0, const uint32_t cnt, const uint32_t cellring,
                                            const int tile, const int C0, const int Y0, const int zc0, const int zc1, const int wib, const int lane) {
   const int B = p.build_layer;
   S3Build<EDGE, NPREV, TEST> s{p, ring, full0, cnt};
@@ -2239,7 +2243,15 @@ __device__ __forceinline__ void s3_consume(const SweepParams &p, const uint32_t 
   s.sum_out = p.sum_out + cell0;
   if (NPREV) { prefetch_l2(s.sum_prev); prefetch_l2(s.sum_prev + 32); prefetch_l2(s.sum_prev + 64); }
   s.zlast = zc1 + 1;
-  s.prev_next = NPREV ? __ldg(s.sum_prev) : make_uint4(0x7FC07FC0u, 0x7FC07FC0u, 0x7FC07FC0u, 0u);
+  s.cellring = cellring + (uint32_t)wib * 2048u + (uint32_t)lane * 16u;
+  if (NPREV) {
+    // planes zc0 .. zc0 + 2 of the other layer's cells: three commit groups (a plane past the chunk's end commits an empty one)
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      if (zc0 + k <= s.zlast) cp_async16(s.cellring + (((uint32_t)zc0 + (uint32_t)k) & 3u) * 512u, s.sum_prev + k * 32);
+      cp_async_commit();
+    }
+  }
 
   double2 A[S3_WR], Bw[S3_WR], Cw[S3_WR];
   mbar_wait(full0, 0);
@@ -2279,6 +2291,7 @@ __global__ void __launch_bounds__(F3_CW * 32, 2) scan3d_build_kernel(const __gri
   const uint32_t ring_u32 = smem_u32(fb_smem);
   const uint32_t full0 = ring_u32 + (uint32_t)S3_NST * S3_STAGE_BYTES;
   unsigned *cnt = reinterpret_cast<unsigned *>(fb_smem + (size_t)S3_NST * S3_STAGE_BYTES + 8u * S3_NST);
+  const uint32_t cellring_u32 = (ring_u32 + (uint32_t)S3_NST * S3_STAGE_BYTES + 12u * S3_NST + 15u) & ~15u;     // 8 warps x 4 planes x 512 bytes
   int b = blockIdx.x;
   const int bx = b % p.nsx; b /= p.nsx;
   const int by = b % p.nsy;
@@ -2301,8 +2314,8 @@ __global__ void __launch_bounds__(F3_CW * 32, 2) scan3d_build_kernel(const __gri
   __syncthreads();
   const int tile = by * p.nsx + bx;
   const bool interior = C0 >= max(1, p.lb[0]) && C0 + 63 <= min(p.W - 2, p.ub[0]) && Y0 >= max(1, p.lb[1]) && Y0 + F3_TROWS <= min(p.H - 2, p.ub[1]);
-  if (interior) s3_consume<false, NPREV, TEST>(p, ring_u32, full0, smem_u32(cnt), tile, C0, Y0, zc0, zc1, wib, lane);
-  else s3_consume<true, NPREV, TEST>(p, ring_u32, full0, smem_u32(cnt), tile, C0, Y0, zc0, zc1, wib, lane);
+  if (interior) s3_consume<false, NPREV, TEST>(p, ring_u32, full0, smem_u32(cnt), cellring_u32, tile, C0, Y0, zc0, zc1, wib, lane);
+  else s3_consume<true, NPREV, TEST>(p, ring_u32, full0, smem_u32(cnt), cellring_u32, tile, C0, Y0, zc0, zc1, wib, lane);
 }
 
 // cells only: the final ordinal sweep (one layer) and re-sweeps (both layers' cells exist)
@@ -2342,7 +2355,7 @@ __global__ void __launch_bounds__(F3_CW * 32) scan3d_cells_kernel(const __grid_c
   }
 }
 
-static size_t s3_smem_bytes() { return (size_t)S3_NST * S3_STAGE_BYTES + (size_t)S3_NST * 8 + (size_t)S3_NST * 4; }
+static size_t s3_smem_bytes() { return (size_t)S3_NST * S3_STAGE_BYTES + (size_t)S3_NST * 8 + (size_t)S3_NST * 4 + 16 + (size_t)F3_CW * 2048; }
 
 size_t scan3d_cells_per_layer(const SweepParams &p) { return (size_t)p.nsx * p.nsy * F3_CW * (size_t)(p.D + 1) * 32u; }
 
