@@ -145,7 +145,7 @@ struct ftkb_ctx {
   struct Scratch { void *p = nullptr; size_t cap = 0; bool in_slab = false; };
   void *fz_slab = nullptr;          // one allocation behind the slots a finalize plans together (scratch_plan)
   size_t fz_slab_cap = 0;
-  Scratch fz[12];          // 10, 11: the streaming grow step's neighbour lists and counts
+  Scratch fz[14];          // 10, 11: the streaming grow step's neighbour lists and counts; 12, 13: the sorted records and their keys
   void *grow_stage = nullptr;   // page-locked staging of a grow step's batch
   size_t grow_stage_cap = 0;
 
@@ -306,8 +306,6 @@ extern "C" void ftkb_destroy(ftkb_ctx *c) {
   cudaFree(c->d_pts);
   cudaFree(c->d_coords);
   cudaFree(c->d_f32);
-  cudaFree(c->d_pts_sorted);
-  cudaFree(c->d_keys_sorted);
   for (auto &s : c->fz) if (!s.in_slab) cudaFree(s.p);
   cudaFree(c->fz_slab);
   for (auto &e : c->ev) if (e) cudaEventDestroy(e);
@@ -1611,8 +1609,8 @@ static int ensure_sorted(ftkb_ctx *c) {
   CK(cudaSetDevice(c->cfg.device));
   { const int rc = drain(c); if (rc) return rc; }
   if (c->sorted) return FTKB_OK;
-  cudaFree(c->d_pts_sorted); c->d_pts_sorted = nullptr;
-  cudaFree(c->d_keys_sorted); c->d_keys_sorted = nullptr;
+  c->d_pts_sorted = nullptr;         // (slots 12 / 13 of the finalize scratch: nothing to free here)
+  c->d_keys_sorted = nullptr;
   c->pts_sorted.clear();
   c->nsorted = 0;
   const uint64_t n = c->npts;
@@ -1630,8 +1628,9 @@ static int ensure_sorted(ftkb_ctx *c) {
     // everything this sort and the trace after it will ask for (the cub sizes are queries: nothing is launched)
     const size_t tb0 = std::max(sort_pairs_u64(nullptr, 0, nullptr, nullptr, nullptr, nullptr, n, c->stream),
                                 unique_by_key_u64(nullptr, 0, nullptr, nullptr, nullptr, nullptr, c->d_scalars + ftkb_ctx::SLOT_UQ, n, c->stream));
-    const size_t plan[9] = {8 * n, 8 * n, 4 * n, 4 * n, tb0, c->streaming ? 0 : 4 * 8 * n, c->streaming ? 0 : 4 * n, c->streaming ? 0 : 4 * n, c->streaming ? 0 : 4 * n};
-    const int rp = scratch_plan(c, plan, 9);
+    const size_t plan[14] = {8 * n, 8 * n, 4 * n, 4 * n, tb0, c->streaming ? 0 : 4 * 8 * n, c->streaming ? 0 : 4 * n, c->streaming ? 0 : 4 * n, c->streaming ? 0 : 4 * n,
+                             0, 0, 0, sizeof(ftkb_point) * n, 8 * n};
+    const int rp = scratch_plan(c, plan, 14);
     if (rp) return rp;
   }
   { int rs = scratch(c, 0, 8 * n, (void **)&k0); if (!rs) rs = scratch(c, 1, 8 * n, (void **)&k1); if (!rs) rs = scratch(c, 2, 4 * n, (void **)&i0);
@@ -1647,8 +1646,7 @@ static int ensure_sorted(ftkb_ctx *c) {
   CKC(cudaStreamSynchronize(c->stream));
   const uint64_t nu = c->h_scalars[ftkb_ctx::SLOT_UQ];
   laps.lap("sort+unique");
-  CKC(cudaMalloc(&c->d_pts_sorted, sizeof(ftkb_point) * nu));
-  CKC(cudaMalloc(&c->d_keys_sorted, 8 * nu));
+  { int rs = scratch(c, 12, sizeof(ftkb_point) * nu, (void **)&c->d_pts_sorted); if (!rs) rs = scratch(c, 13, 8 * nu, (void **)&c->d_keys_sorted); if (rs) return rs; }
   launch_gather_points(c->d_pts, i0, nu, c->d_pts_sorted, c->stream);
   CKC(cudaMemcpyAsync(c->d_keys_sorted, k0, 8 * nu, cudaMemcpyDeviceToDevice, c->stream));      // unique sorted keys
   CKC(cudaEventRecord(c->ev[1], c->stream));
