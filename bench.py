@@ -222,7 +222,9 @@ def reference_arm(args, rank):
 
 def cpu_baseline_sample(config):
     """bounded sample (about 10-30 s of CPU work) of the reference CPU tracker on this box's host cores"""
-    cmd, simplices, sample, cores, have = _ref_sample_cmd(config, {"T": 3, "dims2": [1536, 1536], "dims3": [96, 96, 96]})
+    # sized for about 10 s of wall clock on 16 host threads (the earlier 1536^2 / 96^3 sample took 3.8 s)
+    cmd, simplices, sample, cores, have = _ref_sample_cmd(config, {"T": 3, "dims2": [2560, 2560], "dims3": [128, 128, 128]} if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "ftk_ref_oracle"))
+                                                          else {"T": 3, "dims2": [1536, 1536], "dims3": [96, 96, 96]})
     try:
         if have:
             st = _run_ref(cmd)
